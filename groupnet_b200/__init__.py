@@ -1,0 +1,15 @@
+"""groupnet_b200 — B200-native (sm_100a) multiscale hypergraph message-passing layers.
+
+Drop-in for `model/MS_HGNN_batch.py` of TaliMotzkin/GroupNet: same nn.Module API,
+hand-written CUDA kernels behind a C ABI (include/groupnet_b200.h).
+"""
+from .layers import (MLP, MLP_dict, MLP_dict_softmax, MS_HGNN_hyper, MS_HGNN_oridinary,
+                     edge_aggregation)
+from .ops import corr_topk_h, topk_h
+from ._lib import GroupNetLibraryError, LIB_PATH
+
+__all__ = [
+    "MS_HGNN_oridinary", "MS_HGNN_hyper", "MLP", "MLP_dict", "MLP_dict_softmax",
+    "edge_aggregation", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,120 @@
+"""ctypes binding of libgroupnet_b200.so (the C ABI declared in include/groupnet_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared library is missing or was
+built for another ABI version every op raises `GroupNetLibraryError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgroupnet_b200.so")
+ABI_VERSION = 1
+
+GN_MAX_AGENTS = 64
+GN_MAX_SCALES = 8
+GN_FP32 = 0
+GN_BF16_TC = 1
+GN_NOISE_GIVEN = 0
+GN_NOISE_PHILOX = 1
+
+# every symbol include/groupnet_b200.h declares
+EXPORTS = (
+    "gn_abi_version",
+    "gn_error_string",
+    "gn_corr_topk_h",
+    "gn_topk_h",
+    "gn_stage_workspace_bytes",
+    "gn_stage_fwd",
+    "gn_stage_launch_count",
+)
+
+
+class GroupNetLibraryError(RuntimeError):
+    pass
+
+
+class StageWeights(C.Structure):
+    """struct gn_stage_weights (24 device pointers, header order)."""
+    FIELDS = (
+        "node_w0t", "node_b0", "node_w1t", "node_b1",
+        "att_wpqt", "att_b0", "att_w1", "att_b1",
+        "init_w0t", "init_b0", "init_w1t", "init_b1",
+        "df_w0t", "df_b0", "df_w1", "df_b1",
+        "agg_w0t", "agg_b0", "agg_w1t", "agg_b1",
+        "post_w0t", "post_b0", "post_w1t", "post_b1",
+    )
+    _fields_ = [(name, C.c_void_p) for name in FIELDS]
+
+
+class StageCfg(C.Structure):
+    """struct gn_stage_cfg."""
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("Dout", C.c_int32),
+        ("E", C.c_int32), ("T", C.c_int32), ("pairwise", C.c_int32), ("precision", C.c_int32),
+        ("noise_mode", C.c_int32), ("stage_index", C.c_int32),
+        ("seed", C.c_uint64), ("scene_offset", C.c_int64),
+    ]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library once; raise loudly if it is absent or mismatched."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise GroupNetLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C groupnet_b200/csrc`. groupnet_b200 has no CPU / PyTorch fallback.")
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as exc:  # missing libcudart etc.
+            raise GroupNetLibraryError(f"cannot load {LIB_PATH}: {exc}") from exc
+        for name in EXPORTS:
+            if not hasattr(lib, name):
+                raise GroupNetLibraryError(f"{LIB_PATH} does not export {name}")
+        lib.gn_abi_version.restype = C.c_int
+        lib.gn_error_string.restype = C.c_char_p
+        lib.gn_error_string.argtypes = [C.c_int]
+        lib.gn_corr_topk_h.restype = C.c_int
+        lib.gn_corr_topk_h.argtypes = [
+            C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32,
+            C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_void_p, C.c_void_p]
+        lib.gn_topk_h.restype = C.c_int
+        lib.gn_topk_h.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_int64, C.c_void_p]
+        lib.gn_stage_workspace_bytes.restype = C.c_size_t
+        lib.gn_stage_workspace_bytes.argtypes = [C.POINTER(StageCfg)]
+        lib.gn_stage_launch_count.restype = C.c_int
+        lib.gn_stage_launch_count.argtypes = [C.POINTER(StageCfg)]
+        lib.gn_stage_fwd.restype = C.c_int
+        lib.gn_stage_fwd.argtypes = [
+            C.POINTER(StageCfg), C.POINTER(StageWeights), C.c_void_p, C.c_void_p, C.c_void_p,
+            C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        got = lib.gn_abi_version()
+        if got != ABI_VERSION:
+            raise GroupNetLibraryError(f"{LIB_PATH} has ABI version {got}, expected {ABI_VERSION}")
+        _lib = lib
+        return _lib
+
+
+def check(code: int, what: str) -> None:
+    """Map a C return code to the exception the reference would raise."""
+    if code == 0:
+        return
+    msg = load().gn_error_string(code).decode()
+    if code == -3:
+        # torch.topk in the reference (MS_HGNN_batch.py:382) raises RuntimeError with this text
+        raise RuntimeError("selected index k out of range")
+    if code < 0:
+        raise ValueError(f"{what}: {msg} (gn_error {code})")
+    raise RuntimeError(f"{what}: CUDA error {code}: {msg}")

@@ -1,0 +1,850 @@
+// fp32 (FFMA) kernels of one message-passing stage — the 1e-5 parity path.
+//
+// Stage = node2edge -> MLP_dict_softmax -> edge2node -> closing MLP
+// (model/MS_HGNN_batch.py:173-195 / :425-441), restructured so that nothing of
+// size (B,E,N,128) is ever materialised:
+//
+//   k1 node_pre     rows B*N   x' = node2edge_start_mlp(h); pq = W0split x';
+//                              pairwise only: P = h W0_agg^T (aggregation collapse)
+//   k2 node2edge    per scene  attention softmax over the incidence + weighted
+//                              gather: edges (B*E,64); hyper: eo = H h (B*E,D)
+//   k3 edge_mlp     rows B*E   init_MLP, [distribution|factor] MLPs, Gumbel
+//                              softmax, sigmoid: dist (B,E,T), edge_feat (B*E,T)
+//   k4 edge_agg     rows B*E   hyper only: ef = sum_t edge_feat_t * agg_mlp_t(eo)
+//   k5 edge2node    per scene  pairwise: G = scatter of relu(P_i+P_j+b)*w (collapsed);
+//                              hyper: agg = H^T ef
+//   k6 node_post    rows B*N   pairwise: agg = G W1cat^T + S b1; incoming =
+//                              [agg | h]/N; closing MLP 2D -> 128 -> Dout
+//
+// Algebra of the pairwise collapse (validated to 3e-7): the
+// first Linear of every agg_mlp commutes with H @ ori and the second with
+// H^T @ ., so both run on N rows/scene instead of N^2.
+#include "gn_gemm_simt.cuh"
+
+namespace gn {
+
+// ===========================================================================
+// k1: node_pre
+// ===========================================================================
+// smem: hT [Dp][LD] | hidT [128][LD] | xT [64][LD] | wp [2*KC*128]
+template <int TM>
+__global__ void __launch_bounds__(GN_THREADS)
+node_pre_kernel(const float* __restrict__ h, int R, int D, int Dp, int T, int pairwise,
+                gn_stage_weights W, float* __restrict__ xprime, float* __restrict__ pq,
+                float* __restrict__ P) {
+  constexpr int LD = TM + 4, RM = TM / 16;
+  extern __shared__ __align__(16) float smem[];
+  float* hT = smem;
+  float* hidT = hT + Dp * LD;
+  float* xT = hidT + 128 * LD;
+  float* wp = xT + 64 * LD;
+  const int ntiles = (R + TM - 1) / TM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * TM, nrows = min(TM, R - row0);
+    load_tile_kmajor<TM>(hT, h + static_cast<size_t>(row0) * D, D, nrows, D, Dp, 1.f, false);
+    // x' = W1 relu(W0 h + b0) + b1, hidden processed in two 128-column halves
+    float accx[RM][4];
+    acc_zero(accx);
+    for (int half = 0; half < 2; ++half) {
+      float acc1[RM][8];
+      acc_zero(acc1);
+      gemm_accum<TM, 128>(acc1, hT, W.node_w0t, GN_NODE_HIDDEN, half * 128, Dp, wp);
+      const float* b0 = W.node_b0 + half * 128;
+      acc_store_kmajor<TM, 128>(acc1, hidT, 0,
+                                [&](int col, int, float v) { return fmaxf(v + __ldg(b0 + col), 0.f); });
+      gemm_accum<TM, 64>(accx, hidT, W.node_w1t + static_cast<size_t>(half) * 128 * GN_ATT_DIM,
+                         GN_ATT_DIM, 0, 128, wp);
+    }
+    acc_foreach<TM, 64>(accx, [&](int r, int c, float& v) {
+      v += __ldg(W.node_b1 + c);
+      if (r < nrows) xprime[static_cast<size_t>(row0 + r) * GN_ATT_DIM + c] = v;
+    });
+    acc_store_kmajor<TM, 64>(accx, xT, 0, [](int, int, float v) { return v; });
+    // pq = [W0a x' | W0b x'] (bias added per edge later)
+    float accp[RM][4];
+    acc_zero(accp);
+    gemm_accum<TM, 64>(accp, xT, W.att_wpqt, GN_ATT_DIM, 0, GN_ATT_DIM, wp);
+    acc_foreach<TM, 64>(accp, [&](int r, int c, float& v) {
+      if (r < nrows) pq[static_cast<size_t>(row0 + r) * GN_ATT_DIM + c] = v;
+    });
+    if (pairwise) {
+      const int ldp = T * GN_MLP_HIDDEN;
+      for (int t = 0; t < T; ++t) {
+        float accP[RM][8];
+        acc_zero(accP);
+        gemm_accum<TM, 128>(accP, hT, W.agg_w0t, ldp, t * 128, Dp, wp);
+        acc_foreach<TM, 128>(accP, [&](int r, int c, float& v) {
+          if (r < nrows) P[static_cast<size_t>(row0 + r) * ldp + t * 128 + c] = v;
+        });
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// k2a: node2edge, pairwise (incidence implicit: edge e = i*N + j, self loops
+// carry incidence 2).  Work item = (scene, chunk of EC edges).
+// ===========================================================================
+constexpr int N2E_LD = GN_ATT_DIM + 4;   // 68: rows 4 banks apart
+constexpr int N2E_EC = 1024;
+
+__global__ void __launch_bounds__(GN_THREADS)
+node2edge_pair_kernel(const float* __restrict__ xprime, const float* __restrict__ pq,
+                      int B, int N, gn_stage_weights W, float* __restrict__ edges) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                       // [N][68]
+  float* ps = xs + N * N2E_LD;            // [N][68]  pn | q
+  float* wts = ps + N * N2E_LD;           // [EC][2]
+  __shared__ float sb0[GN_ATT_HIDDEN], sw1[GN_ATT_HIDDEN];
+  const int tid = threadIdx.x;
+  if (tid < GN_ATT_HIDDEN) { sb0[tid] = __ldg(W.att_b0 + tid); sw1[tid] = __ldg(W.att_w1 + tid); }
+  const float b1 = __ldg(W.att_b1);
+  const int E = N * N;
+  const int nchunk = (E + N2E_EC - 1) / N2E_EC;
+  const long long nwork = static_cast<long long>(B) * nchunk;
+  for (long long wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int b = static_cast<int>(wi / nchunk), ch = static_cast<int>(wi - static_cast<long long>(b) * nchunk);
+    const int e0 = ch * N2E_EC, ec = min(N2E_EC, E - e0);
+    __syncthreads();
+    for (int i = tid; i < N * 16; i += GN_THREADS) {
+      int n = i >> 4, c = i & 15;
+      size_t g = (static_cast<size_t>(b) * N + n) * GN_ATT_DIM + 4 * c;
+      *reinterpret_cast<float4*>(xs + n * N2E_LD + 4 * c) = ldg_f4(xprime + g);
+      *reinterpret_cast<float4*>(ps + n * N2E_LD + 4 * c) = ldg_f4(pq + g);
+    }
+    __syncthreads();
+    // phase A: one thread per edge -> attention weights of its (<= 2) members
+    for (int el = tid; el < ec; el += GN_THREADS) {
+      const int e = e0 + el, i = e / N, j = e - i * N;
+      const float* pi = ps + i * N2E_LD;
+      const float* pj = ps + j * N2E_LD;
+      const float hs = (i == j) ? 2.f : 1.f;      // self loop: edge_init = 2 x_i
+      float ai = 0.f, aj = 0.f;
+#pragma unroll
+      for (int k4 = 0; k4 < GN_ATT_HIDDEN; k4 += 4) {
+        float4 ni = *reinterpret_cast<const float4*>(pi + k4);
+        float4 nj = *reinterpret_cast<const float4*>(pj + k4);
+        float4 qi = *reinterpret_cast<const float4*>(pi + 32 + k4);
+        float4 qj = *reinterpret_cast<const float4*>(pj + 32 + k4);
+        float pe0, pe1, pe2, pe3;
+        if (i == j) {
+          pe0 = 2.f * qi.x; pe1 = 2.f * qi.y; pe2 = 2.f * qi.z; pe3 = 2.f * qi.w;
+        } else {
+          pe0 = qi.x + qj.x; pe1 = qi.y + qj.y; pe2 = qi.z + qj.z; pe3 = qi.w + qj.w;
+        }
+        pe0 += sb0[k4]; pe1 += sb0[k4 + 1]; pe2 += sb0[k4 + 2]; pe3 += sb0[k4 + 3];
+        ai = fmaf(fmaxf(ni.x + pe0, 0.f), sw1[k4], ai);
+        ai = fmaf(fmaxf(ni.y + pe1, 0.f), sw1[k4 + 1], ai);
+        ai = fmaf(fmaxf(ni.z + pe2, 0.f), sw1[k4 + 2], ai);
+        ai = fmaf(fmaxf(ni.w + pe3, 0.f), sw1[k4 + 3], ai);
+        aj = fmaf(fmaxf(nj.x + pe0, 0.f), sw1[k4], aj);
+        aj = fmaf(fmaxf(nj.y + pe1, 0.f), sw1[k4 + 1], aj);
+        aj = fmaf(fmaxf(nj.z + pe2, 0.f), sw1[k4 + 2], aj);
+        aj = fmaf(fmaxf(nj.w + pe3, 0.f), sw1[k4 + 3], aj);
+      }
+      // softmax over ALL N nodes of (a * H): non-members enter with logit 0 (:135-137)
+      float si = (ai + b1) * hs, sj = (aj + b1) * hs;
+      float wi_, wj_;
+      if (i == j) {
+        float mx = (N > 1) ? fmaxf(si, 0.f) : si;
+        float ei = expf(si - mx);
+        float den = ei + static_cast<float>(N - 1) * expf(-mx);
+        wi_ = ei / den * 2.f; wj_ = 0.f;
+      } else {
+        float mx = fmaxf(si, sj);
+        if (N > 2) mx = fmaxf(mx, 0.f);
+        float ei = expf(si - mx), ej = expf(sj - mx);
+        float den = ei + ej + static_cast<float>(N - 2) * expf(-mx);
+        wi_ = ei / den; wj_ = ej / den;
+      }
+      wts[2 * el] = wi_; wts[2 * el + 1] = wj_;
+    }
+    __syncthreads();
+    // phase B: edges[e][:] = w_i x'_i + w_j x'_j, one float4 per task, coalesced stores
+    for (int t = tid; t < ec * 16; t += GN_THREADS) {
+      const int el = t >> 4, c = t & 15;
+      const int e = e0 + el, i = e / N, j = e - i * N;
+      float wi_ = wts[2 * el], wj_ = wts[2 * el + 1];
+      float4 xi = *reinterpret_cast<const float4*>(xs + i * N2E_LD + 4 * c);
+      float4 xj = *reinterpret_cast<const float4*>(xs + j * N2E_LD + 4 * c);
+      float4 o;
+      o.x = fmaf(wi_, xi.x, wj_ * xj.x); o.y = fmaf(wi_, xi.y, wj_ * xj.y);
+      o.z = fmaf(wi_, xi.z, wj_ * xj.z); o.w = fmaf(wi_, xi.w, wj_ * xj.w);
+      *reinterpret_cast<float4*>(edges + (static_cast<size_t>(b) * E + e) * GN_ATT_DIM + 4 * c) = o;
+    }
+  }
+}
+
+// ===========================================================================
+// k2b: node2edge, hyper (incidence H (B,E,N) given, E <= N <= 64).
+// Work item = scene.  Also emits eo = H @ h for the aggregation MLPs.
+// ===========================================================================
+__global__ void __launch_bounds__(GN_THREADS)
+node2edge_hyper_kernel(const float* __restrict__ xprime, const float* __restrict__ pq,
+                       const float* __restrict__ h, const float* __restrict__ H,
+                       int B, int N, int E, int D, gn_stage_weights W,
+                       float* __restrict__ edges, float* __restrict__ eo) {
+  extern __shared__ __align__(16) float smem[];
+  const int ldh = D + 4, ldn = N + 1;
+  float* xs = smem;                       // [N][68]
+  float* ps = xs + N * N2E_LD;            // [N][68]
+  float* hs = ps + N * N2E_LD;            // [N][D+4]
+  float* Hs = hs + N * ldh;               // [E][N+1]
+  float* att = Hs + ((E * ldn + 3) & ~3); // [E][N+1]
+  float* pe = att + ((E * ldn + 3) & ~3); // [E][33]
+  __shared__ float sb0[GN_ATT_HIDDEN], sw1[GN_ATT_HIDDEN];
+  const int tid = threadIdx.x;
+  if (tid < GN_ATT_HIDDEN) { sb0[tid] = __ldg(W.att_b0 + tid); sw1[tid] = __ldg(W.att_w1 + tid); }
+  const float b1 = __ldg(W.att_b1);
+  const int d4 = D >> 2;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < N * 16; i += GN_THREADS) {
+      int n = i >> 4, c = i & 15;
+      size_t g = (static_cast<size_t>(b) * N + n) * GN_ATT_DIM + 4 * c;
+      *reinterpret_cast<float4*>(xs + n * N2E_LD + 4 * c) = ldg_f4(xprime + g);
+      *reinterpret_cast<float4*>(ps + n * N2E_LD + 4 * c) = ldg_f4(pq + g);
+    }
+    for (int i = tid; i < N * d4; i += GN_THREADS) {
+      int n = i / d4, c = i - n * d4;
+      *reinterpret_cast<float4*>(hs + n * ldh + 4 * c) =
+          ldg_f4(h + (static_cast<size_t>(b) * N + n) * D + 4 * c);
+    }
+    for (int i = tid; i < E * N; i += GN_THREADS) {
+      int e = i / N, n = i - e * N;
+      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b) * E * N + i);
+    }
+    __syncthreads();
+    // pe[e][k] = sum_n H[e,n] q_n[k] + b0[k]
+    for (int i = tid; i < E * GN_ATT_HIDDEN; i += GN_THREADS) {
+      int e = i >> 5, k = i & 31;
+      float s = 0.f;
+      for (int n = 0; n < N; ++n) s = fmaf(Hs[e * ldn + n], ps[n * N2E_LD + 32 + k], s);
+      pe[e * 33 + k] = s + sb0[k];
+    }
+    __syncthreads();
+    // att[e][n] = H[e,n] * (w1 . relu(pn_n + pe_e) + b1); exactly 0 for non-members
+    for (int i = tid; i < E * N; i += GN_THREADS) {
+      int e = i / N, n = i - e * N;
+      float hv = Hs[e * ldn + n], a = 0.f;
+      if (hv != 0.f) {
+#pragma unroll 8
+        for (int k = 0; k < GN_ATT_HIDDEN; ++k)
+          a = fmaf(fmaxf(ps[n * N2E_LD + k] + pe[e * 33 + k], 0.f), sw1[k], a);
+        a = (a + b1) * hv;
+      }
+      att[e * ldn + n] = a;
+    }
+    __syncthreads();
+    // softmax over all N nodes, then mask by H again (:135-137)
+    for (int e = tid; e < E; e += GN_THREADS) {
+      float mx = -INFINITY;
+      for (int n = 0; n < N; ++n) mx = fmaxf(mx, att[e * ldn + n]);
+      float den = 0.f;
+      for (int n = 0; n < N; ++n) den += expf(att[e * ldn + n] - mx);
+      for (int n = 0; n < N; ++n)
+        att[e * ldn + n] = expf(att[e * ldn + n] - mx) / den * Hs[e * ldn + n];
+    }
+    __syncthreads();
+    // edges[e][:] = sum_n att[e,n] x'_n ;  eo[e][:] = sum_n H[e,n] h_n
+    for (int i = tid; i < E * 16; i += GN_THREADS) {
+      int e = i >> 4, c = i & 15;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int n = 0; n < N; ++n) {
+        float w = att[e * ldn + n];
+        if (w != 0.f) {
+          float4 v = *reinterpret_cast<const float4*>(xs + n * N2E_LD + 4 * c);
+          o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y);
+          o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
+        }
+      }
+      *reinterpret_cast<float4*>(edges + (static_cast<size_t>(b) * E + e) * GN_ATT_DIM + 4 * c) = o;
+    }
+    for (int i = tid; i < E * d4; i += GN_THREADS) {
+      int e = i / d4, c = i - e * d4;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int n = 0; n < N; ++n) {
+        float w = Hs[e * ldn + n];
+        if (w != 0.f) {
+          float4 v = *reinterpret_cast<const float4*>(hs + n * ldh + 4 * c);
+          o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y);
+          o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
+        }
+      }
+      *reinterpret_cast<float4*>(eo + (static_cast<size_t>(b) * E + e) * D + 4 * c) = o;
+    }
+  }
+}
+
+// ===========================================================================
+// k3: edge_mlp — MLP_dict_softmax (:31-53) + Gumbel softmax (:446-520)
+// rows = B*E edge rows, row independent.
+// smem: eT [64][LD] (reused for z) | bufT [128][LD] | wp [2*KC*128] |
+//       w1s [256][16] | part [TM][17] | io [TM*16]
+// ===========================================================================
+template <int TM>
+__global__ void __launch_bounds__(GN_THREADS)
+edge_mlp_kernel(const float* __restrict__ edges, long long R, int T, int E,
+                gn_stage_weights W, const float* __restrict__ U, int noise_mode,
+                unsigned long long seed, long long scene_offset, int stage_index,
+                float* __restrict__ dist_out, float* __restrict__ edge_feat) {
+  constexpr int LD = TM + 4, RM = TM / 16;
+  constexpr int NPART = GN_THREADS / TM;            // threads per row in the small layer
+  extern __shared__ __align__(16) float smem[];
+  float* eT = smem;
+  float* bufT = eT + 64 * LD;
+  float* wp = bufT + 128 * LD;
+  float* w1s = wp + 2 * KC * 128;
+  float* part = w1s + 256 * GN_SMALL_OUT;
+  float* io = part + TM * 17;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 256 * GN_SMALL_OUT; i += GN_THREADS) w1s[i] = __ldg(W.df_w1 + i);
+  const long long ntiles = (R + TM - 1) / TM;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TM;
+    const int nrows = static_cast<int>(min(static_cast<long long>(TM), R - row0));
+    load_tile_kmajor<TM>(eT, edges + static_cast<size_t>(row0) * GN_ATT_DIM, GN_ATT_DIM, nrows,
+                         GN_ATT_DIM, GN_ATT_DIM, 1.f, false);
+    if (noise_mode == GN_NOISE_GIVEN) {
+      const float* us = U + static_cast<size_t>(row0) * T;
+      for (int i = tid; i < nrows * T; i += GN_THREADS) io[i] = __ldg(us + i);
+    }
+    // init_MLP: 64 -> 128 -> 64
+    {
+      float acc[RM][8];
+      acc_zero(acc);
+      gemm_accum<TM, 128>(acc, eT, W.init_w0t, 128, 0, 64, wp);
+      acc_store_kmajor<TM, 128>(acc, bufT, 0, [&](int col, int, float v) {
+        return fmaxf(v + __ldg(W.init_b0 + col), 0.f);
+      });
+    }
+    {
+      float acc[RM][4];
+      acc_zero(acc);
+      gemm_accum<TM, 64>(acc, bufT, W.init_w1t, 64, 0, 128, wp);
+      acc_store_kmajor<TM, 64>(acc, eT, 0, [&](int col, int, float v) {
+        return v + __ldg(W.init_b1 + col);
+      });
+    }
+    // [MLP_distribution | MLP_factor] first layers (64 -> 256) in two halves, each
+    // followed by its slice of the 256 -> 16 second layer
+    float lg[GN_SMALL_OUT];
+#pragma unroll
+    for (int o = 0; o < GN_SMALL_OUT; ++o) lg[o] = 0.f;
+    const int prow = tid % TM, ppart = tid / TM;
+    for (int half = 0; half < 2; ++half) {
+      float acc[RM][8];
+      acc_zero(acc);
+      gemm_accum<TM, 128>(acc, eT, W.df_w0t, 256, half * 128, 64, wp);
+      const float* b0 = W.df_b0 + half * 128;
+      acc_store_kmajor<TM, 128>(acc, bufT, 0, [&](int col, int, float v) {
+        return fmaxf(v + __ldg(b0 + col), 0.f);
+      });
+      __syncthreads();
+      constexpr int KPP = 128 / NPART;
+      const float* wsl = w1s + (half * 128 + ppart * KPP) * GN_SMALL_OUT;
+      const float* asl = bufT + (ppart * KPP) * LD + prow;
+#pragma unroll 4
+      for (int k = 0; k < KPP; ++k) {
+        float a = asl[k * LD];
+        const float4* wr = reinterpret_cast<const float4*>(wsl + k * GN_SMALL_OUT);
+        float4 w0 = wr[0], w1 = wr[1], w2 = wr[2], w3 = wr[3];
+        lg[0] = fmaf(a, w0.x, lg[0]); lg[1] = fmaf(a, w0.y, lg[1]);
+        lg[2] = fmaf(a, w0.z, lg[2]); lg[3] = fmaf(a, w0.w, lg[3]);
+        lg[4] = fmaf(a, w1.x, lg[4]); lg[5] = fmaf(a, w1.y, lg[5]);
+        lg[6] = fmaf(a, w1.z, lg[6]); lg[7] = fmaf(a, w1.w, lg[7]);
+        lg[8] = fmaf(a, w2.x, lg[8]); lg[9] = fmaf(a, w2.y, lg[9]);
+        lg[10] = fmaf(a, w2.z, lg[10]); lg[11] = fmaf(a, w2.w, lg[11]);
+        lg[12] = fmaf(a, w3.x, lg[12]); lg[13] = fmaf(a, w3.y, lg[13]);
+        lg[14] = fmaf(a, w3.z, lg[14]); lg[15] = fmaf(a, w3.w, lg[15]);
+      }
+      __syncthreads();                    // bufT is overwritten by the next half
+    }
+    // combine the NPART partial sums of each row (parts live in different warps)
+    for (int pp = 1; pp < NPART; ++pp) {
+      if (ppart == pp) {
+#pragma unroll
+        for (int o = 0; o < GN_SMALL_OUT; ++o) part[prow * 17 + o] = lg[o];
+      }
+      __syncthreads();
+      if (ppart == 0) {
+#pragma unroll
+        for (int o = 0; o < GN_SMALL_OUT; ++o) lg[o] += part[prow * 17 + o];
+      }
+      __syncthreads();
+    }
+    if (ppart == 0 && prow < nrows) {
+      // y = (logits + g) / tau, tau = 1/2; dist = softmax(y); factor = sigmoid(.)
+      const long long grow = row0 + prow;
+      float y[GN_SMALL_OUT - 1];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < GN_SMALL_OUT - 1; ++t) {
+        if (t < T) {
+          float u;
+          if (noise_mode == GN_NOISE_GIVEN) {
+            u = io[prow * T + t];
+          } else {
+            unsigned long long el =
+                (static_cast<unsigned long long>(scene_offset) * E + grow) * T + t;
+            u = Philox::uniform(el, static_cast<uint32_t>(stage_index), seed);
+          }
+          y[t] = (lg[t] + __ldg(W.df_b1 + t) + gumbel_from_uniform(u)) / 0.5f;
+          mx = fmaxf(mx, y[t]);
+        }
+      }
+      float den = 0.f;
+#pragma unroll
+      for (int t = 0; t < GN_SMALL_OUT - 1; ++t)
+        if (t < T) { y[t] = expf(y[t] - mx); den += y[t]; }
+      float fl = 0.f;
+#pragma unroll
+      for (int o = 0; o < GN_SMALL_OUT; ++o)
+        if (o == T) fl = lg[o] + __ldg(W.df_b1 + o);
+      float factor = 1.f / (1.f + expf(-fl));
+#pragma unroll
+      for (int t = 0; t < GN_SMALL_OUT - 1; ++t)
+        if (t < T) {
+          float d = y[t] / den;
+          io[prow * T + t] = d;                      // dist (staged for a coalesced copy)
+          part[prow * 17 + t] = factor * d;          // edge_feat
+        }
+    }
+    __syncthreads();
+    {
+      float* ef = edge_feat + static_cast<size_t>(row0) * T;
+      for (int i = tid; i < nrows * T; i += GN_THREADS) {
+        int r = i / T, t = i - r * T;
+        ef[i] = part[r * 17 + t];
+      }
+      if (dist_out != nullptr) {
+        float* dd = dist_out + static_cast<size_t>(row0) * T;
+        for (int i = tid; i < nrows * T; i += GN_THREADS) dd[i] = io[i];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// k4: edge_agg (hyper, as written :259-265): rows = B*E,
+//   ef = sum_t edge_feat[:,t] * (W1_t relu(W0_t eo + b0_t) + b1_t)
+// The per-row scale is applied to the hidden activations, so the T second
+// Linears accumulate into ONE output tile (K = T*128).
+// smem: eoT [Dp][LD] | hidT [128][LD] | wp | sc [TM][16]
+// ===========================================================================
+template <int TM, int TN, int NCH>
+__global__ void __launch_bounds__(GN_THREADS)
+edge_agg_kernel(const float* __restrict__ eo, const float* __restrict__ edge_feat, long long R,
+                int D, int Dp, int Dc, int T, gn_stage_weights W, float* __restrict__ ef) {
+  constexpr int LD = TM + 4, RM = TM / 16, RN = TN / 16;
+  extern __shared__ __align__(16) float smem[];
+  float* eoT = smem;
+  float* hidT = eoT + Dp * LD;
+  float* wp = hidT + 128 * LD;
+  float* sc = wp + 2 * KC * 128;
+  const int tid = threadIdx.x;
+  const long long ntiles = (R + TM - 1) / TM;
+  const int ldw0 = T * GN_MLP_HIDDEN;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * TM;
+    const int nrows = static_cast<int>(min(static_cast<long long>(TM), R - row0));
+    load_tile_kmajor<TM>(eoT, eo + static_cast<size_t>(row0) * D, D, nrows, D, Dp, 1.f, false);
+    for (int i = tid; i < TM * 16; i += GN_THREADS) {
+      int r = i >> 4, t = i & 15;
+      sc[i] = (r < nrows && t < T) ? __ldg(edge_feat + static_cast<size_t>(row0 + r) * T + t) : 0.f;
+    }
+    float acc2[NCH][RM][RN];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) acc_zero(acc2[c]);
+    for (int t = 0; t < T; ++t) {
+      float acc1[RM][8];
+      acc_zero(acc1);
+      gemm_accum<TM, 128>(acc1, eoT, W.agg_w0t, ldw0, t * 128, Dp, wp);
+      const float* b0 = W.agg_b0 + t * 128;
+      acc_store_kmajor<TM, 128>(acc1, hidT, 0, [&](int col, int row, float v) {
+        return fmaxf(v + __ldg(b0 + col), 0.f) * sc[row * 16 + t];
+      });
+      const float* w1 = W.agg_w1t + static_cast<size_t>(t) * 128 * Dc;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c)
+        if (c * TN < Dc) gemm_accum<TM, TN>(acc2[c], hidT, w1, Dc, c * TN, 128, wp);
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      acc_foreach<TM, TN>(acc2[c], [&](int r, int cc, float& v) {
+        int col = c * TN + cc;
+        if (r < nrows && col < D) {
+          float bsum = 0.f;
+          for (int t = 0; t < T; ++t) bsum = fmaf(sc[r * 16 + t], __ldg(W.agg_b1 + t * D + col), bsum);
+          ef[static_cast<size_t>(row0 + r) * D + col] = v + bsum;
+        }
+      });
+    }
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// k5a: edge2node, pairwise collapse.  Work item = scene.
+//   wsym[n][j] = ef[(n,j),t] + ef[(j,n),t]          (= sum_e H[e,n] ef[e,t] split by partner j)
+//   G[n][t][c] = sum_j wsym[n][j] * relu(P[n][t][c] + P[j][t][c] + b0[t][c])
+//   S[n][t]    = sum_j wsym[n][j]
+// smem: efs [N*N*T] | Pt [N][128] | wsym [N][N+1]
+// ===========================================================================
+__global__ void __launch_bounds__(GN_THREADS)
+edge2node_pair_kernel(const float* __restrict__ P, const float* __restrict__ edge_feat,
+                      int B, int N, int T, gn_stage_weights W,
+                      float* __restrict__ G, float* __restrict__ S) {
+  extern __shared__ __align__(16) float smem[];
+  const int E = N * N, ldn = N + 1, ldp = T * GN_MLP_HIDDEN;
+  float* efs = smem;
+  float* Pt = efs + ((E * T + 3) & ~3);
+  float* wsym = Pt + N * GN_MLP_HIDDEN;
+  const int tid = threadIdx.x, c = tid & 127, ng = tid >> 7;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    const float* efg = edge_feat + static_cast<size_t>(b) * E * T;
+    for (int i = tid; i < E * T; i += GN_THREADS) efs[i] = __ldg(efg + i);
+    for (int t = 0; t < T; ++t) {
+      __syncthreads();
+      for (int i = tid; i < N * 32; i += GN_THREADS) {
+        int n = i >> 5, c4 = i & 31;
+        *reinterpret_cast<float4*>(Pt + n * GN_MLP_HIDDEN + 4 * c4) =
+            ldg_f4(P + (static_cast<size_t>(b) * N + n) * ldp + t * GN_MLP_HIDDEN + 4 * c4);
+      }
+      for (int i = tid; i < E; i += GN_THREADS) {
+        int n = i / N, j = i - n * N;
+        wsym[n * ldn + j] = efs[(n * N + j) * T + t] + efs[(j * N + n) * T + t];
+      }
+      __syncthreads();
+      const float bb = __ldg(W.agg_b0 + t * GN_MLP_HIDDEN + c);
+      for (int n = ng; n < N; n += 2) {
+        const float pn = Pt[n * GN_MLP_HIDDEN + c] + bb;
+        float g = 0.f;
+        for (int j = 0; j < N; ++j)
+          g = fmaf(wsym[n * ldn + j], fmaxf(pn + Pt[j * GN_MLP_HIDDEN + c], 0.f), g);
+        G[(static_cast<size_t>(b) * N + n) * ldp + t * GN_MLP_HIDDEN + c] = g;
+      }
+      if (tid < N) {
+        float s = 0.f;
+        for (int j = 0; j < N; ++j) s += wsym[tid * ldn + j];
+        S[(static_cast<size_t>(b) * N + tid) * 16 + t] = s;
+      }
+    }
+  }
+}
+
+// ===========================================================================
+// k5b: edge2node, hyper: agg[n][:] = sum_e H[e,n] ef[e][:]   (:267)
+// ===========================================================================
+__global__ void __launch_bounds__(GN_THREADS)
+edge2node_hyper_kernel(const float* __restrict__ ef, const float* __restrict__ H,
+                       int B, int N, int E, int D, float* __restrict__ agg) {
+  extern __shared__ __align__(16) float smem[];
+  const int ldn = N + 1, d4 = D >> 2;
+  float* Hs = smem;                                   // [E][N+1]
+  const int tid = threadIdx.x;
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < E * N; i += GN_THREADS) {
+      int e = i / N, n = i - e * N;
+      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b) * E * N + i);
+    }
+    __syncthreads();
+    for (int i = tid; i < N * d4; i += GN_THREADS) {
+      int n = i / d4, c4 = i - n * d4;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = 0; e < E; ++e) {
+        float w = Hs[e * ldn + n];
+        if (w != 0.f) {
+          float4 v = ldg_f4(ef + (static_cast<size_t>(b) * E + e) * D + 4 * c4);
+          o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y);
+          o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
+        }
+      }
+      *reinterpret_cast<float4*>(agg + (static_cast<size_t>(b) * N + n) * D + 4 * c4) = o;
+    }
+  }
+}
+
+// ===========================================================================
+// k6: node_post — incoming = cat(agg, h) / N (:267,:120,:355); closing MLP
+// 2D -> 128 -> Dout (:195).  rows = B*N.
+// pairwise: agg = G W1cat^T + S b1 (second half of the collapse), K = T*128
+// streamed from HBM in 64-wide chunks.
+// smem: incT [K2p][LD] | hidT [128][LD] | stg [64][LD] | wp | Ss [TM][16]
+// ===========================================================================
+template <int TM, int TN, int NCH>
+__global__ void __launch_bounds__(GN_THREADS)
+node_post_kernel(const float* __restrict__ h, const float* __restrict__ aggin,
+                 const float* __restrict__ G, const float* __restrict__ S,
+                 int R, int N, int D, int Dc, int K2p, int T, int Dout, int Doutc, int pairwise,
+                 gn_stage_weights W, float* __restrict__ out) {
+  constexpr int LD = TM + 4, RM = TM / 16, RN = TN / 16;
+  extern __shared__ __align__(16) float smem[];
+  float* incT = smem;
+  float* hidT = incT + K2p * LD;
+  float* stg = hidT + 128 * LD;
+  float* wp = stg + 64 * LD;
+  float* Ss = wp + 2 * KC * 128;
+  const int tid = threadIdx.x;
+  const float fN = static_cast<float>(N);
+  const int ntiles = (R + TM - 1) / TM;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * TM, nrows = min(TM, R - row0);
+    // zero the K padding rows [2D, K2p)
+    for (int i = tid; i < (K2p - 2 * D) * LD; i += GN_THREADS) incT[2 * D * LD + i] = 0.f;
+    // skip half: h / N
+    load_tile_kmajor<TM>(incT + D * LD, h + static_cast<size_t>(row0) * D, D, nrows, D, D, fN, true);
+    if (!pairwise) {
+      load_tile_kmajor<TM>(incT, aggin + static_cast<size_t>(row0) * D, D, nrows, D, D, fN, true);
+    } else {
+      const int Kg = T * GN_MLP_HIDDEN;
+      for (int i = tid; i < TM * 16; i += GN_THREADS) {
+        int r = i >> 4, t = i & 15;
+        Ss[i] = (r < nrows && t < T) ? __ldg(S + static_cast<size_t>(row0 + r) * 16 + t) : 0.f;
+      }
+      float acc[NCH][RM][RN];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) acc_zero(acc[c]);
+      for (int k0 = 0; k0 < Kg; k0 += 64) {
+        load_tile_kmajor<TM>(stg, G + static_cast<size_t>(row0) * Kg + k0, Kg, nrows, 64, 64, 1.f, false);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c)
+          if (c * TN < Dc)
+            gemm_accum<TM, TN>(acc[c], stg, W.agg_w1t + static_cast<size_t>(k0) * Dc, Dc, c * TN, 64, wp);
+      }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (c * TN < Dc) {
+          acc_foreach<TM, TN>(acc[c], [&](int r, int cc, float& v) {
+            int col = c * TN + cc;
+            if (col < D) {
+              float bsum = 0.f;
+              for (int t = 0; t < T; ++t) bsum = fmaf(Ss[r * 16 + t], __ldg(W.agg_b1 + t * D + col), bsum);
+              incT[col * LD + r] = __fdiv_rn(v + bsum, fN);
+            }
+          });
+        }
+      }
+    }
+    // closing MLP
+    {
+      float acc[RM][8];
+      acc_zero(acc);
+      gemm_accum<TM, 128>(acc, incT, W.post_w0t, 128, 0, K2p, wp);
+      acc_store_kmajor<TM, 128>(acc, hidT, 0, [&](int col, int, float v) {
+        return fmaxf(v + __ldg(W.post_b0 + col), 0.f);
+      });
+    }
+    for (int c0 = 0; c0 < Doutc; c0 += 64) {
+      float acc[RM][4];
+      acc_zero(acc);
+      gemm_accum<TM, 64>(acc, hidT, W.post_w1t, Doutc, c0, 128, wp);
+      acc_foreach<TM, 64>(acc, [&](int r, int cc, float& v) {
+        int col = c0 + cc;
+        if (r < nrows && col < Dout)
+          out[static_cast<size_t>(row0 + r) * Dout + col] = v + __ldg(W.post_b1 + col);
+      });
+    }
+    __syncthreads();
+  }
+}
+
+// ===========================================================================
+// host side
+// ===========================================================================
+struct StagePlan {
+  int Dp, Dc, K2p, Doutc;
+  size_t off_xprime, off_pq, off_P, off_edges, off_eo, off_efeat, off_ef, off_G, off_S, off_agg;
+  size_t total;
+};
+
+static int make_plan(const gn_stage_cfg* c, StagePlan& p) {
+  if (c->B < 0 || c->N < 1 || c->N > GN_MAX_AGENTS) return GN_E_SHAPE;
+  if (c->D < 4 || (c->D & 3) || c->D > 256) return GN_E_SHAPE;
+  if (c->Dout < 1 || c->T < 1 || c->T > GN_SMALL_OUT - 1) return GN_E_SHAPE;
+  if (c->pairwise) { if (c->E != c->N * c->N) return GN_E_SHAPE; }
+  else if (c->E < 1 || c->E > GN_MAX_AGENTS) return GN_E_SHAPE;
+  p.Dp = round_up(c->D, 16);
+  p.Dc = c->D <= 64 ? 64 : round_up(c->D, 128);   // multiple of the TN the agg_w1t GEMMs use
+  p.K2p = round_up(2 * c->D, 16);
+  p.Doutc = round_up(c->Dout, 64);
+  const size_t R = static_cast<size_t>(c->B) * c->N, RE = static_cast<size_t>(c->B) * c->E;
+  size_t o = 0;
+  auto take = [&](size_t floats) { size_t at = o; o += round_up_sz(floats * 4, 256); return at; };
+  p.off_xprime = take(R * 64);
+  p.off_pq = take(R * 64);
+  p.off_edges = take(RE * 64);
+  p.off_efeat = take(RE * c->T);
+  if (c->pairwise) {
+    p.off_P = take(R * c->T * 128);
+    p.off_G = take(R * c->T * 128);
+    p.off_S = take(R * 16);
+    p.off_eo = p.off_ef = p.off_agg = 0;
+  } else {
+    p.off_eo = take(RE * c->D);
+    p.off_ef = take(RE * c->D);
+    p.off_agg = take(R * c->D);
+    p.off_P = p.off_G = p.off_S = 0;
+  }
+  p.total = o;
+  return GN_OK;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t bytes) {
+  if (bytes > 227 * 1024) return GN_E_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(bytes));
+  return e == cudaSuccess ? GN_OK : static_cast<int>(e);
+}
+
+static int grid_for(long long work, size_t smem) {
+  int per_sm = smem > 113 * 1024 ? 1 : (smem > 75 * 1024 ? 2 : (smem > 56 * 1024 ? 3 : 4));
+  long long g = static_cast<long long>(GN_SM_COUNT) * per_sm;
+  if (work < g) g = work;
+  return g < 1 ? 1 : static_cast<int>(g);
+}
+
+int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
+                   const float* H, const float* U, float* node_out, float* dist_out,
+                   void* ws, size_t ws_bytes, cudaStream_t st, bool skip_edge_mlp);
+
+}  // namespace gn
+
+namespace gn {
+
+#define GN_TRY(expr) do { int rc__ = (expr); if (rc__ != GN_OK) return rc__; } while (0)
+
+int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
+                   const float* H, const float* U, float* node_out, float* dist_out,
+                   void* ws, size_t ws_bytes, cudaStream_t st, bool skip_edge_mlp) {
+  StagePlan p;
+  GN_TRY(make_plan(c, p));
+  if (ws_bytes < p.total) return GN_E_WORKSPACE;
+  if (c->B == 0) return GN_OK;
+  char* base = static_cast<char*>(ws);
+  float* xprime = reinterpret_cast<float*>(base + p.off_xprime);
+  float* pq = reinterpret_cast<float*>(base + p.off_pq);
+  float* edges = reinterpret_cast<float*>(base + p.off_edges);
+  float* efeat = reinterpret_cast<float*>(base + p.off_efeat);
+  float* P = reinterpret_cast<float*>(base + p.off_P);
+  float* G = reinterpret_cast<float*>(base + p.off_G);
+  float* S = reinterpret_cast<float*>(base + p.off_S);
+  float* eo = reinterpret_cast<float*>(base + p.off_eo);
+  float* ef = reinterpret_cast<float*>(base + p.off_ef);
+  float* agg = reinterpret_cast<float*>(base + p.off_agg);
+  const int B = c->B, N = c->N, D = c->D, E = c->E, T = c->T;
+  const int R = B * N;
+  const long long RE = static_cast<long long>(B) * E;
+
+  // k1
+  {
+    constexpr int TM = 64, LD = TM + 4;
+    size_t smem = static_cast<size_t>(p.Dp + 128 + 64) * LD * 4 + 2 * KC * 128 * 4;
+    auto kern = node_pre_kernel<TM>;
+    GN_TRY(set_smem(kern, smem));
+    int grid = grid_for((R + TM - 1) / TM, smem);
+    kern<<<grid, GN_THREADS, smem, st>>>(h, R, D, p.Dp, T, c->pairwise, *w, xprime, pq, P);
+    GN_LAUNCH_CHECK();
+  }
+  // k2
+  if (c->pairwise) {
+    int ecmax = E < N2E_EC ? E : N2E_EC;
+    size_t smem = (static_cast<size_t>(2 * N) * N2E_LD + 2 * ecmax) * 4;
+    auto kern = node2edge_pair_kernel;
+    GN_TRY(set_smem(kern, smem));
+    long long work = static_cast<long long>(B) * ((E + N2E_EC - 1) / N2E_EC);
+    kern<<<grid_for(work, smem), GN_THREADS, smem, st>>>(xprime, pq, B, N, *w, edges);
+    GN_LAUNCH_CHECK();
+  } else {
+    if (!H) return GN_E_NULL;
+    size_t fl = static_cast<size_t>(2 * N) * N2E_LD + static_cast<size_t>(N) * (D + 4) +
+                2 * ((static_cast<size_t>(E) * (N + 1) + 3) & ~size_t(3)) + static_cast<size_t>(E) * 33;
+    size_t smem = fl * 4;
+    auto kern = node2edge_hyper_kernel;
+    GN_TRY(set_smem(kern, smem));
+    kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(xprime, pq, h, H, B, N, E, D, *w, edges, eo);
+    GN_LAUNCH_CHECK();
+  }
+  // k3
+  if (!skip_edge_mlp) {
+    if (c->noise_mode == GN_NOISE_GIVEN && !U) return GN_E_NULL;
+    constexpr int TM = 128, LD = TM + 4;
+    size_t smem = (static_cast<size_t>(64 + 128) * LD + 2 * KC * 128 + 256 * GN_SMALL_OUT +
+                   TM * 17 + TM * 16) * 4;
+    auto kern = edge_mlp_kernel<TM>;
+    GN_TRY(set_smem(kern, smem));
+    kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(
+        edges, RE, T, E, *w, U, c->noise_mode, c->seed, c->scene_offset, c->stage_index,
+        dist_out, efeat);
+    GN_LAUNCH_CHECK();
+  }
+  // k4 / k5
+  if (c->pairwise) {
+    size_t smem = (((static_cast<size_t>(E) * T + 3) & ~size_t(3)) + static_cast<size_t>(N) * 128 +
+                   static_cast<size_t>(N) * (N + 1)) * 4;
+    auto kern = edge2node_pair_kernel;
+    GN_TRY(set_smem(kern, smem));
+    kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(P, efeat, B, N, T, *w, G, S);
+    GN_LAUNCH_CHECK();
+  } else {
+    if (D <= 64) {
+      constexpr int TM = 128, LD = TM + 4;
+      size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
+      auto kern = edge_agg_kernel<TM, 64, 1>;
+      GN_TRY(set_smem(kern, smem));
+      kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef);
+    } else if (D <= 128) {
+      constexpr int TM = 128, LD = TM + 4;
+      size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
+      auto kern = edge_agg_kernel<TM, 128, 1>;
+      GN_TRY(set_smem(kern, smem));
+      kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef);
+    } else {
+      constexpr int TM = 64, LD = TM + 4;
+      size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
+      auto kern = edge_agg_kernel<TM, 128, 2>;
+      GN_TRY(set_smem(kern, smem));
+      kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef);
+    }
+    GN_LAUNCH_CHECK();
+    size_t smem = static_cast<size_t>(E) * (N + 1) * 4;
+    auto kern = edge2node_hyper_kernel;
+    GN_TRY(set_smem(kern, smem));
+    kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(ef, H, B, N, E, D, agg);
+    GN_LAUNCH_CHECK();
+  }
+  // k6
+  {
+    constexpr int TM = 64, LD = TM + 4;
+    size_t smem = (static_cast<size_t>(p.K2p + 128 + 64) * LD + 2 * KC * 128 + TM * 16) * 4;
+    int grid = grid_for((R + TM - 1) / TM, smem);
+    if (D <= 64) {
+      auto kern = node_post_kernel<TM, 64, 1>;
+      GN_TRY(set_smem(kern, smem));
+      kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out);
+    } else if (D <= 128) {
+      auto kern = node_post_kernel<TM, 128, 1>;
+      GN_TRY(set_smem(kern, smem));
+      kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out);
+    } else {
+      auto kern = node_post_kernel<TM, 128, 2>;
+      GN_TRY(set_smem(kern, smem));
+      kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out);
+    }
+    GN_LAUNCH_CHECK();
+  }
+  return GN_OK;
+}
+
+size_t stage_workspace_bytes_simt(const gn_stage_cfg* c) {
+  StagePlan p;
+  if (make_plan(c, p) != GN_OK) return 0;
+  return p.total;
+}
+
+}  // namespace gn

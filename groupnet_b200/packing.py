@@ -1,0 +1,163 @@
+"""Weight packing for the C ABI (`struct gn_stage_weights`).
+
+The kernels read every Linear as a K-major matrix `Wt[k][n]` (the transpose of
+`nn.Linear.weight`), zero-padded in K to a multiple of 16 and in N to a
+multiple of the GEMM chunk width, with the columns of each chunk permuted so a
+thread's columns are contiguous in shared memory (csrc/gn_gemm_simt.cuh).
+Packing is pure host-side plumbing over the module's own parameters; packed
+copies are cached and rebuilt when any parameter's `_version` changes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+def chunk_permutation(tn: int) -> torch.Tensor:
+    """src[pos] = original column (inside a TN chunk) stored at packed position
+    `pos`.  Thread tx owns original columns tx + 16*j; they are stored at
+    (j//4)*64 + tx*4 + j%4 (TN = 128) or tx*4 + j (TN = 64)."""
+    src = torch.empty(tn, dtype=torch.long)
+    rn = tn // 16
+    for tx in range(16):
+        for j in range(rn):
+            pos = (j // 4) * 64 + tx * 4 + (j % 4)
+            src[pos] = tx + 16 * j
+    return src
+
+
+def permute_cols(wt: torch.Tensor, tn: int) -> torch.Tensor:
+    k, n = wt.shape
+    assert n % tn == 0
+    src = chunk_permutation(tn).to(wt.device)
+    idx = (torch.arange(0, n, tn, device=wt.device)[:, None] + src[None, :]).reshape(-1)
+    return wt[:, idx].contiguous()
+
+
+def _kmajor(weight: torch.Tensor, kp: int, nc: int, tn: int) -> torch.Tensor:
+    """nn.Linear.weight (N_out, K) -> packed K-major (kp, nc)."""
+    n_out, k = weight.shape
+    wt = torch.zeros(kp, nc, dtype=torch.float32, device=weight.device)
+    wt[:k, :n_out] = weight.detach().t()
+    return permute_cols(wt, tn)
+
+
+def agg_out_cols(d: int) -> Tuple[int, int]:
+    """(Dc, TN) of the aggregation output GEMM; must match make_plan() in
+    csrc/gn_stage_simt.cu."""
+    if d <= 64:
+        return 64, 64
+    return _round_up(d, 128), 128
+
+
+def stage_modules(layer, s: int):
+    """Sub-modules used by message-passing stage `s` of a layer with L = nmp_layers
+    (MS_HGNN_batch.py:173-195): dict-softmax, closing MLP."""
+    n_stage = max(layer.nmp_layers, 1)
+    dict_mod = layer.nmp_mlp_start if s == 0 else layer.nmp_mlps[2 * s - 1]
+    post_mod = layer.nmp_mlp_end if s == n_stage - 1 else layer.nmp_mlps[2 * s]
+    return dict_mod, post_mod
+
+
+def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
+    d = layer.h_dim
+    t = layer.edge_types
+    dp = _round_up(d, 16)
+    k2p = _round_up(2 * d, 16)
+    dict_mod, post_mod = stage_modules(layer, s)
+    node = layer.node2edge_start_mlp[s].layers
+    att = layer.attention_mlp[s].layers
+    agg = layer.edge_aggregation_list[s].agg_mlp
+    dout = post_mod.layers[1].weight.shape[0]
+    doutc = _round_up(dout, 64)
+    dc, agg_tn = agg_out_cols(d)
+
+    def dev(x):
+        return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    out: Dict[str, torch.Tensor] = {}
+    out["node_w0t"] = _kmajor(dev(node[0].weight), dp, 256, 128)
+    out["node_b0"] = dev(node[0].bias)
+    out["node_w1t"] = _kmajor(dev(node[1].weight), 256, 64, 64)
+    out["node_b1"] = dev(node[1].bias)
+
+    w0 = dev(att[0].weight)                                   # (32, 128): [x_n ; edge_init_e]
+    wpq = torch.cat((w0[:, :64].t(), w0[:, 64:].t()), dim=1)  # (64, 64): pn | q
+    out["att_wpqt"] = permute_cols(wpq.contiguous(), 64)
+    out["att_b0"] = dev(att[0].bias)
+    out["att_w1"] = dev(att[1].weight).reshape(-1)
+    out["att_b1"] = dev(att[1].bias).reshape(-1)
+
+    init, dist, fac = dict_mod.init_MLP.layers, dict_mod.MLP_distribution.layers, dict_mod.MLP_factor.layers
+    out["init_w0t"] = _kmajor(dev(init[0].weight), 64, 128, 128)
+    out["init_b0"] = dev(init[0].bias)
+    out["init_w1t"] = _kmajor(dev(init[1].weight), 128, 64, 64)
+    out["init_b1"] = dev(init[1].bias)
+    df0 = torch.cat((dev(dist[0].weight), dev(fac[0].weight)), dim=0)     # (256, 64)
+    out["df_w0t"] = _kmajor(df0, 64, 256, 128)
+    out["df_b0"] = torch.cat((dev(dist[0].bias), dev(fac[0].bias)))
+    w1 = torch.zeros(256, 16, dtype=torch.float32, device=device)
+    w1[:128, :t] = dev(dist[1].weight).t()
+    w1[128:, t] = dev(fac[1].weight).reshape(-1)
+    out["df_w1"] = w1
+    b1 = torch.zeros(16, dtype=torch.float32, device=device)
+    b1[:t] = dev(dist[1].bias)
+    b1[t] = dev(fac[1].bias).reshape(-1)[0]
+    out["df_b1"] = b1
+
+    a0 = torch.cat([dev(m.layers[0].weight) for m in agg], dim=0)         # (T*128, D)
+    out["agg_w0t"] = _kmajor(a0, dp, t * 128, 128)
+    out["agg_b0"] = torch.cat([dev(m.layers[0].bias) for m in agg])
+    a1 = torch.zeros(t * 128, dc, dtype=torch.float32, device=device)
+    for i, m in enumerate(agg):
+        a1[i * 128:(i + 1) * 128, :d] = dev(m.layers[1].weight).t()
+    out["agg_w1t"] = permute_cols(a1, agg_tn)
+    out["agg_b1"] = torch.stack([dev(m.layers[1].bias) for m in agg]).contiguous()
+
+    out["post_w0t"] = _kmajor(dev(post_mod.layers[0].weight), k2p, 128, 128)
+    out["post_b0"] = dev(post_mod.layers[0].bias)
+    out["post_w1t"] = _kmajor(dev(post_mod.layers[1].weight), 128, doutc, 64)
+    out["post_b1"] = dev(post_mod.layers[1].bias)
+    return out
+
+
+class PackedStage:
+    """Device copies of one stage's packed weights + the ctypes struct over them."""
+
+    def __init__(self, layer, s: int, device: torch.device):
+        self.tensors = pack_stage(layer, s, device)
+        self.dout = int(self.tensors["post_b1"].numel())
+        self.struct = _lib.StageWeights()
+        for name in _lib.StageWeights.FIELDS:
+            tens = self.tensors[name]
+            assert tens.is_contiguous() and tens.dtype == torch.float32
+            setattr(self.struct, name, C.c_void_p(tens.data_ptr()))
+
+
+class PackCache:
+    """Per-layer cache of PackedStage objects, invalidated when a parameter is
+    modified in place (optimizer step, load_state_dict) or moved."""
+
+    def __init__(self) -> None:
+        self._key = None
+        self._stages: List[PackedStage] = []
+
+    @staticmethod
+    def _fingerprint(layer, device) -> tuple:
+        return (str(device),) + tuple((p.data_ptr(), p._version) for p in layer.parameters())
+
+    def get(self, layer, device: torch.device) -> List[PackedStage]:
+        key = self._fingerprint(layer, device)
+        if key != self._key:
+            n_stage = max(layer.nmp_layers, 1)
+            self._stages = [PackedStage(layer, s, device) for s in range(n_stage)]
+            self._key = key
+        return self._stages

@@ -1,0 +1,169 @@
+/*
+ * groupnet_b200.h — C ABI of libgroupnet_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the hot path of TaliMotzkin/GroupNet:
+ * model/MS_HGNN_batch.py (MS_HGNN_oridinary, MS_HGNN_hyper).  The reference
+ * has no FFI of its own (it is pure PyTorch); its boundary is the nn.Module
+ * API.  groupnet_b200/layers.py keeps that API (constructor + forward
+ * signatures, state_dict schema) and calls the entry points below through
+ * ctypes.  Every entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *  - plain C types only; all tensor arguments are DEVICE pointers to
+ *    contiguous fp32 buffers owned by the caller; `stream` is a cudaStream_t
+ *    passed as void* (NULL = legacy default stream);
+ *  - the library never allocates device memory and keeps no global state:
+ *    the caller passes outputs and a workspace (gn_stage_workspace_bytes);
+ *  - return value: 0 = ok, <0 = GN_E_* argument error (nothing launched),
+ *    >0 = cudaError_t from a launch; nothing throws across the ABI;
+ *  - re-entrant: one process per GPU or several streams may call concurrently.
+ */
+#ifndef GROUPNET_B200_H
+#define GROUPNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GN_ABI_VERSION 1
+
+#define GN_MAX_AGENTS 64      /* N <= 64: one 64-bit membership word per hyperedge */
+#define GN_MAX_SCALES 8
+#define GN_ATT_DIM 64         /* hdim_extend, MS_HGNN_batch.py:72,:292 */
+#define GN_ATT_HIDDEN 32      /* attention_mlp hidden, :80,:301 */
+#define GN_NODE_HIDDEN 256    /* node2edge_start_mlp hidden, :84,:306 */
+#define GN_MLP_HIDDEN 128     /* every other hidden size, :75,:77,:254 */
+#define GN_SMALL_OUT 16       /* padded width of [distribution logits | factor logit] */
+
+enum gn_error {
+  GN_OK = 0,
+  GN_E_NULL = -1,        /* required pointer is NULL */
+  GN_E_SHAPE = -2,       /* unsupported or inconsistent shape */
+  GN_E_SCALE = -3,       /* scale > N: the reference raises "selected index k out of range" (:382) */
+  GN_E_WORKSPACE = -4,   /* workspace too small */
+  GN_E_PRECISION = -5,   /* unknown precision / path not built */
+  GN_E_ALIGN = -6        /* pointer not 16-byte aligned */
+};
+
+enum gn_precision {
+  GN_FP32 = 0,           /* fp32 FFMA everywhere: the 1e-5 parity path */
+  GN_BF16_TC = 1         /* bf16 tcgen05/TMEM GEMMs for the per-edge MLP chain, fp32 accumulate (2e-2) */
+};
+
+enum gn_noise_mode {
+  GN_NOISE_GIVEN = 0,    /* U (B,E,T) uniform[0,1) supplied by the caller (reference RNG order) */
+  GN_NOISE_PHILOX = 1    /* Philox4x32-10 on device, keyed by (seed, stage, global element index) */
+};
+
+typedef void* gn_stream_t;
+
+/* One message-passing stage = node2edge -> MLP_dict_softmax -> edge2node -> MLP
+ * (MS_HGNN_batch.py:173-195 / :425-441).  nmp_layers = L is L stages chained by
+ * the host.  All weights are fp32 device pointers, pre-arranged by
+ * groupnet_b200/packing.py ("t" = transposed to [K][N_out], K-major; K padded
+ * to a multiple of 16 and N_out to a multiple of 64 with zeros). */
+typedef struct gn_stage_weights {
+  /* node2edge_start_mlp[i]  (:84,:125)   D -> 256 -> 64 */
+  const float* node_w0t;  /* [Dp][256] */
+  const float* node_b0;   /* [256] */
+  const float* node_w1t;  /* [256][64] */
+  const float* node_b1;   /* [64] */
+  /* attention_mlp[i]  (:80,:134)   [x_n ; edge_init_e] 128 -> 32 -> 1, first layer split */
+  const float* att_wpqt;  /* [64][64]: cols 0..31 = W0[:, :64]^T (node half), 32..63 = W0[:, 64:]^T (edge half) */
+  const float* att_b0;    /* [32] */
+  const float* att_w1;    /* [32] */
+  const float* att_b1;    /* [1] */
+  /* MLP_dict_softmax  (:31-53) */
+  const float* init_w0t;  /* [64][128] */
+  const float* init_b0;   /* [128] */
+  const float* init_w1t;  /* [128][64] */
+  const float* init_b1;   /* [64] */
+  const float* df_w0t;    /* [64][256]: cols 0..127 MLP_distribution.layers.0, 128..255 MLP_factor.layers.0 */
+  const float* df_b0;     /* [256] */
+  const float* df_w1;     /* [256][16]: rows <128 -> cols 0..T-1 (distribution), rows >=128 -> col T (factor) */
+  const float* df_b1;     /* [16] */
+  /* edge_aggregation.agg_mlp[t]  (:247-268)   D -> 128 -> D, T of them */
+  const float* agg_w0t;   /* [Dp][T*128] */
+  const float* agg_b0;    /* [T*128] */
+  const float* agg_w1t;   /* [T*128][Dc], Dc = D rounded up to 64 */
+  const float* agg_b1;    /* [T][D] */
+  /* nmp_mlps[2l] or nmp_mlp_end  (:77,:195)   2D -> 128 -> Dout */
+  const float* post_w0t;  /* [(2D)p][128]: rows 0..D-1 act on the aggregated half, D..2D-1 on the skip half */
+  const float* post_b0;   /* [128] */
+  const float* post_w1t;  /* [128][Doutc] */
+  const float* post_b1;   /* [Dout] */
+} gn_stage_weights;
+
+typedef struct gn_stage_cfg {
+  int32_t B;            /* scenes in this call */
+  int32_t N;            /* agents per scene, 1..GN_MAX_AGENTS */
+  int32_t D;            /* h_dim, multiple of 4 */
+  int32_t Dout;         /* output width of the stage's closing MLP */
+  int32_t E;            /* edges per scene: N*N (pairwise), N or 1 (hyper) */
+  int32_t T;            /* edge types: 6 pairwise (:74), 10 hyper (:294); <= 15 */
+  int32_t pairwise;     /* 1: ordered pairs incl. self loops, incidence implicit (:143-160); 0: H given */
+  int32_t precision;    /* enum gn_precision */
+  int32_t noise_mode;   /* enum gn_noise_mode */
+  int32_t stage_index;  /* 0..L-1, separates Philox streams of chained stages */
+  uint64_t seed;        /* Philox key */
+  int64_t scene_offset; /* global index of scene 0 of this call: results do not depend on sharding */
+} gn_stage_cfg;
+
+/* ABI version of the loaded library (== GN_ABI_VERSION). */
+int gn_abi_version(void);
+
+/* Static string for a return code (GN_E_* or cudaError_t). */
+const char* gn_error_string(int code);
+
+/* Fused feature correlation + per-agent top-k hyperedge selection for every
+ * scale + incidence emission.  Replaces F.normalize + matmul
+ * (model/GroupNet_nba.py:284-286) and init_adj_attention
+ * (model/MS_HGNN_batch.py:372-388) for S scales in one pass over x.
+ *   x            (B,N,D)
+ *   scales[s]    reference `scale` argument; <1 is clamped to 1, ==N gives the
+ *                single all-ones hyperedge, >N returns GN_E_SCALE
+ *   H_out[s]     element (b,e,n) is written at H_out[s][b*H_scene_stride[s] + e*N + n],
+ *                e < (scales[s]==N ? 1 : N); a stride larger than E*N lets the
+ *                caller write straight into the concatenated (B,sum E,N) tensor
+ *                the encoders build (model/GroupNet_nba.py:296,299)
+ *   corr_out     optional (B,N,N), may be NULL
+ * Ties: among equal correlations the lower agent index is selected. */
+int gn_corr_topk_h(const float* x, int32_t B, int32_t N, int32_t D,
+                   const int32_t* scales, int32_t S,
+                   float* const* H_out, const int64_t* H_scene_stride,
+                   float* corr_out, gn_stream_t stream);
+
+/* Top-k incidence from a caller-supplied correlation tensor: exactly
+ * init_adj_attention (model/MS_HGNN_batch.py:372-388).  corr (B,N,N). */
+int gn_topk_h(const float* corr, int32_t B, int32_t N, int32_t scale,
+              float* H_out, int64_t H_scene_stride, gn_stream_t stream);
+
+/* Bytes of device workspace gn_stage_fwd needs for this configuration. */
+size_t gn_stage_workspace_bytes(const gn_stage_cfg* cfg);
+
+/* One message-passing stage forward.
+ *   h_in      (B,N,D)    node features entering the stage
+ *   H         (B,E,N)    incidence (0/1 fp32) for hyper stages; ignored (may be NULL) when cfg->pairwise
+ *   U         (B,E,T)    uniform draws when noise_mode == GN_NOISE_GIVEN, else may be NULL
+ *   node_out  (B,N,Dout) output of the closing MLP (node_feat)
+ *   dist_out  (B,E,T)    optional: the categorical `distribution` the reference returns as
+ *                        `factors` (:53,:178,:427); may be NULL for stages > 0
+ * Replaces node2edge (:122-141/:357-370), MLP_dict_softmax.forward (:41-53),
+ * gumbel_softmax (:446-520), edge2node/edge_aggregation (:116-120,:259-268) and
+ * the closing MLP (:195,:441). */
+int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
+                 const float* h_in, const float* H, const float* U,
+                 float* node_out, float* dist_out,
+                 void* workspace, size_t workspace_bytes, gn_stream_t stream);
+
+/* Number of kernel launches the last-described configuration issues per
+ * gn_stage_fwd call (for bench.py's gpu_launches accounting). */
+int gn_stage_launch_count(const gn_stage_cfg* cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GROUPNET_B200_H */

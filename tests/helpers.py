@@ -1,0 +1,74 @@
+"""Shared test helpers: golden fixtures, weight regeneration, parity criterion."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+REFERENCE_DIR = os.environ.get("GROUPNET_REF", "/root/reference")
+
+# fp32 parity criterion (SURVEY.md §7 "Tolerance definition", BASELINE.json north_star):
+# per output tensor  max|got - ref| <= 1e-5 * max|ref|
+FP32_REL = 1e-5
+BF16_REL = 2e-2
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0]
+                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    g = {k: z[k] for k in z.files}
+    for k in ("B", "N", "D", "Bo", "L", "scale", "emb", "weight_seed"):
+        g[k] = int(g[k])
+    g["kind"] = str(g["kind"])
+    g["weight_sha256"] = str(g["weight_sha256"])
+    g["noise"] = [g[f"U{i}"] for i in range(max(g["L"], 1))]
+    return g
+
+
+def state_sha(module) -> str:
+    hsh = hashlib.sha256()
+    for k, v in module.state_dict().items():
+        hsh.update(k.encode())
+        hsh.update(v.detach().cpu().numpy().astype(np.float32).tobytes())
+    return hsh.hexdigest()
+
+
+def build_layer(g):
+    """Regenerate the fixture's weights in the drop-in layer (CPU) and check the pin."""
+    import groupnet_b200 as gb
+    torch.manual_seed(g["weight_seed"])
+    if g["kind"] == "pairwise":
+        m = gb.MS_HGNN_oridinary(embedding_dim=g["emb"], h_dim=g["D"], mlp_dim=64,
+                                 bottleneck_dim=g["Bo"], batch_norm=0, nmp_layers=g["L"])
+    else:
+        m = gb.MS_HGNN_hyper(embedding_dim=g["emb"], h_dim=g["D"], mlp_dim=64,
+                             bottleneck_dim=g["Bo"], batch_norm=0, nmp_layers=g["L"], scale=g["scale"])
+    got = state_sha(m)
+    assert got == g["weight_sha256"], (
+        "regenerated weights differ from the ones the golden outputs were computed with "
+        "(torch RNG / init drift): regenerate tests/golden with make_golden.py")
+    return m.eval()
+
+
+def rel_err(got, ref) -> float:
+    got = torch.as_tensor(got, dtype=torch.float64).cpu()
+    ref = torch.as_tensor(ref, dtype=torch.float64).cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    den = ref.abs().max().item()
+    return (got - ref).abs().max().item() / (den if den > 0 else 1.0)
+
+
+def assert_close(got, ref, rel, what=""):
+    e = rel_err(got, ref)
+    assert e <= rel, f"{what}: max|d|/max|ref| = {e:.3e} > {rel:.1e}"
+
+
+def have_reference() -> bool:
+    return os.path.exists(os.path.join(REFERENCE_DIR, "model", "MS_HGNN_batch.py"))

@@ -1,0 +1,138 @@
+"""Host-side boundary checks that need no GPU: the C-ABI library loads and
+exports every symbol include/groupnet_b200.h declares, the drop-in modules keep
+the reference's state_dict schema, packing is a pure permutation, and the
+product path refuses to run without CUDA (no CPU fallback)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+import groupnet_b200 as gb
+from groupnet_b200 import _lib, packing
+from helpers import REFERENCE_DIR, ROOT, build_layer, golden_names, have_reference, load_golden
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "groupnet_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = _declared_symbols()
+    assert set(syms) == set(_lib.EXPORTS), (syms, _lib.EXPORTS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(lib, s), f"libgroupnet_b200.so does not export {s}"
+    assert _lib.load().gn_abi_version() == _lib.ABI_VERSION
+    assert _lib.load().gn_error_string(-3) == b"selected index k out of range"
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(_lib.StageWeights) == 24 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.StageCfg) == 10 * 4 + 8 + 8
+    text = open(os.path.join(ROOT, "include", "groupnet_b200.h")).read()
+    body = text[text.index("typedef struct gn_stage_weights"):text.index("} gn_stage_weights;")]
+    fields = re.findall(r"const float\*\s+(\w+);", body)
+    assert tuple(fields) == _lib.StageWeights.FIELDS
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not present")
+@pytest.mark.parametrize("layers", [1, 2, 3])
+def test_state_dict_matches_reference(layers):
+    if REFERENCE_DIR not in sys.path:
+        sys.path.insert(0, REFERENCE_DIR)
+    import model.MS_HGNN_batch as ref
+    for ctor_r, ctor_m, kw in (
+            (ref.MS_HGNN_oridinary, gb.MS_HGNN_oridinary, dict(embedding_dim=16)),
+            (ref.MS_HGNN_hyper, gb.MS_HGNN_hyper, dict(embedding_dim=64, scale=5))):
+        torch.manual_seed(5)
+        r = ctor_r(h_dim=64, mlp_dim=64, bottleneck_dim=48, batch_norm=0, nmp_layers=layers, **kw)
+        torch.manual_seed(5)
+        m = ctor_m(h_dim=64, mlp_dim=64, bottleneck_dim=48, batch_norm=0, nmp_layers=layers, **kw)
+        rs, ms = r.state_dict(), m.state_dict()
+        assert list(rs.keys()) == list(ms.keys())
+        assert [n for n, _ in r.named_parameters()] == [n for n, _ in m.named_parameters()]
+        for k in rs:
+            assert rs[k].shape == ms[k].shape and torch.equal(rs[k], ms[k]), k
+        m.load_state_dict(rs, strict=True)
+        r.load_state_dict(ms, strict=True)
+
+
+def test_default_constructor_signature():
+    import inspect
+    sig = inspect.signature(gb.MS_HGNN_oridinary.__init__)
+    assert list(sig.parameters)[1:] == ["embedding_dim", "h_dim", "mlp_dim", "bottleneck_dim", "activation",
+                                        "batch_norm", "dropout", "nmp_layers", "vis"]
+    sig = inspect.signature(gb.MS_HGNN_hyper.__init__)
+    assert list(sig.parameters)[1:] == ["embedding_dim", "h_dim", "mlp_dim", "bottleneck_dim", "activation",
+                                        "batch_norm", "dropout", "nmp_layers", "scale", "vis", "actor_number"]
+    m = gb.MS_HGNN_hyper(h_dim=64, bottleneck_dim=64, nmp_layers=1)
+    assert m.scale == 2 and m.edge_types == 10 and m.listall is False
+    assert sum(p.numel() for p in m.parameters()) == 283340
+    m = gb.MS_HGNN_oridinary(h_dim=64, bottleneck_dim=64, nmp_layers=1)
+    assert sum(p.numel() for p in m.parameters()) == 212168
+
+
+@pytest.mark.parametrize("name", ["nba_pairwise", "l2_hyper", "crowd_hyper2"])
+def test_golden_weights_regenerate(name):
+    build_layer(load_golden(name))
+
+
+@pytest.mark.parametrize("tn", [64, 128])
+def test_chunk_permutation_is_permutation(tn):
+    src = packing.chunk_permutation(tn)
+    assert sorted(src.tolist()) == list(range(tn))
+    w = torch.arange(3 * 2 * tn, dtype=torch.float32).reshape(3, 2 * tn)
+    p = packing.permute_cols(w, tn)
+    for tx in range(16):
+        for j in range(tn // 16):
+            pos = (j // 4) * 64 + tx * 4 + (j % 4)
+            assert torch.equal(p[:, tn + pos], w[:, tn + tx + 16 * j])
+
+
+def test_pack_stage_shapes_and_content():
+    m = build_layer(load_golden("l2_hyper"))      # D=64, Bo=96, L=2, T=10
+    for s in range(2):
+        t = packing.pack_stage(m, s, torch.device("cpu"))
+        assert t["node_w0t"].shape == (64, 256) and t["agg_w0t"].shape == (64, 1280)
+        assert t["agg_w1t"].shape == (1280, 64) and t["post_w0t"].shape == (128, 128)
+        assert t["post_w1t"].shape == (128, 64 if s == 0 else 128)
+        assert t["post_b1"].numel() == (64 if s == 0 else 96)
+        assert t["df_w1"].shape == (256, 16) and float(t["df_w1"][:128, 10:].abs().sum()) == 0.0
+    # un-permuting recovers the transposed Linear weight
+    t = packing.pack_stage(m, 0, torch.device("cpu"))
+    src = packing.chunk_permutation(128)
+    w = m.nmp_mlp_start.init_MLP.layers[0].weight.detach()           # (128, 64)
+    un = torch.empty(64, 128)
+    un[:, src] = t["init_w0t"]
+    assert torch.equal(un, w.t())
+
+
+def test_no_cpu_fallback():
+    m = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(2, 3, 64))
+    h = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        h(torch.randn(2, 3, 64), torch.randn(2, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gb.corr_topk_h(torch.randn(2, 3, 64), [2])
+    with pytest.raises(RuntimeError):
+        m.nmp_mlp_end(torch.randn(2, 128))       # containers do not compute
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "groupnet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("test oracle", ""), f"{f} mentions the oracle"
+
+
+def test_all_goldens_present():
+    assert len(golden_names()) >= 20

@@ -1,0 +1,274 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors from
+the live reference and against the CPU oracle.  Run on the B200 box: -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import groupnet_b200 as gb
+from groupnet_b200 import _lib
+from helpers import BF16_REL, FP32_REL, assert_close, build_layer, golden_names, load_golden, rel_err
+from oracle import ms_hgnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_native_library_is_loaded():
+    lib = _lib.load()
+    assert lib.gn_abi_version() == 1
+    maps = open("/proc/self/maps").read()
+    assert "libgroupnet_b200.so" in maps
+
+
+# ---- T1: H from the reference's corr, bit-exact ---------------------------------
+@pytest.mark.parametrize("name", [n for n in golden_names() if "hyper" in n])
+def test_topk_h_bit_exact_vs_golden(name):
+    g = load_golden(name)
+    h = gb.topk_h(torch.from_numpy(g["corr"]).to(DEV), g["scale"])
+    assert h.shape == g["H"].shape
+    assert torch.equal(h.cpu(), torch.from_numpy(g["H"]))
+
+
+@pytest.mark.parametrize("n,d,scales", [(11, 64, [5, 11]), (8, 64, [3, 5, 8]), (20, 64, [5, 8]),
+                                        (64, 256, [2, 4, 8, 16]), (5, 32, [0, 1, 5]), (33, 128, [7, 32]),
+                                        (2, 8, [1, 2]), (1, 64, [1])])
+def test_topk_h_vs_oracle_random(n, d, scales):
+    gen = torch.Generator().manual_seed(n * 1000 + d)
+    x = torch.randn(257, n, d, generator=gen)
+    corr = O.feature_correlation(x)
+    for s in scales:
+        ref = O.incidence_topk(corr, s)
+        got = gb.topk_h(corr.to(DEV), s).cpu()
+        gap = O.topk_gap(corr, s)
+        ok = (got == ref).all(dim=2)
+        if ref.shape[1] == n:
+            bad = ~ok & (gap > 0)
+            assert not bad.any(), f"{int(bad.sum())} tie-free rows differ (n={n}, scale={s})"
+            assert torch.equal(got, torch.from_numpy(O.incidence_topk_lowest_index(corr.numpy(), s)))
+        else:
+            assert ok.all()
+
+
+# ---- T2: constructed ties ---------------------------------------------------------
+def test_topk_ties_lowest_index():
+    corr = torch.zeros(3, 6, 6)
+    corr[0] = 0.5                      # everything tied
+    corr[1, :, 3:] = 1.0               # tie among the top three
+    corr[2] = torch.tensor([0.1, 0.9, 0.9, 0.1, 0.9, 0.9]).repeat(6, 1)
+    for k in (1, 2, 3, 4):
+        got = gb.topk_h(corr.to(DEV), k).cpu().numpy()
+        ref = O.incidence_topk_lowest_index(corr.numpy(), k)
+        assert np.array_equal(got, ref)
+    # zero feature rows normalise to 0 and tie with everything: lowest indices win
+    x = torch.zeros(2, 5, 16)
+    hs = gb.corr_topk_h(x.to(DEV), [2])
+    assert hs[0].cpu()[0, 0].tolist() == [1, 1, 0, 0, 0]
+
+
+def test_scale_errors_and_edge_cases():
+    corr = torch.eye(4).repeat(2, 1, 1).to(DEV)
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        gb.topk_h(corr, 5)
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        gb.corr_topk_h(torch.randn(2, 4, 8, device=DEV), [2, 9])
+    assert gb.topk_h(corr, 4).shape == (2, 1, 4)
+    assert torch.equal(gb.topk_h(corr, 0), gb.topk_h(corr, 1))
+    assert torch.equal(gb.topk_h(corr, 1).cpu(), torch.eye(4).repeat(2, 1, 1))
+    empty = gb.topk_h(torch.empty(0, 4, 4, device=DEV), 2)
+    assert empty.shape == (0, 4, 4)
+    with pytest.raises(RuntimeError, match="Float"):
+        gb.topk_h(corr.double(), 2)
+
+
+# ---- T3: fused corr + top-k --------------------------------------------------------
+@pytest.mark.parametrize("n,d,scales,b", [(11, 64, [5, 11], 1000), (8, 64, [3, 5, 8], 333),
+                                          (20, 64, [5, 8], 130), (64, 256, [2, 4, 8, 16], 70),
+                                          (7, 36, [2, 7], 50), (3, 4, [1, 2], 9)])
+def test_fused_corr_topk(n, d, scales, b):
+    gen = torch.Generator().manual_seed(b)
+    x = torch.randn(b, n, d, generator=gen)
+    (hs, full), corr = gb.corr_topk_h(x.to(DEV), scales, concat=True, return_corr=True)
+    corr = corr.cpu()
+    ref_corr = O.feature_correlation(x)
+    assert (corr - ref_corr).abs().max().item() <= 2e-6
+    assert full.shape == (b, sum(1 if s == n else n for s in scales), n)
+    off = 0
+    for s, hm in zip(scales, hs):
+        hm = hm.cpu()
+        # self-consistency: H == topk(own corr) with the documented tie rule
+        assert np.array_equal(hm.numpy(), O.incidence_topk_lowest_index(corr.numpy(), s))
+        # vs the reference corr: only rows whose k/k+1 gap is within the corr error may differ
+        ref = O.incidence_topk(ref_corr, s)
+        if hm.shape[1] == n:
+            bad = ~(hm == ref).all(dim=2)
+            assert (O.topk_gap(ref_corr, s)[bad] < 4e-6).all()
+            assert hm.sum(2).eq(max(s, 1)).all()
+        assert torch.equal(full[:, off:off + hm.shape[1]].cpu(), hm)
+        off += hm.shape[1]
+    sep = gb.corr_topk_h(x.to(DEV), scales)
+    for a, c in zip(sep, hs):
+        assert torch.equal(a, c.contiguous())
+
+
+# ---- T4: layer forward vs golden (reference outputs) ---------------------------------
+def _run_layer(g, precision="fp32"):
+    m = build_layer(g).to(DEV).set_precision(precision)
+    h = torch.from_numpy(g["h"]).to(DEV)
+    noise = [torch.from_numpy(u).to(DEV) for u in g["noise"]]
+    if g["kind"] == "pairwise":
+        node, fac = m(h, noise=noise)
+        hinc = None
+    else:
+        node, fac, hinc = m(h, torch.from_numpy(g["corr"]).to(DEV), noise=noise)
+    torch.cuda.synchronize()
+    return node, fac, hinc
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_layer_forward_fp32_vs_golden(name):
+    g = load_golden(name)
+    node, fac, hinc = _run_layer(g)
+    if hinc is not None:
+        assert torch.equal(hinc.cpu(), torch.from_numpy(g["H"]))
+    assert node.shape == g["node_feat"].shape and fac.shape == g["factors"].shape
+    assert_close(fac, g["factors"], FP32_REL, f"{name} factors")
+    assert_close(node, g["node_feat"], FP32_REL, f"{name} node_feat")
+    assert torch.allclose(fac.sum(-1), torch.ones_like(fac[..., 0]), atol=1e-5)
+
+
+# ---- larger seeded batches vs the oracle (sizes the oracle finishes in seconds) -------
+@pytest.mark.parametrize("kind,n,d,bo,scale,layers,b", [
+    ("pairwise", 11, 64, 64, 0, 1, 300), ("hyper", 11, 64, 64, 5, 1, 700), ("hyper", 11, 64, 64, 11, 1, 700),
+    ("pairwise", 8, 64, 64, 0, 2, 130), ("hyper", 20, 64, 64, 8, 2, 200), ("hyper", 64, 256, 256, 4, 1, 9),
+    ("pairwise", 5, 96, 72, 0, 1, 129), ("hyper", 9, 128, 64, 3, 1, 257),
+])
+def test_layer_forward_fp32_vs_oracle(kind, n, d, bo, scale, layers, b):
+    torch.manual_seed(1000 + n + d + layers)
+    if kind == "pairwise":
+        m = gb.MS_HGNN_oridinary(16, d, 64, bo, batch_norm=0, nmp_layers=layers)
+        e, t = n * n, 6
+    else:
+        m = gb.MS_HGNN_hyper(d, d, 64, bo, batch_norm=0, nmp_layers=layers, scale=scale)
+        e, t = (1 if scale == n else n), 10
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(b)
+    h = torch.randn(b, n, d, generator=gen)
+    noise = [torch.rand(b, e, t, generator=gen) for _ in range(layers)]
+    m = m.to(DEV)
+    m.workspace_limit_bytes = 64 << 20          # force batch chunking
+    with torch.no_grad():
+        if kind == "pairwise":
+            ref_node, ref_fac = O.forward_pairwise(sd, h, noise, nmp_layers=layers)
+            node, fac = m(h.to(DEV), noise=noise)
+        else:
+            corr = O.feature_correlation(h)
+            ref_node, ref_fac, ref_h = O.forward_hyper(sd, h, corr, scale, noise, nmp_layers=layers)
+            node, fac, hm = m(h.to(DEV), corr.to(DEV), noise=noise)
+            assert torch.equal(hm.cpu(), ref_h)
+    assert_close(fac, ref_fac, FP32_REL, "factors")
+    assert_close(node, ref_node, FP32_REL, "node_feat")
+
+
+# ---- RNG contracts ------------------------------------------------------------------
+def test_cpu_compat_rng_consumes_reference_stream():
+    g = load_golden("l2_pairwise")
+    m = build_layer(g).to(DEV).set_rng("cpu-compat")
+    h = torch.from_numpy(g["h"]).to(DEV)
+    torch.manual_seed(4242)
+    node, fac = m(h)
+    torch.manual_seed(4242)
+    noise = [torch.rand(s) for s in O.noise_shapes(g["B"], g["N"], True, 0, g["L"])]
+    after = torch.rand(1)
+    node2, fac2 = m(h, noise=noise)
+    assert torch.equal(node, node2) and torch.equal(fac, fac2)
+    torch.manual_seed(4242)
+    m(h)
+    assert torch.equal(torch.rand(1), after)     # exactly L draws of (B,E,T) were consumed
+
+
+def test_philox_statistics_and_sharding_invariance():
+    g = load_golden("nba_hyper5")
+    m = build_layer(g).to(DEV)
+    gen = torch.Generator().manual_seed(5)
+    h = torch.randn(4096, 11, 64, generator=gen).to(DEV)
+    corr = O.feature_correlation(h.cpu()).to(DEV)
+    m.set_rng("philox", seed=77)
+    node, fac, _ = m(h, corr)
+    m.set_rng("philox", seed=77)
+    node_b, fac_b, _ = m(h, corr)
+    assert torch.equal(node, node_b) and torch.equal(fac, fac_b)     # deterministic
+    m.set_rng("philox", seed=78)
+    assert not torch.equal(m(h, corr)[1], fac)                        # seed matters
+    # T8: the same global batch processed as 1, 2 or 4 shards gives bit-identical scenes
+    for shards in (2, 4):
+        parts_n, parts_f = [], []
+        step = 4096 // shards
+        for r in range(shards):
+            m.set_rng("philox", seed=77, scene_offset=r * step)
+            a, f, _ = m(h[r * step:(r + 1) * step], corr[r * step:(r + 1) * step])
+            parts_n.append(a); parts_f.append(f)
+        assert torch.equal(torch.cat(parts_n), node) and torch.equal(torch.cat(parts_f), fac)
+    # the implied uniforms are uniform: recover the categorical's entropy range and row sums
+    assert torch.allclose(fac.sum(-1), torch.ones_like(fac[..., 0]), atol=1e-5)
+    # successive calls draw fresh noise
+    m.set_rng("philox", seed=77)
+    f1 = m(h, corr)[1]
+    f2 = m(h, corr)[1]
+    assert torch.equal(f1, fac) and not torch.equal(f2, f1)
+
+
+def test_philox_matches_distribution_of_reference_noise():
+    """Mean categorical under device Philox noise agrees with the mean under torch.rand noise."""
+    g = load_golden("nba_pairwise")
+    m = build_layer(g).to(DEV)
+    gen = torch.Generator().manual_seed(9)
+    h = torch.randn(2048, 11, 64, generator=gen).to(DEV)
+    m.set_rng("philox", seed=3)
+    f_dev = m(h)[1].mean(dim=(0, 1))
+    m.set_rng("cpu-compat")
+    torch.manual_seed(3)
+    f_cpu = m(h)[1].mean(dim=(0, 1))
+    assert (f_dev - f_cpu).abs().max().item() < 5e-3
+
+
+# ---- full-size properties (BASELINE.json shapes) ----------------------------------------
+def test_full_size_nba_properties():
+    b, n, d = 65536, 11, 64
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(b, n, d, generator=gen).to(DEV)
+    (hs, full), corr = gb.corr_topk_h(x, [5, 11], concat=True, return_corr=True)
+    assert full.shape == (b, 12, 11)
+    assert hs[0].sum(2).eq(5).all() and hs[1].eq(1).all()
+    assert torch.diagonal(hs[0], dim1=1, dim2=2).eq(1).all()          # corr[i,i] is the row max
+    assert (corr - corr.transpose(1, 2)).abs().max().item() == 0.0    # Gram symmetry is exact
+    assert torch.equal(gb.topk_h(corr, 5), hs[0].contiguous())        # idempotent: topk(own corr)
+    torch.manual_seed(1234)
+    pair = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=1).to(DEV).set_rng("philox", 0)
+    hyp = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=5).to(DEV).set_rng("philox", 0)
+    node, fac = pair(x)
+    assert node.shape == (b, n, 64) and fac.shape == (b, 121, 6)
+    assert torch.isfinite(node).all() and torch.allclose(fac.sum(-1), torch.ones_like(fac[..., 0]), atol=1e-5)
+    node_h, fac_h, hm = hyp(x, corr, H=hs[0])
+    assert torch.isfinite(node_h).all() and torch.allclose(fac_h.sum(-1), torch.ones_like(fac_h[..., 0]), atol=1e-5)
+    # permutation equivariance over scenes: reversing the batch reverses the outputs (injected noise)
+    sl = slice(0, 512)
+    u = torch.rand(512, 121, 6, generator=gen).to(DEV)
+    a, fa = pair(x[sl], noise=[u])
+    bwd, fb = pair(x[sl].flip(0).contiguous(), noise=[u.flip(0).contiguous()])
+    assert torch.equal(a, bwd.flip(0)) and torch.equal(fa, fb.flip(0))
+
+
+def test_inputs_not_mutated_and_fresh_outputs():
+    g = load_golden("fish8_hyper3")
+    m = build_layer(g).to(DEV)
+    h = torch.from_numpy(g["h"]).to(DEV)
+    corr = torch.from_numpy(g["corr"]).to(DEV)
+    h0, c0 = h.clone(), corr.clone()
+    noise = [torch.from_numpy(u).to(DEV) for u in g["noise"]]
+    a1, f1, hm1 = m(h, corr, noise=noise)
+    a2, f2, hm2 = m(h, corr, noise=noise)
+    assert torch.equal(h, h0) and torch.equal(corr, c0)
+    assert a1.data_ptr() != a2.data_ptr() and torch.equal(a1, a2) and torch.equal(f1, f2)
+    assert not hm1.requires_grad
+    with pytest.raises(RuntimeError, match="Float"):
+        m(h.double(), corr.double())
