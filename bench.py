@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — MS-HGNN forward scenes/s on the NBA-shaped synthetic workload
+(BASELINE.json configs[2]: 65,536 scenes x 11 agents, h_dim 64, scales {5,11}).
+
+One "step" = one pass of the hot path over one batch of synthetic scenes:
+fused corr + top-k + H for both scales, the pairwise layer and both hyper
+layers (what PastEncoder.forward runs, model/GroupNet_nba.py:284-309).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU, scenes sharded by batch, no
+data-path collective: weak scaling, 65,536 scenes per GPU).  Rank 0 prints ONE
+JSON line.  `--impl reference` times the reference's CPU algorithm (the oracle
+port, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SCENES, AGENTS, HDIM, SCALES = 65536, 11, 64, (5, 11)
+WORKLOAD = "nba_synth_B65536_N11_D64_scales5-11"
+METRIC = "ms_hgnn_forward_scenes_per_sec"
+
+
+# ---------------------------------------------------------------------------
+# algorithmic work per launch
+# ---------------------------------------------------------------------------
+def layer_shapes(n):
+    """(name, E, T, pairwise) of the three layers of the workload."""
+    out = [("pairwise", n * n, 6, True)]
+    for s in SCALES:
+        out.append((f"hyper{s}", 1 if s == n else n, 10, False))
+    return out
+
+
+def kernel_work(b, n, d):
+    """{kernel: (flops, bytes, bound)} summed over the launches of ONE step."""
+    w = {}
+
+    def add(k, flops, byts, bound):
+        f0, b0, _ = w.get(k, (0, 0, bound))
+        w[k] = (f0 + flops, b0 + byts, bound)
+
+    # fused corr + top-k + H: read x once, write every H_s (SURVEY §8d row a)
+    hbytes = sum((1 if s == n else n) * n * 4 for s in SCALES)
+    add("corr_topk_h", 2 * b * n * n * d, b * (n * d * 4 + hbytes), "hbm")
+    for name, e, t, pair in layer_shapes(n):
+        rows_n, rows_e = b * n, b * e
+        node_macs = d * 256 + 256 * 64 + 64 * 64 + (d * t * 128 if pair else 0)
+        add("node_pre", 2 * rows_n * node_macs,
+            rows_n * 4 * (d + 128 + (t * 128 if pair else 0)), "tensor")
+        if pair:
+            add("node2edge_pair", rows_e * (2 * 64 * 2 + 4 * 64), (rows_n * 128 + rows_e * 64) * 4, "hbm")
+        else:
+            add("node2edge_hyper", rows_e * n * (64 + 2 * 64 + 2 * d),
+                (rows_n * (128 + d) + rows_e * (n + 64 + d)) * 4, "hbm")
+        mlp_macs = 64 * 128 + 128 * 64 + 64 * 256 + 256 * (t + 1)
+        add("edge_mlp", 2 * rows_e * mlp_macs, rows_e * (64 + 2 * t) * 4, "tensor")
+        if pair:
+            add("edge2node_pair", rows_n * n * t * 128 * 4, (rows_n * (2 * t * 128 + 16) + rows_e * t) * 4, "hbm")
+            post_macs = t * 128 * d + 2 * d * 128 + 128 * d
+            add("node_post", 2 * rows_n * post_macs, rows_n * (t * 128 + 16 + 2 * d) * 4, "tensor")
+        else:
+            add("edge_agg", 2 * rows_e * t * 2 * d * 128, rows_e * (2 * d + t) * 4, "tensor")
+            add("edge2node_hyper", 2 * rows_n * e * d, (rows_e * (d + n) + rows_n * d) * 4, "hbm")
+            add("node_post", 2 * rows_n * (2 * d * 128 + 128 * d), rows_n * 3 * d * 4, "tensor")
+    return w
+
+
+# ---------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample DURING the timed region)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
+                              ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm (test infrastructure used
+# here ONLY as the thing being timed on the host, never on the product path)
+# ---------------------------------------------------------------------------
+def build_cpu_arm():
+    from oracle import ms_hgnn_oracle as O
+    import groupnet_b200 as gb
+    torch.manual_seed(1234)
+    m = gb.MultiScaleInteraction(HDIM, SCALES)
+    sds = [{k: v.detach().clone() for k, v in l.state_dict().items()} for l in m.layers()]
+
+    def forward(x):
+        with torch.no_grad():
+            corr = O.feature_correlation(x)
+            b, n, _ = x.shape
+            O.forward_pairwise(sds[0], x, [torch.rand(b, n * n, 6)])
+            for sd, s in zip(sds[1:], SCALES):
+                e = 1 if s == n else n
+                O.forward_hyper(sd, x, corr, s, [torch.rand(b, e, 10)])
+    return forward
+
+
+def time_cpu(forward, scenes, chunk=256):
+    x = torch.randn(scenes, AGENTS, HDIM, generator=torch.Generator().manual_seed(0))
+    t0 = time.perf_counter()
+    for b0 in range(0, scenes, chunk):
+        forward(x[b0:b0 + chunk])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline(budget_s=12.0):
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    fwd = build_cpu_arm()
+    time_cpu(fwd, 256)                                  # warm-up
+    done, spent = 0, 0.0
+    while spent < budget_s and done < 16384:
+        spent += time_cpu(fwd, 512)
+        done += 512
+    return {"value": done / spent, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} of {SCENES} scenes in chunks of 256 (oracle port of model/MS_HGNN_batch.py, "
+                      f"fp32, torch CPU, as-written algorithm), {spent:.1f} s"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    fwd = build_cpu_arm()
+    sample = 1024
+    for _ in range(max(args.warmup, 1)):
+        time_cpu(fwd, 256)
+    t = [time_cpu(fwd, sample) for _ in range(args.steps)]
+    per_step = sum(t) / len(t)
+    val = sample / per_step
+    desc = {"value": val, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample} scenes per step in chunks of 256 (oracle port, fp32 torch CPU)"}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "scenes/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample_scenes_per_step": sample,
+                                         "agents": AGENTS, "h_dim": HDIM, "scales": list(SCALES)},
+        "cpu_baseline": desc,
+        "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=SCENES, help="scenes per GPU (default: BASELINE config)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import groupnet_b200 as gb
+    from groupnet_b200 import _lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    b, n, d = args.scenes, AGENTS, HDIM
+
+    torch.manual_seed(1234)                         # weights
+    model = gb.MultiScaleInteraction(d, SCALES).to(dev).eval().set_precision(args.precision)
+    model.set_rng("philox", seed=0, scene_offset=rank * b)
+    for l in model.layers():
+        l.workspace_limit_bytes = 9 << 30          # one launch per kernel for the whole shard
+    x_host = torch.randn(b, n, d, generator=torch.Generator().manual_seed(rank)).pin_memory()
+    x = x_host.to(dev)
+    feat = torch.empty(b, n, model.feature_width(), device=dev)
+    hcat = torch.empty(b, model.incidence_rows(n), n, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(x, out_feature=feat, out_H=hcat)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            e0.record()
+            for _ in range(args.steps):
+                model(x, out_feature=feat, out_H=hcat)
+            e1.record()
+            barrier()
+        ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        value = world * b / (ms_step * 1e-3)
+
+        # per-kernel durations, CUDA events on the launch stream (library profiling hook)
+        _lib.profile_enable(True)
+        prof_steps = 2
+        for _ in range(prof_steps):
+            model(x, out_feature=feat, out_H=hcat)
+        torch.cuda.synchronize(dev)
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+        launches_per_step = sum(c for _, c in prof.values()) // prof_steps
+
+        # end to end through the public host API: pinned host in, pinned host out
+        out_f = torch.empty(b, n, model.feature_width(), dtype=torch.float32).pin_memory()
+        out_h = torch.empty(b, model.incidence_rows(n), n, dtype=torch.float32).pin_memory()
+        for _ in range(2):
+            model.forward_host(x_host, out_f, out_h)
+        barrier()
+        e0.record()
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(e2e_steps):
+            model.forward_host(x_host, out_f, out_h)
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured"
+    except Exception:
+        peak_src = "fallback"
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    work = kernel_work(b, n, d)
+    kernels = {}
+    for k, (tot_ms, cnt) in prof.items():
+        per_step_ms = tot_ms / prof_steps
+        fl, by, bound = work.get(k, (0, 0, "hbm"))
+        kernels[k] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": cnt // prof_steps,
+                      "bound": bound,
+                      "tflops": round(fl / (per_step_ms * 1e-3) / 1e12, 3) if per_step_ms > 0 else None,
+                      "gbs": round(by / (per_step_ms * 1e-3) / 1e9, 1) if per_step_ms > 0 else None}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+    kd = kernels[dom]
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    if kd["bound"] == "tensor":
+        ach, pk, unit = kd["tflops"], tensor_peak, "TFLOP/s"
+    else:
+        ach, pk, unit = kd["gbs"], hbm_peak, "GB/s"
+    roofline = {"kernel": dom, "bound": kd["bound"], "achieved": ach, "peak": pk, "unit": unit,
+                "frac": round(ach / pk, 5), "traffic": traffic, "peak_source": peak_src,
+                "share_of_step": round(kd["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()), 3)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline()
+
+    h2d = b * n * d * 4
+    d2h = out_f.numel() * 4 + out_h.numel() * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scenes_per_gpu": b, "agents": n, "h_dim": d, "scales": list(SCALES),
+                   "noise": "philox on device (distribution-equal to the reference's torch.rand)",
+                   "weights": "torch.manual_seed(1234) default init",
+                   "l2": "no flush: x (184 MB) and the per-step scratch (GBs) exceed the 126 MB L2",
+                   "sharding": "batch-sharded, no collective on the forward path"},
+        "clocks": clocks.summary(),
+        "e2e": {"value": world * b / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "MultiScaleInteraction.forward_host (pinned host in/out, 3-stream chunk pipeline)"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
+        "kernels": kernels,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

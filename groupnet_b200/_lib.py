@@ -29,6 +29,8 @@ EXPORTS = (
     "gn_stage_workspace_bytes",
     "gn_stage_fwd",
     "gn_stage_launch_count",
+    "gn_profile_enable",
+    "gn_profile_collect",
 )
 
 
@@ -55,6 +57,7 @@ class StageCfg(C.Structure):
         ("B", C.c_int32), ("N", C.c_int32), ("D", C.c_int32), ("Dout", C.c_int32),
         ("E", C.c_int32), ("T", C.c_int32), ("pairwise", C.c_int32), ("precision", C.c_int32),
         ("noise_mode", C.c_int32), ("stage_index", C.c_int32),
+        ("out_ld", C.c_int32), ("h_stride", C.c_int32),
         ("seed", C.c_uint64), ("scene_offset", C.c_int64),
     ]
 
@@ -100,6 +103,10 @@ def load() -> C.CDLL:
         lib.gn_stage_fwd.argtypes = [
             C.POINTER(StageCfg), C.POINTER(StageWeights), C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.gn_profile_enable.restype = None
+        lib.gn_profile_enable.argtypes = [C.c_int]
+        lib.gn_profile_collect.restype = C.c_int
+        lib.gn_profile_collect.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
         got = lib.gn_abi_version()
         if got != ABI_VERSION:
             raise GroupNetLibraryError(f"{LIB_PATH} has ABI version {got}, expected {ABI_VERSION}")
@@ -118,3 +125,18 @@ def check(code: int, what: str) -> None:
     if code < 0:
         raise ValueError(f"{what}: {msg} (gn_error {code})")
     raise RuntimeError(f"{what}: CUDA error {code}: {msg}")
+
+
+def profile_enable(on: bool) -> None:
+    load().gn_profile_enable(1 if on else 0)
+
+
+def profile_collect() -> dict:
+    """{kernel name: (total_ms, launches)} since the last collect (synchronises)."""
+    lib = load()
+    names = C.create_string_buffer(4096)
+    ms = (C.c_float * 64)()
+    cnt = (C.c_int * 64)()
+    n = lib.gn_profile_collect(names, 4096, ms, cnt, 64)
+    keys = [k for k in names.value.decode().split(";") if k]
+    return {keys[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}

@@ -8,6 +8,73 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
 size_t stage_workspace_bytes_simt(const gn_stage_cfg* c);
 }  // namespace gn
 
+// ---------------------------------------------------------------------------
+// profiling hook: brackets every kernel launch with CUDA events on the launch
+// stream while enabled; bench.py uses it for the live per-kernel roofline.
+// ---------------------------------------------------------------------------
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+namespace gn {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(const char* name, cudaStream_t st) : name_(name), st_(st), rec_(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec* r = new ProfRec{name, nullptr, nullptr};
+  cudaEventCreate(&r->a);
+  cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, st);
+  rec_ = r;
+}
+ProfScope::~ProfScope() {
+  if (!rec_) return;
+  ProfRec* r = static_cast<ProfRec*>(rec_);
+  cudaEventRecord(r->b, st_);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(*r);
+  delete r;
+}
+}  // namespace gn
+
+extern "C" void gn_profile_enable(int on) { gn::g_prof_on.store(on ? 1 : 0); }
+
+extern "C" int gn_profile_collect(char* names, int names_len, float* total_ms, int* counts, int max_entries) {
+  std::lock_guard<std::mutex> lk(gn::g_prof_mu);
+  std::vector<std::string> keys;
+  std::vector<float> ms;
+  std::vector<int> cnt;
+  for (auto& r : gn::g_prof) {
+    cudaEventSynchronize(r.b);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+    size_t i = 0;
+    for (; i < keys.size(); ++i) if (keys[i] == r.name) break;
+    if (i == keys.size()) { keys.push_back(r.name); ms.push_back(0.f); cnt.push_back(0); }
+    ms[i] += t; cnt[i] += 1;
+  }
+  gn::g_prof.clear();
+  int n = static_cast<int>(keys.size()) < max_entries ? static_cast<int>(keys.size()) : max_entries;
+  std::string joined;
+  for (int i = 0; i < n; ++i) {
+    if (total_ms) total_ms[i] = ms[i];
+    if (counts) counts[i] = cnt[i];
+    joined += keys[i];
+    joined += ';';
+  }
+  if (names && names_len > 0) {
+    std::strncpy(names, joined.c_str(), names_len - 1);
+    names[names_len - 1] = 0;
+  }
+  return n;
+}
+
 extern "C" int gn_abi_version(void) { return GN_ABI_VERSION; }
 
 extern "C" const char* gn_error_string(int code) {

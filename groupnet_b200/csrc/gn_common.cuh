@@ -79,6 +79,16 @@ static inline size_t round_up_sz(size_t v, size_t m) { return (v + m - 1) / m * 
 
 }  // namespace gn
 
+namespace gn {
+// Optional per-kernel CUDA-event timing (gn_profile_enable / gn_profile_collect).
+// Disabled by default: the constructor is then a single relaxed load.
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t st);
+  ~ProfScope();
+  const char* name_; cudaStream_t st_; void* rec_;
+};
+}  // namespace gn
+
 #define GN_LAUNCH_CHECK()                                  \
   do {                                                     \
     cudaError_t e__ = cudaGetLastError();                  \

@@ -183,7 +183,7 @@ node2edge_pair_kernel(const float* __restrict__ xprime, const float* __restrict_
 __global__ void __launch_bounds__(GN_THREADS)
 node2edge_hyper_kernel(const float* __restrict__ xprime, const float* __restrict__ pq,
                        const float* __restrict__ h, const float* __restrict__ H,
-                       int B, int N, int E, int D, gn_stage_weights W,
+                       int B, int N, int E, int D, long long hstride, gn_stage_weights W,
                        float* __restrict__ edges, float* __restrict__ eo) {
   extern __shared__ __align__(16) float smem[];
   const int ldh = D + 4, ldn = N + 1;
@@ -213,7 +213,7 @@ node2edge_hyper_kernel(const float* __restrict__ xprime, const float* __restrict
     }
     for (int i = tid; i < E * N; i += GN_THREADS) {
       int e = i / N, n = i - e * N;
-      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b) * E * N + i);
+      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b) * hstride + i);
     }
     __syncthreads();
     // pe[e][k] = sum_n H[e,n] q_n[k] + b0[k]
@@ -541,7 +541,7 @@ edge2node_pair_kernel(const float* __restrict__ P, const float* __restrict__ edg
 // ===========================================================================
 __global__ void __launch_bounds__(GN_THREADS)
 edge2node_hyper_kernel(const float* __restrict__ ef, const float* __restrict__ H,
-                       int B, int N, int E, int D, float* __restrict__ agg) {
+                       int B, int N, int E, int D, long long hstride, float* __restrict__ agg) {
   extern __shared__ __align__(16) float smem[];
   const int ldn = N + 1, d4 = D >> 2;
   float* Hs = smem;                                   // [E][N+1]
@@ -550,7 +550,7 @@ edge2node_hyper_kernel(const float* __restrict__ ef, const float* __restrict__ H
     __syncthreads();
     for (int i = tid; i < E * N; i += GN_THREADS) {
       int e = i / N, n = i - e * N;
-      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b) * E * N + i);
+      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b) * hstride + i);
     }
     __syncthreads();
     for (int i = tid; i < N * d4; i += GN_THREADS) {
@@ -581,7 +581,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 node_post_kernel(const float* __restrict__ h, const float* __restrict__ aggin,
                  const float* __restrict__ G, const float* __restrict__ S,
                  int R, int N, int D, int Dc, int K2p, int T, int Dout, int Doutc, int pairwise,
-                 gn_stage_weights W, float* __restrict__ out) {
+                 gn_stage_weights W, float* __restrict__ out, int ld_out) {
   constexpr int LD = TM + 4, RM = TM / 16, RN = TN / 16;
   extern __shared__ __align__(16) float smem[];
   float* incT = smem;
@@ -646,7 +646,7 @@ node_post_kernel(const float* __restrict__ h, const float* __restrict__ aggin,
       acc_foreach<TM, 64>(acc, [&](int r, int cc, float& v) {
         int col = c0 + cc;
         if (r < nrows && col < Dout)
-          out[static_cast<size_t>(row0 + r) * Dout + col] = v + __ldg(W.post_b1 + col);
+          out[static_cast<size_t>(row0 + r) * ld_out + col] = v + __ldg(W.post_b1 + col);
       });
     }
     __syncthreads();
@@ -740,6 +740,8 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
   const int B = c->B, N = c->N, D = c->D, E = c->E, T = c->T;
   const int R = B * N;
   const long long RE = static_cast<long long>(B) * E;
+  const long long hstride = c->h_stride > 0 ? c->h_stride : static_cast<long long>(E) * N;
+  if (hstride < static_cast<long long>(E) * N) return GN_E_SHAPE;
 
   // k1
   {
@@ -748,7 +750,8 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
     auto kern = node_pre_kernel<TM>;
     GN_TRY(set_smem(kern, smem));
     int grid = grid_for((R + TM - 1) / TM, smem);
-    kern<<<grid, GN_THREADS, smem, st>>>(h, R, D, p.Dp, T, c->pairwise, *w, xprime, pq, P);
+    { ProfScope ps__("node_pre", st);
+      kern<<<grid, GN_THREADS, smem, st>>>(h, R, D, p.Dp, T, c->pairwise, *w, xprime, pq, P); }
     GN_LAUNCH_CHECK();
   }
   // k2
@@ -758,7 +761,8 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
     auto kern = node2edge_pair_kernel;
     GN_TRY(set_smem(kern, smem));
     long long work = static_cast<long long>(B) * ((E + N2E_EC - 1) / N2E_EC);
-    kern<<<grid_for(work, smem), GN_THREADS, smem, st>>>(xprime, pq, B, N, *w, edges);
+    { ProfScope ps__("node2edge_pair", st);
+      kern<<<grid_for(work, smem), GN_THREADS, smem, st>>>(xprime, pq, B, N, *w, edges); }
     GN_LAUNCH_CHECK();
   } else {
     if (!H) return GN_E_NULL;
@@ -767,7 +771,8 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
     size_t smem = fl * 4;
     auto kern = node2edge_hyper_kernel;
     GN_TRY(set_smem(kern, smem));
-    kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(xprime, pq, h, H, B, N, E, D, *w, edges, eo);
+    { ProfScope ps__("node2edge_hyper", st);
+      kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(xprime, pq, h, H, B, N, E, D, hstride, *w, edges, eo); }
     GN_LAUNCH_CHECK();
   }
   // k3
@@ -778,9 +783,10 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
                    TM * 17 + TM * 16) * 4;
     auto kern = edge_mlp_kernel<TM>;
     GN_TRY(set_smem(kern, smem));
-    kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(
-        edges, RE, T, E, *w, U, c->noise_mode, c->seed, c->scene_offset, c->stage_index,
-        dist_out, efeat);
+    { ProfScope ps__("edge_mlp", st);
+      kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(
+          edges, RE, T, E, *w, U, c->noise_mode, c->seed, c->scene_offset, c->stage_index,
+          dist_out, efeat); }
     GN_LAUNCH_CHECK();
   }
   // k4 / k5
@@ -789,7 +795,8 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
                    static_cast<size_t>(N) * (N + 1)) * 4;
     auto kern = edge2node_pair_kernel;
     GN_TRY(set_smem(kern, smem));
-    kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(P, efeat, B, N, T, *w, G, S);
+    { ProfScope ps__("edge2node_pair", st);
+      kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(P, efeat, B, N, T, *w, G, S); }
     GN_LAUNCH_CHECK();
   } else {
     if (D <= 64) {
@@ -797,44 +804,53 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
       size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
       auto kern = edge_agg_kernel<TM, 64, 1>;
       GN_TRY(set_smem(kern, smem));
-      kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef);
+      { ProfScope ps__("edge_agg", st);
+        kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef); }
     } else if (D <= 128) {
       constexpr int TM = 128, LD = TM + 4;
       size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
       auto kern = edge_agg_kernel<TM, 128, 1>;
       GN_TRY(set_smem(kern, smem));
-      kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef);
+      { ProfScope ps__("edge_agg", st);
+        kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef); }
     } else {
       constexpr int TM = 64, LD = TM + 4;
       size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
       auto kern = edge_agg_kernel<TM, 128, 2>;
       GN_TRY(set_smem(kern, smem));
-      kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef);
+      { ProfScope ps__("edge_agg", st);
+        kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef); }
     }
     GN_LAUNCH_CHECK();
     size_t smem = static_cast<size_t>(E) * (N + 1) * 4;
     auto kern = edge2node_hyper_kernel;
     GN_TRY(set_smem(kern, smem));
-    kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(ef, H, B, N, E, D, agg);
+    { ProfScope ps__("edge2node_hyper", st);
+      kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(ef, H, B, N, E, D, hstride, agg); }
     GN_LAUNCH_CHECK();
   }
   // k6
   {
     constexpr int TM = 64, LD = TM + 4;
+    const int ld_out = c->out_ld > 0 ? c->out_ld : c->Dout;
+    if (ld_out < c->Dout) return GN_E_SHAPE;
     size_t smem = (static_cast<size_t>(p.K2p + 128 + 64) * LD + 2 * KC * 128 + TM * 16) * 4;
     int grid = grid_for((R + TM - 1) / TM, smem);
     if (D <= 64) {
       auto kern = node_post_kernel<TM, 64, 1>;
       GN_TRY(set_smem(kern, smem));
-      kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out);
+      { ProfScope ps__("node_post", st);
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out); }
     } else if (D <= 128) {
       auto kern = node_post_kernel<TM, 128, 1>;
       GN_TRY(set_smem(kern, smem));
-      kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out);
+      { ProfScope ps__("node_post", st);
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out); }
     } else {
       auto kern = node_post_kernel<TM, 128, 2>;
       GN_TRY(set_smem(kern, smem));
-      kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out);
+      { ProfScope ps__("node_post", st);
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out); }
     }
     GN_LAUNCH_CHECK();
   }

@@ -299,7 +299,8 @@ static int launch_topk(const float* x, const float* corr, int B, int N, int D,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          static_cast<int>(smem));                           \
     if (e != cudaSuccess) return static_cast<int>(e);                                       \
-    kern<<<grid, GN_THREADS, smem, stream>>>(x, corr, B, N, D, SG, a, corr_out);            \
+    { ProfScope ps__(FROM_CORR ? "topk_h" : "corr_topk_h", stream);                         \
+      kern<<<grid, GN_THREADS, smem, stream>>>(x, corr, B, N, D, SG, a, corr_out); }        \
   } break;
   switch (P) {
     GN_TOPK_CASE(1) GN_TOPK_CASE(2) GN_TOPK_CASE(4) GN_TOPK_CASE(8)

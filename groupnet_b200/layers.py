@@ -161,13 +161,15 @@ class _MessagePassingLayer(nn.Module):
             return [torch.rand(batch, e, t).float().to(device, non_blocking=True) for _ in range(n_stage)]
         return None
 
-    def _run(self, h_states: torch.Tensor, inc: Optional[torch.Tensor], e: int, noise):
+    def _run(self, h_states: torch.Tensor, inc: Optional[torch.Tensor], e: int, noise,
+             node_out: Optional[torch.Tensor] = None, dist_out: Optional[torch.Tensor] = None,
+             want_dist: bool = True):
+        """Chain the L stages through gn_stage_fwd.  `node_out` may be a view whose
+        rows are further apart than bottleneck_dim (a slice of a concatenated
+        feature tensor); it must have unit stride in the last dim."""
         ops._require_cuda_f32(h_states, "h_states")
         if h_states.dim() != 3:
             raise ValueError("h_states must be (B, N, h_dim)")
-        if torch.is_grad_enabled() and (h_states.requires_grad or any(p.requires_grad for p in self.parameters())) \
-                and getattr(self, "_autograd", None) is not None:
-            return self._autograd(h_states, inc, e, noise)
         h = h_states.detach().contiguous()
         b, n, d = h.shape
         if d != self.h_dim:
@@ -182,9 +184,20 @@ class _MessagePassingLayer(nn.Module):
             self._philox_calls += 1
         else:
             seed = 0
-        node_out = torch.empty(b, n, stages[-1].dout, dtype=torch.float32, device=dev)
-        dist = torch.empty(b, e, t, dtype=torch.float32, device=dev)
+        dout = stages[-1].dout
+        if node_out is None:
+            node_out = torch.empty(b, n, dout, dtype=torch.float32, device=dev)
+        else:
+            ops._require_cuda_f32(node_out, "node_out")
+            if tuple(node_out.shape) != (b, n, dout) or node_out.stride(2) != 1 \
+                    or node_out.stride(0) != n * node_out.stride(1):
+                raise ValueError("node_out must be (B,N,bottleneck_dim) with uniform row stride")
+        out_ld = node_out.stride(1) if b * n > 1 else dout
+        if dist_out is None and want_dist:
+            dist_out = torch.empty(b, e, t, dtype=torch.float32, device=dev)
         mids = [torch.empty(b, n, stages[s].dout, dtype=torch.float32, device=dev) for s in range(n_stage - 1)]
+        if b == 0:
+            return node_out, dist_out
 
         cfg = _lib.StageCfg()
         cfg.N, cfg.D, cfg.E, cfg.T = n, d, e, t
@@ -195,21 +208,24 @@ class _MessagePassingLayer(nn.Module):
         # bound the scratch: split the batch so one call's workspace stays under the limit
         cfg.B, cfg.Dout, cfg.stage_index, cfg.scene_offset = 1, max(s.dout for s in stages), 0, 0
         per_scene = max(ops.stage_workspace_bytes(cfg), 1)
-        chunk = max(1, min(b, self.workspace_limit_bytes // per_scene)) if b > 0 else 1
+        chunk = max(1, min(b, self.workspace_limit_bytes // per_scene))
         for b0 in range(0, b, chunk):
             b1 = min(b, b0 + chunk)
             cur = h[b0:b1]
             for s in range(n_stage):
+                last = s == n_stage - 1
                 cfg.B, cfg.Dout, cfg.stage_index = b1 - b0, stages[s].dout, s
+                cfg.out_ld = out_ld if last else 0
+                cfg.h_stride = 0 if inc is None else inc.stride(0)
                 cfg.scene_offset = self.scene_offset + b0
                 ws = self._ws.get(ops.stage_workspace_bytes(cfg), dev)
-                dst = node_out[b0:b1] if s == n_stage - 1 else mids[s][b0:b1]
+                dst = node_out[b0:b1] if last else mids[s][b0:b1]
                 ops.stage_forward(cfg, stages[s], cur,
                                   None if inc is None else inc[b0:b1],
                                   None if us is None else us[s][b0:b1],
-                                  dst, dist[b0:b1] if s == 0 else None, ws)
+                                  dst, dist_out[b0:b1] if (s == 0 and dist_out is not None) else None, ws)
                 cur = dst
-        return node_out, dist
+        return node_out, dist_out
 
     def launches_per_forward(self, batch: int, n: int, e: int) -> int:
         """Kernel launches one forward issues (for bench.py's gpu_launches)."""
@@ -245,9 +261,9 @@ class MS_HGNN_oridinary(_MessagePassingLayer):
         self.edge_types = 6
         self._build_tree(h_dim, bottleneck_dim, nmp_layers)
 
-    def forward(self, h_states, *, noise=None):
+    def forward(self, h_states, *, noise=None, out=None, want_factors=True):
         n = h_states.shape[1]
-        return self._run(h_states, None, n * n, noise)
+        return self._run(h_states, None, n * n, noise, node_out=out, want_dist=want_factors)
 
 
 class MS_HGNN_hyper(_MessagePassingLayer):
@@ -286,13 +302,15 @@ class MS_HGNN_hyper(_MessagePassingLayer):
         ops._require_cuda_f32(feat, "feat")
         return ops.topk_h(feat_corr, scale_factor)
 
-    def forward(self, h_states, corr=None, *, noise=None, H=None):
+    def forward(self, h_states, corr=None, *, noise=None, H=None, out=None, want_factors=True):
         if H is None:
             if corr is None:
                 raise TypeError("forward() missing 1 required positional argument: 'corr'")
             H = self.init_adj_attention(h_states, corr, scale_factor=self.scale)
         else:
             ops._require_cuda_f32(H, "H")
-        inc = H if H.is_contiguous() else H.contiguous()
-        node_feat, factor = self._run(h_states, inc, inc.shape[1], noise)
+        # rows of a concatenated (B, sum E, N) incidence are accepted as they are
+        ok = H.dim() == 3 and H.stride(2) == 1 and H.stride(1) == H.shape[2]
+        inc = H if ok else H.contiguous()
+        node_feat, factor = self._run(h_states, inc, inc.shape[1], noise, node_out=out, want_dist=want_factors)
         return node_feat, factor, H

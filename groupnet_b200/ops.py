@@ -62,6 +62,9 @@ def corr_topk_h(x: torch.Tensor, scales: Sequence[int], *, concat: bool = False,
             outs = [torch.empty(b, r, n, dtype=torch.float32, device=x.device) for r in rows]
             strides = [r * n for r in rows]
         corr = torch.empty(b, n, n, dtype=torch.float32, device=x.device) if return_corr else None
+        if b == 0:          # empty batch: nothing to launch (empty tensors have NULL data pointers)
+            result = (outs, full) if concat else outs
+            return (result, corr) if return_corr else result
         sc = (C.c_int32 * len(scales))(*scales)
         hp = (C.c_void_p * len(scales))(*[o.data_ptr() for o in outs])
         st = (C.c_int64 * len(scales))(*strides)
@@ -71,6 +74,36 @@ def corr_topk_h(x: torch.Tensor, scales: Sequence[int], *, concat: bool = False,
     _lib.check(rc, "gn_corr_topk_h")
     result = (outs, full) if concat else outs
     return (result, corr) if return_corr else result
+
+
+def corr_topk_h_into(x: torch.Tensor, scales: Sequence[int], out_h: torch.Tensor) -> List[torch.Tensor]:
+    """Same kernel, writing every H_s into a caller-owned concatenated
+    (B, sum E_s, N) tensor; returns the per-scale views."""
+    _require_cuda_f32(x, "x")
+    _require_cuda_f32(out_h, "out_H")
+    lib = _lib.load()
+    b, n, d = x.shape
+    scales = [int(s) for s in scales]
+    for s in scales:
+        if s > n:
+            raise RuntimeError("selected index k out of range")
+    rows = [incidence_rows(n, s) for s in scales]
+    if tuple(out_h.shape) != (b, sum(rows), n) or not out_h.is_contiguous() or not x.is_contiguous():
+        raise ValueError("out_H must be a contiguous (B, sum E_s, N) tensor and x contiguous")
+    views, off = [], 0
+    for r in rows:
+        views.append(out_h[:, off:off + r, :])
+        off += r
+    if b == 0:
+        return views
+    with torch.cuda.device(x.device):
+        sc = (C.c_int32 * len(scales))(*scales)
+        hp = (C.c_void_p * len(scales))(*[v.data_ptr() for v in views])
+        st = (C.c_int64 * len(scales))(*([sum(rows) * n] * len(scales)))
+        rc = lib.gn_corr_topk_h(C.c_void_p(x.data_ptr()), b, n, d, sc, len(scales), hp, st,
+                                C.c_void_p(0), _stream_ptr(x.device))
+    _lib.check(rc, "gn_corr_topk_h")
+    return views
 
 
 def topk_h(corr: torch.Tensor, scale: int) -> torch.Tensor:
@@ -87,6 +120,8 @@ def topk_h(corr: torch.Tensor, scale: int) -> torch.Tensor:
     e = incidence_rows(n, scale)
     with torch.cuda.device(corr.device):
         h = torch.empty(b, e, n, dtype=torch.float32, device=corr.device)
+        if b == 0:
+            return h
         rc = lib.gn_topk_h(C.c_void_p(corr.data_ptr()), b, n, scale, C.c_void_p(h.data_ptr()),
                            e * n, _stream_ptr(corr.device))
     _lib.check(rc, "gn_topk_h")

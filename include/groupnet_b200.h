@@ -108,6 +108,10 @@ typedef struct gn_stage_cfg {
   int32_t precision;    /* enum gn_precision */
   int32_t noise_mode;   /* enum gn_noise_mode */
   int32_t stage_index;  /* 0..L-1, separates Philox streams of chained stages */
+  int32_t out_ld;       /* row stride (floats) of node_out; 0 = Dout.  Lets the stage write its slice of the
+                           concatenated feature tensor the encoders build (model/GroupNet_nba.py:301-309) */
+  int32_t h_stride;     /* floats between consecutive scenes of H; 0 = E*N.  Lets a hyper stage read its
+                           rows of the concatenated (B, sum E, N) incidence (model/GroupNet_nba.py:296,299) */
   uint64_t seed;        /* Philox key */
   int64_t scene_offset; /* global index of scene 0 of this call: results do not depend on sharding */
 } gn_stage_cfg;
@@ -148,7 +152,7 @@ size_t gn_stage_workspace_bytes(const gn_stage_cfg* cfg);
  *   h_in      (B,N,D)    node features entering the stage
  *   H         (B,E,N)    incidence (0/1 fp32) for hyper stages; ignored (may be NULL) when cfg->pairwise
  *   U         (B,E,T)    uniform draws when noise_mode == GN_NOISE_GIVEN, else may be NULL
- *   node_out  (B,N,Dout) output of the closing MLP (node_feat)
+ *   node_out  (B,N,Dout) output of the closing MLP (node_feat); rows cfg->out_ld floats apart when out_ld != 0
  *   dist_out  (B,E,T)    optional: the categorical `distribution` the reference returns as
  *                        `factors` (:53,:178,:427); may be NULL for stages > 0
  * Replaces node2edge (:122-141/:357-370), MLP_dict_softmax.forward (:41-53),
@@ -162,6 +166,14 @@ int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
 /* Number of kernel launches the last-described configuration issues per
  * gn_stage_fwd call (for bench.py's gpu_launches accounting). */
 int gn_stage_launch_count(const gn_stage_cfg* cfg);
+
+/* Profiling hook (the only process-wide state in the library; off by default).
+ * While enabled every kernel launch is bracketed by CUDA events on its launch
+ * stream.  gn_profile_collect synchronises those events, sums the durations by
+ * kernel name into total_ms[i] / counts[i], writes the names ';'-separated into
+ * `names`, clears the records and returns the number of distinct kernels. */
+void gn_profile_enable(int on);
+int gn_profile_collect(char* names, int names_len, float* total_ms, int* counts, int max_entries);
 
 #ifdef __cplusplus
 }

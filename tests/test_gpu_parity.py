@@ -272,3 +272,36 @@ def test_inputs_not_mutated_and_fresh_outputs():
     assert not hm1.requires_grad
     with pytest.raises(RuntimeError, match="Float"):
         m(h.double(), corr.double())
+
+
+# ---- the block the encoders run: MultiScaleInteraction (GroupNet_nba.py:284-309) -------
+def test_multiscale_interaction_matches_layers_and_host_pipeline():
+    torch.manual_seed(1234)
+    m = gb.MultiScaleInteraction(64, (5, 11)).to(DEV).eval()
+    gen = torch.Generator().manual_seed(3)
+    b, n = 1000, 11
+    x = torch.randn(b, n, 64, generator=gen)
+    noise = [torch.rand(b, 121, 6, generator=gen), torch.rand(b, 11, 10, generator=gen),
+             torch.rand(b, 1, 10, generator=gen)]
+    feat, new_h = m(x.to(DEV), noise=[u.to(DEV) for u in noise])
+    assert feat.shape == (b, n, 256) and new_h.shape == (b, 12, 11)
+    # against the oracle, layer by layer, concatenated the way PastEncoder does
+    sds = [{k: v.detach().cpu() for k, v in l.state_dict().items()} for l in m.layers()]
+    with torch.no_grad():
+        corr = O.feature_correlation(x)
+        a, _ = O.forward_pairwise(sds[0], x, [noise[0]])
+        h5, _, H5 = O.forward_hyper(sds[1], x, corr, 5, [noise[1]])
+        h11, _, H11 = O.forward_hyper(sds[2], x, corr, 11, [noise[2]])
+    ref = torch.cat((x, a, h5, h11), dim=-1)
+    assert torch.equal(new_h.cpu(), torch.cat((H5, H11), dim=1))
+    assert torch.equal(feat[:, :, :64].cpu(), x)
+    assert_close(feat, ref, FP32_REL, "final_feature")
+    # host pipeline: chunking must not change anything (philox keyed by global scene index)
+    m.set_rng("philox", seed=11)
+    f_dev, h_dev = m(x.to(DEV))
+    for cs in (1000, 256, 77):
+        m.set_rng("philox", seed=11)
+        f_host, h_host = m.forward_host(x.pin_memory(), chunk_scenes=cs)
+        torch.cuda.synchronize()
+        assert torch.equal(f_host, f_dev.cpu()) and torch.equal(h_host, h_dev.cpu()), cs
+    assert m.launches_per_forward(b, n) == 1 + 5 + 6 + 6
