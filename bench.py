@@ -92,7 +92,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -166,7 +166,7 @@ def cpu_baseline(budget_s=12.0):
     fwd = build_cpu_arm()
     time_cpu(fwd, 256)                                  # warm-up
     done, spent = 0, 0.0
-    while spent < budget_s and done < 16384:
+    while spent < budget_s and done < SCENES:
         spent += time_cpu(fwd, 512)
         done += 512
     return {"value": done / spent, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
@@ -204,7 +204,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=SCENES, help="scenes per GPU (default: BASELINE config)")

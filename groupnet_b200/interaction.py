@@ -128,6 +128,7 @@ class MultiScaleInteraction(nn.Module):
             ev_cmp = [torch.cuda.Event() for _ in range(2)]
             ev_out = [torch.cuda.Event() for _ in range(2)]
             base_offsets = [l.scene_offset for l in self.layers()]
+            base_calls = [l._philox_calls for l in self.layers()]   # the whole host batch is ONE forward
             start = torch.cuda.Event()
             start.record(main)
             s_in.wait_event(start)
@@ -145,8 +146,8 @@ class MultiScaleInteraction(nn.Module):
                 main.wait_event(ev_in[k])
                 if c >= 2:
                     main.wait_event(ev_out[k])                   # D2H of chunk c-2 finished reading fd / hd
-                for l, off in zip(self.layers(), base_offsets):
-                    l.scene_offset = off + b0
+                for l, off, calls in zip(self.layers(), base_offsets, base_calls):
+                    l.scene_offset, l._philox_calls = off + b0, calls
                 self.forward(xd[:m], out_feature=fd[:m], out_H=hd[:m] if rows else None)
                 ev_cmp[k].record(main)
                 with torch.cuda.stream(s_out):
@@ -155,8 +156,8 @@ class MultiScaleInteraction(nn.Module):
                     if rows:
                         out_H_host[b0:b1].copy_(hd[:m], non_blocking=True)
                     ev_out[k].record(s_out)
-            for l, off in zip(self.layers(), base_offsets):
-                l.scene_offset = off
+            for l, off, calls in zip(self.layers(), base_offsets, base_calls):
+                l.scene_offset, l._philox_calls = off, calls + 1
             main.wait_stream(s_out)
         return out_feature_host, out_H_host
 
