@@ -111,6 +111,7 @@ extern "C" int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (cfg->precision) {
     case GN_FP32:
+    case GN_BF16_TC:
       return gn::stage_fwd_simt(cfg, w, h_in, H, U, node_out, dist_out, workspace, workspace_bytes, st, false);
     default:
       return GN_E_PRECISION;

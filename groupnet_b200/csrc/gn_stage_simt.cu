@@ -712,6 +712,9 @@ static int grid_for(long long work, size_t smem) {
 int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
                    const float* H, const float* U, float* node_out, float* dist_out,
                    void* ws, size_t ws_bytes, cudaStream_t st, bool skip_edge_mlp);
+int launch_edge_mlp_tc(const float* edges, long long R, int T, int E, const gn_stage_weights* w,
+                       const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
+                       int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
 
 }  // namespace gn
 
@@ -776,8 +779,11 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
     GN_LAUNCH_CHECK();
   }
   // k3
-  if (!skip_edge_mlp) {
-    if (c->noise_mode == GN_NOISE_GIVEN && !U) return GN_E_NULL;
+  if (c->noise_mode == GN_NOISE_GIVEN && !U) return GN_E_NULL;
+  if (c->precision == GN_BF16_TC) {
+    GN_TRY(launch_edge_mlp_tc(edges, RE, T, E, w, U, c->noise_mode, c->seed, c->scene_offset,
+                              c->stage_index, dist_out, efeat, st));
+  } else if (!skip_edge_mlp) {
     constexpr int TM = 128, LD = TM + 4;
     size_t smem = (static_cast<size_t>(64 + 128) * LD + 2 * KC * 128 + 256 * GN_SMALL_OUT +
                    TM * 17 + TM * 16) * 4;

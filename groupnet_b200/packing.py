@@ -50,6 +50,14 @@ def _kmajor(weight: torch.Tensor, kp: int, nc: int, tn: int) -> torch.Tensor:
     return permute_cols(wt, tn)
 
 
+def canonical_bf16(weight: torch.Tensor) -> torch.Tensor:
+    """nn.Linear.weight (N, K) -> bf16 in the canonical K-major no-swizzle UMMA
+    operand layout [K/8][N][8] (csrc/gn_tc.cuh): byte(n,k) = (k/8)*(N*16) + n*16 + (k%8)*2."""
+    n, k = weight.shape
+    assert k % 8 == 0 and n % 8 == 0
+    return weight.detach().reshape(n, k // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+
+
 def agg_out_cols(d: int) -> Tuple[int, int]:
     """(Dc, TN) of the aggregation output GEMM; must match make_plan() in
     csrc/gn_stage_simt.cu."""
@@ -122,6 +130,12 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
     out["agg_w1t"] = permute_cols(a1, agg_tn)
     out["agg_b1"] = torch.stack([dev(m.layers[1].bias) for m in agg]).contiguous()
 
+    # tensor-core (bf16) copies of the per-edge MLP chain
+    out["tc_init_w0"] = canonical_bf16(dev(init[0].weight))                      # (128, 64)
+    out["tc_init_w1"] = canonical_bf16(dev(init[1].weight))                      # (64, 128)
+    out["tc_df_w0"] = canonical_bf16(df0)                                        # (256, 64)
+    out["tc_df_w1"] = canonical_bf16(w1.t().contiguous())                        # (16, 256)
+
     out["post_w0t"] = _kmajor(dev(post_mod.layers[0].weight), k2p, 128, 128)
     out["post_b0"] = dev(post_mod.layers[0].bias)
     out["post_w1t"] = _kmajor(dev(post_mod.layers[1].weight), 128, doutc, 64)
@@ -138,7 +152,7 @@ class PackedStage:
         self.struct = _lib.StageWeights()
         for name in _lib.StageWeights.FIELDS:
             tens = self.tensors[name]
-            assert tens.is_contiguous() and tens.dtype == torch.float32
+            assert tens.is_contiguous() and tens.dtype == (torch.bfloat16 if name.startswith("tc_") else torch.float32)
             setattr(self.struct, name, C.c_void_p(tens.data_ptr()))
 
 

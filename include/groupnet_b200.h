@@ -95,6 +95,13 @@ typedef struct gn_stage_weights {
   const float* post_b0;   /* [128] */
   const float* post_w1t;  /* [128][Doutc] */
   const float* post_b1;   /* [Dout] */
+  /* bf16 copies for the tcgen05 path (required when precision == GN_BF16_TC, else may be NULL):
+   * nn.Linear.weight [N][K] in the canonical K-major no-swizzle UMMA operand layout
+   * byte(n,k) = (k/8)*(N*16) + n*16 + (k%8)*2   (csrc/gn_tc.cuh) */
+  const void* tc_init_w0; /* N=128, K=64   init_MLP.layers.0 */
+  const void* tc_init_w1; /* N=64,  K=128  init_MLP.layers.1 */
+  const void* tc_df_w0;   /* N=256, K=64   [MLP_distribution | MLP_factor].layers.0 */
+  const void* tc_df_w1;   /* N=16,  K=256  rows < T: distribution head on k < 128; row T: factor head on k >= 128 */
 } gn_stage_weights;
 
 typedef struct gn_stage_cfg {

@@ -305,3 +305,32 @@ def test_multiscale_interaction_matches_layers_and_host_pipeline():
         torch.cuda.synchronize()
         assert torch.equal(f_host, f_dev.cpu()) and torch.equal(h_host, h_dev.cpu()), cs
     assert m.launches_per_forward(b, n) == 1 + 5 + 6 + 6
+
+
+# ---- bf16 tensor-core (tcgen05) path: 2e-2 (BASELINE.json north_star) ------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_layer_forward_bf16_tc_vs_golden(name):
+    g = load_golden(name)
+    node, fac, hinc = _run_layer(g, precision="bf16")
+    if hinc is not None:
+        assert torch.equal(hinc.cpu(), torch.from_numpy(g["H"]))      # membership stays bit-exact
+    assert_close(fac, g["factors"], BF16_REL, f"{name} factors (bf16)")
+    assert_close(node, g["node_feat"], BF16_REL, f"{name} node_feat (bf16)")
+    assert torch.allclose(fac.sum(-1), torch.ones_like(fac[..., 0]), atol=1e-5)
+
+
+def test_bf16_tc_large_batch_vs_fp32_path():
+    """Many tiles per CTA, ragged last tile: tcgen05 path vs the fp32 path on the same inputs."""
+    torch.manual_seed(77)
+    m = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=1).to(DEV)
+    gen = torch.Generator().manual_seed(8)
+    b = 3001                                   # 3001 * 121 rows: not a multiple of 128
+    h = torch.randn(b, 11, 64, generator=gen).to(DEV)
+    u = torch.rand(b, 121, 6, generator=gen).to(DEV)
+    n32, f32 = m(h, noise=[u])
+    m.set_precision("bf16")
+    n16, f16 = m(h, noise=[u])
+    assert_close(f16, f32, BF16_REL, "factors bf16 vs fp32")
+    assert_close(n16, n32, BF16_REL, "node_feat bf16 vs fp32")
+    n16b, f16b = m(h, noise=[u])
+    assert torch.equal(n16, n16b) and torch.equal(f16, f16b)          # deterministic
