@@ -1,12 +1,7 @@
 // C-ABI entry points of libgroupnet_b200.so that are not tied to one kernel file.
 #include "gn_common.cuh"
 
-namespace gn {
-int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
-                   const float* H, const float* U, float* node_out, float* dist_out,
-                   void* ws, size_t ws_bytes, cudaStream_t st, bool skip_edge_mlp);
-size_t stage_workspace_bytes_simt(const gn_stage_cfg* c);
-}  // namespace gn
+#include "gn_stage.h"
 
 // ---------------------------------------------------------------------------
 // profiling hook: brackets every kernel launch with CUDA events on the launch
@@ -94,12 +89,12 @@ extern "C" const char* gn_error_string(int code) {
 
 extern "C" size_t gn_stage_workspace_bytes(const gn_stage_cfg* cfg) {
   if (!cfg) return 0;
-  return gn::stage_workspace_bytes_simt(cfg);
+  return gn::stage_workspace_bytes(cfg);
 }
 
 extern "C" int gn_stage_launch_count(const gn_stage_cfg* cfg) {
   if (!cfg) return 0;
-  return cfg->pairwise ? 5 : 6;
+  return gn::stage_launch_count(cfg);
 }
 
 extern "C" int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
@@ -109,11 +104,6 @@ extern "C" int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
   if (!cfg || !w || !h_in || !node_out || !workspace) return GN_E_NULL;
   if ((reinterpret_cast<uintptr_t>(h_in) | reinterpret_cast<uintptr_t>(workspace)) & 15) return GN_E_ALIGN;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (cfg->precision) {
-    case GN_FP32:
-    case GN_BF16_TC:
-      return gn::stage_fwd_simt(cfg, w, h_in, H, U, node_out, dist_out, workspace, workspace_bytes, st, false);
-    default:
-      return GN_E_PRECISION;
-  }
+  return gn::stage_fwd(cfg, w, h_in, H, U, node_out, dist_out, workspace, workspace_bytes, st);
+
 }

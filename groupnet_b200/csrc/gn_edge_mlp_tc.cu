@@ -19,6 +19,7 @@
 // (+ 128 * 4,096 for the padded N = 16 head) = 9.4 MFLOP; algorithmic HBM
 // bytes per row: 256 (edges) + 8 T (dist, edge_feat).
 #include "gn_tc.cuh"
+#include "gn_stage.h"
 
 namespace gn {
 

@@ -1,0 +1,36 @@
+// Internal host-side interfaces between the translation units of libgroupnet_b200.
+#pragma once
+#include <cstring>
+#include <cuda_bf16.h>
+#include "gn_common.cuh"
+
+namespace gn {
+
+// generic tcgen05 row-tile linear (gn_tc_linear.cu)
+struct TcLinArgs {
+  const void* A0; int a0_is_f32; long long lda0; int K0;   // columns [0, K0)
+  const float* A1; long long lda1; int K1;                 // columns [K0, K0+K1), fp32, optional
+  float a_div;                                             // != 0: A is divided by it (true division)
+  const __nv_bfloat16* W; int Ntot; int n0; int N;         // canonical [K/8][Ntot][8]; rows [n0, n0+N)
+  const float* bias;                                       // [Ntot] or null, indexed n0 + col
+  int relu;
+  const float* rowscale; int rs_ld; int rs_shift;          // scale = rowscale[row*rs_ld + ((n0+col) >> rs_shift)]
+  const float* bias_mat; int bm_T; int bm_ld;              // out += sum_t rowscale[row*rs_ld + t] * bias_mat[t*bm_ld + n0+col]
+  void* out; int out_is_f32; long long ldo; int out_col0;  // row-major, written at column out_col0 + col
+  float out_div;                                           // != 0: result divided by it
+  long long R;
+};
+int launch_tc_linear(const TcLinArgs& a, const char* name, cudaStream_t st);
+
+// fused per-edge MLP chain on tcgen05 (gn_edge_mlp_tc.cu)
+int launch_edge_mlp_tc(const float* edges, long long R, int T, int E, const gn_stage_weights* w,
+                       const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
+                       int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
+
+// stage driver (gn_stage_simt.cu)
+int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h, const float* H,
+              const float* U, float* node_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t stage_workspace_bytes(const gn_stage_cfg* c);
+int stage_launch_count(const gn_stage_cfg* c);
+
+}  // namespace gn

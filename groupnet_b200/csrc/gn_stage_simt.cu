@@ -653,12 +653,22 @@ node_post_kernel(const float* __restrict__ h, const float* __restrict__ aggin,
   }
 }
 
+}  // namespace gn
+
 // ===========================================================================
-// host side
+// host side: one stage = a fixed sequence of launches on the caller's stream
 // ===========================================================================
+#include "gn_stage.h"
+
+namespace gn {
+
+#define GN_TRY(expr) do { int rc__ = (expr); if (rc__ != GN_OK) return rc__; } while (0)
+
 struct StagePlan {
   int Dp, Dc, K2p, Doutc;
+  bool tc_nodes;          // node-level / aggregation GEMMs on tcgen05 (bf16 path, D % 16 == 0, Dout % 16 == 0)
   size_t off_xprime, off_pq, off_P, off_edges, off_eo, off_efeat, off_ef, off_G, off_S, off_agg;
+  size_t off_hid, off_hid2, off_hidden;   // bf16 scratch of the tensor-core path
   size_t total;
 };
 
@@ -668,27 +678,35 @@ static int make_plan(const gn_stage_cfg* c, StagePlan& p) {
   if (c->Dout < 1 || c->T < 1 || c->T > GN_SMALL_OUT - 1) return GN_E_SHAPE;
   if (c->pairwise) { if (c->E != c->N * c->N) return GN_E_SHAPE; }
   else if (c->E < 1 || c->E > GN_MAX_AGENTS) return GN_E_SHAPE;
+  if (c->precision != GN_FP32 && c->precision != GN_BF16_TC) return GN_E_PRECISION;
   p.Dp = round_up(c->D, 16);
   p.Dc = c->D <= 64 ? 64 : round_up(c->D, 128);   // multiple of the TN the agg_w1t GEMMs use
   p.K2p = round_up(2 * c->D, 16);
   p.Doutc = round_up(c->Dout, 64);
+  p.tc_nodes = c->precision == GN_BF16_TC && (c->D % 16 == 0) && (c->Dout % 16 == 0) && c->Dout <= 256;
   const size_t R = static_cast<size_t>(c->B) * c->N, RE = static_cast<size_t>(c->B) * c->E;
   size_t o = 0;
-  auto take = [&](size_t floats) { size_t at = o; o += round_up_sz(floats * 4, 256); return at; };
-  p.off_xprime = take(R * 64);
-  p.off_pq = take(R * 64);
-  p.off_edges = take(RE * 64);
-  p.off_efeat = take(RE * c->T);
+  auto take = [&](size_t bytes) { size_t at = o; o += round_up_sz(bytes, 256); return at; };
+  p.off_xprime = take(R * 64 * 4);
+  p.off_pq = take(R * 64 * 4);
+  p.off_edges = take(RE * 64 * 4);
+  p.off_efeat = take(RE * c->T * 4);
+  p.off_P = p.off_G = p.off_S = p.off_eo = p.off_ef = p.off_agg = 0;
+  p.off_hid = p.off_hid2 = p.off_hidden = 0;
   if (c->pairwise) {
-    p.off_P = take(R * c->T * 128);
-    p.off_G = take(R * c->T * 128);
-    p.off_S = take(R * 16);
-    p.off_eo = p.off_ef = p.off_agg = 0;
+    p.off_P = take(R * c->T * 128 * 4);
+    p.off_G = take(R * c->T * 128 * 4);
+    p.off_S = take(R * 16 * 4);
+    if (p.tc_nodes) p.off_agg = take(R * c->D * 4);
   } else {
-    p.off_eo = take(RE * c->D);
-    p.off_ef = take(RE * c->D);
-    p.off_agg = take(R * c->D);
-    p.off_P = p.off_G = p.off_S = 0;
+    p.off_eo = take(RE * c->D * 4);
+    p.off_ef = take(RE * c->D * 4);
+    p.off_agg = take(R * c->D * 4);
+    if (p.tc_nodes) p.off_hidden = take(RE * c->T * 128 * 2);
+  }
+  if (p.tc_nodes) {
+    p.off_hid = take(R * 256 * 2);
+    p.off_hid2 = take(R * 128 * 2);
   }
   p.total = o;
   return GN_OK;
@@ -709,45 +727,125 @@ static int grid_for(long long work, size_t smem) {
   return g < 1 ? 1 : static_cast<int>(g);
 }
 
-int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
-                   const float* H, const float* U, float* node_out, float* dist_out,
-                   void* ws, size_t ws_bytes, cudaStream_t st, bool skip_edge_mlp);
-int launch_edge_mlp_tc(const float* edges, long long R, int T, int E, const gn_stage_weights* w,
-                       const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
-                       int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
+// ---- scene-kernel launchers (shared by the fp32 and the bf16 path) ----
+static int launch_node2edge_pair(const float* xprime, const float* pq, int B, int N,
+                                 const gn_stage_weights* w, float* edges, cudaStream_t st) {
+  const int E = N * N, ecmax = E < N2E_EC ? E : N2E_EC;
+  size_t smem = (static_cast<size_t>(2 * N) * N2E_LD + 2 * ecmax) * 4;
+  GN_TRY(set_smem(node2edge_pair_kernel, smem));
+  long long work = static_cast<long long>(B) * ((E + N2E_EC - 1) / N2E_EC);
+  { ProfScope ps__("node2edge_pair", st);
+    node2edge_pair_kernel<<<grid_for(work, smem), GN_THREADS, smem, st>>>(xprime, pq, B, N, *w, edges); }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
 
-}  // namespace gn
+static int launch_node2edge_hyper(const float* xprime, const float* pq, const float* h, const float* H,
+                                  int B, int N, int E, int D, long long hstride, const gn_stage_weights* w,
+                                  float* edges, float* eo, cudaStream_t st) {
+  size_t fl = static_cast<size_t>(2 * N) * N2E_LD + static_cast<size_t>(N) * (D + 4) +
+              2 * ((static_cast<size_t>(E) * (N + 1) + 3) & ~size_t(3)) + static_cast<size_t>(E) * 33;
+  size_t smem = fl * 4;
+  GN_TRY(set_smem(node2edge_hyper_kernel, smem));
+  { ProfScope ps__("node2edge_hyper", st);
+    node2edge_hyper_kernel<<<grid_for(B, smem), GN_THREADS, smem, st>>>(xprime, pq, h, H, B, N, E, D, hstride,
+                                                                        *w, edges, eo); }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
 
-namespace gn {
+static int launch_edge2node_pair(const float* P, const float* efeat, int B, int N, int T,
+                                 const gn_stage_weights* w, float* G, float* S, cudaStream_t st) {
+  const int E = N * N;
+  size_t smem = (((static_cast<size_t>(E) * T + 3) & ~size_t(3)) + static_cast<size_t>(N) * 128 +
+                 static_cast<size_t>(N) * (N + 1)) * 4;
+  GN_TRY(set_smem(edge2node_pair_kernel, smem));
+  { ProfScope ps__("edge2node_pair", st);
+    edge2node_pair_kernel<<<grid_for(B, smem), GN_THREADS, smem, st>>>(P, efeat, B, N, T, *w, G, S); }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
 
-#define GN_TRY(expr) do { int rc__ = (expr); if (rc__ != GN_OK) return rc__; } while (0)
+static int launch_edge2node_hyper(const float* ef, const float* H, int B, int N, int E, int D,
+                                  long long hstride, float* agg, cudaStream_t st) {
+  size_t smem = static_cast<size_t>(E) * (N + 1) * 4;
+  GN_TRY(set_smem(edge2node_hyper_kernel, smem));
+  { ProfScope ps__("edge2node_hyper", st);
+    edge2node_hyper_kernel<<<grid_for(B, smem), GN_THREADS, smem, st>>>(ef, H, B, N, E, D, hstride, agg); }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
 
-int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
-                   const float* H, const float* U, float* node_out, float* dist_out,
-                   void* ws, size_t ws_bytes, cudaStream_t st, bool skip_edge_mlp) {
+static TcLinArgs lin_args() {
+  TcLinArgs a;
+  memset(&a, 0, sizeof(a));
+  return a;
+}
+
+int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
+              const float* H, const float* U, float* node_out, float* dist_out,
+              void* ws, size_t ws_bytes, cudaStream_t st) {
   StagePlan p;
   GN_TRY(make_plan(c, p));
   if (ws_bytes < p.total) return GN_E_WORKSPACE;
   if (c->B == 0) return GN_OK;
   char* base = static_cast<char*>(ws);
-  float* xprime = reinterpret_cast<float*>(base + p.off_xprime);
-  float* pq = reinterpret_cast<float*>(base + p.off_pq);
-  float* edges = reinterpret_cast<float*>(base + p.off_edges);
-  float* efeat = reinterpret_cast<float*>(base + p.off_efeat);
-  float* P = reinterpret_cast<float*>(base + p.off_P);
-  float* G = reinterpret_cast<float*>(base + p.off_G);
-  float* S = reinterpret_cast<float*>(base + p.off_S);
-  float* eo = reinterpret_cast<float*>(base + p.off_eo);
-  float* ef = reinterpret_cast<float*>(base + p.off_ef);
-  float* agg = reinterpret_cast<float*>(base + p.off_agg);
+  auto fptr = [&](size_t off) { return reinterpret_cast<float*>(base + off); };
+  float* xprime = fptr(p.off_xprime);
+  float* pq = fptr(p.off_pq);
+  float* edges = fptr(p.off_edges);
+  float* efeat = fptr(p.off_efeat);
+  float* P = fptr(p.off_P);
+  float* G = fptr(p.off_G);
+  float* S = fptr(p.off_S);
+  float* eo = fptr(p.off_eo);
+  float* ef = fptr(p.off_ef);
+  float* agg = fptr(p.off_agg);
+  __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(base + p.off_hid);
+  __nv_bfloat16* hid2 = reinterpret_cast<__nv_bfloat16*>(base + p.off_hid2);
+  __nv_bfloat16* hidden = reinterpret_cast<__nv_bfloat16*>(base + p.off_hidden);
   const int B = c->B, N = c->N, D = c->D, E = c->E, T = c->T;
   const int R = B * N;
   const long long RE = static_cast<long long>(B) * E;
   const long long hstride = c->h_stride > 0 ? c->h_stride : static_cast<long long>(E) * N;
   if (hstride < static_cast<long long>(E) * N) return GN_E_SHAPE;
+  const int ld_out = c->out_ld > 0 ? c->out_ld : c->Dout;
+  if (ld_out < c->Dout) return GN_E_SHAPE;
+  if (c->noise_mode == GN_NOISE_GIVEN && !U) return GN_E_NULL;
+  if (!c->pairwise && !H) return GN_E_NULL;
+  const bool tcn = p.tc_nodes;
+  if (tcn && (!w->tc_node_w0 || !w->tc_node_w1 || !w->tc_att_wpq || !w->tc_agg_w0 || !w->tc_agg_w1 ||
+              !w->tc_post_w0 || !w->tc_post_w1)) return GN_E_NULL;
 
-  // k1
-  {
+  // ---- k1: node-level prologue: x', pq (and P for the pairwise collapse)
+  if (tcn) {
+    TcLinArgs a = lin_args();
+    a.A0 = h; a.a0_is_f32 = 1; a.lda0 = D; a.K0 = D; a.R = R;
+    a.W = static_cast<const __nv_bfloat16*>(w->tc_node_w0); a.Ntot = 256; a.N = 256;
+    a.bias = w->node_b0; a.relu = 1; a.out = hid; a.out_is_f32 = 0; a.ldo = 256;
+    GN_TRY(launch_tc_linear(a, "node_mlp0_tc", st));
+    a = lin_args();
+    a.A0 = hid; a.a0_is_f32 = 0; a.lda0 = 256; a.K0 = 256; a.R = R;
+    a.W = static_cast<const __nv_bfloat16*>(w->tc_node_w1); a.Ntot = 64; a.N = 64;
+    a.bias = w->node_b1; a.out = xprime; a.out_is_f32 = 1; a.ldo = 64;
+    GN_TRY(launch_tc_linear(a, "node_mlp1_tc", st));
+    a = lin_args();
+    a.A0 = xprime; a.a0_is_f32 = 1; a.lda0 = 64; a.K0 = 64; a.R = R;
+    a.W = static_cast<const __nv_bfloat16*>(w->tc_att_wpq); a.Ntot = 64; a.N = 64;
+    a.out = pq; a.out_is_f32 = 1; a.ldo = 64;
+    GN_TRY(launch_tc_linear(a, "att_proj_tc", st));
+    if (c->pairwise) {
+      const int NT = T * 128;
+      for (int n0 = 0; n0 < NT; n0 += 256) {
+        a = lin_args();
+        a.A0 = h; a.a0_is_f32 = 1; a.lda0 = D; a.K0 = D; a.R = R;
+        a.W = static_cast<const __nv_bfloat16*>(w->tc_agg_w0); a.Ntot = NT; a.n0 = n0;
+        a.N = NT - n0 < 256 ? NT - n0 : 256;
+        a.out = P; a.out_is_f32 = 1; a.ldo = NT; a.out_col0 = n0;
+        GN_TRY(launch_tc_linear(a, "agg_in_tc", st));
+      }
+    }
+  } else {
     constexpr int TM = 64, LD = TM + 4;
     size_t smem = static_cast<size_t>(p.Dp + 128 + 64) * LD * 4 + 2 * KC * 128 * 4;
     auto kern = node_pre_kernel<TM>;
@@ -757,33 +855,16 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
       kern<<<grid, GN_THREADS, smem, st>>>(h, R, D, p.Dp, T, c->pairwise, *w, xprime, pq, P); }
     GN_LAUNCH_CHECK();
   }
-  // k2
-  if (c->pairwise) {
-    int ecmax = E < N2E_EC ? E : N2E_EC;
-    size_t smem = (static_cast<size_t>(2 * N) * N2E_LD + 2 * ecmax) * 4;
-    auto kern = node2edge_pair_kernel;
-    GN_TRY(set_smem(kern, smem));
-    long long work = static_cast<long long>(B) * ((E + N2E_EC - 1) / N2E_EC);
-    { ProfScope ps__("node2edge_pair", st);
-      kern<<<grid_for(work, smem), GN_THREADS, smem, st>>>(xprime, pq, B, N, *w, edges); }
-    GN_LAUNCH_CHECK();
-  } else {
-    if (!H) return GN_E_NULL;
-    size_t fl = static_cast<size_t>(2 * N) * N2E_LD + static_cast<size_t>(N) * (D + 4) +
-                2 * ((static_cast<size_t>(E) * (N + 1) + 3) & ~size_t(3)) + static_cast<size_t>(E) * 33;
-    size_t smem = fl * 4;
-    auto kern = node2edge_hyper_kernel;
-    GN_TRY(set_smem(kern, smem));
-    { ProfScope ps__("node2edge_hyper", st);
-      kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(xprime, pq, h, H, B, N, E, D, hstride, *w, edges, eo); }
-    GN_LAUNCH_CHECK();
-  }
-  // k3
-  if (c->noise_mode == GN_NOISE_GIVEN && !U) return GN_E_NULL;
+
+  // ---- k2: node2edge
+  if (c->pairwise) GN_TRY(launch_node2edge_pair(xprime, pq, B, N, w, edges, st));
+  else GN_TRY(launch_node2edge_hyper(xprime, pq, h, H, B, N, E, D, hstride, w, edges, eo, st));
+
+  // ---- k3: per-edge MLP chain + Gumbel softmax
   if (c->precision == GN_BF16_TC) {
     GN_TRY(launch_edge_mlp_tc(edges, RE, T, E, w, U, c->noise_mode, c->seed, c->scene_offset,
                               c->stage_index, dist_out, efeat, st));
-  } else if (!skip_edge_mlp) {
+  } else {
     constexpr int TM = 128, LD = TM + 4;
     size_t smem = (static_cast<size_t>(64 + 128) * LD + 2 * KC * 128 + 256 * GN_SMALL_OUT +
                    TM * 17 + TM * 16) * 4;
@@ -795,23 +876,36 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
           dist_out, efeat); }
     GN_LAUNCH_CHECK();
   }
-  // k4 / k5
+
+  // ---- k4/k5: aggregation
   if (c->pairwise) {
-    size_t smem = (((static_cast<size_t>(E) * T + 3) & ~size_t(3)) + static_cast<size_t>(N) * 128 +
-                   static_cast<size_t>(N) * (N + 1)) * 4;
-    auto kern = edge2node_pair_kernel;
-    GN_TRY(set_smem(kern, smem));
-    { ProfScope ps__("edge2node_pair", st);
-      kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(P, efeat, B, N, T, *w, G, S); }
-    GN_LAUNCH_CHECK();
+    GN_TRY(launch_edge2node_pair(P, efeat, B, N, T, w, G, S, st));
   } else {
-    if (D <= 64) {
+    if (tcn) {
+      const int NT = T * 128;
+      for (int n0 = 0; n0 < NT; n0 += 256) {        // hidden = relu(eo W0^T + b0) * edge_feat[:, t]
+        TcLinArgs a = lin_args();
+        a.A0 = eo; a.a0_is_f32 = 1; a.lda0 = D; a.K0 = D; a.R = RE;
+        a.W = static_cast<const __nv_bfloat16*>(w->tc_agg_w0); a.Ntot = NT; a.n0 = n0;
+        a.N = NT - n0 < 256 ? NT - n0 : 256;
+        a.bias = w->agg_b0; a.relu = 1; a.rowscale = efeat; a.rs_ld = T; a.rs_shift = 7;
+        a.out = hidden; a.out_is_f32 = 0; a.ldo = NT; a.out_col0 = n0;
+        GN_TRY(launch_tc_linear(a, "agg_hidden_tc", st));
+      }
+      TcLinArgs a = lin_args();                      // ef = hidden W1cat^T + sum_t edge_feat_t b1_t
+      a.A0 = hidden; a.a0_is_f32 = 0; a.lda0 = NT; a.K0 = NT; a.R = RE;
+      a.W = static_cast<const __nv_bfloat16*>(w->tc_agg_w1); a.Ntot = D; a.N = D;
+      a.rowscale = efeat; a.rs_ld = T; a.bias_mat = w->agg_b1; a.bm_T = T; a.bm_ld = D;
+      a.out = ef; a.out_is_f32 = 1; a.ldo = D;
+      GN_TRY(launch_tc_linear(a, "agg_out_tc", st));
+    } else if (D <= 64) {
       constexpr int TM = 128, LD = TM + 4;
       size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
       auto kern = edge_agg_kernel<TM, 64, 1>;
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("edge_agg", st);
         kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef); }
+      GN_LAUNCH_CHECK();
     } else if (D <= 128) {
       constexpr int TM = 128, LD = TM + 4;
       size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
@@ -819,6 +913,7 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("edge_agg", st);
         kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef); }
+      GN_LAUNCH_CHECK();
     } else {
       constexpr int TM = 64, LD = TM + 4;
       size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
@@ -826,20 +921,36 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("edge_agg", st);
         kern<<<grid_for((RE + TM - 1) / TM, smem), GN_THREADS, smem, st>>>(eo, efeat, RE, D, p.Dp, p.Dc, T, *w, ef); }
+      GN_LAUNCH_CHECK();
     }
-    GN_LAUNCH_CHECK();
-    size_t smem = static_cast<size_t>(E) * (N + 1) * 4;
-    auto kern = edge2node_hyper_kernel;
-    GN_TRY(set_smem(kern, smem));
-    { ProfScope ps__("edge2node_hyper", st);
-      kern<<<grid_for(B, smem), GN_THREADS, smem, st>>>(ef, H, B, N, E, D, hstride, agg); }
-    GN_LAUNCH_CHECK();
+    GN_TRY(launch_edge2node_hyper(ef, H, B, N, E, D, hstride, agg, st));
   }
-  // k6
-  {
+
+  // ---- k6: closing MLP on [agg | h] / N
+  if (tcn) {
+    TcLinArgs a;
+    if (c->pairwise) {                               // agg = G W1cat^T + S b1  (second half of the collapse)
+      const int NT = T * 128;
+      a = lin_args();
+      a.A0 = G; a.a0_is_f32 = 1; a.lda0 = NT; a.K0 = NT; a.R = R;
+      a.W = static_cast<const __nv_bfloat16*>(w->tc_agg_w1); a.Ntot = D; a.N = D;
+      a.rowscale = S; a.rs_ld = 16; a.bias_mat = w->agg_b1; a.bm_T = T; a.bm_ld = D;
+      a.out = agg; a.out_is_f32 = 1; a.ldo = D;
+      GN_TRY(launch_tc_linear(a, "agg_out_tc", st));
+    }
+    a = lin_args();
+    a.A0 = agg; a.a0_is_f32 = 1; a.lda0 = D; a.K0 = D; a.A1 = h; a.lda1 = D; a.K1 = D;
+    a.a_div = static_cast<float>(N); a.R = R;
+    a.W = static_cast<const __nv_bfloat16*>(w->tc_post_w0); a.Ntot = 128; a.N = 128;
+    a.bias = w->post_b0; a.relu = 1; a.out = hid2; a.out_is_f32 = 0; a.ldo = 128;
+    GN_TRY(launch_tc_linear(a, "post_mlp0_tc", st));
+    a = lin_args();
+    a.A0 = hid2; a.a0_is_f32 = 0; a.lda0 = 128; a.K0 = 128; a.R = R;
+    a.W = static_cast<const __nv_bfloat16*>(w->tc_post_w1); a.Ntot = c->Dout; a.N = c->Dout;
+    a.bias = w->post_b1; a.out = node_out; a.out_is_f32 = 1; a.ldo = ld_out;
+    GN_TRY(launch_tc_linear(a, "post_mlp1_tc", st));
+  } else {
     constexpr int TM = 64, LD = TM + 4;
-    const int ld_out = c->out_ld > 0 ? c->out_ld : c->Dout;
-    if (ld_out < c->Dout) return GN_E_SHAPE;
     size_t smem = (static_cast<size_t>(p.K2p + 128 + 64) * LD + 2 * KC * 128 + TM * 16) * 4;
     int grid = grid_for((R + TM - 1) / TM, smem);
     if (D <= 64) {
@@ -863,10 +974,18 @@ int stage_fwd_simt(const gn_stage_cfg* c, const gn_stage_weights* w, const float
   return GN_OK;
 }
 
-size_t stage_workspace_bytes_simt(const gn_stage_cfg* c) {
+size_t stage_workspace_bytes(const gn_stage_cfg* c) {
   StagePlan p;
   if (make_plan(c, p) != GN_OK) return 0;
   return p.total;
+}
+
+int stage_launch_count(const gn_stage_cfg* c) {
+  StagePlan p;
+  if (make_plan(c, p) != GN_OK) return 0;
+  if (!p.tc_nodes) return c->pairwise ? 5 : 6;
+  const int chunks = (c->T * 128 + 255) / 256;
+  return c->pairwise ? (3 + chunks) + 1 + 1 + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
 }
 
 }  // namespace gn

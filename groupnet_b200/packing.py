@@ -136,6 +136,16 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
     out["tc_df_w0"] = canonical_bf16(df0)                                        # (256, 64)
     out["tc_df_w1"] = canonical_bf16(w1.t().contiguous())                        # (16, 256)
 
+    tc_ok = d % 16 == 0 and dout % 16 == 0 and dout <= 256       # must match make_plan() (tc_nodes)
+    if tc_ok:
+        out["tc_node_w0"] = canonical_bf16(dev(node[0].weight))                                   # (256, D)
+        out["tc_node_w1"] = canonical_bf16(dev(node[1].weight))                                   # (64, 256)
+        out["tc_att_wpq"] = canonical_bf16(torch.cat((w0[:, :64], w0[:, 64:]), dim=0))            # (64, 64)
+        out["tc_agg_w0"] = canonical_bf16(a0)                                                     # (T*128, D)
+        out["tc_agg_w1"] = canonical_bf16(torch.cat([dev(m.layers[1].weight) for m in agg], dim=1))  # (D, T*128)
+        out["tc_post_w0"] = canonical_bf16(dev(post_mod.layers[0].weight))                        # (128, 2D)
+        out["tc_post_w1"] = canonical_bf16(dev(post_mod.layers[1].weight))                        # (Dout, 128)
+
     out["post_w0t"] = _kmajor(dev(post_mod.layers[0].weight), k2p, 128, 128)
     out["post_b0"] = dev(post_mod.layers[0].bias)
     out["post_w1t"] = _kmajor(dev(post_mod.layers[1].weight), 128, doutc, 64)
@@ -151,7 +161,10 @@ class PackedStage:
         self.dout = int(self.tensors["post_b1"].numel())
         self.struct = _lib.StageWeights()
         for name in _lib.StageWeights.FIELDS:
-            tens = self.tensors[name]
+            tens = self.tensors.get(name)
+            if tens is None:                      # optional tensor-core copies (shape not eligible)
+                setattr(self.struct, name, C.c_void_p(0))
+                continue
             assert tens.is_contiguous() and tens.dtype == (torch.bfloat16 if name.startswith("tc_") else torch.float32)
             setattr(self.struct, name, C.c_void_p(tens.data_ptr()))
 

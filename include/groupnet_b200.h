@@ -102,6 +102,13 @@ typedef struct gn_stage_weights {
   const void* tc_init_w1; /* N=64,  K=128  init_MLP.layers.1 */
   const void* tc_df_w0;   /* N=256, K=64   [MLP_distribution | MLP_factor].layers.0 */
   const void* tc_df_w1;   /* N=16,  K=256  rows < T: distribution head on k < 128; row T: factor head on k >= 128 */
+  const void* tc_node_w0; /* N=256,   K=D      node2edge_start_mlp.layers.0 */
+  const void* tc_node_w1; /* N=64,    K=256    node2edge_start_mlp.layers.1 */
+  const void* tc_att_wpq; /* N=64,    K=64     rows 0..31 = attention W0[:, :64], rows 32..63 = W0[:, 64:] */
+  const void* tc_agg_w0;  /* N=T*128, K=D      agg_mlp[t].layers.0 stacked over t */
+  const void* tc_agg_w1;  /* N=D,     K=T*128  agg_mlp[t].layers.1 concatenated along K */
+  const void* tc_post_w0; /* N=128,   K=2D     closing MLP layers.0 */
+  const void* tc_post_w1; /* N=Dout,  K=128    closing MLP layers.1 */
 } gn_stage_weights;
 
 typedef struct gn_stage_cfg {
