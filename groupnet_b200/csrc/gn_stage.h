@@ -22,10 +22,12 @@ struct TcLinArgs {
 };
 int launch_tc_linear(const TcLinArgs& a, const char* name, cudaStream_t st);
 
-// fused per-edge MLP chain on tcgen05 (gn_edge_mlp_tc.cu)
-int launch_edge_mlp_tc(const float* edges, long long R, int T, int E, const gn_stage_weights* w,
-                       const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
-                       int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
+// fused per-edge chain on tcgen05 (gn_edge_mlp_tc.cu); pair = node2edge fused in (pairwise layer)
+bool edge_chain_pair_fits(int N);
+int launch_edge_chain_tc(bool pair, const float* edges, const float* xprime, const float* pq,
+                         int N, int E, int T, long long R, const gn_stage_weights* w,
+                         const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
+                         int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
 
 // stage driver (gn_stage_simt.cu)
 int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h, const float* H,

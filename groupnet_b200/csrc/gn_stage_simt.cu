@@ -856,14 +856,16 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     GN_LAUNCH_CHECK();
   }
 
-  // ---- k2: node2edge
-  if (c->pairwise) GN_TRY(launch_node2edge_pair(xprime, pq, B, N, w, edges, st));
+  // ---- k2: node2edge (fused into the tensor-core chain for the pairwise bf16 path)
+  const bool tc = c->precision == GN_BF16_TC;
+  const bool fuse_pair = tc && c->pairwise && edge_chain_pair_fits(N);
+  if (c->pairwise) { if (!fuse_pair) GN_TRY(launch_node2edge_pair(xprime, pq, B, N, w, edges, st)); }
   else GN_TRY(launch_node2edge_hyper(xprime, pq, h, H, B, N, E, D, hstride, w, edges, eo, st));
 
   // ---- k3: per-edge MLP chain + Gumbel softmax
-  if (c->precision == GN_BF16_TC) {
-    GN_TRY(launch_edge_mlp_tc(edges, RE, T, E, w, U, c->noise_mode, c->seed, c->scene_offset,
-                              c->stage_index, dist_out, efeat, st));
+  if (tc) {
+    GN_TRY(launch_edge_chain_tc(fuse_pair, edges, xprime, pq, N, E, T, RE, w, U, c->noise_mode,
+                                c->seed, c->scene_offset, c->stage_index, dist_out, efeat, st));
   } else {
     constexpr int TM = 128, LD = TM + 4;
     size_t smem = (static_cast<size_t>(64 + 128) * LD + 2 * KC * 128 + 256 * GN_SMALL_OUT +
@@ -983,9 +985,10 @@ size_t stage_workspace_bytes(const gn_stage_cfg* c) {
 int stage_launch_count(const gn_stage_cfg* c) {
   StagePlan p;
   if (make_plan(c, p) != GN_OK) return 0;
-  if (!p.tc_nodes) return c->pairwise ? 5 : 6;
+  const int fused = (c->precision == GN_BF16_TC && c->pairwise && edge_chain_pair_fits(c->N)) ? 1 : 0;
+  if (!p.tc_nodes) return (c->pairwise ? 5 : 6) - fused;
   const int chunks = (c->T * 128 + 255) / 256;
-  return c->pairwise ? (3 + chunks) + 1 + 1 + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
+  return c->pairwise ? (3 + chunks) + (2 - fused) + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
 }
 
 }  // namespace gn

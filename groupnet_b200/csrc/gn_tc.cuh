@@ -97,6 +97,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// issue-only variant: several loads may be in flight before one tmem_ld_wait()
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
   asm volatile(
@@ -138,9 +154,51 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// {lo = a, hi = b} -> bf16x2 with ReLU fused into the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16_fast(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+
 // byte offset of the 16-byte k-group `k8` of row `r` in an R-row canonical operand
 __device__ __forceinline__ uint32_t canon_off(int r, int k8, int R) {
   return static_cast<uint32_t>(k8) * (R * 16) + static_cast<uint32_t>(r) * 16;
+}
+
+// Bias through the tensor core: D[128 x N] = ones[128 x 16] * biasB[N x 16]^T where ones has 1.0 in
+// k = 0,1 and biasB holds bf16(b) in k = 0 and bf16(b - bf16(b)) in k = 1 (bias exact to ~16 bits).
+// The GEMM proper then accumulates on top, and the epilogue needs no bias load / add.
+__device__ __forceinline__ void issue_bias(uint32_t tmem_d, uint32_t ones_saddr, uint32_t biasb_saddr, int N) {
+  const uint32_t idesc = make_idesc_bf16(128, N);
+  uint64_t da = make_smem_desc(ones_saddr, 128 * 16, 128);
+  uint64_t db = make_smem_desc(biasb_saddr, static_cast<uint32_t>(N) * 16, 128);
+  mma_bf16_ss(tmem_d, da, db, idesc, 0u);
+}
+
+// build the [N x 16] bias operand (canonical layout) from fp32 biases; called by all threads of the CTA
+__device__ __forceinline__ void build_bias_operand(unsigned char* dst, const float* __restrict__ b, int N,
+                                                   int tid, int nthreads) {
+  for (int n = tid; n < N; n += nthreads) {
+    float v = __ldg(b + n);
+    __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    uint32_t w0 = static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&hi)) |
+                  (static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&lo)) << 16);
+    *reinterpret_cast<uint4*>(dst + n * 16) = make_uint4(w0, 0u, 0u, 0u);            // k-group 0
+    *reinterpret_cast<uint4*>(dst + N * 16 + n * 16) = make_uint4(0u, 0u, 0u, 0u);   // k-group 1
+  }
+}
+__device__ __forceinline__ void build_ones_operand(unsigned char* dst, int tid, int nthreads) {
+  for (int r = tid; r < 128; r += nthreads) {
+    *reinterpret_cast<uint4*>(dst + r * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // bf16 1.0, 1.0
+    *reinterpret_cast<uint4*>(dst + 128 * 16 + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // Issue the K/16 MMAs of one GEMM:  D[128 x N] (+)= A[128 x K] * B[N x K]^T
