@@ -1,0 +1,296 @@
+// Fused edge2node for the pairwise layer (bf16 tensor-core path).
+//
+// Reference (model/MS_HGNN_batch.py:259-268 with H = rel_rec + rel_send, :116-120):
+//   edges_e = h_i + h_j;  ef_e = sum_t edge_feat[e,t] * (W1_t relu(W0_t edges_e + b0_t) + b1_t)
+//   agg_n = sum_e H[e,n] ef_e
+// Collapsed form: the first Linear acts per node, the second per node:
+//   P'_n[t] = W0_t h_n + b0_t / 2                                        (GEMM 1, tensor core)
+//   w[n][j][t] = edge_feat[(n,j),t] + edge_feat[(j,n),t]                  (symmetric, from smem)
+//   G_n[t]  = sum_j w[n][j][t] * relu(P'_n[t] + P'_j[t])                  (SIMT, shared memory)
+//   agg_n   = sum_t W1_t G_n[t] + (sum_j w[n][j][t]) b1_t                 (GEMM 2, tensor core, K = T*128)
+//
+// One persistent CTA per SM; a tile = SC = floor(128/N) whole scenes = SC*N <= 128 node rows.
+// Per t: GEMM 1 of step t+1 runs on the tensor core while the 256 threads do the relu-sum of
+// step t; P'/G never leave the SM (the unfused path moves 2 x 2.2 GB of P and G through HBM).
+// W0_t / W1_t (16 KB each) are streamed from L2 with cp.async.
+//
+// Bound: the SIMT relu-sum (3 instructions per (n, j, t, c)): N * T * 128 * 3 thread-instructions
+// per node row.  Algorithmic HBM bytes per scene: N*D*4 (h) + N*N*T*4 (edge_feat) + N*D*4 (agg).
+#include "gn_tc.cuh"
+#include "gn_stage.h"
+
+namespace gn {
+
+struct PairAggArgs {
+  const float* h;            // (B*N, 64)
+  const float* edge_feat;    // (B, N*N, T)
+  const __nv_bfloat16* w0;   // canonical (T*128, 64): tc_agg_w0
+  const __nv_bfloat16* w1;   // canonical (64, T*128): tc_agg_w1
+  const float* b0;           // (T*128)
+  const float* b1;           // (T, 64)
+  float* agg;                // (B*N, 64)
+  int B, N, T, SC;
+};
+
+namespace pagg {
+constexpr int D = 64;
+constexpr uint32_t OFF_A = 0;                          // h tile, bf16 canonical [128 x 64]      16 KB
+constexpr int PLD = 132;                                // padded P' row (floats): rows 4 banks apart
+constexpr uint32_t OFF_P = OFF_A + 128 * 64 * 2;       // P'_t fp32 [128][PLD]                   66 KB
+constexpr uint32_t OFF_G = OFF_P + 128 * PLD * 4;      // G_t bf16 canonical [128 x 128]         32 KB
+constexpr uint32_t OFF_W0 = OFF_G + 128 * 128 * 2;     // W0_t double buffer [128 x 64] x 2      32 KB
+constexpr uint32_t OFF_W1 = OFF_W0 + 2 * 128 * 64 * 2; // W1_t [64 x 128]                        16 KB
+constexpr uint32_t OFF_ONES = OFF_W1 + 64 * 128 * 2;   // ones operand                            4 KB
+constexpr uint32_t OFF_BB = OFF_ONES + 128 * 32;       // b0_t/2 operand double buffer            8 KB
+constexpr uint32_t OFF_S = OFF_BB + 2 * 128 * 32;      // S[128][16] fp32                         8 KB
+constexpr uint32_t OFF_BAR = OFF_S + 128 * 16 * 4;     // mbarA, mbarB, tmem slot
+constexpr uint32_t OFF_EF = OFF_BAR + 32;              // edge_feat of the tile: SC*N*N*T fp32
+constexpr uint32_t TM_P = 0, TM_AGG = 256;             // TMEM columns: P' double buffer 2 x 128, agg 64
+}  // namespace pagg
+
+__global__ void __launch_bounds__(GN_THREADS, 1)
+pair_agg_tc_kernel(PairAggArgs a) {
+  using namespace pagg;
+  using namespace tc;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = tid & 127, chalf = tid >> 7;          // tile row (TMEM lane), 64-column half
+  float* sP = reinterpret_cast<float*>(smem + OFF_P);
+  float* sS = reinterpret_cast<float*>(smem + OFF_S);
+  float* sEF = reinterpret_cast<float*>(smem + OFF_EF);
+  uint64_t* mbarA = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* mbarB = mbarA + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+  const int N = a.N, T = a.T, SC = a.SC, E = N * N;
+  const int NT = T * 128;
+
+  build_ones_operand(smem + OFF_ONES, tid, GN_THREADS);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) { mbar_init(mbarA, 1); mbar_init(mbarB, 1); }
+  fence_proxy_async_smem();
+  fence_before_thread_sync();
+  __syncthreads();
+  fence_after_thread_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+  const uint32_t sbase = smem_u32(smem);
+  uint32_t phA = 0, phB = 0;
+
+  // W0_t: rows [t*128, t*128+128) of the canonical (NT x 64) operand: 8 k-groups x 2 KB
+  auto load_w0 = [&](int t, int buf) {
+    for (int i = tid; i < 8 * 128; i += GN_THREADS) {
+      const int k8 = i >> 7, n = i & 127;
+      cp_async16(smem + OFF_W0 + buf * (128 * 64 * 2) + (k8 * 128 + n) * 16,
+                 a.w0 + (static_cast<size_t>(k8) * NT + t * 128 + n) * 8);
+    }
+  };
+  // W1_t: k-groups [t*16, t*16+16) of the canonical (64 x NT) operand: 16 KB contiguous
+  auto load_w1 = [&](int t) {
+    const __nv_bfloat16* src = a.w1 + static_cast<size_t>(t) * 16 * 64 * 8;
+    for (int i = tid; i < 16 * 64; i += GN_THREADS) cp_async16(smem + OFF_W1 + i * 16, src + i * 8);
+  };
+  // b0_t / 2 as a [128 x 16] bias operand
+  auto build_bb = [&](int t, int buf) {
+    if (tid < 128) {
+      const float v = 0.5f * __ldg(a.b0 + t * 128 + tid);
+      __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+      const uint32_t w0 = static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&hi)) |
+                          (static_cast<uint32_t>(*reinterpret_cast<unsigned short*>(&lo)) << 16);
+      unsigned char* dst = smem + OFF_BB + buf * (128 * 32);
+      *reinterpret_cast<uint4*>(dst + tid * 16) = make_uint4(w0, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(dst + 128 * 16 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  auto issue_gemm1 = [&](int t) {     // P'_t = A W0_t^T + b0_t/2 -> TMEM columns (t&1)*128
+    const int buf = t & 1;
+    issue_bias(tmem_base + TM_P + buf * 128, sbase + OFF_ONES, sbase + OFF_BB + buf * (128 * 32), 128);
+    issue_gemm(tmem_base + TM_P + buf * 128, sbase + OFF_A, sbase + OFF_W0 + buf * (128 * 64 * 2), 128, 64, true);
+    mma_commit(mbarA);
+  };
+
+  const int rows_per_tile = SC * N;
+  const int ntiles = (a.B + SC - 1) / SC;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0s = tile * SC;
+    const int ns = min(SC, a.B - b0s);
+    const int nv = ns * N;                                  // valid node rows of this tile
+    const size_t grow0 = static_cast<size_t>(b0s) * N;
+    const bool live = row < nv;
+    const int sc = row / N, ni = row - sc * N;              // scene in tile, node in scene
+
+    // ---- tile prologue: h tile -> bf16 A operand, edge_feat -> smem, W0_0, W1_0, bias operand 0 ----
+    {
+      const float* ef = a.edge_feat + static_cast<size_t>(b0s) * E * T;
+      const int n4 = (ns * E * T) >> 2;                     // SC*E*T*4 bytes is 16-byte aligned when E*T % 4 == 0
+      if (((E * T) & 3) == 0) {
+        for (int i = tid; i < n4; i += GN_THREADS) cp_async16(sEF + 4 * i, ef + 4 * i);
+      } else {
+        for (int i = tid; i < ns * E * T; i += GN_THREADS) sEF[i] = __ldg(ef + i);
+      }
+      load_w0(0, 0);
+      if (T > 1) load_w0(1, 1);
+      load_w1(0);
+      cp_async_commit();
+      build_bb(0, 0);
+      if (T > 1) build_bb(1, 1);
+      if (tid < 128) {
+        const float* src = a.h + (grow0 + row) * D;
+#pragma unroll
+        for (int k8 = 0; k8 < 8; ++k8) {
+          uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+          if (live) {
+            float4 x = ldg_f4(src + 8 * k8), y = ldg_f4(src + 8 * k8 + 4);
+            pk = make_uint4(pack_bf16_fast(x.x, x.y), pack_bf16_fast(x.z, x.w),
+                            pack_bf16_fast(y.x, y.y), pack_bf16_fast(y.z, y.w));
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_A + canon_off(row, k8, 128)) = pk;
+        }
+      }
+      for (int i = tid; i < 128 * 16; i += GN_THREADS) sS[i] = 0.f;
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      fence_before_thread_sync();
+      __syncthreads();
+      if (tid == 0) { fence_after_thread_sync(); issue_gemm1(0); }
+    }
+
+    for (int t = 0; t < T; ++t) {
+      // (a) P'_t ready in TMEM
+      mbar_wait(mbarA, phA); phA ^= 1;
+      fence_after_thread_sync();
+      // (b) drain this thread's half row: keep it in registers, publish it for the scene mates
+      float own[64];
+      {
+        uint32_t r[2][32];
+        tmem_ld32_nowait(tmem_lane + TM_P + (t & 1) * 128 + chalf * 64, r[0]);
+        tmem_ld32_nowait(tmem_lane + TM_P + (t & 1) * 128 + chalf * 64 + 32, r[1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 64; ++c) own[c] = __uint_as_float(r[c >> 5][c & 31]);
+        float* dst = sP + row * PLD + chalf * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(own[c], own[c + 1], own[c + 2], own[c + 3]);
+      }
+      cp_async_wait<0>();                                    // W0_{t+1} (issued one step ago) has landed
+      fence_proxy_async_smem();
+      fence_before_thread_sync();
+      __syncthreads();                                       // P'_t visible; W0_{t+1} / bias operand staged
+      // (c) tensor core: P'_{t+1} while the SIMT part of step t runs
+      if (tid == 0 && t + 1 < T) { fence_after_thread_sync(); issue_gemm1(t + 1); }
+      // GEMM 2 of step t-1 has had a whole drain to finish: its operand buffers are free again
+      if (t > 0) {
+        mbar_wait(mbarB, phB); phB ^= 1;
+        fence_after_thread_sync();
+        load_w1(t);
+      }
+      cp_async_commit();                                     // group 1: W1_t (needed by GEMM 2 of this step)
+      // W0 / bias buffers (t & 1) were last read by GEMM 1 of step t (complete): stage step t+2
+      if (t + 2 < T) { load_w0(t + 2, t & 1); build_bb(t + 2, t & 1); }
+      cp_async_commit();                                     // group 2: W0_{t+2} (needed one step later)
+      // (d) relu-sum over the scene mates
+      float acc[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+      float ssum = 0.f;
+      if (live) {
+        const float* efs = sEF + sc * E * T;
+        const float* prow = sP + (sc * N) * PLD + chalf * 64;
+        for (int j = 0; j < N; ++j) {
+          const float w = efs[(ni * N + j) * T + t] + efs[(j * N + ni) * T + t];
+          ssum += w;
+          const float* pj = prow + j * PLD;
+#pragma unroll
+          for (int c = 0; c < 64; c += 4) {
+            const float4 p = *reinterpret_cast<const float4*>(pj + c);
+            acc[c] = fmaf(w, fmaxf(own[c] + p.x, 0.f), acc[c]);
+            acc[c + 1] = fmaf(w, fmaxf(own[c + 1] + p.y, 0.f), acc[c + 1]);
+            acc[c + 2] = fmaf(w, fmaxf(own[c + 2] + p.z, 0.f), acc[c + 2]);
+            acc[c + 3] = fmaf(w, fmaxf(own[c + 3] + p.w, 0.f), acc[c + 3]);
+          }
+        }
+        if (chalf == 0) sS[row * 16 + t] = ssum;
+      }
+      // G_t -> bf16 A operand of GEMM 2
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        uint4 pk = make_uint4(pack_bf16_fast(acc[8 * g], acc[8 * g + 1]), pack_bf16_fast(acc[8 * g + 2], acc[8 * g + 3]),
+                              pack_bf16_fast(acc[8 * g + 4], acc[8 * g + 5]), pack_bf16_fast(acc[8 * g + 6], acc[8 * g + 7]));
+        *reinterpret_cast<uint4*>(smem + OFF_G + canon_off(row, chalf * 8 + g, 128)) = pk;
+      }
+      cp_async_wait<1>();                                    // W1_t landed (the step t+2 prefetch may still fly)
+      fence_proxy_async_smem();
+      fence_before_thread_sync();
+      __syncthreads();                                       // also: everyone is done reading P'_t
+      // (e) agg += G_t W1_t^T
+      if (tid == 0) {
+        fence_after_thread_sync();
+        issue_gemm(tmem_base + TM_AGG, sbase + OFF_G, sbase + OFF_W1, D, 128, t > 0);
+        mma_commit(mbarB);
+      }
+    }
+    // ---- epilogue: agg = acc + sum_t S[row][t] b1_t ----
+    mbar_wait(mbarB, phB); phB ^= 1;
+    fence_after_thread_sync();
+    {
+      float v[32];
+      tmem_ld32(tmem_lane + TM_AGG + chalf * 32, v);
+      if (live) {
+        for (int t = 0; t < T; ++t) {
+          const float s = sS[row * 16 + t];
+          const float* b1 = a.b1 + t * D + chalf * 32;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = fmaf(s, __ldg(b1 + c), v[c]);
+        }
+        float* dst = a.agg + (grow0 + row) * D + chalf * 32;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+      }
+    }
+    fence_before_thread_sync();
+    __syncthreads();                                         // TMEM / smem reused by the next tile
+  }
+
+  fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) {
+    fence_after_thread_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+  (void)lane; (void)rows_per_tile;
+}
+
+// shared-memory footprint; the fused kernel is used when it fits and D == 64
+static size_t pair_agg_smem(int N, int T) {
+  const int SC = 128 / N;
+  return pagg::OFF_EF + static_cast<size_t>(SC) * N * N * T * 4;
+}
+
+bool pair_agg_fits(int N, int D, int T) {
+  return D == 64 && N >= 1 && N <= 128 && T <= 15 && pair_agg_smem(N, T) <= 227 * 1024;
+}
+
+int launch_pair_agg_tc(const float* h, const float* edge_feat, int B, int N, int T,
+                       const gn_stage_weights* w, float* agg, cudaStream_t st) {
+  if (!w->tc_agg_w0 || !w->tc_agg_w1) return GN_E_NULL;
+  PairAggArgs a;
+  a.h = h; a.edge_feat = edge_feat;
+  a.w0 = static_cast<const __nv_bfloat16*>(w->tc_agg_w0);
+  a.w1 = static_cast<const __nv_bfloat16*>(w->tc_agg_w1);
+  a.b0 = w->agg_b0; a.b1 = w->agg_b1; a.agg = agg;
+  a.B = B; a.N = N; a.T = T; a.SC = 128 / N;
+  const size_t smem = pair_agg_smem(N, T);
+  cudaError_t e = cudaFuncSetAttribute(pair_agg_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int ntiles = (B + a.SC - 1) / a.SC;
+  const int grid = ntiles < GN_SM_COUNT ? ntiles : GN_SM_COUNT;
+  {
+    ProfScope ps__("pair_agg_tc", st);
+    pair_agg_tc_kernel<<<grid, GN_THREADS, smem, st>>>(a);
+  }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
+
+}  // namespace gn

@@ -29,6 +29,11 @@ int launch_edge_chain_tc(bool pair, const float* edges, const float* xprime, con
                          const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
                          int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
 
+// fused pairwise edge2node on tensor cores (gn_pair_agg_tc.cu)
+bool pair_agg_fits(int N, int D, int T);
+int launch_pair_agg_tc(const float* h, const float* edge_feat, int B, int N, int T,
+                       const gn_stage_weights* w, float* agg, cudaStream_t st);
+
 // stage driver (gn_stage_simt.cu)
 int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h, const float* H,
               const float* U, float* node_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);

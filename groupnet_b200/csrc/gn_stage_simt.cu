@@ -814,6 +814,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   if (c->noise_mode == GN_NOISE_GIVEN && !U) return GN_E_NULL;
   if (!c->pairwise && !H) return GN_E_NULL;
   const bool tcn = p.tc_nodes;
+  const bool fused_agg = tcn && c->pairwise && pair_agg_fits(N, D, T);   // P / G stay on chip
   if (tcn && (!w->tc_node_w0 || !w->tc_node_w1 || !w->tc_att_wpq || !w->tc_agg_w0 || !w->tc_agg_w1 ||
               !w->tc_post_w0 || !w->tc_post_w1)) return GN_E_NULL;
 
@@ -834,7 +835,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     a.W = static_cast<const __nv_bfloat16*>(w->tc_att_wpq); a.Ntot = 64; a.N = 64;
     a.out = pq; a.out_is_f32 = 1; a.ldo = 64;
     GN_TRY(launch_tc_linear(a, "att_proj_tc", st));
-    if (c->pairwise) {
+    if (c->pairwise && !fused_agg) {
       const int NT = T * 128;
       for (int n0 = 0; n0 < NT; n0 += 256) {
         a = lin_args();
@@ -881,7 +882,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
 
   // ---- k4/k5: aggregation
   if (c->pairwise) {
-    GN_TRY(launch_edge2node_pair(P, efeat, B, N, T, w, G, S, st));
+    if (fused_agg) GN_TRY(launch_pair_agg_tc(h, efeat, B, N, T, w, agg, st));
+    else GN_TRY(launch_edge2node_pair(P, efeat, B, N, T, w, G, S, st));
   } else {
     if (tcn) {
       const int NT = T * 128;
@@ -931,7 +933,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   // ---- k6: closing MLP on [agg | h] / N
   if (tcn) {
     TcLinArgs a;
-    if (c->pairwise) {                               // agg = G W1cat^T + S b1  (second half of the collapse)
+    if (c->pairwise && !fused_agg) {                 // agg = G W1cat^T + S b1  (second half of the collapse)
       const int NT = T * 128;
       a = lin_args();
       a.A0 = G; a.a0_is_f32 = 1; a.lda0 = NT; a.K0 = NT; a.R = R;
@@ -988,6 +990,7 @@ int stage_launch_count(const gn_stage_cfg* c) {
   const int fused = (c->precision == GN_BF16_TC && c->pairwise && edge_chain_pair_fits(c->N)) ? 1 : 0;
   if (!p.tc_nodes) return (c->pairwise ? 5 : 6) - fused;
   const int chunks = (c->T * 128 + 255) / 256;
+  if (c->pairwise && pair_agg_fits(c->N, c->D, c->T)) return 3 + (2 - fused) + 1 + 2;
   return c->pairwise ? (3 + chunks) + (2 - fused) + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
 }
 
