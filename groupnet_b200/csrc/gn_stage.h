@@ -34,6 +34,11 @@ bool pair_agg_fits(int N, int D, int T);
 int launch_pair_agg_tc(const float* h, const float* edge_feat, int B, int N, int T,
                        const gn_stage_weights* w, float* agg, cudaStream_t st);
 
+// fused hyper edge_aggregation on tensor cores (gn_hyper_agg_tc.cu)
+bool hyper_agg_fits(int D, int T);
+int launch_hyper_agg_tc(const float* eo, const float* edge_feat, long long R, int T,
+                        const gn_stage_weights* w, float* ef, cudaStream_t st);
+
 // stage driver (gn_stage_simt.cu)
 int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h, const float* H,
               const float* U, float* node_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);
