@@ -45,7 +45,9 @@ def layer_shapes(n):
 
 
 def kernel_work(b, n, d):
-    """{kernel: (flops, bytes, bound)} summed over the launches of ONE step."""
+    """{kernel: (flops, bytes, bound)} summed over the launches of ONE step.
+    ALGORITHMIC work only: FLOPs of the math each kernel is
+    responsible for, bytes = compulsory HBM traffic of its inputs and outputs."""
     w = {}
 
     def add(k, flops, byts, bound):
@@ -56,25 +58,37 @@ def kernel_work(b, n, d):
     hbytes = sum((1 if s == n else n) * n * 4 for s in SCALES)
     add("corr_topk_h", 2 * b * n * n * d, b * (n * d * 4 + hbytes), "hbm")
     for name, e, t, pair in layer_shapes(n):
-        rows_n, rows_e = b * n, b * e
-        node_macs = d * 256 + 256 * 64 + 64 * 64 + (d * t * 128 if pair else 0)
-        add("node_pre", 2 * rows_n * node_macs,
-            rows_n * 4 * (d + 128 + (t * 128 if pair else 0)), "tensor")
-        if pair:
-            add("node2edge_pair", rows_e * (2 * 64 * 2 + 4 * 64), (rows_n * 128 + rows_e * 64) * 4, "hbm")
-        else:
-            add("node2edge_hyper", rows_e * n * (64 + 2 * 64 + 2 * d),
-                (rows_n * (128 + d) + rows_e * (n + 64 + d)) * 4, "hbm")
+        rn, re = b * n, b * e
         mlp_macs = 64 * 128 + 128 * 64 + 64 * 256 + 256 * (t + 1)
-        add("edge_mlp", 2 * rows_e * mlp_macs, rows_e * (64 + 2 * t) * 4, "tensor")
+        agg_macs_row = t * 2 * d * 128                      # both Linears of the T agg MLPs, per row
+        # ---- fp32 (FFMA) path kernels
+        add("node_pre", 2 * rn * (d * 256 + 256 * 64 + 64 * 64 + (d * t * 128 if pair else 0)),
+            rn * 4 * (d + 128 + (t * 128 if pair else 0)), "tensor")
+        add("edge_mlp", 2 * re * mlp_macs, re * (64 + 2 * t) * 4, "tensor")
         if pair:
-            add("edge2node_pair", rows_n * n * t * 128 * 4, (rows_n * (2 * t * 128 + 16) + rows_e * t) * 4, "hbm")
-            post_macs = t * 128 * d + 2 * d * 128 + 128 * d
-            add("node_post", 2 * rows_n * post_macs, rows_n * (t * 128 + 16 + 2 * d) * 4, "tensor")
+            add("node2edge_pair", re * (2 * 64 * 2 + 4 * 64), (rn * 128 + re * 64) * 4, "hbm")
+            add("edge2node_pair", rn * n * t * 128 * 4, (rn * (2 * t * 128 + 16) + re * t) * 4, "hbm")
+            add("node_post", 2 * rn * (t * 128 * d + 2 * d * 128 + 128 * d), rn * (t * 128 + 16 + 2 * d) * 4, "tensor")
         else:
-            add("edge_agg", 2 * rows_e * t * 2 * d * 128, rows_e * (2 * d + t) * 4, "tensor")
-            add("edge2node_hyper", 2 * rows_n * e * d, (rows_e * (d + n) + rows_n * d) * 4, "hbm")
-            add("node_post", 2 * rows_n * (2 * d * 128 + 128 * d), rows_n * 3 * d * 4, "tensor")
+            add("node2edge_hyper", re * n * (64 + 2 * 64 + 2 * d),
+                (rn * (128 + d) + re * (n + 64 + d)) * 4, "hbm")
+            add("edge_agg", 2 * re * agg_macs_row, re * (2 * d + t) * 4, "tensor")
+            add("edge2node_hyper", 2 * rn * e * d, (re * (d + n) + rn * d) * 4, "hbm")
+            add("node_post", 2 * rn * (2 * d * 128 + 128 * d), rn * 3 * d * 4, "tensor")
+        # ---- bf16 tensor-core path kernels
+        add("node_mlp0_tc", 2 * rn * d * 256, rn * (d * 4 + 256 * 2), "tensor")
+        add("node_mlp1_tc", 2 * rn * 256 * 64, rn * (256 * 2 + 64 * 4), "tensor")
+        add("att_proj_tc", 2 * rn * 64 * 64, rn * 128 * 4, "tensor")
+        add("post_mlp0_tc", 2 * rn * 2 * d * 128, rn * (2 * d * 4 + 128 * 2), "tensor")
+        add("post_mlp1_tc", 2 * rn * 128 * d, rn * (128 * 2 + d * 4), "tensor")
+        if pair:
+            # node2edge (attention + gather, ~600 FLOP/row) + MLP chain; x', pq in, dist/edge_feat out
+            add("edge_chain_pair_tc", 2 * re * mlp_macs + re * 600, (rn * 128 + re * t) * 4, "tensor")
+            # P' GEMM + relu-sum (3 FLOP per (n,j,t,c)) + G GEMM; h, edge_feat in, agg out
+            add("pair_agg_tc", 2 * rn * agg_macs_row + rn * n * t * 128 * 3, (rn * 2 * d + re * t) * 4, "tensor")
+        else:
+            add("edge_chain_tc", 2 * re * mlp_macs, re * (64 + t) * 4, "tensor")
+            add("hyper_agg_tc", 2 * re * agg_macs_row, re * (2 * d + t) * 4, "tensor")
     return w
 
 
@@ -208,7 +222,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=SCENES, help="scenes per GPU (default: BASELINE config)")
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16: tcgen05 tensor-core path (2e-2 parity); fp32: FFMA path (1e-5 parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -268,6 +283,21 @@ def main():
             barrier()
         ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
         value = world * b / (ms_step * 1e-3)
+
+        # the other precision path on the same inputs, for reference (short run, same timing rules)
+        other = "fp32" if args.precision == "bf16" else "bf16"
+        model.set_precision(other)
+        for _ in range(3):
+            model(x, out_feature=feat, out_H=hcat)
+        barrier()
+        o_steps = max(3, min(args.steps, 5))
+        e0.record()
+        for _ in range(o_steps):
+            model(x, out_feature=feat, out_H=hcat)
+        e1.record()
+        barrier()
+        other_ms = max_over_ranks(e0.elapsed_time(e1) / o_steps)
+        model.set_precision(args.precision)
 
         # per-kernel durations, CUDA events on the launch stream (library profiling hook)
         _lib.profile_enable(True)
@@ -335,7 +365,7 @@ def main():
         cpu = cpu_baseline()
 
     h2d = b * n * d * 4
-    d2h = out_f.numel() * 4 + out_h.numel() * 4
+    d2h = b * n * (model.feature_width() - d) * 4 + out_h.numel() * 4   # the x slice is filled on the host
     line = {
         "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -350,6 +380,12 @@ def main():
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "MultiScaleInteraction.forward_host (pinned host in/out, 3-stream chunk pipeline)"},
         "gpu_launches": launches_per_step * args.steps,
+        "parity": {"path": args.precision,
+                   "tolerance": "2e-2 (bf16 tensor-core path)" if args.precision == "bf16" else "1e-5 (fp32 path)",
+                   "criterion": "max|d| <= tol * max|ref| per output tensor vs the reference outputs; "
+                                "hyperedge membership bit-exact", "checked_by": "tests/test_gpu_parity.py"},
+        "other_path": {"precision": other, "value": world * b / (other_ms * 1e-3), "unit": "scenes/s",
+                       "ms_per_step": other_ms, "steps": o_steps},
         "roofline": roofline,
         "kernels": kernels,
     }

@@ -25,6 +25,26 @@ from .layers import MS_HGNN_hyper, MS_HGNN_oridinary
 
 _HYPER_NAMES = ("interaction_hyper", "interaction_hyper2", "interaction_hyper3")
 
+_cudart = None
+
+
+def _memcpy2d_d2h(dst_host: torch.Tensor, src_dev: torch.Tensor, col0: int, ncols: int, stream) -> None:
+    """Copy columns [col0, col0+ncols) of every (b, n) row of a (m, N, W) fp32 device tensor into the
+    same columns of a pinned host tensor of the same shape: one strided cudaMemcpy2DAsync."""
+    global _cudart
+    import ctypes
+    if _cudart is None:
+        _cudart = ctypes.CDLL("libcudart.so.12")
+        _cudart.cudaMemcpy2DAsync.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                              ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        _cudart.cudaMemcpy2DAsync.restype = ctypes.c_int
+    m, n, w = src_dev.shape
+    assert dst_host.shape == src_dev.shape and dst_host.is_contiguous() and src_dev.is_contiguous()
+    rc = _cudart.cudaMemcpy2DAsync(dst_host.data_ptr() + 4 * col0, 4 * w, src_dev.data_ptr() + 4 * col0, 4 * w,
+                                   4 * ncols, m * n, 2, stream.cuda_stream)      # 2 = cudaMemcpyDeviceToHost
+    if rc != 0:
+        raise RuntimeError(f"cudaMemcpy2DAsync failed with cudaError {rc}")
+
 
 class MultiScaleInteraction(nn.Module):
     def __init__(self, model_dim: int = 64, hyper_scales: Sequence[int] = (5, 11), nmp_layers: int = 1):
@@ -70,7 +90,8 @@ class MultiScaleInteraction(nn.Module):
 
     # ------------------------------------------------------------------
     def forward(self, ftraj_input: torch.Tensor, *, out_feature: Optional[torch.Tensor] = None,
-                out_H: Optional[torch.Tensor] = None, noise=None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+                out_H: Optional[torch.Tensor] = None, noise=None,
+                write_input_slice: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         """ftraj_input (B,N,D) -> (final_feature (B,N,D*(2+S)), new_H (B,sum E_s,N))
         == model/GroupNet_nba.py:284-309 (before the final .view)."""
         ops._require_cuda_f32(ftraj_input, "ftraj_input")
@@ -88,7 +109,8 @@ class MultiScaleInteraction(nn.Module):
                 out_H = torch.empty(b, sum(rows), n, dtype=torch.float32, device=dev)
             hs = ops.corr_topk_h_into(x, self.hyper_scales, out_H)
             new_h = out_H
-        out_feature[:, :, :d].copy_(x)                              # skip connection slice (:301-309)
+        if write_input_slice:
+            out_feature[:, :, :d].copy_(x)                          # skip connection slice (:301-309)
         noise = list(noise) if noise is not None else [None] * (1 + len(self.hyper_scales))
         self.interaction(x, out=out_feature[:, :, d:2 * d], want_factors=False, noise=noise[0])
         for i, name in enumerate(_HYPER_NAMES[:len(self.hyper_scales)]):
@@ -148,14 +170,17 @@ class MultiScaleInteraction(nn.Module):
                     main.wait_event(ev_out[k])                   # D2H of chunk c-2 finished reading fd / hd
                 for l, off, calls in zip(self.layers(), base_offsets, base_calls):
                     l.scene_offset, l._philox_calls = off + b0, calls
-                self.forward(xd[:m], out_feature=fd[:m], out_H=hd[:m] if rows else None)
+                # the x slice of final_feature is already on the host: do not move it over PCIe twice
+                self.forward(xd[:m], out_feature=fd[:m], out_H=hd[:m] if rows else None,
+                             write_input_slice=False)
                 ev_cmp[k].record(main)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[k])
-                    out_feature_host[b0:b1].copy_(fd[:m], non_blocking=True)
+                    _memcpy2d_d2h(out_feature_host[b0:b1], fd[:m], d, width - d, s_out)
                     if rows:
                         out_H_host[b0:b1].copy_(hd[:m], non_blocking=True)
                     ev_out[k].record(s_out)
+                out_feature_host[b0:b1, :, :d].copy_(x_host[b0:b1])   # host-side, overlaps the GPU work
             for l, off, calls in zip(self.layers(), base_offsets, base_calls):
                 l.scene_offset, l._philox_calls = off, calls + 1
             main.wait_stream(s_out)

@@ -1,0 +1,63 @@
+"""N > 1 host logic on CPU: world_size-2 gloo processes exercise the shard
+arithmetic, the rank configuration of the layers and the gather helper."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from groupnet_b200 import sharding
+
+
+def test_shard_ranges_cover_batch():
+    for total in (0, 1, 7, 65536, 65537):
+        for world in (1, 2, 3, 4, 8):
+            r = sharding.shard_ranges(total, world)
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.shard_range(10, 2, 2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, total):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import groupnet_b200 as gb
+        a, b = sharding.shard_range(total, rank, world)
+        # every rank builds the same weights (replicated), and is pointed at its slice
+        torch.manual_seed(1234)
+        m = gb.MultiScaleInteraction(64, (5, 11))
+        sharding.configure_layer_for_rank(m, total, rank, world, seed=7)
+        assert all(l.rng == "philox" and l.scene_offset == a for l in m.layers())
+        assert len({l.philox_seed for l in m.layers()}) == 3          # distinct streams per layer
+        sd = torch.cat([p.detach().flatten() for p in m.parameters()])
+        ref = sd.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(sd, ref), "replicated weights differ across ranks"
+        # scenes come back in global order
+        local = torch.arange(a, b, dtype=torch.float32)[:, None].repeat(1, 3)
+        full = sharding.gather_scenes(local, total)
+        assert torch.equal(full[:, 0], torch.arange(total, dtype=torch.float32))
+        # weak-scaling throughput reduction used by bench.py: MAX over ranks of the step time
+        t = torch.tensor([1.0 + rank], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert t.item() == float(world)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding():
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, 1001), nprocs=2, join=True)
