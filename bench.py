@@ -96,52 +96,59 @@ def kernel_work(b, n, d):
 # clocks sampler (B200_PROFILING.md: sample DURING the timed region)
 # ---------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons DURING the timed region (NVML, 5 ms period;
+    falls back to one `nvidia-smi` query if pynvml is unavailable)."""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20),
+               ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.max_mhz, self.reasons = index, [], None, set()
+        self._stop = threading.Event()
+        self.thread = None
+
+    def _loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                mask = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)) \
+                    if hasattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.005)
+        except Exception:
+            self._smi_once()
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                  "-i", str(self.index)], capture_output=True, text=True, timeout=10).stdout
+            a, b = [float(v) for v in out.strip().split(",")]
+            self.sm.append(a); self.max_mhz = b
+        except Exception:
+            pass
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
-                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
+        time.sleep(0.02)
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6),
-                              ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 # ---------------------------------------------------------------------------
@@ -240,6 +247,9 @@ def main():
     from groupnet_b200 import _lib
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    # torchrun pins OMP_NUM_THREADS=1; the host side of the e2e pipeline (x slice of final_feature)
+    # may use this rank's share of the host cores
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
