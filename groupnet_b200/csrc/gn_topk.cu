@@ -274,9 +274,202 @@ corr_topk_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Small-N fast path (N <= 16: NBA N=11, fish N=8).  At the HBM roofline an SM has ~145 cycles per
+// NBA scene, i.e. ~580 warp-instructions: a shuffle network per 11-element row does not fit.  Here
+//   * one THREAD per feature row loads it (16 independent 128-bit loads), stages it raw in shared
+//     memory and keeps 1 / max(||x||, 1e-12);
+//   * the Gram matrix is computed on the raw rows in 4x4 register blocks over the upper block
+//     triangle and scaled by inv_i * inv_j (differs from normalise-then-dot by ~1e-7);
+//   * one THREAD per correlation row holds the row in registers and runs the all-pairs comparator
+//     network (NP(NP-1)/2 compare-and-count steps, (value desc, index asc) order): rank[n];
+//   * the same thread emits its row of every H_s (rank[n] < k_s): consecutive threads write
+//     consecutive rows, so each H_s block of the group is written contiguously.
+// ---------------------------------------------------------------------------
+template <int NP, bool FROM_CORR>
+__global__ void __launch_bounds__(GN_THREADS)
+corr_topk_small_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
+                       int B, int N, int D, int SG, TopkArgs a, float* __restrict__ corr_out) {
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x;
+  const int ldx = D + 4, ldc = N | 1;                    // odd row stride: conflict-free row-per-thread reads
+  const int rows_max = SG * N;
+  float* xs = smem;
+  float* inv = xs + (FROM_CORR ? 0 : rows_max * ldx);
+  float* cs = inv + ((rows_max + 3) & ~3);
+  const int ngroups = (B + SG - 1) / SG;
+  for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+    const int b0 = grp * SG;
+    const int ns = min(SG, B - b0);
+    const int rows = ns * N;
+    if (!FROM_CORR) {
+      __syncthreads();                                   // previous group's readers are done
+      const int d4 = D >> 2;
+      for (int r = tid; r < rows; r += GN_THREADS) {
+        const float* src = x + (static_cast<size_t>(b0) * N + r) * D;
+        float* dst = xs + r * ldx;
+        float ss = 0.f;
+#pragma unroll 4
+        for (int c = 0; c < d4; ++c) {
+          float4 v = ldg_stream_f4(src + 4 * c);
+          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+          *reinterpret_cast<float4*>(dst + 4 * c) = v;
+        }
+        inv[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+      }
+      __syncthreads();
+      const int nb = (N + 3) >> 2;
+      const int ntri = nb * (nb + 1) / 2;
+      const int ks = (D % 8 == 0) ? 2 : 1;
+      const int ntask = ns * ntri * ks;
+      for (int base = 0; base < ntask; base += GN_THREADS) {
+        int task = base + tid;
+        bool valid = task < ntask;
+        int tt = valid ? task : 0;
+        int half = tt % ks; tt /= ks;
+        int tri = tt % ntri; int g = tt / ntri;
+        int bi = 0, rem = tri;
+        while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+        int bj = bi + rem;
+        const float* qa[4]; const float* qb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          qa[u] = xs + (g * N + min(4 * bi + u, N - 1)) * ldx;
+          qb[u] = xs + (g * N + min(4 * bj + u, N - 1)) * ldx;
+        }
+        float acc[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int w = 0; w < 4; ++w) acc[u][w] = 0.f;
+        const int kbeg = half * (D / ks), kend = kbeg + D / ks;
+        for (int k = kbeg; k < kend; k += 4) {
+          float4 av[4], bv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            av[u] = *reinterpret_cast<const float4*>(qa[u] + k);
+            bv[u] = *reinterpret_cast<const float4*>(qb[u] + k);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              acc[u][w] = fmaf(av[u].x, bv[w].x, acc[u][w]);
+              acc[u][w] = fmaf(av[u].y, bv[w].y, acc[u][w]);
+              acc[u][w] = fmaf(av[u].z, bv[w].z, acc[u][w]);
+              acc[u][w] = fmaf(av[u].w, bv[w].w, acc[u][w]);
+            }
+        }
+        if (ks == 2) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) acc[u][w] += __shfl_xor_sync(0xffffffffu, acc[u][w], 1);
+        }
+        if (valid && half == 0) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              int i = 4 * bi + u, j = 4 * bj + w;
+              if (i < N && j < N) {
+                float c = acc[u][w] * (inv[g * N + i] * inv[g * N + j]);   // commutative: exact symmetry
+                cs[(g * N + i) * ldc + j] = c;
+                if (bi != bj) cs[(g * N + j) * ldc + i] = c;
+              }
+            }
+        }
+      }
+      __syncthreads();
+      if (corr_out != nullptr) {
+        float* dst = corr_out + static_cast<size_t>(b0) * N * N;
+        for (int i = tid; i < rows * N; i += GN_THREADS) {
+          int r = i / N, c = i - r * N;
+          dst[i] = cs[r * ldc + c];
+        }
+      }
+    }
+    // ---- rank + emit: one thread per correlation row
+    for (int r = tid; r < rows; r += GN_THREADS) {
+      float v[NP];
+      int rank[NP];
+      if (FROM_CORR) {
+        const float* src = corr_in + (static_cast<size_t>(b0) * N + r) * N;
+#pragma unroll
+        for (int n = 0; n < NP; ++n) v[n] = (n < N) ? __ldg(src + n) : -INFINITY;
+      } else {
+#pragma unroll
+        for (int n = 0; n < NP; ++n) v[n] = (n < N) ? cs[r * ldc + n] : -INFINITY;
+      }
+#pragma unroll
+      for (int n = 0; n < NP; ++n) rank[n] = 0;
+#pragma unroll
+      for (int j = 1; j < NP; ++j)
+#pragma unroll
+        for (int m = 0; m < j; ++m) {
+          // m < j: m precedes j iff v[m] >= v[j] (ties to the lower index)
+          bool mfirst = v[m] >= v[j];
+          rank[j] += mfirst ? 1 : 0;
+          rank[m] += mfirst ? 0 : 1;
+        }
+      const int sc = r / N, e = r - sc * N;
+      for (int s = 0; s < a.S; ++s) {
+        float* Hs = a.H[s] + static_cast<long long>(b0 + sc) * a.stride[s];
+        if (a.ones[s]) {
+          if (e == 0) {
+#pragma unroll
+            for (int n = 0; n < NP; ++n) if (n < N) Hs[n] = 1.0f;
+          }
+        } else {
+          const int k = a.k[s];
+          float* dst = Hs + e * N;
+#pragma unroll
+          for (int n = 0; n < NP; ++n) if (n < N) dst[n] = rank[n] < k ? 1.0f : 0.0f;
+        }
+      }
+    }
+  }
+}
+
+template <bool FROM_CORR>
+static int launch_topk_small(const float* x, const float* corr, int B, int N, int D,
+                             const TopkArgs& a, float* corr_out, cudaStream_t stream) {
+  auto smem_bytes = [&](int sg) -> size_t {
+    size_t rows = static_cast<size_t>(sg) * N;
+    size_t f = (FROM_CORR ? 0 : rows * (D + 4)) + ((rows + 3) & ~size_t(3)) + rows * (N | 1) + 4;
+    return f * 4;
+  };
+  int SG = GN_THREADS / N; if (SG < 1) SG = 1;
+  while (SG > 1 && smem_bytes(SG) > 72 * 1024) --SG;     // 3 CTAs / SM
+  size_t smem = smem_bytes(SG);
+  if (smem > 227 * 1024) return GN_E_SHAPE;
+  int ngroups = (B + SG - 1) / SG;
+  int ctas_per_sm = smem > 113 * 1024 ? 1 : (smem > 75 * 1024 ? 2 : 3);
+  int grid = ngroups < GN_SM_COUNT * ctas_per_sm ? ngroups : GN_SM_COUNT * ctas_per_sm;
+  if (grid < 1) grid = 1;
+  const int NP = (N + 3) & ~3;
+#define GN_TOPK_SMALL(NPV)                                                                       \
+  case NPV: {                                                                                    \
+    auto kern = corr_topk_small_kernel<NPV, FROM_CORR>;                                          \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         static_cast<int>(smem));                                \
+    if (e != cudaSuccess) return static_cast<int>(e);                                            \
+    { ProfScope ps__(FROM_CORR ? "topk_h" : "corr_topk_h", stream);                              \
+      kern<<<grid, GN_THREADS, smem, stream>>>(x, corr, B, N, D, SG, a, corr_out); }             \
+  } break;
+  switch (NP) {
+    GN_TOPK_SMALL(4) GN_TOPK_SMALL(8) GN_TOPK_SMALL(12) GN_TOPK_SMALL(16)
+    default: return GN_E_SHAPE;
+  }
+#undef GN_TOPK_SMALL
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
+
 template <bool FROM_CORR>
 static int launch_topk(const float* x, const float* corr, int B, int N, int D,
                        const TopkArgs& a, float* corr_out, cudaStream_t stream) {
+  if (N <= 16) return launch_topk_small<FROM_CORR>(x, corr, B, N, D, a, corr_out, stream);
   // scenes per group: enough rows to keep 8 warps busy, bounded by shared memory
   int SG = 96 / N; if (SG < 1) SG = 1; if (SG > 8) SG = 8;
   auto smem_bytes = [&](int sg) -> size_t {
