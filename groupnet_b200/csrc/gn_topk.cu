@@ -287,7 +287,7 @@ corr_topk_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
 //     consecutive rows, so each H_s block of the group is written contiguously.
 // ---------------------------------------------------------------------------
 template <int NP, bool FROM_CORR>
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, 2)
 corr_topk_small_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
                        int B, int N, int D, int SG, TopkArgs a, float* __restrict__ corr_out) {
   extern __shared__ __align__(16) float smem[];
@@ -305,79 +305,147 @@ corr_topk_small_kernel(const float* __restrict__ x, const float* __restrict__ co
     if (!FROM_CORR) {
       __syncthreads();                                   // previous group's readers are done
       const int d4 = D >> 2;
-      for (int r = tid; r < rows; r += GN_THREADS) {
-        const float* src = x + (static_cast<size_t>(b0) * N + r) * D;
-        float* dst = xs + r * ldx;
-        float ss = 0.f;
-#pragma unroll 4
-        for (int c = 0; c < d4; ++c) {
-          float4 v = ldg_stream_f4(src + 4 * c);
-          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
-          *reinterpret_cast<float4*>(dst + 4 * c) = v;
+      // ---- 1. stage the group's (contiguous) x block with cp.async: no register staging
+      {
+        const float* src = x + static_cast<size_t>(b0) * N * D;
+        for (int i = tid; i < rows * d4; i += GN_THREADS) {
+          int r = i / d4, c = i - r * d4;
+          cp_async16(xs + r * ldx + 4 * c, src + static_cast<size_t>(r) * D + 4 * c);
         }
-        inv[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        cp_async_commit();
+        cp_async_wait<0>();
       }
       __syncthreads();
-      const int nb = (N + 3) >> 2;
-      const int ntri = nb * (nb + 1) / 2;
-      const int ks = (D % 8 == 0) ? 2 : 1;
-      const int ntask = ns * ntri * ks;
-      for (int base = 0; base < ntask; base += GN_THREADS) {
-        int task = base + tid;
-        bool valid = task < ntask;
-        int tt = valid ? task : 0;
-        int half = tt % ks; tt /= ks;
-        int tri = tt % ntri; int g = tt / ntri;
-        int bi = 0, rem = tri;
-        while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
-        int bj = bi + rem;
-        const float* qa[4]; const float* qb[4];
+      if (NP <= 12 && (D & 7) == 0) {
+        // ---- 2a. raw Gram in k-slices: 4 adjacent lanes per scene, lane t owns float2 columns
+        //          {t, t+4, ...}; every x element is read from shared memory exactly once.  The
+        //          squared norms are the Gram diagonal.  Partial sums are reduced over the 4 lanes.
+        constexpr int NPAIR = NP * (NP + 1) / 2;
+        const int d2 = D >> 1;
+        const int ntask = ns * 4;
+        for (int base = 0; base < ntask; base += GN_THREADS) {
+          const int task = base + tid;
+          const bool valid = task < ntask;
+          const int g = (valid ? task : 0) >> 2, t = task & 3;
+          const float* xg = xs + g * N * ldx;
+          float acc[NPAIR];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          qa[u] = xs + (g * N + min(4 * bi + u, N - 1)) * ldx;
-          qb[u] = xs + (g * N + min(4 * bj + u, N - 1)) * ldx;
-        }
-        float acc[4][4];
+          for (int p = 0; p < NPAIR; ++p) acc[p] = 0.f;
+#pragma unroll 2
+          for (int c = t; c < d2; c += 4) {
+            float2 v[NP];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+            for (int r = 0; r < NP; ++r)
+              v[r] = (r < N) ? *reinterpret_cast<const float2*>(xg + r * ldx + 2 * c) : make_float2(0.f, 0.f);
+            int p = 0;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) acc[u][w] = 0.f;
-        const int kbeg = half * (D / ks), kend = kbeg + D / ks;
-        for (int k = kbeg; k < kend; k += 4) {
-          float4 av[4], bv[4];
+            for (int i = 0; i < NP; ++i)
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            av[u] = *reinterpret_cast<const float4*>(qa[u] + k);
-            bv[u] = *reinterpret_cast<const float4*>(qb[u] + k);
+              for (int j = i; j < NP; ++j, ++p) {
+                acc[p] = fmaf(v[i].x, v[j].x, acc[p]);
+                acc[p] = fmaf(v[i].y, v[j].y, acc[p]);
+              }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+          for (int p = 0; p < NPAIR; ++p) {
+            acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 1);
+            acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 2);
+          }
+          if (valid) {
+            // every lane holds all sums; lane t writes the pairs with p % 4 == t (mirrored)
+            float invn[NP];
+            int p = 0;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              acc[u][w] = fmaf(av[u].x, bv[w].x, acc[u][w]);
-              acc[u][w] = fmaf(av[u].y, bv[w].y, acc[u][w]);
-              acc[u][w] = fmaf(av[u].z, bv[w].z, acc[u][w]);
-              acc[u][w] = fmaf(av[u].w, bv[w].w, acc[u][w]);
+            for (int i = 0; i < NP; ++i) {
+              invn[i] = 1.0f / fmaxf(sqrtf(acc[p]), 1e-12f);
+              p += NP - i;
             }
-        }
-        if (ks == 2) {
+            p = 0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
+            for (int i = 0; i < NP; ++i)
 #pragma unroll
-            for (int w = 0; w < 4; ++w) acc[u][w] += __shfl_xor_sync(0xffffffffu, acc[u][w], 1);
-        }
-        if (valid && half == 0) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              int i = 4 * bi + u, j = 4 * bj + w;
-              if (i < N && j < N) {
-                float c = acc[u][w] * (inv[g * N + i] * inv[g * N + j]);   // commutative: exact symmetry
-                cs[(g * N + i) * ldc + j] = c;
-                if (bi != bj) cs[(g * N + j) * ldc + i] = c;
+              for (int j = i; j < NP; ++j, ++p) {
+                if ((p & 3) == t && i < N && j < N) {
+                  const float c = acc[p] * (invn[i] * invn[j]);
+                  cs[(g * N + i) * ldc + j] = c;
+                  cs[(g * N + j) * ldc + i] = c;
+                }
               }
+          }
+        }
+      } else {
+        // ---- 2b. generic: row norms (one thread per row from smem), then 4x4 register blocks
+        for (int r = tid; r < rows; r += GN_THREADS) {
+          const float* src = xs + r * ldx;
+          float ss = 0.f;
+          for (int c = 0; c < d4; ++c) {
+            float4 v = *reinterpret_cast<const float4*>(src + 4 * c);
+            ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+          }
+          inv[r] = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+        }
+        __syncthreads();
+        const int nb = (N + 3) >> 2;
+        const int ntri = nb * (nb + 1) / 2;
+        const int ks = (D % 8 == 0) ? 2 : 1;
+        const int ntask = ns * ntri * ks;
+        for (int base = 0; base < ntask; base += GN_THREADS) {
+          int task = base + tid;
+          bool valid = task < ntask;
+          int tt = valid ? task : 0;
+          int half = tt % ks; tt /= ks;
+          int tri = tt % ntri; int g = tt / ntri;
+          int bi = 0, rem = tri;
+          while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+          int bj = bi + rem;
+          const float* qa[4]; const float* qb[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            qa[u] = xs + (g * N + min(4 * bi + u, N - 1)) * ldx;
+            qb[u] = xs + (g * N + min(4 * bj + u, N - 1)) * ldx;
+          }
+          float acc[4][4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) acc[u][w] = 0.f;
+          const int kbeg = half * (D / ks), kend = kbeg + D / ks;
+          for (int k = kbeg; k < kend; k += 4) {
+            float4 av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              av[u] = *reinterpret_cast<const float4*>(qa[u] + k);
+              bv[u] = *reinterpret_cast<const float4*>(qb[u] + k);
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                acc[u][w] = fmaf(av[u].x, bv[w].x, acc[u][w]);
+                acc[u][w] = fmaf(av[u].y, bv[w].y, acc[u][w]);
+                acc[u][w] = fmaf(av[u].z, bv[w].z, acc[u][w]);
+                acc[u][w] = fmaf(av[u].w, bv[w].w, acc[u][w]);
+              }
+          }
+          if (ks == 2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int w = 0; w < 4; ++w) acc[u][w] += __shfl_xor_sync(0xffffffffu, acc[u][w], 1);
+          }
+          if (valid && half == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                int i = 4 * bi + u, j = 4 * bj + w;
+                if (i < N && j < N) {
+                  float c = acc[u][w] * (inv[g * N + i] * inv[g * N + j]);   // commutative: exact symmetry
+                  cs[(g * N + i) * ldc + j] = c;
+                  if (bi != bj) cs[(g * N + j) * ldc + i] = c;
+                }
+              }
+          }
         }
       }
       __syncthreads();
@@ -440,11 +508,11 @@ static int launch_topk_small(const float* x, const float* corr, int B, int N, in
     return f * 4;
   };
   int SG = GN_THREADS / N; if (SG < 1) SG = 1;
-  while (SG > 1 && smem_bytes(SG) > 72 * 1024) --SG;     // 3 CTAs / SM
+  while (SG > 1 && smem_bytes(SG) > 100 * 1024) --SG;    // 2 CTAs / SM (register-limited)
   size_t smem = smem_bytes(SG);
   if (smem > 227 * 1024) return GN_E_SHAPE;
   int ngroups = (B + SG - 1) / SG;
-  int ctas_per_sm = smem > 113 * 1024 ? 1 : (smem > 75 * 1024 ? 2 : 3);
+  int ctas_per_sm = smem > 113 * 1024 ? 1 : 2;
   int grid = ngroups < GN_SM_COUNT * ctas_per_sm ? ngroups : GN_SM_COUNT * ctas_per_sm;
   if (grid < 1) grid = 1;
   const int NP = (N + 3) & ~3;
