@@ -76,6 +76,8 @@ def kernel_work(b, n, d):
             add("edge2node_hyper", 2 * rn * e * d, (re * (d + n) + rn * d) * 4, "hbm")
             add("node_post", 2 * rn * (2 * d * 128 + 128 * d), rn * 3 * d * 4, "tensor")
         # ---- bf16 tensor-core path kernels
+        add("node_pre_chain_tc", 2 * rn * (d * 256 + 256 * 64 + 64 * 64), rn * (d + 128) * 4, "tensor")
+        add("node_post_chain_tc", 2 * rn * (2 * d * 128 + 128 * d), rn * 3 * d * 4, "tensor")
         add("node_mlp0_tc", 2 * rn * d * 256, rn * (d * 4 + 256 * 2), "tensor")
         add("node_mlp1_tc", 2 * rn * 256 * 64, rn * (256 * 2 + 64 * 4), "tensor")
         add("att_proj_tc", 2 * rn * 64 * 64, rn * 128 * 4, "tensor")

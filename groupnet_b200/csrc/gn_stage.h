@@ -39,6 +39,23 @@ bool hyper_agg_fits(int D, int T);
 int launch_hyper_agg_tc(const float* eo, const float* edge_feat, long long R, int T,
                         const gn_stage_weights* w, float* ef, cudaStream_t st);
 
+// fused node-level GEMM chains on tensor cores (gn_node_chain_tc.cu)
+struct NodeChainStep {
+  const __nv_bfloat16* W;     // canonical (N x K)
+  const float* bias;          // [N] or null
+  int K, N, relu;
+  float* out; long long ldo; int out_col0;   // optional fp32 store of this step's output
+};
+struct NodeChainArgs {
+  const float* A0; long long lda0; int K0;   // input columns [0, K0)
+  const float* A1; long long lda1; int K1;   // input columns [K0, K0+K1), optional
+  float a_div;                               // != 0: input divided by it
+  int nsteps;
+  NodeChainStep step[3];
+  long long R;
+};
+int launch_node_chain_tc(const NodeChainArgs& a, const char* name, cudaStream_t st);
+
 // stage driver (gn_stage_simt.cu)
 int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h, const float* H,
               const float* U, float* node_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -582,33 +582,46 @@ edge2node_pair_kernel(const float* __restrict__ P, const float* __restrict__ edg
 
 // ===========================================================================
 // k5b: edge2node, hyper: agg[n][:] = sum_e H[e,n] ef[e][:]   (:267)
+// A CTA of 128 threads owns SC whole scenes at a time; their ef rows and
+// incidence rows (both contiguous in HBM) are staged in shared memory; one
+// thread per (node, 4-column group) accumulates over the scene's edges.
 // ===========================================================================
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(N2H_THREADS)
 edge2node_hyper_kernel(const float* __restrict__ ef, const float* __restrict__ H,
-                       int B, int N, int E, int D, long long hstride, float* __restrict__ agg) {
+                       int B, int N, int E, int D, long long hstride, int SC, float* __restrict__ agg) {
   extern __shared__ __align__(16) float smem[];
-  const int ldn = N + 1, d4 = D >> 2;
-  float* Hs = smem;                                   // [E][N+1]
+  const int ldn = N + 1, lde = D + 4, d4 = D >> 2;
+  float* es = smem;                                   // [SC*E][D+4]
+  float* Hs = es + SC * E * lde;                      // [SC*E][N+1]
   const int tid = threadIdx.x;
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  const int ntiles = (B + SC - 1) / SC;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0s = tile * SC, ns = min(SC, B - b0s);
+    const int ne = ns * E, nn = ns * N;
     __syncthreads();
-    for (int i = tid; i < E * N; i += GN_THREADS) {
-      int e = i / N, n = i - e * N;
-      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b) * hstride + i);
+    for (int i = tid; i < ne * d4; i += N2H_THREADS) {
+      int e = i / d4, c = i - e * d4;
+      *reinterpret_cast<float4*>(es + e * lde + 4 * c) =
+          ldg_f4(ef + (static_cast<size_t>(b0s) * E + e) * D + 4 * c);
+    }
+    for (int i = tid; i < ne * N; i += N2H_THREADS) {
+      int e = i / N, n = i - e * N, sc = e / E;
+      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + static_cast<size_t>(e - sc * E) * N + n);
     }
     __syncthreads();
-    for (int i = tid; i < N * d4; i += GN_THREADS) {
-      int n = i / d4, c4 = i - n * d4;
+    for (int i = tid; i < nn * d4; i += N2H_THREADS) {
+      int nr = i / d4, c4 = i - nr * d4;              // node row in tile, column group
+      int sc = nr / N, n = nr - sc * N;
       float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int e = 0; e < E; ++e) {
-        float w = Hs[e * ldn + n];
+        float w = Hs[(sc * E + e) * ldn + n];
         if (w != 0.f) {
-          float4 v = ldg_f4(ef + (static_cast<size_t>(b) * E + e) * D + 4 * c4);
+          float4 v = *reinterpret_cast<const float4*>(es + (sc * E + e) * lde + 4 * c4);
           o.x = fmaf(w, v.x, o.x); o.y = fmaf(w, v.y, o.y);
           o.z = fmaf(w, v.z, o.z); o.w = fmaf(w, v.w, o.w);
         }
       }
-      *reinterpret_cast<float4*>(agg + (static_cast<size_t>(b) * N + n) * D + 4 * c4) = o;
+      *reinterpret_cast<float4*>(agg + (static_cast<size_t>(b0s) * N + nr) * D + 4 * c4) = o;
     }
   }
 }
@@ -821,10 +834,17 @@ static int launch_edge2node_pair(const float* P, const float* efeat, int B, int 
 
 static int launch_edge2node_hyper(const float* ef, const float* H, int B, int N, int E, int D,
                                   long long hstride, float* agg, cudaStream_t st) {
-  size_t smem = static_cast<size_t>(E) * (N + 1) * 4;
+  auto bytes = [&](int sc) -> size_t {
+    return (static_cast<size_t>(sc) * E * (D + 4) + static_cast<size_t>(sc) * E * (N + 1)) * 4;
+  };
+  int SC = N2H_THREADS / N; if (SC < 1) SC = 1; if (SC > 16) SC = 16;
+  while (SC > 1 && bytes(SC) > 48 * 1024) --SC;
+  size_t smem = bytes(SC);
   GN_TRY(set_smem(edge2node_hyper_kernel, smem));
+  const int ntiles = (B + SC - 1) / SC;
+  int grid = ntiles < GN_SM_COUNT * 4 ? ntiles : GN_SM_COUNT * 4;
   { ProfScope ps__("edge2node_hyper", st);
-    edge2node_hyper_kernel<<<grid_for(B, smem), GN_THREADS, smem, st>>>(ef, H, B, N, E, D, hstride, agg); }
+    edge2node_hyper_kernel<<<grid, N2H_THREADS, smem, st>>>(ef, H, B, N, E, D, hstride, SC, agg); }
   GN_LAUNCH_CHECK();
   return GN_OK;
 }
@@ -872,7 +892,16 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
               !w->tc_post_w0 || !w->tc_post_w1)) return GN_E_NULL;
 
   // ---- k1: node-level prologue: x', pq (and P for the pairwise collapse)
-  if (tcn) {
+  const bool chain_ok = tcn && D == 64 && (c->Dout % 32 == 0) && c->Dout <= 128;
+  if (chain_ok && (!c->pairwise || fused_agg)) {
+    NodeChainArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A0 = h; a.lda0 = D; a.K0 = D; a.R = R; a.nsteps = 3;
+    a.step[0] = {static_cast<const __nv_bfloat16*>(w->tc_node_w0), w->node_b0, D, 256, 1, nullptr, 0, 0};
+    a.step[1] = {static_cast<const __nv_bfloat16*>(w->tc_node_w1), w->node_b1, 256, 64, 0, xprime, 64, 0};
+    a.step[2] = {static_cast<const __nv_bfloat16*>(w->tc_att_wpq), nullptr, 64, 64, 0, pq, 64, 0};
+    GN_TRY(launch_node_chain_tc(a, "node_pre_chain_tc", st));
+  } else if (tcn) {
     TcLinArgs a = lin_args();
     a.A0 = h; a.a0_is_f32 = 1; a.lda0 = D; a.K0 = D; a.R = R;
     a.W = static_cast<const __nv_bfloat16*>(w->tc_node_w0); a.Ntot = 256; a.N = 256;
@@ -997,6 +1026,16 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
       a.out = agg; a.out_is_f32 = 1; a.ldo = D;
       GN_TRY(launch_tc_linear(a, "agg_out_tc", st));
     }
+    if (chain_ok) {
+      NodeChainArgs n;
+      memset(&n, 0, sizeof(n));
+      n.A0 = agg; n.lda0 = D; n.K0 = D; n.A1 = h; n.lda1 = D; n.K1 = D; n.a_div = static_cast<float>(N);
+      n.R = R; n.nsteps = 2;
+      n.step[0] = {static_cast<const __nv_bfloat16*>(w->tc_post_w0), w->post_b0, 2 * D, 128, 1, nullptr, 0, 0};
+      n.step[1] = {static_cast<const __nv_bfloat16*>(w->tc_post_w1), w->post_b1, 128, c->Dout, 0, node_out, ld_out, 0};
+      GN_TRY(launch_node_chain_tc(n, "node_post_chain_tc", st));
+      return GN_OK;
+    }
     a = lin_args();
     a.A0 = agg; a.a0_is_f32 = 1; a.lda0 = D; a.K0 = D; a.A1 = h; a.lda1 = D; a.K1 = D;
     a.a_div = static_cast<float>(N); a.R = R;
@@ -1045,8 +1084,10 @@ int stage_launch_count(const gn_stage_cfg* c) {
   const int fused = (c->precision == GN_BF16_TC && c->pairwise && edge_chain_pair_fits(c->N)) ? 1 : 0;
   if (!p.tc_nodes) return (c->pairwise ? 5 : 6) - fused;
   const int chunks = (c->T * 128 + 255) / 256;
-  if (c->pairwise && pair_agg_fits(c->N, c->D, c->T)) return 3 + (2 - fused) + 1 + 2;
-  if (!c->pairwise && hyper_agg_fits(c->D, c->T)) return 3 + 1 + 1 + 1 + 1 + 2;
+  const bool chain = c->D == 64 && (c->Dout % 32 == 0) && c->Dout <= 128;
+  const int pre = chain ? 1 : 3, post = chain ? 1 : 2;
+  if (c->pairwise && pair_agg_fits(c->N, c->D, c->T)) return pre + (2 - fused) + 1 + post;
+  if (!c->pairwise && hyper_agg_fits(c->D, c->T)) return pre + 1 + 1 + 1 + 1 + post;
   return c->pairwise ? (3 + chunks) + (2 - fused) + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
 }
 
