@@ -29,6 +29,9 @@ EXPORTS = (
     "gn_stage_workspace_bytes",
     "gn_stage_fwd",
     "gn_stage_launch_count",
+    "gn_stage_saved_offsets",
+    "gn_stage_bwd_workspace_bytes",
+    "gn_stage_bwd",
     "gn_profile_enable",
     "gn_profile_collect",
 )
@@ -62,6 +65,21 @@ class StageCfg(C.Structure):
         ("out_ld", C.c_int32), ("h_stride", C.c_int32),
         ("seed", C.c_uint64), ("scene_offset", C.c_int64),
     ]
+
+
+class Lin(C.Structure):
+    """struct gn_lin."""
+    _fields_ = [("W", C.c_void_p), ("b", C.c_void_p), ("dW", C.c_void_p), ("db", C.c_void_p),
+                ("N", C.c_int32), ("K", C.c_int32)]
+
+
+class TrainParams(C.Structure):
+    """struct gn_train_params."""
+    _fields_ = [("node0", Lin), ("node1", Lin), ("attpq", Lin),
+                ("att_b0", C.c_void_p), ("att_w1", C.c_void_p), ("att_b1", C.c_void_p),
+                ("d_att_b0", C.c_void_p), ("d_att_w1", C.c_void_p), ("d_att_b1", C.c_void_p),
+                ("init0", Lin), ("init1", Lin), ("dist0", Lin), ("dist1", Lin), ("fac0", Lin), ("fac1", Lin),
+                ("agg0", Lin * 15), ("agg1", Lin * 15), ("post0", Lin), ("post1", Lin)]
 
 
 _lock = threading.Lock()
@@ -105,6 +123,14 @@ def load() -> C.CDLL:
         lib.gn_stage_fwd.argtypes = [
             C.POINTER(StageCfg), C.POINTER(StageWeights), C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.gn_stage_saved_offsets.restype = C.c_int
+        lib.gn_stage_saved_offsets.argtypes = [C.POINTER(StageCfg), C.POINTER(C.c_size_t)]
+        lib.gn_stage_bwd_workspace_bytes.restype = C.c_size_t
+        lib.gn_stage_bwd_workspace_bytes.argtypes = [C.POINTER(StageCfg)]
+        lib.gn_stage_bwd.restype = C.c_int
+        lib.gn_stage_bwd.argtypes = [C.POINTER(StageCfg), C.POINTER(TrainParams), C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                     C.c_void_p]
         lib.gn_profile_enable.restype = None
         lib.gn_profile_enable.argtypes = [C.c_int]
         lib.gn_profile_collect.restype = C.c_int

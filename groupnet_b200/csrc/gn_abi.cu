@@ -107,3 +107,30 @@ extern "C" int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
   return gn::stage_fwd(cfg, w, h_in, H, U, node_out, dist_out, workspace, workspace_bytes, st);
 
 }
+
+extern "C" int gn_stage_saved_offsets(const gn_stage_cfg* cfg, size_t* out5) {
+  if (!cfg || !out5) return GN_E_NULL;
+  return gn::stage_saved_offsets(cfg, out5);
+}
+
+extern "C" size_t gn_stage_bwd_workspace_bytes(const gn_stage_cfg* cfg) {
+  if (!cfg) return 0;
+  return gn::stage_bwd_workspace_bytes(cfg);
+}
+
+extern "C" int gn_stage_bwd(const gn_stage_cfg* cfg, const gn_train_params* params,
+                            const float* h_in, const float* H, const void* fwd_workspace,
+                            const float* d_node_out, int64_t ld_dout, const float* d_dist, float* d_h,
+                            void* workspace, size_t workspace_bytes, gn_stream_t stream) {
+  if (!cfg || !params || !h_in || !fwd_workspace || !d_node_out || !d_h || !workspace) return GN_E_NULL;
+  if (cfg->precision != GN_FP32) return GN_E_PRECISION;
+  if (!cfg->pairwise && !H) return GN_E_NULL;
+  size_t off[5];
+  int rc = gn::stage_saved_offsets(cfg, off);
+  if (rc != GN_OK) return rc;
+  const char* fw = static_cast<const char*>(fwd_workspace);
+  auto F = [&](size_t o) { return reinterpret_cast<const float*>(fw + o); };
+  return gn::stage_bwd(cfg, params, h_in, H, F(off[0]), F(off[1]), F(off[2]), F(off[3]), F(off[4]),
+                       d_node_out, ld_dout, d_dist, d_h, workspace, workspace_bytes,
+                       static_cast<cudaStream_t>(stream));
+}

@@ -60,6 +60,14 @@ int launch_node_chain_tc(const NodeChainArgs& a, const char* name, cudaStream_t 
 int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h, const float* H,
               const float* U, float* node_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t stage_workspace_bytes(const gn_stage_cfg* c);
+int stage_saved_offsets(const gn_stage_cfg* c, size_t* out5);
+
+// backward of one stage, fp32 (gn_train.cu)
+size_t stage_bwd_workspace_bytes(const gn_stage_cfg* c);
+int stage_bwd(const gn_stage_cfg* c, const gn_train_params* P, const float* h, const float* H,
+              const float* xprime, const float* pq, const float* edges, const float* efeat, const float* agg,
+              const float* d_out, long long ld_dout, const float* d_dist, float* d_h,
+              void* ws, size_t ws_bytes, cudaStream_t st);
 int stage_launch_count(const gn_stage_cfg* c);
 
 }  // namespace gn

@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 node_post_kernel(const float* __restrict__ h, const float* __restrict__ aggin,
                  const float* __restrict__ G, const float* __restrict__ S,
                  int R, int N, int D, int Dc, int K2p, int T, int Dout, int Doutc, int pairwise,
-                 gn_stage_weights W, float* __restrict__ out, int ld_out) {
+                 gn_stage_weights W, float* __restrict__ out, int ld_out, float* __restrict__ agg_out) {
   constexpr int LD = TM + 4, RM = TM / 16, RN = TN / 16;
   extern __shared__ __align__(16) float smem[];
   float* incT = smem;
@@ -682,6 +682,7 @@ node_post_kernel(const float* __restrict__ h, const float* __restrict__ aggin,
               float bsum = 0.f;
               for (int t = 0; t < T; ++t) bsum = fmaf(Ss[r * 16 + t], __ldg(W.agg_b1 + t * D + col), bsum);
               incT[col * LD + r] = __fdiv_rn(v + bsum, fN);
+              if (agg_out != nullptr && r < nrows) agg_out[static_cast<size_t>(row0 + r) * D + col] = v + bsum;
             }
           });
         }
@@ -754,7 +755,7 @@ static int make_plan(const gn_stage_cfg* c, StagePlan& p) {
     p.off_P = take(R * c->T * 128 * 4);
     p.off_G = take(R * c->T * 128 * 4);
     p.off_S = take(R * 16 * 4);
-    if (p.tc_nodes) p.off_agg = take(R * c->D * 4);
+    p.off_agg = take(R * c->D * 4);
   } else {
     p.off_eo = take(RE * c->D * 4);
     p.off_ef = take(RE * c->D * 4);
@@ -1055,20 +1056,27 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
       auto kern = node_post_kernel<TM, 64, 1>;
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("node_post", st);
-        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out); }
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out, c->pairwise ? agg : nullptr); }
     } else if (D <= 128) {
       auto kern = node_post_kernel<TM, 128, 1>;
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("node_post", st);
-        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out); }
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out, c->pairwise ? agg : nullptr); }
     } else {
       auto kern = node_post_kernel<TM, 128, 2>;
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("node_post", st);
-        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out); }
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out, c->pairwise ? agg : nullptr); }
     }
     GN_LAUNCH_CHECK();
   }
+  return GN_OK;
+}
+
+int stage_saved_offsets(const gn_stage_cfg* c, size_t* out5) {
+  StagePlan p;
+  GN_TRY(make_plan(c, p));
+  out5[0] = p.off_xprime; out5[1] = p.off_pq; out5[2] = p.off_edges; out5[3] = p.off_efeat; out5[4] = p.off_agg;
   return GN_OK;
 }
 

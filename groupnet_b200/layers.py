@@ -170,6 +170,8 @@ class _MessagePassingLayer(nn.Module):
         ops._require_cuda_f32(h_states, "h_states")
         if h_states.dim() != 3:
             raise ValueError("h_states must be (B, N, h_dim)")
+        if torch.is_grad_enabled() and (h_states.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._run_train(h_states, inc, e, noise, node_out, want_dist)
         h = h_states.detach().contiguous()
         b, n, d = h.shape
         if d != self.h_dim:
@@ -226,6 +228,36 @@ class _MessagePassingLayer(nn.Module):
                                   dst, dist_out[b0:b1] if (s == 0 and dist_out is not None) else None, ws)
                 cur = dst
         return node_out, dist_out
+
+    def _run_train(self, h_states, inc, e, noise, node_out, want_dist):
+        """Differentiable forward: every stage goes through autograd.StageFunction (fp32 kernels
+        forward, gn_stage_bwd backward).  The tensor-core path is inference-only."""
+        from .autograd import StageFunction, stage_param_list
+        b, n, d = h_states.shape
+        if d != self.h_dim:
+            raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied (h_dim {d} != {self.h_dim})")
+        dev = h_states.device
+        stages = self._packs.get(self, dev)
+        n_stage = len(stages)
+        t = self.edge_types
+        us = self._noise_list(noise, b, e, n_stage, dev)
+        if us is None:
+            seed = (self.philox_seed + 0x9E3779B97F4A7C15 * self._philox_calls) & _MASK64
+            self._philox_calls += 1
+        else:
+            seed = 0
+        cur = h_states
+        dist0 = None
+        for s in range(n_stage):
+            meta = (b, n, d, stages[s].dout, e, t, 1 if self._pairwise else 0,
+                    _lib.GN_NOISE_GIVEN if us is not None else _lib.GN_NOISE_PHILOX, s, seed, self.scene_offset)
+            cur, dist = StageFunction.apply(cur, inc, None if us is None else us[s], meta, stages[s],
+                                            *stage_param_list(self, s))
+            if s == 0:
+                dist0 = dist
+        if node_out is not None:
+            node_out.copy_(cur)
+        return cur, (dist0 if want_dist else None)
 
     def launches_per_forward(self, batch: int, n: int, e: int) -> int:
         """Kernel launches one forward issues (for bench.py's gpu_launches)."""

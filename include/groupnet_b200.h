@@ -181,6 +181,49 @@ int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
  * gn_stage_fwd call (for bench.py's gpu_launches accounting). */
 int gn_stage_launch_count(const gn_stage_cfg* cfg);
 
+/* ---- training: backward of one stage (fp32) -------------------------------------------------
+ * Gradients flow to h_in and to every parameter the forward uses; H, corr and the noise get none
+ * (model/MS_HGNN_batch.py:382 uses top-k indices only).  Parameters are read in their native
+ * nn.Linear layout (weight (N_out, K) row-major, bias (N_out)); dW / db are ACCUMULATED into the
+ * caller's buffers (zero them for a fresh gradient).  A NULL dW skips that parameter. */
+typedef struct gn_lin {
+  const float* W;   /* (N, K) */
+  const float* b;   /* (N) or NULL */
+  float* dW;        /* (N, K), accumulated; may be NULL */
+  float* db;        /* (N), accumulated; may be NULL */
+  int32_t N, K;
+} gn_lin;
+
+typedef struct gn_train_params {
+  gn_lin node0, node1;            /* node2edge_start_mlp[i].layers.{0,1} */
+  gn_lin attpq;                   /* (64, 64): rows 0..31 = attention W0[:, :64], rows 32..63 = W0[:, 64:]; no bias */
+  const float* att_b0;            /* attention_mlp[i].layers.0.bias (32) */
+  const float* att_w1;            /* attention_mlp[i].layers.1.weight (32) */
+  const float* att_b1;            /* attention_mlp[i].layers.1.bias (1) */
+  float* d_att_b0; float* d_att_w1; float* d_att_b1;   /* accumulated */
+  gn_lin init0, init1, dist0, dist1, fac0, fac1;       /* MLP_dict_softmax */
+  gn_lin agg0[15], agg1[15];      /* edge_aggregation.agg_mlp[t].layers.{0,1}, t < T */
+  gn_lin post0, post1;            /* closing MLP */
+} gn_train_params;
+
+/* Byte offsets, inside the workspace gn_stage_fwd (precision GN_FP32) was given, of the tensors the
+ * backward needs: out5 = { x' (B*N,64), pq (B*N,64), edges (B*E,64), edge_feat (B*E,T), agg (B*N,D) }.
+ * Keep that workspace alive until gn_stage_bwd has run. */
+int gn_stage_saved_offsets(const gn_stage_cfg* cfg, size_t* out5);
+
+/* Scratch bytes gn_stage_bwd needs. */
+size_t gn_stage_bwd_workspace_bytes(const gn_stage_cfg* cfg);
+
+/* Backward of gn_stage_fwd (cfg->precision must be GN_FP32).
+ *   fwd_workspace  the forward's workspace (read only)
+ *   d_node_out     (B,N,Dout) gradient of node_out, rows ld_dout floats apart
+ *   d_dist         optional (B,E,T) gradient of dist_out, may be NULL
+ *   d_h            (B,N,D) gradient of h_in (overwritten) */
+int gn_stage_bwd(const gn_stage_cfg* cfg, const gn_train_params* params,
+                 const float* h_in, const float* H, const void* fwd_workspace,
+                 const float* d_node_out, int64_t ld_dout, const float* d_dist, float* d_h,
+                 void* workspace, size_t workspace_bytes, gn_stream_t stream);
+
 /* Profiling hook (the only process-wide state in the library; off by default).
  * While enabled every kernel launch is bracketed by CUDA events on its launch
  * stream.  gn_profile_collect synchronises those events, sums the durations by

@@ -65,9 +65,14 @@ def rel_err(got, ref) -> float:
     return (got - ref).abs().max().item() / (den if den > 0 else 1.0)
 
 
-def assert_close(got, ref, rel, what=""):
-    e = rel_err(got, ref)
-    assert e <= rel, f"{what}: max|d|/max|ref| = {e:.3e} > {rel:.1e}"
+def assert_close(got, ref, rel, what="", atol=0.0):
+    """max|got - ref| <= rel * max|ref| + atol  (atol: floor for tensors that are analytically ~0)."""
+    got64 = torch.as_tensor(got, dtype=torch.float64).cpu()
+    ref64 = torch.as_tensor(ref, dtype=torch.float64).cpu()
+    assert got64.shape == ref64.shape, (got64.shape, ref64.shape)
+    err = (got64 - ref64).abs().max().item() if ref64.numel() else 0.0
+    bound = rel * (ref64.abs().max().item() if ref64.numel() else 0.0) + atol
+    assert err <= bound, f"{what}: max|d| = {err:.3e} > {bound:.3e} (rel {rel:.1e}, atol {atol:.1e})"
 
 
 def have_reference() -> bool:

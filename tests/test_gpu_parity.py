@@ -13,6 +13,17 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+@pytest.fixture(autouse=True)
+def _inference_mode(request):
+    """Forward parity tests run like the reference's eval scripts (torch.set_grad_enabled(False),
+    test_nba.py:571); tests marked `train` keep autograd on."""
+    if "train" in request.keywords:
+        yield
+    else:
+        with torch.no_grad():
+            yield
+
+
 def test_native_library_is_loaded():
     lib = _lib.load()
     assert lib.gn_abi_version() == 1
@@ -334,3 +345,76 @@ def test_bf16_tc_large_batch_vs_fp32_path():
     assert_close(n16, n32, BF16_REL, "node_feat bf16 vs fp32")
     n16b, f16b = m(h, noise=[u])
     assert torch.equal(n16, n16b) and torch.equal(f16, f16b)          # deterministic
+
+
+# ---- T7: backward (gn_stage_bwd) vs torch autograd through the CPU oracle ---------------------
+@pytest.mark.train
+@pytest.mark.parametrize("kind,n,d,bo,scale,layers,b", [
+    ("pairwise", 5, 64, 64, 0, 1, 7), ("hyper", 6, 64, 64, 3, 1, 9), ("hyper", 6, 64, 64, 6, 1, 9),
+    ("pairwise", 11, 64, 64, 0, 1, 33), ("hyper", 11, 64, 64, 5, 1, 33),
+    ("pairwise", 4, 32, 48, 0, 2, 5), ("hyper", 7, 128, 64, 2, 2, 6),
+])
+def test_backward_matches_oracle_autograd(kind, n, d, bo, scale, layers, b):
+    torch.manual_seed(500 + n + d + layers)
+    if kind == "pairwise":
+        m = gb.MS_HGNN_oridinary(16, d, 64, bo, batch_norm=0, nmp_layers=layers)
+        e, t = n * n, 6
+    else:
+        m = gb.MS_HGNN_hyper(d, d, 64, bo, batch_norm=0, nmp_layers=layers, scale=scale)
+        e, t = (1 if scale == n else n), 10
+    gen = torch.Generator().manual_seed(b)
+    h = torch.randn(b, n, d, generator=gen)
+    noise = [torch.rand(b, e, t, generator=gen) for _ in range(layers)]
+    w_node = torch.randn(b, n, bo, generator=gen)
+    w_fac = torch.randn(b, e, t, generator=gen)
+    # reference gradients: torch autograd through the CPU oracle on the same weights
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    h_ref = h.clone().requires_grad_(True)
+    if kind == "pairwise":
+        node_r, fac_r = O.forward_pairwise(sd, h_ref, noise, nmp_layers=layers)
+    else:
+        corr = O.feature_correlation(h)
+        node_r, fac_r, _ = O.forward_hyper(sd, h_ref, corr, scale, noise, nmp_layers=layers)
+    ((node_r * w_node).sum() + (fac_r * w_fac).sum()).backward()
+    # ours
+    m = m.to(DEV).train()
+    h_dev = h.to(DEV).requires_grad_(True)
+    if kind == "pairwise":
+        node, fac = m(h_dev, noise=[u.to(DEV) for u in noise])
+    else:
+        node, fac, hm = m(h_dev, corr.to(DEV), noise=[u.to(DEV) for u in noise])
+        assert not hm.requires_grad
+    assert node.requires_grad and fac.requires_grad
+    assert_close(node, node_r.detach(), FP32_REL, "train-mode node_feat")
+    ((node * w_node.to(DEV)).sum() + (fac * w_fac.to(DEV)).sum()).backward()
+    assert_close(h_dev.grad, h_ref.grad, 1e-4, "d h_states", atol=1e-7)
+    used, unused = 0, 0
+    for name, p in m.named_parameters():
+        ref_g = sd[name].grad
+        if ref_g is None:
+            assert p.grad is None, f"{name}: never-used parameter must keep grad None"
+            unused += 1
+        else:
+            assert p.grad is not None, f"{name}: missing gradient"
+            assert_close(p.grad, ref_g, 1e-4, f"grad {name}", atol=1e-7)
+            used += 1
+    assert used > 20 and unused >= 4          # edge_aggregation.mlp (+ spatial_* for the hyper layer)
+
+
+@pytest.mark.train
+def test_backward_accumulates_and_optimizer_step_repacks():
+    torch.manual_seed(3)
+    m = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=1).to(DEV)
+    opt = torch.optim.SGD([p for p in m.parameters()], lr=0.1)
+    h = torch.randn(4, 5, 64, device=DEV)
+    u = torch.rand(4, 25, 6, device=DEV)
+    out1, _ = m(h, noise=[u])
+    out1.sum().backward()
+    g1 = m.nmp_mlp_end.layers[1].bias.grad.clone()
+    out1b, _ = m(h, noise=[u])
+    out1b.sum().backward()                                            # grads accumulate like torch
+    assert torch.allclose(m.nmp_mlp_end.layers[1].bias.grad, 2 * g1)
+    opt.step()
+    with torch.no_grad():
+        out2, _ = m(h, noise=[u])
+    assert not torch.equal(out1.detach(), out2)                       # packed weights were refreshed
