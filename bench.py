@@ -223,6 +223,67 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+def run_train(args, rank, world, local):
+    """BASELINE config 5: training step (fwd + bwd through the 3 layers, fp32 kernels) data-parallel over
+    the GPUs of one box with ONE NCCL all-reduce of the flat gradient bucket per step."""
+    import torch.distributed as dist
+    import groupnet_b200 as gb
+    from groupnet_b200.ddp import FlatGradBucket
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    b = args.scenes if args.scenes != SCENES else 8192
+    n, d = AGENTS, HDIM
+    torch.manual_seed(1234)
+    model = gb.MultiScaleInteraction(d, SCALES).to(dev).train()
+    model.set_rng("philox", seed=0, scene_offset=rank * b)
+    bucket = FlatGradBucket(model.parameters())
+    x = torch.randn(b, n, d, generator=torch.Generator().manual_seed(rank)).to(dev)
+    wgt = torch.randn(b, n, model.feature_width(), generator=torch.Generator().manual_seed(100 + rank)).to(dev)
+
+    def step():
+        for p in model.parameters():
+            p.grad = None
+        feat, _ = model(x)
+        loss = (feat * wgt).sum() / b
+        loss.backward()
+        bucket.allreduce_mean()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank == 0:
+        print(json.dumps({
+            "metric": "ms_hgnn_train_step_scenes_per_sec", "value": world * b / (ms * 1e-3), "unit": "scenes/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "nba_train_step_fwd_bwd_3layers", "scenes_per_gpu": b, "agents": n, "h_dim": d,
+                       "scales": list(SCALES), "grad_bucket_floats": bucket.numel,
+                       "collective": "one NCCL all-reduce(sum) of the flat fp32 gradient bucket per step"},
+            "loss": float(loss.item())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -234,6 +295,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core path (2e-2 parity); fp32: FFMA path (1e-5 parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"],
+                    help="train: fwd+bwd through the three layers + one NCCL all-reduce of the flat gradient "
+                         "bucket (BASELINE config 5); per-GPU batch --scenes (default 8192 in this mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -247,6 +311,8 @@ def main():
     import torch.distributed as dist
     import groupnet_b200 as gb
     from groupnet_b200 import _lib
+    if args.mode == "train":
+        return run_train(args, rank, world, local)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     # torchrun pins OMP_NUM_THREADS=1; the host side of the e2e pipeline (x slice of final_feature)

@@ -61,3 +61,33 @@ def _worker(rank, world, port, total):
 def test_two_rank_gloo_sharding():
     port = _free_port()
     mp.spawn(_worker, args=(2, port, 1001), nprocs=2, join=True)
+
+
+def _ddp_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import groupnet_b200 as gb
+        from groupnet_b200.ddp import FlatGradBucket
+        torch.manual_seed(5)
+        m = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=3)
+        used = [p for n, p in m.named_parameters() if not n.startswith(("spatial_", "edge_aggregation_list.0.mlp"))]
+        for i, p in enumerate(used):                      # fake per-rank grads; unused params keep grad None
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        bucket = FlatGradBucket(m.parameters())
+        assert bucket.numel == sum(p.numel() for p in m.parameters()) == 283340
+        bucket.allreduce_mean()
+        mean = sum(range(1, world + 1)) / world
+        for i, p in enumerate(used):
+            assert torch.allclose(p.grad, torch.full_like(p, mean * (i + 1)))
+        for n, p in m.named_parameters():
+            if n.startswith("spatial_"):
+                assert p.grad is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_flat_bucket_allreduce():
+    port = _free_port()
+    mp.spawn(_ddp_worker, args=(2, port), nprocs=2, join=True)
