@@ -34,6 +34,7 @@ EXPORTS = (
     "gn_stage_bwd",
     "gn_profile_enable",
     "gn_profile_collect",
+    "gn_profile_set_trace",
 )
 
 
@@ -131,6 +132,8 @@ def load() -> C.CDLL:
         lib.gn_stage_bwd.argtypes = [C.POINTER(StageCfg), C.POINTER(TrainParams), C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.c_void_p]
+        lib.gn_profile_set_trace.restype = None
+        lib.gn_profile_set_trace.argtypes = [C.c_void_p]
         lib.gn_profile_enable.restype = None
         lib.gn_profile_enable.argtypes = [C.c_int]
         lib.gn_profile_collect.restype = C.c_int

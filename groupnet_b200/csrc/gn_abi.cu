@@ -134,3 +134,6 @@ extern "C" int gn_stage_bwd(const gn_stage_cfg* cfg, const gn_train_params* para
                        d_node_out, ld_dout, d_dist, d_h, workspace, workspace_bytes,
                        static_cast<cudaStream_t>(stream));
 }
+
+namespace gn { extern unsigned long long* g_trace_buffer; }
+extern "C" void gn_profile_set_trace(unsigned long long* device_buffer) { gn::g_trace_buffer = device_buffer; }

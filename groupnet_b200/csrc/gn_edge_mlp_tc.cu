@@ -39,6 +39,7 @@ struct TcChainArgs {
   long long R;
   const float* U; int noise_mode; unsigned long long seed; long long scene_offset; int stage_index;
   float* dist_out; float* edge_feat;
+  unsigned long long* trace;          // optional: clock64() per phase, block 0, first tiles (gn_profile_set_trace)
 };
 
 namespace tcmlp {
@@ -98,6 +99,9 @@ __device__ __forceinline__ void drain_to_smem(uint32_t tmem_addr, unsigned char*
 }
 
 // TT = compile-time number of edge types (6 pairwise, 10 hyper); 0 = runtime a.T (<= 15)
+#define GN_TRACE(pt) do { if (a.trace != nullptr && blockIdx.x == 0 && gtid == 0 && titer < 8) \
+    a.trace[(grp * 8 + titer) * 16 + (pt)] = clock64(); } while (0)
+
 template <bool PAIR, int TT>
 __global__ void __launch_bounds__(GN_THREADS, 1)
 edge_chain_tc_kernel(TcChainArgs a) {
@@ -165,10 +169,13 @@ edge_chain_tc_kernel(TcChainArgs a) {
     cp_async_commit();
   };
   if (PAIR) prefetch_nodes(static_cast<long long>(blockIdx.x) * 2 + grp);
+  int titer = -1;
   for (long long tile = static_cast<long long>(blockIdx.x) * 2 + grp; tile < ntiles;
        tile += static_cast<long long>(gridDim.x) * 2) {
     const long long grow = tile * 128 + row;
     const bool live = grow < a.R;
+    ++titer;
+    GN_TRACE(0);
 
     // ---- stage this thread's edge row as 64 bf16 of the A operand ----
     if (PAIR) {
@@ -248,6 +255,7 @@ edge_chain_tc_kernel(TcChainArgs a) {
     fence_before_thread_sync();
     chain_group_bar(grp);
     if (PAIR) prefetch_nodes(tile + static_cast<long long>(gridDim.x) * 2);   // overlaps the whole MMA chain
+    GN_TRACE(1);
 
     // ---- G1: 64 -> 128 ----
     if (gtid == 0) {
@@ -257,6 +265,7 @@ edge_chain_tc_kernel(TcChainArgs a) {
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase); phase ^= 1;
+    GN_TRACE(2);
     fence_after_thread_sync();
     drain_to_smem<true, 4>(tmem_row, sA1, row);
     fence_proxy_async_smem();
@@ -271,6 +280,7 @@ edge_chain_tc_kernel(TcChainArgs a) {
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase); phase ^= 1;
+    GN_TRACE(4);
     fence_after_thread_sync();
     drain_to_smem<false, 2>(tmem_row, sA0, row);
     fence_proxy_async_smem();
@@ -285,6 +295,7 @@ edge_chain_tc_kernel(TcChainArgs a) {
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase); phase ^= 1;
+    GN_TRACE(6);
     fence_after_thread_sync();
     drain_to_smem<true, 4>(tmem_row, sA1, row);
     fence_proxy_async_smem();
@@ -297,7 +308,8 @@ edge_chain_tc_kernel(TcChainArgs a) {
       issue_gemm(tmem_grp, sA1_addr, sbase + OFF_W4, 16, 128, true);
       mma_commit(mbar);
     }
-    mbar_wait(mbar, phase); phase ^= 1;       // A1 is free again
+    mbar_wait(mbar, phase); phase ^= 1;
+    GN_TRACE(8);       // A1 is free again
     fence_after_thread_sync();
     drain_to_smem<true, 4>(tmem_row + 128, sA1, row);
     fence_proxy_async_smem();
@@ -310,6 +322,7 @@ edge_chain_tc_kernel(TcChainArgs a) {
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase); phase ^= 1;
+    GN_TRACE(10);
     fence_after_thread_sync();
 
     // ---- epilogue 4: T logits | factor logit (biases already inside) ----
@@ -375,6 +388,7 @@ edge_chain_tc_kernel(TcChainArgs a) {
           }
       }
     }
+    GN_TRACE(11);
     // the next tile's G1 overwrites this group's TMEM columns and A0
     fence_before_thread_sync();
     chain_group_bar(grp);
@@ -410,6 +424,8 @@ bool edge_chain_pair_fits(int N) {
   return (127 / E + 2) * N <= tcmlp::MAXN;
 }
 
+unsigned long long* g_trace_buffer = nullptr;
+
 int launch_edge_chain_tc(bool pair, const float* edges, const float* xprime, const float* pq,
                          int N, int E, int T, long long R, const gn_stage_weights* w,
                          const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
@@ -423,6 +439,7 @@ int launch_edge_chain_tc(bool pair, const float* edges, const float* xprime, con
   a.N = N; a.E = E; a.T = T; a.R = R;
   a.U = U; a.noise_mode = noise_mode; a.seed = seed; a.scene_offset = scene_offset; a.stage_index = stage_index;
   a.dist_out = dist_out; a.edge_feat = edge_feat;
+  a.trace = g_trace_buffer;
   long long ntiles = (R + 127) / 128, want = (ntiles + 1) / 2;
   int grid = want < GN_SM_COUNT ? static_cast<int>(want) : GN_SM_COUNT;
   if (pair) {

@@ -231,6 +231,9 @@ int gn_stage_bwd(const gn_stage_cfg* cfg, const gn_train_params* params,
  * `names`, clears the records and returns the number of distinct kernels. */
 void gn_profile_enable(int on);
 int gn_profile_collect(char* names, int names_len, float* total_ms, int* counts, int max_entries);
+/* Optional device buffer (>= 2*8*16 uint64) that the edge-chain kernel fills with clock64() phase stamps of
+ * block 0's first tiles; NULL (default) disables tracing. */
+void gn_profile_set_trace(unsigned long long* device_buffer);
 
 #ifdef __cplusplus
 }
