@@ -16,6 +16,7 @@
 //
 // Bound: the SIMT relu-sum (3 instructions per (n, j, t, c)): N * T * 128 * 3 thread-instructions
 // per node row.  Algorithmic HBM bytes per scene: N*D*4 (h) + N*N*T*4 (edge_feat) + N*D*4 (agg).
+#include <cuda_fp16.h>
 #include "gn_tc.cuh"
 #include "gn_stage.h"
 
@@ -35,9 +36,9 @@ struct PairAggArgs {
 namespace pagg {
 constexpr int D = 64;
 constexpr uint32_t OFF_A = 0;                          // h tile, bf16 canonical [128 x 64]      16 KB
-constexpr int PLD = 132;                                // padded P' row (floats): rows 4 banks apart
-constexpr uint32_t OFF_P = OFF_A + 128 * 64 * 2;       // P'_t fp32 [128][PLD]                   66 KB
-constexpr uint32_t OFF_G = OFF_P + 128 * PLD * 4;      // G_t bf16 canonical [128 x 128]         32 KB
+constexpr int PLD = 136;                                // padded P' row (halfs): 272 B, rows 4 banks apart
+constexpr uint32_t OFF_P = OFF_A + 128 * 64 * 2;       // P'_t fp16 [128][PLD]                   34 KB
+constexpr uint32_t OFF_G = OFF_P + 128 * PLD * 2;      // G_t bf16 canonical [128 x 128]         32 KB
 constexpr uint32_t OFF_W0 = OFF_G + 128 * 128 * 2;     // W0_t double buffer [128 x 64] x 2      32 KB
 constexpr uint32_t OFF_W1 = OFF_W0 + 2 * 128 * 64 * 2; // W1_t [64 x 128]                        16 KB
 constexpr uint32_t OFF_ONES = OFF_W1 + 64 * 128 * 2;   // ones operand                            4 KB
@@ -55,7 +56,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row = tid & 127, chalf = tid >> 7;          // tile row (TMEM lane), 64-column half
-  float* sP = reinterpret_cast<float*>(smem + OFF_P);
+  __half* sP = reinterpret_cast<__half*>(smem + OFF_P);
   float* sS = reinterpret_cast<float*>(smem + OFF_S);
   float* sEF = reinterpret_cast<float*>(smem + OFF_EF);
   uint64_t* mbarA = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -159,18 +160,22 @@ pair_agg_tc_kernel(PairAggArgs a) {
       // (a) P'_t ready in TMEM
       mbar_wait(mbarA, phA); phA ^= 1;
       fence_after_thread_sync();
-      // (b) drain this thread's half row: keep it in registers, publish it for the scene mates
-      float own[64];
+      // (b) drain this thread's half row as fp16x2: keep it in registers, publish it for the scene mates
+      __half2 own[32];
       {
         uint32_t r[2][32];
         tmem_ld32_nowait(tmem_lane + TM_P + (t & 1) * 128 + chalf * 64, r[0]);
         tmem_ld32_nowait(tmem_lane + TM_P + (t & 1) * 128 + chalf * 64 + 32, r[1]);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 64; ++c) own[c] = __uint_as_float(r[c >> 5][c & 31]);
-        float* dst = sP + row * PLD + chalf * 64;
+        for (int c = 0; c < 32; ++c)
+          own[c] = __floats2half2_rn(__uint_as_float(r[(2 * c) >> 5][(2 * c) & 31]),
+                                     __uint_as_float(r[(2 * c + 1) >> 5][(2 * c + 1) & 31]));
+        uint4* dst = reinterpret_cast<uint4*>(sP + row * PLD + chalf * 64);
 #pragma unroll
-        for (int c = 0; c < 64; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(own[c], own[c + 1], own[c + 2], own[c + 3]);
+        for (int c = 0; c < 8; ++c)
+          dst[c] = make_uint4(*reinterpret_cast<uint32_t*>(&own[4 * c]), *reinterpret_cast<uint32_t*>(&own[4 * c + 1]),
+                              *reinterpret_cast<uint32_t*>(&own[4 * c + 2]), *reinterpret_cast<uint32_t*>(&own[4 * c + 3]));
       }
       cp_async_wait<0>();                                    // W0_{t+1} (issued one step ago) has landed
       fence_proxy_async_smem();
@@ -188,25 +193,30 @@ pair_agg_tc_kernel(PairAggArgs a) {
       // W0 / bias buffers (t & 1) were last read by GEMM 1 of step t (complete): stage step t+2
       if (t + 2 < T) { load_w0(t + 2, t & 1); build_bb(t + 2, t & 1); }
       cp_async_commit();                                     // group 2: W0_{t+2} (needed one step later)
-      // (d) relu-sum over the scene mates
-      float acc[64];
+      // (d) relu-sum over the scene mates in packed fp16x2: relu(own + p) is one HFMA2.RELU, the
+      //     weighted accumulation one HFMA2 (fp16 keeps 11 mantissa bits; the result feeds a bf16 operand)
+      __half2 acc[32];
 #pragma unroll
-      for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+      for (int c = 0; c < 32; ++c) acc[c] = __floats2half2_rn(0.f, 0.f);
       float ssum = 0.f;
       if (live) {
         const float* efs = sEF + sc * E * T;
-        const float* prow = sP + (sc * N) * PLD + chalf * 64;
+        const __half* prow = sP + (sc * N) * PLD + chalf * 64;
+        const __half2 one2 = __floats2half2_rn(1.f, 1.f);
         for (int j = 0; j < N; ++j) {
           const float w = efs[(ni * N + j) * T + t] + efs[(j * N + ni) * T + t];
           ssum += w;
-          const float* pj = prow + j * PLD;
+          const __half2 w2 = __floats2half2_rn(w, w);
+          const uint4* pj = reinterpret_cast<const uint4*>(prow + j * PLD);
 #pragma unroll
-          for (int c = 0; c < 64; c += 4) {
-            const float4 p = *reinterpret_cast<const float4*>(pj + c);
-            acc[c] = fmaf(w, fmaxf(own[c] + p.x, 0.f), acc[c]);
-            acc[c + 1] = fmaf(w, fmaxf(own[c + 1] + p.y, 0.f), acc[c + 1]);
-            acc[c + 2] = fmaf(w, fmaxf(own[c + 2] + p.z, 0.f), acc[c + 2]);
-            acc[c + 3] = fmaf(w, fmaxf(own[c + 3] + p.w, 0.f), acc[c + 3]);
+          for (int c = 0; c < 8; ++c) {
+            const uint4 p = pj[c];
+            const __half2 p0 = *reinterpret_cast<const __half2*>(&p.x), p1 = *reinterpret_cast<const __half2*>(&p.y);
+            const __half2 p2 = *reinterpret_cast<const __half2*>(&p.z), p3 = *reinterpret_cast<const __half2*>(&p.w);
+            acc[4 * c] = __hfma2(w2, __hfma2_relu(own[4 * c], one2, p0), acc[4 * c]);
+            acc[4 * c + 1] = __hfma2(w2, __hfma2_relu(own[4 * c + 1], one2, p1), acc[4 * c + 1]);
+            acc[4 * c + 2] = __hfma2(w2, __hfma2_relu(own[4 * c + 2], one2, p2), acc[4 * c + 2]);
+            acc[4 * c + 3] = __hfma2(w2, __hfma2_relu(own[4 * c + 3], one2, p3), acc[4 * c + 3]);
           }
         }
         if (chalf == 0) sS[row * 16 + t] = ssum;
@@ -214,8 +224,10 @@ pair_agg_tc_kernel(PairAggArgs a) {
       // G_t -> bf16 A operand of GEMM 2
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        uint4 pk = make_uint4(pack_bf16_fast(acc[8 * g], acc[8 * g + 1]), pack_bf16_fast(acc[8 * g + 2], acc[8 * g + 3]),
-                              pack_bf16_fast(acc[8 * g + 4], acc[8 * g + 5]), pack_bf16_fast(acc[8 * g + 6], acc[8 * g + 7]));
+        float2 f0 = __half22float2(acc[4 * g]), f1 = __half22float2(acc[4 * g + 1]);
+        float2 f2 = __half22float2(acc[4 * g + 2]), f3 = __half22float2(acc[4 * g + 3]);
+        uint4 pk = make_uint4(pack_bf16_fast(f0.x, f0.y), pack_bf16_fast(f1.x, f1.y),
+                              pack_bf16_fast(f2.x, f2.y), pack_bf16_fast(f3.x, f3.y));
         *reinterpret_cast<uint4*>(smem + OFF_G + canon_off(row, chalf * 8 + g, 128)) = pk;
       }
       cp_async_wait<1>();                                    // W1_t landed (the step t+2 prefetch may still fly)
