@@ -5,12 +5,13 @@ hand-written CUDA kernels behind a C ABI (include/groupnet_b200.h).
 """
 from .layers import (MLP, MLP_dict, MLP_dict_softmax, MS_HGNN_hyper, MS_HGNN_oridinary,
                      edge_aggregation)
+from .encoder import PastEncoder, PositionalAgentEncoding
 from .interaction import MultiScaleInteraction
 from .ops import corr_topk_h, topk_h
 from ._lib import GroupNetLibraryError, LIB_PATH
 
 __all__ = [
     "MS_HGNN_oridinary", "MS_HGNN_hyper", "MLP", "MLP_dict", "MLP_dict_softmax",
-    "edge_aggregation", "MultiScaleInteraction", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
+    "edge_aggregation", "MultiScaleInteraction", "PastEncoder", "PositionalAgentEncoding", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
 ]
 __version__ = "0.1.0"

@@ -29,6 +29,7 @@ EXPORTS = (
     "gn_stage_workspace_bytes",
     "gn_stage_fwd",
     "gn_stage_launch_count",
+    "gn_past_frontend",
     "gn_stage_saved_offsets",
     "gn_stage_bwd_workspace_bytes",
     "gn_stage_bwd",
@@ -124,6 +125,9 @@ def load() -> C.CDLL:
         lib.gn_stage_fwd.argtypes = [
             C.POINTER(StageCfg), C.POINTER(StageWeights), C.c_void_p, C.c_void_p, C.c_void_p,
             C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.gn_past_frontend.restype = C.c_int
+        lib.gn_past_frontend.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
         lib.gn_stage_saved_offsets.restype = C.c_int
         lib.gn_stage_saved_offsets.argtypes = [C.POINTER(StageCfg), C.POINTER(C.c_size_t)]
         lib.gn_stage_bwd_workspace_bytes.restype = C.c_size_t

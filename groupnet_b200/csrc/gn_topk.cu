@@ -620,3 +620,62 @@ extern "C" int gn_topk_h(const float* corr, int32_t B, int32_t N, int32_t scale,
   if (B == 0) return GN_OK;
   return gn::launch_topk<true>(nullptr, corr, B, N, 4, a, nullptr, static_cast<cudaStream_t>(stream));
 }
+
+
+// ---------------------------------------------------------------------------
+// PastEncoder front-end (model/GroupNet_nba.py:269-280).  In eval mode
+// input_fc -> [x ; pos_enc] -> pos_encoder.fc -> input_fc2 -> add_category -> input_fc3 has no
+// nonlinearity, so the host folds it into one affine map (groupnet_b200/encoder.py):
+//   ftraj[b,n,:] = Mt^T u[b,n,:] + bias_agent[n,:],   u = the agent's (T x in_dim) window, K = T*in_dim
+// One thread per (row, 4 output columns); Mt / bias table in shared memory; HBM-bound
+// (K*4 bytes in, 256 bytes out per agent row).
+// ---------------------------------------------------------------------------
+namespace gn {
+__global__ void __launch_bounds__(GN_THREADS)
+past_frontend_kernel(const float* __restrict__ u, long long R, int K, int N, int C,
+                     const float* __restrict__ Mt, const float* __restrict__ bias_agent,
+                     float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sM = smem;                    // [K][C]
+  float* sB = sM + K * C;              // [N][C]
+  for (int i = threadIdx.x; i < K * C; i += GN_THREADS) sM[i] = __ldg(Mt + i);
+  for (int i = threadIdx.x; i < N * C; i += GN_THREADS) sB[i] = __ldg(bias_agent + i);
+  __syncthreads();
+  const int c4n = C >> 2;
+  const long long total = R * c4n;
+  for (long long i = static_cast<long long>(blockIdx.x) * GN_THREADS + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * GN_THREADS) {
+    const long long r = i / c4n;
+    const int c = static_cast<int>(i - r * c4n) * 4;
+    const int n = static_cast<int>(r % N);
+    float4 acc = *reinterpret_cast<const float4*>(sB + n * C + c);
+    const float* ur = u + r * K;
+    for (int k = 0; k < K; ++k) {
+      const float x = __ldg(ur + k);
+      const float4 m = *reinterpret_cast<const float4*>(sM + k * C + c);
+      acc.x = fmaf(x, m.x, acc.x); acc.y = fmaf(x, m.y, acc.y);
+      acc.z = fmaf(x, m.z, acc.z); acc.w = fmaf(x, m.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(out + r * C + c) = acc;
+  }
+}
+}  // namespace gn
+
+extern "C" int gn_past_frontend(const float* inputs, int64_t R, int32_t K, int32_t N, int32_t C,
+                                const float* Mt, const float* bias_agent, float* out, gn_stream_t stream) {
+  if (!inputs || !Mt || !bias_agent || !out) return GN_E_NULL;
+  if (R < 0 || K < 1 || N < 1 || C < 4 || (C & 3)) return GN_E_SHAPE;
+  if (R == 0) return GN_OK;
+  size_t smem = (static_cast<size_t>(K) + N) * C * 4;
+  if (smem > 200 * 1024) return GN_E_SHAPE;
+  cudaError_t e = cudaFuncSetAttribute(gn::past_frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  long long work = (R * (C >> 2) + GN_THREADS - 1) / GN_THREADS;
+  int grid = work < GN_SM_COUNT * 8 ? static_cast<int>(work) : GN_SM_COUNT * 8;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  { gn::ProfScope ps__("past_frontend", st);
+    gn::past_frontend_kernel<<<grid, GN_THREADS, smem, st>>>(inputs, R, K, N, C, Mt, bias_agent, out); }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}

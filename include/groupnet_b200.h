@@ -181,6 +181,13 @@ int gn_stage_fwd(const gn_stage_cfg* cfg, const gn_stage_weights* w,
  * gn_stage_fwd call (for bench.py's gpu_launches accounting). */
 int gn_stage_launch_count(const gn_stage_cfg* cfg);
 
+/* PastEncoder front-end (model/GroupNet_nba.py:269-280), eval mode: the chain input_fc ->
+ * PositionalAgentEncoding (concat + fc) -> input_fc2 -> add_category -> input_fc3 is affine, folded by the
+ * host into Mt (K x C, K = past_length*in_dim) and a per-agent bias table (N x C):
+ *   out[r,:] = Mt^T inputs[r,:] + bias_agent[r % N,:]        inputs (R,K), out (R,C), R = B*N */
+int gn_past_frontend(const float* inputs, int64_t R, int32_t K, int32_t N, int32_t C,
+                     const float* Mt, const float* bias_agent, float* out, gn_stream_t stream);
+
 /* ---- training: backward of one stage (fp32) -------------------------------------------------
  * Gradients flow to h_in and to every parameter the forward uses; H, corr and the noise get none
  * (model/MS_HGNN_batch.py:382 uses top-k indices only).  Parameters are read in their native

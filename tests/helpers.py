@@ -16,9 +16,13 @@ FP32_REL = 1e-5
 BF16_REL = 2e-2
 
 
-def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0]
-                  for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+def golden_names(prefix=None):
+    """Layer fixtures by default; `prefix="pastenc"` selects the whole-encoder fixtures."""
+    names = sorted(os.path.splitext(os.path.basename(p))[0]
+                   for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    if prefix is None:
+        return [n for n in names if not n.startswith("pastenc")]
+    return [n for n in names if n.startswith(prefix)]
 
 
 def load_golden(name):
@@ -28,7 +32,7 @@ def load_golden(name):
         g[k] = int(g[k])
     g["kind"] = str(g["kind"])
     g["weight_sha256"] = str(g["weight_sha256"])
-    g["noise"] = [g[f"U{i}"] for i in range(max(g["L"], 1))]
+    g["noise"] = [g[f"U{i}"] for i in range(3 if g["kind"] == "past_encoder" else max(g["L"], 1))]
     return g
 
 
@@ -38,6 +42,16 @@ def state_sha(module) -> str:
         hsh.update(k.encode())
         hsh.update(v.detach().cpu().numpy().astype(np.float32).tobytes())
     return hsh.hexdigest()
+
+
+def build_past_encoder(g):
+    import types
+    import groupnet_b200 as gb
+    args = types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], past_length=5)
+    torch.manual_seed(g["weight_seed"])
+    m = gb.PastEncoder(args)
+    assert state_sha(m) == g["weight_sha256"], "regenerated PastEncoder weights differ from the golden run"
+    return m.eval()
 
 
 def build_layer(g):

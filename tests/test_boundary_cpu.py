@@ -136,3 +136,36 @@ def test_product_does_not_import_oracle():
 
 def test_all_goldens_present():
     assert len(golden_names()) >= 20
+
+
+@pytest.mark.skipif(not have_reference(), reason="reference tree not present")
+def test_past_encoder_state_dict_matches_reference():
+    import types
+    for missing in ("tkinter", "glob2"):
+        if missing not in sys.modules:
+            stub = types.ModuleType(missing)
+            stub.TRUE = True
+            sys.modules[missing] = stub
+    if REFERENCE_DIR not in sys.path:
+        sys.path.insert(0, REFERENCE_DIR)
+    from model.GroupNet_nba import PastEncoder as RefPastEncoder
+    for scales in ([5, 11], [3, 5, 8], []):
+        args = types.SimpleNamespace(hidden_dim=64, hyper_scales=scales, past_length=5)
+        torch.manual_seed(9)
+        r = RefPastEncoder(args)
+        torch.manual_seed(9)
+        m = gb.PastEncoder(args)
+        rs, ms = r.state_dict(), m.state_dict()
+        assert list(rs.keys()) == list(ms.keys())
+        assert all(torch.equal(rs[k], ms[k]) for k in rs)
+        m.load_state_dict(rs, strict=True)
+        # the folded affine front-end equals the reference's module chain (eval mode)
+        if len(scales) == 2:
+            r.eval()
+            inp = torch.randn(3 * 11, 5, 4)
+            with torch.no_grad():
+                tf = r.pos_encoder(r.input_fc(inp).view(33, 5, 64), num_a=33).view(3, 11, 5, 64)
+                f = r.input_fc3(r.add_category(r.input_fc2(tf.contiguous().view(3, 11, 320))))
+            mt, bias = m.folded_frontend(11, 5, torch.device("cpu"))
+            mine = (inp.view(33, 20) @ mt + bias.repeat(3, 1)).view(3, 11, 64)
+            assert (mine - f).abs().max().item() <= 1e-6

@@ -6,7 +6,8 @@ import torch
 
 import groupnet_b200 as gb
 from groupnet_b200 import _lib
-from helpers import BF16_REL, FP32_REL, assert_close, build_layer, golden_names, load_golden, rel_err
+from helpers import (BF16_REL, FP32_REL, assert_close, build_layer, build_past_encoder, golden_names,
+                     load_golden, rel_err)
 from oracle import ms_hgnn_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -418,3 +419,30 @@ def test_backward_accumulates_and_optimizer_step_repacks():
     with torch.no_grad():
         out2, _ = m(h, noise=[u])
     assert not torch.equal(out1.detach(), out2)                       # packed weights were refreshed
+
+
+# ---- T6 / §8(f) rank 1: the whole PastEncoder against the reference's own PastEncoder --------
+@pytest.mark.parametrize("name", golden_names("pastenc"))
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_REL), ("bf16", BF16_REL)])
+def test_past_encoder_vs_reference_golden(name, precision, tol):
+    g = load_golden(name)
+    enc = build_past_encoder(g).to(DEV)
+    for l in enc.layers():
+        l.set_precision(precision)
+    inputs = torch.from_numpy(g["inputs"]).to(DEV)
+    feat, new_h = enc(inputs, g["B"], g["N"], noise=[torch.from_numpy(u).to(DEV) for u in g["noise"]])
+    assert feat.shape == g["output_feature"].shape and new_h.shape == g["new_H"].shape
+    assert torch.equal(new_h.cpu(), torch.from_numpy(g["new_H"]))            # hyperedge membership bit-exact
+    ref = torch.from_numpy(g["output_feature"])
+    assert_close(feat[:, :64], ref[:, :64], 1e-5, "ftraj_input (folded front-end)")
+    for i, part in enumerate(("pairwise", "hyper5", "hyper11")):
+        assert_close(feat[:, 64 * (i + 1):64 * (i + 2)], ref[:, 64 * (i + 1):64 * (i + 2)], tol, part)
+
+
+def test_past_encoder_errors_like_reference():
+    import types
+    enc = gb.PastEncoder(types.SimpleNamespace(hidden_dim=64, hyper_scales=[3], past_length=5)).to(DEV).eval()
+    with pytest.raises(IndexError):                       # add_category indexes agent 10 (:264)
+        enc(torch.randn(2 * 8, 5, 4, device=DEV), 2, 8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.randn(2 * 11, 5, 4), 2, 11)
