@@ -30,8 +30,8 @@ sgemm_kernel(const float* __restrict__ X, long long ldx, const float* __restrict
              const float* __restrict__ bias, float* __restrict__ Y, long long ldy,
              long long M, int N, int K, int relu, int accumulate,
              const float* __restrict__ maskref, long long ldm) {
-  __shared__ float xs[SG_K][SG_T + 1];
-  __shared__ float ws[SG_K][SG_T + 1];
+  __shared__ __align__(16) float xs[SG_K][SG_T + 4];
+  __shared__ __align__(16) float ws[SG_K][SG_T + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const long long m0 = static_cast<long long>(blockIdx.x) * SG_T;
   const int n0 = blockIdx.y * SG_T;
@@ -56,9 +56,9 @@ sgemm_kernel(const float* __restrict__ X, long long ldx, const float* __restrict
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < SG_K; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = xs[k][ty * 4 + u]; b[u] = ws[k][tx * 4 + u]; }
+      const float4 av = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&ws[k][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(256)
 sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ Bm, long long ldb,
                 float* __restrict__ C, long long ldc, float* __restrict__ cb,
                 long long M, int N, int K, long long rows_per_slice) {
-  __shared__ float as[SG_K][SG_T + 1];
-  __shared__ float bs[SG_K][SG_T + 1];
+  __shared__ __align__(16) float as[SG_K][SG_T + 4];
+  __shared__ __align__(16) float bs[SG_K][SG_T + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int n0 = blockIdx.x * SG_T, k0 = blockIdx.y * SG_T;
   const long long mbeg = static_cast<long long>(blockIdx.z) * rows_per_slice;
@@ -107,9 +107,9 @@ sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restr
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < SG_K; ++r) {
-      float a[4], b[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) { a[u] = as[r][ty * 4 + u]; b[u] = bs[r][tx * 4 + u]; }
+      const float4 av = *reinterpret_cast<const float4*>(&as[r][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&bs[r][tx * 4]);
+      const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (tx == 0) bsum[u] += a[u];
