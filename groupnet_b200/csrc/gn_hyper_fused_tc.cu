@@ -1,0 +1,358 @@
+// Fused hyper edge_aggregation for wide layers (h_dim = 256, E == N <= 64): the crowd shape.
+//
+//   eo   = H @ h                                    (model/MS_HGNN_batch.py:263, edges <- nodes)
+//   ef   = sum_t edge_feat[:, t] * (W1_t relu(W0_t eo + b0_t) + b1_t)      (:264-265, T MLPs 256->128->256)
+//   agg  = H^T @ ef                                 (:267, nodes <- edges)
+//
+// One persistent CTA per SM walks 128-row tiles (SC = 128 / N whole scenes: edge rows and node rows
+// of a tile belong to the same scenes, so both incidence products are tile-local).  Everything runs
+// on tcgen05 with fp32 accumulators in TMEM; the only HBM traffic is h, H, edge_feat in and agg out
+// (the generic path wrote and re-read eo, a (B*E, T*128) bf16 hidden tensor and ef).
+//
+//   gather   eo[128 x 256]   = Hblk[128 x 128] * hT[256 x 128]^T        (block-diagonal incidence)
+//   per t    hid_j[128 x 64] = [eo | 1][128 x 272] * [W0_tj | b0_tj]^T   j = 0,1  (bias through the MMA)
+//            ef[128 x 256]  += A2_j[128 x 64(+16)] * [W1_tj (| b1_t)]^T  A2_j = bf16(relu(hid_j) * edge_feat_t)
+//   scatter  agg[128 x 256]  = HblkT[128 x 128] * efT[256 x 128]^T
+//
+// Warp roles (320 threads): warps 0-3 / 4-7 drain the two hidden halves (TMEM -> bf16 A2 operand),
+// warp 8 streams the weight chunks with cp.async.bulk (TMA bulk copy, mbarrier complete_tx) through a
+// 3-stage ring in the order the MMAs consume them (host-packed as ONE linear stream, packing.py),
+// warp 9 issues every tcgen05.mma.  G1 of step t+1 is issued before G2 of step t, so the drains
+// overlap the tensor pipe.  Per 128-row tile the weight stream is 1.41 MB from L2: the kernel is
+// L2->SM bandwidth bound (~42 B/clk/SM), not tensor-pipe bound; see DESIGN.md.
+#include "gn_tc.cuh"
+#include "gn_stage.h"
+
+namespace gn {
+namespace hf {
+constexpr int D = 256;
+constexpr int THREADS = 320;
+constexpr uint32_t W0_CHUNK = 64 * 272 * 2;      // 64 hidden units x (256 + 16 bias k-columns)
+constexpr uint32_t W1A_CHUNK = 256 * 80 * 2;     // 256 outputs x (64 hidden + 16 b1 k-columns)
+constexpr uint32_t W1B_CHUNK = 256 * 64 * 2;
+constexpr uint32_t STAGE = 40960;
+constexpr int NSTAGE = 3;
+constexpr uint32_t OFF_EO = 0;                   // eo A operand [128 x 256]; epilogue: efT B operand [256 x 128]
+constexpr uint32_t OFF_ONES = 65536;             // k-groups 32,33 of the A operand: 1.0, 1.0, 0...
+constexpr uint32_t OFF_A2 = OFF_ONES + 4096;     // A2_0 [128 x 80] | A2_1 [128 x 64]; staging: Hblk; epilogue: HblkT
+constexpr uint32_t A2_0_BYTES = 128 * 80 * 2;
+constexpr uint32_t OFF_A2_1 = OFF_A2 + A2_0_BYTES;
+constexpr uint32_t OFF_RING = OFF_A2 + A2_0_BYTES + 128 * 64 * 2;     // 3 stages; staging: hT [256 x 128]
+constexpr uint32_t OFF_BAR = OFF_RING + NSTAGE * STAGE;
+enum { B_WFULL = 0, B_WEMPTY = 3, B_HFULL = 6, B_HFREE = 10, B_A2FULL = 14, B_A2FREE = 16, B_STAGE = 18,
+       B_EOFULL = 19, B_EOREADY = 20, B_EFFULL = 21, B_EFTREADY = 22, B_AGGFULL = 23, NBAR = 24 };
+constexpr uint32_t SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "hyper_fused_tc: shared memory budget");
+constexpr uint32_t TM_EF = 0, TM_HB = 256, TM_AGG = 256;
+}  // namespace hf
+
+struct HyperFusedArgs {
+  const float* h; const float* H; const float* edge_feat; const unsigned char* wstream;
+  float* agg; int B, N, T; long long hstride;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc::smem_u32(b)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, no tensor map), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(hf::THREADS, 1)
+hyper_fused_tc_kernel(HyperFusedArgs a) {
+  using namespace hf;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + NBAR * 8);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NBAR; ++i) {
+      uint32_t cnt = 1;
+      if (i >= B_HFREE && i < B_HFREE + 4) cnt = 128;
+      if (i >= B_A2FULL && i < B_A2FULL + 2) cnt = 128;
+      if (i == B_STAGE || i == B_EOREADY || i == B_EFTREADY) cnt = 256;
+      tc::mbar_init(bars + i, cnt);
+    }
+  }
+  if (warp == 9) tc::tmem_alloc(tmem_slot, 512);
+  if (tid < 256) tc::build_ones_operand(smem + OFF_ONES, tid, 256);
+  tc::fence_proxy_async_smem();
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  tc::fence_after_thread_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sbase = tc::smem_u32(smem);
+  const int N = a.N, SC = 128 / N, T = a.T;
+  const int ntiles = (a.B + SC - 1) / SC;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------ weight stream producer
+    if (lane == 0) {
+      uint32_t ph_empty = 0x7u, ph_eofull = 0u;
+      int stage = 0;
+      auto load = [&](const unsigned char*& src, uint32_t bytes) {
+        tc::mbar_wait(bars + B_WEMPTY + stage, (ph_empty >> stage) & 1u);
+        ph_empty ^= 1u << stage;
+        mbar_expect_tx(bars + B_WFULL + stage, bytes);
+        bulk_g2s(sbase + OFF_RING + stage * STAGE, src, bytes, bars + B_WFULL + stage);
+        src += bytes;
+        stage = stage == NSTAGE - 1 ? 0 : stage + 1;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        tc::mbar_wait(bars + B_EOFULL, ph_eofull);      // hT (ring stages 0-1) consumed by the gather MMA
+        ph_eofull ^= 1u;
+        const unsigned char* src = a.wstream;
+        for (int s = 0; s <= T; ++s) {
+          if (s < T) { load(src, W0_CHUNK); load(src, W0_CHUNK); }
+          if (s >= 1) { load(src, W1A_CHUNK); load(src, W1B_CHUNK); }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t ph = 0u;                                  // bit i = parity to wait for on barrier i
+      ph |= 0xFu << B_HFREE;                             // "free" barriers: the first wait passes
+      int stage = 0;
+      auto wait = [&](int i) { tc::mbar_wait(bars + i, (ph >> i) & 1u); ph ^= 1u << i; };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        wait(B_STAGE);
+        tc::fence_after_thread_sync();
+        tc::issue_gemm(tmem + TM_EF, sbase + OFF_A2, sbase + OFF_RING, 256, 128, false);     // eo = Hblk * h
+        tc::mma_commit(bars + B_EOFULL);
+        wait(B_EOREADY);
+        tc::fence_after_thread_sync();
+        for (int s = 0; s <= T; ++s) {
+          if (s < T) {
+            const int p = s & 1;
+            for (int j = 0; j < 2; ++j) {
+              wait(B_HFREE + j * 2 + p);
+              wait(B_WFULL + stage);
+              tc::fence_after_thread_sync();
+              tc::issue_gemm(tmem + TM_HB + (p * 2 + j) * 64, sbase + OFF_EO, sbase + OFF_RING + stage * STAGE,
+                             64, 272, false);
+              tc::mma_commit(bars + B_WEMPTY + stage);
+              tc::mma_commit(bars + B_HFULL + j * 2 + p);
+              stage = stage == NSTAGE - 1 ? 0 : stage + 1;
+            }
+          }
+          if (s >= 1) {
+            for (int j = 0; j < 2; ++j) {
+              wait(B_A2FULL + j);
+              wait(B_WFULL + stage);
+              tc::fence_after_thread_sync();
+              tc::issue_gemm(tmem + TM_EF, sbase + (j ? OFF_A2_1 : OFF_A2), sbase + OFF_RING + stage * STAGE,
+                             256, j ? 64 : 80, !(s == 1 && j == 0));
+              tc::mma_commit(bars + B_WEMPTY + stage);
+              tc::mma_commit(bars + B_A2FREE + j);
+              stage = stage == NSTAGE - 1 ? 0 : stage + 1;
+            }
+          }
+        }
+        tc::mma_commit(bars + B_EFFULL);
+        wait(B_EFTREADY);
+        tc::fence_after_thread_sync();
+        tc::issue_gemm(tmem + TM_AGG, sbase + OFF_A2, sbase + OFF_EO, 256, 128, false);       // agg = HblkT * ef
+        tc::mma_commit(bars + B_AGGFULL);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ staging / drain warps
+    const int g = warp >> 2;                             // hidden half / column half
+    const int row = (warp & 3) * 32 + lane;              // TMEM lane = tile row
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    uint32_t ph = 0u;
+    ph |= 0x3u << B_A2FREE;
+    auto wait = [&](int i) { tc::mbar_wait(bars + i, (ph >> i) & 1u); ph ^= 1u << i; };
+    const int r128 = tid & 127, half = tid >> 7;
+    const int sc_r = r128 / N, in_r = r128 - sc_r * N;   // scene-in-tile and index-in-scene of row r128
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int b0s = tile * SC;
+      const int ns = min(SC, a.B - b0s);
+      const int rows_used = ns * N;
+      // ---- Hblk[edge row][node column] (A operand, block diagonal), rows = r128, k-groups of this half
+      {
+        const bool valid = r128 < rows_used;
+        const float* Hrow = a.H + static_cast<size_t>(b0s + sc_r) * a.hstride + static_cast<size_t>(in_r) * N;
+#pragma unroll 2
+        for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = kg * 8 + i - sc_r * N;
+            v[i] = (valid && n >= 0 && n < N) ? __ldg(Hrow + n) : 0.f;
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) =
+              make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
+                         tc::pack_bf16(v[6], v[7]));
+        }
+      }
+      // ---- hT[column c][node k] (B operand): thread = column, 8 nodes per 16-byte store
+      {
+        const float* hsrc = a.h + static_cast<size_t>(b0s) * N * D + tid;
+#pragma unroll 2
+        for (int kg = 0; kg < 16; ++kg) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int node = kg * 8 + i;
+            v[i] = node < rows_used ? __ldg(hsrc + static_cast<size_t>(node) * D) : 0.f;
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_RING + kg * 4096 + tid * 16) =
+              make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
+                         tc::pack_bf16(v[6], v[7]));
+        }
+      }
+      tc::fence_proxy_async_smem();
+      mbar_arrive(bars + B_STAGE);
+      const bool rowvalid = row < rows_used;
+      const float* efrow = a.edge_feat + (static_cast<size_t>(b0s) * N + row) * T;
+      float wnext = rowvalid ? __ldg(efrow) : 0.f;
+      // ---- eo: TMEM -> bf16 A operand, this group's 128 columns
+      wait(B_EOFULL);
+      tc::fence_after_thread_sync();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[32];
+        tc::tmem_ld32(tmem + lane_addr + TM_EF + g * 128 + cc * 32, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(smem + OFF_EO + (g * 16 + cc * 4 + q) * 2048 + row * 16) =
+              make_uint4(tc::pack_bf16_fast(v[8 * q], v[8 * q + 1]), tc::pack_bf16_fast(v[8 * q + 2], v[8 * q + 3]),
+                         tc::pack_bf16_fast(v[8 * q + 4], v[8 * q + 5]), tc::pack_bf16_fast(v[8 * q + 6], v[8 * q + 7]));
+      }
+      tc::fence_proxy_async_smem();
+      tc::fence_before_thread_sync();
+      mbar_arrive(bars + B_EOREADY);
+      // ---- main loop: hidden half g of step t -> A2_g
+      unsigned char* a2 = smem + (g ? OFF_A2_1 : OFF_A2);
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const int p = t & 1;
+        const float w = wnext;
+        if (t + 1 < T) wnext = rowvalid ? __ldg(efrow + t + 1) : 0.f;
+        wait(B_HFULL + g * 2 + p);
+        tc::fence_after_thread_sync();
+        uint32_t r0[32], r1[32];
+        tc::tmem_ld32_nowait(tmem + lane_addr + TM_HB + (p * 2 + g) * 64, r0);
+        tc::tmem_ld32_nowait(tmem + lane_addr + TM_HB + (p * 2 + g) * 64 + 32, r1);
+        tc::tmem_ld_wait();
+        tc::fence_before_thread_sync();
+        mbar_arrive(bars + B_HFREE + g * 2 + p);
+        wait(B_A2FREE + g);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = tc::pack_bf16_relu(__uint_as_float(r0[8 * q]) * w, __uint_as_float(r0[8 * q + 1]) * w);
+          o.y = tc::pack_bf16_relu(__uint_as_float(r0[8 * q + 2]) * w, __uint_as_float(r0[8 * q + 3]) * w);
+          o.z = tc::pack_bf16_relu(__uint_as_float(r0[8 * q + 4]) * w, __uint_as_float(r0[8 * q + 5]) * w);
+          o.w = tc::pack_bf16_relu(__uint_as_float(r0[8 * q + 6]) * w, __uint_as_float(r0[8 * q + 7]) * w);
+          *reinterpret_cast<uint4*>(a2 + q * 2048 + row * 16) = o;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = tc::pack_bf16_relu(__uint_as_float(r1[8 * q]) * w, __uint_as_float(r1[8 * q + 1]) * w);
+          o.y = tc::pack_bf16_relu(__uint_as_float(r1[8 * q + 2]) * w, __uint_as_float(r1[8 * q + 3]) * w);
+          o.z = tc::pack_bf16_relu(__uint_as_float(r1[8 * q + 4]) * w, __uint_as_float(r1[8 * q + 5]) * w);
+          o.w = tc::pack_bf16_relu(__uint_as_float(r1[8 * q + 6]) * w, __uint_as_float(r1[8 * q + 7]) * w);
+          *reinterpret_cast<uint4*>(a2 + (4 + q) * 2048 + row * 16) = o;
+        }
+        if (g == 0) {                                   // k = 64..66: edge_feat_t (hi, hi, lo) against (b1 hi, b1 lo, b1 hi)
+          const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+          const float lo = w - __bfloat162float(hi);
+          const uint32_t hi16 = static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(&hi));
+          *reinterpret_cast<uint4*>(a2 + 8 * 2048 + row * 16) =
+              make_uint4(hi16 | (hi16 << 16), tc::pack_bf16(lo, 0.f), 0u, 0u);
+          *reinterpret_cast<uint4*>(a2 + 9 * 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        tc::fence_proxy_async_smem();
+        mbar_arrive(bars + B_A2FULL + g);
+      }
+      // ---- epilogue: HblkT (A), efT (B), then agg out
+      wait(B_EFFULL);
+      tc::fence_after_thread_sync();
+      {
+        const bool valid = r128 < rows_used;             // r128 = node row here
+        const float* Hcol = a.H + static_cast<size_t>(b0s + sc_r) * a.hstride + in_r;
+#pragma unroll 2
+        for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int e = kg * 8 + i - sc_r * N;
+            v[i] = (valid && e >= 0 && e < N) ? __ldg(Hcol + static_cast<size_t>(e) * N) : 0.f;
+          }
+          *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) =
+              make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
+                         tc::pack_bf16(v[6], v[7]));
+        }
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[32];
+        tc::tmem_ld32(tmem + lane_addr + TM_EF + g * 128 + cc * 32, v);
+        unsigned char* dst = smem + OFF_EO + (row >> 3) * 4096 + (row & 7) * 2 + (g * 128 + cc * 32) * 16;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const __nv_bfloat16 b = __float2bfloat16_rn(v[i]);
+          *reinterpret_cast<__nv_bfloat16*>(dst + i * 16) = b;
+        }
+      }
+      tc::fence_proxy_async_smem();
+      tc::fence_before_thread_sync();
+      mbar_arrive(bars + B_EFTREADY);
+      wait(B_AGGFULL);
+      tc::fence_after_thread_sync();
+      float* out = a.agg + (static_cast<size_t>(b0s) * N + row) * D + g * 128;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[32];
+        tc::tmem_ld32(tmem + lane_addr + TM_AGG + g * 128 + cc * 32, v);
+        if (rowvalid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(out + cc * 32 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+      tc::fence_before_thread_sync();
+    }
+  }
+  tc::fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 9) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
+bool hyper_fused_fits(int N, int E, int D, int T) {
+  return D == hf::D && E == N && N >= 2 && N <= 64 && T >= 1 && T <= 15;
+}
+
+int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat, int B, int N, int T,
+                          long long hstride, const gn_stage_weights* w, float* agg, cudaStream_t st) {
+  if (!w->tc_hfuse_w) return GN_E_NULL;
+  if (B <= 0) return GN_OK;
+  HyperFusedArgs a;
+  a.h = h; a.H = H; a.edge_feat = edge_feat;
+  a.wstream = static_cast<const unsigned char*>(w->tc_hfuse_w);
+  a.agg = agg; a.B = B; a.N = N; a.T = T; a.hstride = hstride;
+  const int SC = 128 / N;
+  const int ntiles = (B + SC - 1) / SC;
+  const int grid = ntiles < GN_SM_COUNT ? ntiles : GN_SM_COUNT;
+  cudaError_t e = cudaFuncSetAttribute(hyper_fused_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(hf::SMEM_BYTES));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  { ProfScope ps__("hyper_fused_tc", st);
+    hyper_fused_tc_kernel<<<grid, hf::THREADS, hf::SMEM_BYTES, st>>>(a); }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
+
+}  // namespace gn

@@ -39,6 +39,11 @@ bool hyper_agg_fits(int D, int T);
 int launch_hyper_agg_tc(const float* eo, const float* edge_feat, long long R, int T,
                         const gn_stage_weights* w, float* ef, cudaStream_t st);
 
+// fused wide hyper aggregation, h_dim 256: H@h gather + T MLPs + H^T scatter (gn_hyper_fused_tc.cu)
+bool hyper_fused_fits(int N, int E, int D, int T);
+int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat, int B, int N, int T,
+                          long long hstride, const gn_stage_weights* w, float* agg, cudaStream_t st);
+
 // fused node-level GEMM chains on tensor cores (gn_node_chain_tc.cu)
 struct NodeChainStep {
   const __nv_bfloat16* W;     // canonical (N x K)

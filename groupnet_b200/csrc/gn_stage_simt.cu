@@ -322,6 +322,129 @@ node2edge_hyper_kernel(const float* __restrict__ xprime, const float* __restrict
 }
 
 // ===========================================================================
+// k2c: node2edge, hyper, ONE WARP PER HYPEREDGE (N <= 64, D % 4 == 0, D <= 256).
+// Same math as k2b (model/MS_HGNN_batch.py:357-370) with the 32 lanes of a warp across the attention
+// hidden units (32) / the feature columns, so a CTA of 8 warps keeps every lane busy whatever E is:
+// the crowd shape (N = E = 64, h_dim 256) left k2b with 64 active threads per SM.  A CTA stages SC
+// whole scenes (x', pq, H and — only when the caller wants eo = H @ h — h) in shared memory with
+// 128-bit loads; the member list of an edge is two ballots over its incidence row.
+// ===========================================================================
+constexpr int N2W_THREADS = 256;
+
+__global__ void __launch_bounds__(N2W_THREADS)
+node2edge_hyper_warp_kernel(const float* __restrict__ xprime, const float* __restrict__ pq,
+                            const float* __restrict__ h, const float* __restrict__ H,
+                            int B, int N, int E, int D, long long hstride, int SC, gn_stage_weights W,
+                            float* __restrict__ edges, float* __restrict__ eo) {
+  extern __shared__ __align__(16) float smem[];
+  const int maxnodes = SC * N, maxedges = SC * E;
+  float* xs = smem;                               // [SC*N][64]
+  float* ps = xs + maxnodes * 64;                 // [SC*N][64]  pn | q
+  float* Hs = ps + maxnodes * 64;                 // [SC*E][N]
+  float* hs = Hs + ((maxedges * N + 3) & ~3);     // [SC*N][D]   (only when eo != nullptr)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float b0 = __ldg(W.att_b0 + lane), w1 = __ldg(W.att_w1 + lane), b1 = __ldg(W.att_b1);
+  const int ntiles = (B + SC - 1) / SC;
+  const int dch = (D + 31) >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0s = tile * SC, ns = min(SC, B - b0s);
+    const int nn = ns * N, ne = ns * E;
+    __syncthreads();
+    for (int i = tid; i < nn * 16; i += N2W_THREADS) {
+      const size_t g = static_cast<size_t>(b0s) * N * 64 + 4 * static_cast<size_t>(i);
+      *reinterpret_cast<float4*>(xs + 4 * i) = ldg_f4(xprime + g);
+      *reinterpret_cast<float4*>(ps + 4 * i) = ldg_f4(pq + g);
+    }
+    if (eo != nullptr) {
+      const int tot4 = nn * (D >> 2);
+      const float* src = h + static_cast<size_t>(b0s) * N * D;
+      for (int i = tid; i < tot4; i += N2W_THREADS)
+        *reinterpret_cast<float4*>(hs + 4 * i) = ldg_f4(src + 4 * static_cast<size_t>(i));
+    }
+    {
+      const int per = E * N;
+      for (int i = tid; i < ns * per; i += N2W_THREADS) {
+        const int sc = i / per, r = i - sc * per;
+        Hs[i] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + r);
+      }
+    }
+    __syncthreads();
+    for (int e = warp; e < ne; e += N2W_THREADS / 32) {
+      const int sc = e / E, nb = sc * N;
+      const float* Hr = Hs + e * N;
+      const float v0 = lane < N ? Hr[lane] : 0.f;
+      const float v1 = lane + 32 < N ? Hr[lane + 32] : 0.f;
+      const unsigned m0 = __ballot_sync(0xffffffffu, v0 != 0.f), m1 = __ballot_sync(0xffffffffu, v1 != 0.f);
+      const int cnt = __popc(m0) + __popc(m1);
+      // pe[k] = b0[k] + sum_m H[e,m] q_m[k]      (lane = k)
+      float pe = b0;
+      for (unsigned mm = m0; mm; mm &= mm - 1) {
+        const int n = __ffs(mm) - 1;
+        pe = fmaf(__shfl_sync(0xffffffffu, v0, n), ps[(nb + n) * 64 + 32 + lane], pe);
+      }
+      for (unsigned mm = m1; mm; mm &= mm - 1) {
+        const int n = __ffs(mm) - 1;
+        pe = fmaf(__shfl_sync(0xffffffffu, v1, n), ps[(nb + n + 32) * 64 + 32 + lane], pe);
+      }
+      // a_m = (w1 . relu(pn_m + pe) + b1) * H[e,m]; member position p lives in lane p & 31, slot p >> 5
+      float a_lo = 0.f, a_hi = 0.f, hv_lo = 0.f, hv_hi = 0.f;
+      float mx = (cnt < N) ? 0.f : -INFINITY;
+      int p = 0;
+      for (unsigned mm = m0; mm; mm &= mm - 1, ++p) {
+        const int n = __ffs(mm) - 1;
+        const float hv = __shfl_sync(0xffffffffu, v0, n);
+        const float a = (warp_sum(fmaxf(ps[(nb + n) * 64 + lane] + pe, 0.f) * w1) + b1) * hv;
+        mx = fmaxf(mx, a);
+        if (lane == (p & 31)) { if (p < 32) { a_lo = a; hv_lo = hv; } else { a_hi = a; hv_hi = hv; } }
+      }
+      for (unsigned mm = m1; mm; mm &= mm - 1, ++p) {
+        const int n = __ffs(mm) - 1 + 32;
+        const float hv = __shfl_sync(0xffffffffu, v1, n - 32);
+        const float a = (warp_sum(fmaxf(ps[(nb + n) * 64 + lane] + pe, 0.f) * w1) + b1) * hv;
+        mx = fmaxf(mx, a);
+        if (lane == (p & 31)) { if (p < 32) { a_lo = a; hv_lo = hv; } else { a_hi = a; hv_hi = hv; } }
+      }
+      // softmax over ALL N nodes (non-members enter with logit 0, :135-137), times H
+      const float ex_lo = lane < cnt ? expf(a_lo - mx) : 0.f;
+      const float ex_hi = lane + 32 < cnt ? expf(a_hi - mx) : 0.f;
+      const float den = warp_sum(ex_lo + ex_hi) + static_cast<float>(N - cnt) * expf(-mx);
+      const float w_lo = ex_lo / den * hv_lo, w_hi = ex_hi / den * hv_hi;
+      // edges_e = sum_m w_m x'_m (lane owns columns lane, lane+32);  eo_e = sum_m H[e,m] h_m
+      float acc0 = 0.f, acc1 = 0.f;
+      float eacc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) eacc[j] = 0.f;
+      p = 0;
+      for (int half = 0; half < 2; ++half) {
+        for (unsigned mm = half ? m1 : m0; mm; mm &= mm - 1, ++p) {
+          const int n = __ffs(mm) - 1 + 32 * half;
+          const float wgt = __shfl_sync(0xffffffffu, p < 32 ? w_lo : w_hi, p & 31);
+          const float* xr = xs + (nb + n) * 64;
+          acc0 = fmaf(wgt, xr[lane], acc0);
+          acc1 = fmaf(wgt, xr[lane + 32], acc1);
+          if (eo != nullptr) {
+            const float hv = __shfl_sync(0xffffffffu, half ? v1 : v0, n & 31);
+            const float* hr = hs + (nb + n) * D;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < dch && j * 32 + lane < D) eacc[j] = fmaf(hv, hr[j * 32 + lane], eacc[j]);
+          }
+        }
+      }
+      float* dst = edges + (static_cast<size_t>(b0s) * E + e) * GN_ATT_DIM;
+      dst[lane] = acc0;
+      dst[lane + 32] = acc1;
+      if (eo != nullptr) {
+        float* de = eo + (static_cast<size_t>(b0s) * E + e) * D;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < dch && j * 32 + lane < D) de[j * 32 + lane] = eacc[j];
+      }
+    }
+  }
+}
+
+// ===========================================================================
 // k3: edge_mlp — MLP_dict_softmax (:31-53) + Gumbel softmax (:446-520)
 // rows = B*E edge rows, row independent.
 // smem: eT [64][LD] (reused for z) | bufT [128][LD] | wp [2*KC*128] |
@@ -756,6 +879,8 @@ static int make_plan(const gn_stage_cfg* c, StagePlan& p) {
     p.off_G = take(R * c->T * 128 * 4);
     p.off_S = take(R * 16 * 4);
     p.off_agg = take(R * c->D * 4);
+  } else if (p.tc_nodes && hyper_fused_fits(c->N, c->E, c->D, c->T)) {
+    p.off_agg = take(R * c->D * 4);                  // eo, hidden and ef stay on chip
   } else {
     p.off_eo = take(RE * c->D * 4);
     p.off_ef = take(RE * c->D * 4);
@@ -801,6 +926,28 @@ static int launch_node2edge_pair(const float* xprime, const float* pq, int B, in
 static int launch_node2edge_hyper(const float* xprime, const float* pq, const float* h, const float* H,
                                   int B, int N, int E, int D, long long hstride, const gn_stage_weights* w,
                                   float* edges, float* eo, cudaStream_t st) {
+  if (N <= 64 && E <= 64 && D <= 256 && (D & 3) == 0) {          // warp per hyperedge
+    auto wbytes = [&](int sc) -> size_t {
+      size_t nodes = static_cast<size_t>(sc) * N, ed = static_cast<size_t>(sc) * E;
+      return (2 * nodes * 64 + ((ed * N + 3) & ~size_t(3)) + (eo ? nodes * D : 0)) * 4;
+    };
+    int SC = 64 / E;                                              // ~8 edges per warp per tile
+    if (SC < 1) SC = 1;
+    if (SC > 16) SC = 16;
+    while (SC > 1 && wbytes(SC) > 72 * 1024) --SC;
+    const size_t smem = wbytes(SC);
+    GN_TRY(set_smem(node2edge_hyper_warp_kernel, smem));
+    const int ntiles = (B + SC - 1) / SC;
+    int per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    const int grid = ntiles < GN_SM_COUNT * per_sm ? ntiles : GN_SM_COUNT * per_sm;
+    { ProfScope ps__("node2edge_hyper", st);
+      node2edge_hyper_warp_kernel<<<grid, N2W_THREADS, smem, st>>>(xprime, pq, h, H, B, N, E, D, hstride, SC,
+                                                                   *w, edges, eo); }
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+  }
   auto bytes = [&](int sc) -> size_t {
     size_t nodes = static_cast<size_t>(sc) * N, ed = static_cast<size_t>(sc) * E;
     size_t fl = 2 * nodes * N2E_LD + nodes * (D + 4) + 2 * ((ed * (N + 1) + 3) & ~size_t(3));
@@ -943,8 +1090,11 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   // ---- k2: node2edge (fused into the tensor-core chain for the pairwise bf16 path)
   const bool tc = c->precision == GN_BF16_TC;
   const bool fuse_pair = tc && c->pairwise && edge_chain_pair_fits(N);
+  const bool fused_hyper = tcn && !c->pairwise && hyper_fused_fits(N, E, D, T);   // eo / ef never leave the SM
+  if (fused_hyper && !w->tc_hfuse_w) return GN_E_NULL;
   if (c->pairwise) { if (!fuse_pair) GN_TRY(launch_node2edge_pair(xprime, pq, B, N, w, edges, st)); }
-  else GN_TRY(launch_node2edge_hyper(xprime, pq, h, H, B, N, E, D, hstride, w, edges, eo, st));
+  else GN_TRY(launch_node2edge_hyper(xprime, pq, h, H, B, N, E, D, hstride, w, edges,
+                                     fused_hyper ? nullptr : eo, st));
 
   // ---- k3: per-edge MLP chain + Gumbel softmax
   if (tc) {
@@ -967,6 +1117,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   if (c->pairwise) {
     if (fused_agg) GN_TRY(launch_pair_agg_tc(h, efeat, B, N, T, w, agg, st));
     else GN_TRY(launch_edge2node_pair(P, efeat, B, N, T, w, G, S, st));
+  } else if (fused_hyper) {
+    GN_TRY(launch_hyper_fused_tc(h, H, efeat, B, N, T, hstride, w, agg, st));
   } else {
     if (tcn && hyper_agg_fits(D, T)) {
       GN_TRY(launch_hyper_agg_tc(eo, efeat, RE, T, w, ef, st));
@@ -1095,6 +1247,7 @@ int stage_launch_count(const gn_stage_cfg* c) {
   const bool chain = c->D == 64 && (c->Dout % 32 == 0) && c->Dout <= 128;
   const int pre = chain ? 1 : 3, post = chain ? 1 : 2;
   if (c->pairwise && pair_agg_fits(c->N, c->D, c->T)) return pre + (2 - fused) + 1 + post;
+  if (!c->pairwise && hyper_fused_fits(c->N, c->E, c->D, c->T)) return pre + 1 + 1 + 1 + post;
   if (!c->pairwise && hyper_agg_fits(c->D, c->T)) return pre + 1 + 1 + 1 + 1 + post;
   return c->pairwise ? (3 + chunks) + (2 - fused) + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
 }

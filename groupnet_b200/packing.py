@@ -58,6 +58,44 @@ def canonical_bf16(weight: torch.Tensor) -> torch.Tensor:
     return weight.detach().reshape(n, k // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
 
 
+def _canon(m: torch.Tensor) -> torch.Tensor:
+    """(R, K) fp32 -> flat bf16 in the canonical operand layout [K/8][R][8]."""
+    r, k = m.shape
+    return m.reshape(r, k // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16).reshape(-1)
+
+
+def _hi_lo(v: torch.Tensor):
+    hi = v.to(torch.bfloat16).to(torch.float32)
+    return hi, (v - hi).to(torch.bfloat16).to(torch.float32)
+
+
+def hyper_fused_stream(agg_mlps, d: int) -> torch.Tensor:
+    """Weight stream of csrc/gn_hyper_fused_tc.cu (h_dim 256): the aggregation MLPs' chunks in MMA
+    consumption order — G1 of step s before G2 of step s-1 — each chunk one canonical operand."""
+    t = len(agg_mlps)
+    dev = agg_mlps[0].layers[0].weight.device
+    parts = []
+    for s in range(t + 1):
+        if s < t:
+            w0 = agg_mlps[s].layers[0].weight.detach().float()        # (128, D)
+            hi, lo = _hi_lo(agg_mlps[s].layers[0].bias.detach().float())
+            for j in range(2):
+                blk = torch.zeros(64, d + 16, dtype=torch.float32, device=dev)
+                blk[:, :d] = w0[j * 64:(j + 1) * 64]
+                blk[:, d] = hi[j * 64:(j + 1) * 64]
+                blk[:, d + 1] = lo[j * 64:(j + 1) * 64]
+                parts.append(_canon(blk))
+        if s >= 1:
+            w1 = agg_mlps[s - 1].layers[1].weight.detach().float()    # (D, 128)
+            hi, lo = _hi_lo(agg_mlps[s - 1].layers[1].bias.detach().float())
+            blk = torch.zeros(d, 80, dtype=torch.float32, device=dev)
+            blk[:, :64] = w1[:, :64]
+            blk[:, 64], blk[:, 65], blk[:, 66] = hi, lo, hi
+            parts.append(_canon(blk))
+            parts.append(_canon(w1[:, 64:].contiguous()))
+    return torch.cat(parts).contiguous()
+
+
 def agg_out_cols(d: int) -> Tuple[int, int]:
     """(Dc, TN) of the aggregation output GEMM; must match make_plan() in
     csrc/gn_stage_simt.cu."""
@@ -145,6 +183,8 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
         out["tc_agg_w1"] = canonical_bf16(torch.cat([dev(m.layers[1].weight) for m in agg], dim=1))  # (D, T*128)
         out["tc_post_w0"] = canonical_bf16(dev(post_mod.layers[0].weight))                        # (128, 2D)
         out["tc_post_w1"] = canonical_bf16(dev(post_mod.layers[1].weight))                        # (Dout, 128)
+        if d == 256 and not layer._pairwise and t <= 15:
+            out["tc_hfuse_w"] = hyper_fused_stream([m.to(device) for m in agg], d)
 
     out["post_w0t"] = _kmajor(dev(post_mod.layers[0].weight), k2p, 128, 128)
     out["post_b0"] = dev(post_mod.layers[0].bias)

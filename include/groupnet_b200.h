@@ -109,6 +109,11 @@ typedef struct gn_stage_weights {
   const void* tc_agg_w1;  /* N=D,     K=T*128  agg_mlp[t].layers.1 concatenated along K */
   const void* tc_post_w0; /* N=128,   K=2D     closing MLP layers.0 */
   const void* tc_post_w1; /* N=Dout,  K=128    closing MLP layers.1 */
+  /* weight stream of the fused wide hyper aggregation (csrc/gn_hyper_fused_tc.cu; D == 256 only, else
+   * NULL): the agg_mlp chunks in the order the kernel consumes them, each a canonical operand:
+   * for s = 0..T: [s < T: W0_s rows 0..63 | b0 (hi,lo) (64 x 272), W0_s rows 64..127 (64 x 272)]
+   *               [s >= 1, t = s-1: W1_t[:, 0:64] | b1_t (hi,lo,hi) (256 x 80), W1_t[:, 64:128] (256 x 64)] */
+  const void* tc_hfuse_w;
 } gn_stage_weights;
 
 typedef struct gn_stage_cfg {
