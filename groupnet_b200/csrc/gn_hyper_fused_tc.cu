@@ -20,6 +20,7 @@
 // warp 9 issues every tcgen05.mma.  G1 of step t+1 is issued before G2 of step t, so the drains
 // overlap the tensor pipe.  Per 128-row tile the weight stream is 1.41 MB from L2: the kernel is
 // L2->SM bandwidth bound (~42 B/clk/SM), not tensor-pipe bound; see DESIGN.md.
+#include <cstdlib>
 #include "gn_tc.cuh"
 #include "gn_stage.h"
 
@@ -48,7 +49,7 @@ constexpr uint32_t TM_EF = 0, TM_HB = 256, TM_AGG = 256;
 
 struct HyperFusedArgs {
   const float* h; const float* H; const float* edge_feat; const unsigned char* wstream;
-  float* agg; int B, N, T; long long hstride;
+  float* agg; int B, N, T; long long hstride; int dbg;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
@@ -98,18 +99,24 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       auto load = [&](const unsigned char*& src, uint32_t bytes) {
         tc::mbar_wait(bars + B_WEMPTY + stage, (ph_empty >> stage) & 1u);
         ph_empty ^= 1u << stage;
+        if (a.dbg & 1) mbar_arrive(bars + B_WFULL + stage);
+        else {
         mbar_expect_tx(bars + B_WFULL + stage, bytes);
         bulk_g2s(sbase + OFF_RING + stage * STAGE, src, bytes, bars + B_WFULL + stage);
+        }
         src += bytes;
         stage = stage == NSTAGE - 1 ? 0 : stage + 1;
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const unsigned char* src = a.wstream;
+        stage = NSTAGE - 1;                              // every tile starts in the stage hT does not cover
+        load(src, W0_CHUNK);
         tc::mbar_wait(bars + B_EOFULL, ph_eofull);      // hT (ring stages 0-1) consumed by the gather MMA
         ph_eofull ^= 1u;
-        const unsigned char* src = a.wstream;
-        for (int s = 0; s <= T; ++s) {
+        load(src, W0_CHUNK);
+        for (int s = 1; s <= T; ++s) {
           if (s < T) { load(src, W0_CHUNK); load(src, W0_CHUNK); }
-          if (s >= 1) { load(src, W1A_CHUNK); load(src, W1B_CHUNK); }
+          load(src, W1A_CHUNK); load(src, W1B_CHUNK);
         }
       }
     }
@@ -127,6 +134,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         tc::mma_commit(bars + B_EOFULL);
         wait(B_EOREADY);
         tc::fence_after_thread_sync();
+        stage = NSTAGE - 1;
         for (int s = 0; s <= T; ++s) {
           if (s < T) {
             const int p = s & 1;
@@ -134,6 +142,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
               wait(B_HFREE + j * 2 + p);
               wait(B_WFULL + stage);
               tc::fence_after_thread_sync();
+              if (!(a.dbg & 2))
               tc::issue_gemm(tmem + TM_HB + (p * 2 + j) * 64, sbase + OFF_EO, sbase + OFF_RING + stage * STAGE,
                              64, 272, false);
               tc::mma_commit(bars + B_WEMPTY + stage);
@@ -146,6 +155,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
               wait(B_A2FULL + j);
               wait(B_WFULL + stage);
               tc::fence_after_thread_sync();
+              if (!(a.dbg & 4))
               tc::issue_gemm(tmem + TM_EF, sbase + (j ? OFF_A2_1 : OFF_A2), sbase + OFF_RING + stage * STAGE,
                              256, j ? 64 : 80, !(s == 1 && j == 0));
               tc::mma_commit(bars + B_WEMPTY + stage);
@@ -179,13 +189,21 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       {
         const bool valid = r128 < rows_used;
         const float* Hrow = a.H + static_cast<size_t>(b0s + sc_r) * a.hstride + static_cast<size_t>(in_r) * N;
-#pragma unroll 2
+        const bool vec = ((N & 7) == 0) && ((a.hstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.H) & 15) == 0);
+#pragma unroll 4
         for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
           float v[8];
+          const int n0 = kg * 8 - sc_r * N;
+          if (vec) {                                      // N % 8 == 0: a k-group never straddles a scene
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+            if (valid && n0 >= 0 && n0 < N) { x = ldg_f4(Hrow + n0); y = ldg_f4(Hrow + n0 + 4); }
+            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+          } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = kg * 8 + i - sc_r * N;
-            v[i] = (valid && n >= 0 && n < N) ? __ldg(Hrow + n) : 0.f;
+            for (int i = 0; i < 8; ++i) {
+              const int n = n0 + i;
+              v[i] = (valid && n >= 0 && n < N) ? __ldg(Hrow + n) : 0.f;
+            }
           }
           *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) =
               make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
@@ -195,13 +213,13 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       // ---- hT[column c][node k] (B operand): thread = column, 8 nodes per 16-byte store
       {
         const float* hsrc = a.h + static_cast<size_t>(b0s) * N * D + tid;
-#pragma unroll 2
+#pragma unroll 4
         for (int kg = 0; kg < 16; ++kg) {
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int node = kg * 8 + i;
-            v[i] = node < rows_used ? __ldg(hsrc + static_cast<size_t>(node) * D) : 0.f;
+            v[i] = (node < rows_used) ? __ldg(hsrc + static_cast<size_t>(node) * D) : 0.f;
           }
           *reinterpret_cast<uint4*>(smem + OFF_RING + kg * 4096 + tid * 16) =
               make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
@@ -297,11 +315,16 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       for (int cc = 0; cc < 4; ++cc) {
         float v[32];
         tc::tmem_ld32(tmem + lane_addr + TM_EF + g * 128 + cc * 32, v);
-        unsigned char* dst = smem + OFF_EO + (row >> 3) * 4096 + (row & 7) * 2 + (g * 128 + cc * 32) * 16;
+        // rows (2m, 2m+1) share a 32-bit word of the K-major operand: exchange with the neighbour lane so each
+        // lane stores full words (even lane: even columns, odd lane: odd columns)
+        unsigned char* dst = smem + OFF_EO + (row >> 3) * 4096 + ((row & 7) >> 1) * 4 +
+                             (g * 128 + cc * 32 + (lane & 1)) * 16;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const __nv_bfloat16 b = __float2bfloat16_rn(v[i]);
-          *reinterpret_cast<__nv_bfloat16*>(dst + i * 16) = b;
+        for (int i = 0; i < 32; i += 2) {
+          const float send = (lane & 1) ? v[i] : v[i + 1];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+          const uint32_t word = (lane & 1) ? tc::pack_bf16(recv, v[i + 1]) : tc::pack_bf16(v[i], recv);
+          *reinterpret_cast<uint32_t*>(dst + i * 16) = word;
         }
       }
       tc::fence_proxy_async_smem();
@@ -343,6 +366,8 @@ int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat
   a.h = h; a.H = H; a.edge_feat = edge_feat;
   a.wstream = static_cast<const unsigned char*>(w->tc_hfuse_w);
   a.agg = agg; a.B = B; a.N = N; a.T = T; a.hstride = hstride;
+  a.dbg = getenv("GN_HF_DBG") ? atoi(getenv("GN_HF_DBG")) : 0;
+  if (getenv("GN_HF_T")) a.T = atoi(getenv("GN_HF_T"));
   const int SC = 128 / N;
   const int ntiles = (B + SC - 1) / SC;
   const int grid = ntiles < GN_SM_COUNT ? ntiles : GN_SM_COUNT;
