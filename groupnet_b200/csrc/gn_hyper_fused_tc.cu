@@ -41,15 +41,23 @@ constexpr uint32_t OFF_A2_1 = OFF_A2 + A2_0_BYTES;
 constexpr uint32_t OFF_RING = OFF_A2 + A2_0_BYTES + 128 * 64 * 2;     // 3 stages; staging: hT [256 x 128]
 constexpr uint32_t OFF_BAR = OFF_RING + NSTAGE * STAGE;
 enum { B_WFULL = 0, B_WEMPTY = 3, B_HFULL = 6, B_HFREE = 10, B_A2FULL = 14, B_A2FREE = 16, B_STAGE = 18,
-       B_EOFULL = 19, B_EOREADY = 20, B_EFFULL = 21, B_EFTREADY = 22, B_AGGFULL = 23, NBAR = 24 };
+       B_EOFULL = 19, B_EOREADY = 20, B_EFFULL = 21, B_EFTREADY = 22, B_AGGFULL = 23,
+       B_PXFULL = 24, B_PXEMPTY = 25, B_PAREADY = 26, B_O1FULL = 27, B_O1READY = 28, B_OUTFULL = 29, NBAR = 30 };
 constexpr uint32_t SMEM_BYTES = OFF_BAR + NBAR * 8 + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "hyper_fused_tc: shared memory budget");
-constexpr uint32_t TM_EF = 0, TM_HB = 256, TM_AGG = 256;
+constexpr uint32_t TM_EF = 0, TM_HB = 256, TM_AGG = 256, TM_O1 = 0, TM_OUT = 256;
+// closing MLP (post) weight chunks, streamed after the aggregation chunks: buffers alternate between ring
+// stage 2 ("Y") and the A2 region ("X"); the [agg | h]/N operand sits in the eo region and ring stages 0-1
+constexpr uint32_t P0_CHUNK = 128 * 128 * 2;            // post_w0[:, 128c : 128c+128]
+constexpr uint32_t P0B_CHUNK = P0_CHUNK + 128 * 16 * 2; // last one carries the bias block
+constexpr uint32_t OFF_X = OFF_A2, OFF_Y = OFF_RING + 2 * STAGE, OFF_AH = OFF_RING;
+static_assert(P0B_CHUNK <= A2_0_BYTES + 128 * 64 * 2, "post chunk must fit the A2 region");
 }  // namespace hf
 
 struct HyperFusedArgs {
   const float* h; const float* H; const float* edge_feat; const unsigned char* wstream;
   float* agg; int B, N, T; long long hstride; int dbg;
+  float* node_out; long long ld_out; int Dout; int post; size_t post_off;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
@@ -76,7 +84,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       uint32_t cnt = 1;
       if (i >= B_HFREE && i < B_HFREE + 4) cnt = 128;
       if (i >= B_A2FULL && i < B_A2FULL + 2) cnt = 128;
-      if (i == B_STAGE || i == B_EOREADY || i == B_EFTREADY) cnt = 256;
+      if (i == B_STAGE || i == B_EOREADY || i == B_EFTREADY || i == B_PAREADY || i == B_O1READY) cnt = 256;
       tc::mbar_init(bars + i, cnt);
     }
   }
@@ -94,7 +102,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
   if (warp == 8) {
     // ------------------------------------------------------------------ weight stream producer
     if (lane == 0) {
-      uint32_t ph_empty = 0x7u, ph_eofull = 0u;
+      uint32_t ph_empty = 0x7u, ph_eofull = 0u, ph_px = 1u, ph_agg = 0u;
       int stage = 0;
       auto load = [&](const unsigned char*& src, uint32_t bytes) {
         tc::mbar_wait(bars + B_WEMPTY + stage, (ph_empty >> stage) & 1u);
@@ -117,6 +125,24 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         for (int s = 1; s <= T; ++s) {
           if (s < T) { load(src, W0_CHUNK); load(src, W0_CHUNK); }
           load(src, W1A_CHUNK); load(src, W1B_CHUNK);
+        }
+        if (a.post) {
+          const unsigned char* ps = a.wstream + a.post_off;
+          const uint32_t c4 = static_cast<uint32_t>(a.Dout) * 160u, c5 = static_cast<uint32_t>(a.Dout) * 128u;
+          auto load_y = [&](uint32_t bytes) { stage = NSTAGE - 1; load(ps, bytes); };
+          auto load_x = [&](uint32_t bytes) {
+            tc::mbar_wait(bars + B_PXEMPTY, ph_px); ph_px ^= 1u;
+            mbar_expect_tx(bars + B_PXFULL, bytes);
+            bulk_g2s(sbase + OFF_X, ps, bytes, bars + B_PXFULL);
+            ps += bytes;
+          };
+          load_y(P0_CHUNK);
+          tc::mbar_wait(bars + B_AGGFULL, ph_agg); ph_agg ^= 1u;   // HblkT (A2 region) consumed
+          load_x(P0_CHUNK);
+          load_y(P0_CHUNK);
+          load_x(P0B_CHUNK);
+          load_y(c4);
+          load_x(c5);
         }
       }
     }
@@ -169,6 +195,41 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         tc::fence_after_thread_sync();
         tc::issue_gemm(tmem + TM_AGG, sbase + OFF_A2, sbase + OFF_EO, 256, 128, false);       // agg = HblkT * ef
         tc::mma_commit(bars + B_AGGFULL);
+        if (a.post) {
+          // o1 = relu([agg | h]/N W0^T + b0): four K chunks of 128 (A: eo region, then ring stages 0-1)
+          wait(B_PAREADY);
+          wait(B_WFULL + 2);
+          tc::fence_after_thread_sync();
+          tc::issue_gemm(tmem + TM_O1, sbase + OFF_EO, sbase + OFF_Y, 128, 128, false);
+          tc::mma_commit(bars + B_WEMPTY + 2);
+          wait(B_PXFULL);
+          tc::fence_after_thread_sync();
+          tc::issue_gemm(tmem + TM_O1, sbase + OFF_EO + 16 * 2048, sbase + OFF_X, 128, 128, true);
+          tc::mma_commit(bars + B_PXEMPTY);
+          wait(B_WFULL + 2);
+          tc::fence_after_thread_sync();
+          tc::issue_gemm(tmem + TM_O1, sbase + OFF_AH, sbase + OFF_Y, 128, 128, true);
+          tc::mma_commit(bars + B_WEMPTY + 2);
+          wait(B_PXFULL);
+          tc::fence_after_thread_sync();
+          tc::issue_gemm(tmem + TM_O1, sbase + OFF_AH + 16 * 2048, sbase + OFF_X, 128, 128, true);
+          tc::issue_gemm(tmem + TM_O1, sbase + OFF_ONES, sbase + OFF_X + P0_CHUNK, 128, 16, true);
+          tc::mma_commit(bars + B_PXEMPTY);
+          tc::mma_commit(bars + B_O1FULL);
+          // out = o1 W1^T + b1: two K chunks of 64
+          wait(B_O1READY);
+          wait(B_WFULL + 2);
+          tc::fence_after_thread_sync();
+          tc::issue_gemm(tmem + TM_OUT, sbase + OFF_EO, sbase + OFF_Y, a.Dout, 64, false);
+          tc::issue_gemm(tmem + TM_OUT, sbase + OFF_ONES, sbase + OFF_Y + static_cast<uint32_t>(a.Dout) * 128u,
+                         a.Dout, 16, true);
+          tc::mma_commit(bars + B_WEMPTY + 2);
+          wait(B_PXFULL);
+          tc::fence_after_thread_sync();
+          tc::issue_gemm(tmem + TM_OUT, sbase + OFF_EO + 8 * 2048, sbase + OFF_X, a.Dout, 64, true);
+          tc::mma_commit(bars + B_PXEMPTY);
+          tc::mma_commit(bars + B_OUTFULL);
+        }
       }
     }
   } else {
@@ -330,6 +391,81 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       tc::fence_proxy_async_smem();
       tc::fence_before_thread_sync();
       mbar_arrive(bars + B_EFTREADY);
+      if (a.post) {
+        const float inv_n = 1.f / static_cast<float>(N);
+        // h rows / N -> A operand columns 256..511 (ring stages 0-1 are idle since ef_full)
+        {
+          const bool valid = r128 < rows_used;
+          const float* hrow = a.h + (static_cast<size_t>(b0s) * N + r128) * D;
+#pragma unroll 4
+          for (int kg = half * 16; kg < half * 16 + 16; ++kg) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+            if (valid) { x = ldg_f4(hrow + kg * 8); y = ldg_f4(hrow + kg * 8 + 4); }
+            *reinterpret_cast<uint4*>(smem + OFF_AH + kg * 2048 + r128 * 16) =
+                make_uint4(tc::pack_bf16(x.x * inv_n, x.y * inv_n), tc::pack_bf16(x.z * inv_n, x.w * inv_n),
+                           tc::pack_bf16(y.x * inv_n, y.y * inv_n), tc::pack_bf16(y.z * inv_n, y.w * inv_n));
+          }
+        }
+        wait(B_AGGFULL);
+        tc::fence_after_thread_sync();
+        // agg / N -> A operand columns 0..255 (eo region; efT was consumed by the scatter MMA)
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[32];
+          tc::tmem_ld32(tmem + lane_addr + TM_AGG + g * 128 + cc * 32, v);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(smem + OFF_EO + (g * 16 + cc * 4 + q) * 2048 + row * 16) =
+                make_uint4(tc::pack_bf16(v[8 * q] * inv_n, v[8 * q + 1] * inv_n),
+                           tc::pack_bf16(v[8 * q + 2] * inv_n, v[8 * q + 3] * inv_n),
+                           tc::pack_bf16(v[8 * q + 4] * inv_n, v[8 * q + 5] * inv_n),
+                           tc::pack_bf16(v[8 * q + 6] * inv_n, v[8 * q + 7] * inv_n));
+        }
+        tc::fence_proxy_async_smem();
+        tc::fence_before_thread_sync();
+        mbar_arrive(bars + B_PAREADY);
+        // o1: relu -> bf16 A operand [128 x 128] (eo region), this group's 64 columns
+        wait(B_O1FULL);
+        tc::fence_after_thread_sync();
+        {
+          uint32_t r0[32], r1[32];
+          tc::tmem_ld32_nowait(tmem + lane_addr + TM_O1 + g * 64, r0);
+          tc::tmem_ld32_nowait(tmem + lane_addr + TM_O1 + g * 64 + 32, r1);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            *reinterpret_cast<uint4*>(smem + OFF_EO + (g * 8 + q) * 2048 + row * 16) = make_uint4(
+                tc::pack_bf16_relu(__uint_as_float(r0[8 * q]), __uint_as_float(r0[8 * q + 1])),
+                tc::pack_bf16_relu(__uint_as_float(r0[8 * q + 2]), __uint_as_float(r0[8 * q + 3])),
+                tc::pack_bf16_relu(__uint_as_float(r0[8 * q + 4]), __uint_as_float(r0[8 * q + 5])),
+                tc::pack_bf16_relu(__uint_as_float(r0[8 * q + 6]), __uint_as_float(r0[8 * q + 7])));
+            *reinterpret_cast<uint4*>(smem + OFF_EO + (g * 8 + 4 + q) * 2048 + row * 16) = make_uint4(
+                tc::pack_bf16_relu(__uint_as_float(r1[8 * q]), __uint_as_float(r1[8 * q + 1])),
+                tc::pack_bf16_relu(__uint_as_float(r1[8 * q + 2]), __uint_as_float(r1[8 * q + 3])),
+                tc::pack_bf16_relu(__uint_as_float(r1[8 * q + 4]), __uint_as_float(r1[8 * q + 5])),
+                tc::pack_bf16_relu(__uint_as_float(r1[8 * q + 6]), __uint_as_float(r1[8 * q + 7])));
+          }
+        }
+        tc::fence_proxy_async_smem();
+        tc::fence_before_thread_sync();
+        mbar_arrive(bars + B_O1READY);
+        // node_feat rows: 32-column chunks alternate between the two groups
+        wait(B_OUTFULL);
+        tc::fence_after_thread_sync();
+        float* orow = a.node_out + (static_cast<size_t>(b0s) * N + row) * a.ld_out;
+#pragma unroll 1
+        for (int cc = g; cc * 32 < a.Dout; cc += 2) {
+          float v[32];
+          tc::tmem_ld32(tmem + lane_addr + TM_OUT + cc * 32, v);
+          if (rowvalid) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(orow + cc * 32 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
+        }
+        tc::fence_before_thread_sync();
+        continue;
+      }
       wait(B_AGGFULL);
       tc::fence_after_thread_sync();
       float* out = a.agg + (static_cast<size_t>(b0s) * N + row) * D + g * 128;
@@ -358,14 +494,22 @@ bool hyper_fused_fits(int N, int E, int D, int T) {
   return D == hf::D && E == N && N >= 2 && N <= 64 && T >= 1 && T <= 15;
 }
 
+bool hyper_fused_post_fits(int Dout, long long ld_out) {
+  return Dout >= 32 && Dout <= 256 && (Dout & 31) == 0 && (ld_out & 3) == 0;
+}
+
 int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat, int B, int N, int T,
-                          long long hstride, const gn_stage_weights* w, float* agg, cudaStream_t st) {
+                          long long hstride, const gn_stage_weights* w, float* agg,
+                          float* node_out, long long ld_out, int Dout, cudaStream_t st) {
   if (!w->tc_hfuse_w) return GN_E_NULL;
   if (B <= 0) return GN_OK;
   HyperFusedArgs a;
   a.h = h; a.H = H; a.edge_feat = edge_feat;
   a.wstream = static_cast<const unsigned char*>(w->tc_hfuse_w);
   a.agg = agg; a.B = B; a.N = N; a.T = T; a.hstride = hstride;
+  a.node_out = node_out; a.ld_out = ld_out; a.Dout = Dout;
+  a.post = node_out != nullptr ? 1 : 0;
+  a.post_off = static_cast<size_t>(T) * (2 * hf::W0_CHUNK + hf::W1A_CHUNK + hf::W1B_CHUNK);
   a.dbg = getenv("GN_HF_DBG") ? atoi(getenv("GN_HF_DBG")) : 0;
   if (getenv("GN_HF_T")) a.T = atoi(getenv("GN_HF_T"));
   const int SC = 128 / N;

@@ -41,8 +41,11 @@ int launch_hyper_agg_tc(const float* eo, const float* edge_feat, long long R, in
 
 // fused wide hyper aggregation, h_dim 256: H@h gather + T MLPs + H^T scatter (gn_hyper_fused_tc.cu)
 bool hyper_fused_fits(int N, int E, int D, int T);
+bool hyper_fused_post_fits(int Dout, long long ld_out);
+// node_out != nullptr: the closing MLP on [agg | h] / N runs in the same kernel and agg is not written
 int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat, int B, int N, int T,
-                          long long hstride, const gn_stage_weights* w, float* agg, cudaStream_t st);
+                          long long hstride, const gn_stage_weights* w, float* agg,
+                          float* node_out, long long ld_out, int Dout, cudaStream_t st);
 
 // fused node-level GEMM chains on tensor cores (gn_node_chain_tc.cu)
 struct NodeChainStep {

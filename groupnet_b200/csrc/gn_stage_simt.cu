@@ -1118,7 +1118,10 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     if (fused_agg) GN_TRY(launch_pair_agg_tc(h, efeat, B, N, T, w, agg, st));
     else GN_TRY(launch_edge2node_pair(P, efeat, B, N, T, w, G, S, st));
   } else if (fused_hyper) {
-    GN_TRY(launch_hyper_fused_tc(h, H, efeat, B, N, T, hstride, w, agg, st));
+    const bool post_in = hyper_fused_post_fits(c->Dout, ld_out);
+    GN_TRY(launch_hyper_fused_tc(h, H, efeat, B, N, T, hstride, w, agg, post_in ? node_out : nullptr,
+                                 ld_out, c->Dout, st));
+    if (post_in) return GN_OK;
   } else {
     if (tcn && hyper_agg_fits(D, T)) {
       GN_TRY(launch_hyper_agg_tc(eo, efeat, RE, T, w, ef, st));
@@ -1247,7 +1250,8 @@ int stage_launch_count(const gn_stage_cfg* c) {
   const bool chain = c->D == 64 && (c->Dout % 32 == 0) && c->Dout <= 128;
   const int pre = chain ? 1 : 3, post = chain ? 1 : 2;
   if (c->pairwise && pair_agg_fits(c->N, c->D, c->T)) return pre + (2 - fused) + 1 + post;
-  if (!c->pairwise && hyper_fused_fits(c->N, c->E, c->D, c->T)) return pre + 1 + 1 + 1 + post;
+  if (!c->pairwise && hyper_fused_fits(c->N, c->E, c->D, c->T))
+    return pre + 1 + 1 + 1 + (hyper_fused_post_fits(c->Dout, c->out_ld > 0 ? c->out_ld : c->Dout) ? 0 : post);
   if (!c->pairwise && hyper_agg_fits(c->D, c->T)) return pre + 1 + 1 + 1 + 1 + post;
   return c->pairwise ? (3 + chunks) + (2 - fused) + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
 }

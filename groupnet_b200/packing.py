@@ -69,16 +69,35 @@ def _hi_lo(v: torch.Tensor):
     return hi, (v - hi).to(torch.bfloat16).to(torch.float32)
 
 
-def hyper_fused_stream(agg_mlps, d: int) -> torch.Tensor:
+def hyper_fused_post_stream(w0, b0, w1, b1) -> torch.Tensor:
+    """Closing-MLP chunks appended to the fused kernel's stream (Dout % 32 == 0, <= 256):
+    post_w0 in four K chunks of 128 (the last with its bias block), post_w1 in two K chunks of 64."""
+    dev = w0.device                                                    # w0 (128, 2D), w1 (Dout, 128), fp32
+    parts = [_canon(w0[:, 128 * c:128 * (c + 1)].contiguous()) for c in range(4)]
+    hi, lo = _hi_lo(b0)
+    blk = torch.zeros(128, 16, dtype=torch.float32, device=dev)
+    blk[:, 0], blk[:, 1] = hi, lo
+    parts.append(_canon(blk))
+    dout = w1.shape[0]
+    parts.append(_canon(w1[:, :64].contiguous()))
+    hi, lo = _hi_lo(b1)
+    blk = torch.zeros(dout, 16, dtype=torch.float32, device=dev)
+    blk[:, 0], blk[:, 1] = hi, lo
+    parts.append(_canon(blk))
+    parts.append(_canon(w1[:, 64:].contiguous()))
+    return torch.cat(parts).contiguous()
+
+
+def hyper_fused_stream(agg_params, d: int) -> torch.Tensor:
     """Weight stream of csrc/gn_hyper_fused_tc.cu (h_dim 256): the aggregation MLPs' chunks in MMA
     consumption order — G1 of step s before G2 of step s-1 — each chunk one canonical operand."""
-    t = len(agg_mlps)
-    dev = agg_mlps[0].layers[0].weight.device
+    t = len(agg_params)                                                # [(w0 (128,D), b0, w1 (D,128), b1)] fp32
+    dev = agg_params[0][0].device
     parts = []
     for s in range(t + 1):
         if s < t:
-            w0 = agg_mlps[s].layers[0].weight.detach().float()        # (128, D)
-            hi, lo = _hi_lo(agg_mlps[s].layers[0].bias.detach().float())
+            w0 = agg_params[s][0]
+            hi, lo = _hi_lo(agg_params[s][1])
             for j in range(2):
                 blk = torch.zeros(64, d + 16, dtype=torch.float32, device=dev)
                 blk[:, :d] = w0[j * 64:(j + 1) * 64]
@@ -86,8 +105,8 @@ def hyper_fused_stream(agg_mlps, d: int) -> torch.Tensor:
                 blk[:, d + 1] = lo[j * 64:(j + 1) * 64]
                 parts.append(_canon(blk))
         if s >= 1:
-            w1 = agg_mlps[s - 1].layers[1].weight.detach().float()    # (D, 128)
-            hi, lo = _hi_lo(agg_mlps[s - 1].layers[1].bias.detach().float())
+            w1 = agg_params[s - 1][2]
+            hi, lo = _hi_lo(agg_params[s - 1][3])
             blk = torch.zeros(d, 80, dtype=torch.float32, device=dev)
             blk[:, :64] = w1[:, :64]
             blk[:, 64], blk[:, 65], blk[:, 66] = hi, lo, hi
@@ -184,7 +203,13 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
         out["tc_post_w0"] = canonical_bf16(dev(post_mod.layers[0].weight))                        # (128, 2D)
         out["tc_post_w1"] = canonical_bf16(dev(post_mod.layers[1].weight))                        # (Dout, 128)
         if d == 256 and not layer._pairwise and t <= 15:
-            out["tc_hfuse_w"] = hyper_fused_stream([m.to(device) for m in agg], d)
+            stream = hyper_fused_stream([(dev(m.layers[0].weight), dev(m.layers[0].bias),
+                                          dev(m.layers[1].weight), dev(m.layers[1].bias)) for m in agg], d)
+            if dout % 32 == 0:
+                stream = torch.cat((stream, hyper_fused_post_stream(
+                    dev(post_mod.layers[0].weight), dev(post_mod.layers[0].bias),
+                    dev(post_mod.layers[1].weight), dev(post_mod.layers[1].bias))))
+            out["tc_hfuse_w"] = stream.contiguous()
 
     out["post_w0t"] = _kmajor(dev(post_mod.layers[0].weight), k2p, 128, 128)
     out["post_b0"] = dev(post_mod.layers[0].bias)

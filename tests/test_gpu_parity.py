@@ -348,6 +348,32 @@ def test_bf16_tc_large_batch_vs_fp32_path():
     assert torch.equal(n16, n16b) and torch.equal(f16, f16b)          # deterministic
 
 
+@pytest.mark.parametrize("n,scale,bo,b", [(64, 4, 256, 37), (64, 16, 96, 301), (20, 5, 256, 45), (32, 8, 80, 19),
+                                          (7, 3, 128, 130)])
+def test_bf16_wide_hyper_fused_vs_fp32_path(n, scale, bo, b):
+    """h_dim 256 hyper layers run the fused gather + T MLPs + scatter (+ closing MLP) kernel
+    (csrc/gn_hyper_fused_tc.cu): many tiles per CTA, ragged last tile (b % (128 // n) != 0), scene
+    counts per tile that do not fill 128 rows (n = 20, 7), closing MLP fused (bo % 32 == 0) or not (bo = 80)."""
+    torch.manual_seed(91)
+    m = gb.MS_HGNN_hyper(256, 256, 64, bo, batch_norm=0, nmp_layers=1, scale=scale).to(DEV)
+    gen = torch.Generator().manual_seed(9)
+    h = torch.randn(b, n, 256, generator=gen).to(DEV)
+    corr = torch.bmm(torch.nn.functional.normalize(h, dim=2), torch.nn.functional.normalize(h, dim=2).transpose(1, 2))
+    u = torch.rand(b, n, 10, generator=gen).to(DEV)
+    n32, f32, h32 = m(h, corr, noise=[u])
+    m.set_precision("bf16")
+    n16, f16, h16 = m(h, corr, noise=[u])
+    assert torch.equal(h32, h16)
+    assert_close(f16, f32, BF16_REL, "factors bf16 vs fp32")
+    assert_close(n16, n32, BF16_REL, "node_feat bf16 vs fp32")
+    n16b, _, _ = m(h, corr, noise=[u])
+    assert torch.equal(n16, n16b)                                      # deterministic
+    # strided output (the concatenated feature tensor of PastEncoder.forward, :301-309)
+    wide = torch.zeros(b, n, bo + 64, device=DEV)
+    m(h, corr, noise=[u], out=wide[:, :, 32:32 + bo], want_factors=False)
+    assert torch.equal(wide[:, :, 32:32 + bo], n16) and float(wide[:, :, :32].abs().max()) == 0.0
+
+
 # ---- T7: backward (gn_stage_bwd) vs torch autograd through the CPU oracle ---------------------
 @pytest.mark.train
 @pytest.mark.parametrize("kind,n,d,bo,scale,layers,b", [
