@@ -445,6 +445,164 @@ node2edge_hyper_warp_kernel(const float* __restrict__ xprime, const float* __res
 }
 
 // ===========================================================================
+// k2d: node2edge, hyper, FOUR LANES PER HYPEREDGE (E >= 4, N <= 64).  Same math as k2b/k2c.
+// Lane q of a quad owns attention hidden units [8q, 8q+8) and feature columns [16q, 16q+16) (and a
+// quarter of the h columns when eo = H @ h is wanted), so the per-member work is 128-bit shared-memory
+// loads + FMAs with one 2-step quad reduction for the logit: ~7x fewer warp instructions per edge than
+// the warp-per-edge form, and a 256-thread CTA is fully busy at E = 64 (crowd) and at 5 NBA scenes.
+// The softmax over all N nodes (:135-137) is accumulated online (running max, rescale on change), so
+// the member list — a 64-bit mask from the incidence row — is walked only twice.
+// ===========================================================================
+template <int EOC>   // float4 chunks of eo per lane = D / 16 (0: eo not wanted)
+__global__ void __launch_bounds__(256, EOC <= 4 ? 3 : 2)
+node2edge_hyper_quad_kernel(const float* __restrict__ xprime, const float* __restrict__ pq,
+                            const float* __restrict__ h, const float* __restrict__ H,
+                            int B, int N, int E, long long hstride, int SC, gn_stage_weights W,
+                            float* __restrict__ edges, float* __restrict__ eo) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int D = EOC * 16, LDH = D + 4;
+  const int maxnodes = SC * N, maxedges = SC * E;
+  float* xs = smem;                               // [SC*N][68]
+  float* ps = xs + maxnodes * N2E_LD;             // [SC*N][68]  pn | q
+  float* Hs = ps + maxnodes * N2E_LD;             // [SC*E][N]
+  float* hs = Hs + ((maxedges * N + 3) & ~3);     // [SC*N][D+4]
+  const int tid = threadIdx.x, q = tid & 3, slot = tid >> 2;
+  const unsigned qmask = 0xFu << (tid & 28);      // the quad's lanes: member loops diverge between quads
+  float b0[8], w1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { b0[k] = __ldg(W.att_b0 + q * 8 + k); w1[k] = __ldg(W.att_w1 + q * 8 + k); }
+  const float b1 = __ldg(W.att_b1);
+  const int ntiles = (B + SC - 1) / SC;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b0s = tile * SC, ns = min(SC, B - b0s);
+    const int nn = ns * N, ne = ns * E;
+    __syncthreads();
+    for (int i = tid; i < nn * 16; i += 256) {
+      const int n = i >> 4, c = i & 15;
+      const size_t g = (static_cast<size_t>(b0s) * N + n) * 64 + 4 * c;
+      *reinterpret_cast<float4*>(xs + n * N2E_LD + 4 * c) = ldg_f4(xprime + g);
+      *reinterpret_cast<float4*>(ps + n * N2E_LD + 4 * c) = ldg_f4(pq + g);
+    }
+    if (EOC > 0) {
+      constexpr int d4 = D / 4 > 0 ? D / 4 : 1;
+      const float* src = h + static_cast<size_t>(b0s) * N * D;
+      for (int i = tid; i < nn * d4; i += 256) {
+        const int n = i / d4, c = i - n * d4;
+        *reinterpret_cast<float4*>(hs + n * LDH + 4 * c) = ldg_f4(src + static_cast<size_t>(n) * D + 4 * c);
+      }
+    }
+    {
+      const int per = E * N;
+      if (((per | static_cast<int>(hstride & 3)) & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
+        const int per4 = per >> 2;
+        for (int i = tid; i < ns * per4; i += 256) {
+          const int sc = i / per4, r = i - sc * per4;
+          *reinterpret_cast<float4*>(Hs + 4 * i) = ldg_f4(H + static_cast<size_t>(b0s + sc) * hstride + 4 * r);
+        }
+      } else {
+        for (int i = tid; i < ns * per; i += 256) {
+          const int sc = i / per, r = i - sc * per;
+          Hs[i] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + r);
+        }
+      }
+    }
+    __syncthreads();
+    for (int e = slot; e < ne; e += 64) {
+      const bool live = true;
+      const int ee = e;
+      const int sc = ee / E, nb = sc * N;
+      const float* Hr = Hs + ee * N;
+      // membership mask: lane q tests agents [16q, 16q+16)
+      unsigned lo = 0u, hi = 0u;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = q * 16 + i;
+        if (live && n < N && Hr[n] != 0.f) { if (n < 32) lo |= 1u << n; else hi |= 1u << (n - 32); }
+      }
+      lo |= __shfl_xor_sync(qmask, lo, 1); hi |= __shfl_xor_sync(qmask, hi, 1);
+      lo |= __shfl_xor_sync(qmask, lo, 2); hi |= __shfl_xor_sync(qmask, hi, 2);
+      const int cnt = __popc(lo) + __popc(hi);
+      // pe[k] = b0[k] + sum_m H[e,m] q_m[k]
+      float pe[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) pe[k] = b0[k];
+      for (int half = 0; half < 2; ++half)
+        for (unsigned mm = half ? hi : lo; mm; mm &= mm - 1) {
+          const int n = __ffs(mm) - 1 + 32 * half;
+          const float hv = Hr[n];
+          const float* qr = ps + (nb + n) * N2E_LD + 32 + q * 8;
+          const float4 u = *reinterpret_cast<const float4*>(qr), v = *reinterpret_cast<const float4*>(qr + 4);
+          pe[0] = fmaf(hv, u.x, pe[0]); pe[1] = fmaf(hv, u.y, pe[1]); pe[2] = fmaf(hv, u.z, pe[2]); pe[3] = fmaf(hv, u.w, pe[3]);
+          pe[4] = fmaf(hv, v.x, pe[4]); pe[5] = fmaf(hv, v.y, pe[5]); pe[6] = fmaf(hv, v.z, pe[6]); pe[7] = fmaf(hv, v.w, pe[7]);
+        }
+      // logits + online softmax over ALL N nodes (non-members: logit 0) + weighted gather
+      float mx = (cnt < N) ? 0.f : -INFINITY;
+      float den = static_cast<float>(N - cnt);
+      float acc[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+      float eacc[EOC > 0 ? EOC * 4 : 1];
+#pragma unroll
+      for (int c = 0; c < (EOC > 0 ? EOC * 4 : 1); ++c) eacc[c] = 0.f;
+      for (int half = 0; half < 2; ++half)
+        for (unsigned mm = half ? hi : lo; mm; mm &= mm - 1) {
+          const int n = __ffs(mm) - 1 + 32 * half;
+          const float hv = Hr[n];
+          const float* pr = ps + (nb + n) * N2E_LD + q * 8;
+          const float4 u = *reinterpret_cast<const float4*>(pr), v = *reinterpret_cast<const float4*>(pr + 4);
+          float part = fmaxf(u.x + pe[0], 0.f) * w1[0];
+          part = fmaf(fmaxf(u.y + pe[1], 0.f), w1[1], part); part = fmaf(fmaxf(u.z + pe[2], 0.f), w1[2], part);
+          part = fmaf(fmaxf(u.w + pe[3], 0.f), w1[3], part); part = fmaf(fmaxf(v.x + pe[4], 0.f), w1[4], part);
+          part = fmaf(fmaxf(v.y + pe[5], 0.f), w1[5], part); part = fmaf(fmaxf(v.z + pe[6], 0.f), w1[6], part);
+          part = fmaf(fmaxf(v.w + pe[7], 0.f), w1[7], part);
+          part += __shfl_xor_sync(qmask, part, 1);
+          part += __shfl_xor_sync(qmask, part, 2);
+          const float a = (part + b1) * hv;
+          if (a > mx) {
+            const float s = expf(mx - a);
+            den *= s;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) acc[c] *= s;
+            mx = a;
+          }
+          const float ex = expf(a - mx);
+          den += ex;
+          const float wgt = ex * hv;
+          const float* xr = xs + (nb + n) * N2E_LD + q * 16;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(xr + c);
+            acc[c] = fmaf(wgt, xv.x, acc[c]); acc[c + 1] = fmaf(wgt, xv.y, acc[c + 1]);
+            acc[c + 2] = fmaf(wgt, xv.z, acc[c + 2]); acc[c + 3] = fmaf(wgt, xv.w, acc[c + 3]);
+          }
+          if (EOC > 0) {
+            const float* hr = hs + (nb + n) * LDH + q * (EOC * 4);
+#pragma unroll
+            for (int c = 0; c < EOC * 4; c += 4) {
+              const float4 hv4 = *reinterpret_cast<const float4*>(hr + c);
+              eacc[c] = fmaf(hv, hv4.x, eacc[c]); eacc[c + 1] = fmaf(hv, hv4.y, eacc[c + 1]);
+              eacc[c + 2] = fmaf(hv, hv4.z, eacc[c + 2]); eacc[c + 3] = fmaf(hv, hv4.w, eacc[c + 3]);
+            }
+          }
+        }
+      if (live) {
+        const float inv = 1.f / den;
+        float* dst = edges + (static_cast<size_t>(b0s) * E + e) * GN_ATT_DIM + q * 16;
+#pragma unroll
+        for (int c = 0; c < 16; c += 4)
+          *reinterpret_cast<float4*>(dst + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+        if (EOC > 0) {
+          float* de = eo + (static_cast<size_t>(b0s) * E + e) * D + q * (EOC * 4);
+#pragma unroll
+          for (int c = 0; c < EOC * 4; c += 4)
+            *reinterpret_cast<float4*>(de + c) = make_float4(eacc[c], eacc[c + 1], eacc[c + 2], eacc[c + 3]);
+        }
+      }
+    }
+  }
+}
+
+// ===========================================================================
 // k3: edge_mlp — MLP_dict_softmax (:31-53) + Gumbel softmax (:446-520)
 // rows = B*E edge rows, row independent.
 // smem: eT [64][LD] (reused for z) | bufT [128][LD] | wp [2*KC*128] |
@@ -926,6 +1084,34 @@ static int launch_node2edge_pair(const float* xprime, const float* pq, int B, in
 static int launch_node2edge_hyper(const float* xprime, const float* pq, const float* h, const float* H,
                                   int B, int N, int E, int D, long long hstride, const gn_stage_weights* w,
                                   float* edges, float* eo, cudaStream_t st) {
+  const int eoc = eo ? D / 16 : 0;
+  if (N <= 64 && E >= 4 && E <= 64 && (!eo || D == 64 || D == 128 || D == 256)) {   // four lanes per hyperedge
+    auto qbytes = [&](int sc) -> size_t {
+      size_t nodes = static_cast<size_t>(sc) * N, ed = static_cast<size_t>(sc) * E;
+      return (2 * nodes * N2E_LD + ((ed * N + 3) & ~size_t(3)) + (eo ? nodes * (D + 4) : 0)) * 4;
+    };
+    int SC = 64 / E;
+    if (SC < 1) SC = 1;
+    while (SC > 1 && qbytes(SC) > 56 * 1024) --SC;
+    const size_t smem = qbytes(SC);
+    const int ntiles = (B + SC - 1) / SC;
+    auto go = [&](auto kern) -> int {
+      GN_TRY(set_smem(kern, smem));
+      int occ = 1;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem) != cudaSuccess || occ < 1) occ = 1;
+      const int grid = ntiles < GN_SM_COUNT * occ ? ntiles : GN_SM_COUNT * occ;
+      { ProfScope ps__("node2edge_hyper", st);
+        kern<<<grid, 256, smem, st>>>(xprime, pq, h, H, B, N, E, hstride, SC, *w, edges, eo); }
+      GN_LAUNCH_CHECK();
+      return GN_OK;
+    };
+    switch (eoc) {
+      case 0:  return go(node2edge_hyper_quad_kernel<0>);
+      case 4:  return go(node2edge_hyper_quad_kernel<4>);
+      case 8:  return go(node2edge_hyper_quad_kernel<8>);
+      default: return go(node2edge_hyper_quad_kernel<16>);
+    }
+  }
   if (N <= 64 && E <= 64 && D <= 256 && (D & 3) == 0) {          // warp per hyperedge
     auto wbytes = [&](int sc) -> size_t {
       size_t nodes = static_cast<size_t>(sc) * N, ed = static_cast<size_t>(sc) * E;
