@@ -44,7 +44,7 @@ class GroupNetLibraryError(RuntimeError):
 
 
 class StageWeights(C.Structure):
-    """struct gn_stage_weights (36 device pointers, header order)."""
+    """struct gn_stage_weights (37 device pointers, header order)."""
     FIELDS = (
         "node_w0t", "node_b0", "node_w1t", "node_b1",
         "att_wpqt", "att_b0", "att_w1", "att_b1",
@@ -53,7 +53,7 @@ class StageWeights(C.Structure):
         "agg_w0t", "agg_b0", "agg_w1t", "agg_b1",
         "post_w0t", "post_b0", "post_w1t", "post_b1",
         "tc_init_w0", "tc_init_w1", "tc_df_w0", "tc_df_w1",
-        "tc_node_w0", "tc_node_w1", "tc_att_wpq", "tc_agg_w0", "tc_agg_w1", "tc_post_w0", "tc_post_w1", "tc_hfuse_w",
+        "tc_node_w0", "tc_node_w1", "tc_att_wpq", "tc_agg_w0", "tc_agg_w1", "tc_post_w0", "tc_post_w1", "tc_hfuse_w", "tc_npre_w",
     )
     _fields_ = [(name, C.c_void_p) for name in FIELDS]
 

@@ -47,6 +47,11 @@ int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat
                           long long hstride, const gn_stage_weights* w, float* agg,
                           float* node_out, long long ld_out, int Dout, cudaStream_t st);
 
+// fused wide node prologue h -> x', pq for h_dim 256 (gn_node_pre256_tc.cu)
+bool node_pre256_fits(int D);
+int launch_node_pre256_tc(const float* h, long long R, const gn_stage_weights* w, float* xprime, float* pq,
+                          cudaStream_t st);
+
 // fused node-level GEMM chains on tensor cores (gn_node_chain_tc.cu)
 struct NodeChainStep {
   const __nv_bfloat16* W;     // canonical (N x K)

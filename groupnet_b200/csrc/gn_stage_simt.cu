@@ -1237,6 +1237,9 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     GN_TRY(launch_node_chain_tc(a, "node_pre_chain_tc", st));
   } else if (tcn) {
     TcLinArgs a = lin_args();
+    if (node_pre256_fits(D)) {
+      GN_TRY(launch_node_pre256_tc(h, R, w, xprime, pq, st));
+    } else {
     a.A0 = h; a.a0_is_f32 = 1; a.lda0 = D; a.K0 = D; a.R = R;
     a.W = static_cast<const __nv_bfloat16*>(w->tc_node_w0); a.Ntot = 256; a.N = 256;
     a.bias = w->node_b0; a.relu = 1; a.out = hid; a.out_is_f32 = 0; a.ldo = 256;
@@ -1251,6 +1254,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     a.W = static_cast<const __nv_bfloat16*>(w->tc_att_wpq); a.Ntot = 64; a.N = 64;
     a.out = pq; a.out_is_f32 = 1; a.ldo = 64;
     GN_TRY(launch_tc_linear(a, "att_proj_tc", st));
+    }
     if (c->pairwise && !fused_agg) {
       const int NT = T * 128;
       for (int n0 = 0; n0 < NT; n0 += 256) {
@@ -1434,12 +1438,12 @@ int stage_launch_count(const gn_stage_cfg* c) {
   if (!p.tc_nodes) return (c->pairwise ? 5 : 6) - fused;
   const int chunks = (c->T * 128 + 255) / 256;
   const bool chain = c->D == 64 && (c->Dout % 32 == 0) && c->Dout <= 128;
-  const int pre = chain ? 1 : 3, post = chain ? 1 : 2;
+  const int pre = (chain || node_pre256_fits(c->D)) ? 1 : 3, post = chain ? 1 : 2;
   if (c->pairwise && pair_agg_fits(c->N, c->D, c->T)) return pre + (2 - fused) + 1 + post;
   if (!c->pairwise && hyper_fused_fits(c->N, c->E, c->D, c->T))
     return pre + 1 + 1 + 1 + (hyper_fused_post_fits(c->Dout, c->out_ld > 0 ? c->out_ld : c->Dout) ? 0 : post);
   if (!c->pairwise && hyper_agg_fits(c->D, c->T)) return pre + 1 + 1 + 1 + 1 + post;
-  return c->pairwise ? (3 + chunks) + (2 - fused) + 1 + 3 : 3 + 1 + 1 + (chunks + 1) + 1 + 2;
+  return c->pairwise ? (pre + chunks) + (2 - fused) + 1 + 3 : pre + 1 + 1 + (chunks + 1) + 1 + 2;
 }
 
 }  // namespace gn

@@ -69,6 +69,24 @@ def _hi_lo(v: torch.Tensor):
     return hi, (v - hi).to(torch.bfloat16).to(torch.float32)
 
 
+def node_pre256_stream(w0, b0, w1, b1, wpq) -> torch.Tensor:
+    """Weight stream of csrc/gn_node_pre256_tc.cu: w0 (256, 256) in four K chunks of 64 with its bias block
+    after the last, [w1 (64, 256) | b1], wpq (64, 64) = [Wp ; Wq]."""
+    dev = w0.device
+    parts = [_canon(w0[:, 64 * c:64 * (c + 1)].contiguous()) for c in range(4)]
+    hi, lo = _hi_lo(b0)
+    blk = torch.zeros(256, 16, dtype=torch.float32, device=dev)
+    blk[:, 0], blk[:, 1] = hi, lo
+    parts.append(_canon(blk))
+    hi, lo = _hi_lo(b1)
+    blk = torch.zeros(64, 272, dtype=torch.float32, device=dev)
+    blk[:, :256] = w1
+    blk[:, 256], blk[:, 257] = hi, lo
+    parts.append(_canon(blk))
+    parts.append(_canon(wpq))
+    return torch.cat(parts).contiguous()
+
+
 def hyper_fused_post_stream(w0, b0, w1, b1) -> torch.Tensor:
     """Closing-MLP chunks appended to the fused kernel's stream (Dout % 32 == 0, <= 256):
     post_w0 in four K chunks of 128 (the last with its bias block), post_w1 in two K chunks of 64."""
@@ -202,6 +220,9 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
         out["tc_agg_w1"] = canonical_bf16(torch.cat([dev(m.layers[1].weight) for m in agg], dim=1))  # (D, T*128)
         out["tc_post_w0"] = canonical_bf16(dev(post_mod.layers[0].weight))                        # (128, 2D)
         out["tc_post_w1"] = canonical_bf16(dev(post_mod.layers[1].weight))                        # (Dout, 128)
+        if d == 256:
+            out["tc_npre_w"] = node_pre256_stream(dev(node[0].weight), dev(node[0].bias), dev(node[1].weight),
+                                                  dev(node[1].bias), torch.cat((w0[:, :64], w0[:, 64:]), dim=0).contiguous())
         if d == 256 and not layer._pairwise and t <= 15:
             stream = hyper_fused_stream([(dev(m.layers[0].weight), dev(m.layers[0].bias),
                                           dev(m.layers[1].weight), dev(m.layers[1].bias)) for m in agg], d)

@@ -114,6 +114,10 @@ typedef struct gn_stage_weights {
    * for s = 0..T: [s < T: W0_s rows 0..63 | b0 (hi,lo) (64 x 272), W0_s rows 64..127 (64 x 272)]
    *               [s >= 1, t = s-1: W1_t[:, 0:64] | b1_t (hi,lo,hi) (256 x 80), W1_t[:, 64:128] (256 x 64)] */
   const void* tc_hfuse_w;
+  /* weight stream of the fused wide node prologue (csrc/gn_node_pre256_tc.cu; D == 256 only, else NULL):
+   * node W0[:, 64c:64c+64] (256 x 64) for c = 0..3, b0 (hi,lo) block (256 x 16), [W1 | b1 (hi,lo)] (64 x 272),
+   * [Wp ; Wq] (64 x 64) */
+  const void* tc_npre_w;
 } gn_stage_weights;
 
 typedef struct gn_stage_cfg {
