@@ -20,7 +20,6 @@
 // warp 9 issues every tcgen05.mma.  G1 of step t+1 is issued before G2 of step t, so the drains
 // overlap the tensor pipe.  Per 128-row tile the weight stream is 1.41 MB from L2: the kernel is
 // L2->SM bandwidth bound (~42 B/clk/SM), not tensor-pipe bound; see DESIGN.md.
-#include <cstdlib>
 #include "gn_tc.cuh"
 #include "gn_stage.h"
 
@@ -54,10 +53,13 @@ constexpr uint32_t OFF_X = OFF_A2, OFF_Y = OFF_RING + 2 * STAGE, OFF_AH = OFF_RI
 static_assert(P0B_CHUNK <= A2_0_BYTES + 128 * 64 * 2, "post chunk must fit the A2 region");
 }  // namespace hf
 
+extern unsigned long long* g_trace_buffer;
+
 struct HyperFusedArgs {
   const float* h; const float* H; const float* edge_feat; const unsigned char* wstream;
-  float* agg; int B, N, T; long long hstride; int dbg;
+  float* agg; int B, N, T; long long hstride;
   float* node_out; long long ld_out; int Dout; int post; size_t post_off;
+  unsigned long long* trace;          // optional: clock64() per phase, block 0, first tiles (gn_profile_set_trace)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
@@ -70,6 +72,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void drain_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Coalesced copy of the tile's incidence blocks (ns scenes x N x N fp32) into shared memory, row stride ldr
+// floats ((N rounded up to 4) + 4: a thread reading "its" row with 128-bit loads does not bank-conflict).
+__device__ __forceinline__ void stage_raw_H(float* raw, const float* __restrict__ H, long long hstride,
+                                            int b0s, int ns, int N, int ldr, int tid) {
+  const int per = N * N;
+  if ((N & 3) == 0 && (hstride & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
+    const int n4 = N >> 2, per4 = per >> 2;
+    for (int i = tid; i < ns * per4; i += 256) {
+      const int sc = i / per4, r4 = i - sc * per4;
+      const int e = r4 / n4, c4 = r4 - e * n4;
+      *reinterpret_cast<float4*>(raw + (sc * N + e) * ldr + 4 * c4) =
+          ldg_f4(H + static_cast<size_t>(b0s + sc) * hstride + 4 * r4);
+    }
+  } else {
+    for (int i = tid; i < ns * per; i += 256) {
+      const int sc = i / per, r = i - sc * per;
+      const int e = r / N, n = r - e * N;
+      raw[(sc * N + e) * ldr + n] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + r);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(hf::THREADS, 1)
@@ -107,11 +133,8 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       auto load = [&](const unsigned char*& src, uint32_t bytes) {
         tc::mbar_wait(bars + B_WEMPTY + stage, (ph_empty >> stage) & 1u);
         ph_empty ^= 1u << stage;
-        if (a.dbg & 1) mbar_arrive(bars + B_WFULL + stage);
-        else {
         mbar_expect_tx(bars + B_WFULL + stage, bytes);
         bulk_g2s(sbase + OFF_RING + stage * STAGE, src, bytes, bars + B_WFULL + stage);
-        }
         src += bytes;
         stage = stage == NSTAGE - 1 ? 0 : stage + 1;
       };
@@ -153,7 +176,16 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       ph |= 0xFu << B_HFREE;                             // "free" barriers: the first wait passes
       int stage = 0;
       auto wait = [&](int i) { tc::mbar_wait(bars + i, (ph >> i) & 1u); ph ^= 1u << i; };
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      long long wacc[4] = {0, 0, 0, 0};
+      int ititer = 0;
+      auto wait_t = [&](int i, int slot) {
+        if (a.trace == nullptr) { wait(i); return; }
+        const long long t0 = clock64(); wait(i); wacc[slot] += clock64() - t0;
+      };
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ititer) {
+        if (a.trace != nullptr && blockIdx.x == 0 && ititer > 0 && ititer <= 8) {
+          for (int k = 0; k < 4; ++k) { a.trace[128 + (ititer - 1) * 4 + k] = wacc[k]; wacc[k] = 0; }
+        }
         wait(B_STAGE);
         tc::fence_after_thread_sync();
         tc::issue_gemm(tmem + TM_EF, sbase + OFF_A2, sbase + OFF_RING, 256, 128, false);     // eo = Hblk * h
@@ -165,10 +197,9 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
           if (s < T) {
             const int p = s & 1;
             for (int j = 0; j < 2; ++j) {
-              wait(B_HFREE + j * 2 + p);
-              wait(B_WFULL + stage);
+              wait_t(B_HFREE + j * 2 + p, 0);
+              wait_t(B_WFULL + stage, 1);
               tc::fence_after_thread_sync();
-              if (!(a.dbg & 2))
               tc::issue_gemm(tmem + TM_HB + (p * 2 + j) * 64, sbase + OFF_EO, sbase + OFF_RING + stage * STAGE,
                              64, 272, false);
               tc::mma_commit(bars + B_WEMPTY + stage);
@@ -178,10 +209,9 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
           }
           if (s >= 1) {
             for (int j = 0; j < 2; ++j) {
-              wait(B_A2FULL + j);
-              wait(B_WFULL + stage);
+              wait_t(B_A2FULL + j, 2);
+              wait_t(B_WFULL + stage, 3);
               tc::fence_after_thread_sync();
-              if (!(a.dbg & 4))
               tc::issue_gemm(tmem + TM_EF, sbase + (j ? OFF_A2_1 : OFF_A2), sbase + OFF_RING + stage * STAGE,
                              256, j ? 64 : 80, !(s == 1 && j == 0));
               tc::mma_commit(bars + B_WEMPTY + stage);
@@ -242,28 +272,36 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
     auto wait = [&](int i) { tc::mbar_wait(bars + i, (ph >> i) & 1u); ph ^= 1u << i; };
     const int r128 = tid & 127, half = tid >> 7;
     const int sc_r = r128 / N, in_r = r128 - sc_r * N;   // scene-in-tile and index-in-scene of row r128
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ldr = ((N + 3) & ~3) + 4;                  // row stride of the raw incidence staging
+    int titer = 0;
+#define HF_TRACE(pt) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && titer < 8) \
+    a.trace[titer * 16 + (pt)] = clock64(); } while (0)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
       const int b0s = tile * SC;
+      HF_TRACE(0);
       const int ns = min(SC, a.B - b0s);
       const int rows_used = ns * N;
-      // ---- Hblk[edge row][node column] (A operand, block diagonal), rows = r128, k-groups of this half
+      // ---- Hblk[edge row][node column] (A operand, block diagonal): raw incidence rows staged coalesced in
+      //      the (idle) eo region, then each thread packs the k-groups of its row
       {
+        float* raw = reinterpret_cast<float*>(smem + OFF_EO);
+        drain_bar();                                      // the previous tile's output transposes used this region
+        stage_raw_H(raw, a.H, a.hstride, b0s, ns, N, ldr, tid);
+        drain_bar();
         const bool valid = r128 < rows_used;
-        const float* Hrow = a.H + static_cast<size_t>(b0s + sc_r) * a.hstride + static_cast<size_t>(in_r) * N;
-        const bool vec = ((N & 7) == 0) && ((a.hstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.H) & 15) == 0);
+        const float* Hrow = raw + r128 * ldr;
 #pragma unroll 4
         for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
           float v[8];
           const int n0 = kg * 8 - sc_r * N;
-          if (vec) {                                      // N % 8 == 0: a k-group never straddles a scene
-            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-            if (valid && n0 >= 0 && n0 < N) { x = ldg_f4(Hrow + n0); y = ldg_f4(Hrow + n0 + 4); }
+          if (valid && n0 >= 0 && n0 + 8 <= N && (N & 3) == 0) {
+            const float4 x = *reinterpret_cast<const float4*>(Hrow + n0), y = *reinterpret_cast<const float4*>(Hrow + n0 + 4);
             v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int n = n0 + i;
-              v[i] = (valid && n >= 0 && n < N) ? __ldg(Hrow + n) : 0.f;
+              v[i] = (valid && n >= 0 && n < N) ? Hrow[n] : 0.f;
             }
           }
           *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) =
@@ -271,6 +309,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
                          tc::pack_bf16(v[6], v[7]));
         }
       }
+      HF_TRACE(1);
       // ---- hT[column c][node k] (B operand): thread = column, 8 nodes per 16-byte store
       {
         const float* hsrc = a.h + static_cast<size_t>(b0s) * N * D + tid;
@@ -289,11 +328,13 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       }
       tc::fence_proxy_async_smem();
       mbar_arrive(bars + B_STAGE);
+      HF_TRACE(2);
       const bool rowvalid = row < rows_used;
       const float* efrow = a.edge_feat + (static_cast<size_t>(b0s) * N + row) * T;
       float wnext = rowvalid ? __ldg(efrow) : 0.f;
       // ---- eo: TMEM -> bf16 A operand, this group's 128 columns
       wait(B_EOFULL);
+      HF_TRACE(3);
       tc::fence_after_thread_sync();
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
@@ -308,6 +349,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       tc::fence_proxy_async_smem();
       tc::fence_before_thread_sync();
       mbar_arrive(bars + B_EOREADY);
+      HF_TRACE(4);
       // ---- main loop: hidden half g of step t -> A2_g
       unsigned char* a2 = smem + (g ? OFF_A2_1 : OFF_A2);
 #pragma unroll 1
@@ -315,6 +357,21 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         const int p = t & 1;
         const float w = wnext;
         if (t + 1 < T) wnext = rowvalid ? __ldg(efrow + t + 1) : 0.f;
+        if (t == 1 && tile + static_cast<int>(gridDim.x) < ntiles) {      // next tile's h, H, edge_feat -> L2
+          const int nb0 = (tile + gridDim.x) * SC;
+          const int nns = min(SC, a.B - nb0);
+          const char* hp = reinterpret_cast<const char*>(a.h + static_cast<size_t>(nb0) * N * D);
+          const int hlines = (nns * N * D * 4 + 127) >> 7;
+          for (int i = tid; i < hlines; i += 256) asm volatile("prefetch.global.L2 [%0];" :: "l"(hp + (static_cast<size_t>(i) << 7)));
+          const int per_lines = (N * N * 4 + 127) >> 7;
+          for (int i = tid; i < nns * per_lines; i += 256) {
+            const int sc = i / per_lines, l = i - sc * per_lines;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(a.H + static_cast<size_t>(nb0 + sc) * a.hstride) + (static_cast<size_t>(l) << 7)));
+          }
+          const char* ep = reinterpret_cast<const char*>(a.edge_feat + static_cast<size_t>(nb0) * N * T);
+          const int elines = (nns * N * T * 4 + 127) >> 7;
+          for (int i = tid; i < elines; i += 256) asm volatile("prefetch.global.L2 [%0];" :: "l"(ep + (static_cast<size_t>(i) << 7)));
+        }
         wait(B_HFULL + g * 2 + p);
         tc::fence_after_thread_sync();
         uint32_t r0[32], r1[32];
@@ -354,24 +411,30 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         mbar_arrive(bars + B_A2FULL + g);
       }
       // ---- epilogue: HblkT (A), efT (B), then agg out
+      HF_TRACE(5);
       wait(B_EFFULL);
+      HF_TRACE(6);
       tc::fence_after_thread_sync();
       {
+        float* raw = reinterpret_cast<float*>(smem + OFF_AH);     // ring stages 0-1 are idle since ef_full
+        stage_raw_H(raw, a.H, a.hstride, b0s, ns, N, ldr, tid);
+        drain_bar();
         const bool valid = r128 < rows_used;             // r128 = node row here
-        const float* Hcol = a.H + static_cast<size_t>(b0s + sc_r) * a.hstride + in_r;
+        const float* Hcol = raw + sc_r * N * ldr + in_r;
 #pragma unroll 2
         for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int e = kg * 8 + i - sc_r * N;
-            v[i] = (valid && e >= 0 && e < N) ? __ldg(Hcol + static_cast<size_t>(e) * N) : 0.f;
+            v[i] = (valid && e >= 0 && e < N) ? Hcol[e * ldr] : 0.f;
           }
           *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) =
               make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
                          tc::pack_bf16(v[6], v[7]));
         }
       }
+      HF_TRACE(7);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         float v[32];
@@ -391,22 +454,32 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       tc::fence_proxy_async_smem();
       tc::fence_before_thread_sync();
       mbar_arrive(bars + B_EFTREADY);
+      HF_TRACE(8);
       if (a.post) {
         const float inv_n = 1.f / static_cast<float>(N);
-        // h rows / N -> A operand columns 256..511 (ring stages 0-1 are idle since ef_full)
+        // h rows / N -> A operand columns 256..511 (ring stages 0-1; the raw incidence copy there is dead once
+        // every thread has built its HblkT rows).  A warp pass covers 8 rows x 4 k-groups: 128 contiguous
+        // bytes per row from L2.
+        drain_bar();
         {
-          const bool valid = r128 < rows_used;
-          const float* hrow = a.h + (static_cast<size_t>(b0s) * N + r128) * D;
-#pragma unroll 4
-          for (int kg = half * 16; kg < half * 16 + 16; ++kg) {
+          const int r8 = lane & 7, kq = lane >> 3;
+#pragma unroll 8
+          for (int it = 0; it < 16; ++it) {
+            const int combo = warp * 16 + it;             // (row block 0..15) x (k-group block 0..7)
+            const int r = (combo >> 3) * 8 + r8, kg = (combo & 7) * 4 + kq;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-            if (valid) { x = ldg_f4(hrow + kg * 8); y = ldg_f4(hrow + kg * 8 + 4); }
-            *reinterpret_cast<uint4*>(smem + OFF_AH + kg * 2048 + r128 * 16) =
+            if (r < rows_used) {
+              const float* src = a.h + (static_cast<size_t>(b0s) * N + r) * D + kg * 8;
+              x = ldg_f4(src); y = ldg_f4(src + 4);
+            }
+            *reinterpret_cast<uint4*>(smem + OFF_AH + kg * 2048 + r * 16) =
                 make_uint4(tc::pack_bf16(x.x * inv_n, x.y * inv_n), tc::pack_bf16(x.z * inv_n, x.w * inv_n),
                            tc::pack_bf16(y.x * inv_n, y.y * inv_n), tc::pack_bf16(y.z * inv_n, y.w * inv_n));
           }
         }
+        HF_TRACE(9);
         wait(B_AGGFULL);
+        HF_TRACE(10);
         tc::fence_after_thread_sync();
         // agg / N -> A operand columns 0..255 (eo region; efT was consumed by the scatter MMA)
 #pragma unroll 1
@@ -424,8 +497,10 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         tc::fence_proxy_async_smem();
         tc::fence_before_thread_sync();
         mbar_arrive(bars + B_PAREADY);
+        HF_TRACE(11);
         // o1: relu -> bf16 A operand [128 x 128] (eo region), this group's 64 columns
         wait(B_O1FULL);
+        HF_TRACE(12);
         tc::fence_after_thread_sync();
         {
           uint32_t r0[32], r1[32];
@@ -449,21 +524,37 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         tc::fence_proxy_async_smem();
         tc::fence_before_thread_sync();
         mbar_arrive(bars + B_O1READY);
+        HF_TRACE(13);
         // node_feat rows: 32-column chunks alternate between the two groups
         wait(B_OUTFULL);
+        HF_TRACE(14);
         tc::fence_after_thread_sync();
-        float* orow = a.node_out + (static_cast<size_t>(b0s) * N + row) * a.ld_out;
+        // transpose each 32 x 32 block through shared memory (the eo region is dead): a warp store
+        // instruction then covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes
+        {
+          float* tb = reinterpret_cast<float*>(smem + OFF_EO) + warp * (32 * 36);
+          const int rr = lane >> 3, c4 = (lane & 7) * 4;
+          const int wrow0 = (warp & 3) * 32;
 #pragma unroll 1
-        for (int cc = g; cc * 32 < a.Dout; cc += 2) {
-          float v[32];
-          tc::tmem_ld32(tmem + lane_addr + TM_OUT + cc * 32, v);
-          if (rowvalid) {
+          for (int cc = g; cc * 32 < a.Dout; cc += 2) {
+            float v[32];
+            tc::tmem_ld32(tmem + lane_addr + TM_OUT + cc * 32, v);
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              *reinterpret_cast<float4*>(orow + cc * 32 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              *reinterpret_cast<float4*>(tb + lane * 36 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rr;
+              if (wrow0 + r < rows_used)
+                *reinterpret_cast<float4*>(a.node_out + (static_cast<size_t>(b0s) * N + wrow0 + r) * a.ld_out + cc * 32 + c4) =
+                    *reinterpret_cast<const float4*>(tb + r * 36 + c4);
+            }
           }
         }
         tc::fence_before_thread_sync();
+        HF_TRACE(15);
         continue;
       }
       wait(B_AGGFULL);
@@ -510,8 +601,7 @@ int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat
   a.node_out = node_out; a.ld_out = ld_out; a.Dout = Dout;
   a.post = node_out != nullptr ? 1 : 0;
   a.post_off = static_cast<size_t>(T) * (2 * hf::W0_CHUNK + hf::W1A_CHUNK + hf::W1B_CHUNK);
-  a.dbg = getenv("GN_HF_DBG") ? atoi(getenv("GN_HF_DBG")) : 0;
-  if (getenv("GN_HF_T")) a.T = atoi(getenv("GN_HF_T"));
+  a.trace = g_trace_buffer;
   const int SC = 128 / N;
   const int ntiles = (B + SC - 1) / SC;
   const int grid = ntiles < GN_SM_COUNT ? ntiles : GN_SM_COUNT;

@@ -206,10 +206,13 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, ui
                                            int N, int K, bool accumulate_first) {
   const uint32_t idesc = make_idesc_bf16(128, N);
   const uint32_t a_lbo = 128 * 16, b_lbo = static_cast<uint32_t>(N) * 16;
+  // one descriptor per operand, then the start-address field (bytes >> 4) advances by two k-groups per MMA:
+  // the issuing thread spends ~4 instructions per MMA instead of rebuilding both descriptors
+  uint64_t da = make_smem_desc(a_saddr, a_lbo, 128), db = make_smem_desc(b_saddr, b_lbo, 128);
+  const uint64_t ia = (2u * a_lbo) >> 4, ib = (2u * b_lbo) >> 4;
   for (int k = 0; k < K; k += 16) {
-    uint64_t da = make_smem_desc(a_saddr + (k >> 3) * a_lbo, a_lbo, 128);
-    uint64_t db = make_smem_desc(b_saddr + (k >> 3) * b_lbo, b_lbo, 128);
     mma_bf16_ss(tmem_d, da, db, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
+    da += ia; db += ib;
   }
 }
 
