@@ -10,8 +10,8 @@
 // (the generic path wrote and re-read eo, a (B*E, T*128) bf16 hidden tensor and ef).
 //
 //   gather   eo[128 x 256]   = Hblk[128 x 128] * hT[256 x 128]^T        (block-diagonal incidence)
-//   per t    hid_j[128 x 64] = [eo | 1][128 x 272] * [W0_tj | b0_tj]^T   j = 0,1  (bias through the MMA)
-//            ef[128 x 256]  += A2_j[128 x 64(+16)] * [W1_tj (| b1_t)]^T  A2_j = bf16(relu(hid_j) * edge_feat_t)
+//   per t    hid[128 x 128]  = [eo | 1][128 x 272] * [W0_t | b0_t]^T     (bias through the MMA; two K chunks)
+//            ef[128 x 256]  += A2_j[128 x 64(+16)] * [W1_tj (| b1_t)]^T  A2_j = bf16(relu(hid[:, 64j:64j+64]) * edge_feat_t)
 //   scatter  agg[128 x 256]  = HblkT[128 x 128] * efT[256 x 128]^T
 //
 // Warp roles (320 threads): warps 0-3 / 4-7 drain the two hidden halves (TMEM -> bf16 A2 operand),
@@ -27,7 +27,8 @@ namespace gn {
 namespace hf {
 constexpr int D = 256;
 constexpr int THREADS = 320;
-constexpr uint32_t W0_CHUNK = 64 * 272 * 2;      // 64 hidden units x (256 + 16 bias k-columns)
+constexpr uint32_t W0A_CHUNK = 128 * 128 * 2;    // W0_t[:, 0:128]
+constexpr uint32_t W0B_CHUNK = 128 * 144 * 2;    // W0_t[:, 128:256] | 16 bias k-columns
 constexpr uint32_t W1A_CHUNK = 256 * 80 * 2;     // 256 outputs x (64 hidden + 16 b1 k-columns)
 constexpr uint32_t W1B_CHUNK = 256 * 64 * 2;
 constexpr uint32_t STAGE = 40960;
@@ -108,7 +109,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
   if (tid == 0) {
     for (int i = 0; i < NBAR; ++i) {
       uint32_t cnt = 1;
-      if (i >= B_HFREE && i < B_HFREE + 4) cnt = 128;
+      if (i >= B_HFREE && i < B_HFREE + 4) cnt = 256;
       if (i >= B_A2FULL && i < B_A2FULL + 2) cnt = 128;
       if (i == B_STAGE || i == B_EOREADY || i == B_EFTREADY || i == B_PAREADY || i == B_O1READY) cnt = 256;
       tc::mbar_init(bars + i, cnt);
@@ -141,12 +142,12 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const unsigned char* src = a.wstream;
         stage = NSTAGE - 1;                              // every tile starts in the stage hT does not cover
-        load(src, W0_CHUNK);
+        load(src, W0A_CHUNK);
         tc::mbar_wait(bars + B_EOFULL, ph_eofull);      // hT (ring stages 0-1) consumed by the gather MMA
         ph_eofull ^= 1u;
-        load(src, W0_CHUNK);
+        load(src, W0B_CHUNK);
         for (int s = 1; s <= T; ++s) {
-          if (s < T) { load(src, W0_CHUNK); load(src, W0_CHUNK); }
+          if (s < T) { load(src, W0A_CHUNK); load(src, W0B_CHUNK); }
           load(src, W1A_CHUNK); load(src, W1B_CHUNK);
         }
         if (a.post) {
@@ -194,18 +195,21 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         tc::fence_after_thread_sync();
         stage = NSTAGE - 1;
         for (int s = 0; s <= T; ++s) {
-          if (s < T) {
+          if (s < T) {                                   // hid[128 x 128] = [eo | 1] * [W0_s | b0_s]^T, two K chunks
             const int p = s & 1;
-            for (int j = 0; j < 2; ++j) {
-              wait_t(B_HFREE + j * 2 + p, 0);
-              wait_t(B_WFULL + stage, 1);
-              tc::fence_after_thread_sync();
-              tc::issue_gemm(tmem + TM_HB + (p * 2 + j) * 64, sbase + OFF_EO, sbase + OFF_RING + stage * STAGE,
-                             64, 272, false);
-              tc::mma_commit(bars + B_WEMPTY + stage);
-              tc::mma_commit(bars + B_HFULL + j * 2 + p);
-              stage = stage == NSTAGE - 1 ? 0 : stage + 1;
-            }
+            wait_t(B_HFREE + p, 0);
+            wait_t(B_WFULL + stage, 1);
+            tc::fence_after_thread_sync();
+            tc::issue_gemm(tmem + TM_HB + p * 128, sbase + OFF_EO, sbase + OFF_RING + stage * STAGE, 128, 128, false);
+            tc::mma_commit(bars + B_WEMPTY + stage);
+            stage = stage == NSTAGE - 1 ? 0 : stage + 1;
+            wait_t(B_WFULL + stage, 1);
+            tc::fence_after_thread_sync();
+            tc::issue_gemm(tmem + TM_HB + p * 128, sbase + OFF_EO + 16 * 2048, sbase + OFF_RING + stage * STAGE,
+                           128, 144, true);
+            tc::mma_commit(bars + B_WEMPTY + stage);
+            tc::mma_commit(bars + B_HFULL + p);
+            stage = stage == NSTAGE - 1 ? 0 : stage + 1;
           }
           if (s >= 1) {
             for (int j = 0; j < 2; ++j) {
@@ -372,14 +376,14 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
           const int elines = (nns * N * T * 4 + 127) >> 7;
           for (int i = tid; i < elines; i += 256) asm volatile("prefetch.global.L2 [%0];" :: "l"(ep + (static_cast<size_t>(i) << 7)));
         }
-        wait(B_HFULL + g * 2 + p);
+        wait(B_HFULL + p);
         tc::fence_after_thread_sync();
         uint32_t r0[32], r1[32];
-        tc::tmem_ld32_nowait(tmem + lane_addr + TM_HB + (p * 2 + g) * 64, r0);
-        tc::tmem_ld32_nowait(tmem + lane_addr + TM_HB + (p * 2 + g) * 64 + 32, r1);
+        tc::tmem_ld32_nowait(tmem + lane_addr + TM_HB + p * 128 + g * 64, r0);
+        tc::tmem_ld32_nowait(tmem + lane_addr + TM_HB + p * 128 + g * 64 + 32, r1);
         tc::tmem_ld_wait();
         tc::fence_before_thread_sync();
-        mbar_arrive(bars + B_HFREE + g * 2 + p);
+        mbar_arrive(bars + B_HFREE + p);
         wait(B_A2FREE + g);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -600,7 +604,7 @@ int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat
   a.agg = agg; a.B = B; a.N = N; a.T = T; a.hstride = hstride;
   a.node_out = node_out; a.ld_out = ld_out; a.Dout = Dout;
   a.post = node_out != nullptr ? 1 : 0;
-  a.post_off = static_cast<size_t>(T) * (2 * hf::W0_CHUNK + hf::W1A_CHUNK + hf::W1B_CHUNK);
+  a.post_off = static_cast<size_t>(T) * (hf::W0A_CHUNK + hf::W0B_CHUNK + hf::W1A_CHUNK + hf::W1B_CHUNK);
   a.trace = g_trace_buffer;
   const int SC = 128 / N;
   const int ntiles = (B + SC - 1) / SC;

@@ -116,12 +116,11 @@ def hyper_fused_stream(agg_params, d: int) -> torch.Tensor:
         if s < t:
             w0 = agg_params[s][0]
             hi, lo = _hi_lo(agg_params[s][1])
-            for j in range(2):
-                blk = torch.zeros(64, d + 16, dtype=torch.float32, device=dev)
-                blk[:, :d] = w0[j * 64:(j + 1) * 64]
-                blk[:, d] = hi[j * 64:(j + 1) * 64]
-                blk[:, d + 1] = lo[j * 64:(j + 1) * 64]
-                parts.append(_canon(blk))
+            parts.append(_canon(w0[:, :128].contiguous()))             # K chunk 0
+            blk = torch.zeros(128, d - 128 + 16, dtype=torch.float32, device=dev)
+            blk[:, :d - 128] = w0[:, 128:]
+            blk[:, d - 128], blk[:, d - 127] = hi, lo
+            parts.append(_canon(blk))                                  # K chunk 1 | bias k-columns
         if s >= 1:
             w1 = agg_params[s - 1][2]
             hi, lo = _hi_lo(agg_params[s - 1][3])

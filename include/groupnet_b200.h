@@ -111,7 +111,7 @@ typedef struct gn_stage_weights {
   const void* tc_post_w1; /* N=Dout,  K=128    closing MLP layers.1 */
   /* weight stream of the fused wide hyper aggregation (csrc/gn_hyper_fused_tc.cu; D == 256 only, else
    * NULL): the agg_mlp chunks in the order the kernel consumes them, each a canonical operand:
-   * for s = 0..T: [s < T: W0_s rows 0..63 | b0 (hi,lo) (64 x 272), W0_s rows 64..127 (64 x 272)]
+   * for s = 0..T: [s < T: W0_s[:, 0:128] (128 x 128), W0_s[:, 128:256] | b0 (hi,lo) (128 x 144)]
    *               [s >= 1, t = s-1: W1_t[:, 0:64] | b1_t (hi,lo,hi) (256 x 80), W1_t[:, 64:128] (256 x 64)] */
   const void* tc_hfuse_w;
   /* weight stream of the fused wide node prologue (csrc/gn_node_pre256_tc.cu; D == 256 only, else NULL):
