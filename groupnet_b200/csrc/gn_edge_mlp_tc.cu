@@ -99,8 +99,12 @@ __device__ __forceinline__ void drain_to_smem(uint32_t tmem_addr, unsigned char*
 }
 
 // TT = compile-time number of edge types (6 pairwise, 10 hyper); 0 = runtime a.T (<= 15)
+#ifdef GN_ENABLE_TRACE   // make NVFLAGS+=-DGN_ENABLE_TRACE: clock64() stamps per phase (profiles/trace_chain.py)
 #define GN_TRACE(pt) do { if (a.trace != nullptr && blockIdx.x == 0 && gtid == 0 && titer < 8) \
     a.trace[(grp * 8 + titer) * 16 + (pt)] = clock64(); } while (0)
+#else
+#define GN_TRACE(pt) do { } while (0)
+#endif
 
 template <bool PAIR, int TT>
 __global__ void __launch_bounds__(GN_THREADS, 1)

@@ -180,13 +180,17 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
       long long wacc[4] = {0, 0, 0, 0};
       int ititer = 0;
       auto wait_t = [&](int i, int slot) {
-        if (a.trace == nullptr) { wait(i); return; }
-        const long long t0 = clock64(); wait(i); wacc[slot] += clock64() - t0;
+#ifdef GN_ENABLE_TRACE
+        if (a.trace != nullptr) { const long long t0 = clock64(); wait(i); wacc[slot] += clock64() - t0; return; }
+#endif
+        wait(i);
       };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++ititer) {
+#ifdef GN_ENABLE_TRACE
         if (a.trace != nullptr && blockIdx.x == 0 && ititer > 0 && ititer <= 8) {
           for (int k = 0; k < 4; ++k) { a.trace[128 + (ititer - 1) * 4 + k] = wacc[k]; wacc[k] = 0; }
         }
+#endif
         wait(B_STAGE);
         tc::fence_after_thread_sync();
         tc::issue_gemm(tmem + TM_EF, sbase + OFF_A2, sbase + OFF_RING, 256, 128, false);     // eo = Hblk * h
@@ -278,8 +282,12 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
     const int sc_r = r128 / N, in_r = r128 - sc_r * N;   // scene-in-tile and index-in-scene of row r128
     const int ldr = ((N + 3) & ~3) + 4;                  // row stride of the raw incidence staging
     int titer = 0;
+#ifdef GN_ENABLE_TRACE
 #define HF_TRACE(pt) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && titer < 8) \
     a.trace[titer * 16 + (pt)] = clock64(); } while (0)
+#else
+#define HF_TRACE(pt) do { } while (0)
+#endif
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
       const int b0s = tile * SC;
       HF_TRACE(0);
