@@ -47,6 +47,12 @@ int launch_hyper_fused_tc(const float* h, const float* H, const float* edge_feat
                           long long hstride, const gn_stage_weights* w, float* agg,
                           float* node_out, long long ld_out, int Dout, cudaStream_t st);
 
+// fused hyper layer tail for h_dim 64: gather + T MLPs + scatter + closing MLP (gn_hyper_fused64_tc.cu)
+bool hyper_fused64_fits(int N, int E, int D, int T, int Dout, long long ld_out);
+int launch_hyper_fused64_tc(const float* h, const float* H, const float* edge_feat, int B, int N, int T,
+                            long long hstride, const gn_stage_weights* w, float* node_out, long long ld_out,
+                            int Dout, cudaStream_t st);
+
 // fused wide node prologue h -> x', pq for h_dim 256 (gn_node_pre256_tc.cu)
 bool node_pre256_fits(int D);
 int launch_node_pre256_tc(const float* h, long long R, const gn_stage_weights* w, float* xprime, float* pq,

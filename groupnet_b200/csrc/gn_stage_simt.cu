@@ -1280,7 +1280,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   // ---- k2: node2edge (fused into the tensor-core chain for the pairwise bf16 path)
   const bool tc = c->precision == GN_BF16_TC;
   const bool fuse_pair = tc && c->pairwise && edge_chain_pair_fits(N);
-  const bool fused_hyper = tcn && !c->pairwise && hyper_fused_fits(N, E, D, T);   // eo / ef never leave the SM
+  const bool fused_hyper64 = tcn && !c->pairwise && hyper_fused64_fits(N, E, D, T, c->Dout, ld_out);
+  const bool fused_hyper = fused_hyper64 || (tcn && !c->pairwise && hyper_fused_fits(N, E, D, T));   // eo / ef never leave the SM
   if (fused_hyper && !w->tc_hfuse_w) return GN_E_NULL;
   if (c->pairwise) { if (!fuse_pair) GN_TRY(launch_node2edge_pair(xprime, pq, B, N, w, edges, st)); }
   else GN_TRY(launch_node2edge_hyper(xprime, pq, h, H, B, N, E, D, hstride, w, edges,
@@ -1307,6 +1308,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   if (c->pairwise) {
     if (fused_agg) GN_TRY(launch_pair_agg_tc(h, efeat, B, N, T, w, agg, st));
     else GN_TRY(launch_edge2node_pair(P, efeat, B, N, T, w, G, S, st));
+  } else if (fused_hyper64) {
+    return launch_hyper_fused64_tc(h, H, efeat, B, N, T, hstride, w, node_out, ld_out, c->Dout, st);
   } else if (fused_hyper) {
     const bool post_in = hyper_fused_post_fits(c->Dout, ld_out);
     GN_TRY(launch_hyper_fused_tc(h, H, efeat, B, N, T, hstride, w, agg, post_in ? node_out : nullptr,
@@ -1440,6 +1443,8 @@ int stage_launch_count(const gn_stage_cfg* c) {
   const bool chain = c->D == 64 && (c->Dout % 32 == 0) && c->Dout <= 128;
   const int pre = (chain || node_pre256_fits(c->D)) ? 1 : 3, post = chain ? 1 : 2;
   if (c->pairwise && pair_agg_fits(c->N, c->D, c->T)) return pre + (2 - fused) + 1 + post;
+  if (!c->pairwise && hyper_fused64_fits(c->N, c->E, c->D, c->T, c->Dout, c->out_ld > 0 ? c->out_ld : c->Dout))
+    return pre + 1 + 1 + 1;
   if (!c->pairwise && hyper_fused_fits(c->N, c->E, c->D, c->T))
     return pre + 1 + 1 + 1 + (hyper_fused_post_fits(c->Dout, c->out_ld > 0 ? c->out_ld : c->Dout) ? 0 : post);
   if (!c->pairwise && hyper_agg_fits(c->D, c->T)) return pre + 1 + 1 + 1 + 1 + post;

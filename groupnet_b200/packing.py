@@ -87,6 +87,41 @@ def node_pre256_stream(w0, b0, w1, b1, wpq) -> torch.Tensor:
     return torch.cat(parts).contiguous()
 
 
+def hyper_fused64_stream(agg_params, post_w0, post_b0, post_w1, post_b1) -> torch.Tensor:
+    """Weight stream of csrc/gn_hyper_fused64_tc.cu (h_dim 64): per step s = 0..T the chunks [W0_s | b0_s]
+    (128 x 80) for s < T and [W1_{s-1} | b1_{s-1}] (64 x 144) for s >= 1, then the closing MLP:
+    [W0 | b0] (128 x 144), W1 (Dout x 128), b1 block (Dout x 16)."""
+    t = len(agg_params)
+    dev = post_w0.device
+    parts = []
+    for s in range(t + 1):
+        if s < t:
+            w0, b0 = agg_params[s][0], agg_params[s][1]               # (128, 64), (128,)
+            hi, lo = _hi_lo(b0)
+            blk = torch.zeros(128, 80, dtype=torch.float32, device=dev)
+            blk[:, :64] = w0
+            blk[:, 64], blk[:, 65] = hi, lo
+            parts.append(_canon(blk))
+        if s >= 1:
+            w1, b1 = agg_params[s - 1][2], agg_params[s - 1][3]       # (64, 128), (64,)
+            hi, lo = _hi_lo(b1)
+            blk = torch.zeros(64, 144, dtype=torch.float32, device=dev)
+            blk[:, :128] = w1
+            blk[:, 128], blk[:, 129], blk[:, 130] = hi, lo, hi
+            parts.append(_canon(blk))
+    hi, lo = _hi_lo(post_b0)
+    blk = torch.zeros(128, 144, dtype=torch.float32, device=dev)
+    blk[:, :128] = post_w0
+    blk[:, 128], blk[:, 129] = hi, lo
+    parts.append(_canon(blk))
+    parts.append(_canon(post_w1.contiguous()))
+    hi, lo = _hi_lo(post_b1)
+    blk = torch.zeros(post_w1.shape[0], 16, dtype=torch.float32, device=dev)
+    blk[:, 0], blk[:, 1] = hi, lo
+    parts.append(_canon(blk))
+    return torch.cat(parts).contiguous()
+
+
 def hyper_fused_post_stream(w0, b0, w1, b1) -> torch.Tensor:
     """Closing-MLP chunks appended to the fused kernel's stream (Dout % 32 == 0, <= 256):
     post_w0 in four K chunks of 128 (the last with its bias block), post_w1 in two K chunks of 64."""
@@ -222,6 +257,12 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
         if d == 256:
             out["tc_npre_w"] = node_pre256_stream(dev(node[0].weight), dev(node[0].bias), dev(node[1].weight),
                                                   dev(node[1].bias), torch.cat((w0[:, :64], w0[:, 64:]), dim=0).contiguous())
+        if d == 64 and not layer._pairwise and t <= 15 and dout in (32, 64):
+            out["tc_hfuse_w"] = hyper_fused64_stream(
+                [(dev(m.layers[0].weight), dev(m.layers[0].bias), dev(m.layers[1].weight), dev(m.layers[1].bias))
+                 for m in agg],
+                dev(post_mod.layers[0].weight), dev(post_mod.layers[0].bias),
+                dev(post_mod.layers[1].weight), dev(post_mod.layers[1].bias))
         if d == 256 and not layer._pairwise and t <= 15:
             stream = hyper_fused_stream([(dev(m.layers[0].weight), dev(m.layers[0].bias),
                                           dev(m.layers[1].weight), dev(m.layers[1].bias)) for m in agg], d)

@@ -112,7 +112,10 @@ typedef struct gn_stage_weights {
   /* weight stream of the fused wide hyper aggregation (csrc/gn_hyper_fused_tc.cu; D == 256 only, else
    * NULL): the agg_mlp chunks in the order the kernel consumes them, each a canonical operand:
    * for s = 0..T: [s < T: W0_s[:, 0:128] (128 x 128), W0_s[:, 128:256] | b0 (hi,lo) (128 x 144)]
-   *               [s >= 1, t = s-1: W1_t[:, 0:64] | b1_t (hi,lo,hi) (256 x 80), W1_t[:, 64:128] (256 x 64)] */
+   *               [s >= 1, t = s-1: W1_t[:, 0:64] | b1_t (hi,lo,hi) (256 x 80), W1_t[:, 64:128] (256 x 64)]
+   * h_dim == 64 hyper layers with Dout in {32, 64} (csrc/gn_hyper_fused64_tc.cu) use the same field:
+   * for s = 0..T: [s < T: W0_s | b0 (128 x 80)] [s >= 1: W1_{s-1} | b1 (64 x 144)], then the closing MLP
+   * [W0 | b0] (128 x 144), W1 (Dout x 128), b1 block (Dout x 16). */
   const void* tc_hfuse_w;
   /* weight stream of the fused wide node prologue (csrc/gn_node_pre256_tc.cu; D == 256 only, else NULL):
    * node W0[:, 64c:64c+64] (256 x 64) for c = 0..3, b0 (hi,lo) block (256 x 16), [W1 | b1 (hi,lo)] (64 x 272),

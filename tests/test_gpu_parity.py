@@ -348,16 +348,18 @@ def test_bf16_tc_large_batch_vs_fp32_path():
     assert torch.equal(n16, n16b) and torch.equal(f16, f16b)          # deterministic
 
 
-@pytest.mark.parametrize("n,scale,bo,b", [(64, 4, 256, 37), (64, 16, 96, 301), (20, 5, 256, 45), (32, 8, 80, 19),
-                                          (7, 3, 128, 130)])
-def test_bf16_wide_hyper_fused_vs_fp32_path(n, scale, bo, b):
-    """h_dim 256 hyper layers run the fused gather + T MLPs + scatter (+ closing MLP) kernel
-    (csrc/gn_hyper_fused_tc.cu): many tiles per CTA, ragged last tile (b % (128 // n) != 0), scene
+@pytest.mark.parametrize("d,n,scale,bo,b", [(256, 64, 4, 256, 37), (256, 64, 16, 96, 301), (256, 20, 5, 256, 45),
+                                            (256, 32, 8, 80, 19), (256, 7, 3, 128, 130),
+                                            (64, 11, 5, 64, 3001), (64, 20, 8, 32, 77), (64, 8, 3, 64, 1000),
+                                            (64, 64, 16, 64, 9), (64, 3, 2, 64, 4099)])
+def test_bf16_wide_hyper_fused_vs_fp32_path(d, n, scale, bo, b):
+    """h_dim 256 / 64 hyper layers run the fused gather + T MLPs + scatter (+ closing MLP) kernels
+    (csrc/gn_hyper_fused_tc.cu, gn_hyper_fused64_tc.cu): many tiles per CTA, ragged last tile (b % (128 // n) != 0), scene
     counts per tile that do not fill 128 rows (n = 20, 7), closing MLP fused (bo % 32 == 0) or not (bo = 80)."""
     torch.manual_seed(91)
-    m = gb.MS_HGNN_hyper(256, 256, 64, bo, batch_norm=0, nmp_layers=1, scale=scale).to(DEV)
+    m = gb.MS_HGNN_hyper(d, d, 64, bo, batch_norm=0, nmp_layers=1, scale=scale).to(DEV)
     gen = torch.Generator().manual_seed(9)
-    h = torch.randn(b, n, 256, generator=gen).to(DEV)
+    h = torch.randn(b, n, d, generator=gen).to(DEV)
     corr = torch.bmm(torch.nn.functional.normalize(h, dim=2), torch.nn.functional.normalize(h, dim=2).transpose(1, 2))
     u = torch.rand(b, n, 10, generator=gen).to(DEV)
     n32, f32, h32 = m(h, corr, noise=[u])
