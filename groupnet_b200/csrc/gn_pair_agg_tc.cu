@@ -49,13 +49,15 @@ constexpr uint32_t OFF_EF = OFF_BAR + 32;              // edge_feat of the tile:
 constexpr uint32_t TM_P = 0, TM_AGG = 256;             // TMEM columns: P' double buffer 2 x 128, agg 64
 }  // namespace pagg
 
-__global__ void __launch_bounds__(GN_THREADS, 1)
+constexpr int PA_THREADS = 512;   // (tile row, 32-column quarter): 16 warps hide the latency of the SIMT relu-sum
+
+__global__ void __launch_bounds__(PA_THREADS, 1)
 pair_agg_tc_kernel(PairAggArgs a) {
   using namespace pagg;
   using namespace tc;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = tid & 127, chalf = tid >> 7;          // tile row (TMEM lane), 64-column half
+  const int row = tid & 127, cq = tid >> 7;             // tile row (TMEM lane), 32-column quarter
   __half* sP = reinterpret_cast<__half*>(smem + OFF_P);
   float* sS = reinterpret_cast<float*>(smem + OFF_S);
   float* sEF = reinterpret_cast<float*>(smem + OFF_EF);
@@ -65,7 +67,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
   const int N = a.N, T = a.T, SC = a.SC, E = N * N;
   const int NT = T * 128;
 
-  build_ones_operand(smem + OFF_ONES, tid, GN_THREADS);
+  build_ones_operand(smem + OFF_ONES, tid, PA_THREADS);
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (tid == 32) { mbar_init(mbarA, 1); mbar_init(mbarB, 1); }
   fence_proxy_async_smem();
@@ -79,7 +81,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
 
   // W0_t: rows [t*128, t*128+128) of the canonical (NT x 64) operand: 8 k-groups x 2 KB
   auto load_w0 = [&](int t, int buf) {
-    for (int i = tid; i < 8 * 128; i += GN_THREADS) {
+    for (int i = tid; i < 8 * 128; i += PA_THREADS) {
       const int k8 = i >> 7, n = i & 127;
       cp_async16(smem + OFF_W0 + buf * (128 * 64 * 2) + (k8 * 128 + n) * 16,
                  a.w0 + (static_cast<size_t>(k8) * NT + t * 128 + n) * 8);
@@ -88,7 +90,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
   // W1_t: k-groups [t*16, t*16+16) of the canonical (64 x NT) operand: 16 KB contiguous
   auto load_w1 = [&](int t) {
     const __nv_bfloat16* src = a.w1 + static_cast<size_t>(t) * 16 * 64 * 8;
-    for (int i = tid; i < 16 * 64; i += GN_THREADS) cp_async16(smem + OFF_W1 + i * 16, src + i * 8);
+    for (int i = tid; i < 16 * 64; i += PA_THREADS) cp_async16(smem + OFF_W1 + i * 16, src + i * 8);
   };
   // b0_t / 2 as a [128 x 16] bias operand
   auto build_bb = [&](int t, int buf) {
@@ -125,9 +127,9 @@ pair_agg_tc_kernel(PairAggArgs a) {
       const float* ef = a.edge_feat + static_cast<size_t>(b0s) * E * T;
       const int n4 = (ns * E * T) >> 2;                     // SC*E*T*4 bytes is 16-byte aligned when E*T % 4 == 0
       if (((E * T) & 3) == 0) {
-        for (int i = tid; i < n4; i += GN_THREADS) cp_async16(sEF + 4 * i, ef + 4 * i);
+        for (int i = tid; i < n4; i += PA_THREADS) cp_async16(sEF + 4 * i, ef + 4 * i);
       } else {
-        for (int i = tid; i < ns * E * T; i += GN_THREADS) sEF[i] = __ldg(ef + i);
+        for (int i = tid; i < ns * E * T; i += PA_THREADS) sEF[i] = __ldg(ef + i);
       }
       load_w0(0, 0);
       if (T > 1) load_w0(1, 1);
@@ -148,7 +150,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
           *reinterpret_cast<uint4*>(smem + OFF_A + canon_off(row, k8, 128)) = pk;
         }
       }
-      for (int i = tid; i < 128 * 16; i += GN_THREADS) sS[i] = 0.f;
+      for (int i = tid; i < 128 * 16; i += PA_THREADS) sS[i] = 0.f;
       cp_async_wait<0>();
       fence_proxy_async_smem();
       fence_before_thread_sync();
@@ -161,19 +163,15 @@ pair_agg_tc_kernel(PairAggArgs a) {
       mbar_wait(mbarA, phA); phA ^= 1;
       fence_after_thread_sync();
       // (b) drain this thread's half row as fp16x2: keep it in registers, publish it for the scene mates
-      __half2 own[32];
+      __half2 own[16];
       {
-        uint32_t r[2][32];
-        tmem_ld32_nowait(tmem_lane + TM_P + (t & 1) * 128 + chalf * 64, r[0]);
-        tmem_ld32_nowait(tmem_lane + TM_P + (t & 1) * 128 + chalf * 64 + 32, r[1]);
-        tmem_ld_wait();
+        float r[32];
+        tmem_ld32(tmem_lane + TM_P + (t & 1) * 128 + cq * 32, r);
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          own[c] = __floats2half2_rn(__uint_as_float(r[(2 * c) >> 5][(2 * c) & 31]),
-                                     __uint_as_float(r[(2 * c + 1) >> 5][(2 * c + 1) & 31]));
-        uint4* dst = reinterpret_cast<uint4*>(sP + row * PLD + chalf * 64);
+        for (int c = 0; c < 16; ++c) own[c] = __floats2half2_rn(r[2 * c], r[2 * c + 1]);
+        uint4* dst = reinterpret_cast<uint4*>(sP + row * PLD + cq * 32);
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
+        for (int c = 0; c < 4; ++c)
           dst[c] = make_uint4(*reinterpret_cast<uint32_t*>(&own[4 * c]), *reinterpret_cast<uint32_t*>(&own[4 * c + 1]),
                               *reinterpret_cast<uint32_t*>(&own[4 * c + 2]), *reinterpret_cast<uint32_t*>(&own[4 * c + 3]));
       }
@@ -195,13 +193,13 @@ pair_agg_tc_kernel(PairAggArgs a) {
       cp_async_commit();                                     // group 2: W0_{t+2} (needed one step later)
       // (d) relu-sum over the scene mates in packed fp16x2: relu(own + p) is one HFMA2.RELU, the
       //     weighted accumulation one HFMA2 (fp16 keeps 11 mantissa bits; the result feeds a bf16 operand)
-      __half2 acc[32];
+      __half2 acc[16];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = __floats2half2_rn(0.f, 0.f);
+      for (int c = 0; c < 16; ++c) acc[c] = __floats2half2_rn(0.f, 0.f);
       float ssum = 0.f;
       if (live) {
         const float* efs = sEF + sc * E * T;
-        const __half* prow = sP + (sc * N) * PLD + chalf * 64;
+        const __half* prow = sP + (sc * N) * PLD + cq * 32;
         const __half2 one2 = __floats2half2_rn(1.f, 1.f);
         for (int j = 0; j < N; ++j) {
           const float w = efs[(ni * N + j) * T + t] + efs[(j * N + ni) * T + t];
@@ -209,7 +207,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
           const __half2 w2 = __floats2half2_rn(w, w);
           const uint4* pj = reinterpret_cast<const uint4*>(prow + j * PLD);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < 4; ++c) {
             const uint4 p = pj[c];
             const __half2 p0 = *reinterpret_cast<const __half2*>(&p.x), p1 = *reinterpret_cast<const __half2*>(&p.y);
             const __half2 p2 = *reinterpret_cast<const __half2*>(&p.z), p3 = *reinterpret_cast<const __half2*>(&p.w);
@@ -219,16 +217,16 @@ pair_agg_tc_kernel(PairAggArgs a) {
             acc[4 * c + 3] = __hfma2(w2, __hfma2_relu(own[4 * c + 3], one2, p3), acc[4 * c + 3]);
           }
         }
-        if (chalf == 0) sS[row * 16 + t] = ssum;
+        if (cq == 0) sS[row * 16 + t] = ssum;
       }
       // G_t -> bf16 A operand of GEMM 2
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         float2 f0 = __half22float2(acc[4 * g]), f1 = __half22float2(acc[4 * g + 1]);
         float2 f2 = __half22float2(acc[4 * g + 2]), f3 = __half22float2(acc[4 * g + 3]);
         uint4 pk = make_uint4(pack_bf16_fast(f0.x, f0.y), pack_bf16_fast(f1.x, f1.y),
                               pack_bf16_fast(f2.x, f2.y), pack_bf16_fast(f3.x, f3.y));
-        *reinterpret_cast<uint4*>(smem + OFF_G + canon_off(row, chalf * 8 + g, 128)) = pk;
+        *reinterpret_cast<uint4*>(smem + OFF_G + canon_off(row, cq * 4 + g, 128)) = pk;
       }
       cp_async_wait<1>();                                    // W1_t landed (the step t+2 prefetch may still fly)
       fence_proxy_async_smem();
@@ -245,18 +243,18 @@ pair_agg_tc_kernel(PairAggArgs a) {
     mbar_wait(mbarB, phB); phB ^= 1;
     fence_after_thread_sync();
     {
-      float v[32];
-      tmem_ld32(tmem_lane + TM_AGG + chalf * 32, v);
+      float v[16];
+      tmem_ld16(tmem_lane + TM_AGG + cq * 16, v);
       if (live) {
         for (int t = 0; t < T; ++t) {
           const float s = sS[row * 16 + t];
-          const float* b1 = a.b1 + t * D + chalf * 32;
+          const float* b1 = a.b1 + t * D + cq * 16;
 #pragma unroll
-          for (int c = 0; c < 32; ++c) v[c] = fmaf(s, __ldg(b1 + c), v[c]);
+          for (int c = 0; c < 16; ++c) v[c] = fmaf(s, __ldg(b1 + c), v[c]);
         }
-        float* dst = a.agg + (grow0 + row) * D + chalf * 32;
+        float* dst = a.agg + (grow0 + row) * D + cq * 16;
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+        for (int c = 0; c < 16; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
       }
     }
     fence_before_thread_sync();
@@ -299,7 +297,7 @@ int launch_pair_agg_tc(const float* h, const float* edge_feat, int B, int N, int
   const int grid = ntiles < GN_SM_COUNT ? ntiles : GN_SM_COUNT;
   {
     ProfScope ps__("pair_agg_tc", st);
-    pair_agg_tc_kernel<<<grid, GN_THREADS, smem, st>>>(a);
+    pair_agg_tc_kernel<<<grid, PA_THREADS, smem, st>>>(a);
   }
   GN_LAUNCH_CHECK();
   return GN_OK;
