@@ -138,7 +138,17 @@ corr_topk_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
       //         K split over 2 adjacent lanes when D % 8 == 0
       const int nb = (N + 3) >> 2;
       const int ntri = nb * (nb + 1) / 2;
-      const int ks = (D % 8 == 0) ? 2 : 1;
+      // K split over ks adjacent lanes: pick the split that minimises passes x slice length
+      // (N = 64: 136 blocks -> ks = 8 gives 5 passes of 8 k-steps instead of 2 passes of 32)
+      int ks = 1;
+      {
+        int best = 1 << 30;
+        for (int cand = 1; cand <= 8; cand <<= 1) {
+          if (D % (4 * cand)) break;
+          const int cost = ((ns * ntri * cand + GN_THREADS - 1) / GN_THREADS) * (D / (4 * cand));
+          if (cost < best) { best = cost; ks = cand; }
+        }
+      }
       const int ntask = ns * ntri * ks;
       for (int base = 0; base < ntask; base += GN_THREADS) {
         int task = base + tid;
@@ -162,8 +172,8 @@ corr_topk_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
         for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int w = 0; w < 4; ++w) acc[u][w] = 0.f;
-        int kbeg = half * (D / ks), kend = kbeg + D / ks;
-        for (int k = kbeg; k < kend; k += 4) {
+        // interleaved K slices: the ks lanes of a block read consecutive float4s (no bank conflicts)
+        for (int k = 4 * half; k < D; k += 4 * ks) {
           float4 av[4], bv[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -180,12 +190,12 @@ corr_topk_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
               acc[u][w] = fmaf(av[u].w, bv[w].w, acc[u][w]);
             }
         }
-        if (ks == 2) {
+        for (int o = 1; o < ks; o <<= 1) {
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int w = 0; w < 4; ++w)
-              acc[u][w] += __shfl_xor_sync(0xffffffffu, acc[u][w], 1);
+              acc[u][w] += __shfl_xor_sync(0xffffffffu, acc[u][w], o);
         }
         if (valid && half == 0) {
 #pragma unroll
