@@ -44,11 +44,12 @@ def layer_shapes(n):
     return out
 
 
-def kernel_work(b, n, d):
-    """{kernel: (flops, bytes, bound)} summed over the launches of ONE step.
+def kernel_work(b, n, d, precision="bf16"):
+    """{kernel: (flops, bytes, bound)} summed over the launches of ONE step on the given path.
     ALGORITHMIC work only: FLOPs of the math each kernel is
     responsible for, bytes = compulsory HBM traffic of its inputs and outputs."""
     w = {}
+    tc = precision == "bf16"
 
     def add(k, flops, byts, bound):
         f0, b0, _ = w.get(k, (0, 0, bound))
@@ -61,36 +62,43 @@ def kernel_work(b, n, d):
         rn, re = b * n, b * e
         mlp_macs = 64 * 128 + 128 * 64 + 64 * 256 + 256 * (t + 1)
         agg_macs_row = t * 2 * d * 128                      # both Linears of the T agg MLPs, per row
-        # ---- fp32 (FFMA) path kernels
-        add("node_pre", 2 * rn * (d * 256 + 256 * 64 + 64 * 64 + (d * t * 128 if pair else 0)),
-            rn * 4 * (d + 128 + (t * 128 if pair else 0)), "tensor")
-        add("edge_mlp", 2 * re * mlp_macs, re * (64 + 2 * t) * 4, "tensor")
-        if pair:
-            add("node2edge_pair", re * (2 * 64 * 2 + 4 * 64), (rn * 128 + re * 64) * 4, "hbm")
-            add("edge2node_pair", rn * n * t * 128 * 4, (rn * (2 * t * 128 + 16) + re * t) * 4, "hbm")
-            add("node_post", 2 * rn * (t * 128 * d + 2 * d * 128 + 128 * d), rn * (t * 128 + 16 + 2 * d) * 4, "tensor")
-        else:
-            add("node2edge_hyper", re * n * (64 + 2 * 64 + 2 * d),
-                (rn * (128 + d) + re * (n + 64 + d)) * 4, "hbm")
-            add("edge_agg", 2 * re * agg_macs_row, re * (2 * d + t) * 4, "tensor")
-            add("edge2node_hyper", 2 * rn * e * d, (re * (d + n) + rn * d) * 4, "hbm")
-            add("node_post", 2 * rn * (2 * d * 128 + 128 * d), rn * 3 * d * 4, "tensor")
+        post_flops = 2 * rn * (2 * d * 128 + 128 * d)
+        if not tc:
+            # ---- fp32 (FFMA) path kernels
+            add("node_pre", 2 * rn * (d * 256 + 256 * 64 + 64 * 64 + (d * t * 128 if pair else 0)),
+                rn * 4 * (d + 128 + (t * 128 if pair else 0)), "tensor")
+            add("edge_mlp", 2 * re * mlp_macs, re * (64 + 2 * t) * 4, "tensor")
+            if pair:
+                add("node2edge_pair", re * (2 * 64 * 2 + 4 * 64), (rn * 128 + re * 64) * 4, "hbm")
+                add("edge2node_pair", rn * n * t * 128 * 4, (rn * (2 * t * 128 + 16) + re * t) * 4, "hbm")
+                add("node_post", 2 * rn * (t * 128 * d + 2 * d * 128 + 128 * d), rn * (t * 128 + 16 + 2 * d) * 4, "tensor")
+            else:
+                add("node2edge_hyper", re * n * (64 + 2 * 64 + 2 * d),
+                    (rn * (128 + d) + re * (n + 64 + d)) * 4, "hbm")
+                add("edge_agg", 2 * re * agg_macs_row, re * (2 * d + t) * 4, "tensor")
+                add("edge2node_hyper", 2 * rn * e * d, (re * (d + n) + rn * d) * 4, "hbm")
+                add("node_post", post_flops, rn * 3 * d * 4, "tensor")
+            continue
         # ---- bf16 tensor-core path kernels
         add("node_pre_chain_tc", 2 * rn * (d * 256 + 256 * 64 + 64 * 64), rn * (d + 128) * 4, "tensor")
-        add("node_post_chain_tc", 2 * rn * (2 * d * 128 + 128 * d), rn * 3 * d * 4, "tensor")
-        add("node_mlp0_tc", 2 * rn * d * 256, rn * (d * 4 + 256 * 2), "tensor")
-        add("node_mlp1_tc", 2 * rn * 256 * 64, rn * (256 * 2 + 64 * 4), "tensor")
-        add("att_proj_tc", 2 * rn * 64 * 64, rn * 128 * 4, "tensor")
-        add("post_mlp0_tc", 2 * rn * 2 * d * 128, rn * (2 * d * 4 + 128 * 2), "tensor")
-        add("post_mlp1_tc", 2 * rn * 128 * d, rn * (128 * 2 + d * 4), "tensor")
         if pair:
             # node2edge (attention + gather, ~600 FLOP/row) + MLP chain; x', pq in, dist/edge_feat out
             add("edge_chain_pair_tc", 2 * re * mlp_macs + re * 600, (rn * 128 + re * t) * 4, "tensor")
             # P' GEMM + relu-sum (3 FLOP per (n,j,t,c)) + G GEMM; h, edge_feat in, agg out
             add("pair_agg_tc", 2 * rn * agg_macs_row + rn * n * t * 128 * 3, (rn * 2 * d + re * t) * 4, "tensor")
+            add("node_post_chain_tc", post_flops, rn * 3 * d * 4, "tensor")
+            continue
+        add("edge_chain_tc", 2 * re * mlp_macs, re * (64 + t) * 4, "tensor")
+        if e == n and d == 64:
+            # fused tail: gather + T MLPs + scatter + closing MLP; h, H, edge_feat in, node_feat out
+            add("node2edge_hyper", re * n * (64 + 2 * 64), (rn * 128 + re * (n + 64)) * 4, "hbm")
+            add("hyper_fused64_tc", 2 * re * agg_macs_row + post_flops + 4 * re * n * d,
+                (rn * 2 * d + re * (n + t)) * 4, "tensor")
         else:
-            add("edge_chain_tc", 2 * re * mlp_macs, re * (64 + t) * 4, "tensor")
+            add("node2edge_hyper", re * n * (64 + 2 * 64 + 2 * d), (rn * (128 + d) + re * (n + 64 + d)) * 4, "hbm")
             add("hyper_agg_tc", 2 * re * agg_macs_row, re * (2 * d + t) * 4, "tensor")
+            add("edge2node_hyper", 2 * rn * e * d, (re * (d + n) + rn * d) * 4, "hbm")
+            add("node_post_chain_tc", post_flops, rn * 3 * d * 4, "tensor")
     return w
 
 
@@ -512,7 +520,7 @@ def main():
         peak_src = "fallback"
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-    work = kernel_work(b, n, d)
+    work = kernel_work(b, n, d, args.precision)
     kernels = {}
     for k, (tot_ms, cnt) in prof.items():
         per_step_ms = tot_ms / prof_steps
