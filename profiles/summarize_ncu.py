@@ -11,7 +11,6 @@ want = [
     ("dram write", "dram__bytes_write.sum"),
     ("dram throughput % of peak", "FBSP.TriageCompute.dram__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("tensor pipe active % (realtime)", "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
-    ("bf16 MMA ops % of peak", "sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed"),
     ("tensor-memory (operand fetch) cycles active %", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
     ("tmem pipe inst % ", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active"),
     ("issue active %", "smsp__issue_active.avg.pct"),
