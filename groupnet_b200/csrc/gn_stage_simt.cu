@@ -1280,7 +1280,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   // ---- k2: node2edge (fused into the tensor-core chain for the pairwise bf16 path)
   const bool tc = c->precision == GN_BF16_TC;
   const bool fuse_pair = tc && c->pairwise && edge_chain_pair_fits(N);
-  const bool fused_hyper64 = tcn && !c->pairwise && hyper_fused64_fits(N, E, D, T, c->Dout, ld_out);
+  const bool out_aligned = (reinterpret_cast<uintptr_t>(node_out) & 15) == 0;   // fused tails store 128-bit rows
+  const bool fused_hyper64 = tcn && !c->pairwise && out_aligned && hyper_fused64_fits(N, E, D, T, c->Dout, ld_out);
   const bool fused_hyper = fused_hyper64 || (tcn && !c->pairwise && hyper_fused_fits(N, E, D, T));   // eo / ef never leave the SM
   if (fused_hyper && !w->tc_hfuse_w) return GN_E_NULL;
   if (c->pairwise) { if (!fuse_pair) GN_TRY(launch_node2edge_pair(xprime, pq, B, N, w, edges, st)); }
@@ -1311,7 +1312,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   } else if (fused_hyper64) {
     return launch_hyper_fused64_tc(h, H, efeat, B, N, T, hstride, w, node_out, ld_out, c->Dout, st);
   } else if (fused_hyper) {
-    const bool post_in = hyper_fused_post_fits(c->Dout, ld_out);
+    const bool post_in = out_aligned && hyper_fused_post_fits(c->Dout, ld_out);
     GN_TRY(launch_hyper_fused_tc(h, H, efeat, B, N, T, hstride, w, agg, post_in ? node_out : nullptr,
                                  ld_out, c->Dout, st));
     if (post_in) return GN_OK;
