@@ -132,10 +132,195 @@ sgemm_tn_kernel(const float* __restrict__ A, long long lda, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------
+// Fast variants for the aligned shapes of the backward (everything except the T- and 1-wide heads):
+// 128 x 64 output tile, 8 x 4 per thread, k-step 16, shared memory double-buffered with a register
+// prefetch of the next k-tile (one __syncthreads per step).  Same semantics as the kernels above.
+// ---------------------------------------------------------------------------
+template <bool WT>
+__global__ void __launch_bounds__(256)
+sgemm128_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ W, long long ldw,
+                const float* __restrict__ bias, float* __restrict__ Y, long long ldy,
+                long long M, int N, int K, int relu, int accumulate,
+                const float* __restrict__ maskref, long long ldm) {
+  __shared__ __align__(16) float xs[2][SG_K][128 + 4];
+  __shared__ __align__(16) float ws[2][SG_K][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long m0 = static_cast<long long>(blockIdx.x) * 128;
+  const int n0 = blockIdx.y * 64;
+  float4 xr[2], wr;
+  const int xk4 = tid & 3, xrow = tid >> 2;              // X tile: rows xrow, xrow + 64; 4 floats at k = 4 * xk4
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long m = m0 + xrow + 64 * i;
+      xr[i] = m < M ? ldg_f4(X + m * ldx + k0 + 4 * xk4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (WT) {
+      const int n = n0 + (tid >> 2);
+      wr = n < N ? ldg_f4(W + static_cast<long long>(n) * ldw + k0 + 4 * (tid & 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const int k = tid >> 4, n = n0 + 4 * (tid & 15);
+      const float* src = W + static_cast<long long>(k0 + k) * ldw + n;
+      if (n + 3 < N) wr = ldg_f4(src);
+      else wr = make_float4(n < N ? __ldg(src) : 0.f, n + 1 < N ? __ldg(src + 1) : 0.f, n + 2 < N ? __ldg(src + 2) : 0.f, 0.f);
+    }
+  };
+  auto sstore = [&](int b) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = xrow + 64 * i;
+      xs[b][4 * xk4][r] = xr[i].x; xs[b][4 * xk4 + 1][r] = xr[i].y; xs[b][4 * xk4 + 2][r] = xr[i].z; xs[b][4 * xk4 + 3][r] = xr[i].w;
+    }
+    if (WT) {
+      const int c = tid >> 2, k4 = tid & 3;
+      ws[b][4 * k4][c] = wr.x; ws[b][4 * k4 + 1][c] = wr.y; ws[b][4 * k4 + 2][c] = wr.z; ws[b][4 * k4 + 3][c] = wr.w;
+    } else {
+      *reinterpret_cast<float4*>(&ws[b][tid >> 4][4 * (tid & 15)]) = wr;
+    }
+  };
+  float acc[8][4] = {};
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int b = 0;
+  for (int k0 = 0; k0 < K; k0 += SG_K, b ^= 1) {
+    const bool more = k0 + SG_K < K;
+    if (more) gload(k0 + SG_K);
+#pragma unroll
+    for (int k = 0; k < SG_K; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&xs[b][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&xs[b][k][ty * 8 + 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&ws[b][k][tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bw[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(av[u], bw[v], acc[u][v]);
+    }
+    if (more) sstore(b ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const long long m = m0 + ty * 8 + u;
+    if (m >= M) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int n = n0 + tx * 4 + v;
+      if (n >= N) continue;
+      float y = acc[u][v];
+      if (bias != nullptr) y += bias[n];
+      if (relu) y = fmaxf(y, 0.f);
+      if (maskref != nullptr && !(maskref[m * ldm + n] > 0.f)) y = 0.f;
+      if (accumulate) y += Y[m * ldy + n];
+      Y[m * ldy + n] = y;
+    }
+  }
+}
+
+// C[N x K] += A^T B over this block's row slice; TN_ x TK_ output tile, (TN_/16) x (TK_/16) per thread
+template <int TN_, int TK_>
+__global__ void __launch_bounds__(256)
+sgemm_tn_fast_kernel(const float* __restrict__ A, long long lda, const float* __restrict__ Bm, long long ldb,
+                     float* __restrict__ C, long long ldc, float* __restrict__ cb,
+                     long long M, int N, int K, long long rows_per_slice) {
+  constexpr int RN = TN_ / 16, RK = TK_ / 16, A4 = TN_ / 4, B4 = TK_ / 4;
+  __shared__ __align__(16) float as[2][SG_K][TN_ + 4];
+  __shared__ __align__(16) float bs[2][SG_K][TK_ + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int n0 = blockIdx.x * TN_, k0 = blockIdx.y * TK_;
+  const long long mbeg = static_cast<long long>(blockIdx.z) * rows_per_slice;
+  const long long mend = min(M, mbeg + rows_per_slice);
+  constexpr int NA = SG_K * A4 / 256, NB = SG_K * B4 / 256;   // float4 loads per thread
+  float4 ar[NA], br[NB];
+  auto gload = [&](long long m0) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = tid + 256 * i, r = idx / A4, c4 = idx - r * A4;
+      const long long m = m0 + r;
+      const int n = n0 + 4 * c4;
+      ar[i] = (m < mend && n < N) ? ldg_f4(A + m * lda + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int idx = tid + 256 * i, r = idx / B4, c4 = idx - r * B4;
+      const long long m = m0 + r;
+      const int k = k0 + 4 * c4;
+      br[i] = (m < mend && k < K) ? ldg_f4(Bm + m * ldb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto sstore = [&](int b) {
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+      const int idx = tid + 256 * i, r = idx / A4, c4 = idx - r * A4;
+      *reinterpret_cast<float4*>(&as[b][r][4 * c4]) = ar[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int idx = tid + 256 * i, r = idx / B4, c4 = idx - r * B4;
+      *reinterpret_cast<float4*>(&bs[b][r][4 * c4]) = br[i];
+    }
+  };
+  float acc[RN][RK] = {};
+  float bsum[RN] = {};
+  gload(mbeg);
+  sstore(0);
+  __syncthreads();
+  int b = 0;
+  for (long long m0 = mbeg; m0 < mend; m0 += SG_K, b ^= 1) {
+    const bool more = m0 + SG_K < mend;
+    if (more) gload(m0 + SG_K);
+#pragma unroll
+    for (int r = 0; r < SG_K; ++r) {
+      float av[RN], bw[RK];
+#pragma unroll
+      for (int u = 0; u < RN; u += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&as[b][r][ty * RN + u]);
+        av[u] = t.x; av[u + 1] = t.y; av[u + 2] = t.z; av[u + 3] = t.w;
+      }
+#pragma unroll
+      for (int v = 0; v < RK; v += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(&bs[b][r][tx * RK + v]);
+        bw[v] = t.x; bw[v + 1] = t.y; bw[v + 2] = t.z; bw[v + 3] = t.w;
+      }
+#pragma unroll
+      for (int u = 0; u < RN; ++u) {
+        if (tx == 0) bsum[u] += av[u];
+#pragma unroll
+        for (int v = 0; v < RK; ++v) acc[u][v] = fmaf(av[u], bw[v], acc[u][v]);
+      }
+    }
+    if (more) sstore(b ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < RN; ++u) {
+    const int n = n0 + ty * RN + u;
+    if (n >= N) continue;
+    if (cb != nullptr && blockIdx.y == 0 && tx == 0) atomicAdd(cb + n, bsum[u]);
+#pragma unroll
+    for (int v = 0; v < RK; ++v) {
+      const int k = k0 + tx * RK + v;
+      if (k < K) atomicAdd(C + static_cast<long long>(n) * ldc + k, acc[u][v]);
+    }
+  }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 static int sgemm_nt(const float* X, long long ldx, const float* W, long long ldw, const float* bias,
                     float* Y, long long ldy, long long M, int N, int K, int relu, int accumulate,
                     cudaStream_t st) {
   if (M <= 0) return GN_OK;
+  if ((K % SG_K) == 0 && (ldx & 3) == 0 && (ldw & 3) == 0 && al16(X) && al16(W) && N >= 32) {
+    dim3 grid(static_cast<unsigned>((M + 127) / 128), (N + 63) / 64);
+    { ProfScope ps__("bwd_sgemm", st);
+      sgemm128_kernel<true><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, Y, ldy, M, N, K, relu, accumulate, nullptr, 0); }
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+  }
   dim3 grid(static_cast<unsigned>((M + SG_T - 1) / SG_T), (N + SG_T - 1) / SG_T);
   { ProfScope ps__("bwd_sgemm", st);
     sgemm_kernel<true><<<grid, 256, 0, st>>>(X, ldx, W, ldw, bias, Y, ldy, M, N, K, relu, accumulate, nullptr, 0); }
@@ -147,6 +332,14 @@ static int sgemm_dgrad(const float* dY, long long ldy, const float* W, long long
                        long long M, int N, int K, int accumulate, const float* ref, long long ldr,
                        cudaStream_t st) {
   if (M <= 0) return GN_OK;
+  // here the contraction runs over N (the Linear's outputs) and the output has K columns
+  if ((N % SG_K) == 0 && (ldy & 3) == 0 && (ldw & 3) == 0 && al16(dY) && al16(W) && K >= 32) {
+    dim3 grid(static_cast<unsigned>((M + 127) / 128), (K + 63) / 64);
+    { ProfScope ps__("bwd_sgemm", st);
+      sgemm128_kernel<false><<<grid, 256, 0, st>>>(dY, ldy, W, ldw, nullptr, dX, ldx, M, K, N, 0, accumulate, ref, ldr); }
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+  }
   dim3 grid(static_cast<unsigned>((M + SG_T - 1) / SG_T), (K + SG_T - 1) / SG_T);
   { ProfScope ps__("bwd_sgemm", st);
     sgemm_kernel<false><<<grid, 256, 0, st>>>(dY, ldy, W, ldw, nullptr, dX, ldx, M, K, N, 0, accumulate, ref, ldr); }
@@ -156,10 +349,29 @@ static int sgemm_dgrad(const float* dY, long long ldy, const float* W, long long
 static int sgemm_wgrad(const float* dY, long long ldy, const float* X, long long ldx, float* dW, float* db,
                        long long M, int N, int K, cudaStream_t st) {
   if (M <= 0 || dW == nullptr) return GN_OK;
+  // row slices: at most 4096 rows each, but enough of them to fill the GPU twice when M is small
+  // (the hyper layers have 12x / 121x fewer edge rows than the pairwise layer)
+  const long long tiles = static_cast<long long>((N + 127) / 128) * ((K + 63) / 64);
+  long long want = (2 * GN_SM_COUNT + tiles - 1) / tiles;
   long long slices = (M + 4095) / 4096;
+  if (slices < want) slices = want;
+  if (slices > (M + 255) / 256) slices = (M + 255) / 256;
+  if (slices < 1) slices = 1;
   if (slices > 1024) slices = 1024;
   const long long rps = ((M + slices - 1) / slices + SG_K - 1) / SG_K * SG_K;
   slices = (M + rps - 1) / rps;
+  if ((ldy & 3) == 0 && (ldx & 3) == 0 && (N & 3) == 0 && (K & 3) == 0 && al16(dY) && al16(X) && N >= 32 && K >= 32) {
+    ProfScope ps__("bwd_wgrad", st);
+    if (N >= 128) {
+      dim3 grid((N + 127) / 128, (K + 63) / 64, static_cast<unsigned>(slices));
+      sgemm_tn_fast_kernel<128, 64><<<grid, 256, 0, st>>>(dY, ldy, X, ldx, dW, K, db, M, N, K, rps);
+    } else {
+      dim3 grid((N + 63) / 64, (K + 127) / 128, static_cast<unsigned>(slices));
+      sgemm_tn_fast_kernel<64, 128><<<grid, 256, 0, st>>>(dY, ldy, X, ldx, dW, K, db, M, N, K, rps);
+    }
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+  }
   dim3 grid((N + SG_T - 1) / SG_T, (K + SG_T - 1) / SG_T, static_cast<unsigned>(slices));
   { ProfScope ps__("bwd_wgrad", st);
     sgemm_tn_kernel<<<grid, 256, 0, st>>>(dY, ldy, X, ldx, dW, K, db, M, N, K, rps); }
