@@ -470,6 +470,25 @@ __global__ void rowscale_kernel(const float* __restrict__ in, const float* __res
   if (i >= R * D) return;
   out[i] = scale[(i / D) * lds] * in[i];
 }
+// fused pair of the two above for the aggregation MLPs: one warp per row, one pass over d_ef:
+//   col[r*ldc] = d_ef[r] . v[r]   and   dv[r] = scale[r*lds] * d_ef[r]
+__global__ void __launch_bounds__(256)
+rowdot_scale_kernel(const float* __restrict__ def, const float* __restrict__ v, float* __restrict__ col, long long ldc,
+                    const float* __restrict__ scale, long long lds, float* __restrict__ dv, long long R, int D) {
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const float sc = __ldg(scale + r * lds);
+  float s = 0.f;
+  for (int c = 4 * lane; c < D; c += 128) {
+    const float4 a = ldg_f4(def + r * D + c), b = ldg_f4(v + r * D + c);
+    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    *reinterpret_cast<float4*>(dv + r * D + c) = make_float4(sc * a.x, sc * a.y, sc * a.z, sc * a.w);
+  }
+  s = warp_sum(s);
+  if (lane == 0) col[r * ldc] = s;
+}
+
 // Gumbel-softmax / sigmoid backward per edge row.  edge_feat = f * dist, sum_t dist = 1  =>
 // f = sum_t edge_feat, dist = edge_feat / f.  y = (logits + g)/tau, tau = 1/2:
 //   d_dist_t = d_ef_t * f (+ external d_dist_t);  d_f = sum_t d_ef_t dist_t
@@ -515,6 +534,9 @@ n2e_bwd_kernel(const float* __restrict__ xprime, const float* __restrict__ pq, c
   __syncthreads();
   const float b1 = att_b1[0];
   const long long be = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  float lw1[32], lb0[32], lb1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { lw1[k] = 0.f; lb0[k] = 0.f; }
   if (be < B * E) {
     const int e = static_cast<int>(be % E);
     const long long b = be / E;
@@ -558,25 +580,35 @@ n2e_bwd_kernel(const float* __restrict__ xprime, const float* __restrict__ pq, c
     }
     float dpe[32];
     for (int k = 0; k < 32; ++k) dpe[k] = 0.f;
-    float db1 = 0.f;
     for (int m = 0; m < cnt; ++m) {
       const float p = expf(s[m] - mx) / den;
       const float da = p * (dp[m] - pdot) * hv[m];     // d a_m
-      db1 += da;
+      lb1 += da;
+#pragma unroll
       for (int k = 0; k < 32; ++k) {
         const float pre = pb[mem[m] * 64 + k] + pe[k];
         const float act = fmaxf(pre, 0.f);
-        atomicAdd(&g_w1[k], act * da);
+        lw1[k] = fmaf(act, da, lw1[k]);
         const float r = (pre > 0.f) ? sw1[k] * da : 0.f;
         atomicAdd(d_pq + (b * N + mem[m]) * 64 + k, r);       // d pn_m
         dpe[k] += r;
       }
     }
+#pragma unroll
     for (int k = 0; k < 32; ++k) {
-      atomicAdd(&g_b0[k], dpe[k]);
+      lb0[k] += dpe[k];
       for (int m = 0; m < cnt; ++m) atomicAdd(d_pq + (b * N + mem[m]) * 64 + 32 + k, hv[m] * dpe[k]);   // d q_m
     }
-    atomicAdd(&g_b1, db1);
+  }
+  // attention-tail parameter gradients: per-thread partials -> warp reduction -> one shared atomic per warp
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float a = warp_sum(lw1[k]), c = warp_sum(lb0[k]);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&g_w1[k], a); atomicAdd(&g_b0[k], c); }
+  }
+  {
+    const float a = warp_sum(lb1);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&g_b1, a);
   }
   __syncthreads();
   if (threadIdx.x < 32) { atomicAdd(d_b0 + threadIdx.x, g_b0[threadIdx.x]); atomicAdd(d_w1 + threadIdx.x, g_w1[threadIdx.x]); }
@@ -645,8 +677,9 @@ int stage_bwd(const gn_stage_cfg* c, const gn_train_params* P, const float* h, c
   GN_TRYB(sgemm_dgrad(F(p.d_o1), 128, Lp0.W, 2 * D, F(p.d_inc), 2 * D, R, 128, 2 * D, 0, nullptr, 0, st));
   split_inc_kernel<<<nblk(R * 2 * D), 256, 0, st>>>(F(p.d_inc), F(p.d_agg), d_h, R, D, fN);
   // ---- agg = H^T ef  =>  d_ef = H d_agg ;  eo = H h
-  inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_agg), F(p.d_ef), B, N, E, D);
-  inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, h, F(p.eo), B, N, E, D);
+  { ProfScope ps__("bwd_gather", st);
+    inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_agg), F(p.d_ef), B, N, E, D);
+    inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, h, F(p.eo), B, N, E, D); }
   GN_LAUNCH_CHECK();
   cudaMemsetAsync(F(p.d_eo), 0, static_cast<size_t>(RE) * D * 4, st);
   // ---- T aggregation MLPs as written: ef = sum_t efeat_t (W1_t relu(W0_t eo + b0_t) + b1_t)
@@ -654,14 +687,16 @@ int stage_bwd(const gn_stage_cfg* c, const gn_train_params* P, const float* h, c
     const gn_lin& A0 = P->agg0[t]; const gn_lin& A1 = P->agg1[t];
     GN_TRYB(sgemm_nt(F(p.eo), D, A0.W, D, A0.b, F(p.u), 128, RE, 128, D, 1, 0, st));
     GN_TRYB(sgemm_nt(F(p.u), 128, A1.W, 128, A1.b, F(p.v), D, RE, D, 128, 0, 0, st));
-    rowdot_kernel<<<nblk(RE), 256, 0, st>>>(F(p.d_ef), F(p.v), F(p.d_efeat) + t, T, RE, D);
-    rowscale_kernel<<<nblk(RE * D), 256, 0, st>>>(F(p.d_ef), efeat + t, T, F(p.dv), RE, D);
+    { ProfScope ps__("bwd_rowops", st);
+      rowdot_scale_kernel<<<nblk(RE, 8), 256, 0, st>>>(F(p.d_ef), F(p.v), F(p.d_efeat) + t, T, efeat + t, T,
+                                                       F(p.dv), RE, D); }
     GN_TRYB(sgemm_wgrad(F(p.dv), D, F(p.u), 128, A1.dW, A1.db, RE, D, 128, st));
     GN_TRYB(sgemm_dgrad(F(p.dv), D, A1.W, 128, F(p.du), 128, RE, D, 128, 0, F(p.u), 128, st));
     GN_TRYB(sgemm_wgrad(F(p.du), 128, F(p.eo), D, A0.dW, A0.db, RE, 128, D, st));
     GN_TRYB(sgemm_dgrad(F(p.du), 128, A0.W, D, F(p.d_eo), D, RE, 128, D, 1, nullptr, 0, st));
   }
-  inc_scatter_kernel<<<nblk(R * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_eo), d_h, B, N, E, D, 1);
+  { ProfScope ps__("bwd_scatter", st);
+    inc_scatter_kernel<<<nblk(R * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_eo), d_h, B, N, E, D, 1); }
   // ---- edge_feat = sigmoid(fl) * softmax(2 (logits + g))
   gumbel_bwd_kernel<<<nblk(RE), 256, 0, st>>>(efeat, F(p.d_efeat), d_dist, F(p.d_logits), F(p.d_fl), RE, T);
   GN_LAUNCH_CHECK();
@@ -685,9 +720,10 @@ int stage_bwd(const gn_stage_cfg* c, const gn_train_params* P, const float* h, c
   // ---- node2edge: attention softmax + weighted gather
   cudaMemsetAsync(F(p.d_x), 0, static_cast<size_t>(R) * 64 * 4, st);
   cudaMemsetAsync(F(p.d_pq), 0, static_cast<size_t>(R) * 64 * 4, st);
+  { ProfScope ps__("bwd_n2e", st);
   n2e_bwd_kernel<<<nblk(RE, 128), 128, 0, st>>>(xprime, pq, H, hstride, c->pairwise, P->att_b0, P->att_w1, P->att_b1,
                                                F(p.d_edges), F(p.d_x), F(p.d_pq), P->d_att_b0, P->d_att_w1,
-                                               P->d_att_b1, B, N, E);
+                                               P->d_att_b1, B, N, E); }
   GN_LAUNCH_CHECK();
   // ---- pq = x' Wpq^T ; x' = W1 relu(W0 h + b0) + b1
   GN_TRYB(sgemm_wgrad(F(p.d_pq), 64, xprime, 64, Lpq.dW, nullptr, R, 64, 64, st));
