@@ -489,6 +489,34 @@ rowdot_scale_kernel(const float* __restrict__ def, const float* __restrict__ v, 
   if (lane == 0) col[r * ldc] = s;
 }
 
+// Row part of one aggregation MLP's backward (one warp per edge row, hidden width 128).  With
+// g = d_ef W1 (the un-scaled hidden gradient), u = relu(W0 eo + b0), w = edge_feat_t:
+//   d edge_feat_t = u . g + d_ef . b1     (= d_ef . (W1 u + b1): the second Linear is never re-run)
+//   du = w * g * (u > 0)  (in place over g)      dv = w * d_ef  (the dY operand of dW1 / db1)
+__global__ void __launch_bounds__(256)
+agg_bwd_rows_kernel(const float* __restrict__ u, float* __restrict__ g, const float* __restrict__ def,
+                    const float* __restrict__ b1, const float* __restrict__ w, long long ldw,
+                    float* __restrict__ d_w, long long ldd, float* __restrict__ dv, long long R, int D) {
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int lane = threadIdx.x & 31;
+  const float sc = __ldg(w + r * ldw);
+  const float4 uu = ldg_f4(u + r * 128 + 4 * lane);
+  float4 gg = *reinterpret_cast<const float4*>(g + r * 128 + 4 * lane);
+  float s = uu.x * gg.x;
+  s = fmaf(uu.y, gg.y, s); s = fmaf(uu.z, gg.z, s); s = fmaf(uu.w, gg.w, s);
+  gg.x = uu.x > 0.f ? sc * gg.x : 0.f; gg.y = uu.y > 0.f ? sc * gg.y : 0.f;
+  gg.z = uu.z > 0.f ? sc * gg.z : 0.f; gg.w = uu.w > 0.f ? sc * gg.w : 0.f;
+  *reinterpret_cast<float4*>(g + r * 128 + 4 * lane) = gg;
+  for (int c = 4 * lane; c < D; c += 128) {
+    const float4 a = ldg_f4(def + r * D + c), b = ldg_f4(b1 + c);
+    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+    *reinterpret_cast<float4*>(dv + r * D + c) = make_float4(sc * a.x, sc * a.y, sc * a.z, sc * a.w);
+  }
+  s = warp_sum(s);
+  if (lane == 0) d_w[r * ldd] = s;
+}
+
 // Gumbel-softmax / sigmoid backward per edge row.  edge_feat = f * dist, sum_t dist = 1  =>
 // f = sum_t edge_feat, dist = edge_feat / f.  y = (logits + g)/tau, tau = 1/2:
 //   d_dist_t = d_ef_t * f (+ external d_dist_t);  d_f = sum_t d_ef_t dist_t
@@ -686,12 +714,11 @@ int stage_bwd(const gn_stage_cfg* c, const gn_train_params* P, const float* h, c
   for (int t = 0; t < T; ++t) {
     const gn_lin& A0 = P->agg0[t]; const gn_lin& A1 = P->agg1[t];
     GN_TRYB(sgemm_nt(F(p.eo), D, A0.W, D, A0.b, F(p.u), 128, RE, 128, D, 1, 0, st));
-    GN_TRYB(sgemm_nt(F(p.u), 128, A1.W, 128, A1.b, F(p.v), D, RE, D, 128, 0, 0, st));
+    GN_TRYB(sgemm_dgrad(F(p.d_ef), D, A1.W, 128, F(p.du), 128, RE, D, 128, 0, nullptr, 0, st));   // g = d_ef W1
     { ProfScope ps__("bwd_rowops", st);
-      rowdot_scale_kernel<<<nblk(RE, 8), 256, 0, st>>>(F(p.d_ef), F(p.v), F(p.d_efeat) + t, T, efeat + t, T,
-                                                       F(p.dv), RE, D); }
+      agg_bwd_rows_kernel<<<nblk(RE, 8), 256, 0, st>>>(F(p.u), F(p.du), F(p.d_ef), A1.b, efeat + t, T,
+                                                       F(p.d_efeat) + t, T, F(p.dv), RE, D); }
     GN_TRYB(sgemm_wgrad(F(p.dv), D, F(p.u), 128, A1.dW, A1.db, RE, D, 128, st));
-    GN_TRYB(sgemm_dgrad(F(p.dv), D, A1.W, 128, F(p.du), 128, RE, D, 128, 0, F(p.u), 128, st));
     GN_TRYB(sgemm_wgrad(F(p.du), 128, F(p.eo), D, A0.dW, A0.db, RE, 128, D, st));
     GN_TRYB(sgemm_dgrad(F(p.du), 128, A0.W, D, F(p.d_eo), D, RE, 128, D, 1, nullptr, 0, st));
   }
