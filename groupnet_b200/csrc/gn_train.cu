@@ -517,6 +517,107 @@ agg_bwd_rows_kernel(const float* __restrict__ u, float* __restrict__ g, const fl
   if (lane == 0) d_w[r * ldd] = s;
 }
 
+// Pairwise aggregation backward on NODE rows (the collapse of the forward): with
+// P_t = h W0_t^T, Q_t = d_agg W1_t (both R x 128), c_t[n] = d_agg[n] . b1_t and, per edge e = (i, j) of a scene,
+//   u = relu(P_t[i] + P_t[j] + b0_t),   d_ef_e = d_agg[i] + d_agg[j]      (self loop: incidence 2, :124)
+//   d edge_feat[e, t] = (Q_t[i] + Q_t[j]) . u + c_t[i] + c_t[j]
+//   d pre_e = edge_feat[e, t] * (Q_t[i] + Q_t[j]) * (pre > 0);   dP_t[i] += d pre_e,  dP_t[j] += d pre_e
+//   G_t[i] += edge_feat[e, t] * u, G_t[j] likewise   (dW1_t = d_agg^T G_t, as in the forward)
+// the edge-level GEMMs (N^2 rows) of the as-written backward become node-level ones (N rows); this kernel does
+// the per-scene O(N^2 * 128) part.  One 128-thread CTA per (scene, t) item, thread = hidden column; (i, j)
+// and (j, i) share u, so the loop runs over unordered pairs.
+struct PairBwdPtrs { const float* b0[15]; const float* b1[15]; float* db0[15]; float* db1[15]; };
+
+__global__ void __launch_bounds__(128)
+pair_agg_bwd_kernel(const float* __restrict__ Pn, const float* __restrict__ Qn, const float* __restrict__ efeat,
+                    const float* __restrict__ d_agg, PairBwdPtrs ptrs,
+                    float* __restrict__ dPn, float* __restrict__ Gn, float* __restrict__ d_efeat,
+                    long long B, int N, int T, int D) {
+  extern __shared__ __align__(16) float sm[];
+  float* Ps = sm;                    // [N][128]
+  float* Qs = Ps + N * 128;          // [N][128]
+  float* dPs = Qs + N * 128;         // [N][128]
+  float* Gs = dPs + N * 128;         // [N][128]
+  float* qs = Gs + N * 128;          // [N][D]
+  float* ws = qs + N * D;            // [N*N]  edge_feat[:, t] of the scene
+  float* dws = ws + N * N;           // [N*N]  (Q_i + Q_j) . u per unordered pair, stored at [i][j], i <= j
+  float* cs = dws + N * N;           // [N]
+  float* Ss = cs + N;                // [N]
+  const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  const int E = N * N, LD = T * 128;
+  const long long items = B * T;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const long long b = item / T;
+    const int t = static_cast<int>(item - b * T);
+    __syncthreads();
+    for (int n = 0; n < N; ++n) {
+      const long long row = b * N + n;
+      Ps[n * 128 + c] = Pn[row * LD + t * 128 + c];
+      Qs[n * 128 + c] = Qn[row * LD + t * 128 + c];
+      dPs[n * 128 + c] = 0.f;
+      Gs[n * 128 + c] = 0.f;
+    }
+    for (int i = c; i < N * D; i += 128) qs[i] = d_agg[b * N * D + i];
+    for (int e = c; e < E; e += 128) { ws[e] = efeat[(b * E + e) * T + t]; dws[e] = 0.f; }
+    __syncthreads();
+    for (int n = warp; n < N; n += 4) {                  // c_t[n] = d_agg[n] . b1_t
+      float s = 0.f;
+      for (int k = lane; k < D; k += 32) s = fmaf(qs[n * D + k], __ldg(ptrs.b1[t] + k), s);
+      s = warp_sum(s);
+      if (lane == 0) cs[n] = s;
+    }
+    const float bb = __ldg(ptrs.b0[t] + c);
+    float db0 = 0.f;
+    for (int i = 0; i < N; ++i) {
+      const float pi = Ps[i * 128 + c], qi = Qs[i * 128 + c];
+      float dpi = 0.f, gi = 0.f;
+      {                                                  // self loop (i, i): eo = 2 h_i, d_ef = 2 d_agg[i]
+        const float pre = 2.f * pi + bb, u = fmaxf(pre, 0.f), t1 = 2.f * qi, w = ws[i * N + i];
+        const float dwp = warp_sum(t1 * u);
+        if (lane == 0) atomicAdd(&dws[i * N + i], dwp);
+        const float dpre = pre > 0.f ? w * t1 : 0.f;
+        dpi += 2.f * dpre; gi += 2.f * w * u; db0 += dpre;
+      }
+      for (int j = i + 1; j < N; ++j) {
+        const float pre = pi + Ps[j * 128 + c] + bb, u = fmaxf(pre, 0.f), t1 = qi + Qs[j * 128 + c];
+        const float w = ws[i * N + j] + ws[j * N + i];
+        const float dwp = warp_sum(t1 * u);
+        if (lane == 0) atomicAdd(&dws[i * N + j], dwp);
+        const float dpre = pre > 0.f ? w * t1 : 0.f;
+        dpi += dpre; gi += w * u; db0 += dpre;
+        dPs[j * 128 + c] += dpre;
+        Gs[j * 128 + c] += w * u;
+      }
+      dPs[i * 128 + c] += dpi;
+      Gs[i * 128 + c] += gi;
+    }
+    if (c < N) {                                         // S_t[n] = sum of edge_feat over the edges incident to n
+      float s = 0.f;
+      for (int j = 0; j < N; ++j) s += ws[c * N + j] + ws[j * N + c];
+      Ss[c] = s;
+    }
+    __syncthreads();
+    for (int n = 0; n < N; ++n) {
+      const long long row = b * N + n;
+      dPn[row * LD + t * 128 + c] = dPs[n * 128 + c];
+      Gn[row * LD + t * 128 + c] = Gs[n * 128 + c];
+    }
+    for (int e = c; e < E; e += 128) {
+      const int i = e / N, j = e - i * N;
+      const float d = dws[i <= j ? e : j * N + i] + (i == j ? 2.f * cs[i] : cs[i] + cs[j]);
+      d_efeat[(b * E + e) * T + t] = d;
+    }
+    if (ptrs.db0[t] != nullptr) atomicAdd(ptrs.db0[t] + c, db0);
+    if (ptrs.db1[t] != nullptr) {
+      for (int k = c; k < D; k += 128) {
+        float s = 0.f;
+        for (int n = 0; n < N; ++n) s = fmaf(Ss[n], qs[n * D + k], s);
+        atomicAdd(ptrs.db1[t] + k, s);
+      }
+    }
+  }
+}
+
 // Gumbel-softmax / sigmoid backward per edge row.  edge_feat = f * dist, sum_t dist = 1  =>
 // f = sum_t edge_feat, dist = edge_feat / f.  y = (logits + g)/tau, tau = 1/2:
 //   d_dist_t = d_ef_t * f (+ external d_dist_t);  d_f = sum_t d_ef_t dist_t
@@ -649,6 +750,7 @@ n2e_bwd_kernel(const float* __restrict__ xprime, const float* __restrict__ pq, c
 struct BwdPlan {
   size_t inc, o1, d_o1, d_inc, d_agg, d_ef, eo, d_eo, u, v, dv, du, d_efeat, d_logits, d_fl,
          z1, z, hd, hf, d_hd, d_z, d_z1, d_edges, d_x, d_pq, hid, d_hid, total;
+  size_t Pn, Qn, dPn, Gn;            // pairwise collapse: node-level (R x T*128) tensors
 };
 
 static void make_bwd_plan(const gn_stage_cfg* c, BwdPlan& p) {
@@ -657,8 +759,15 @@ static void make_bwd_plan(const gn_stage_cfg* c, BwdPlan& p) {
   size_t o = 0;
   auto take = [&](size_t floats) { size_t at = o; o += round_up_sz(floats * 4, 256); return at; };
   p.inc = take(R * 2 * D); p.o1 = take(R * 128); p.d_o1 = take(R * 128); p.d_inc = take(R * 2 * D);
-  p.d_agg = take(R * D); p.d_ef = take(RE * D); p.eo = take(RE * D); p.d_eo = take(RE * D);
-  p.u = take(RE * 128); p.v = take(RE * D); p.dv = take(RE * D); p.du = take(RE * 128);
+  p.d_agg = take(R * D);
+  p.d_ef = p.eo = p.d_eo = p.u = p.v = p.dv = p.du = 0;
+  p.Pn = p.Qn = p.dPn = p.Gn = 0;
+  if (c->pairwise) {                 // the aggregation backward runs on node rows (see pair_agg_bwd_kernel)
+    p.Pn = take(R * T * 128); p.Qn = take(R * T * 128); p.dPn = take(R * T * 128); p.Gn = take(R * T * 128);
+  } else {
+    p.d_ef = take(RE * D); p.eo = take(RE * D); p.d_eo = take(RE * D);
+    p.u = take(RE * 128); p.v = take(RE * D); p.dv = take(RE * D); p.du = take(RE * 128);
+  }
   p.d_efeat = take(RE * T); p.d_logits = take(RE * T); p.d_fl = take(RE);
   p.z1 = take(RE * 128); p.z = take(RE * 64); p.hd = take(RE * 128); p.hf = take(RE * 128);
   p.d_hd = take(RE * 128); p.d_z = take(RE * 64); p.d_z1 = take(RE * 128); p.d_edges = take(RE * 64);
@@ -704,26 +813,60 @@ int stage_bwd(const gn_stage_cfg* c, const gn_train_params* P, const float* h, c
   GN_TRYB(sgemm_wgrad(F(p.d_o1), 128, F(p.inc), 2 * D, Lp0.dW, Lp0.db, R, 128, 2 * D, st));
   GN_TRYB(sgemm_dgrad(F(p.d_o1), 128, Lp0.W, 2 * D, F(p.d_inc), 2 * D, R, 128, 2 * D, 0, nullptr, 0, st));
   split_inc_kernel<<<nblk(R * 2 * D), 256, 0, st>>>(F(p.d_inc), F(p.d_agg), d_h, R, D, fN);
+  if (c->pairwise) {
+    // ---- pairwise: aggregation backward on node rows (pair_agg_bwd_kernel)
+    const int LD = T * 128;
+    PairBwdPtrs pp;
+    memset(&pp, 0, sizeof(pp));
+    for (int t = 0; t < T; ++t) {
+      const gn_lin& A0 = P->agg0[t]; const gn_lin& A1 = P->agg1[t];
+      pp.b0[t] = A0.b; pp.b1[t] = A1.b; pp.db0[t] = A0.db; pp.db1[t] = A1.db;
+      GN_TRYB(sgemm_nt(h, D, A0.W, D, nullptr, F(p.Pn) + t * 128, LD, R, 128, D, 0, 0, st));              // P_t = h W0_t^T
+      GN_TRYB(sgemm_dgrad(F(p.d_agg), D, A1.W, 128, F(p.Qn) + t * 128, LD, R, D, 128, 0, nullptr, 0, st));  // Q_t = d_agg W1_t
+    }
+    {
+      const size_t smem = (static_cast<size_t>(4) * N * 128 + static_cast<size_t>(N) * D + 2 * static_cast<size_t>(N) * N + 2 * N) * 4;
+      cudaError_t e = cudaFuncSetAttribute(pair_agg_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));
+      if (per_sm < 1) per_sm = 1;
+      if (per_sm > 12) per_sm = 12;
+      const long long items = B * T;
+      const long long cap = static_cast<long long>(GN_SM_COUNT) * per_sm;
+      const unsigned grid = static_cast<unsigned>(items < cap ? items : cap);
+      ProfScope ps__("bwd_pair_agg", st);
+      pair_agg_bwd_kernel<<<grid, 128, smem, st>>>(F(p.Pn), F(p.Qn), efeat, F(p.d_agg), pp, F(p.dPn), F(p.Gn),
+                                                   F(p.d_efeat), B, N, T, D);
+    }
+    GN_LAUNCH_CHECK();
+    for (int t = 0; t < T; ++t) {
+      const gn_lin& A0 = P->agg0[t]; const gn_lin& A1 = P->agg1[t];
+      GN_TRYB(sgemm_wgrad(F(p.dPn) + t * 128, LD, h, D, A0.dW, nullptr, R, 128, D, st));                  // dW0_t = dP_t^T h
+      GN_TRYB(sgemm_dgrad(F(p.dPn) + t * 128, LD, A0.W, D, d_h, D, R, 128, D, 1, nullptr, 0, st));         // dh += dP_t W0_t
+      GN_TRYB(sgemm_wgrad(F(p.d_agg), D, F(p.Gn) + t * 128, LD, A1.dW, nullptr, R, D, 128, st));          // dW1_t = d_agg^T G_t
+    }
+  } else {
   // ---- agg = H^T ef  =>  d_ef = H d_agg ;  eo = H h
-  { ProfScope ps__("bwd_gather", st);
-    inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_agg), F(p.d_ef), B, N, E, D);
-    inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, h, F(p.eo), B, N, E, D); }
-  GN_LAUNCH_CHECK();
-  cudaMemsetAsync(F(p.d_eo), 0, static_cast<size_t>(RE) * D * 4, st);
-  // ---- T aggregation MLPs as written: ef = sum_t efeat_t (W1_t relu(W0_t eo + b0_t) + b1_t)
-  for (int t = 0; t < T; ++t) {
-    const gn_lin& A0 = P->agg0[t]; const gn_lin& A1 = P->agg1[t];
-    GN_TRYB(sgemm_nt(F(p.eo), D, A0.W, D, A0.b, F(p.u), 128, RE, 128, D, 1, 0, st));
-    GN_TRYB(sgemm_dgrad(F(p.d_ef), D, A1.W, 128, F(p.du), 128, RE, D, 128, 0, nullptr, 0, st));   // g = d_ef W1
-    { ProfScope ps__("bwd_rowops", st);
-      agg_bwd_rows_kernel<<<nblk(RE, 8), 256, 0, st>>>(F(p.u), F(p.du), F(p.d_ef), A1.b, efeat + t, T,
-                                                       F(p.d_efeat) + t, T, F(p.dv), RE, D); }
-    GN_TRYB(sgemm_wgrad(F(p.dv), D, F(p.u), 128, A1.dW, A1.db, RE, D, 128, st));
-    GN_TRYB(sgemm_wgrad(F(p.du), 128, F(p.eo), D, A0.dW, A0.db, RE, 128, D, st));
-    GN_TRYB(sgemm_dgrad(F(p.du), 128, A0.W, D, F(p.d_eo), D, RE, 128, D, 1, nullptr, 0, st));
+    { ProfScope ps__("bwd_gather", st);
+      inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_agg), F(p.d_ef), B, N, E, D);
+      inc_gather_kernel<<<nblk(RE * D), 256, 0, st>>>(H, hstride, c->pairwise, h, F(p.eo), B, N, E, D); }
+    GN_LAUNCH_CHECK();
+    cudaMemsetAsync(F(p.d_eo), 0, static_cast<size_t>(RE) * D * 4, st);
+    // ---- T aggregation MLPs as written: ef = sum_t efeat_t (W1_t relu(W0_t eo + b0_t) + b1_t)
+    for (int t = 0; t < T; ++t) {
+      const gn_lin& A0 = P->agg0[t]; const gn_lin& A1 = P->agg1[t];
+      GN_TRYB(sgemm_nt(F(p.eo), D, A0.W, D, A0.b, F(p.u), 128, RE, 128, D, 1, 0, st));
+      GN_TRYB(sgemm_dgrad(F(p.d_ef), D, A1.W, 128, F(p.du), 128, RE, D, 128, 0, nullptr, 0, st));   // g = d_ef W1
+      { ProfScope ps__("bwd_rowops", st);
+        agg_bwd_rows_kernel<<<nblk(RE, 8), 256, 0, st>>>(F(p.u), F(p.du), F(p.d_ef), A1.b, efeat + t, T,
+                                                         F(p.d_efeat) + t, T, F(p.dv), RE, D); }
+      GN_TRYB(sgemm_wgrad(F(p.dv), D, F(p.u), 128, A1.dW, A1.db, RE, D, 128, st));
+      GN_TRYB(sgemm_wgrad(F(p.du), 128, F(p.eo), D, A0.dW, A0.db, RE, 128, D, st));
+      GN_TRYB(sgemm_dgrad(F(p.du), 128, A0.W, D, F(p.d_eo), D, RE, 128, D, 1, nullptr, 0, st));
+    }
+    { ProfScope ps__("bwd_scatter", st);
+      inc_scatter_kernel<<<nblk(R * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_eo), d_h, B, N, E, D, 1); }
   }
-  { ProfScope ps__("bwd_scatter", st);
-    inc_scatter_kernel<<<nblk(R * D), 256, 0, st>>>(H, hstride, c->pairwise, F(p.d_eo), d_h, B, N, E, D, 1); }
   // ---- edge_feat = sigmoid(fl) * softmax(2 (logits + g))
   gumbel_bwd_kernel<<<nblk(RE), 256, 0, st>>>(efeat, F(p.d_efeat), d_dist, F(p.d_logits), F(p.d_fl), RE, T);
   GN_LAUNCH_CHECK();
