@@ -382,6 +382,8 @@ def test_bf16_wide_hyper_fused_vs_fp32_path(d, n, scale, bo, b):
     ("pairwise", 5, 64, 64, 0, 1, 7), ("hyper", 6, 64, 64, 3, 1, 9), ("hyper", 6, 64, 64, 6, 1, 9),
     ("pairwise", 11, 64, 64, 0, 1, 33), ("hyper", 11, 64, 64, 5, 1, 33),
     ("pairwise", 4, 32, 48, 0, 2, 5), ("hyper", 7, 128, 64, 2, 2, 6),
+    ("pairwise", 1, 64, 64, 0, 1, 5), ("pairwise", 2, 64, 32, 0, 1, 300), ("pairwise", 20, 64, 64, 0, 1, 3),
+    ("pairwise", 6, 128, 64, 0, 1, 17),
 ])
 def test_backward_matches_oracle_autograd(kind, n, d, bo, scale, layers, b):
     torch.manual_seed(500 + n + d + layers)
