@@ -370,6 +370,11 @@ def test_bf16_wide_hyper_fused_vs_fp32_path(d, n, scale, bo, b):
     assert_close(n16, n32, BF16_REL, "node_feat bf16 vs fp32")
     n16b, _, _ = m(h, corr, noise=[u])
     assert torch.equal(n16, n16b)                                      # deterministic
+    # incidence read in place from a concatenated new_H (scene stride > E*N, model/GroupNet_nba.py:296-299)
+    hcat = torch.zeros(b, 2 * n + 1, n, device=DEV)
+    hcat[:, n + 1:] = h16
+    n16c, _, _ = m(h, corr, noise=[u], H=hcat[:, n + 1:])
+    assert torch.equal(n16c, n16)
     # strided output (the concatenated feature tensor of PastEncoder.forward, :301-309)
     wide = torch.zeros(b, n, bo + 64, device=DEV)
     m(h, corr, noise=[u], out=wide[:, :, 32:32 + bo], want_factors=False)
