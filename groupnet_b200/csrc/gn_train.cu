@@ -308,6 +308,81 @@ sgemm_tn_fast_kernel(const float* __restrict__ A, long long lda, const float* __
   }
 }
 
+// ---------------------------------------------------------------------------
+// Narrow heads (the T-wide distribution head and the 1-wide factor head, N <= 16): the 64-wide tiles above
+// would idle 90 % of their lanes; these two are plain streaming kernels.
+//   dgrad:  dX[m][k] (+)= sum_n dY[m][n] W[n][k], optional ReLU mask;  thread = (row, 4 columns)
+//   wgrad:  dW[n][k] += sum_m dY[m][n] X[m][k], db[n] += sum_m dY[m][n];  thread = column k, rows sliced
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dgrad_narrow_kernel(const float* __restrict__ dY, long long ldy, const float* __restrict__ W, long long ldw,
+                    float* __restrict__ dX, long long ldx, long long M, int N, int K, int accumulate,
+                    const float* __restrict__ ref, long long ldr) {
+  extern __shared__ __align__(16) float wsm[];          // [N][K]
+  for (int i = threadIdx.x; i < N * K; i += 256) wsm[i] = W[static_cast<long long>(i / K) * ldw + (i % K)];
+  __syncthreads();
+  const int k4n = K >> 2;
+  const long long total = M * k4n;
+  for (long long i = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * 256) {
+    const long long m = i / k4n;
+    const int k = static_cast<int>(i - m * k4n) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = 0; n < N; ++n) {
+      const float y = __ldg(dY + m * ldy + n);
+      const float4 w = *reinterpret_cast<const float4*>(wsm + n * K + k);
+      acc.x = fmaf(y, w.x, acc.x); acc.y = fmaf(y, w.y, acc.y); acc.z = fmaf(y, w.z, acc.z); acc.w = fmaf(y, w.w, acc.w);
+    }
+    if (ref != nullptr) {
+      const float4 r = ldg_f4(ref + m * ldr + k);
+      if (!(r.x > 0.f)) acc.x = 0.f;
+      if (!(r.y > 0.f)) acc.y = 0.f;
+      if (!(r.z > 0.f)) acc.z = 0.f;
+      if (!(r.w > 0.f)) acc.w = 0.f;
+    }
+    float4* dst = reinterpret_cast<float4*>(dX + m * ldx + k);
+    if (accumulate) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+    *dst = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+wgrad_narrow_kernel(const float* __restrict__ dY, long long ldy, const float* __restrict__ X, long long ldx,
+                    float* __restrict__ dW, long long ldc, float* __restrict__ db,
+                    long long M, int N, int K, long long rows_per_slice) {
+  const int k = threadIdx.x;                             // blockDim.x == K (<= 256)
+  const long long mbeg = static_cast<long long>(blockIdx.x) * rows_per_slice;
+  const long long mend = min(M, mbeg + rows_per_slice);
+  float acc[16], bsum[16];
+#pragma unroll
+  for (int n = 0; n < 16; ++n) { acc[n] = 0.f; bsum[n] = 0.f; }
+  for (long long m0 = mbeg; m0 < mend; m0 += 8) {        // 8 independent row loads in flight per thread
+    float x[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) x[r] = (m0 + r < mend) ? __ldg(X + (m0 + r) * ldx + k) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      if (m0 + r < mend) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+          if (n < N) {
+            const float y = __ldg(dY + (m0 + r) * ldy + n);
+            acc[n] = fmaf(y, x[r], acc[n]);
+            if (k == 0) bsum[n] += y;
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 16; ++n) {
+    if (n < N) {
+      atomicAdd(dW + static_cast<long long>(n) * ldc + k, acc[n]);
+      if (k == 0 && db != nullptr) atomicAdd(db + n, bsum[n]);
+    }
+  }
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int sgemm_nt(const float* X, long long ldx, const float* W, long long ldw, const float* bias,
@@ -332,6 +407,17 @@ static int sgemm_dgrad(const float* dY, long long ldy, const float* W, long long
                        long long M, int N, int K, int accumulate, const float* ref, long long ldr,
                        cudaStream_t st) {
   if (M <= 0) return GN_OK;
+  if (N <= 16 && (K & 3) == 0 && (ldx & 3) == 0 && al16(dX) && (ref == nullptr || ((ldr & 3) == 0 && al16(ref))) &&
+      static_cast<size_t>(N) * K * 4 <= 48 * 1024) {
+    const long long total = M * (K >> 2);
+    long long blocks = (total + 255) / 256;
+    if (blocks > GN_SM_COUNT * 16) blocks = GN_SM_COUNT * 16;
+    { ProfScope ps__("bwd_sgemm", st);
+      dgrad_narrow_kernel<<<static_cast<unsigned>(blocks), 256, static_cast<size_t>(N) * K * 4, st>>>(
+          dY, ldy, W, ldw, dX, ldx, M, N, K, accumulate, ref, ldr); }
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+  }
   // here the contraction runs over N (the Linear's outputs) and the output has K columns
   if ((N % SG_K) == 0 && (ldy & 3) == 0 && (ldw & 3) == 0 && al16(dY) && al16(W) && K >= 32) {
     dim3 grid(static_cast<unsigned>((M + 127) / 128), (K + 63) / 64);
@@ -349,6 +435,18 @@ static int sgemm_dgrad(const float* dY, long long ldy, const float* W, long long
 static int sgemm_wgrad(const float* dY, long long ldy, const float* X, long long ldx, float* dW, float* db,
                        long long M, int N, int K, cudaStream_t st) {
   if (M <= 0 || dW == nullptr) return GN_OK;
+  if (N <= 16 && K <= 256 && (K & 31) == 0) {
+    long long slices = (M + 2047) / 2048;
+    if (slices < 4 * GN_SM_COUNT) slices = 4 * GN_SM_COUNT;
+    if (slices > (M + 63) / 64) slices = (M + 63) / 64;
+    if (slices < 1) slices = 1;
+    const long long rps = (M + slices - 1) / slices;
+    slices = (M + rps - 1) / rps;
+    { ProfScope ps__("bwd_wgrad", st);
+      wgrad_narrow_kernel<<<static_cast<unsigned>(slices), K, 0, st>>>(dY, ldy, X, ldx, dW, K, db, M, N, K, rps); }
+    GN_LAUNCH_CHECK();
+    return GN_OK;
+  }
   // row slices: at most 4096 rows each, but enough of them to fill the GPU twice when M is small
   // (the hyper layers have 12x / 121x fewer edge rows than the pairwise layer)
   const long long tiles = static_cast<long long>((N + 127) / 128) * ((K + 63) / 64);
