@@ -396,14 +396,21 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core path (2e-2 parity); fp32: FFMA path (1e-5 parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="nba", choices=["nba", "crowd"],
+    ap.add_argument("--workload", default="nba", choices=["nba", "crowd", "fish8", "fish20"],
                     help="nba: BASELINE configs[2] (the headline line); crowd: configs[3], N=64, h_dim 256, "
-                         "scales {2,4,8,16}, 262,144 scenes sharded over the GPUs (strong scaling)")
+                         "scales {2,4,8,16}, 262,144 scenes sharded over the GPUs (strong scaling); fish8 / fish20: "
+                         "configs[1], the MS_HGNN layers at the fish dataset shapes (8 agents, scales {3,5,8}; "
+                         "20 agents, scales {5,8}; SURVEY.md 8d), 65,536 synthetic scenes per GPU")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: fwd+bwd through the three layers + one NCCL all-reduce of the flat gradient "
                          "bucket (BASELINE config 5); per-GPU batch --scenes (default 8192 in this mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global AGENTS, SCALES, WORKLOAD
+    if args.workload == "fish8":
+        AGENTS, SCALES, WORKLOAD = 8, (3, 5, 8), "fish_synth_B65536_N8_D64_scales3-5-8"
+    elif args.workload == "fish20":
+        AGENTS, SCALES, WORKLOAD = 20, (5, 8), "fish_synth_B65536_N20_D64_scales5-8"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
