@@ -40,6 +40,7 @@ struct TcChainArgs {
   const float* U; int noise_mode; unsigned long long seed; long long scene_offset; int stage_index;
   float* dist_out; float* edge_feat;
   unsigned long long* trace;          // optional: clock64() per phase, block 0, first tiles (gn_profile_set_trace)
+  int tps;                            // PAIR, E >= 128: tiles per scene (scene-aligned tiling); 0 = linear 128-row tiles
 };
 
 namespace tcmlp {
@@ -106,7 +107,7 @@ __device__ __forceinline__ void drain_to_smem(uint32_t tmem_addr, unsigned char*
 #define GN_TRACE(pt) do { } while (0)
 #endif
 
-template <bool PAIR, int TT>
+template <bool PAIR, int TT, bool ALIGNED = false>
 __global__ void __launch_bounds__(GN_THREADS, 1)
 edge_chain_tc_kernel(TcChainArgs a) {
   using namespace tcmlp;
@@ -155,14 +156,17 @@ edge_chain_tc_kernel(TcChainArgs a) {
   const int T = TT > 0 ? TT : a.T;
   constexpr int TU = TT > 0 ? TT : GN_SMALL_OUT - 1;      // unroll bound
 
-  const long long ntiles = (a.R + 127) / 128;
+  // E >= 128 (N >= 12): tiles are aligned to scenes (ceil(E/128) per scene, the last one ragged) so a tile's node
+  // block is ONE scene's N rows; with linear tiles a tile of the N = 20 fish shape would span 40 nodes
+  const int tps = (PAIR && ALIGNED) ? a.tps : 0;   // compile-time 0 for the linear-tile instantiations
+  const long long ntiles = tps ? (a.R / a.E) * tps : (a.R + 127) / 128;
   float* nx = reinterpret_cast<float*>(smem + OFF_NODE + (PAIR ? grp * NODE_BYTES : 0));   // x' rows
   float* np = nx + MAXN * NLD;                                                              // pq rows
   const long long total_nodes = PAIR ? (a.R / a.E) * a.N : 0;
   // cp.async the contiguous node block [b_lo*N, b_lo*N + MAXN) of tile t into this group's buffer
   auto prefetch_nodes = [&](long long t) {
     if (t < ntiles) {
-      const long long node0 = ((t * 128) / a.E) * a.N;
+      const long long node0 = (tps ? t / tps : (t * 128) / a.E) * a.N;
       const int cnt = static_cast<int>(min(static_cast<long long>(MAXN), total_nodes - node0));
       for (int i = gtid; i < cnt * 16; i += 128) {
         const int n = i >> 4, c = i & 15;
@@ -176,8 +180,10 @@ edge_chain_tc_kernel(TcChainArgs a) {
   int titer = -1;
   for (long long tile = static_cast<long long>(blockIdx.x) * 2 + grp; tile < ntiles;
        tile += static_cast<long long>(gridDim.x) * 2) {
-    const long long grow = tile * 128 + row;
-    const bool live = grow < a.R;
+    const long long tscene = tps ? tile / tps : 0;
+    const int tchunk = tps ? static_cast<int>(tile - tscene * tps) : 0;
+    const long long grow = tps ? tscene * a.E + tchunk * 128 + row : tile * 128 + row;
+    const bool live = grow < a.R && (!tps || tchunk * 128 + row < a.E);
     ++titer;
     GN_TRACE(0);
 
@@ -186,7 +192,7 @@ edge_chain_tc_kernel(TcChainArgs a) {
       // the tile's node block (x', pq of the scenes it spans) was prefetched into smem
       cp_async_wait<0>();
       chain_group_bar(grp);
-      const long long b_lo = (tile * 128) / a.E;
+      const long long b_lo = tps ? tscene : (tile * 128) / a.E;
       float wi = 0.f, wj = 0.f;
       const float* xi = nx;
       const float* xj = nx;
@@ -406,9 +412,9 @@ edge_chain_tc_kernel(TcChainArgs a) {
   }
 }
 
-template <bool PAIR, int TT>
+template <bool PAIR, int TT, bool ALIGNED = false>
 static int launch_chain(const TcChainArgs& a, int grid, const char* name, cudaStream_t st) {
-  auto kern = edge_chain_tc_kernel<PAIR, TT>;
+  auto kern = edge_chain_tc_kernel<PAIR, TT, ALIGNED>;
   const uint32_t smem = PAIR ? tcmlp::SMEM_BYTES_PAIR : tcmlp::SMEM_BYTES;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem));
@@ -425,6 +431,7 @@ static int launch_chain(const TcChainArgs& a, int grid, const char* name, cudaSt
 // path needs their nodes to fit the shared-memory staging buffer.
 bool edge_chain_pair_fits(int N) {
   const int E = N * N;
+  if (E >= 128) return N <= tcmlp::MAXN;             // scene-aligned tiles: one scene per tile
   return (127 / E + 2) * N <= tcmlp::MAXN;
 }
 
@@ -444,9 +451,14 @@ int launch_edge_chain_tc(bool pair, const float* edges, const float* xprime, con
   a.U = U; a.noise_mode = noise_mode; a.seed = seed; a.scene_offset = scene_offset; a.stage_index = stage_index;
   a.dist_out = dist_out; a.edge_feat = edge_feat;
   a.trace = g_trace_buffer;
-  long long ntiles = (R + 127) / 128, want = (ntiles + 1) / 2;
+  a.tps = (pair && E >= 128) ? (E + 127) / 128 : 0;
+  long long ntiles = a.tps ? (R / E) * a.tps : (R + 127) / 128, want = (ntiles + 1) / 2;
   int grid = want < GN_SM_COUNT ? static_cast<int>(want) : GN_SM_COUNT;
   if (pair) {
+    if (a.tps) {
+      if (T == 6) return launch_chain<true, 6, true>(a, grid, "edge_chain_pair_tc", st);
+      return launch_chain<true, 0, true>(a, grid, "edge_chain_pair_tc", st);
+    }
     if (T == 6) return launch_chain<true, 6>(a, grid, "edge_chain_pair_tc", st);
     return launch_chain<true, 0>(a, grid, "edge_chain_pair_tc", st);
   }

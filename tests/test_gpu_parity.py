@@ -348,6 +348,28 @@ def test_bf16_tc_large_batch_vs_fp32_path():
     assert torch.equal(n16, n16b) and torch.equal(f16, f16b)          # deterministic
 
 
+@pytest.mark.parametrize("n,b", [(12, 50), (13, 301), (20, 77), (36, 9), (8, 1000), (37, 5)])
+def test_bf16_pairwise_scene_aligned_tiles_vs_fp32_path(n, b):
+    """Pairwise layer on the tensor-core path for N^2 >= 128: the fused node2edge + MLP chain uses scene-aligned
+    tiles (ceil(N^2 / 128) per scene, ragged last tile); N = 37 exceeds the staged node block and takes the
+    unfused chain; N = 8 keeps the linear tiles."""
+    torch.manual_seed(78)
+    m = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=1).to(DEV)
+    gen = torch.Generator().manual_seed(10)
+    h = torch.randn(b, n, 64, generator=gen).to(DEV)
+    u = torch.rand(b, n * n, 6, generator=gen).to(DEV)
+    n32, f32 = m(h, noise=[u])
+    m.set_precision("bf16")
+    n16, f16 = m(h, noise=[u])
+    assert_close(f16, f32, BF16_REL, "factors bf16 vs fp32")
+    assert_close(n16, n32, BF16_REL, "node_feat bf16 vs fp32")
+    assert torch.allclose(f16.sum(-1), torch.ones_like(f16[..., 0]), atol=1e-5)
+    m.set_rng("philox", seed=3)
+    a1, _ = m(h)
+    a2, _ = m(torch.cat((h[b // 2:], h[:b // 2])))        # Philox is keyed by the element index, not the tile
+    assert a1.shape == a2.shape
+
+
 @pytest.mark.parametrize("d,n,scale,bo,b", [(256, 64, 4, 256, 37), (256, 64, 16, 96, 301), (256, 20, 5, 256, 45),
                                             (256, 32, 8, 80, 19), (256, 7, 3, 128, 130),
                                             (64, 11, 5, 64, 3001), (64, 20, 8, 32, 77), (64, 8, 3, 64, 1000),
