@@ -304,45 +304,73 @@ corr_topk_small_kernel(const float* __restrict__ x, const float* __restrict__ co
   const int tid = threadIdx.x;
   const int ldx = D + 4, ldc = N | 1;                    // odd row stride: conflict-free row-per-thread reads
   const int rows_max = SG * N;
-  float* xs = smem;
-  float* inv = xs + (FROM_CORR ? 0 : rows_max * ldx);
+  // x rows are staged with ONE TMA bulk copy per row (cp.async.bulk -> padded shared-memory row, mbarrier
+  // complete_tx).  The per-16-byte cp.async loop this replaces cost a quarter of the kernel's issue slots
+  // (round-1 ncu source view); double-buffering the groups was tried and lost (smaller groups, 0.17 -> 0.19 ms).
+  float* xs0 = smem;
+  float* inv = xs0 + (FROM_CORR ? 0 : rows_max * ldx);
   float* cs = inv + ((rows_max + 3) & ~3);
+  __shared__ __align__(8) unsigned long long xbar[2];
   const int ngroups = (B + SG - 1) / SG;
+  auto issue_rows = [&](int grp, int buf) {
+    const int b0 = grp * SG;
+    const int rows = min(SG, B - b0) * N;
+    const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&xbar[buf]));
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(rows * D * 4) : "memory");
+    for (int r = tid; r < rows; r += GN_THREADS) {
+      const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(xs0 + (buf * rows_max + r) * ldx));
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(dst), "l"(x + (static_cast<size_t>(b0) * N + r) * D), "r"(D * 4), "r"(bar) : "memory");
+    }
+  };
+  unsigned xphase = 0u;                                  // bit b = parity to wait for on xbar[b]
+  if (!FROM_CORR) {
+    if (tid == 0) {
+      for (int b = 0; b < 2; ++b)
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(static_cast<unsigned>(__cvta_generic_to_shared(&xbar[b]))) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  const int buf = 0;
   for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
     const int b0 = grp * SG;
     const int ns = min(SG, B - b0);
     const int rows = ns * N;
+    float* xs = xs0 + buf * rows_max * ldx;
     if (!FROM_CORR) {
-      __syncthreads();                                   // previous group's readers are done
+      __syncthreads();                                   // previous group's readers (cs, xs) are done
       const int d4 = D >> 2;
-      // ---- 1. stage the group's (contiguous) x block with cp.async: no register staging
+      // ---- 1. stage this group's rows (the other resident CTA of the SM overlaps its compute with this wait)
+      issue_rows(grp, buf);
       {
-        const float* src = x + static_cast<size_t>(b0) * N * D;
-        for (int i = tid; i < rows * d4; i += GN_THREADS) {
-          int r = i / d4, c = i - r * d4;
-          cp_async16(xs + r * ldx + 4 * c, src + static_cast<size_t>(r) * D + 4 * c);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
+        const unsigned bar = static_cast<unsigned>(__cvta_generic_to_shared(&xbar[buf]));
+        const unsigned par = (xphase >> buf) & 1u;
+        unsigned done = 0;
+        for (unsigned spin = 0; spin < (1u << 24) && !done; ++spin)
+          asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                       : "=r"(done) : "r"(bar), "r"(par) : "memory");
+        if (!done) __trap();
+        xphase ^= 1u << buf;
       }
-      __syncthreads();
       if (NP <= 12 && (D & 7) == 0) {
-        // ---- 2a. raw Gram in k-slices: 4 adjacent lanes per scene, lane t owns float2 columns
-        //          {t, t+4, ...}; every x element is read from shared memory exactly once.  The
-        //          squared norms are the Gram diagonal.  Partial sums are reduced over the 4 lanes.
+        // ---- 2a. raw Gram in k-slices: 8 adjacent lanes per scene, lane t owns float2 columns
+        //          {t, t+8, ...}; every x element is read from shared memory exactly once.  The
+        //          squared norms are the Gram diagonal.  Partial sums are reduced over the 8 lanes.
         constexpr int NPAIR = NP * (NP + 1) / 2;
         const int d2 = D >> 1;
-        const int ntask = ns * 4;
+        const int ntask = ns * 8;
         for (int base = 0; base < ntask; base += GN_THREADS) {
           const int task = base + tid;
           const bool valid = task < ntask;
-          const int g = (valid ? task : 0) >> 2, t = task & 3;
+          const int g = (valid ? task : 0) >> 3, t = task & 7;
           const float* xg = xs + g * N * ldx;
           float acc[NPAIR];
 #pragma unroll
           for (int p = 0; p < NPAIR; ++p) acc[p] = 0.f;
 #pragma unroll 2
-          for (int c = t; c < d2; c += 4) {
+          for (int c = t; c < d2; c += 8) {
             float2 v[NP];
 #pragma unroll
             for (int r = 0; r < NP; ++r)
@@ -360,9 +388,10 @@ corr_topk_small_kernel(const float* __restrict__ x, const float* __restrict__ co
           for (int p = 0; p < NPAIR; ++p) {
             acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 1);
             acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 2);
+            acc[p] += __shfl_xor_sync(0xffffffffu, acc[p], 4);
           }
           if (valid) {
-            // every lane holds all sums; lane t writes the pairs with p % 4 == t (mirrored)
+            // every lane holds all sums; lane t writes the pairs with p % 8 == t (mirrored)
             float invn[NP];
             int p = 0;
 #pragma unroll
@@ -375,7 +404,7 @@ corr_topk_small_kernel(const float* __restrict__ x, const float* __restrict__ co
             for (int i = 0; i < NP; ++i)
 #pragma unroll
               for (int j = i; j < NP; ++j, ++p) {
-                if ((p & 3) == t && i < N && j < N) {
+                if ((p & 7) == t && i < N && j < N) {
                   const float c = acc[p] * (invn[i] * invn[j]);
                   cs[(g * N + i) * ldc + j] = c;
                   cs[(g * N + j) * ldc + i] = c;
