@@ -51,38 +51,9 @@ struct HyperFused64Args {
 };
 
 namespace {
-__device__ __forceinline__ void arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc::smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void drain_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// coalesced copy of the tile's incidence blocks into shared memory, row stride ldr floats
-__device__ __forceinline__ void stage_raw_H(float* raw, const float* __restrict__ H, long long hstride,
-                                            int b0s, int ns, int N, int ldr, int tid) {
-  const int per = N * N;
-  if ((N & 3) == 0 && (hstride & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
-    const int n4 = N >> 2, per4 = per >> 2;
-    for (int i = tid; i < ns * per4; i += 256) {
-      const int sc = i / per4, r4 = i - sc * per4;
-      const int e = r4 / n4, c4 = r4 - e * n4;
-      *reinterpret_cast<float4*>(raw + (sc * N + e) * ldr + 4 * c4) =
-          ldg_f4(H + static_cast<size_t>(b0s + sc) * hstride + 4 * r4);
-    }
-  } else {
-    for (int i = tid; i < ns * per; i += 256) {
-      const int sc = i / per, r = i - sc * per;
-      const int e = r / N, n = r - e * N;
-      raw[(sc * N + e) * ldr + n] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + r);
-    }
-  }
-}
+__device__ __forceinline__ void arrive(uint64_t* b) { tc::mbar_arrive(b); }
+__device__ __forceinline__ void expect_tx(uint64_t* b, uint32_t bytes) { tc::mbar_expect_tx(b, bytes); }
+using tc::bulk_g2s; using tc::drain_bar; using tc::stage_raw_H;
 }  // namespace
 
 __global__ void __launch_bounds__(hf64::THREADS, 2)

@@ -39,15 +39,10 @@ struct NodePre256Args {
   const float* h; const unsigned char* wstream; float* xprime; float* pq; long long R;
 };
 
-__device__ __forceinline__ void np_arrive(uint64_t* b) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(tc::smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void np_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc::smem_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void np_bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+__device__ __forceinline__ void np_arrive(uint64_t* b) { tc::mbar_arrive(b); }
+__device__ __forceinline__ void np_expect_tx(uint64_t* b, uint32_t bytes) { tc::mbar_expect_tx(b, bytes); }
+__device__ __forceinline__ void np_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  tc::bulk_g2s(dst, src, bytes, bar);
 }
 
 __global__ void __launch_bounds__(np2::THREADS, 1)

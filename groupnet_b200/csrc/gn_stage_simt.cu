@@ -176,156 +176,13 @@ node2edge_pair_kernel(const float* __restrict__ xprime, const float* __restrict_
   }
 }
 
-// ===========================================================================
-// k2b: node2edge, hyper (incidence H (B,E,N) given, E <= N <= 64).
-// A CTA of 128 threads owns SC whole scenes at a time (SC*max(E,N) <= 128): the
-// scenes' node rows (x', pq, h) and incidence rows are contiguous in HBM and
-// are staged once in shared memory with 128-bit loads; then ONE THREAD PER
-// HYPEREDGE walks its member list: attention logits, softmax over all N nodes
-// (non-members enter with logit 0, :135-137), weighted gather of x' (edges) and
-// plain gather of h (eo = H @ h for the aggregation MLPs).
-// ===========================================================================
-constexpr int N2H_THREADS = 128;
-
-__global__ void __launch_bounds__(N2H_THREADS)
-node2edge_hyper_kernel(const float* __restrict__ xprime, const float* __restrict__ pq,
-                       const float* __restrict__ h, const float* __restrict__ H,
-                       int B, int N, int E, int D, long long hstride, int SC, gn_stage_weights W,
-                       float* __restrict__ edges, float* __restrict__ eo) {
-  extern __shared__ __align__(16) float smem[];
-  const int ldh = D + 4, ldn = N + 1;
-  const int maxnodes = SC * N, maxedges = SC * E;
-  float* xs = smem;                              // [SC*N][68]
-  float* ps = xs + maxnodes * N2E_LD;            // [SC*N][68]  pn | q
-  float* hs = ps + maxnodes * N2E_LD;            // [SC*N][D+4]
-  float* Hs = hs + maxnodes * ldh;               // [SC*E][N+1]
-  float* att = Hs + ((maxedges * ldn + 3) & ~3); // [SC*E][N+1]  a_m, then softmax weights (member order)
-  unsigned char* mid = reinterpret_cast<unsigned char*>(att + ((maxedges * ldn + 3) & ~3));   // [SC*E][N] member ids
-  __shared__ float sb0[GN_ATT_HIDDEN], sw1[GN_ATT_HIDDEN];
-  const int tid = threadIdx.x;
-  if (tid < GN_ATT_HIDDEN) { sb0[tid] = __ldg(W.att_b0 + tid); sw1[tid] = __ldg(W.att_w1 + tid); }
-  const float b1 = __ldg(W.att_b1);
-  const int d4 = D >> 2;
-  const int ntiles = (B + SC - 1) / SC;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int b0s = tile * SC, ns = min(SC, B - b0s);
-    const int nn = ns * N, ne = ns * E;
-    __syncthreads();
-    for (int i = tid; i < nn * 16; i += N2H_THREADS) {
-      int n = i >> 4, c = i & 15;
-      size_t g = (static_cast<size_t>(b0s) * N + n) * GN_ATT_DIM + 4 * c;
-      *reinterpret_cast<float4*>(xs + n * N2E_LD + 4 * c) = ldg_f4(xprime + g);
-      *reinterpret_cast<float4*>(ps + n * N2E_LD + 4 * c) = ldg_f4(pq + g);
-    }
-    for (int i = tid; i < nn * d4; i += N2H_THREADS) {
-      int n = i / d4, c = i - n * d4;
-      *reinterpret_cast<float4*>(hs + n * ldh + 4 * c) =
-          ldg_f4(h + (static_cast<size_t>(b0s) * N + n) * D + 4 * c);
-    }
-    for (int i = tid; i < ne * N; i += N2H_THREADS) {
-      int e = i / N, n = i - e * N;              // e = scene-in-tile * E + edge
-      int sc = e / E;
-      Hs[e * ldn + n] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + static_cast<size_t>(e - sc * E) * N + n);
-    }
-    __syncthreads();
-    if (tid < ne) {
-      const int e = tid, sc = e / E;
-      const float* Hr = Hs + e * ldn;
-      float* ar = att + e * ldn;
-      unsigned char* mr = mid + e * N;
-      const int nb = sc * N;                     // first node row of this edge's scene
-      // member list
-      int cnt = 0;
-      for (int n = 0; n < N; ++n)
-        if (Hr[n] != 0.f) mr[cnt++] = static_cast<unsigned char>(n);
-      // pe[k] = sum_m H[e,m] q_m[k] + b0[k]
-      float pe[GN_ATT_HIDDEN];
-#pragma unroll
-      for (int k = 0; k < GN_ATT_HIDDEN; ++k) pe[k] = sb0[k];
-      for (int m = 0; m < cnt; ++m) {
-        const int n = mr[m];
-        const float hv = Hr[n];
-        const float* q = ps + (nb + n) * N2E_LD + 32;
-#pragma unroll
-        for (int k4 = 0; k4 < GN_ATT_HIDDEN; k4 += 4) {
-          float4 v = *reinterpret_cast<const float4*>(q + k4);
-          pe[k4] = fmaf(hv, v.x, pe[k4]); pe[k4 + 1] = fmaf(hv, v.y, pe[k4 + 1]);
-          pe[k4 + 2] = fmaf(hv, v.z, pe[k4 + 2]); pe[k4 + 3] = fmaf(hv, v.w, pe[k4 + 3]);
-        }
-      }
-      // logits of the members (times H), running max over ALL N nodes
-      float mx = (cnt < N) ? 0.f : -INFINITY;
-      for (int m = 0; m < cnt; ++m) {
-        const int n = mr[m];
-        const float* pn = ps + (nb + n) * N2E_LD;
-        float a = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < GN_ATT_HIDDEN; k4 += 4) {
-          float4 v = *reinterpret_cast<const float4*>(pn + k4);
-          a = fmaf(fmaxf(v.x + pe[k4], 0.f), sw1[k4], a);
-          a = fmaf(fmaxf(v.y + pe[k4 + 1], 0.f), sw1[k4 + 1], a);
-          a = fmaf(fmaxf(v.z + pe[k4 + 2], 0.f), sw1[k4 + 2], a);
-          a = fmaf(fmaxf(v.w + pe[k4 + 3], 0.f), sw1[k4 + 3], a);
-        }
-        a = (a + b1) * Hr[n];
-        ar[m] = a;
-        mx = fmaxf(mx, a);
-      }
-      float den = static_cast<float>(N - cnt) * expf(-mx);
-      for (int m = 0; m < cnt; ++m) { float ex = expf(ar[m] - mx); ar[m] = ex; den += ex; }
-      for (int m = 0; m < cnt; ++m) ar[m] = ar[m] / den * Hr[mr[m]];
-      // edges_e = sum_m w_m x'_m   (64 wide), written as one 256-byte row
-      {
-        float acc[GN_ATT_DIM];
-#pragma unroll
-        for (int c = 0; c < GN_ATT_DIM; ++c) acc[c] = 0.f;
-        for (int m = 0; m < cnt; ++m) {
-          const float wgt = ar[m];
-          const float* xr = xs + (nb + mr[m]) * N2E_LD;
-#pragma unroll
-          for (int c = 0; c < GN_ATT_DIM; c += 4) {
-            float4 v = *reinterpret_cast<const float4*>(xr + c);
-            acc[c] = fmaf(wgt, v.x, acc[c]); acc[c + 1] = fmaf(wgt, v.y, acc[c + 1]);
-            acc[c + 2] = fmaf(wgt, v.z, acc[c + 2]); acc[c + 3] = fmaf(wgt, v.w, acc[c + 3]);
-          }
-        }
-        float* dst = edges + (static_cast<size_t>(b0s) * E + e) * GN_ATT_DIM;
-#pragma unroll
-        for (int c = 0; c < GN_ATT_DIM; c += 4)
-          *reinterpret_cast<float4*>(dst + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-      }
-      // eo_e = sum_m H[e,m] h_m   (D wide, 64 columns at a time)
-      for (int c0 = 0; c0 < D; c0 += 64) {
-        float acc[64];
-#pragma unroll
-        for (int c = 0; c < 64; ++c) acc[c] = 0.f;
-        const int w4 = min(64, D - c0);
-        for (int m = 0; m < cnt; ++m) {
-          const float hv = Hr[mr[m]];
-          const float* hr = hs + (nb + mr[m]) * ldh + c0;
-#pragma unroll
-          for (int c = 0; c < 64; c += 4) {
-            if (c < w4) {
-              float4 v = *reinterpret_cast<const float4*>(hr + c);
-              acc[c] = fmaf(hv, v.x, acc[c]); acc[c + 1] = fmaf(hv, v.y, acc[c + 1]);
-              acc[c + 2] = fmaf(hv, v.z, acc[c + 2]); acc[c + 3] = fmaf(hv, v.w, acc[c + 3]);
-            }
-          }
-        }
-        float* dst = eo + (static_cast<size_t>(b0s) * E + e) * D + c0;
-#pragma unroll
-        for (int c = 0; c < 64; c += 4)
-          if (c < w4) *reinterpret_cast<float4*>(dst + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
-      }
-    }
-  }
-}
+constexpr int N2H_THREADS = 128;                        // block size of edge2node_hyper
 
 // ===========================================================================
 // k2c: node2edge, hyper, ONE WARP PER HYPEREDGE (N <= 64, D % 4 == 0, D <= 256).
-// Same math as k2b (model/MS_HGNN_batch.py:357-370) with the 32 lanes of a warp across the attention
+// model/MS_HGNN_batch.py:357-370, with the 32 lanes of a warp across the attention
 // hidden units (32) / the feature columns, so a CTA of 8 warps keeps every lane busy whatever E is:
-// the crowd shape (N = E = 64, h_dim 256) left k2b with 64 active threads per SM.  A CTA stages SC
+// a thread-per-hyperedge form left the crowd shape (N = E = 64, h_dim 256) with 64 active threads per SM.  A CTA stages SC
 // whole scenes (x', pq, H and — only when the caller wants eo = H @ h — h) in shared memory with
 // 128-bit loads; the member list of an edge is two ballots over its incidence row.
 // ===========================================================================
@@ -445,7 +302,7 @@ node2edge_hyper_warp_kernel(const float* __restrict__ xprime, const float* __res
 }
 
 // ===========================================================================
-// k2d: node2edge, hyper, FOUR LANES PER HYPEREDGE (E >= 4, N <= 64).  Same math as k2b/k2c.
+// k2d: node2edge, hyper, FOUR LANES PER HYPEREDGE (E >= 4, N <= 64).  Same math as k2c.
 // Lane q of a quad owns attention hidden units [8q, 8q+8) and feature columns [16q, 16q+16) (and a
 // quarter of the h columns when eo = H @ h is wanted), so the per-member work is 128-bit shared-memory
 // loads + FMAs with one 2-step quad reduction for the logit: ~7x fewer warp instructions per edge than
@@ -1134,24 +991,7 @@ static int launch_node2edge_hyper(const float* xprime, const float* pq, const fl
     GN_LAUNCH_CHECK();
     return GN_OK;
   }
-  auto bytes = [&](int sc) -> size_t {
-    size_t nodes = static_cast<size_t>(sc) * N, ed = static_cast<size_t>(sc) * E;
-    size_t fl = 2 * nodes * N2E_LD + nodes * (D + 4) + 2 * ((ed * (N + 1) + 3) & ~size_t(3));
-    return fl * 4 + ed * N + 16;
-  };
-  int SC = N2H_THREADS / (E > N ? E : N);
-  if (SC < 1) SC = 1;
-  while (SC > 1 && bytes(SC) > 110 * 1024) --SC;
-  size_t smem = bytes(SC);
-  GN_TRY(set_smem(node2edge_hyper_kernel, smem));
-  const int ntiles = (B + SC - 1) / SC;
-  int per_sm = smem > 113 * 1024 ? 1 : (smem > 75 * 1024 ? 2 : (smem > 56 * 1024 ? 3 : 4));
-  int grid = ntiles < GN_SM_COUNT * per_sm ? ntiles : GN_SM_COUNT * per_sm;
-  { ProfScope ps__("node2edge_hyper", st);
-    node2edge_hyper_kernel<<<grid, N2H_THREADS, smem, st>>>(xprime, pq, h, H, B, N, E, D, hstride, SC,
-                                                            *w, edges, eo); }
-  GN_LAUNCH_CHECK();
-  return GN_OK;
+  return GN_E_SHAPE;                                     // unreachable for the shapes make_plan() admits
 }
 
 static int launch_edge2node_pair(const float* P, const float* efeat, int B, int N, int T,

@@ -148,6 +148,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   __trap();
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(mbar)) : "memory");
+}
+// one arrival + `bytes` of pending transaction count (completed by the bulk copies that name this barrier)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (1-D, no tensor map): 16-byte aligned addresses and size, completion counted in
+// bytes on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(smem_u32(mbar)) : "memory");
+}
+
 // pack two floats into one bf16x2 word (lo = a, hi = b), round-to-nearest-even
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -213,6 +227,32 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, ui
   for (int k = 0; k < K; k += 16) {
     mma_bf16_ss(tmem_d, da, db, idesc, (k > 0 || accumulate_first) ? 1u : 0u);
     da += ia; db += ib;
+  }
+}
+
+// named barrier over the 256 staging / drain threads of the warp-specialised kernels (warps 0-7)
+__device__ __forceinline__ void drain_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Coalesced copy of a tile's incidence blocks (ns scenes x N x N fp32, scene stride hstride) into shared memory,
+// row stride ldr floats ((N rounded up to 4) + 4: a thread reading "its" row with 128-bit loads does not
+// bank-conflict).  Called by the 256 staging threads.
+__device__ __forceinline__ void stage_raw_H(float* raw, const float* __restrict__ H, long long hstride,
+                                            int b0s, int ns, int N, int ldr, int tid) {
+  const int per = N * N;
+  if ((N & 3) == 0 && (hstride & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
+    const int n4 = N >> 2, per4 = per >> 2;
+    for (int i = tid; i < ns * per4; i += 256) {
+      const int sc = i / per4, r4 = i - sc * per4;
+      const int e = r4 / n4, c4 = r4 - e * n4;
+      *reinterpret_cast<float4*>(raw + (sc * N + e) * ldr + 4 * c4) =
+          ldg_f4(H + static_cast<size_t>(b0s + sc) * hstride + 4 * r4);
+    }
+  } else {
+    for (int i = tid; i < ns * per; i += 256) {
+      const int sc = i / per, r = i - sc * per;
+      const int e = r / N, n = r - e * N;
+      raw[(sc * N + e) * ldr + n] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + r);
+    }
   }
 }
 
