@@ -169,3 +169,66 @@ def test_past_encoder_state_dict_matches_reference():
             mt, bias = m.folded_frontend(11, 5, torch.device("cpu"))
             mine = (inp.view(33, 20) @ mt + bias.repeat(3, 1)).view(3, 11, 64)
             assert (mine - f).abs().max().item() <= 1e-6
+
+
+def _canon_ref(m):
+    """byte(n, k) = (k/8)*(N*16) + n*16 + (k%8)*2 of the canonical operand, as a flat bf16 tensor (include/groupnet_b200.h)."""
+    n, k = m.shape
+    out = torch.empty(n * k, dtype=torch.bfloat16)
+    mb = m.to(torch.bfloat16)
+    for kk in range(k):
+        for nn_ in range(n):
+            out[(kk // 8) * (n * 8) + nn_ * 8 + (kk % 8)] = mb[nn_, kk]
+    return out
+
+
+def test_fused_kernel_weight_streams_follow_the_header_layout():
+    """tc_hfuse_w / tc_npre_w are linear streams of canonical operands in MMA consumption order
+    (include/groupnet_b200.h); spot-check sizes and a few chunks against a literal restatement of the layout."""
+    torch.manual_seed(3)
+    # h_dim 64 hyper layer: [W0_s | b0] (128 x 80), [W1_{s-1} | b1] (64 x 144) ..., closing [W0 | b0] (128 x 144), W1, b1 block
+    l64 = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=3)
+    t = packing.pack_stage(l64, 0, torch.device("cpu"))
+    T = 10
+    assert t["tc_hfuse_w"].dtype == torch.bfloat16 and "tc_npre_w" not in t
+    assert t["tc_hfuse_w"].numel() * 2 == T * (128 * 80 * 2 + 64 * 144 * 2) + 128 * 144 * 2 + 64 * 128 * 2 + 64 * 16 * 2
+    agg = l64.edge_aggregation_list[0].agg_mlp
+    blk = torch.zeros(128, 80)
+    blk[:, :64] = agg[0].layers[0].weight.detach()
+    b = agg[0].layers[0].bias.detach()
+    hi = b.to(torch.bfloat16).float()
+    blk[:, 64], blk[:, 65] = hi, (b - hi).to(torch.bfloat16).float()
+    assert torch.equal(t["tc_hfuse_w"][:128 * 80], _canon_ref(blk))
+    # second chunk of the stream is W0 of step 1, third is [W1_0 | b1_0]
+    off = 2 * 128 * 80
+    blk1 = torch.zeros(64, 144)
+    blk1[:, :128] = agg[0].layers[1].weight.detach()
+    b1 = agg[0].layers[1].bias.detach()
+    hi1 = b1.to(torch.bfloat16).float()
+    blk1[:, 128], blk1[:, 129], blk1[:, 130] = hi1, (b1 - hi1).to(torch.bfloat16).float(), hi1
+    assert torch.equal(t["tc_hfuse_w"][off:off + 64 * 144], _canon_ref(blk1))
+    # h_dim 256: sizes of both streams
+    l256 = gb.MS_HGNN_hyper(256, 256, 64, 256, batch_norm=0, nmp_layers=1, scale=4)
+    t = packing.pack_stage(l256, 0, torch.device("cpu"))
+    assert t["tc_hfuse_w"].numel() * 2 == T * (128 * 128 * 2 + 128 * 144 * 2 + 256 * 80 * 2 + 256 * 64 * 2) \
+        + 4 * 128 * 128 * 2 + 128 * 16 * 2 + 256 * 64 * 2 + 256 * 16 * 2 + 256 * 64 * 2
+    assert t["tc_npre_w"].numel() * 2 == 4 * 256 * 64 * 2 + 256 * 16 * 2 + 64 * 272 * 2 + 64 * 64 * 2
+    node = l256.node2edge_start_mlp[0].layers
+    assert torch.equal(t["tc_npre_w"][:256 * 64], _canon_ref(node[0].weight.detach()[:, :64]))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm, no GPU needed) prints one JSON line with the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("nba_synth")
