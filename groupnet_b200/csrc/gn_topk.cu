@@ -270,13 +270,23 @@ corr_topk_kernel(const float* __restrict__ x, const float* __restrict__ corr_in,
           Hs[static_cast<long long>(b0 + g) * st + n] = 1.0f;
         }
       } else {
+        // one warp per correlation row, lanes over the agents: consecutive rows are contiguous in H, so the
+        // stores stay coalesced and the loop has no integer divisions (they were 25 % of this kernel's samples)
         const int k = a.k[s];
-        const int per = N * N;
-        for (int i = tid; i < ns * per; i += GN_THREADS) {
-          int g = i / per, o = i - g * per;
-          int e = o / N, n = o - e * N;
-          float hv = rk[(g * N + e) * np4 + n] < k ? 1.0f : 0.0f;
-          Hs[static_cast<long long>(b0 + g) * st + o] = hv;
+        if (N >= 32) {
+          for (int r = warp; r < rows; r += NWARP) {
+            const int g = r / N, e = r - g * N;
+            const unsigned char* rr = rk + r * np4;
+            float* dst = Hs + static_cast<long long>(b0 + g) * st + static_cast<long long>(e) * N;
+            for (int n = lane; n < N; n += 32) dst[n] = rr[n] < k ? 1.0f : 0.0f;
+          }
+        } else {                                         // short rows: a flat index keeps every lane busy
+          const int per = N * N;
+          for (int i = tid; i < ns * per; i += GN_THREADS) {
+            int g = i / per, o = i - g * per;
+            int e = o / N, n = o - e * N;
+            Hs[static_cast<long long>(b0 + g) * st + o] = rk[(g * N + e) * np4 + n] < k ? 1.0f : 0.0f;
+          }
         }
       }
     }
