@@ -369,12 +369,13 @@ node2edge_hyper_quad_kernel(const float* __restrict__ xprime, const float* __res
       const int ee = e;
       const int sc = ee / E, nb = sc * N;
       const float* Hr = Hs + ee * N;
-      // membership mask: lane q tests agents [16q, 16q+16)
+      // membership mask: lane q tests agents q, q+4, ... (ceil(N/4) branch-free steps; the [16q, 16q+16) split
+      // this replaces spent 24 % of the kernel's samples in 16 predicated iterations, 3 lanes of 4 idle at N = 11)
       unsigned lo = 0u, hi = 0u;
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = q * 16 + i;
-        if (live && n < N && Hr[n] != 0.f) { if (n < 32) lo |= 1u << n; else hi |= 1u << (n - 32); }
+      for (int n = q; n < N; n += 4) {
+        const unsigned bit = (live && Hr[n] != 0.f) ? 1u : 0u;
+        lo |= n < 32 ? bit << (n & 31) : 0u;
+        hi |= n < 32 ? 0u : bit << (n & 31);
       }
       lo |= __shfl_xor_sync(qmask, lo, 1); hi |= __shfl_xor_sync(qmask, hi, 1);
       lo |= __shfl_xor_sync(qmask, lo, 2); hi |= __shfl_xor_sync(qmask, hi, 2);
