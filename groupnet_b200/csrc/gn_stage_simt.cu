@@ -948,9 +948,9 @@ static int launch_node2edge_hyper(const float* xprime, const float* pq, const fl
       size_t nodes = static_cast<size_t>(sc) * N, ed = static_cast<size_t>(sc) * E;
       return (2 * nodes * N2E_LD + ((ed * N + 3) & ~size_t(3)) + (eo ? nodes * (D + 4) : 0)) * 4;
     };
-    int SC = 64 / E;
+    int SC = 128 / E;                                             // two 64-edge passes per tile: half the barriers per edge
     if (SC < 1) SC = 1;
-    while (SC > 1 && qbytes(SC) > 56 * 1024) --SC;
+    while (SC > 1 && qbytes(SC) > 72 * 1024) --SC;
     const size_t smem = qbytes(SC);
     const int ntiles = (B + SC - 1) / SC;
     auto go = [&](auto kern) -> int {
