@@ -239,19 +239,31 @@ __device__ __forceinline__ void drain_bar() { asm volatile("bar.sync 1, 256;" ::
 __device__ __forceinline__ void stage_raw_H(float* raw, const float* __restrict__ H, long long hstride,
                                             int b0s, int ns, int N, int ldr, int tid) {
   const int per = N * N;
+  // (scene, row, column) of the flat index advance incrementally: no integer division in the loops
   if ((N & 3) == 0 && (hstride & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
-    const int n4 = N >> 2, per4 = per >> 2;
-    for (int i = tid; i < ns * per4; i += 256) {
-      const int sc = i / per4, r4 = i - sc * per4;
-      const int e = r4 / n4, c4 = r4 - e * n4;
+    const int n4 = N >> 2, per4 = per >> 2, total = ns * per4;
+    int sc = tid / per4, r4 = tid - sc * per4;
+    int e = r4 / n4, c4 = r4 - e * n4;
+    const int de = 256 / n4, dc = 256 - de * n4;         // 256 float4s further: de rows and dc columns
+#pragma unroll 4
+    for (int i = tid; i < total; i += 256) {
       *reinterpret_cast<float4*>(raw + (sc * N + e) * ldr + 4 * c4) =
-          ldg_f4(H + static_cast<size_t>(b0s + sc) * hstride + 4 * r4);
+          ldg_f4(H + static_cast<size_t>(b0s + sc) * hstride + 4 * (e * n4 + c4));
+      c4 += dc; e += de;
+      if (c4 >= n4) { c4 -= n4; ++e; }
+      while (e >= N) { e -= N; ++sc; }
     }
   } else {
-    for (int i = tid; i < ns * per; i += 256) {
-      const int sc = i / per, r = i - sc * per;
-      const int e = r / N, n = r - e * N;
-      raw[(sc * N + e) * ldr + n] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + r);
+    const int total = ns * per;
+    int sc = tid / per, r = tid - sc * per;
+    int e = r / N, n = r - e * N;
+    const int de = 256 / N, dn = 256 - de * N;
+#pragma unroll 4
+    for (int i = tid; i < total; i += 256) {
+      raw[(sc * N + e) * ldr + n] = __ldg(H + static_cast<size_t>(b0s + sc) * hstride + e * N + n);
+      n += dn; e += de;
+      if (n >= N) { n -= N; ++e; }
+      while (e >= N) { e -= N; ++sc; }
     }
   }
 }
