@@ -45,9 +45,12 @@ static_assert(OFF_PB + 64 * 16 * 2 <= OFF_BAR, "hyper_fused64: scratch layout");
 constexpr uint32_t TM_S = 0, TM_HID = 64;
 }  // namespace hf64
 
+extern unsigned long long* g_trace_buffer;
+
 struct HyperFused64Args {
   const float* h; const float* H; const float* edge_feat; const unsigned char* wstream;
   float* node_out; long long ld_out; int Dout; int B, N, T; long long hstride;
+  unsigned long long* trace;          // optional phase timeline (build with -DGN_ENABLE_TRACE)
 };
 
 namespace {
@@ -178,8 +181,16 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
     const int ldr = ((N + 3) & ~3) + 4;
     const float inv_n = 1.f / static_cast<float>(N);
     float* raw = reinterpret_cast<float*>(smem + OFF_A2);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int titer = 0;
+#ifdef GN_ENABLE_TRACE
+#define HF64_TRACE(pt) do { if (a.trace != nullptr && blockIdx.x == 0 && tid == 0 && titer < 8) \
+    a.trace[titer * 16 + (pt)] = clock64(); } while (0)
+#else
+#define HF64_TRACE(pt) do { } while (0)
+#endif
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++titer) {
       const int b0s = tile * SC;
+      HF64_TRACE(0);
       const int ns = min(SC, a.B - b0s);
       const int rows_used = ns * N;
       const bool rowvalid = row < rows_used;
@@ -192,16 +203,21 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
 #pragma unroll 4
         for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
           float v[8];
+          if (!valid || kg * 8 + 7 < sc_r * N || kg * 8 >= sc_r * N + N) {   // k-group outside this row's scene block
+            *reinterpret_cast<uint4*>(smem + OFF_SCR + kg * 2048 + r128 * 16) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int n = kg * 8 + i - sc_r * N;
-            v[i] = (valid && n >= 0 && n < N) ? Hrow[n] : 0.f;
+            v[i] = (n >= 0 && n < N) ? Hrow[n] : 0.f;
           }
           *reinterpret_cast<uint4*>(smem + OFF_SCR + kg * 2048 + r128 * 16) =
               make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
                          tc::pack_bf16(v[6], v[7]));
         }
       }
+      HF64_TRACE(1);
       // ---- hT[column c][node k] (B operand, 64 rows): thread = (column, 4 k-groups)
       {
         const int c = tid & 63, kq = tid >> 6;
@@ -222,10 +238,12 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
       }
       tc::fence_proxy_async_smem();
       arrive(bars + B_STAGE);
+      HF64_TRACE(2);
       const float* efrow = a.edge_feat + (static_cast<size_t>(b0s) * N + row) * T;
       float wnext = rowvalid ? __ldg(efrow) : 0.f;
       // ---- eo: TMEM -> bf16 A operand, this group's 32 columns
       wait(B_EOFULL);
+      HF64_TRACE(3);
       tc::fence_after_thread_sync();
       {
         float v[32];
@@ -239,6 +257,7 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
       tc::fence_proxy_async_smem();
       tc::fence_before_thread_sync();
       arrive(bars + B_EOREADY);
+      HF64_TRACE(4);
       // ---- main loop: hidden columns [64g, 64g+64) of step t -> A2
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
@@ -299,7 +318,9 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
         arrive(bars + B_A2FULL);
       }
       // ---- scatter operands: HblkT (A, scratch) from a raw incidence copy (A2 region), efT (B)
+      HF64_TRACE(5);
       wait(B_EFFULL);
+      HF64_TRACE(6);
       tc::fence_after_thread_sync();
       stage_raw_H(raw, a.H, a.hstride, b0s, ns, N, ldr, tid);
       drain_bar();
@@ -309,10 +330,14 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
 #pragma unroll 2
         for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
           float v[8];
+          if (!valid || kg * 8 + 7 < sc_r * N || kg * 8 >= sc_r * N + N) {   // k-group outside this row's scene block
+            *reinterpret_cast<uint4*>(smem + OFF_SCR + kg * 2048 + r128 * 16) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int e = kg * 8 + i - sc_r * N;
-            v[i] = (valid && e >= 0 && e < N) ? Hcol[e * ldr] : 0.f;
+            v[i] = (e >= 0 && e < N) ? Hcol[e * ldr] : 0.f;
           }
           *reinterpret_cast<uint4*>(smem + OFF_SCR + kg * 2048 + r128 * 16) =
               make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
@@ -335,6 +360,7 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
       tc::fence_proxy_async_smem();
       tc::fence_before_thread_sync();
       arrive(bars + B_EFTREADY);
+      HF64_TRACE(7);
       // ---- closing MLP input [agg | h] / N (+ ones) -> A2 region (the raw incidence copy there is dead)
       drain_bar();
       {
@@ -357,7 +383,9 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
           *reinterpret_cast<uint4*>(smem + OFF_A2 + 17 * 2048 + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
+      HF64_TRACE(8);
       wait(B_AGGFULL);
+      HF64_TRACE(9);
       tc::fence_after_thread_sync();
       {
         float v[32];
@@ -373,8 +401,10 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
       tc::fence_proxy_async_smem();
       tc::fence_before_thread_sync();
       arrive(bars + B_PAREADY);
+      HF64_TRACE(10);
       // ---- o1: ReLU -> bf16 A operand (over inc; the ones k-groups stay)
       wait(B_O1FULL);
+      HF64_TRACE(11);
       tc::fence_after_thread_sync();
       {
         uint32_t r0[32], r1[32];
@@ -398,8 +428,10 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
       tc::fence_proxy_async_smem();
       tc::fence_before_thread_sync();
       arrive(bars + B_O1READY);
+      HF64_TRACE(12);
       // ---- node_feat rows: 32-column chunk g, transposed through scratch for 128-byte row segments
       wait(B_OUTFULL);
+      HF64_TRACE(13);
       tc::fence_after_thread_sync();
       if (g * 32 < a.Dout) {
         float* tb = reinterpret_cast<float*>(smem + OFF_SCR) + warp * (32 * 36);
@@ -420,6 +452,7 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
         }
       }
       tc::fence_before_thread_sync();
+      HF64_TRACE(14);
     }
   }
   tc::fence_before_thread_sync();
@@ -444,6 +477,7 @@ int launch_hyper_fused64_tc(const float* h, const float* H, const float* edge_fe
   a.h = h; a.H = H; a.edge_feat = edge_feat;
   a.wstream = static_cast<const unsigned char*>(w->tc_hfuse_w);
   a.node_out = node_out; a.ld_out = ld_out; a.Dout = Dout; a.B = B; a.N = N; a.T = T; a.hstride = hstride;
+  a.trace = g_trace_buffer;
   const int SC = 128 / N;
   const int ntiles = (B + SC - 1) / SC;
   const int grid = ntiles < 2 * GN_SM_COUNT ? ntiles : 2 * GN_SM_COUNT;

@@ -272,14 +272,18 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
         for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
           float v[8];
           const int n0 = kg * 8 - sc_r * N;
-          if (valid && n0 >= 0 && n0 + 8 <= N && (N & 3) == 0) {
+          if (!valid || n0 + 7 < 0 || n0 >= N) {           // k-group outside this row's scene block
+            *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+          }
+          if (n0 >= 0 && n0 + 8 <= N && (N & 3) == 0) {
             const float4 x = *reinterpret_cast<const float4*>(Hrow + n0), y = *reinterpret_cast<const float4*>(Hrow + n0 + 4);
             v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int n = n0 + i;
-              v[i] = (valid && n >= 0 && n < N) ? Hrow[n] : 0.f;
+              v[i] = (n >= 0 && n < N) ? Hrow[n] : 0.f;
             }
           }
           *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) =
@@ -402,10 +406,14 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
 #pragma unroll 2
         for (int kg = half * 8; kg < half * 8 + 8; ++kg) {
           float v[8];
+          if (!valid || kg * 8 + 7 < sc_r * N || kg * 8 >= sc_r * N + N) {   // k-group outside this row's scene block
+            *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int e = kg * 8 + i - sc_r * N;
-            v[i] = (valid && e >= 0 && e < N) ? Hcol[e * ldr] : 0.f;
+            v[i] = (e >= 0 && e < N) ? Hcol[e * ldr] : 0.f;
           }
           *reinterpret_cast<uint4*>(smem + OFF_A2 + kg * 2048 + r128 * 16) =
               make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]), tc::pack_bf16(v[4], v[5]),
