@@ -311,11 +311,11 @@ def test_multiscale_interaction_matches_layers_and_host_pipeline():
     # host pipeline: chunking must not change anything (philox keyed by global scene index)
     m.set_rng("philox", seed=11)
     f_dev, h_dev = m(x.to(DEV))
-    for cs in (1000, 256, 77):
+    for cs, mode in ((1000, "auto"), (256, "host"), (77, "device"), (300, "device")):
         m.set_rng("philox", seed=11)
-        f_host, h_host = m.forward_host(x.pin_memory(), chunk_scenes=cs)
+        f_host, h_host = m.forward_host(x.pin_memory(), chunk_scenes=cs, input_slice=mode)
         torch.cuda.synchronize()
-        assert torch.equal(f_host, f_dev.cpu()) and torch.equal(h_host, h_dev.cpu()), cs
+        assert torch.equal(f_host, f_dev.cpu()) and torch.equal(h_host, h_dev.cpu()), (cs, mode)
     assert m.launches_per_forward(b, n) == 1 + 5 + 6 + 6
 
 
