@@ -505,7 +505,7 @@ def main():
         out_h = torch.empty(b, model.incidence_rows(n), n, dtype=torch.float32).pin_memory()
         # x slice of final_feature: filled on the host when this rank has cores to spare, else written by the GPU
         # and copied back with the rest (8 ranks x 2 threads: the host-side fill was the bottleneck)
-        slice_mode = "host" if torch.get_num_threads() >= 8 else "device"
+        slice_mode = os.environ.get("GN_E2E_INPUT_SLICE") or ("host" if torch.get_num_threads() >= 16 else "device")
         for _ in range(2):
             model.forward_host(x_host, out_f, out_h, input_slice=slice_mode)
         barrier()
