@@ -213,6 +213,32 @@ def test_fused_kernel_weight_streams_follow_the_header_layout():
     assert t["tc_hfuse_w"].numel() * 2 == T * (128 * 128 * 2 + 128 * 144 * 2 + 256 * 80 * 2 + 256 * 64 * 2) \
         + 4 * 128 * 128 * 2 + 128 * 16 * 2 + 256 * 64 * 2 + 256 * 16 * 2 + 256 * 64 * 2
     assert t["tc_npre_w"].numel() * 2 == 4 * 256 * 64 * 2 + 256 * 16 * 2 + 64 * 272 * 2 + 64 * 64 * 2
+    # h_dim 256 stream, chunk by chunk for step 0 / 1: W0_0[:, :128] | [W0_0[:, 128:] | b0] | W0_1 ... | [W1_0[:, :64] | b1] | W1_0[:, 64:]
+    agg = l256.edge_aggregation_list[0].agg_mlp
+
+    def hi_lo(v):
+        hi_ = v.to(torch.bfloat16).float()
+        return hi_, (v - hi_).to(torch.bfloat16).float()
+
+    st = t["tc_hfuse_w"]
+    w0 = agg[0].layers[0].weight.detach()
+    assert torch.equal(st[:128 * 128], _canon_ref(w0[:, :128]))
+    blk = torch.zeros(128, 144)
+    blk[:, :128] = w0[:, 128:]
+    blk[:, 128], blk[:, 129] = hi_lo(agg[0].layers[0].bias.detach())
+    assert torch.equal(st[128 * 128:128 * 128 + 128 * 144], _canon_ref(blk))
+    off = 2 * (128 * 128 + 128 * 144)                      # after the W0 chunks of steps 0 and 1
+    w1 = agg[0].layers[1].weight.detach()
+    blk = torch.zeros(256, 80)
+    blk[:, :64] = w1[:, :64]
+    hi, lo = hi_lo(agg[0].layers[1].bias.detach())
+    blk[:, 64], blk[:, 65], blk[:, 66] = hi, lo, hi
+    assert torch.equal(st[off:off + 256 * 80], _canon_ref(blk))
+    assert torch.equal(st[off + 256 * 80:off + 256 * 80 + 256 * 64], _canon_ref(w1[:, 64:]))
+    # closing MLP chunks start after the T aggregation steps
+    post = T * (128 * 128 + 128 * 144 + 256 * 80 + 256 * 64)
+    pw0 = l256.nmp_mlp_end.layers[0].weight.detach()
+    assert torch.equal(st[post:post + 128 * 128], _canon_ref(pw0[:, :128]))
     node = l256.node2edge_start_mlp[0].layers
     assert torch.equal(t["tc_npre_w"][:256 * 64], _canon_ref(node[0].weight.detach()[:, :64]))
 
