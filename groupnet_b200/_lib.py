@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgroupnet_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 GN_MAX_AGENTS = 64
 GN_MAX_SCALES = 8

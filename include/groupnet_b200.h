@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 1
+#define GN_ABI_VERSION 2     /* 2: gn_stage_weights gained tc_hfuse_w, tc_npre_w */
 
 #define GN_MAX_AGENTS 64      /* N <= 64: one 64-bit membership word per hyperedge */
 #define GN_MAX_SCALES 8
