@@ -86,7 +86,17 @@ def assert_close(got, ref, rel, what="", atol=0.0):
     assert got64.shape == ref64.shape, (got64.shape, ref64.shape)
     err = (got64 - ref64).abs().max().item() if ref64.numel() else 0.0
     bound = rel * (ref64.abs().max().item() if ref64.numel() else 0.0) + atol
-    assert err <= bound, f"{what}: max|d| = {err:.3e} > {bound:.3e} (rel {rel:.1e}, atol {atol:.1e})"
+    if err <= bound:
+        return
+    # failure report: where, how many, and the values there (enough to tell a rounding excursion
+    # from a wrong element without re-running)
+    diff = (got64 - ref64).abs()
+    over = (diff > bound).nonzero()
+    worst = [int(i) for i in torch.unravel_index(diff.argmax(), diff.shape)]
+    where = "; ".join(f"{tuple(int(j) for j in ix)}: got {got64[tuple(ix)].item():.9g} ref {ref64[tuple(ix)].item():.9g}"
+                      for ix in over[:6])
+    raise AssertionError(f"{what}: max|d| = {err:.3e} > {bound:.3e} (rel {rel:.1e}, atol {atol:.1e}); "
+                         f"worst at {worst}, {over.shape[0]} of {diff.numel()} elements over the bound: {where}")
 
 
 def have_reference() -> bool:
