@@ -1,0 +1,91 @@
+"""Graph-replayed `PastEncoder` forward for rollouts at a fixed small batch.
+
+The reference's simulator calls the model thousands of times at batch 1 (Simulator.py:231-238,332-334); at that
+size a forward is launch-bound (16 kernels; ~520 us of host time launched eagerly against ~170 us of device
+time on a B200).  `libgroupnet_b200.so` allocates nothing and launches only on the caller's stream, so one
+forward is captured once into a CUDA graph and replayed per call.
+
+RNG contract (model/MS_HGNN_batch.py:454): every call still draws one `torch.rand(B, E, T)` per
+`MLP_dict_softmax` from the global CPU generator, in module call order (pairwise, then the hyper scales) —
+the draws land in static device buffers the captured kernels read, so a replay sees fresh noise and the
+results are bit-identical to the eager `PastEncoder.forward` under the same `torch.manual_seed`.
+(Philox seeds are kernel arguments passed by value and would be frozen by the capture, so this helper always
+uses the reference's CPU stream.)
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+
+from . import ops
+from .encoder import PastEncoder
+
+
+class GraphedPastEncoder:
+    """encoder: a `groupnet_b200.PastEncoder` on a CUDA device, in eval mode.
+
+        g = GraphedPastEncoder(encoder, batch_size=1, agent_num=11, length=5)
+        feature, new_H = g(inputs)          # inputs (B*N, T, in_dim), host or device
+
+    The returned tensors are the graph's static outputs: they are overwritten by the next call
+    (pass `clone=True` to get private copies).  Weights are read in place: after an optimizer step or
+    `load_state_dict` call `recapture()`."""
+
+    def __init__(self, encoder: PastEncoder, batch_size: int, agent_num: int, length: int, in_dim: int = 4):
+        dev = next(encoder.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedPastEncoder needs the encoder on a CUDA device")
+        if encoder.training:
+            raise RuntimeError("GraphedPastEncoder is eval-only (PastEncoder's fused front-end is)")
+        self.encoder, self.device = encoder, dev
+        self.batch_size, self.agent_num = int(batch_size), int(agent_num)
+        b, n = self.batch_size, self.agent_num
+        self._x = torch.zeros(b * n, length, in_dim, dtype=torch.float32, device=dev)
+        self._shapes: List[List[Tuple[int, int, int]]] = []
+        for i, layer in enumerate(encoder.layers()):
+            e = n * n if i == 0 else ops.incidence_rows(n, layer.scale)
+            self._shapes.append([(b, e, layer.edge_types)] * max(layer.nmp_layers, 1))
+        self._u_dev = [[torch.zeros(s, dtype=torch.float32, device=dev) for s in per] for per in self._shapes]
+        self._u_host = [[torch.zeros(s, dtype=torch.float32).pin_memory() for s in per] for per in self._shapes]
+        self._copied = torch.cuda.Event()
+        self._graph = None
+        self.recapture()
+
+    def _forward(self):
+        return self.encoder(self._x, self.batch_size, self.agent_num, noise=self._u_dev)
+
+    @torch.no_grad()
+    def recapture(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):               # warm-up outside the capture: packs weights, sizes the workspaces
+            self._forward()
+        cur.wait_stream(side)
+        # the captured kernels hold raw pointers: keep what they point at alive even if the layers later swap in
+        # a larger workspace (bigger eager batch) or re-packed weights (optimizer step)
+        self._keepalive = [(l._ws.buf, l._packs._stages) for l in self.encoder.layers()]
+        self._keepalive.append(self.encoder.folded_frontend(self.agent_num, self._x.shape[1], self.device))
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._feature, self._new_h = self._forward()
+        self._copied.record(cur)
+
+    @torch.no_grad()
+    def __call__(self, inputs: torch.Tensor, clone: bool = False):
+        if tuple(inputs.shape) != tuple(self._x.shape):
+            raise RuntimeError(f"inputs must be {tuple(self._x.shape)}, got {tuple(inputs.shape)}")
+        if inputs.dtype != torch.float32:
+            raise RuntimeError("expected scalar type Float")
+        self._copied.synchronize()                  # the previous call's H2D copies have left the pinned buffers
+        for per_h, per_d in zip(self._u_host, self._u_dev):
+            for uh, ud in zip(per_h, per_d):
+                torch.rand(uh.shape, out=uh)        # global CPU generator, module call order (:454)
+                ud.copy_(uh, non_blocking=True)
+        self._x.copy_(inputs, non_blocking=True)
+        self._copied.record(torch.cuda.current_stream(self.device))
+        self._graph.replay()
+        if clone:
+            return self._feature.clone(), self._new_h.clone()
+        return self._feature, self._new_h

@@ -258,3 +258,11 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"].startswith("nba_synth")
+
+
+def test_graphed_past_encoder_refuses_a_cpu_encoder():
+    import types
+    import groupnet_b200 as gb
+    enc = gb.PastEncoder(types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], past_length=5)).eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        gb.GraphedPastEncoder(enc, 1, 11, 5)

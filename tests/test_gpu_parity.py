@@ -517,3 +517,35 @@ def test_past_encoder_errors_like_reference():
         enc(torch.randn(2 * 8, 5, 4, device=DEV), 2, 8)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         enc(torch.randn(2 * 11, 5, 4), 2, 11)
+
+
+# ---- graph-replayed rollout forward ---------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_graphed_past_encoder_matches_eager_and_consumes_the_same_rng_stream(precision):
+    import types
+    args = types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], past_length=5)
+    torch.manual_seed(31)
+    enc = gb.PastEncoder(args).to(DEV).eval()
+    enc._interaction_block().set_precision(precision)
+    for b in (1, 3):
+        x = torch.randn(b * 11, 5, 4)
+        g = gb.GraphedPastEncoder(enc, b, 11, 5)
+        for trial in range(3):
+            xt = x + trial
+            torch.manual_seed(100 + trial)
+            f0, h0 = enc(xt.to(DEV), b, 11)
+            after0 = torch.rand(1)
+            torch.manual_seed(100 + trial)
+            f1, h1 = g(xt)
+            after1 = torch.rand(1)
+            assert torch.equal(f0, f1) and torch.equal(h0, h1)      # fresh noise per replay, same kernels
+            assert torch.equal(after0, after1)                       # the same draws left the CPU generator
+        big = torch.randn(64 * 11, 5, 4, device=DEV)                 # eager call that grows the layers' workspaces
+        enc(big, 64, 11)
+        torch.manual_seed(7)
+        f0, _ = enc(x.to(DEV), b, 11)
+        torch.manual_seed(7)
+        f1, _ = g(x, clone=True)
+        assert torch.equal(f0, f1)
+    with pytest.raises(RuntimeError):
+        g(torch.zeros(5, 5, 4))
