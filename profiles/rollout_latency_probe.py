@@ -72,6 +72,34 @@ def main():
                 except Exception as exc:      # report, do not hide
                     line += f" | graph capture failed: {type(exc).__name__}: {str(exc)[:200]}"
             print(line, flush=True)
+    # the packaged helper, with the reference's RNG contract (fresh torch.rand per call), one dependent call
+    # after another as a rollout issues them: wall time per call including the final synchronize
+    for precision in ("fp32", "bf16"):
+        block.set_precision(precision)
+        block.set_rng("cpu-compat")
+        for b in (1, 8):
+            x = torch.randn(b * N, T, 4, device=DEV)
+            g = gb.GraphedPastEncoder(enc, b, N, T)
+            with torch.no_grad():
+                def eager_step():
+                    f, _ = enc(x, b, N)
+                    torch.cuda.synchronize()
+
+                def graph_step():
+                    f, _ = g(x)
+                    torch.cuda.synchronize()
+                for fn in (eager_step, graph_step):
+                    for _ in range(20):
+                        fn()
+                t0 = time.perf_counter()
+                for _ in range(300):
+                    eager_step()
+                t1 = time.perf_counter()
+                for _ in range(300):
+                    graph_step()
+                t2 = time.perf_counter()
+            print(f"{precision} B={b} cpu-compat noise, synchronised per call: eager {(t1 - t0) / 300 * 1e6:7.1f} us, "
+                  f"GraphedPastEncoder {(t2 - t1) / 300 * 1e6:7.1f} us", flush=True)
 
 
 if __name__ == "__main__":
