@@ -19,6 +19,7 @@ GN_FP32 = 0
 GN_BF16_TC = 1
 GN_NOISE_GIVEN = 0
 GN_NOISE_PHILOX = 1
+GN_NOISE_PHILOX_DEVICE_SEED = 2
 
 # every symbol include/groupnet_b200.h declares
 EXPORTS = (

@@ -350,12 +350,15 @@ edge_chain_tc_kernel(TcChainArgs a) {
               (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(grow)) * T;
           const unsigned long long blk0 = el0 >> 2;
           const int lead = static_cast<int>(el0 & 3);
+          // device-resident seed (graph replay): read where it is used, so the other modes keep their registers
+          const unsigned long long seed = (a.noise_mode == GN_NOISE_PHILOX_DEVICE_SEED)
+                                              ? __ldg(reinterpret_cast<const unsigned long long*>(a.U)) : a.seed;
 #pragma unroll
           for (int t = 0; t < TU; ++t) u[t] = 0.5f;
 #pragma unroll
           for (int bi = 0; bi < (TU + 3 + 3) / 4; ++bi) {
             if (bi * 4 < lead + T) {
-              const uint4 r = Philox::block(blk0 + bi, static_cast<uint32_t>(a.stage_index), a.seed);
+              const uint4 r = Philox::block(blk0 + bi, static_cast<uint32_t>(a.stage_index), seed);
               const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
               for (int s = 0; s < 4; ++s) {

@@ -482,6 +482,7 @@ edge_mlp_kernel(const float* __restrict__ edges, long long R, int T, int E,
   float* part = w1s + 256 * GN_SMALL_OUT;
   float* io = part + TM * 17;
   const int tid = threadIdx.x;
+  if (noise_mode == GN_NOISE_PHILOX_DEVICE_SEED) seed = __ldg(reinterpret_cast<const unsigned long long*>(U));
   for (int i = tid; i < 256 * GN_SMALL_OUT; i += GN_THREADS) w1s[i] = __ldg(W.df_w1 + i);
   const long long ntiles = (R + TM - 1) / TM;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1059,7 +1060,9 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   if (hstride < static_cast<long long>(E) * N) return GN_E_SHAPE;
   const int ld_out = c->out_ld > 0 ? c->out_ld : c->Dout;
   if (ld_out < c->Dout) return GN_E_SHAPE;
-  if (c->noise_mode == GN_NOISE_GIVEN && !U) return GN_E_NULL;
+  if (c->noise_mode < GN_NOISE_GIVEN || c->noise_mode > GN_NOISE_PHILOX_DEVICE_SEED) return GN_E_SHAPE;
+  if (c->noise_mode != GN_NOISE_PHILOX && !U) return GN_E_NULL;
+  if (c->noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && (reinterpret_cast<uintptr_t>(U) & 7)) return GN_E_SHAPE;
   if (!c->pairwise && !H) return GN_E_NULL;
   const bool tcn = p.tc_nodes;
   const bool fused_agg = tcn && c->pairwise && pair_agg_fits(N, D, T);   // P / G stay on chip

@@ -14,7 +14,9 @@ Differences a caller can observe (all documented in DESIGN.md):
     whatever torch.topk does);
   * Gumbel noise: `rng="cpu-compat"` (default) draws `torch.rand(B,E,T)` from
     the global CPU generator in the reference's order, `rng="philox"` draws on
-    the device, `forward(..., noise=[U])` injects the uniforms.
+    the device, `rng="philox-device"` is the same stream with the per-call seed
+    kept (and advanced) in device memory so a captured CUDA graph can be
+    replayed, `forward(..., noise=[U])` injects the uniforms.
 """
 from __future__ import annotations
 
@@ -27,6 +29,12 @@ from . import _lib, ops
 from .packing import PackCache
 
 _MASK64 = (1 << 64) - 1
+_PHILOX_CALL_STRIDE = 0x9E3779B97F4A7C15        # seed of call k = philox_seed + k * stride (mod 2^64)
+
+
+def _as_int64(v: int) -> int:
+    v &= _MASK64
+    return v - (1 << 64) if v >= (1 << 63) else v
 
 
 # --------------------------------------------------------------------------
@@ -132,10 +140,22 @@ class _MessagePassingLayer(nn.Module):
     def set_rng(self, mode: str, seed: int = 0, scene_offset: int = 0):
         """mode in {"cpu-compat", "philox"}; `scene_offset` is the global index of
         this shard's first scene (results are then independent of the sharding)."""
-        if mode not in ("cpu-compat", "philox"):
+        if mode not in ("cpu-compat", "philox", "philox-device"):
             raise ValueError(mode)
         self.rng, self.philox_seed, self.scene_offset, self._philox_calls = mode, int(seed), int(scene_offset), 0
+        seed_dev = self.__dict__.get("_seed_dev")
+        if seed_dev is not None:
+            seed_dev.fill_(_as_int64(self.philox_seed))      # in place: a captured graph keeps reading this buffer
         return self
+
+    def _device_seed(self, device) -> torch.Tensor:
+        """One int64 in device memory holding the Philox seed of the NEXT forward (rng="philox-device")."""
+        t = self.__dict__.get("_seed_dev")
+        if t is None or t.device != device:
+            t = torch.full((1,), _as_int64(self.philox_seed + _PHILOX_CALL_STRIDE * self._philox_calls),
+                           dtype=torch.int64, device=device)
+            self.__dict__["_seed_dev"] = t
+        return t
 
     def set_precision(self, precision: str):
         if precision not in ("fp32", "bf16"):
@@ -181,8 +201,11 @@ class _MessagePassingLayer(nn.Module):
         n_stage = len(stages)
         t = self.edge_types
         us = self._noise_list(noise, b, e, n_stage, dev)
+        seed_dev = None
         if us is None:
-            seed = (self.philox_seed + 0x9E3779B97F4A7C15 * self._philox_calls) & _MASK64
+            seed = (self.philox_seed + _PHILOX_CALL_STRIDE * self._philox_calls) & _MASK64
+            if self.rng == "philox-device":
+                seed_dev = self._device_seed(dev)
             self._philox_calls += 1
         else:
             seed = 0
@@ -199,13 +222,16 @@ class _MessagePassingLayer(nn.Module):
             dist_out = torch.empty(b, e, t, dtype=torch.float32, device=dev)
         mids = [torch.empty(b, n, stages[s].dout, dtype=torch.float32, device=dev) for s in range(n_stage - 1)]
         if b == 0:
+            if seed_dev is not None:
+                seed_dev.add_(_as_int64(_PHILOX_CALL_STRIDE))
             return node_out, dist_out
 
         cfg = _lib.StageCfg()
         cfg.N, cfg.D, cfg.E, cfg.T = n, d, e, t
         cfg.pairwise = 1 if self._pairwise else 0
         cfg.precision = _lib.GN_BF16_TC if self.precision == "bf16" else _lib.GN_FP32
-        cfg.noise_mode = _lib.GN_NOISE_GIVEN if us is not None else _lib.GN_NOISE_PHILOX
+        cfg.noise_mode = (_lib.GN_NOISE_GIVEN if us is not None else
+                          _lib.GN_NOISE_PHILOX_DEVICE_SEED if seed_dev is not None else _lib.GN_NOISE_PHILOX)
         cfg.seed = seed
         # bound the scratch: split the batch so one call's workspace stays under the limit
         cfg.B, cfg.Dout, cfg.stage_index, cfg.scene_offset = 1, max(s.dout for s in stages), 0, 0
@@ -224,9 +250,11 @@ class _MessagePassingLayer(nn.Module):
                 dst = node_out[b0:b1] if last else mids[s][b0:b1]
                 ops.stage_forward(cfg, stages[s], cur,
                                   None if inc is None else inc[b0:b1],
-                                  None if us is None else us[s][b0:b1],
+                                  seed_dev if seed_dev is not None else None if us is None else us[s][b0:b1],
                                   dst, dist_out[b0:b1] if (s == 0 and dist_out is not None) else None, ws)
                 cur = dst
+        if seed_dev is not None:
+            seed_dev.add_(_as_int64(_PHILOX_CALL_STRIDE))      # stream-ordered (and captured): next call's seed
         return node_out, dist_out
 
     def _run_train(self, h_states, inc, e, noise, node_out, want_dist):
@@ -242,7 +270,9 @@ class _MessagePassingLayer(nn.Module):
         t = self.edge_types
         us = self._noise_list(noise, b, e, n_stage, dev)
         if us is None:
-            seed = (self.philox_seed + 0x9E3779B97F4A7C15 * self._philox_calls) & _MASK64
+            if self.rng == "philox-device":
+                raise RuntimeError('rng="philox-device" is an inference mode (graph replay); train with "philox"')
+            seed = (self.philox_seed + _PHILOX_CALL_STRIDE * self._philox_calls) & _MASK64
             self._philox_calls += 1
         else:
             seed = 0

@@ -9,8 +9,10 @@ RNG contract (model/MS_HGNN_batch.py:454): every call still draws one `torch.ran
 `MLP_dict_softmax` from the global CPU generator, in module call order (pairwise, then the hyper scales) —
 the draws land in static device buffers the captured kernels read, so a replay sees fresh noise and the
 results are bit-identical to the eager `PastEncoder.forward` under the same `torch.manual_seed`.
-(Philox seeds are kernel arguments passed by value and would be frozen by the capture, so this helper always
-uses the reference's CPU stream.)
+`rng="philox"` instead keeps the whole step on the device: the layers run in their "philox-device" mode, where
+the per-call seed lives in device memory (GN_NOISE_PHILOX_DEVICE_SEED) and the captured graph itself advances
+it, so replay k is bit-identical to the k-th eager forward under `set_rng("philox", seed)` with no host work
+per call beyond the input copy and the graph launch.
 """
 from __future__ import annotations
 
@@ -32,7 +34,11 @@ class GraphedPastEncoder:
     (pass `clone=True` to get private copies).  Weights are read in place: after an optimizer step or
     `load_state_dict` call `recapture()`."""
 
-    def __init__(self, encoder: PastEncoder, batch_size: int, agent_num: int, length: int, in_dim: int = 4):
+    def __init__(self, encoder: PastEncoder, batch_size: int, agent_num: int, length: int, in_dim: int = 4,
+                 rng: str = "cpu-compat", seed: int = 0):
+        if rng not in ("cpu-compat", "philox"):
+            raise ValueError(rng)
+        self.rng, self.seed = rng, int(seed)
         dev = next(encoder.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedPastEncoder needs the encoder on a CUDA device")
@@ -53,10 +59,14 @@ class GraphedPastEncoder:
         self.recapture()
 
     def _forward(self):
-        return self.encoder(self._x, self.batch_size, self.agent_num, noise=self._u_dev)
+        return self.encoder(self._x, self.batch_size, self.agent_num,
+                            noise=self._u_dev if self.rng == "cpu-compat" else None)
 
     @torch.no_grad()
     def recapture(self) -> None:
+        block = self.encoder._interaction_block()
+        if self.rng == "philox":
+            block.set_rng("philox-device", self.seed)     # NOTE: changes the rng mode of the encoder's layers
         cur = torch.cuda.current_stream(self.device)
         side = torch.cuda.Stream(self.device)
         side.wait_stream(cur)
@@ -70,6 +80,9 @@ class GraphedPastEncoder:
         self._graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph):
             self._feature, self._new_h = self._forward()
+        if self.rng == "philox":
+            block.set_rng("philox-device", self.seed)     # rewind the device seeds (in place): replay 0 == eager call 0
+            self._keepalive.append([l._seed_dev for l in self.encoder.layers()])
         self._copied.record(cur)
 
     @torch.no_grad()
@@ -78,13 +91,15 @@ class GraphedPastEncoder:
             raise RuntimeError(f"inputs must be {tuple(self._x.shape)}, got {tuple(inputs.shape)}")
         if inputs.dtype != torch.float32:
             raise RuntimeError("expected scalar type Float")
-        self._copied.synchronize()                  # the previous call's H2D copies have left the pinned buffers
-        for per_h, per_d in zip(self._u_host, self._u_dev):
-            for uh, ud in zip(per_h, per_d):
-                torch.rand(uh.shape, out=uh)        # global CPU generator, module call order (:454)
-                ud.copy_(uh, non_blocking=True)
+        if self.rng == "cpu-compat":
+            self._copied.synchronize()              # the previous call's H2D copies have left the pinned buffers
+            for per_h, per_d in zip(self._u_host, self._u_dev):
+                for uh, ud in zip(per_h, per_d):
+                    torch.rand(uh.shape, out=uh)    # global CPU generator, module call order (:454)
+                    ud.copy_(uh, non_blocking=True)
         self._x.copy_(inputs, non_blocking=True)
-        self._copied.record(torch.cuda.current_stream(self.device))
+        if self.rng == "cpu-compat":
+            self._copied.record(torch.cuda.current_stream(self.device))
         self._graph.replay()
         if clone:
             return self._feature.clone(), self._new_h.clone()

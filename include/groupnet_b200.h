@@ -55,7 +55,10 @@ enum gn_precision {
 
 enum gn_noise_mode {
   GN_NOISE_GIVEN = 0,    /* U (B,E,T) uniform[0,1) supplied by the caller (reference RNG order) */
-  GN_NOISE_PHILOX = 1    /* Philox4x32-10 on device, keyed by (seed, stage, global element index) */
+  GN_NOISE_PHILOX = 1,   /* Philox4x32-10 on device, keyed by (seed, stage, global element index) */
+  GN_NOISE_PHILOX_DEVICE_SEED = 2  /* same generator; the seed is not cfg->seed but ONE uint64 in device memory that
+                                      U points at, read when the kernel runs: a captured CUDA graph can then be
+                                      replayed with a seed the device itself advances between replays */
 };
 
 typedef void* gn_stream_t;
@@ -177,7 +180,8 @@ size_t gn_stage_workspace_bytes(const gn_stage_cfg* cfg);
 /* One message-passing stage forward.
  *   h_in      (B,N,D)    node features entering the stage
  *   H         (B,E,N)    incidence (0/1 fp32) for hyper stages; ignored (may be NULL) when cfg->pairwise
- *   U         (B,E,T)    uniform draws when noise_mode == GN_NOISE_GIVEN, else may be NULL
+ *   U         (B,E,T)    uniform draws when noise_mode == GN_NOISE_GIVEN; one device uint64 (the Philox seed,
+ *                        8-byte aligned) when GN_NOISE_PHILOX_DEVICE_SEED; may be NULL for GN_NOISE_PHILOX
  *   node_out  (B,N,Dout) output of the closing MLP (node_feat); rows cfg->out_ld floats apart when out_ld != 0
  *   dist_out  (B,E,T)    optional: the categorical `distribution` the reference returns as
  *                        `factors` (:53,:178,:427); may be NULL for stages > 0

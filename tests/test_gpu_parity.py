@@ -549,3 +549,45 @@ def test_graphed_past_encoder_matches_eager_and_consumes_the_same_rng_stream(pre
         assert torch.equal(f0, f1)
     with pytest.raises(RuntimeError):
         g(torch.zeros(5, 5, 4))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_philox_device_seed_mode_equals_philox_and_replays_from_a_graph(precision):
+    import types
+    # layer level, eager: the device-resident seed walks the same sequence as the by-value seed (chunked batch too)
+    for kind, scale in (("pairwise", 0), ("hyper", 5), ("hyper", 11)):
+        torch.manual_seed(3)
+        if kind == "pairwise":
+            m = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=2)
+        else:
+            m = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=2, scale=scale)
+        m = m.to(DEV).set_precision(precision)
+        m.workspace_limit_bytes = 8 << 20
+        h = torch.randn(150, 11, 64, device=DEV)
+        q = torch.nn.functional.normalize(h, dim=2)
+        args = (h,) if kind == "pairwise" else (h, torch.bmm(q, q.transpose(1, 2)))
+        with torch.no_grad():
+            m.set_rng("philox", seed=(1 << 63) + 12345)
+            ref = [tuple(t.clone() for t in m(*args)[:2]) for _ in range(3)]
+            m.set_rng("philox-device", seed=(1 << 63) + 12345)
+            got = [tuple(t.clone() for t in m(*args)[:2]) for _ in range(3)]
+        for r, g in zip(ref, got):
+            assert torch.equal(r[0], g[0]) and torch.equal(r[1], g[1])
+        assert not torch.equal(ref[0][1], ref[1][1])                 # the noise does change from call to call
+    # encoder level, graph replay k == eager philox call k
+    args = types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], past_length=5)
+    torch.manual_seed(31)
+    enc = gb.PastEncoder(args).to(DEV).eval()
+    block = enc._interaction_block()
+    block.set_precision(precision)
+    x = torch.randn(2 * 11, 5, 4, device=DEV)
+    block.set_rng("philox", seed=77)
+    ref = [tuple(t.clone() for t in enc(x, 2, 11)) for _ in range(3)]
+    g = gb.GraphedPastEncoder(enc, 2, 11, 5, rng="philox", seed=77)
+    for k in range(3):
+        f, hh = g(x, clone=True)
+        assert torch.equal(f, ref[k][0]) and torch.equal(hh, ref[k][1])
+    layer_args = (h, torch.bmm(q, q.transpose(1, 2)))
+    with torch.enable_grad(), pytest.raises(RuntimeError, match="philox-device"):
+        m.set_rng("philox-device", 1)
+        m(*layer_args)                                               # parameters require grad -> training path
