@@ -3,8 +3,8 @@ MS-HGNN layers) at rollout batch sizes, launched eagerly and replayed from a cap
 
 The reference's simulator calls the model thousands of times at batch 1 (Simulator.py:231-238), where the
 step is launch-bound; the library allocates nothing and launches only on the caller's stream, so one forward
-is capturable as it stands.  Philox seeds are passed by value, so a replay repeats the captured noise: a
-device-resident seed/offset is the ABI addition a graph-replayed rollout needs (noted in DESIGN.md §8).
+is capturable as it stands.  With the seed passed by value a replay repeats the captured noise (first table);
+`GraphedPastEncoder` keeps the noise fresh either from the CPU generator or from a device-resident Philox seed.
 
     python profiles/rollout_latency_probe.py
 """
@@ -100,6 +100,30 @@ def main():
                 t2 = time.perf_counter()
             print(f"{precision} B={b} cpu-compat noise, synchronised per call: eager {(t1 - t0) / 300 * 1e6:7.1f} us, "
                   f"GraphedPastEncoder {(t2 - t1) / 300 * 1e6:7.1f} us", flush=True)
+            # Philox on the device: eager (seed by value) vs graph replay (seed in device memory, advanced in-graph)
+            block.set_rng("philox", seed=3)
+            gp = gb.GraphedPastEncoder(enc, b, N, T, rng="philox", seed=3)
+            with torch.no_grad():
+                def graph_philox_step():
+                    f, _ = gp(x)
+                    torch.cuda.synchronize()
+                block.set_rng("philox", seed=3)
+                for _ in range(20):
+                    eager_step()
+                t0 = time.perf_counter()
+                for _ in range(300):
+                    eager_step()
+                t1 = time.perf_counter()
+                gp.recapture()
+                for _ in range(20):
+                    graph_philox_step()
+                t2 = time.perf_counter()
+                for _ in range(300):
+                    graph_philox_step()
+                t3 = time.perf_counter()
+            block.set_rng("cpu-compat")
+            print(f"{precision} B={b} philox noise,     synchronised per call: eager {(t1 - t0) / 300 * 1e6:7.1f} us, "
+                  f"GraphedPastEncoder {(t3 - t2) / 300 * 1e6:7.1f} us", flush=True)
 
 
 if __name__ == "__main__":
