@@ -266,3 +266,16 @@ def test_graphed_past_encoder_refuses_a_cpu_encoder():
     enc = gb.PastEncoder(types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], past_length=5)).eval()
     with pytest.raises(RuntimeError, match="CUDA"):
         gb.GraphedPastEncoder(enc, 1, 11, 5)
+
+
+def test_binding_constants_match_the_header_enums():
+    """groupnet_b200/_lib.py restates the header's enumerators and limits: keep them in step."""
+    hdr = open(os.path.join(ROOT, "include", "groupnet_b200.h")).read()
+    enums = {k: int(v) for k, v in re.findall(r"\b(GN_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    defines = {k: int(v) for k, v in re.findall(r"#define\s+(GN_[A-Z0-9_]+)\s+(\d+)\b", hdr)}
+    for name in ("GN_FP32", "GN_BF16_TC", "GN_NOISE_GIVEN", "GN_NOISE_PHILOX", "GN_NOISE_PHILOX_DEVICE_SEED"):
+        assert getattr(_lib, name) == enums[name], name
+    assert _lib.ABI_VERSION == defines["GN_ABI_VERSION"]
+    for name in ("GN_MAX_AGENTS", "GN_MAX_SCALES"):
+        if name in defines:
+            assert getattr(_lib, name) == defines[name], name
