@@ -52,8 +52,20 @@ class GraphedPastEncoder:
         for i, layer in enumerate(encoder.layers()):
             e = n * n if i == 0 else ops.incidence_rows(n, layer.scale)
             self._shapes.append([(b, e, layer.edge_types)] * max(layer.nmp_layers, 1))
-        self._u_dev = [[torch.zeros(s, dtype=torch.float32, device=dev) for s in per] for per in self._shapes]
-        self._u_host = [[torch.zeros(s, dtype=torch.float32).pin_memory() for s in per] for per in self._shapes]
+        # one flat pinned buffer and one flat device buffer for all draws of a call: one H2D copy per call
+        total = sum(s[0] * s[1] * s[2] for per in self._shapes for s in per)
+        self._u_host_flat = torch.zeros(total, dtype=torch.float32).pin_memory()
+        self._u_dev_flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._u_host, self._u_dev, off = [], [], 0
+        for per in self._shapes:
+            hs, ds = [], []
+            for s in per:
+                cnt = s[0] * s[1] * s[2]
+                hs.append(self._u_host_flat[off:off + cnt].view(s))
+                ds.append(self._u_dev_flat[off:off + cnt].view(s))
+                off += cnt
+            self._u_host.append(hs)
+            self._u_dev.append(ds)
         self._copied = torch.cuda.Event()
         self._graph = None
         self.recapture()
@@ -93,10 +105,10 @@ class GraphedPastEncoder:
             raise RuntimeError("expected scalar type Float")
         if self.rng == "cpu-compat":
             self._copied.synchronize()              # the previous call's H2D copies have left the pinned buffers
-            for per_h, per_d in zip(self._u_host, self._u_dev):
-                for uh, ud in zip(per_h, per_d):
+            for per_h in self._u_host:
+                for uh in per_h:
                     torch.rand(uh.shape, out=uh)    # global CPU generator, module call order (:454)
-                    ud.copy_(uh, non_blocking=True)
+            self._u_dev_flat.copy_(self._u_host_flat, non_blocking=True)
         self._x.copy_(inputs, non_blocking=True)
         if self.rng == "cpu-compat":
             self._copied.record(torch.cuda.current_stream(self.device))
