@@ -7,12 +7,13 @@ from .layers import (MLP, MLP_dict, MLP_dict_softmax, MS_HGNN_hyper, MS_HGNN_ori
                      edge_aggregation)
 from .encoder import PastEncoder, PositionalAgentEncoding
 from .interaction import MultiScaleInteraction
+from .decoder import Decoder, DecomposeBlock
 from .rollout import GraphedPastEncoder
 from .ops import corr_topk_h, topk_h
 from ._lib import GroupNetLibraryError, LIB_PATH
 
 __all__ = [
     "MS_HGNN_oridinary", "MS_HGNN_hyper", "MLP", "MLP_dict", "MLP_dict_softmax",
-    "edge_aggregation", "MultiScaleInteraction", "PastEncoder", "PositionalAgentEncoding", "GraphedPastEncoder", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
+    "edge_aggregation", "MultiScaleInteraction", "PastEncoder", "PositionalAgentEncoding", "GraphedPastEncoder", "Decoder", "DecomposeBlock", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
 ]
 __version__ = "0.1.0"

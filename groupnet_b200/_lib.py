@@ -31,6 +31,8 @@ EXPORTS = (
     "gn_stage_fwd",
     "gn_stage_launch_count",
     "gn_past_frontend",
+    "gn_decoder_workspace_bytes",
+    "gn_decoder_fwd",
     "gn_stage_saved_offsets",
     "gn_stage_bwd_workspace_bytes",
     "gn_stage_bwd",
@@ -56,6 +58,14 @@ class StageWeights(C.Structure):
         "tc_init_w0", "tc_init_w1", "tc_df_w0", "tc_df_w1",
         "tc_node_w0", "tc_node_w1", "tc_att_wpq", "tc_agg_w0", "tc_agg_w1", "tc_post_w0", "tc_post_w1", "tc_hfuse_w", "tc_npre_w",
     )
+    _fields_ = [(name, C.c_void_p) for name in FIELDS]
+
+
+class DecoderWeights(C.Structure):
+    """struct gn_decoder_weights (17 device pointers, header order)."""
+    FIELDS = ("conv_w", "conv_b", "gru_wx", "gru_wh", "gru_b",
+              "x_w0", "x_b0", "x_w1", "x_b1", "x_w2", "x_b2",
+              "y_w0", "y_b0", "y_w1", "y_b1", "y_w2", "y_b2")
     _fields_ = [(name, C.c_void_p) for name in FIELDS]
 
 
@@ -129,6 +139,12 @@ def load() -> C.CDLL:
         lib.gn_past_frontend.restype = C.c_int
         lib.gn_past_frontend.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.gn_decoder_workspace_bytes.restype = C.c_size_t
+        lib.gn_decoder_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+        lib.gn_decoder_fwd.restype = C.c_int
+        lib.gn_decoder_fwd.argtypes = [C.POINTER(DecoderWeights), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         lib.gn_stage_saved_offsets.restype = C.c_int
         lib.gn_stage_saved_offsets.argtypes = [C.POINTER(StageCfg), C.POINTER(C.c_size_t)]
         lib.gn_stage_bwd_workspace_bytes.restype = C.c_size_t

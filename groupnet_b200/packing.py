@@ -314,3 +314,56 @@ class PackCache:
             self._stages = [PackedStage(layer, s, device) for s in range(n_stage)]
             self._key = key
         return self._stages
+
+
+# ---------------------------------------------------------------------------
+# trajectory decoder (csrc/gn_decoder_simt.cu)
+# ---------------------------------------------------------------------------
+DEC_STATE, DEC_GATE = 96, 128
+
+
+def _pad_gates(w: torch.Tensor) -> torch.Tensor:
+    """(3*96, K) GRU weight with PyTorch's gate order r|z|n -> (3*128, K), each gate zero-padded to 128 rows."""
+    k = w.shape[1]
+    out = torch.zeros(3 * DEC_GATE, k, dtype=torch.float32, device=w.device)
+    for g in range(3):
+        out[g * DEC_GATE:g * DEC_GATE + DEC_STATE] = w[g * DEC_STATE:(g + 1) * DEC_STATE]
+    return out
+
+
+def pack_decoder_block(block, device: torch.device) -> Dict[str, torch.Tensor]:
+    """Tensors of one `struct gn_decoder_weights` from a DecomposeBlock (model/GroupNet_nba.py:13-46)."""
+
+    def dev(x):
+        return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    gru = block.encoder_past
+    if gru.hidden_size != DEC_STATE or gru.input_size != 32 or gru.num_layers != 1 or gru.bidirectional:
+        raise ValueError("decoder kernel is built for GRU(32 -> 96), one layer")
+    out: Dict[str, torch.Tensor] = {}
+    out["conv_w"] = dev(block.conv_past.weight)                                   # (32, 2, 3)
+    out["conv_b"] = dev(block.conv_past.bias)
+    out["gru_wx"] = _kmajor(_pad_gates(dev(gru.weight_ih_l0)), 32, 3 * DEC_GATE, 128)
+    out["gru_wh"] = _kmajor(_pad_gates(dev(gru.weight_hh_l0)), DEC_STATE, 3 * DEC_GATE, 128)
+    b_ih, b_hh = dev(gru.bias_ih_l0), dev(gru.bias_hh_l0)
+    gb = torch.zeros(4, DEC_GATE, dtype=torch.float32, device=device)
+    gb[0, :DEC_STATE] = b_ih[:DEC_STATE] + b_hh[:DEC_STATE]                       # r
+    gb[1, :DEC_STATE] = b_ih[DEC_STATE:2 * DEC_STATE] + b_hh[DEC_STATE:2 * DEC_STATE]   # z
+    gb[2, :DEC_STATE] = b_ih[2 * DEC_STATE:]                                      # b_in
+    gb[3, :DEC_STATE] = b_hh[2 * DEC_STATE:]                                      # b_hn (inside r * (.))
+    out["gru_b"] = gb
+    for tag, mlp in (("x", block.decoder_x), ("y", block.decoder_y)):
+        l0, l1, l2 = mlp.layers
+        if l0.weight.shape[0] != 512 or l1.weight.shape != (256, 512) or l2.weight.shape[1] != 256 \
+                or l2.weight.shape[0] > 64:
+            raise ValueError("decoder kernel is built for MLPs in -> 512 -> 256 -> (<= 64)")
+        kp = _round_up(l0.weight.shape[1], 16)
+        out[f"{tag}_w0"] = _kmajor(dev(l0.weight), kp, 512, 128)
+        out[f"{tag}_b0"] = dev(l0.bias)
+        out[f"{tag}_w1"] = _kmajor(dev(l1.weight), 512, 256, 128)
+        out[f"{tag}_b1"] = dev(l1.bias)
+        out[f"{tag}_w2"] = _kmajor(dev(l2.weight), 256, 64, 64)
+        b2 = torch.zeros(64, dtype=torch.float32, device=device)
+        b2[:l2.bias.numel()] = dev(l2.bias)
+        out[f"{tag}_b2"] = b2
+    return out

@@ -204,6 +204,40 @@ int gn_stage_launch_count(const gn_stage_cfg* cfg);
 int gn_past_frontend(const float* inputs, int64_t R, int32_t K, int32_t N, int32_t C,
                      const float* Mt, const float* bias_agent, float* out, gn_stream_t stream);
 
+/* ---- trajectory decoder, fp32 ---------------------------------------
+ * Replaces Decoder.forward (model/GroupNet_nba.py:461-505) and DecomposeBlock.forward (:48-79):
+ * per row (scene-agent x sample) and block  res = x_true - x_hat -> conv1d(2->32,k3,pad1)+ReLU ->
+ * GRU(32->96) last state -> [past_feature ; z ; state] -> decoder_x / decoder_y (MLPs -> 512 -> 256 -> out);
+ * reconstruction = sum x_hat, out_seq = sum y_hat + cur_location.
+ * One gn_decoder_weights per DecomposeBlock, packed by groupnet_b200/packing.py::pack_decoder_block
+ * (K-major, column-permuted Linear weights as in gn_stage_weights; the three GRU gates r|z|n each padded
+ * from 96 to 128 columns). */
+typedef struct gn_decoder_weights {
+  const float* conv_w;   /* conv_past.weight (32,2,3) as stored */
+  const float* conv_b;   /* (32) */
+  const float* gru_wx;   /* packed (32, 384): weight_ih_l0^T, gates r|z|n */
+  const float* gru_wh;   /* packed (96, 384): weight_hh_l0^T */
+  const float* gru_b;    /* (4,128): b_ir+b_hr | b_iz+b_hz | b_in | b_hn, zero padded */
+  const float* x_w0; const float* x_b0; const float* x_w1; const float* x_b1; const float* x_w2; const float* x_b2;
+  const float* y_w0; const float* y_b0; const float* y_w1; const float* y_b1; const float* y_w2; const float* y_b2;
+                         /* decoder_x / decoder_y: (Kp,512) (512) (512,256) (256) (256,64) (64), Kp = round16(F+Z+96) */
+} gn_decoder_weights;
+
+/* Bytes of device scratch gn_decoder_fwd needs (the x_hat carried between blocks). */
+size_t gn_decoder_workspace_bytes(int64_t A, int32_t S, int32_t Tp);
+
+/*   blocks        host array of num_blocks structs of device pointers (args.num_decompose)
+ *   past_feature  (A*S, F)   per-row past features (repeat_interleave'd by the caller as the reference does)
+ *   z             (A*S, Z)   latent samples
+ *   past_traj     (A, Tp, 2) x_true;  cur_location (A, 1, 2);  A = batch * agents, S = sample_num
+ *   out_seq       (A*S, Tf, 2) == (A, S, Tf, 2) for mode='inference';  recover (A*S, Tp, 2)
+ * Limits: F % 4 == 0, Z % 4 == 0, Tp <= 32, Tf <= 32, (F + Z) such that the tile fits 227 KB of shared memory
+ * (F + Z <= 444). */
+int gn_decoder_fwd(const gn_decoder_weights* blocks, int32_t num_blocks, const float* past_feature, const float* z,
+                   const float* past_traj, const float* cur_location, int64_t A, int32_t S, int32_t F, int32_t Z,
+                   int32_t Tp, int32_t Tf, float* out_seq, float* recover, void* workspace, size_t workspace_bytes,
+                   gn_stream_t stream);
+
 /* ---- training: backward of one stage (fp32) -------------------------------------------------
  * Gradients flow to h_in and to every parameter the forward uses; H, corr and the noise get none
  * (model/MS_HGNN_batch.py:382 uses top-k indices only).  Parameters are read in their native

@@ -134,3 +134,78 @@ def test_decoder_oracle_vs_live_reference(cfg):
     assert o_out.shape == r_out.shape and o_rec.shape == r_rec.shape
     assert_close(o_out, r_out, FP32_REL, "out_seq")
     assert_close(o_rec, r_rec, FP32_REL, "recover_pre_seq")
+
+
+# ---- host side of the CUDA path: packing (no GPU needed) -------------------------------------------
+def _unpermute(packed, tn):
+    """Inverse of packing.permute_cols: K-major matrix with its original column order."""
+    from groupnet_b200.packing import chunk_permutation
+    src = chunk_permutation(tn)
+    out = torch.empty_like(packed)
+    for c0 in range(0, packed.shape[1], tn):
+        out[:, c0 + src] = packed[:, c0:c0 + tn]
+    return out
+
+
+def _emulate_block(p, feat, x_true, x_hat, past_len, future_len):
+    """csrc/gn_decoder_simt.cu's algorithm on the PACKED tensors (padded gates, padded K, padded outputs)."""
+    rows = feat.shape[0]
+    res = x_true - x_hat
+    xpad = torch.nn.functional.pad(res, (0, 0, 1, 1))                       # time padding 1
+    wx, wh = _unpermute(p["gru_wx"], 128), _unpermute(p["gru_wh"], 128)     # (32,384), (96,384)
+    br, bz, b_in, b_hn = p["gru_b"]
+    h = torch.zeros(rows, 128)
+    for t in range(past_len):
+        win = xpad[:, t:t + 3]                                              # (R, 3, 2): steps t-1, t, t+1
+        e = torch.relu(torch.einsum("rkc,ock->ro", win, p["conv_w"]) + p["conv_b"])
+        r = torch.sigmoid(e @ wx[:, :128] + h[:, :96] @ wh[:, :128] + br)
+        n = torch.tanh(e @ wx[:, 256:] + b_in + r * (h[:, :96] @ wh[:, 256:] + b_hn))
+        zg = torch.sigmoid(e @ wx[:, 128:256] + h[:, :96] @ wh[:, 128:256] + bz)
+        h = (1 - zg) * n + zg * h
+    assert torch.count_nonzero(h[:, 96:]) == 0                              # padded state columns stay exactly 0
+    kp = p["x_w0"].shape[0]
+    full = torch.zeros(rows, kp)
+    full[:, :feat.shape[1]] = feat
+    full[:, feat.shape[1]:feat.shape[1] + 96] = h[:, :96]
+    outs = []
+    for tag, width in (("x", 2 * past_len), ("y", 2 * future_len)):
+        h1 = torch.relu(full @ _unpermute(p[f"{tag}_w0"], 128) + p[f"{tag}_b0"])
+        h2 = torch.relu(h1 @ _unpermute(p[f"{tag}_w1"], 128) + p[f"{tag}_b1"])
+        o = h2 @ _unpermute(p[f"{tag}_w2"], 64) + p[f"{tag}_b2"]
+        assert torch.count_nonzero(o[:, width:]) == 0
+        outs.append(o[:, :width])
+    return outs[0].reshape(rows, past_len, 2), outs[1].reshape(rows, future_len, 2)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_packed_decoder_weights_reproduce_the_oracle(name):
+    from groupnet_b200.packing import pack_decoder_block
+    g = _load(name)
+    m = _schema(g)
+    for blk in m.decompose:                      # the fixtures' GRU / conv biases are zero-initialised: exercise them
+        torch.nn.init.normal_(blk.encoder_past.bias_ih_l0, std=0.3)
+        torch.nn.init.normal_(blk.encoder_past.bias_hh_l0, std=0.3)
+        torch.nn.init.normal_(blk.conv_past.bias, std=0.3)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    s = g["sample_num"]
+    feat = torch.cat((torch.from_numpy(g["past_feature_per_agent"]).repeat_interleave(s, dim=0),
+                      torch.from_numpy(g["z"])), dim=1)
+    x_true = torch.from_numpy(g["past_traj"]).repeat_interleave(s, dim=0)
+    x_hat = torch.zeros_like(x_true)
+    with torch.no_grad():
+        for i, blk in enumerate(m.decompose):
+            p = pack_decoder_block(blk, torch.device("cpu"))
+            assert p["gru_wx"].shape == (32, 384) and p["gru_wh"].shape == (96, 384) and p["gru_b"].shape == (4, 128)
+            ref_x, ref_y = DO.decompose_block(sd, f"decompose.{i}", x_true, x_hat, feat, g["past_length"],
+                                              g["future_length"])
+            got_x, got_y = _emulate_block(p, feat, x_true, x_hat, g["past_length"], g["future_length"])
+            assert_close(got_x, ref_x, FP32_REL, f"{name} block {i} x_hat")
+            assert_close(got_y, ref_y, FP32_REL, f"{name} block {i} y_hat")
+            x_hat = ref_x
+
+
+def test_decoder_dropin_refuses_cpu_tensors_and_autograd():
+    g = _load("single_block_single_row")
+    m = _schema(g)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 256), torch.zeros(1, 32), 1, 1, torch.zeros(1, 5, 2), torch.zeros(1, 1, 2), 1)
