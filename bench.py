@@ -386,6 +386,143 @@ def run_crowd(args, rank, world, local):
 
 
 # ---------------------------------------------------------------------------
+def run_decoder(args, rank, world, local):
+    """the trajectory decoder (model/GroupNet_nba.py:441-505) at the NBA inference shape —
+    11 agents x 20 samples per scene, 2 DecomposeBlocks, fp32 FFMA path.  One step = Decoder.forward on
+    --scenes scenes per GPU (default 1024; weak scaling, scenes are independent, no collective)."""
+    import types
+    import torch.distributed as dist
+    import groupnet_b200 as gb
+    from groupnet_b200 import _lib
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    scenes = args.scenes if args.scenes != SCENES else 1024
+    n, s, f, zd, tp, tf, blocks = 11, 20, 256, 32, 5, 10, 2
+    cfg = types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], zdim=zd, past_length=tp, future_length=tf,
+                                num_decompose=blocks)
+    torch.manual_seed(1234)
+    dec = gb.Decoder(cfg)
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    dec = dec.to(dev)
+    a = scenes * n
+    gen = torch.Generator().manual_seed(rank)
+    pf_h = torch.randn(a, f, generator=gen).repeat_interleave(s, dim=0).pin_memory()
+    z_h = torch.randn(a * s, zd, generator=gen).pin_memory()
+    past_h = torch.randn(a, tp, 2, generator=gen).pin_memory()
+    cur_h = torch.randn(a, 1, 2, generator=gen).pin_memory()
+    pf, z, past, cur = (t.to(dev) for t in (pf_h, z_h, past_h, cur_h))
+    out_h = torch.empty(a, s, tf, 2).pin_memory()
+    rec_h = torch.empty(a * s, tp, 2).pin_memory()
+
+    def step():
+        return dec(pf, z, scenes, n, past, cur, s, mode="inference")
+
+    def step_e2e():
+        o, r = dec(pf_h.to(dev, non_blocking=True), z_h.to(dev, non_blocking=True), scenes, n,
+                   past_h.to(dev, non_blocking=True), cur_h.to(dev, non_blocking=True), s, mode="inference")
+        out_h.copy_(o, non_blocking=True)
+        rec_h.copy_(r, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+            step_e2e()
+        with ClockSampler(local) as clocks:
+            ms = timed(step)
+        ms_e2e = timed(step_e2e)
+        _lib.profile_enable(True)
+        step()
+        torch.cuda.synchronize(dev)
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    macs_row_block = tp * 3 * 96 * (32 + 96) + tp * 32 * 6 + 2 * (384 * 512 + 512 * 256) + 256 * 2 * tp + 256 * 2 * tf
+    flops_scene = 2.0 * macs_row_block * n * s * blocks
+    kernels = {k: {"ms_per_step": round(t, 3), "launches_per_step": c} for k, (t, c) in prof.items()}
+    kms = kernels.get("decoder_block", {}).get("ms_per_step") or ms
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    ach = flops_scene * scenes / (kms * 1e-3) / 1e12
+    ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import decoder_oracle as DO
+        torch.set_num_threads(os.cpu_count() or 1)
+        cs = 32
+        ca = cs * n
+        cpf, cz = pf_h[:ca * s].clone(), z_h[:ca * s].clone()
+        cpast, ccur = past_h[:ca].clone(), cur_h[:ca].clone()
+
+        def cpu_step():
+            with torch.no_grad():
+                DO.decoder_forward(sd, cpf, cz, cs, n, cpast, ccur, s, past_len=tp, future_len=tf,
+                                   num_decompose=blocks, mode="inference")
+        cpu_step()
+        done, spent = 0, 0.0
+        while spent < 10.0 and done < 4096:
+            t0 = time.perf_counter()
+            cpu_step()
+            spent += time.perf_counter() - t0
+            done += cs
+        cpu = {"value": done / spent, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{done} scenes in chunks of {cs} (oracle port of Decoder.forward, fp32 torch CPU), {spent:.1f} s"}
+    h2d = (pf_h.numel() + z_h.numel() + past_h.numel() + cur_h.numel()) * 4
+    d2h = (out_h.numel() + rec_h.numel()) * 4
+    print(json.dumps({
+        "metric": "decoder_forward_scenes_per_sec", "value": world * scenes / (ms * 1e-3), "unit": "scenes/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"nba_decoder_B{scenes}_N11_S20_blocks2", "scenes_per_gpu": scenes, "agents": n,
+                   "samples": s, "rows_per_gpu": a * s, "feature_width": f + zd, "past_length": tp,
+                   "future_length": tf, "num_decompose": blocks,
+                   "l2": "no flush: per-step inputs (%d MB) exceed the 126 MB L2" % (h2d >> 20)
+                         if h2d > (126 << 20) else "inputs fit L2 (weights + activations dominate; compute-bound kernel)",
+                   "sharding": "batch-sharded, no collective"},
+        "flops_per_scene": flops_scene,
+        "e2e": {"value": world * scenes / (ms_e2e * 1e-3), "unit": "scenes/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "groupnet_b200.Decoder.forward (pinned host in/out)"},
+        "clocks": clocks.summary(), "gpu_launches": sum(c for _, c in prof.values()) * args.steps,
+        "roofline": {"kernel": "decoder_block", "bound": "tensor", "achieved": round(ach, 2), "peak": tensor_peak,
+                     "unit": "TFLOP/s", "frac": round(ach / tensor_peak, 4), "traffic": None,
+                     "note": "fp32 FFMA path, not on the tensor pipe yet: %.1f TFLOP/s FFMA peak at 1,965 MHz -> "
+                             "%.3f of it" % (ffma_peak, ach / ffma_peak)},
+        "cpu_baseline": cpu, "kernels": kernels}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -396,7 +533,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core path (2e-2 parity); fp32: FFMA path (1e-5 parity)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="nba", choices=["nba", "crowd", "fish8", "fish20"],
+    ap.add_argument("--workload", default="nba", choices=["nba", "crowd", "fish8", "fish20", "decoder"],
                     help="nba: BASELINE configs[2] (the headline line); crowd: configs[3], N=64, h_dim 256, "
                          "scales {2,4,8,16}, 262,144 scenes sharded over the GPUs (strong scaling); fish8 / fish20: "
                          "configs[1], the MS_HGNN layers at the fish dataset shapes (8 agents, scales {3,5,8}; "
@@ -426,6 +563,8 @@ def main():
         return run_train(args, rank, world, local)
     if args.workload == "crowd":
         return run_crowd(args, rank, world, local)
+    if args.workload == "decoder":
+        return run_decoder(args, rank, world, local)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     # torchrun pins OMP_NUM_THREADS=1; the host side of the e2e pipeline (x slice of final_feature)
