@@ -279,3 +279,19 @@ def test_binding_constants_match_the_header_enums():
     for name in ("GN_MAX_AGENTS", "GN_MAX_SCALES"):
         if name in defines:
             assert getattr(_lib, name) == defines[name], name
+
+
+def test_device_seed_walk_matches_the_by_value_philox_seeds():
+    """rng="philox-device" keeps the per-call seed in an int64 tensor advanced by `add_` (two's-complement wrap);
+    the eager "philox" mode computes (seed + k * stride) mod 2^64 on the host.  Same sequence of 64-bit patterns."""
+    from groupnet_b200 import layers as L
+    for seed in (0, 12345, (1 << 63) + 12345, (1 << 64) - 1):
+        t = torch.full((1,), L._as_int64(seed), dtype=torch.int64)
+        for k in range(6):
+            want = (seed + L._PHILOX_CALL_STRIDE * k) & L._MASK64
+            assert (int(t.item()) & L._MASK64) == want
+            t.add_(L._as_int64(L._PHILOX_CALL_STRIDE))
+    m = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=1)
+    assert m.set_rng("philox-device", 7).rng == "philox-device"
+    with pytest.raises(ValueError):
+        m.set_rng("philox-host")
