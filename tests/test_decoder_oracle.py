@@ -209,3 +209,50 @@ def test_decoder_dropin_refuses_cpu_tensors_and_autograd():
     m = _schema(g)
     with torch.no_grad(), pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 256), torch.zeros(1, 32), 1, 1, torch.zeros(1, 5, 2), torch.zeros(1, 1, 2), 1)
+
+
+# ---- numeric plan of the tensor-core decoder path, checked before the kernel exists -------
+def _bf16(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _lin_bf16(x, w, b):
+    """bf16 operands, fp32 accumulate, fp32 bias: what a tcgen05 kind::f16 GEMM computes."""
+    return _bf16(x) @ _bf16(w).t() + b
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_bf16_operand_plan_for_the_decoder_stays_inside_the_bf16_tolerance(name):
+    """Every Linear (GRU gates included) with bf16 operands and fp32 accumulation, the GRU state carried in fp32 and
+    only its operand copy rounded, conv1d in fp32: 3e-3 .. 5e-3 of max|ref| on the fixtures, against the 2e-2 bar."""
+    import torch.nn.functional as F
+    g = _load(name)
+    sd = {k: v.detach() for k, v in _schema(g).state_dict().items()}
+    s, tp, tf = g["sample_num"], g["past_length"], g["future_length"]
+    f = torch.cat((torch.from_numpy(g["past_feature_per_agent"]).repeat_interleave(s, 0), torch.from_numpy(g["z"])), 1)
+    x_true = torch.from_numpy(g["past_traj"]).repeat_interleave(s, 0)
+    x_hat, pred, rec = torch.zeros_like(x_true), 0.0, 0.0
+    with torch.no_grad():
+        for i in range(g["num_decompose"]):
+            p = f"decompose.{i}"
+            e = torch.relu(F.conv1d((x_true - x_hat).transpose(1, 2), sd[f"{p}.conv_past.weight"],
+                                    sd[f"{p}.conv_past.bias"], padding=1)).transpose(1, 2)
+            h = torch.zeros(x_true.shape[0], 96)
+            for t in range(tp):
+                gi = _lin_bf16(e[:, t], sd[f"{p}.encoder_past.weight_ih_l0"], sd[f"{p}.encoder_past.bias_ih_l0"])
+                gh = _lin_bf16(h, sd[f"{p}.encoder_past.weight_hh_l0"], sd[f"{p}.encoder_past.bias_hh_l0"])
+                rg = torch.sigmoid(gi[:, :96] + gh[:, :96])
+                zg = torch.sigmoid(gi[:, 96:192] + gh[:, 96:192])
+                h = (1 - zg) * torch.tanh(gi[:, 192:] + rg * gh[:, 192:]) + zg * h
+            feat, outs = torch.cat((f, h), 1), []
+            for tag, width in (("decoder_x", tp), ("decoder_y", tf)):
+                a = feat
+                for li in range(3):
+                    a = _lin_bf16(a, sd[f"{p}.{tag}.layers.{li}.weight"], sd[f"{p}.{tag}.layers.{li}.bias"])
+                    a = torch.relu(a) if li < 2 else a
+                outs.append(a.view(-1, width, 2))
+            x_hat = outs[0]
+            pred, rec = pred + outs[1], rec + x_hat
+        out = pred + torch.from_numpy(g["cur_location"]).repeat_interleave(s, 0)
+    assert_close(out, torch.from_numpy(g["out_seq"]).reshape(out.shape), 1e-2, f"{name} out_seq (bf16 plan)")
+    assert_close(rec, g["recover_pre_seq"], 1e-2, f"{name} recover_pre_seq (bf16 plan)")
