@@ -205,9 +205,55 @@ def cpu_baseline(budget_s=12.0):
                       f"fp32, torch CPU, as-written algorithm), {spent:.1f} s"}
 
 
+def run_reference_decoder(args):
+    """--impl reference --workload decoder: the CPU restatement of Decoder.forward (oracle/decoder_oracle.py) on the
+    host cores, a bounded sample of the decoder workload per step."""
+    import types
+    import groupnet_b200 as gb
+    from oracle import decoder_oracle as DO
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n, s, f, zd, tp, tf, blocks, sample = 11, 20, 256, 32, 5, 10, 2, 64
+    torch.manual_seed(1234)
+    dec = gb.Decoder(types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], zdim=zd, past_length=tp,
+                                           future_length=tf, num_decompose=blocks))
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    a = sample * n
+    gen = torch.Generator().manual_seed(0)
+    pf = torch.randn(a, f, generator=gen).repeat_interleave(s, dim=0)
+    z = torch.randn(a * s, zd, generator=gen)
+    past, cur = torch.randn(a, tp, 2, generator=gen), torch.randn(a, 1, 2, generator=gen)
+
+    def step():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            DO.decoder_forward(sd, pf, z, sample, n, past, cur, s, past_len=tp, future_len=tf, num_decompose=blocks,
+                               mode="inference")
+        return time.perf_counter() - t0
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t = [step() for _ in range(args.steps)]
+    per_step = sum(t) / len(t)
+    val = sample / per_step
+    desc = {"value": val, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample} scenes per step (oracle port of Decoder.forward, fp32 torch CPU)"}
+    print(json.dumps({
+        "impl": "reference", "metric": "decoder_forward_scenes_per_sec", "value": val, "unit": "scenes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "nba_decoder_N11_S20_blocks2", "sample_scenes_per_step": sample, "agents": n,
+                   "samples": s, "past_length": tp, "future_length": tf, "num_decompose": blocks},
+        "cpu_baseline": desc,
+        "e2e": {"value": val, "unit": "scenes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
+    if args.workload == "decoder":
+        return run_reference_decoder(args)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     fwd = build_cpu_arm()
