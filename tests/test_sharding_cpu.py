@@ -91,3 +91,42 @@ def _ddp_worker(rank, world, port):
 def test_two_rank_gloo_flat_bucket_allreduce():
     port = _free_port()
     mp.spawn(_ddp_worker, args=(2, port), nprocs=2, join=True)
+
+
+def _decoder_worker(rank, world, port, scenes):
+    """The decoder shards like the layers: contiguous scene ranges, rows = scene x agent x sample, no collective."""
+    import types
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import groupnet_b200 as gb
+        from oracle import decoder_oracle as DO
+        n, s, tp, tf = 11, 4, 5, 10
+        torch.manual_seed(77)
+        dec = gb.Decoder(types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], zdim=32, past_length=tp,
+                                               future_length=tf, num_decompose=2))
+        sd = {k: v.detach() for k, v in dec.state_dict().items()}
+        gen = torch.Generator().manual_seed(5)
+        a_all = scenes * n
+        pf = torch.randn(a_all, 256, generator=gen).repeat_interleave(s, dim=0)
+        z = torch.randn(a_all * s, 32, generator=gen)
+        past, cur = torch.randn(a_all, tp, 2, generator=gen), torch.randn(a_all, 1, 2, generator=gen)
+        a, b = sharding.shard_range(scenes, rank, world)
+        with torch.no_grad():
+            out, rec = DO.decoder_forward(sd, pf[a * n * s:b * n * s], z[a * n * s:b * n * s], b - a, n,
+                                          past[a * n:b * n], cur[a * n:b * n], s, past_len=tp, future_len=tf,
+                                          num_decompose=2, mode="inference")
+            full_out = sharding.gather_scenes(out.reshape(b - a, n * s * tf * 2), scenes)
+            full_rec = sharding.gather_scenes(rec.reshape(b - a, n * s * tp * 2), scenes)
+            ref_out, ref_rec = DO.decoder_forward(sd, pf, z, scenes, n, past, cur, s, past_len=tp, future_len=tf,
+                                                  num_decompose=2, mode="inference")
+        assert torch.allclose(full_out, ref_out.reshape(scenes, -1), rtol=0, atol=2e-6)
+        assert torch.allclose(full_rec, ref_rec.reshape(scenes, -1), rtol=0, atol=2e-6)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_decoder_sharding():
+    port = _free_port()
+    mp.spawn(_decoder_worker, args=(2, port, 7), nprocs=2, join=True)
