@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .layers import MLP
-from .packing import pack_decoder_block
+from .packing import PackCache, pack_decoder_block
 
 
 class DecomposeBlock(nn.Module):
@@ -69,7 +69,7 @@ class Decoder(nn.Module):
         self._ws = ops.Workspace()
 
     def _packs(self, device):
-        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = PackCache._fingerprint(self, device)
         if key != self._pack_key:
             tensors = [pack_decoder_block(blk, device) for blk in self.decompose]
             structs = (_lib.DecoderWeights * len(tensors))()

@@ -295,3 +295,31 @@ def test_device_seed_walk_matches_the_by_value_philox_seeds():
     assert m.set_rng("philox-device", 7).rng == "philox-device"
     with pytest.raises(ValueError):
         m.set_rng("philox-host")
+
+
+def test_pack_cache_is_reused_until_a_parameter_changes():
+    """Packed weights are rebuilt exactly when a parameter is modified in place (optimizer step, load_state_dict),
+    moved / re-typed, or replaced — and not otherwise."""
+    torch.manual_seed(2)
+    m = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=2, scale=3)
+    cpu = torch.device("cpu")
+    first = m._packs.get(m, cpu)
+    assert m._packs.get(m, cpu) is first                                     # unchanged -> cached
+    names = [n for n, _ in m.named_parameters()]
+    flat = packing.PackCache._fingerprint(m, cpu)
+    assert len(flat) == 1 + 2 * len(names)                                   # every parameter, registration order
+    assert list(flat[1::2]) == [p.data_ptr() for p in m.parameters()]
+    w0_before = first[-1].tensors["post_w0t"].clone()                        # a transformed (K-major) copy
+    with torch.no_grad():
+        m.nmp_mlp_end.layers[0].weight.mul_(2.0)                             # in-place update (optimizer step)
+    second = m._packs.get(m, cpu)
+    assert second is not first
+    assert torch.equal(second[-1].tensors["post_w0t"], 2.0 * w0_before)
+    m.load_state_dict({k: v.clone() for k, v in m.state_dict().items()})     # copies in place -> versions bump
+    third = m._packs.get(m, cpu)
+    assert third is not second
+    m.nmp_mlp_end.layers[0].weight = torch.nn.Parameter(torch.zeros_like(m.nmp_mlp_end.layers[0].weight))
+    fourth = m._packs.get(m, cpu)                                            # Parameter object replaced
+    assert fourth is not third and torch.count_nonzero(fourth[-1].tensors["post_w0t"]) == 0
+    m.double().float()                                                       # storage replaced, same values
+    assert m._packs.get(m, cpu) is not fourth
