@@ -20,7 +20,7 @@ Differences a caller can observe (all documented in DESIGN.md):
 """
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Union
+from typing import List, Optional
 
 import torch
 import torch.nn as nn

@@ -8,7 +8,6 @@ import torch
 
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import groupnet_b200 as gb   # noqa: E402
-from groupnet_b200 import _lib  # noqa: E402
 
 DEV = torch.device("cuda:0")
 

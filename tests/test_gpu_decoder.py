@@ -1,6 +1,5 @@
 """Trajectory decoder on the GPU (gn_decoder_fwd through groupnet_b200.Decoder) against the fixtures generated
 from the reference and against the CPU oracle.  fp32 criterion: 1e-5 * max|ref|."""
-import os
 
 import pytest
 import torch
