@@ -256,3 +256,49 @@ def test_bf16_operand_plan_for_the_decoder_stays_inside_the_bf16_tolerance(name)
         out = pred + torch.from_numpy(g["cur_location"]).repeat_interleave(s, 0)
     assert_close(out, torch.from_numpy(g["out_seq"]).reshape(out.shape), 1e-2, f"{name} out_seq (bf16 plan)")
     assert_close(rec, g["recover_pre_seq"], 1e-2, f"{name} recover_pre_seq (bf16 plan)")
+
+
+# ---- randomized differential pin against the live reference (build container only) ---------------------
+try:
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    _HAVE_HYP = True
+except Exception:                                   # pragma: no cover
+    _HAVE_HYP = False
+
+if _HAVE_HYP:
+    @pytest.mark.skipif(not have_reference(), reason="reference tree not present (GPU box)")
+    @settings(max_examples=12, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(hidden=st.sampled_from([8, 16, 32]), n_scales=st.integers(0, 3), zdim=st.sampled_from([4, 8, 32]),
+           tp=st.integers(1, 7), tf=st.integers(1, 9), blocks=st.integers(1, 3), batch=st.integers(1, 3),
+           agents=st.integers(1, 6), s=st.integers(1, 4), inference=st.booleans())
+    def test_decoder_oracle_vs_live_reference_random_configs(hidden, n_scales, zdim, tp, tf, blocks, batch, agents, s,
+                                                             inference):
+        sys.path.insert(0, REFERENCE_DIR)
+        for missing in ("tkinter", "glob2"):
+            if missing not in sys.modules:
+                stub = types.ModuleType(missing)
+                stub.TRUE = True
+                sys.modules[missing] = stub
+        from model.GroupNet_nba import Decoder
+        scales = list(range(2, 2 + n_scales))
+        torch.manual_seed(hidden + tp + tf)
+        ref = Decoder(types.SimpleNamespace(hidden_dim=hidden, hyper_scales=scales, zdim=zdim, past_length=tp,
+                                            future_length=tf, num_decompose=blocks)).eval()
+        for blk in ref.decompose:                    # zero-initialised by the reference: make them count
+            torch.nn.init.normal_(blk.encoder_past.bias_ih_l0, std=0.3)
+            torch.nn.init.normal_(blk.encoder_past.bias_hh_l0, std=0.3)
+            torch.nn.init.normal_(blk.conv_past.bias, std=0.3)
+        a = batch * agents
+        gen = torch.Generator().manual_seed(a + s)
+        pf = torch.randn(a, (2 + n_scales) * hidden, generator=gen).repeat_interleave(s, dim=0)
+        z = torch.randn(a * s, zdim, generator=gen)
+        past, cur = torch.randn(a, tp, 2, generator=gen), torch.randn(a, 1, 2, generator=gen)
+        mode = "inference" if inference else "train"
+        with torch.no_grad():
+            r_out, r_rec = ref(pf, z, batch, agents, past, cur, s, mode=mode)
+            o_out, o_rec = DO.decoder_forward({k: v.detach() for k, v in ref.state_dict().items()}, pf, z, batch,
+                                              agents, past, cur, s, past_len=tp, future_len=tf,
+                                              num_decompose=blocks, mode=mode)
+        assert o_out.shape == r_out.shape and o_rec.shape == r_rec.shape
+        assert_close(o_out, r_out, FP32_REL, "out_seq")
+        assert_close(o_rec, r_rec, FP32_REL, "recover_pre_seq")
