@@ -11,12 +11,13 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgroupnet_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 GN_MAX_AGENTS = 64
 GN_MAX_SCALES = 8
 GN_FP32 = 0
 GN_BF16_TC = 1
+GN_TF32X3 = 2
 GN_NOISE_GIVEN = 0
 GN_NOISE_PHILOX = 1
 GN_NOISE_PHILOX_DEVICE_SEED = 2
@@ -47,7 +48,7 @@ class GroupNetLibraryError(RuntimeError):
 
 
 class StageWeights(C.Structure):
-    """struct gn_stage_weights (37 device pointers, header order)."""
+    """struct gn_stage_weights (43 device pointers, header order)."""
     FIELDS = (
         "node_w0t", "node_b0", "node_w1t", "node_b1",
         "att_wpqt", "att_b0", "att_w1", "att_b1",
@@ -57,6 +58,7 @@ class StageWeights(C.Structure):
         "post_w0t", "post_b0", "post_w1t", "post_b1",
         "tc_init_w0", "tc_init_w1", "tc_df_w0", "tc_df_w1",
         "tc_node_w0", "tc_node_w1", "tc_att_wpq", "tc_agg_w0", "tc_agg_w1", "tc_post_w0", "tc_post_w1", "tc_hfuse_w", "tc_npre_w",
+        "tf_chain_w", "tf_pre_w", "tf_aggin_w", "tf_aggout_w", "tf_hagg_w", "tf_post_w",
     )
     _fields_ = [(name, C.c_void_p) for name in FIELDS]
 

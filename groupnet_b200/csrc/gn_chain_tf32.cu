@@ -1,0 +1,725 @@
+// fp32-grade tensor-core path (precision GN_TF32X3): the dense contractions of one message-passing stage as
+// chains of 3xTF32 GEMMs on tcgen05 / TMEM, 1e-5 parity with the reference's fp32 addmm chain
+// (model/MS_HGNN_batch.py:31-53 MLP_dict_softmax, :201-229 MLP, :247-268 edge_aggregation).
+//
+// ONE engine kernel runs every chain.  A tile = 128 rows (node rows or edge rows), one persistent CTA per SM:
+//
+//   warps 0-3  row threads: thread t owns tile row t = TMEM lane t.  They stage the tile's input rows (fp32
+//              from HBM, or the fused pairwise node2edge) as split hi / lo tf32 operands in shared memory, and
+//              after every GEMM drain the accumulator (tcgen05.ld), apply bias / ReLU / per-row scale in fp32,
+//              and either store fp32 rows to HBM or split the activation again and write it back to TENSOR
+//              MEMORY (tcgen05.st) where the next GEMM reads it as its A operand (TS mode): activations never
+//              touch shared memory or HBM between the Linears of a chain;
+//   warp 4     weight producer: TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of the host-packed
+//              weight stream (hi | lo chunks in consumption order) into a ring of 16 KB stages;
+//   warp 5     MMA issuer: one thread, three kind::tf32 MMAs per K = 8 step (gn_tf32.cuh), tcgen05.commit
+//              releases ring stages and publishes accumulators.
+//
+// The chain itself is data: a list of ops (gn_chain_tf32.cuh) built on the host by the launchers below —
+// TMEM column assignment, which drains feed which op, where the issuer must wait for the row threads.
+// Row threads and the issuer communicate through two rings of NBAR mbarriers (a_ready: operands written,
+// acc_ready: accumulator complete); validate_program() replays the protocol on the host and rejects a program
+// whose producers could run NBAR phases ahead of its consumers.
+//
+// Roofline: tensor pipe at 1/6 of the bf16 rate (tf32 = 1/2, three MMAs per product): 64*N/2 clk per 128 x N x 8.
+#include "gn_chain_tf32.cuh"
+#include "gn_tf32.cuh"
+#include "gn_stage.h"
+
+namespace gn {
+
+namespace tfe {
+
+constexpr int THREADS = 192;
+
+__device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct Bars {
+  uint64_t full[8], empty[8], a_ready[NBAR], acc_ready[NBAR];
+  uint32_t tmem_slot, pad;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+chain_tf32_kernel(const __grid_constant__ Args a) {
+  using namespace tc;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Bars* bars = reinterpret_cast<Bars*>(smem + a.off_bar);
+
+  if (tid == 0) {
+    for (int s = 0; s < a.nstage; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
+    for (int i = 0; i < NBAR; ++i) { mbar_init(&bars->a_ready[i], 128); mbar_init(&bars->acc_ready[i], 1); }
+  }
+  if (warp == 0) tmem_alloc(&bars->tmem_slot, 512);
+  fence_proxy_async_smem();
+  fence_before_thread_sync();
+  __syncthreads();
+  fence_after_thread_sync();
+  const uint32_t tmem = bars->tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == 4) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const unsigned char* src = a.wstream;
+        for (int o = 0; o < a.nops; ++o) {
+          const Op& op = a.ops[o];
+          const uint32_t bytes = static_cast<uint32_t>(op.N) * op.kc * 8;
+          const int nch = op.K / op.kc;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(&bars->empty[s], ph ^ 1u);
+            mbar_expect_tx(&bars->full[s], bytes);
+            bulk_g2s(sbase + a.off_ring + s * STAGE_BYTES, src, bytes, &bars->full[s]);
+            src += bytes;
+            if (++s == a.nstage) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      uint32_t aw = 0, sg = 0;               // a_ready phases consumed, acc_ready phases produced
+      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        for (int o = 0; o < a.nops; ++o) {
+          const Op& op = a.ops[o];
+          for (int w = 0; w < op.wait_n; ++w) { mbar_wait(&bars->a_ready[aw & (NBAR - 1)], (aw / NBAR) & 1u); ++aw; }
+          fence_after_thread_sync();
+          const int N = op.N, K = op.K, kc = op.kc, nch = K / kc;
+          const uint32_t d = tmem + op.acc_col;
+          const uint32_t half = static_cast<uint32_t>(N) * kc * 4;
+          for (int c = 0; c < nch; ++c) {
+            mbar_wait(&bars->full[s], ph);
+            fence_after_thread_sync();
+            const uint32_t b_hi = sbase + a.off_ring + s * STAGE_BYTES, b_lo = b_hi + half;
+            const bool acc_first = (c > 0) || (op.accumulate != 0);
+            if (op.a_src == A_SMEM) {
+              const uint32_t a_hi = sbase + a.off_a0 + op.a_buf * a.a0_buf_bytes + static_cast<uint32_t>(c * kc / 4) * 2048u;
+              tf::issue_x3_ss(d, a_hi, a_hi + a.a0_half_bytes, b_hi, b_lo, N, kc, acc_first);
+            } else {
+              const uint32_t ta = tmem + op.a_col + c * kc;
+              tf::issue_x3_ts(d, ta, ta + K, b_hi, b_lo, N, kc, acc_first);
+            }
+            mma_commit(&bars->empty[s]);
+            if (++s == a.nstage) { s = 0; ph ^= 1u; }
+          }
+          if (op.signal) { mma_commit(&bars->acc_ready[sg & (NBAR - 1)]); ++sg; }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ row threads (stage + drain)
+    const int row = tid;
+    const uint32_t tmem_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    unsigned char* a0 = smem + a.off_a0;
+    uint32_t ar = 0, sg = 0;                 // a_ready phases produced, acc_ready phases consumed
+    const bool pair = a.stage_mode == ST_PAIR;
+    float* nx = reinterpret_cast<float*>(smem + a.off_node);     // x' rows of the tile's node block
+    float* np = nx + MAXN * NLD;                                 // pq rows
+    const long long total_nodes = pair ? (a.R / a.E) * a.N : 0;
+    const int tps = pair ? a.tps : 0;
+    auto prefetch_nodes = [&](long long t) {
+      if (t < a.ntiles) {
+        const long long node0 = (tps ? t / tps : (t * 128) / a.E) * a.N;
+        const int cnt = static_cast<int>(min(static_cast<long long>(MAXN), total_nodes - node0));
+        for (int i = tid; i < cnt * 16; i += 128) {
+          const int n = i >> 4, c = i & 15;
+          cp_async16(nx + n * NLD + 4 * c, a.xprime + (node0 + n) * 64 + 4 * c);
+          cp_async16(np + n * NLD + 4 * c, a.pq + (node0 + n) * 64 + 4 * c);
+        }
+      }
+      cp_async_commit();
+    };
+    if (pair) prefetch_nodes(blockIdx.x);
+    unsigned long long seed = a.seed;
+    if (a.noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && a.U != nullptr)
+      seed = __ldg(reinterpret_cast<const unsigned long long*>(a.U));
+
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      const long long tscene = tps ? tile / tps : 0;
+      const int tchunk = tps ? static_cast<int>(tile - tscene * tps) : 0;
+      const long long grow = tps ? tscene * a.E + tchunk * 128 + row : tile * 128 + row;
+      const bool live = grow < a.R && (!tps || tchunk * 128 + row < a.E);
+      float carry = 0.f;
+
+      for (int e = 0; e < a.nev; ++e) {
+        const Op& op = a.ops[a.ev_op[e]];
+        if (a.ev_type[e] == EV_STAGE) {
+          unsigned char* hi = a0 + op.a_buf * a.a0_buf_bytes;
+          unsigned char* lo = hi + a.a0_half_bytes;
+          if (pair) {
+            // fused node2edge of the pairwise layer: attention over the (<= 2) members of edge (i,j), softmax over
+            // ALL N nodes (non-members enter with logit 0), self loops carry incidence 2 (:124,:135-137)
+            cp_async_wait<0>();
+            row_bar();
+            const long long b_lo = tps ? tscene : (tile * 128) / a.E;
+            float wi = 0.f, wj = 0.f;
+            const float* xi = nx;
+            const float* xj = nx;
+            if (live) {
+              const int N = a.N;
+              const long long b = grow / a.E;
+              const int eidx = static_cast<int>(grow - b * a.E), i = eidx / N, j = eidx - i * N;
+              const int li = static_cast<int>(b - b_lo) * N + i, lj = static_cast<int>(b - b_lo) * N + j;
+              const float* pi = np + li * NLD;
+              const float* pj = np + lj * NLD;
+              xi = nx + li * NLD;
+              xj = nx + lj * NLD;
+              float ai = 0.f, aj = 0.f;
+#pragma unroll
+              for (int k4 = 0; k4 < 32; k4 += 4) {
+                const float4 ni = *reinterpret_cast<const float4*>(pi + k4);
+                const float4 nj = *reinterpret_cast<const float4*>(pj + k4);
+                const float4 qi = *reinterpret_cast<const float4*>(pi + 32 + k4);
+                const float4 qj = *reinterpret_cast<const float4*>(pj + 32 + k4);
+                const float4 b0 = ldg_f4(a.att_b0 + k4);
+                const float4 w1 = ldg_f4(a.att_w1 + k4);
+                const float p0 = qi.x + qj.x + b0.x, p1 = qi.y + qj.y + b0.y;
+                const float p2 = qi.z + qj.z + b0.z, p3 = qi.w + qj.w + b0.w;
+                ai = fmaf(fmaxf(ni.x + p0, 0.f), w1.x, ai); aj = fmaf(fmaxf(nj.x + p0, 0.f), w1.x, aj);
+                ai = fmaf(fmaxf(ni.y + p1, 0.f), w1.y, ai); aj = fmaf(fmaxf(nj.y + p1, 0.f), w1.y, aj);
+                ai = fmaf(fmaxf(ni.z + p2, 0.f), w1.z, ai); aj = fmaf(fmaxf(nj.z + p2, 0.f), w1.z, aj);
+                ai = fmaf(fmaxf(ni.w + p3, 0.f), w1.w, ai); aj = fmaf(fmaxf(nj.w + p3, 0.f), w1.w, aj);
+              }
+              const float b1v = __ldg(a.att_b1);
+              if (i == j) {
+                const float si = 2.f * (ai + b1v);
+                const float mx = (N > 1) ? fmaxf(si, 0.f) : si;
+                const float ei = expf(si - mx);
+                wi = ei / (ei + static_cast<float>(N - 1) * expf(-mx)) * 2.f;
+                wj = 0.f;
+              } else {
+                const float si = ai + b1v, sj = aj + b1v;
+                float mx = fmaxf(si, sj);
+                if (N > 2) mx = fmaxf(mx, 0.f);
+                const float ei = expf(si - mx), ej = expf(sj - mx);
+                const float den = ei + ej + static_cast<float>(N - 2) * expf(-mx);
+                wi = ei / den; wj = ej / den;
+              }
+            }
+#pragma unroll 4
+            for (int k4 = 0; k4 < 16; ++k4) {
+              const float4 u = *reinterpret_cast<const float4*>(xi + 4 * k4);
+              const float4 v = *reinterpret_cast<const float4*>(xj + 4 * k4);
+              uint4 h4, l4;
+              tf::split_tf32(fmaf(wi, u.x, wj * v.x), h4.x, l4.x);
+              tf::split_tf32(fmaf(wi, u.y, wj * v.y), h4.y, l4.y);
+              tf::split_tf32(fmaf(wi, u.z, wj * v.z), h4.z, l4.z);
+              tf::split_tf32(fmaf(wi, u.w, wj * v.w), h4.w, l4.w);
+              *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
+              *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
+            }
+            fence_proxy_async_smem();
+            fence_before_thread_sync();
+            row_bar();                          // every row is done with the node block: refill it for the next tile
+            prefetch_nodes(tile + gridDim.x);
+          } else {
+            const int K = op.K, k0 = op.st_k0;
+            const bool div = a.a_div != 0.f;
+            for (int k4 = 0; k4 < (K >> 2); ++k4) {
+              const int k = k0 + 4 * k4;
+              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (live) {
+                const float* src = (k < a.k_src0) ? a.src0 + grow * a.ld0 + k : a.src1 + grow * a.ld1 + (k - a.k_src0);
+                x = ldg_f4(src);
+                if (div) { x.x /= a.a_div; x.y /= a.a_div; x.z /= a.a_div; x.w /= a.a_div; }
+              }
+              uint4 h4, l4;
+              tf::split_tf32(x.x, h4.x, l4.x); tf::split_tf32(x.y, h4.y, l4.y);
+              tf::split_tf32(x.z, h4.z, l4.z); tf::split_tf32(x.w, h4.w, l4.w);
+              *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
+              *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
+            }
+            fence_proxy_async_smem();
+            fence_before_thread_sync();
+          }
+          mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
+          continue;
+        }
+
+        // ---- EV_DRAIN
+        mbar_wait(&bars->acc_ready[sg & (NBAR - 1)], (sg / NBAR) & 1u); ++sg;
+        fence_after_thread_sync();
+        const int kind = op.drain;
+        if (kind == DR_GUMBEL) {
+          float v[16];
+          tmem_ld16(tmem_row + op.acc_col, v);
+          if (live) {
+            const int T = a.T;
+            constexpr int TU = GN_SMALL_OUT - 1;
+            float u[TU];
+            if (a.noise_mode == GN_NOISE_GIVEN) {
+#pragma unroll
+              for (int t = 0; t < TU; ++t) u[t] = (t < T) ? __ldg(a.U + static_cast<size_t>(grow) * T + t) : 0.5f;
+            } else {
+              // one Philox block yields 4 consecutive elements of the (B,E,T) noise tensor
+              const unsigned long long el0 =
+                  (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(grow)) * T;
+              const unsigned long long blk0 = el0 >> 2;
+              const int lead = static_cast<int>(el0 & 3);
+#pragma unroll
+              for (int t = 0; t < TU; ++t) u[t] = 0.5f;
+#pragma unroll
+              for (int bi = 0; bi < (TU + 3 + 3) / 4; ++bi) {
+                if (bi * 4 < lead + T) {
+                  const uint4 r = Philox::block(blk0 + bi, static_cast<uint32_t>(a.stage_index), seed);
+                  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int s4 = 0; s4 < 4; ++s4) {
+                    const int t = bi * 4 + s4 - lead;
+                    const float uu = static_cast<float>(w[s4] >> 8) * (1.0f / 16777216.0f);
+#pragma unroll
+                    for (int tt = 0; tt < TU; ++tt)
+                      if (tt >= bi * 4 - 3 && tt <= bi * 4 + 3 && tt == t) u[tt] = uu;
+                  }
+                }
+              }
+            }
+            // y = (logit + g) / tau, tau = 1/2; dist = softmax(y); factor = sigmoid(.)   (fp32 math as the FFMA path)
+            float y[TU];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int t = 0; t < TU; ++t)
+              if (t < T) {
+                y[t] = (v[t] + __ldg(a.g_bias + t) + gumbel_from_uniform(u[t])) / 0.5f;
+                mx = fmaxf(mx, y[t]);
+              }
+            float den = 0.f;
+#pragma unroll
+            for (int t = 0; t < TU; ++t)
+              if (t < T) { y[t] = expf(y[t] - mx); den += y[t]; }
+            const float fl = carry + __ldg(a.g_bias + T);
+            const float factor = 1.f / (1.f + expf(-fl));
+            float* ef = a.edge_feat + static_cast<size_t>(grow) * T;
+#pragma unroll
+            for (int t = 0; t < TU; ++t)
+              if (t < T) {
+                const float dd = y[t] / den;
+                if (a.dist_out != nullptr) a.dist_out[static_cast<size_t>(grow) * T + t] = dd;
+                ef[t] = factor * dd;
+              }
+          }
+        } else if (kind != DR_NONE) {
+          float scale = 1.f;
+          if (op.rs_idx >= 0) scale = live ? __ldg(a.rs + grow * a.rs_ld + op.rs_idx) : 0.f;
+          const bool to_tmem = kind == DR_TMEM || kind == DR_TMEM_STORE;
+          const bool to_hbm = (kind == DR_STORE || kind == DR_TMEM_STORE) && live;
+          for (int c0 = 0; c0 < op.dn; c0 += 32) {
+            uint32_t r[32];
+            tmem_ld32_nowait(tmem_row + op.acc_col + c0, r);
+            tmem_ld_wait();
+            // partial sums kept in separate accumulators (short accumulation chains in the tensor core) meet in fp32 here
+            for (int pi = 1; pi < op.nsum; ++pi) {
+              uint32_t q[32];
+              tmem_ld32_nowait(tmem_row + op.acc_col + pi * op.sum_stride + c0, q);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+            }
+            if (op.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b = ldg_f4(op.bias + c0 + 4 * q);
+                r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + b.x);
+                r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + b.y);
+                r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + b.z);
+                r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + b.w);
+              }
+            }
+            if (op.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+            }
+            if (op.rs_idx >= 0) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * scale);
+            }
+            if (kind == DR_DOT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                carry = fmaf(__uint_as_float(r[j]), __ldg(a.dot_w + static_cast<size_t>(c0 + j) * a.dot_stride), carry);
+              continue;
+            }
+            if (op.use_bm && live) {
+              for (int t = 0; t < a.bm_T; ++t) {
+                const float st = __ldg(a.rs + grow * a.rs_ld + t);
+                const float* bt = a.bm + static_cast<size_t>(t) * a.bm_ld + op.out_col0 + c0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 b = ldg_f4(bt + 4 * q);
+                  r[4 * q] = __float_as_uint(fmaf(st, b.x, __uint_as_float(r[4 * q])));
+                  r[4 * q + 1] = __float_as_uint(fmaf(st, b.y, __uint_as_float(r[4 * q + 1])));
+                  r[4 * q + 2] = __float_as_uint(fmaf(st, b.z, __uint_as_float(r[4 * q + 2])));
+                  r[4 * q + 3] = __float_as_uint(fmaf(st, b.w, __uint_as_float(r[4 * q + 3])));
+                }
+              }
+            }
+            if (to_hbm) {
+              float* dst = op.out + grow * op.ldo + op.out_col0 + c0;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<uint4*>(dst + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+            }
+            if (to_tmem) {
+              uint32_t lo[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) tf::split_tf32(__uint_as_float(r[j]), r[j], lo[j]);
+              tf::tmem_st32(tmem_row + op.dst_col + c0, r);
+              tf::tmem_st32(tmem_row + op.dst_col + op.dn + c0, lo);
+            }
+          }
+          if (to_tmem) tf::tmem_st_wait();
+        }
+        if (op.arrive) {
+          fence_before_thread_sync();
+          mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
+        }
+      }
+    }
+    if (pair) cp_async_wait<0>();
+  }
+
+  fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) {
+    fence_after_thread_sync();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ===========================================================================================
+// host side: program construction
+// ===========================================================================================
+struct Builder {
+  Args a;
+  size_t wbytes = 0;       // bytes of one tile's weight stream
+  int a0_K = 0, nbuf = 1;  // staged buffer width / count
+  bool node_block = false;
+  Builder() { memset(&a, 0, sizeof(a)); }
+
+  // largest multiple of 8 that divides K and keeps a [N x kc] hi+lo chunk inside one ring stage
+  static int chunk_k(int N, int K) {
+    int kc = static_cast<int>(STAGE_BYTES / 8) / N;
+    kc = kc / 8 * 8;
+    if (kc > K) kc = K;
+    while (kc > 8 && K % kc) kc -= 8;
+    return kc;
+  }
+  Op& add(int a_src, int a_buf_or_col, int K, int N, int acc_col, int accumulate, int wait_n, int signal) {
+    Op& o = a.ops[a.nops++];
+    memset(&o, 0, sizeof(o));
+    o.a_src = static_cast<short>(a_src);
+    if (a_src == A_SMEM) o.a_buf = static_cast<short>(a_buf_or_col); else o.a_col = static_cast<short>(a_buf_or_col);
+    o.K = static_cast<short>(K); o.N = static_cast<short>(N); o.kc = static_cast<short>(chunk_k(N, K));
+    o.acc_col = static_cast<short>(acc_col); o.accumulate = static_cast<short>(accumulate);
+    o.wait_n = static_cast<short>(wait_n); o.signal = static_cast<short>(signal);
+    o.rs_idx = -1;
+    wbytes += static_cast<size_t>(N) * K * 8;
+    return o;
+  }
+  void ev(int type, int op) { a.ev_type[a.nev] = static_cast<unsigned char>(type); a.ev_op[a.nev] = static_cast<unsigned char>(op); ++a.nev; }
+  static void drain_tmem(Op& o, int dn, int relu, const float* bias, int dst_col, int arrive) {
+    o.drain = DR_TMEM; o.dn = static_cast<short>(dn); o.relu = static_cast<short>(relu); o.bias = bias;
+    o.dst_col = static_cast<short>(dst_col); o.arrive = static_cast<short>(arrive);
+  }
+  static void drain_store(Op& o, int dn, int relu, const float* bias, float* out, long long ldo, int col0, int arrive) {
+    o.drain = DR_STORE; o.dn = static_cast<short>(dn); o.relu = static_cast<short>(relu); o.bias = bias;
+    o.out = out; o.ldo = ldo; o.out_col0 = static_cast<short>(col0); o.arrive = static_cast<short>(arrive);
+  }
+};
+
+// Replays the row-thread / issuer protocol: arrivals must equal waits per tile, signals must equal drains, TMEM
+// ranges must fit, and neither side may get NBAR phases ahead of the other (an mbarrier ring would alias).
+static int validate_program(const Args& a) {
+  if (a.nops < 1 || a.nops > MAX_OPS || a.nev < 1 || a.nev > MAX_EV) return GN_E_SHAPE;
+  int waits = 0, signals = 0;
+  for (int o = 0; o < a.nops; ++o) {
+    const Op& op = a.ops[o];
+    if (op.N < 16 || op.N > 256 || (op.N & 15) || op.K < 8 || (op.K & 7) || op.kc < 8 || (op.kc & 7) || op.K % op.kc) return GN_E_SHAPE;
+    if (static_cast<uint32_t>(op.N) * op.kc * 8 > STAGE_BYTES) return GN_E_SHAPE;
+    if (op.acc_col < 0 || op.acc_col + op.N > 512) return GN_E_SHAPE;
+    if (op.a_src == A_TMEM && (op.a_col < 0 || op.a_col + 2 * op.K > 512)) return GN_E_SHAPE;
+    if (op.a_src == A_SMEM && static_cast<uint32_t>(op.K) * 128 * 4 > a.a0_half_bytes) return GN_E_SHAPE;
+    if (op.signal) {
+      if (op.drain == DR_GUMBEL) { if (op.dn != 16) return GN_E_SHAPE; }
+      else if (op.drain != DR_NONE && ((op.dn & 31) || op.dn > op.N || op.dn < 32)) return GN_E_SHAPE;
+      if (op.nsum > 1 && (op.sum_stride < op.dn || op.acc_col + (op.nsum - 1) * op.sum_stride + op.dn > 512)) return GN_E_SHAPE;
+      if ((op.drain == DR_TMEM || op.drain == DR_TMEM_STORE) && (op.dst_col < 0 || op.dst_col + 2 * op.dn > 512)) return GN_E_SHAPE;
+      if ((op.drain == DR_STORE || op.drain == DR_TMEM_STORE) &&
+          (!op.out || (op.ldo & 3) || (op.out_col0 & 3) || (reinterpret_cast<uintptr_t>(op.out) & 15))) return GN_E_ALIGN;
+      if (op.bias && (reinterpret_cast<uintptr_t>(op.bias) & 15)) return GN_E_ALIGN;
+      ++signals;
+    } else if (op.arrive) return GN_E_SHAPE;
+    waits += op.wait_n;
+  }
+  int arrivals = 0, drains = 0;
+  for (int e = 0; e < a.nev; ++e) {
+    const Op& op = a.ops[a.ev_op[e]];
+    if (a.ev_type[e] == EV_STAGE) ++arrivals;
+    else { ++drains; if (!op.signal) return GN_E_SHAPE; arrivals += op.arrive; }
+  }
+  if (arrivals != waits || drains != signals) return GN_E_SHAPE;
+  // run-ahead check over two consecutive tiles: greedy row threads against a lazy issuer and vice versa
+  for (int greedy_rows = 0; greedy_rows < 2; ++greedy_rows) {
+    int io = 0, ie = 0;                       // issuer op index / row event index (over 2 tiles)
+    int arr = 0, cons = 0, sig = 0, dr = 0;   // produced arrivals, consumed arrivals, produced signals, consumed signals
+    int pend_wait = a.ops[0].wait_n;
+    const int NO = 2 * a.nops, NE = 2 * a.nev;
+    auto step_rows = [&]() -> bool {
+      if (ie >= NE) return false;
+      const int e = ie % a.nev;
+      const Op& op = a.ops[a.ev_op[e]];
+      if (a.ev_type[e] == EV_STAGE) { ++arr; ++ie; return true; }
+      if (dr < sig) { ++dr; arr += op.arrive; ++ie; return true; }
+      return false;
+    };
+    auto step_issuer = [&]() -> bool {
+      if (io >= NO) return false;
+      if (pend_wait > 0) { if (cons < arr) { ++cons; --pend_wait; return true; } return false; }
+      sig += a.ops[io % a.nops].signal;
+      ++io;
+      if (io < NO) pend_wait = a.ops[io % a.nops].wait_n;
+      return true;
+    };
+    for (;;) {
+      bool moved = false;
+      if (greedy_rows) { while (step_rows()) moved = true; if (step_issuer()) moved = true; }
+      else { while (step_issuer()) moved = true; if (step_rows()) moved = true; }
+      if (arr - cons >= NBAR || sig - dr >= NBAR) return GN_E_SHAPE;
+      if (!moved) break;
+    }
+    if (io != NO || ie != NE) return GN_E_SHAPE;           // deadlock
+  }
+  return GN_OK;
+}
+
+static int launch(Builder& b, long long R, long long ntiles, const unsigned char* wstream, const char* name, cudaStream_t st) {
+  Args& a = b.a;
+  a.R = R; a.ntiles = ntiles; a.wstream = wstream;
+  a.a0_half_bytes = static_cast<uint32_t>(b.a0_K) * 128 * 4;
+  a.a0_buf_bytes = 2 * a.a0_half_bytes;
+  a.off_a0 = 0;
+  a.off_ring = static_cast<uint32_t>(b.nbuf) * a.a0_buf_bytes;
+  const uint32_t node_bytes = b.node_block ? 2u * MAXN * NLD * 4 : 0u;
+  const uint32_t fixed = a.off_ring + node_bytes + static_cast<uint32_t>(sizeof(Bars)) + 128;
+  if (fixed + 2 * STAGE_BYTES > 227 * 1024) return GN_E_SHAPE;
+  int ns = static_cast<int>((227 * 1024 - fixed) / STAGE_BYTES);
+  if (ns > 8) ns = 8;
+  a.nstage = ns;
+  a.off_node = a.off_ring + static_cast<uint32_t>(ns) * STAGE_BYTES;
+  a.off_bar = (a.off_node + node_bytes + 127u) & ~127u;
+  const uint32_t smem = a.off_bar + static_cast<uint32_t>(sizeof(Bars));
+  int rc = validate_program(a);
+  if (rc != GN_OK) return rc;
+  if (!wstream || (reinterpret_cast<uintptr_t>(wstream) & 15)) return GN_E_NULL;
+  cudaError_t e = cudaFuncSetAttribute(chain_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int grid = ntiles < GN_SM_COUNT ? static_cast<int>(ntiles) : GN_SM_COUNT;
+  {
+    ProfScope ps__(name, st);
+    chain_tf32_kernel<<<grid, THREADS, smem, st>>>(a);
+  }
+  GN_LAUNCH_CHECK();
+  return GN_OK;
+}
+
+}  // namespace tfe
+
+using namespace tfe;
+
+// ---- per-edge chain: init_MLP -> [MLP_distribution | MLP_factor] -> Gumbel softmax / sigmoid (:41-53)
+//   G1 64->128 (ReLU)  G2 128->64 (z)  G3f 64->128 (factor hidden, ReLU; its 128->1 head is a dot in the drain)
+//   G3d 64->128 (distribution hidden, ReLU)  G4 128->16 (T logits)  -> epilogue
+// TMEM columns: acc1 0 | A1 128,256 | acc2 384 | A2 0,64 | acc3f 128 | acc3d 256 | A3 0,128 | acc4 384
+bool edge_chain_tf32_fits(bool pair, int N, int T) {
+  if (T < 1 || T > GN_SMALL_OUT - 1) return false;
+  if (!pair) return true;
+  const int E = N * N;
+  if (E >= 128) return N <= MAXN;
+  return (127 / E + 2) * N <= MAXN;
+}
+
+int launch_edge_chain_tf32(bool pair, const float* edges, const float* xprime, const float* pq,
+                           int N, int E, int T, long long R, const gn_stage_weights* w,
+                           const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
+                           int stage_index, float* dist_out, float* edge_feat, cudaStream_t st) {
+  if (!w->tf_chain_w) return GN_E_NULL;
+  if (R <= 0) return GN_OK;
+  Builder b;
+  Args& a = b.a;
+  b.a0_K = 64; b.nbuf = 1; b.node_block = pair;
+  Op& g1 = b.add(A_SMEM, 0, 64, 128, 0, 0, 1, 1);
+  Builder::drain_tmem(g1, 128, 1, w->init_b0, 128, 1);
+  Op& g2 = b.add(A_TMEM, 128, 128, 64, 384, 0, 1, 1);
+  Builder::drain_tmem(g2, 64, 0, w->init_b1, 0, 1);
+  Op& g3f = b.add(A_TMEM, 0, 64, 128, 128, 0, 1, 1);
+  g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; g3f.bias = w->df_b0 + 128; g3f.arrive = 0;
+  Op& g3d = b.add(A_TMEM, 0, 64, 128, 256, 0, 0, 1);
+  Builder::drain_tmem(g3d, 128, 1, w->df_b0, 0, 1);
+  Op& g4 = b.add(A_TMEM, 0, 128, 16, 384, 0, 1, 1);
+  g4.drain = DR_GUMBEL; g4.dn = 16; g4.arrive = 0;
+  b.ev(EV_STAGE, 0);
+  for (int o = 0; o < 5; ++o) b.ev(EV_DRAIN, o);
+  a.stage_mode = pair ? ST_PAIR : ST_ROWS;
+  a.src0 = edges; a.ld0 = 64; a.k_src0 = 64; a.src1 = nullptr; a.ld1 = 0; a.a_div = 0.f;
+  a.xprime = xprime; a.pq = pq; a.att_b0 = w->att_b0; a.att_w1 = w->att_w1; a.att_b1 = w->att_b1;
+  a.N = N; a.E = E;
+  a.tps = (pair && E >= 128) ? (E + 127) / 128 : 0;
+  a.dot_w = w->df_w1 + 128 * GN_SMALL_OUT + T; a.dot_stride = GN_SMALL_OUT;
+  a.g_bias = w->df_b1; a.T = T;
+  a.U = U; a.noise_mode = noise_mode; a.seed = seed; a.scene_offset = scene_offset; a.stage_index = stage_index;
+  a.dist_out = dist_out; a.edge_feat = edge_feat;
+  const long long ntiles = a.tps ? (R / E) * a.tps : (R + 127) / 128;
+  return launch(b, R, ntiles, static_cast<const unsigned char*>(w->tf_chain_w),
+                pair ? "edge_chain_pair_tf32" : "edge_chain_tf32", st);
+}
+
+// ---- node prologue: x' = node2edge_start_mlp(h) (D -> 256 -> 64, :84,:125), pq = split attention layer 0 (:80,:134)
+// the 256-wide hidden layer runs as two 128-column halves feeding the second Linear as two K = 128 chunks
+// TMEM columns: acc 0 | A_hid 128,256 | acc_x 384 | A_x 0,64 | acc_pq 448
+bool node_pre_tf32_fits(int D) { return D >= 8 && D <= 128 && (D & 7) == 0; }
+
+int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weights* w, float* xprime, float* pq,
+                         cudaStream_t st) {
+  if (!w->tf_pre_w) return GN_E_NULL;
+  if (R <= 0) return GN_OK;
+  Builder b;
+  Args& a = b.a;
+  b.a0_K = D; b.nbuf = 1;
+  Op& s0a = b.add(A_SMEM, 0, D, 128, 0, 0, 1, 1);
+  Builder::drain_tmem(s0a, 128, 1, w->node_b0, 128, 1);
+  b.add(A_TMEM, 128, 128, 64, 384, 0, 1, 0);
+  Op& s0b = b.add(A_SMEM, 0, D, 128, 0, 0, 0, 1);
+  Builder::drain_tmem(s0b, 128, 1, w->node_b0 + 128, 128, 1);
+  Op& s1b = b.add(A_TMEM, 128, 128, 64, 384, 1, 1, 1);
+  s1b.drain = DR_TMEM_STORE; s1b.dn = 64; s1b.relu = 0; s1b.bias = w->node_b1; s1b.dst_col = 0; s1b.arrive = 1;
+  s1b.out = xprime; s1b.ldo = 64; s1b.out_col0 = 0;
+  Op& s2 = b.add(A_TMEM, 0, 64, 64, 448, 0, 1, 1);
+  Builder::drain_store(s2, 64, 0, nullptr, pq, 64, 0, 0);
+  b.ev(EV_STAGE, 0); b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 2); b.ev(EV_DRAIN, 3); b.ev(EV_DRAIN, 4);
+  a.stage_mode = ST_ROWS; a.src0 = h; a.ld0 = D; a.k_src0 = D;
+  return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_pre_w), "node_pre_tf32", st);
+}
+
+// ---- pairwise aggregation, first half of the collapse: P[:, t*128:(t+1)*128] = h W0_t^T (bias added per edge later)
+bool agg_in_tf32_fits(int D, int T) { return D >= 8 && D <= 128 && (D & 7) == 0 && T >= 1 && T <= MAX_OPS; }
+
+int launch_agg_in_tf32(const float* h, long long R, int D, int T, const gn_stage_weights* w, float* P, cudaStream_t st) {
+  if (!w->tf_aggin_w) return GN_E_NULL;
+  if (R <= 0) return GN_OK;
+  Builder b;
+  Args& a = b.a;
+  b.a0_K = D; b.nbuf = 1;
+  b.ev(EV_STAGE, 0);
+  for (int t = 0; t < T; ++t) {
+    Op& o = b.add(A_SMEM, 0, D, 128, (t & 1) * 128, 0, (t == 0 || t >= 2) ? 1 : 0, 1);
+    Builder::drain_store(o, 128, 0, nullptr, P, static_cast<long long>(T) * 128, 0, (t + 2 < T) ? 1 : 0);
+    o.out = P + t * 128;                 // column block t (out_col0 is a short: keep it 0)
+    b.ev(EV_DRAIN, t);
+  }
+  a.stage_mode = ST_ROWS; a.src0 = h; a.ld0 = D; a.k_src0 = D;
+  return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_aggin_w), "agg_in_tf32", st);
+}
+
+// ---- pairwise aggregation, second half: agg = G W1cat^T + S b1, K = T*128 streamed through two staged buffers
+bool agg_out_tf32_fits(int D, int T) {
+  return D >= 32 && D <= 128 && (D & 31) == 0 && T >= 1 && 2 * T <= MAX_OPS && 4 * T + 2 <= MAX_EV;
+}
+
+int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int T, const gn_stage_weights* w,
+                        float* agg, cudaStream_t st) {
+  if (!w->tf_aggout_w) return GN_E_NULL;
+  if (R <= 0) return GN_OK;
+  Builder b;
+  Args& a = b.a;
+  b.a0_K = 64; b.nbuf = 2;
+  const int n = 2 * T;                    // K chunks of 64
+  // chunk c accumulates into accumulator c % NACC (columns 128 apart): four short chains instead of one long one,
+  // summed in fp32 by the final drain (the tensor core's accumulation rounds toward zero)
+  const int NACC = n < 4 ? n : 4;
+  for (int c = 0; c < n; ++c) {
+    Op& o = b.add(A_SMEM, c & 1, 64, D, (c % NACC) * 128, c >= NACC ? 1 : 0, 1, 1);
+    o.st_k0 = static_cast<short>(64 * c);
+    if (c == n - 1) {
+      // the last chunk goes to accumulator 0, where the drain starts summing (any accumulator may take it)
+      Builder::drain_store(o, D, 0, nullptr, agg, D, 0, 0);
+      o.acc_col = 0; o.accumulate = 1; o.nsum = static_cast<short>(NACC); o.sum_stride = 128;
+      o.use_bm = 1;
+    } else {
+      o.drain = DR_NONE;
+    }
+  }
+  // rows stage two chunks ahead; a buffer is refilled once the MMAs that read it have completed
+  b.ev(EV_STAGE, 0);
+  if (n > 1) b.ev(EV_STAGE, 1);
+  for (int c = 0; c < n; ++c) {
+    b.ev(EV_DRAIN, c);
+    if (c + 2 < n) b.ev(EV_STAGE, c + 2);
+  }
+  a.stage_mode = ST_ROWS; a.src0 = G; a.ld0 = static_cast<long long>(T) * 128; a.k_src0 = T * 128;
+  a.rs = S; a.rs_ld = 16; a.bm = w->agg_b1; a.bm_T = T; a.bm_ld = D;
+  return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_aggout_w), "agg_out_tf32", st);
+}
+
+// ---- hyper edge_aggregation as written (:259-265): ef = sum_t edge_feat_t * (W1_t relu(W0_t eo + b0_t) + b1_t)
+// TMEM columns: acc_hid 0 | A_hid 128,256 | acc_ef 384
+bool hyper_agg_tf32_fits(int D, int T) {
+  return D >= 32 && D <= 128 && (D & 31) == 0 && T >= 1 && 2 * T <= MAX_OPS;
+}
+
+int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, int D, int T,
+                          const gn_stage_weights* w, float* ef, cudaStream_t st) {
+  if (!w->tf_hagg_w) return GN_E_NULL;
+  if (R <= 0) return GN_OK;
+  Builder b;
+  Args& a = b.a;
+  b.a0_K = D; b.nbuf = 1;
+  b.ev(EV_STAGE, 0);
+  for (int t = 0; t < T; ++t) {
+    Op& g1 = b.add(A_SMEM, 0, D, 128, 0, 0, t == 0 ? 1 : 0, 1);
+    Builder::drain_tmem(g1, 128, 1, w->agg_b0 + t * 128, 128, 1);
+    g1.rs_idx = static_cast<short>(t);
+    b.ev(EV_DRAIN, 2 * t);
+    // two short accumulation chains (even / odd t) when they fit beside A_hid, summed in fp32 by the final drain
+    const int NACC = (D <= 64 && T >= 2) ? 2 : 1;
+    const bool last = t == T - 1;
+    Op& g2 = b.add(A_TMEM, 128, 128, D, last ? 384 : 384 + (t % NACC) * 64, (last ? t > 0 : t >= NACC) ? 1 : 0, 1, last ? 1 : 0);
+    if (last) {
+      Builder::drain_store(g2, D, 0, nullptr, ef, D, 0, 0);
+      g2.nsum = static_cast<short>(NACC); g2.sum_stride = 64;
+      g2.use_bm = 1;
+      b.ev(EV_DRAIN, 2 * t + 1);
+    }
+  }
+  a.stage_mode = ST_ROWS; a.src0 = eo; a.ld0 = D; a.k_src0 = D;
+  a.rs = edge_feat; a.rs_ld = T; a.bm = w->agg_b1; a.bm_T = T; a.bm_ld = D;
+  return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_hagg_w), "hyper_agg_tf32", st);
+}
+
+// ---- closing MLP on [agg | h] / N (:120,:355,:195,:441): 2D -> 128 (ReLU) -> Dout
+bool node_post_tf32_fits(int D, int Dout, long long ld_out, const float* node_out) {
+  return D >= 4 && D <= 64 && (D & 3) == 0 && Dout >= 32 && Dout <= 128 && (Dout & 31) == 0 && (ld_out & 3) == 0 &&
+         (reinterpret_cast<uintptr_t>(node_out) & 15) == 0;
+}
+
+int launch_node_post_tf32(const float* agg, const float* h, long long R, int D, int Nagents, int Dout,
+                          const gn_stage_weights* w, float* node_out, long long ld_out, cudaStream_t st) {
+  if (!w->tf_post_w) return GN_E_NULL;
+  if (R <= 0) return GN_OK;
+  Builder b;
+  Args& a = b.a;
+  b.a0_K = 2 * D; b.nbuf = 1;
+  Op& p0 = b.add(A_SMEM, 0, 2 * D, 128, 0, 0, 1, 1);
+  Builder::drain_tmem(p0, 128, 1, w->post_b0, 128, 1);
+  Op& p1 = b.add(A_TMEM, 128, 128, Dout, 384, 0, 1, 1);
+  Builder::drain_store(p1, Dout, 0, w->post_b1, node_out, ld_out, 0, 0);
+  b.ev(EV_STAGE, 0); b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 1);
+  a.stage_mode = ST_ROWS; a.src0 = agg; a.ld0 = D; a.k_src0 = D; a.src1 = h; a.ld1 = D;
+  a.a_div = static_cast<float>(Nagents);
+  return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_post_w), "node_post_tf32", st);
+}
+
+}  // namespace gn

@@ -75,6 +75,27 @@ struct NodeChainArgs {
 };
 int launch_node_chain_tc(const NodeChainArgs& a, const char* name, cudaStream_t st);
 
+// 3xTF32 chains on tcgen05 (gn_chain_tf32.cu): the fp32-grade tensor-core path, precision GN_TF32X3
+bool edge_chain_tf32_fits(bool pair, int N, int T);
+int launch_edge_chain_tf32(bool pair, const float* edges, const float* xprime, const float* pq,
+                           int N, int E, int T, long long R, const gn_stage_weights* w,
+                           const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
+                           int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
+bool node_pre_tf32_fits(int D);
+int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weights* w, float* xprime, float* pq,
+                         cudaStream_t st);
+bool agg_in_tf32_fits(int D, int T);
+int launch_agg_in_tf32(const float* h, long long R, int D, int T, const gn_stage_weights* w, float* P, cudaStream_t st);
+bool agg_out_tf32_fits(int D, int T);
+int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int T, const gn_stage_weights* w,
+                        float* agg, cudaStream_t st);
+bool hyper_agg_tf32_fits(int D, int T);
+int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, int D, int T,
+                          const gn_stage_weights* w, float* ef, cudaStream_t st);
+bool node_post_tf32_fits(int D, int Dout, long long ld_out, const float* node_out);
+int launch_node_post_tf32(const float* agg, const float* h, long long R, int D, int Nagents, int Dout,
+                          const gn_stage_weights* w, float* node_out, long long ld_out, cudaStream_t st);
+
 // stage driver (gn_stage_simt.cu)
 int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h, const float* H,
               const float* U, float* node_out, float* dist_out, void* ws, size_t ws_bytes, cudaStream_t st);

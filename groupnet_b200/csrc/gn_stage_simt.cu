@@ -876,7 +876,7 @@ static int make_plan(const gn_stage_cfg* c, StagePlan& p) {
   if (c->Dout < 1 || c->T < 1 || c->T > GN_SMALL_OUT - 1) return GN_E_SHAPE;
   if (c->pairwise) { if (c->E != c->N * c->N) return GN_E_SHAPE; }
   else if (c->E < 1 || c->E > GN_MAX_AGENTS) return GN_E_SHAPE;
-  if (c->precision != GN_FP32 && c->precision != GN_BF16_TC) return GN_E_PRECISION;
+  if (c->precision != GN_FP32 && c->precision != GN_BF16_TC && c->precision != GN_TF32X3) return GN_E_PRECISION;
   p.Dp = round_up(c->D, 16);
   p.Dc = c->D <= 64 ? 64 : round_up(c->D, 128);   // multiple of the TN the agg_w1t GEMMs use
   p.K2p = round_up(2 * c->D, 16);
@@ -1065,6 +1065,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   if (c->noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && (reinterpret_cast<uintptr_t>(U) & 7)) return GN_E_SHAPE;
   if (!c->pairwise && !H) return GN_E_NULL;
   const bool tcn = p.tc_nodes;
+  const bool tf = c->precision == GN_TF32X3;       // fp32-grade tensor-core chains where the shape fits
   const bool fused_agg = tcn && c->pairwise && pair_agg_fits(N, D, T);   // P / G stay on chip
   if (tcn && (!w->tc_node_w0 || !w->tc_node_w1 || !w->tc_att_wpq || !w->tc_agg_w0 || !w->tc_agg_w1 ||
               !w->tc_post_w0 || !w->tc_post_w1)) return GN_E_NULL;
@@ -1110,6 +1111,9 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
         GN_TRY(launch_tc_linear(a, "agg_in_tc", st));
       }
     }
+  } else if (tf && w->tf_pre_w && node_pre_tf32_fits(D) && (!c->pairwise || (w->tf_aggin_w && agg_in_tf32_fits(D, T)))) {
+    GN_TRY(launch_node_pre_tf32(h, R, D, w, xprime, pq, st));
+    if (c->pairwise) GN_TRY(launch_agg_in_tf32(h, R, D, T, w, P, st));
   } else {
     constexpr int TM = 64, LD = TM + 4;
     size_t smem = static_cast<size_t>(p.Dp + 128 + 64) * LD * 4 + 2 * KC * 128 * 4;
@@ -1123,7 +1127,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
 
   // ---- k2: node2edge (fused into the tensor-core chain for the pairwise bf16 path)
   const bool tc = c->precision == GN_BF16_TC;
-  const bool fuse_pair = tc && c->pairwise && edge_chain_pair_fits(N);
+  const bool tf_chain = tf && w->tf_chain_w != nullptr;
+  const bool fuse_pair = c->pairwise && ((tc && edge_chain_pair_fits(N)) || (tf_chain && edge_chain_tf32_fits(true, N, T)));
   const bool out_aligned = (reinterpret_cast<uintptr_t>(node_out) & 15) == 0;   // fused tails store 128-bit rows
   const bool fused_hyper64 = tcn && !c->pairwise && out_aligned && hyper_fused64_fits(N, E, D, T, c->Dout, ld_out);
   const bool fused_hyper = fused_hyper64 || (tcn && !c->pairwise && hyper_fused_fits(N, E, D, T));   // eo / ef never leave the SM
@@ -1136,6 +1141,9 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   if (tc) {
     GN_TRY(launch_edge_chain_tc(fuse_pair, edges, xprime, pq, N, E, T, RE, w, U, c->noise_mode,
                                 c->seed, c->scene_offset, c->stage_index, dist_out, efeat, st));
+  } else if (tf_chain) {
+    GN_TRY(launch_edge_chain_tf32(fuse_pair, edges, xprime, pq, N, E, T, RE, w, U, c->noise_mode,
+                                  c->seed, c->scene_offset, c->stage_index, dist_out, efeat, st));
   } else {
     constexpr int TM = 128, LD = TM + 4;
     size_t smem = (static_cast<size_t>(64 + 128) * LD + 2 * KC * 128 + 256 * GN_SMALL_OUT +
@@ -1180,6 +1188,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
       a.rowscale = efeat; a.rs_ld = T; a.bias_mat = w->agg_b1; a.bm_T = T; a.bm_ld = D;
       a.out = ef; a.out_is_f32 = 1; a.ldo = D;
       GN_TRY(launch_tc_linear(a, "agg_out_tc", st));
+    } else if (tf && w->tf_hagg_w && hyper_agg_tf32_fits(D, T)) {
+      GN_TRY(launch_hyper_agg_tf32(eo, efeat, RE, D, T, w, ef, st));
     } else if (D <= 64) {
       constexpr int TM = 128, LD = TM + 4;
       size_t smem = (static_cast<size_t>(p.Dp + 128) * LD + 2 * KC * 128 + TM * 16) * 4;
@@ -1241,6 +1251,10 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     a.W = static_cast<const __nv_bfloat16*>(w->tc_post_w1); a.Ntot = c->Dout; a.N = c->Dout;
     a.bias = w->post_b1; a.out = node_out; a.out_is_f32 = 1; a.ldo = ld_out;
     GN_TRY(launch_tc_linear(a, "post_mlp1_tc", st));
+  } else if (tf && w->tf_post_w && node_post_tf32_fits(D, c->Dout, ld_out, node_out) &&
+             (!c->pairwise || (w->tf_aggout_w && agg_out_tf32_fits(D, T)))) {
+    if (c->pairwise) GN_TRY(launch_agg_out_tf32(G, S, R, D, T, w, agg, st));
+    GN_TRY(launch_node_post_tf32(agg, h, R, D, N, c->Dout, w, node_out, ld_out, st));
   } else {
     constexpr int TM = 64, LD = TM + 4;
     size_t smem = (static_cast<size_t>(p.K2p + 128 + 64) * LD + 2 * KC * 128 + TM * 16) * 4;
@@ -1282,6 +1296,16 @@ size_t stage_workspace_bytes(const gn_stage_cfg* c) {
 int stage_launch_count(const gn_stage_cfg* c) {
   StagePlan p;
   if (make_plan(c, p) != GN_OK) return 0;
+  if (c->precision == GN_TF32X3) {
+    // upper bound when every chain fits (weights present): pre (+P), chain (node2edge fused for the pairwise layer),
+    // aggregation, post
+    const bool pre = node_pre_tf32_fits(c->D) && (!c->pairwise || agg_in_tf32_fits(c->D, c->T));
+    const bool post = node_post_tf32_fits(c->D, c->Dout, c->out_ld > 0 ? c->out_ld : c->Dout, nullptr) &&
+                      (!c->pairwise || agg_out_tf32_fits(c->D, c->T));
+    const int fused_tf = (c->pairwise && edge_chain_tf32_fits(true, c->N, c->T)) ? 1 : 0;
+    if (c->pairwise) return (pre ? 2 : 1) + (2 - fused_tf) + 1 + (post ? 2 : 1);
+    return 1 + 1 + 1 + 1 + 1 + 1;
+  }
   const int fused = (c->precision == GN_BF16_TC && c->pairwise && edge_chain_pair_fits(c->N)) ? 1 : 0;
   if (!p.tc_nodes) return (c->pairwise ? 5 : 6) - fused;
   const int chunks = (c->T * 128 + 255) / 256;

@@ -29,6 +29,9 @@ from . import _lib, ops
 from .packing import PackCache
 
 _MASK64 = (1 << 64) - 1
+# "fp32": FFMA kernels (1e-5); "tf32": the same 1e-5 contract on tensor cores (3xTF32 tcgen05 chains);
+# "bf16": bf16 tcgen05 operands, fp32 accumulation (2e-2)
+_PRECISION = {"fp32": _lib.GN_FP32, "bf16": _lib.GN_BF16_TC, "tf32": _lib.GN_TF32X3}
 _PHILOX_CALL_STRIDE = 0x9E3779B97F4A7C15        # seed of call k = philox_seed + k * stride (mod 2^64)
 
 
@@ -158,7 +161,7 @@ class _MessagePassingLayer(nn.Module):
         return t
 
     def set_precision(self, precision: str):
-        if precision not in ("fp32", "bf16"):
+        if precision not in ("fp32", "bf16", "tf32"):
             raise ValueError(precision)
         self.precision = precision
         return self
@@ -229,7 +232,7 @@ class _MessagePassingLayer(nn.Module):
         cfg = _lib.StageCfg()
         cfg.N, cfg.D, cfg.E, cfg.T = n, d, e, t
         cfg.pairwise = 1 if self._pairwise else 0
-        cfg.precision = _lib.GN_BF16_TC if self.precision == "bf16" else _lib.GN_FP32
+        cfg.precision = _PRECISION[self.precision]
         cfg.noise_mode = (_lib.GN_NOISE_GIVEN if us is not None else
                           _lib.GN_NOISE_PHILOX_DEVICE_SEED if seed_dev is not None else _lib.GN_NOISE_PHILOX)
         cfg.seed = seed
@@ -294,7 +297,7 @@ class _MessagePassingLayer(nn.Module):
         cfg = _lib.StageCfg()
         cfg.B, cfg.N, cfg.D, cfg.E, cfg.T = batch, n, self.h_dim, e, self.edge_types
         cfg.Dout, cfg.pairwise = self.bottleneck_dim, 1 if self._pairwise else 0
-        cfg.precision = _lib.GN_BF16_TC if self.precision == "bf16" else _lib.GN_FP32
+        cfg.precision = _PRECISION[self.precision]
         return ops.stage_launch_count(cfg) * max(self.nmp_layers, 1)
 
 

@@ -167,6 +167,53 @@ def hyper_fused_stream(agg_params, d: int) -> torch.Tensor:
     return torch.cat(parts).contiguous()
 
 
+# ---------------------------------------------------------------------------
+# 3xTF32 weight streams (csrc/gn_chain_tf32.cu, csrc/gn_tf32.cuh)
+# ---------------------------------------------------------------------------
+TF_STAGE_BYTES = 16384
+
+
+def tf32_split(w: torch.Tensor):
+    """w (fp32) -> (hi, lo): hi = w rounded to tf32 (11 significand bits, nearest, ties away in magnitude),
+    lo = w - hi rounded the same way.  Both are fp32 tensors whose low 13 bits are zero."""
+    def rnd(x):
+        bits = x.contiguous().view(torch.int32)
+        return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+    hi = rnd(w)
+    return hi, rnd(w - hi)
+
+
+def tf_chunk_k(n: int, k: int) -> int:
+    """Largest multiple of 8 that divides K and keeps an (N x kc) hi+lo chunk inside one 16 KB ring stage;
+    must match tfe::Builder::chunk_k."""
+    kc = (TF_STAGE_BYTES // 8) // n // 8 * 8
+    kc = min(kc, k)
+    while kc > 8 and k % kc:
+        kc -= 8
+    return kc
+
+
+def _canon32(m: torch.Tensor) -> torch.Tensor:
+    """(R, K) fp32 -> flat, canonical K-major operand with 32-bit elements [K/4][R][4]."""
+    r, k = m.shape
+    return m.reshape(r, k // 4, 4).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def tf_stream(mats) -> torch.Tensor:
+    """Weight stream of a chain: for every nn.Linear.weight (N, K) in consumption order, K chunks of kc columns,
+    each chunk = canonical hi copy followed by canonical lo copy."""
+    parts = []
+    for w in mats:
+        n, k = w.shape
+        assert n % 16 == 0 and 16 <= n <= 256 and k % 8 == 0, (n, k)
+        kc = tf_chunk_k(n, k)
+        hi, lo = tf32_split(w.contiguous())
+        for c in range(k // kc):
+            parts.append(_canon32(hi[:, c * kc:(c + 1) * kc].contiguous()))
+            parts.append(_canon32(lo[:, c * kc:(c + 1) * kc].contiguous()))
+    return torch.cat(parts).contiguous()
+
+
 def agg_out_cols(d: int) -> Tuple[int, int]:
     """(Dc, TN) of the aggregation output GEMM; must match make_plan() in
     csrc/gn_stage_simt.cu."""
@@ -272,6 +319,30 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
                     dev(post_mod.layers[1].weight), dev(post_mod.layers[1].bias))))
             out["tc_hfuse_w"] = stream.contiguous()
 
+    # fp32-grade tensor-core path (GN_TF32X3): 3xTF32 weight streams of the chains whose shape fits
+    # (the *_tf32_fits() predicates of csrc/gn_chain_tf32.cu; absent streams fall back to the FFMA kernels)
+    w4 = torch.zeros(16, 128, dtype=torch.float32, device=device)
+    w4[:t] = dev(dist[1].weight)
+    out["tf_chain_w"] = tf_stream([dev(init[0].weight), dev(init[1].weight), dev(fac[0].weight),
+                                   dev(dist[0].weight), w4])
+    if d % 8 == 0 and d <= 128:
+        nw0, nw1 = dev(node[0].weight), dev(node[1].weight)
+        out["tf_pre_w"] = tf_stream([nw0[:128], nw1[:, :128], nw0[128:], nw1[:, 128:],
+                                     torch.cat((w0[:, :64], w0[:, 64:]), dim=0)])
+        if layer._pairwise:
+            out["tf_aggin_w"] = tf_stream([dev(m.layers[0].weight) for m in agg])
+    if d % 32 == 0 and d <= 128:
+        if layer._pairwise:
+            w1cat = torch.cat([dev(m.layers[1].weight) for m in agg], dim=1)      # (D, T*128)
+            out["tf_aggout_w"] = tf_stream([w1cat[:, 64 * c:64 * (c + 1)] for c in range(2 * t)])
+        else:
+            mats = []
+            for m in agg:
+                mats += [dev(m.layers[0].weight), dev(m.layers[1].weight)]
+            out["tf_hagg_w"] = tf_stream(mats)
+    if d % 4 == 0 and d <= 64 and dout % 32 == 0 and dout <= 128:
+        out["tf_post_w"] = tf_stream([dev(post_mod.layers[0].weight), dev(post_mod.layers[1].weight)])
+
     out["post_w0t"] = _kmajor(dev(post_mod.layers[0].weight), k2p, 128, 128)
     out["post_b0"] = dev(post_mod.layers[0].bias)
     out["post_w1t"] = _kmajor(dev(post_mod.layers[1].weight), 128, doutc, 64)
@@ -292,6 +363,7 @@ class PackedStage:
                 setattr(self.struct, name, C.c_void_p(0))
                 continue
             assert tens.is_contiguous() and tens.dtype == (torch.bfloat16 if name.startswith("tc_") else torch.float32)
+            assert tens.data_ptr() % 16 == 0
             setattr(self.struct, name, C.c_void_p(tens.data_ptr()))
 
 

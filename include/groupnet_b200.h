@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 2     /* 2: gn_stage_weights gained tc_hfuse_w, tc_npre_w */
+#define GN_ABI_VERSION 3     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams */
 
 #define GN_MAX_AGENTS 64      /* N <= 64: one 64-bit membership word per hyperedge */
 #define GN_MAX_SCALES 8
@@ -50,7 +50,10 @@ enum gn_error {
 
 enum gn_precision {
   GN_FP32 = 0,           /* fp32 FFMA everywhere: the 1e-5 parity path */
-  GN_BF16_TC = 1         /* bf16 tcgen05/TMEM GEMMs for the per-edge MLP chain, fp32 accumulate (2e-2) */
+  GN_BF16_TC = 1,        /* bf16 tcgen05/TMEM GEMMs for the per-edge MLP chain, fp32 accumulate (2e-2) */
+  GN_TF32X3 = 2          /* fp32-grade tensor-core path: every Linear as three kind::tf32 tcgen05 MMAs on hi/lo
+                            split operands, fp32 accumulate and fp32 epilogues (1e-5, like GN_FP32); shapes the
+                            tensor-core chains do not cover run the GN_FP32 kernels */
 };
 
 enum gn_noise_mode {
@@ -124,6 +127,19 @@ typedef struct gn_stage_weights {
    * node W0[:, 64c:64c+64] (256 x 64) for c = 0..3, b0 (hi,lo) block (256 x 16), [W1 | b1 (hi,lo)] (64 x 272),
    * [Wp ; Wq] (64 x 64) */
   const void* tc_npre_w;
+  /* weight streams of the 3xTF32 chains (csrc/gn_chain_tf32.cu; required when precision == GN_TF32X3 for the
+   * chains whose shape fits, else may be NULL).  A stream is the Linears of one chain in consumption order; each
+   * nn.Linear.weight [N][K] is cut along K into chunks of kc = the largest multiple of 8 that divides K with
+   * N*kc*8 <= 16384, and a chunk is its tf32 "hi" copy followed by its "lo" copy (w = hi + lo, hi = w rounded
+   * to 11 significand bits), each in the canonical K-major no-swizzle layout with 32-bit elements
+   * byte(n,k) = (k/4)*(N*16) + n*16 + (k%4)*4   (csrc/gn_tf32.cuh) */
+  const void* tf_chain_w;  /* init_MLP.0 (128x64), init_MLP.1 (64x128), MLP_factor.0 (128x64), MLP_distribution.0
+                              (128x64), MLP_distribution.1 zero-padded to (16x128) */
+  const void* tf_pre_w;    /* node W0[0:128] (128xD), W1[:,0:128] (64x128), W0[128:256], W1[:,128:256], [Wp;Wq] (64x64) */
+  const void* tf_aggin_w;  /* agg_mlp[t].layers.0 (128xD) for t < T */
+  const void* tf_aggout_w; /* cat_t agg_mlp[t].layers.1 along K, (D x T*128), in K blocks of 64 */
+  const void* tf_hagg_w;   /* per t: agg_mlp[t].layers.0 (128xD), agg_mlp[t].layers.1 (Dx128) */
+  const void* tf_post_w;   /* closing MLP layers.0 (128x2D), layers.1 (Doutx128) */
 } gn_stage_weights;
 
 typedef struct gn_stage_cfg {

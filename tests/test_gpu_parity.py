@@ -494,7 +494,7 @@ def test_backward_accumulates_and_optimizer_step_repacks():
 
 # ---- T6 / §8(f) rank 1: the whole PastEncoder against the reference's own PastEncoder --------
 @pytest.mark.parametrize("name", golden_names("pastenc"))
-@pytest.mark.parametrize("precision,tol", [("fp32", FP32_REL), ("bf16", BF16_REL)])
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_REL), ("tf32", FP32_REL), ("bf16", BF16_REL)])
 def test_past_encoder_vs_reference_golden(name, precision, tol):
     g = load_golden(name)
     enc = build_past_encoder(g).to(DEV)
