@@ -50,6 +50,7 @@ def kernel_work(b, n, d, precision="bf16"):
     responsible for, bytes = compulsory HBM traffic of its inputs and outputs."""
     w = {}
     tc = precision == "bf16"
+    tf = precision == "tf32"
 
     def add(k, flops, byts, bound):
         f0, b0, _ = w.get(k, (0, 0, bound))
@@ -63,6 +64,22 @@ def kernel_work(b, n, d, precision="bf16"):
         mlp_macs = 64 * 128 + 128 * 64 + 64 * 256 + 256 * (t + 1)
         agg_macs_row = t * 2 * d * 128                      # both Linears of the T agg MLPs, per row
         post_flops = 2 * rn * (2 * d * 128 + 128 * d)
+        if tf:
+            # ---- fp32-grade tensor-core path (3xTF32 chains, csrc/gn_chain_tf32.cu); FLOPs are those of the fp32 math
+            add("node_pre_tf32", 2 * rn * (d * 256 + 256 * 64 + 64 * 64), rn * (d + 128) * 4, "tensor")
+            add("node_post_tf32", post_flops, rn * 3 * d * 4, "tensor")
+            if pair:
+                add("edge_chain_pair_tf32", 2 * re * mlp_macs + re * 600, (rn * 128 + re * t) * 4, "tensor")
+                add("agg_in_tf32", 2 * rn * d * t * 128, rn * (d + t * 128) * 4, "tensor")
+                add("edge2node_pair", rn * n * t * 128 * 4, (rn * (2 * t * 128 + 16) + re * t) * 4, "hbm")
+                add("agg_out_tf32", 2 * rn * t * 128 * d, rn * (t * 128 + 16 + d) * 4, "tensor")
+            else:
+                add("edge_chain_tf32", 2 * re * mlp_macs, re * (64 + t) * 4, "tensor")
+                add("node2edge_hyper", re * n * (64 + 2 * 64 + 2 * d),
+                    (rn * (128 + d) + re * (n + 64 + d)) * 4, "hbm")
+                add("hyper_agg_tf32", 2 * re * agg_macs_row, re * (2 * d + t) * 4, "tensor")
+                add("edge2node_hyper", 2 * rn * e * d, (re * (d + n) + rn * d) * 4, "hbm")
+            continue
         if not tc:
             # ---- fp32 (FFMA) path kernels
             add("node_pre", 2 * rn * (d * 256 + 256 * 64 + 64 * 64 + (d * t * 128 if pair else 0)),
@@ -576,8 +593,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=SCENES, help="scenes per GPU (default: BASELINE config)")
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
-                    help="bf16: tcgen05 tensor-core path (2e-2 parity); fp32: FFMA path (1e-5 parity)")
+    ap.add_argument("--precision", default=None, choices=["tf32", "bf16", "fp32"],
+                    help="headline path of the NBA / fish lines. tf32: the reference's precision on tensor cores "
+                         "(3xTF32 tcgen05 chains, 1e-5 parity); bf16: bf16 tcgen05 operands (2e-2 parity); fp32: FFMA "
+                         "kernels (1e-5 parity).  The other tensor-core path is measured the same way and printed as a "
+                         "full object under `paths`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="nba", choices=["nba", "crowd", "fish8", "fish20", "decoder"],
                     help="nba: BASELINE configs[2] (the headline line); crowd: configs[3], N=64, h_dim 256, "
@@ -588,6 +608,9 @@ def main():
                     help="train: fwd+bwd through the three layers + one NCCL all-reduce of the flat gradient "
                          "bucket (BASELINE config 5); per-GPU batch --scenes (default 8192 in this mode)")
     args = ap.parse_args()
+    if args.precision is None:
+        # the reference computes in fp32: the fp32-grade path is the headline wherever its chains cover the shape
+        args.precision = "bf16" if args.workload == "crowd" else "tf32"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     global AGENTS, SCALES, WORKLOAD
     if args.workload == "fish8":
@@ -646,67 +669,6 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            model(x, out_feature=feat, out_H=hcat)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clocks:
-            e0.record()
-            for _ in range(args.steps):
-                model(x, out_feature=feat, out_H=hcat)
-            e1.record()
-            barrier()
-        ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-        value = world * b / (ms_step * 1e-3)
-
-        # the other precision path on the same inputs, for reference (short run, same timing rules)
-        other = "fp32" if args.precision == "bf16" else "bf16"
-        model.set_precision(other)
-        for _ in range(3):
-            model(x, out_feature=feat, out_H=hcat)
-        barrier()
-        o_steps = max(3, min(args.steps, 5))
-        e0.record()
-        for _ in range(o_steps):
-            model(x, out_feature=feat, out_H=hcat)
-        e1.record()
-        barrier()
-        other_ms = max_over_ranks(e0.elapsed_time(e1) / o_steps)
-        model.set_precision(args.precision)
-
-        # per-kernel durations, CUDA events on the launch stream (library profiling hook)
-        _lib.profile_enable(True)
-        prof_steps = 2
-        for _ in range(prof_steps):
-            model(x, out_feature=feat, out_H=hcat)
-        torch.cuda.synchronize(dev)
-        prof = _lib.profile_collect()
-        _lib.profile_enable(False)
-        launches_per_step = sum(c for _, c in prof.values()) // prof_steps
-
-        # end to end through the public host API: pinned host in, pinned host out
-        out_f = torch.empty(b, n, model.feature_width(), dtype=torch.float32).pin_memory()
-        out_h = torch.empty(b, model.incidence_rows(n), n, dtype=torch.float32).pin_memory()
-        # x slice of final_feature: filled on the host when this rank has cores to spare, else written by the GPU
-        # and copied back with the rest (8 ranks x 2 threads: the host-side fill was the bottleneck)
-        slice_mode = os.environ.get("GN_E2E_INPUT_SLICE") or ("host" if torch.get_num_threads() >= 16 else "device")
-        for _ in range(2):
-            model.forward_host(x_host, out_f, out_h, input_slice=slice_mode)
-        barrier()
-        e0.record()
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(e2e_steps):
-            model.forward_host(x_host, out_f, out_h, input_slice=slice_mode)
-        e1.record()
-        barrier()
-        e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -714,60 +676,147 @@ def main():
     except Exception:
         peak_src = "fallback"
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
-    work = kernel_work(b, n, d, args.precision)
-    kernels = {}
-    for k, (tot_ms, cnt) in prof.items():
-        per_step_ms = tot_ms / prof_steps
-        fl, by, bound = work.get(k, (0, 0, "hbm"))
-        kernels[k] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": cnt // prof_steps,
-                      "bound": bound,
-                      "tflops": round(fl / (per_step_ms * 1e-3) / 1e12, 3) if per_step_ms > 0 else None,
-                      "gbs": round(by / (per_step_ms * 1e-3) / 1e9, 1) if per_step_ms > 0 else None}
-    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
-    kd = kernels[dom]
-    traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     except Exception:
-        pass
-    if kd["bound"] == "tensor":
-        ach, pk, unit = kd["tflops"], tensor_peak, "TFLOP/s"
-    else:
-        ach, pk, unit = kd["gbs"], hbm_peak, "GB/s"
-    roofline = {"kernel": dom, "bound": kd["bound"], "achieved": ach, "peak": pk, "unit": unit,
-                "frac": round(ach / pk, 5), "traffic": traffic, "peak_source": peak_src,
-                "share_of_step": round(kd["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()), 3)}
+        traffic_tab = {}
+    out_f = torch.empty(b, n, model.feature_width(), dtype=torch.float32).pin_memory()
+    out_h = torch.empty(b, model.incidence_rows(n), n, dtype=torch.float32).pin_memory()
+    # x slice of final_feature: filled on the host when this rank has cores to spare, else written by the GPU
+    # and copied back with the rest (8 ranks x 2 threads: the host-side fill was the bottleneck)
+    slice_mode = os.environ.get("GN_E2E_INPUT_SLICE") or ("host" if torch.get_num_threads() >= 16 else "device")
+    h2d = b * n * d * 4
+    d2h = b * n * (model.feature_width() - (d if slice_mode == "host" else 0)) * 4 + out_h.numel() * 4
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def measure(precision, steps):
+        """One full measurement of a precision path: device-resident throughput (CUDA events, max over ranks),
+        per-kernel durations, roofline of its dominant kernel, and the end-to-end figure through forward_host."""
+        model.set_precision(precision)
+        with torch.no_grad():
+            for _ in range(args.warmup):
+                model(x, out_feature=feat, out_H=hcat)
+            barrier()
+            with ClockSampler(local) as clocks:
+                e0.record()
+                for _ in range(steps):
+                    model(x, out_feature=feat, out_H=hcat)
+                e1.record()
+                barrier()
+            region_ms = e0.elapsed_time(e1)
+            ms_step = max_over_ranks(region_ms / steps)
+            # per-kernel durations, CUDA events on the launch stream (library profiling hook)
+            _lib.profile_enable(True)
+            prof_steps = 2
+            for _ in range(prof_steps):
+                model(x, out_feature=feat, out_H=hcat)
+            torch.cuda.synchronize(dev)
+            prof = _lib.profile_collect()
+            _lib.profile_enable(False)
+            launches_per_step = sum(c for _, c in prof.values()) // prof_steps
+            # end to end through the public host API: pinned host in, pinned host out
+            for _ in range(2):
+                model.forward_host(x_host, out_f, out_h, input_slice=slice_mode)
+            barrier()
+            e2e_steps = max(3, min(steps, 10))
+            e0.record()
+            for _ in range(e2e_steps):
+                model.forward_host(x_host, out_f, out_h, input_slice=slice_mode)
+            e1.record()
+            barrier()
+            e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+        # a region shorter than ~1 s runs at burst clocks: compare with the burst peak; longer: the sustained one
+        burst = region_ms < 1000.0
+        tensor_peak = float(peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained",
+                                      peaks.get("bf16_tflops", 1590.0)))
+        work = kernel_work(b, n, d, precision)
+        kernels = {}
+        for k, (tot_ms, cnt) in prof.items():
+            per_step_ms = tot_ms / prof_steps
+            fl, by, bound = work.get(k, (0, 0, "hbm"))
+            kernels[k] = {"ms_per_step": round(per_step_ms, 4), "launches_per_step": cnt // prof_steps,
+                          "bound": bound,
+                          "tflops": round(fl / (per_step_ms * 1e-3) / 1e12, 3) if per_step_ms > 0 else None,
+                          "gbs": round(by / (per_step_ms * 1e-3) / 1e9, 1) if per_step_ms > 0 else None}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        kd = kernels[dom]
+        if kd["bound"] == "tensor":
+            ach, pk, unit = kd["tflops"], tensor_peak, "TFLOP/s"
+        else:
+            ach, pk, unit = kd["gbs"], hbm_peak, "GB/s"
+        roofline = {"kernel": dom, "bound": kd["bound"], "achieved": ach, "peak": pk, "unit": unit,
+                    "frac": round(ach / pk, 5), "traffic": traffic_tab.get(dom), "peak_source": peak_src,
+                    "peak_kind": ("burst" if burst else "sustained") + " bf16 cuBLAS" if kd["bound"] == "tensor" else "copy",
+                    "timed_region_ms": round(region_ms, 1),
+                    "share_of_step": round(kd["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()), 3)}
+        if precision == "tf32" and kd["bound"] == "tensor":
+            # a 3xTF32 product costs 6 bf16-equivalent MMA slots (tf32 runs at half rate, three MMAs per product)
+            roofline["tf32x3_ceiling"] = round(pk / 6.0, 1)
+            roofline["frac_of_tf32x3_ceiling"] = round(ach / (pk / 6.0), 4)
+        tol = {"bf16": "2e-2 (bf16 tcgen05 operands, fp32 accumulation)",
+               "tf32": "1e-5 (3xTF32 tcgen05 chains, fp32 accumulation and epilogues)",
+               "fp32": "1e-5 (fp32 FFMA kernels)"}[precision]
+        return {
+            "precision": precision, "dtype": {"bf16": "bf16", "tf32": "f32 (3xTF32 tensor cores)", "fp32": "f32"}[precision],
+            "value": world * b / (ms_step * 1e-3), "unit": "scenes/s", "ms_per_step": ms_step, "steps": steps,
+            "warmup": args.warmup, "clocks": clocks.summary(),
+            "e2e": {"value": world * b / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "input_slice": slice_mode, "steps": e2e_steps,
+                    "api": "MultiScaleInteraction.forward_host (pinned host in/out, 3-stream chunk pipeline)"},
+            "gpu_launches": launches_per_step * steps,
+            "parity": {"path": precision, "tolerance": tol,
+                       "criterion": "max|d| <= tol * max|ref| per output tensor vs the reference outputs; "
+                                    "hyperedge membership bit-exact",
+                       "checked_by": "tests/test_gpu_parity.py, tests/test_gpu_tf32.py"},
+            "roofline": roofline, "kernels": kernels,
+        }
+
+    head = measure(args.precision, args.steps)
+    paths = {args.precision: head}
+    for other in ("tf32", "bf16"):                 # the other tensor-core path, measured by the same protocol
+        if other not in paths:
+            paths[other] = measure(other, args.steps)
+    if "fp32" not in paths and os.environ.get("GN_BENCH_FFMA", "1") != "0":
+        # the FFMA kernels (where shapes the chains do not cover fall back to): device-resident figure only
+        model.set_precision("fp32")
+        with torch.no_grad():
+            for _ in range(3):
+                model(x, out_feature=feat, out_H=hcat)
+            barrier()
+            o_steps = max(3, min(args.steps, 5))
+            e0.record()
+            for _ in range(o_steps):
+                model(x, out_feature=feat, out_H=hcat)
+            e1.record()
+            barrier()
+        fp32_ms = max_over_ranks(e0.elapsed_time(e1) / o_steps)
+        paths["fp32_ffma"] = {"precision": "fp32", "value": world * b / (fp32_ms * 1e-3), "unit": "scenes/s",
+                              "ms_per_step": fp32_ms, "steps": o_steps}
+    model.set_precision(args.precision)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline()
 
-    h2d = b * n * d * 4
-    d2h = b * n * (model.feature_width() - (d if slice_mode == "host" else 0)) * 4 + out_h.numel() * 4
     line = {
-        "metric": METRIC, "value": value, "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+        "metric": METRIC, "value": head["value"], "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenes_per_gpu": b, "agents": n, "h_dim": d, "scales": list(SCALES),
                    "noise": "philox on device (distribution-equal to the reference's torch.rand)",
                    "weights": "torch.manual_seed(1234) default init",
+                   "outputs": "node features of the 1+S layers and every H_s written per step; the layers' `factors` "
+                              "are not (want_factors=False, as PastEncoder discards them, model/GroupNet_nba.py:290-299)",
                    "l2": "no flush: x (184 MB) and the per-step scratch (GBs) exceed the 126 MB L2",
                    "sharding": "batch-sharded, no collective on the forward path"},
-        "clocks": clocks.summary(),
-        "e2e": {"value": world * b / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "input_slice": slice_mode,
-                "api": "MultiScaleInteraction.forward_host (pinned host in/out, 3-stream chunk pipeline)"},
-        "gpu_launches": launches_per_step * args.steps,
-        "parity": {"path": args.precision,
-                   "tolerance": "2e-2 (bf16 tensor-core path)" if args.precision == "bf16" else "1e-5 (fp32 path)",
-                   "criterion": "max|d| <= tol * max|ref| per output tensor vs the reference outputs; "
-                                "hyperedge membership bit-exact", "checked_by": "tests/test_gpu_parity.py"},
-        "other_path": {"precision": other, "value": world * b / (other_ms * 1e-3), "unit": "scenes/s",
-                       "ms_per_step": other_ms, "steps": o_steps},
-        "roofline": roofline,
-        "kernels": kernels,
+        "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "parity": head["parity"],
+        "roofline": head["roofline"], "kernels": head["kernels"],
+        "paths": {k: v for k, v in paths.items() if k != args.precision},
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu

@@ -4,7 +4,8 @@ Drop-in for `model/MS_HGNN_batch.py` of TaliMotzkin/GroupNet: same nn.Module API
 hand-written CUDA kernels behind a C ABI (include/groupnet_b200.h).
 """
 from .layers import (MLP, MLP_dict, MLP_dict_softmax, MS_HGNN_hyper, MS_HGNN_oridinary,
-                     edge_aggregation)
+                     edge_aggregation, encode_onehot, gumbel_softmax, gumbel_softmax_sample, make_mlp, my_softmax,
+                     sample_gumbel)
 from .encoder import PastEncoder, PositionalAgentEncoding
 from .interaction import MultiScaleInteraction
 from .decoder import Decoder, DecomposeBlock
@@ -14,6 +15,7 @@ from ._lib import GroupNetLibraryError, LIB_PATH
 
 __all__ = [
     "MS_HGNN_oridinary", "MS_HGNN_hyper", "MLP", "MLP_dict", "MLP_dict_softmax",
-    "edge_aggregation", "MultiScaleInteraction", "PastEncoder", "PositionalAgentEncoding", "GraphedPastEncoder", "Decoder", "DecomposeBlock", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
+    "edge_aggregation", "encode_onehot", "make_mlp", "sample_gumbel", "gumbel_softmax_sample", "gumbel_softmax",
+    "my_softmax", "MultiScaleInteraction", "PastEncoder", "PositionalAgentEncoding", "GraphedPastEncoder", "Decoder", "DecomposeBlock", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
 ]
 __version__ = "0.1.0"

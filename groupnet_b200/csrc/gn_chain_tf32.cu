@@ -22,6 +22,8 @@
 // whose producers could run NBAR phases ahead of its consumers.
 //
 // Roofline: tensor pipe at 1/6 of the bf16 rate (tf32 = 1/2, three MMAs per product): 64*N/2 clk per 128 x N x 8.
+#include <cstdlib>
+#include <cstring>
 #include "gn_chain_tf32.cuh"
 #include "gn_tf32.cuh"
 #include "gn_stage.h"
@@ -30,14 +32,93 @@ namespace gn {
 
 namespace tfe {
 
-constexpr int THREADS = 192;
+constexpr int ROW_THREADS = 128 * NSLICE;          // 16 row warps
+constexpr int THREADS = ROW_THREADS + 64;          // + weight producer warp + MMA issuer warp
 
-__device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 struct Bars {
   uint64_t full[8], empty[8], a_ready[NBAR], acc_ready[NBAR];
   uint32_t tmem_slot, pad;
 };
+
+// One pass of a thread's share of a drain: 16 accumulator columns [c0, c0 + 16) of its row -> fp32 epilogue -> HBM
+// and / or the next op's A operand in tensor memory (hi | lo split).  16 columns per pass keep the 512 row threads
+// inside their 96-register budget (a spill costs an L2 round trip here: the shared-memory carve-out leaves no L1).
+__device__ __forceinline__ void drain_cols(const Args& a, const Op& op, const float* aux, uint32_t tmem_row, int c0,
+                                           long long grow, bool live, float& carry) {
+  constexpr int W = 16;
+  uint32_t r[W];
+  tf::tmem_ld16_nowait(tmem_row + op.acc_col + c0, r);
+  tc::tmem_ld_wait();
+  // partial sums kept in separate accumulators (short accumulation chains in the tensor core) meet in fp32 here
+  for (int pi = 1; pi < op.nsum; ++pi) {
+    uint32_t q[W];
+    tf::tmem_ld16_nowait(tmem_row + op.acc_col + pi * op.sum_stride + c0, q);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+  }
+  if (op.bias_off >= 0 || op.bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 b = op.bias_off >= 0 ? *reinterpret_cast<const float4*>(aux + op.bias_off + c0 + 4 * q)
+                                        : ldg_f4(op.bias + c0 + 4 * q);
+      r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + b.x);
+      r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + b.y);
+      r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + b.z);
+      r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + b.w);
+    }
+  }
+  if (op.relu) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+  }
+  if (op.rs_idx >= 0) {
+    const float scale = live ? __ldg(a.rs + grow * a.rs_ld + op.rs_idx) : 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * scale);
+  }
+  const int kind = op.drain;
+  if (kind == DR_DOT) {
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q) {
+      const float4 wv = *reinterpret_cast<const float4*>(aux + a.dot_off + c0 + 4 * q);
+      carry = fmaf(__uint_as_float(r[4 * q]), wv.x, carry);
+      carry = fmaf(__uint_as_float(r[4 * q + 1]), wv.y, carry);
+      carry = fmaf(__uint_as_float(r[4 * q + 2]), wv.z, carry);
+      carry = fmaf(__uint_as_float(r[4 * q + 3]), wv.w, carry);
+    }
+    return;
+  }
+  if (op.use_bm && live) {
+    for (int t = 0; t < a.bm_T; ++t) {
+      const float st = __ldg(a.rs + grow * a.rs_ld + t);
+      const float* bt = a.bm + static_cast<size_t>(t) * a.bm_ld + op.out_col0 + c0;
+#pragma unroll
+      for (int q = 0; q < W / 4; ++q) {
+        const float4 b = ldg_f4(bt + 4 * q);
+        r[4 * q] = __float_as_uint(fmaf(st, b.x, __uint_as_float(r[4 * q])));
+        r[4 * q + 1] = __float_as_uint(fmaf(st, b.y, __uint_as_float(r[4 * q + 1])));
+        r[4 * q + 2] = __float_as_uint(fmaf(st, b.z, __uint_as_float(r[4 * q + 2])));
+        r[4 * q + 3] = __float_as_uint(fmaf(st, b.w, __uint_as_float(r[4 * q + 3])));
+      }
+    }
+  }
+  if ((kind == DR_STORE || kind == DR_TMEM_STORE) && live) {
+    float* dst = op.out + grow * op.ldo + op.out_col0 + c0;
+#pragma unroll
+    for (int q = 0; q < W / 4; ++q)
+      *reinterpret_cast<uint4*>(dst + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+  }
+  if (kind == DR_TMEM || kind == DR_TMEM_STORE) {
+    uint32_t lo[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) tf::split_tf32(__uint_as_float(r[j]), r[j], lo[j]);
+    tf::tmem_st16(tmem_row + op.dst_col + c0, r);
+    tf::tmem_st16(tmem_row + op.dst_col + op.dn + c0, lo);
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tf32_kernel(const __grid_constant__ Args a) {
@@ -48,9 +129,12 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
 
   if (tid == 0) {
     for (int s = 0; s < a.nstage; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    for (int i = 0; i < NBAR; ++i) { mbar_init(&bars->a_ready[i], 128); mbar_init(&bars->acc_ready[i], 1); }
+    for (int i = 0; i < NBAR; ++i) { mbar_init(&bars->a_ready[i], ROW_THREADS); mbar_init(&bars->acc_ready[i], 1); }
   }
   if (warp == 0) tmem_alloc(&bars->tmem_slot, 512);
+  float* aux = reinterpret_cast<float*>(smem + a.off_aux);
+  for (int i = 0; i < a.naux; ++i)
+    for (int j = tid; j < a.aux_n[i]; j += THREADS) aux[a.aux_off[i] + j] = __ldg(a.aux_src[i] + j);
   fence_proxy_async_smem();
   fence_before_thread_sync();
   __syncthreads();
@@ -58,44 +142,64 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
   const uint32_t tmem = bars->tmem_slot;
   const uint32_t sbase = smem_u32(smem);
 
-  if (warp == 4) {
+  // The producer and issuer warps run their loops with ALL 32 lanes (warp-uniform control flow and addresses) and
+  // predicate only the asynchronous instructions with elect.sync: tcgen05.mma / tcgen05.commit / cp.async.bulk take
+  // their operands from the uniform datapath, and issued from a divergent single-lane branch each one costs
+  // 160-290 clk of election loop and register->uniform transfers (profiles/probes/mma_probe.cu) instead of ~10.
+  if (warp == ROW_THREADS / 32) {
     // ------------------------------------------------------------------ weight producer
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const unsigned char* src = a.wstream;
-        for (int o = 0; o < a.nops; ++o) {
-          const Op& op = a.ops[o];
-          const uint32_t bytes = static_cast<uint32_t>(op.N) * op.kc * 8;
-          const int nch = op.K / op.kc;
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(&bars->empty[s], ph ^ 1u);
+    int s = 0; uint32_t ph = 0;
+    int titer = 0;
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+      const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
+      unsigned long long* trp = a.trace + titer * TR_SLOTS + TR_CHUNK;
+      int ci = 0;
+      const unsigned char* src = a.wstream;
+      for (int o = 0; o < a.nops; ++o) {
+        const Op& op = a.ops[o];
+        const uint32_t bytes = static_cast<uint32_t>(op.N) * op.kc * 8;
+        const int nch = op.K / op.kc;
+        for (int c = 0; c < nch; ++c, ++ci) {
+          mbar_wait(&bars->empty[s], ph ^ 1u);
+          if (elect_one()) {
             mbar_expect_tx(&bars->full[s], bytes);
-            bulk_g2s(sbase + a.off_ring + s * STAGE_BYTES, src, bytes, &bars->full[s]);
-            src += bytes;
-            if (++s == a.nstage) { s = 0; ph ^= 1u; }
+            bulk_g2s(sbase + a.off_ring + s * a.stage_bytes, src, bytes, &bars->full[s]);
           }
+          __syncwarp();
+          if (tr && ci < TR_MAXCH) trp[4 * ci] = clock64();
+          src += bytes;
+          if (++s == a.nstage) { s = 0; ph ^= 1u; }
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == ROW_THREADS / 32 + 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      uint32_t aw = 0, sg = 0;               // a_ready phases consumed, acc_ready phases produced
-      for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        for (int o = 0; o < a.nops; ++o) {
-          const Op& op = a.ops[o];
-          for (int w = 0; w < op.wait_n; ++w) { mbar_wait(&bars->a_ready[aw & (NBAR - 1)], (aw / NBAR) & 1u); ++aw; }
-          fence_after_thread_sync();
-          const int N = op.N, K = op.K, kc = op.kc, nch = K / kc;
-          const uint32_t d = tmem + op.acc_col;
-          const uint32_t half = static_cast<uint32_t>(N) * kc * 4;
-          for (int c = 0; c < nch; ++c) {
-            mbar_wait(&bars->full[s], ph);
-            fence_after_thread_sync();
-            const uint32_t b_hi = sbase + a.off_ring + s * STAGE_BYTES, b_lo = b_hi + half;
-            const bool acc_first = (c > 0) || (op.accumulate != 0);
+    int s = 0; uint32_t ph = 0;
+    uint32_t aw = 0, sg = 0;               // a_ready phases consumed, acc_ready phases produced
+    int titer = 0;
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+      const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
+      unsigned long long* trp = a.trace + titer * TR_SLOTS;
+      int ci = 0;
+      for (int o = 0; o < a.nops; ++o) {
+        const Op& op = a.ops[o];
+        // weights first (they landed long ago: the producer runs a stage ahead), so that the MMAs go out as soon as the
+        // row threads publish the operands
+        mbar_wait(&bars->full[s], ph);
+        for (int w = 0; w < op.wait_n; ++w) { mbar_wait(&bars->a_ready[aw & (NBAR - 1)], (aw / NBAR) & 1u); ++aw; }
+        fence_after_thread_sync();
+        if (tr) trp[3 * o] = clock64();
+        const int N = op.N, K = op.K, kc = op.kc, nch = K / kc;
+        const uint32_t d = tmem + op.acc_col;
+        const uint32_t half = static_cast<uint32_t>(N) * kc * 4;
+        for (int c = 0; c < nch; ++c, ++ci) {
+          if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 1] = clock64();
+          if (c > 0) { mbar_wait(&bars->full[s], ph); fence_after_thread_sync(); }
+          if (tr && c == 0) trp[3 * o + 1] = clock64();
+          if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 2] = clock64();
+          const uint32_t b_hi = sbase + a.off_ring + s * a.stage_bytes, b_lo = b_hi + half;
+          const bool acc_first = (c > 0) || (op.accumulate != 0);
+          if (elect_one()) {
             if (op.a_src == A_SMEM) {
               const uint32_t a_hi = sbase + a.off_a0 + op.a_buf * a.a0_buf_bytes + static_cast<uint32_t>(c * kc / 4) * 2048u;
               tf::issue_x3_ss(d, a_hi, a_hi + a.a0_half_bytes, b_hi, b_lo, N, kc, acc_first);
@@ -104,31 +208,48 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
               tf::issue_x3_ts(d, ta, ta + K, b_hi, b_lo, N, kc, acc_first);
             }
             mma_commit(&bars->empty[s]);
-            if (++s == a.nstage) { s = 0; ph ^= 1u; }
           }
-          if (op.signal) { mma_commit(&bars->acc_ready[sg & (NBAR - 1)]); ++sg; }
+          __syncwarp();
+          if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 3] = clock64();
+          if (++s == a.nstage) { s = 0; ph ^= 1u; }
         }
+        if (op.signal) {
+          if (elect_one()) mma_commit(&bars->acc_ready[sg & (NBAR - 1)]);
+          __syncwarp();
+          ++sg;
+        }
+        if (tr) trp[3 * o + 2] = clock64();
       }
     }
   } else {
     // ------------------------------------------------------------------ row threads (stage + drain)
-    const int row = tid;
-    const uint32_t tmem_row = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    // 16 warps: warp w serves TMEM lane quarter q = w % 4 (the only lanes it may access) and column slice
+    // sl = w / 4: every tile row is handled by NSLICE threads, each owning a quarter of the columns of every
+    // staging pass and drain (4 warps per scheduler instead of 1 hide the LDTM / LDS / MUFU latencies)
+    const int q = warp & 3, sl = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t tmem_row = tmem + (static_cast<uint32_t>(q * 32) << 16);
     unsigned char* a0 = smem + a.off_a0;
+    float* part = reinterpret_cast<float*>(smem + a.off_scr);    // [NSLICE][128][2] attention-logit partials
+    float* dotp = part + NSLICE * 128 * 2;                       // [NSLICE][128]    DR_DOT partials
+    float* ybuf = dotp + NSLICE * 128;                           // [128][17]        Gumbel-softmax logits
     uint32_t ar = 0, sg = 0;                 // a_ready phases produced, acc_ready phases consumed
     const bool pair = a.stage_mode == ST_PAIR;
-    float* nx = reinterpret_cast<float*>(smem + a.off_node);     // x' rows of the tile's node block
-    float* np = nx + MAXN * NLD;                                 // pq rows
-    const long long total_nodes = pair ? (a.R / a.E) * a.N : 0;
+    float* np = reinterpret_cast<float*>(smem + a.off_node);     // pq rows of the tile's node block   [MAXN][NLD]
+    float* ny = np + MAXN * NLD;                                 // Y = x' W^T rows                    [MAXN][YLD]
+    // pair mode: R < 2^31 (checked by the launcher), so the scene / edge index math is 32-bit unsigned
+    const uint32_t uE = static_cast<uint32_t>(a.E > 0 ? a.E : 1), uN = static_cast<uint32_t>(a.N);
+    const uint32_t total_nodes = pair ? static_cast<uint32_t>(a.R) / uE * uN : 0u;
     const int tps = pair ? a.tps : 0;
     auto prefetch_nodes = [&](long long t) {
       if (t < a.ntiles) {
-        const long long node0 = (tps ? t / tps : (t * 128) / a.E) * a.N;
-        const int cnt = static_cast<int>(min(static_cast<long long>(MAXN), total_nodes - node0));
-        for (int i = tid; i < cnt * 16; i += 128) {
-          const int n = i >> 4, c = i & 15;
-          cp_async16(nx + n * NLD + 4 * c, a.xprime + (node0 + n) * 64 + 4 * c);
-          cp_async16(np + n * NLD + 4 * c, a.pq + (node0 + n) * 64 + 4 * c);
+        const uint32_t ut = static_cast<uint32_t>(t);
+        const uint32_t node0 = (tps ? ut / static_cast<uint32_t>(tps) : (ut * 128u) / uE) * uN;
+        const int cnt = static_cast<int>(min(static_cast<uint32_t>(MAXN), total_nodes - node0));
+        for (int i = tid; i < cnt * 48; i += ROW_THREADS) {       // 16 x 16 B of pq + 32 x 16 B of Y per node
+          const int n = i / 48, c = i - n * 48;
+          if (c < 16) cp_async16(np + n * NLD + 4 * c, a.pq + static_cast<size_t>(node0 + n) * 64 + 4 * c);
+          else cp_async16(ny + n * YLD + 4 * (c - 16), a.ypre + static_cast<size_t>(node0 + n) * 128 + 4 * (c - 16));
         }
       }
       cp_async_commit();
@@ -138,8 +259,11 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     if (a.noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && a.U != nullptr)
       seed = __ldg(reinterpret_cast<const unsigned long long*>(a.U));
 
-    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-      const long long tscene = tps ? tile / tps : 0;
+    int titer = 0;
+    for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
+      const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && tid == 0;
+      unsigned long long* trp = a.trace + titer * TR_SLOTS + TR_ROWS;
+      const long long tscene = tps ? static_cast<long long>(static_cast<uint32_t>(tile) / static_cast<uint32_t>(tps)) : 0;
       const int tchunk = tps ? static_cast<int>(tile - tscene * tps) : 0;
       const long long grow = tps ? tscene * a.E + tchunk * 128 + row : tile * 128 + row;
       const bool live = grow < a.R && (!tps || tchunk * 128 + row < a.E);
@@ -147,36 +271,37 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
 
       for (int e = 0; e < a.nev; ++e) {
         const Op& op = a.ops[a.ev_op[e]];
+        if (tr) trp[3 * e] = clock64();
         if (a.ev_type[e] == EV_STAGE) {
           unsigned char* hi = a0 + op.a_buf * a.a0_buf_bytes;
           unsigned char* lo = hi + a.a0_half_bytes;
           if (pair) {
-            // fused node2edge of the pairwise layer: attention over the (<= 2) members of edge (i,j), softmax over
-            // ALL N nodes (non-members enter with logit 0), self loops carry incidence 2 (:124,:135-137)
+            // fused node2edge of the pairwise layer: attention over the (<= 2) members of edge (i,j), softmax over ALL N
+            // nodes (non-members enter with logit 0), self loops carry incidence 2 (:124,:135-137).  Slice sl sums 8 of
+            // the 32 attention hidden units; the partial logits meet in shared memory.
             cp_async_wait<0>();
             row_bar();
-            const long long b_lo = tps ? tscene : (tile * 128) / a.E;
-            float wi = 0.f, wj = 0.f;
-            const float* xi = nx;
-            const float* xj = nx;
+            if (tr) trp[TR_STAGE - TR_ROWS + 0] = clock64();
+            const uint32_t b_lo = tps ? static_cast<uint32_t>(tscene) : (static_cast<uint32_t>(tile) * 128u) / uE;
+            const int N = a.N;
+            const float* att = aux + a.att_off;                  // b0[32] | w1[32] | b1
+            int li = 0, lj = 0, i = 0, j = 0;
             if (live) {
-              const int N = a.N;
-              const long long b = grow / a.E;
-              const int eidx = static_cast<int>(grow - b * a.E), i = eidx / N, j = eidx - i * N;
-              const int li = static_cast<int>(b - b_lo) * N + i, lj = static_cast<int>(b - b_lo) * N + j;
+              const uint32_t b = static_cast<uint32_t>(grow) / uE;
+              const uint32_t eidx = static_cast<uint32_t>(grow) - b * uE;
+              i = static_cast<int>(eidx / uN); j = static_cast<int>(eidx) - i * N;
+              li = static_cast<int>(b - b_lo) * N + i; lj = static_cast<int>(b - b_lo) * N + j;
               const float* pi = np + li * NLD;
               const float* pj = np + lj * NLD;
-              xi = nx + li * NLD;
-              xj = nx + lj * NLD;
               float ai = 0.f, aj = 0.f;
 #pragma unroll
-              for (int k4 = 0; k4 < 32; k4 += 4) {
+              for (int k4 = 8 * sl; k4 < 8 * sl + 8; k4 += 4) {
                 const float4 ni = *reinterpret_cast<const float4*>(pi + k4);
                 const float4 nj = *reinterpret_cast<const float4*>(pj + k4);
                 const float4 qi = *reinterpret_cast<const float4*>(pi + 32 + k4);
                 const float4 qj = *reinterpret_cast<const float4*>(pj + 32 + k4);
-                const float4 b0 = ldg_f4(a.att_b0 + k4);
-                const float4 w1 = ldg_f4(a.att_w1 + k4);
+                const float4 b0 = *reinterpret_cast<const float4*>(att + k4);
+                const float4 w1 = *reinterpret_cast<const float4*>(att + 32 + k4);
                 const float p0 = qi.x + qj.x + b0.x, p1 = qi.y + qj.y + b0.y;
                 const float p2 = qi.z + qj.z + b0.z, p3 = qi.w + qj.w + b0.w;
                 ai = fmaf(fmaxf(ni.x + p0, 0.f), w1.x, ai); aj = fmaf(fmaxf(nj.x + p0, 0.f), w1.x, aj);
@@ -184,7 +309,20 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
                 ai = fmaf(fmaxf(ni.z + p2, 0.f), w1.z, ai); aj = fmaf(fmaxf(nj.z + p2, 0.f), w1.z, aj);
                 ai = fmaf(fmaxf(ni.w + p3, 0.f), w1.w, ai); aj = fmaf(fmaxf(nj.w + p3, 0.f), w1.w, aj);
               }
-              const float b1v = __ldg(a.att_b1);
+              *reinterpret_cast<float2*>(part + (sl * 128 + row) * 2) = make_float2(ai, aj);
+            }
+            if (tr) trp[TR_STAGE - TR_ROWS + 1] = clock64();
+            row_bar();
+            if (tr) trp[TR_STAGE - TR_ROWS + 2] = clock64();
+            float wi = 0.f, wj = 0.f;
+            if (live) {
+              float ai = 0.f, aj = 0.f;
+#pragma unroll
+              for (int s4 = 0; s4 < NSLICE; ++s4) {          // fixed order: every slice gets the same sums
+                const float2 p = *reinterpret_cast<const float2*>(part + (s4 * 128 + row) * 2);
+                ai += p.x; aj += p.y;
+              }
+              const float b1v = att[64];
               if (i == j) {
                 const float si = 2.f * (ai + b1v);
                 const float mx = (N > 1) ? fmaxf(si, 0.f) : si;
@@ -200,26 +338,41 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
                 wi = ei / den; wj = ej / den;
               }
             }
-#pragma unroll 4
-            for (int k4 = 0; k4 < 16; ++k4) {
-              const float4 u = *reinterpret_cast<const float4*>(xi + 4 * k4);
-              const float4 v = *reinterpret_cast<const float4*>(xj + 4 * k4);
-              uint4 h4, l4;
-              tf::split_tf32(fmaf(wi, u.x, wj * v.x), h4.x, l4.x);
-              tf::split_tf32(fmaf(wi, u.y, wj * v.y), h4.y, l4.y);
-              tf::split_tf32(fmaf(wi, u.z, wj * v.z), h4.z, l4.z);
-              tf::split_tf32(fmaf(wi, u.w, wj * v.w), h4.w, l4.w);
-              *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
-              *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
+            if (tr) trp[TR_STAGE - TR_ROWS + 3] = clock64();
+            // hidden = relu(w_i Y_i + w_j Y_j + b): this slice's 32 of the 128 columns -> tensor memory (hi | lo)
+            {
+              const float* yi = ny + li * YLD + 32 * sl;
+              const float* yj = ny + lj * YLD + 32 * sl;
+              const float* yb = aux + a.yb_off + 32 * sl;
+#pragma unroll 1
+              for (int half = 0; half < 2; ++half) {
+                uint32_t hv[16], lv[16];
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                  const float4 u = *reinterpret_cast<const float4*>(yi + 16 * half + 4 * q4);
+                  const float4 v = *reinterpret_cast<const float4*>(yj + 16 * half + 4 * q4);
+                  const float4 bb = *reinterpret_cast<const float4*>(yb + 16 * half + 4 * q4);
+                  tf::split_tf32(fmaxf(fmaf(wi, u.x, fmaf(wj, v.x, bb.x)), 0.f), hv[4 * q4], lv[4 * q4]);
+                  tf::split_tf32(fmaxf(fmaf(wi, u.y, fmaf(wj, v.y, bb.y)), 0.f), hv[4 * q4 + 1], lv[4 * q4 + 1]);
+                  tf::split_tf32(fmaxf(fmaf(wi, u.z, fmaf(wj, v.z, bb.z)), 0.f), hv[4 * q4 + 2], lv[4 * q4 + 2]);
+                  tf::split_tf32(fmaxf(fmaf(wi, u.w, fmaf(wj, v.w, bb.w)), 0.f), hv[4 * q4 + 3], lv[4 * q4 + 3]);
+                }
+                tf::tmem_st16(tmem_row + op.a_col + 32 * sl + 16 * half, hv);
+                tf::tmem_st16(tmem_row + op.a_col + 128 + 32 * sl + 16 * half, lv);
+              }
+              tf::tmem_st_wait();
             }
-            fence_proxy_async_smem();
+            if (tr) trp[TR_STAGE - TR_ROWS + 4] = clock64();
             fence_before_thread_sync();
-            row_bar();                          // every row is done with the node block: refill it for the next tile
+            if (tr) trp[TR_STAGE - TR_ROWS + 5] = clock64();
+            row_bar();                          // every thread is done with the node block: refill it for the next tile
+            if (tr) trp[TR_STAGE - TR_ROWS + 6] = clock64();
             prefetch_nodes(tile + gridDim.x);
+            if (tr) trp[TR_STAGE - TR_ROWS + 7] = clock64();
           } else {
             const int K = op.K, k0 = op.st_k0;
             const bool div = a.a_div != 0.f;
-            for (int k4 = 0; k4 < (K >> 2); ++k4) {
+            for (int k4 = sl; k4 < (K >> 2); k4 += NSLICE) {
               const int k = k0 + 4 * k4;
               float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
               if (live) {
@@ -237,146 +390,92 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
             fence_before_thread_sync();
           }
           mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
+          if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
+          if (e == 0 && a.edge_feat != nullptr) {
+            // Gumbel noise of this tile's rows (slice sl: edge types [sl*tq, sl*tq + tq)), computed now, while the first
+            // GEMM runs and the row threads would only wait: g = -log(eps - log(U + eps))  (:446-455) -> ybuf
+            const int T = a.T, tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
+            constexpr int TQ = (GN_SMALL_OUT - 1 + NSLICE - 1) / NSLICE;
+            if (live) {
+#pragma unroll
+              for (int jj = 0; jj < TQ; ++jj) {
+                const int t = t0 + jj;
+                if (jj < tq && t < T) {
+                  float u;
+                  if (a.noise_mode == GN_NOISE_GIVEN) {
+                    u = __ldg(a.U + static_cast<size_t>(grow) * T + t);
+                  } else {
+                    const unsigned long long el =
+                        (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(grow)) * T + t;
+                    u = Philox::uniform(el, static_cast<uint32_t>(a.stage_index), seed);
+                  }
+                  ybuf[row * 17 + t] = gumbel_from_uniform(u);
+                }
+              }
+            }
+          }
           continue;
         }
 
         // ---- EV_DRAIN
         mbar_wait(&bars->acc_ready[sg & (NBAR - 1)], (sg / NBAR) & 1u); ++sg;
         fence_after_thread_sync();
+        if (tr) trp[3 * e + 1] = clock64();
         const int kind = op.drain;
         if (kind == DR_GUMBEL) {
+          // slice sl handles the edge types t in [sl*tq, sl*tq + tq): y = (logit + g) / tau with the noise g left in ybuf
+          // by the staging event; the row's y meet in shared memory for the softmax; factor = sigmoid of the dot
+          // partials left by the DR_DOT drain
           float v[16];
           tmem_ld16(tmem_row + op.acc_col, v);
+          const int T = a.T, tq = (T + NSLICE - 1) / NSLICE;
+          constexpr int TQ = (GN_SMALL_OUT - 1 + NSLICE - 1) / NSLICE;
+          const int t0 = sl * tq;
           if (live) {
-            const int T = a.T;
-            constexpr int TU = GN_SMALL_OUT - 1;
-            float u[TU];
-            if (a.noise_mode == GN_NOISE_GIVEN) {
 #pragma unroll
-              for (int t = 0; t < TU; ++t) u[t] = (t < T) ? __ldg(a.U + static_cast<size_t>(grow) * T + t) : 0.5f;
-            } else {
-              // one Philox block yields 4 consecutive elements of the (B,E,T) noise tensor
-              const unsigned long long el0 =
-                  (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(grow)) * T;
-              const unsigned long long blk0 = el0 >> 2;
-              const int lead = static_cast<int>(el0 & 3);
+            for (int jj = 0; jj < TQ; ++jj) {
+              const int t = t0 + jj;
+              if (jj < tq && t < T) {
+                float lg = 0.f;
 #pragma unroll
-              for (int t = 0; t < TU; ++t) u[t] = 0.5f;
-#pragma unroll
-              for (int bi = 0; bi < (TU + 3 + 3) / 4; ++bi) {
-                if (bi * 4 < lead + T) {
-                  const uint4 r = Philox::block(blk0 + bi, static_cast<uint32_t>(a.stage_index), seed);
-                  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                  for (int s4 = 0; s4 < 4; ++s4) {
-                    const int t = bi * 4 + s4 - lead;
-                    const float uu = static_cast<float>(w[s4] >> 8) * (1.0f / 16777216.0f);
-#pragma unroll
-                    for (int tt = 0; tt < TU; ++tt)
-                      if (tt >= bi * 4 - 3 && tt <= bi * 4 + 3 && tt == t) u[tt] = uu;
-                  }
-                }
+                for (int o = 0; o < GN_SMALL_OUT; ++o) if (o == t) lg = v[o];
+                ybuf[row * 17 + t] = (lg + aux[a.gb_off + t] + ybuf[row * 17 + t]) / 0.5f;
               }
             }
-            // y = (logit + g) / tau, tau = 1/2; dist = softmax(y); factor = sigmoid(.)   (fp32 math as the FFMA path)
-            float y[TU];
+          }
+          dotp[sl * 128 + row] = carry;
+          row_bar();
+          if (live) {
             float mx = -INFINITY;
-#pragma unroll
-            for (int t = 0; t < TU; ++t)
-              if (t < T) {
-                y[t] = (v[t] + __ldg(a.g_bias + t) + gumbel_from_uniform(u[t])) / 0.5f;
-                mx = fmaxf(mx, y[t]);
-              }
+            for (int t = 0; t < T; ++t) mx = fmaxf(mx, ybuf[row * 17 + t]);
+            // ex2.approx-based exponentials: 2 ulp, three orders of magnitude inside the 1e-5 bound of outputs in [0, 1]
             float den = 0.f;
+            for (int t = 0; t < T; ++t) den += __expf(ybuf[row * 17 + t] - mx);
+            float fl = aux[a.gb_off + T];
 #pragma unroll
-            for (int t = 0; t < TU; ++t)
-              if (t < T) { y[t] = expf(y[t] - mx); den += y[t]; }
-            const float fl = carry + __ldg(a.g_bias + T);
-            const float factor = 1.f / (1.f + expf(-fl));
-            float* ef = a.edge_feat + static_cast<size_t>(grow) * T;
+            for (int s4 = 0; s4 < NSLICE; ++s4) fl += dotp[s4 * 128 + row];
+            const float factor = 1.f / (1.f + __expf(-fl));
 #pragma unroll
-            for (int t = 0; t < TU; ++t)
-              if (t < T) {
-                const float dd = y[t] / den;
+            for (int jj = 0; jj < TQ; ++jj) {
+              const int t = t0 + jj;
+              if (jj < tq && t < T) {
+                const float dd = __expf(ybuf[row * 17 + t] - mx) / den;
                 if (a.dist_out != nullptr) a.dist_out[static_cast<size_t>(grow) * T + t] = dd;
-                ef[t] = factor * dd;
+                a.edge_feat[static_cast<size_t>(grow) * T + t] = factor * dd;
               }
+            }
           }
+          row_bar();                              // ybuf / dotp are rewritten by the next tile
         } else if (kind != DR_NONE) {
-          float scale = 1.f;
-          if (op.rs_idx >= 0) scale = live ? __ldg(a.rs + grow * a.rs_ld + op.rs_idx) : 0.f;
-          const bool to_tmem = kind == DR_TMEM || kind == DR_TMEM_STORE;
-          const bool to_hbm = (kind == DR_STORE || kind == DR_TMEM_STORE) && live;
-          for (int c0 = 0; c0 < op.dn; c0 += 32) {
-            uint32_t r[32];
-            tmem_ld32_nowait(tmem_row + op.acc_col + c0, r);
-            tmem_ld_wait();
-            // partial sums kept in separate accumulators (short accumulation chains in the tensor core) meet in fp32 here
-            for (int pi = 1; pi < op.nsum; ++pi) {
-              uint32_t q[32];
-              tmem_ld32_nowait(tmem_row + op.acc_col + pi * op.sum_stride + c0, q);
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
-            }
-            if (op.bias != nullptr) {
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const float4 b = ldg_f4(op.bias + c0 + 4 * q);
-                r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + b.x);
-                r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + b.y);
-                r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + b.z);
-                r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + b.w);
-              }
-            }
-            if (op.relu) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
-            }
-            if (op.rs_idx >= 0) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * scale);
-            }
-            if (kind == DR_DOT) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                carry = fmaf(__uint_as_float(r[j]), __ldg(a.dot_w + static_cast<size_t>(c0 + j) * a.dot_stride), carry);
-              continue;
-            }
-            if (op.use_bm && live) {
-              for (int t = 0; t < a.bm_T; ++t) {
-                const float st = __ldg(a.rs + grow * a.rs_ld + t);
-                const float* bt = a.bm + static_cast<size_t>(t) * a.bm_ld + op.out_col0 + c0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 b = ldg_f4(bt + 4 * q);
-                  r[4 * q] = __float_as_uint(fmaf(st, b.x, __uint_as_float(r[4 * q])));
-                  r[4 * q + 1] = __float_as_uint(fmaf(st, b.y, __uint_as_float(r[4 * q + 1])));
-                  r[4 * q + 2] = __float_as_uint(fmaf(st, b.z, __uint_as_float(r[4 * q + 2])));
-                  r[4 * q + 3] = __float_as_uint(fmaf(st, b.w, __uint_as_float(r[4 * q + 3])));
-                }
-              }
-            }
-            if (to_hbm) {
-              float* dst = op.out + grow * op.ldo + op.out_col0 + c0;
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<uint4*>(dst + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-            }
-            if (to_tmem) {
-              uint32_t lo[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) tf::split_tf32(__uint_as_float(r[j]), r[j], lo[j]);
-              tf::tmem_st32(tmem_row + op.dst_col + c0, r);
-              tf::tmem_st32(tmem_row + op.dst_col + op.dn + c0, lo);
-            }
-          }
-          if (to_tmem) tf::tmem_st_wait();
+          const int w = op.dn / NSLICE;                     // 16 or 32 columns per thread
+          for (int c0 = sl * w; c0 < sl * w + w; c0 += 16) drain_cols(a, op, aux, tmem_row, c0, grow, live, carry);
+          if (kind == DR_TMEM || kind == DR_TMEM_STORE) tf::tmem_st_wait();
         }
         if (op.arrive) {
           fence_before_thread_sync();
           mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
         }
+        if (tr) trp[3 * e + 2] = clock64();
       }
     }
     if (pair) cp_async_wait<0>();
@@ -398,11 +497,17 @@ struct Builder {
   size_t wbytes = 0;       // bytes of one tile's weight stream
   int a0_K = 0, nbuf = 1;  // staged buffer width / count
   bool node_block = false;
-  Builder() { memset(&a, 0, sizeof(a)); }
+  uint32_t stage_bytes;
+  // layout_node: reserve the ST_PAIR node block when sizing the ring (the edge chain has ONE weight stream for its
+  // pairwise and hyper forms, so both use the pairwise layout)
+  Builder(int a0_K_, int nbuf_, bool node_block_, bool layout_node) : a0_K(a0_K_), nbuf(nbuf_), node_block(node_block_) {
+    memset(&a, 0, sizeof(a));
+    stage_bytes = ring_stage_bytes(a0_K, nbuf, layout_node);
+  }
 
   // largest multiple of 8 that divides K and keeps a [N x kc] hi+lo chunk inside one ring stage
-  static int chunk_k(int N, int K) {
-    int kc = static_cast<int>(STAGE_BYTES / 8) / N;
+  int chunk_k(int N, int K) const {
+    int kc = static_cast<int>(stage_bytes / 8) / N;
     kc = kc / 8 * 8;
     if (kc > K) kc = K;
     while (kc > 8 && K % kc) kc -= 8;
@@ -416,17 +521,34 @@ struct Builder {
     o.K = static_cast<short>(K); o.N = static_cast<short>(N); o.kc = static_cast<short>(chunk_k(N, K));
     o.acc_col = static_cast<short>(acc_col); o.accumulate = static_cast<short>(accumulate);
     o.wait_n = static_cast<short>(wait_n); o.signal = static_cast<short>(signal);
-    o.rs_idx = -1;
+    o.rs_idx = -1; o.bias_off = -1;
     wbytes += static_cast<size_t>(N) * K * 8;
     return o;
   }
+  // register `n` floats at `src` as smem constants; returns their float offset, or -1 when the block is full
+  int aux_used = 0;
+  int aux(const float* src, int n) {
+    const int n4 = (n + 3) & ~3;
+    if (!src || a.naux >= MAX_AUX || aux_used + n4 > AUX_FLOATS) return -1;
+    a.aux_src[a.naux] = src; a.aux_n[a.naux] = static_cast<short>(n); a.aux_off[a.naux] = static_cast<short>(aux_used);
+    ++a.naux;
+    aux_used += n4;
+    return aux_used - n4;
+  }
+  // bias of a drain: smem constant when it fits, else read from global memory
+  void set_bias(Op& o, const float* bias, int n) {
+    o.bias_off = -1; o.bias = nullptr;
+    if (!bias) return;
+    const int off = aux(bias, n);
+    if (off >= 0) o.bias_off = static_cast<short>(off); else o.bias = bias;
+  }
   void ev(int type, int op) { a.ev_type[a.nev] = static_cast<unsigned char>(type); a.ev_op[a.nev] = static_cast<unsigned char>(op); ++a.nev; }
-  static void drain_tmem(Op& o, int dn, int relu, const float* bias, int dst_col, int arrive) {
-    o.drain = DR_TMEM; o.dn = static_cast<short>(dn); o.relu = static_cast<short>(relu); o.bias = bias;
+  void drain_tmem(Op& o, int dn, int relu, const float* bias, int dst_col, int arrive) {
+    o.drain = DR_TMEM; o.dn = static_cast<short>(dn); o.relu = static_cast<short>(relu); set_bias(o, bias, dn);
     o.dst_col = static_cast<short>(dst_col); o.arrive = static_cast<short>(arrive);
   }
-  static void drain_store(Op& o, int dn, int relu, const float* bias, float* out, long long ldo, int col0, int arrive) {
-    o.drain = DR_STORE; o.dn = static_cast<short>(dn); o.relu = static_cast<short>(relu); o.bias = bias;
+  void drain_store(Op& o, int dn, int relu, const float* bias, float* out, long long ldo, int col0, int arrive) {
+    o.drain = DR_STORE; o.dn = static_cast<short>(dn); o.relu = static_cast<short>(relu); set_bias(o, bias, dn);
     o.out = out; o.ldo = ldo; o.out_col0 = static_cast<short>(col0); o.arrive = static_cast<short>(arrive);
   }
 };
@@ -439,13 +561,13 @@ static int validate_program(const Args& a) {
   for (int o = 0; o < a.nops; ++o) {
     const Op& op = a.ops[o];
     if (op.N < 16 || op.N > 256 || (op.N & 15) || op.K < 8 || (op.K & 7) || op.kc < 8 || (op.kc & 7) || op.K % op.kc) return GN_E_SHAPE;
-    if (static_cast<uint32_t>(op.N) * op.kc * 8 > STAGE_BYTES) return GN_E_SHAPE;
+    if (static_cast<uint32_t>(op.N) * op.kc * 8 > a.stage_bytes) return GN_E_SHAPE;
     if (op.acc_col < 0 || op.acc_col + op.N > 512) return GN_E_SHAPE;
     if (op.a_src == A_TMEM && (op.a_col < 0 || op.a_col + 2 * op.K > 512)) return GN_E_SHAPE;
     if (op.a_src == A_SMEM && static_cast<uint32_t>(op.K) * 128 * 4 > a.a0_half_bytes) return GN_E_SHAPE;
     if (op.signal) {
       if (op.drain == DR_GUMBEL) { if (op.dn != 16) return GN_E_SHAPE; }
-      else if (op.drain != DR_NONE && ((op.dn & 31) || op.dn > op.N || op.dn < 32)) return GN_E_SHAPE;
+      else if (op.drain != DR_NONE && ((op.dn != 64 && op.dn != 128) || op.dn > op.N)) return GN_E_SHAPE;   // NSLICE x 16 / 32
       if (op.nsum > 1 && (op.sum_stride < op.dn || op.acc_col + (op.nsum - 1) * op.sum_stride + op.dn > 512)) return GN_E_SHAPE;
       if ((op.drain == DR_TMEM || op.drain == DR_TMEM_STORE) && (op.dst_col < 0 || op.dst_col + 2 * op.dn > 512)) return GN_E_SHAPE;
       if ((op.drain == DR_STORE || op.drain == DR_TMEM_STORE) &&
@@ -496,21 +618,33 @@ static int validate_program(const Args& a) {
   return GN_OK;
 }
 
+}  // namespace tfe
+extern unsigned long long* g_trace_buffer;      // gn_profile_set_trace (gn_edge_mlp_tc.cu)
+namespace tfe {
+
 static int launch(Builder& b, long long R, long long ntiles, const unsigned char* wstream, const char* name, cudaStream_t st) {
   Args& a = b.a;
+  a.trace = g_trace_buffer;
+  if (a.trace != nullptr) {                      // tracing (profiles/trace_tf32.py): only the named chain writes the buffer
+    const char* only = getenv("GN_TRACE_KERNEL");
+    if (only != nullptr && strcmp(only, name) != 0) a.trace = nullptr;
+  }
   a.R = R; a.ntiles = ntiles; a.wstream = wstream;
   a.a0_half_bytes = static_cast<uint32_t>(b.a0_K) * 128 * 4;
   a.a0_buf_bytes = 2 * a.a0_half_bytes;
   a.off_a0 = 0;
   a.off_ring = static_cast<uint32_t>(b.nbuf) * a.a0_buf_bytes;
-  const uint32_t node_bytes = b.node_block ? 2u * MAXN * NLD * 4 : 0u;
-  const uint32_t fixed = a.off_ring + node_bytes + static_cast<uint32_t>(sizeof(Bars)) + 128;
-  if (fixed + 2 * STAGE_BYTES > 227 * 1024) return GN_E_SHAPE;
-  int ns = static_cast<int>((227 * 1024 - fixed) / STAGE_BYTES);
+  const uint32_t node_bytes = b.node_block ? node_block_bytes() : 0u;
+  const uint32_t fixed = a.off_ring + node_bytes + FIXED_BYTES;
+  a.stage_bytes = b.stage_bytes;
+  if (fixed + 2 * a.stage_bytes > SMEM_BUDGET) return GN_E_SHAPE;
+  int ns = static_cast<int>((SMEM_BUDGET - fixed) / a.stage_bytes);
   if (ns > 8) ns = 8;
   a.nstage = ns;
-  a.off_node = a.off_ring + static_cast<uint32_t>(ns) * STAGE_BYTES;
-  a.off_bar = (a.off_node + node_bytes + 127u) & ~127u;
+  a.off_node = a.off_ring + static_cast<uint32_t>(ns) * a.stage_bytes;
+  a.off_scr = (a.off_node + node_bytes + 127u) & ~127u;
+  a.off_aux = (a.off_scr + SCR_BYTES + 127u) & ~127u;
+  a.off_bar = (a.off_aux + AUX_FLOATS * 4 + 127u) & ~127u;
   const uint32_t smem = a.off_bar + static_cast<uint32_t>(sizeof(Bars));
   int rc = validate_program(a);
   if (rc != GN_OK) return rc;
@@ -542,39 +676,56 @@ bool edge_chain_tf32_fits(bool pair, int N, int T) {
   return (127 / E + 2) * N <= MAXN;
 }
 
-int launch_edge_chain_tf32(bool pair, const float* edges, const float* xprime, const float* pq,
+int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, const float* pq,
                            int N, int E, int T, long long R, const gn_stage_weights* w,
                            const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
                            int stage_index, float* dist_out, float* edge_feat, cudaStream_t st) {
   if (!w->tf_chain_w) return GN_E_NULL;
   if (R <= 0) return GN_OK;
-  Builder b;
+  if (pair && (!ypre || !pq || R >= (1LL << 31))) return GN_E_SHAPE;
+  // pair: the first Linear of init_MLP commutes with the attention-weighted gather (edges_e = w_i x'_i + w_j x'_j, :138),
+  // so it ran once per NODE in the prologue (Y = x' W^T) and the staging pass emits relu(w_i Y_i + w_j Y_j + b) straight
+  // into tensor memory: G1, its drain and its 64 KB of weights per tile are gone from the N^2 edge rows
+  Builder b(pair ? 0 : 64, 1, pair, pair);
+  if (b.stage_bytes != 65536u) return GN_E_SHAPE;          // the stream is packed for 64 KB stages in both forms
   Args& a = b.a;
-  b.a0_K = 64; b.nbuf = 1; b.node_block = pair;
-  Op& g1 = b.add(A_SMEM, 0, 64, 128, 0, 0, 1, 1);
-  Builder::drain_tmem(g1, 128, 1, w->init_b0, 128, 1);
+  int first = 0;
+  if (!pair) {
+    Op& g1 = b.add(A_SMEM, 0, 64, 128, 0, 0, 1, 1);
+    b.drain_tmem(g1, 128, 1, w->init_b0, 128, 1);
+    first = 1;
+  } else {
+    a.yb_off = b.aux(w->init_b0, 128);
+    a.att_off = b.aux(w->att_b0, 32);
+    b.aux(w->att_w1, 32);
+    b.aux(w->att_b1, 1);
+  }
   Op& g2 = b.add(A_TMEM, 128, 128, 64, 384, 0, 1, 1);
-  Builder::drain_tmem(g2, 64, 0, w->init_b1, 0, 1);
+  b.drain_tmem(g2, 64, 0, w->init_b1, 0, 1);
   Op& g3f = b.add(A_TMEM, 0, 64, 128, 128, 0, 1, 1);
-  g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; g3f.bias = w->df_b0 + 128; g3f.arrive = 0;
+  g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; b.set_bias(g3f, w->df_b0 + 128, 128); g3f.arrive = 0;
   Op& g3d = b.add(A_TMEM, 0, 64, 128, 256, 0, 0, 1);
-  Builder::drain_tmem(g3d, 128, 1, w->df_b0, 0, 1);
+  b.drain_tmem(g3d, 128, 1, w->df_b0, 0, 1);
   Op& g4 = b.add(A_TMEM, 0, 128, 16, 384, 0, 1, 1);
   g4.drain = DR_GUMBEL; g4.dn = 16; g4.arrive = 0;
   b.ev(EV_STAGE, 0);
-  for (int o = 0; o < 5; ++o) b.ev(EV_DRAIN, o);
+  for (int o = 0; o < 4 + first; ++o) b.ev(EV_DRAIN, o);
   a.stage_mode = pair ? ST_PAIR : ST_ROWS;
   a.src0 = edges; a.ld0 = 64; a.k_src0 = 64; a.src1 = nullptr; a.ld1 = 0; a.a_div = 0.f;
-  a.xprime = xprime; a.pq = pq; a.att_b0 = w->att_b0; a.att_w1 = w->att_w1; a.att_b1 = w->att_b1;
+  a.ypre = ypre; a.pq = pq;
   a.N = N; a.E = E;
   a.tps = (pair && E >= 128) ? (E + 127) / 128 : 0;
-  a.dot_w = w->df_w1 + 128 * GN_SMALL_OUT + T; a.dot_stride = GN_SMALL_OUT;
-  a.g_bias = w->df_b1; a.T = T;
+  // the stream: init_MLP.0 (64 KB, skipped by the pair form) | the chunks of the ops above | MLP_factor.layers.1.weight
+  const unsigned char* stream = static_cast<const unsigned char*>(w->tf_chain_w);
+  const size_t w1_bytes = 128 * 64 * 8;
+  a.dot_off = b.aux(reinterpret_cast<const float*>(stream + (pair ? w1_bytes : 0) + b.wbytes), 128);
+  a.gb_off = b.aux(w->df_b1, GN_SMALL_OUT);
+  if (a.dot_off < 0 || a.gb_off < 0 || (pair && (a.yb_off < 0 || a.att_off < 0))) return GN_E_SHAPE;
+  a.T = T;
   a.U = U; a.noise_mode = noise_mode; a.seed = seed; a.scene_offset = scene_offset; a.stage_index = stage_index;
   a.dist_out = dist_out; a.edge_feat = edge_feat;
   const long long ntiles = a.tps ? (R / E) * a.tps : (R + 127) / 128;
-  return launch(b, R, ntiles, static_cast<const unsigned char*>(w->tf_chain_w),
-                pair ? "edge_chain_pair_tf32" : "edge_chain_tf32", st);
+  return launch(b, R, ntiles, stream + (pair ? w1_bytes : 0), pair ? "edge_chain_pair_tf32" : "edge_chain_tf32", st);
 }
 
 // ---- node prologue: x' = node2edge_start_mlp(h) (D -> 256 -> 64, :84,:125), pq = split attention layer 0 (:80,:134)
@@ -583,23 +734,28 @@ int launch_edge_chain_tf32(bool pair, const float* edges, const float* xprime, c
 bool node_pre_tf32_fits(int D) { return D >= 8 && D <= 128 && (D & 7) == 0; }
 
 int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weights* w, float* xprime, float* pq,
-                         cudaStream_t st) {
+                         float* ypre, cudaStream_t st) {
   if (!w->tf_pre_w) return GN_E_NULL;
   if (R <= 0) return GN_OK;
-  Builder b;
+  Builder b(D, 1, false, false);
   Args& a = b.a;
-  b.a0_K = D; b.nbuf = 1;
   Op& s0a = b.add(A_SMEM, 0, D, 128, 0, 0, 1, 1);
-  Builder::drain_tmem(s0a, 128, 1, w->node_b0, 128, 1);
+  b.drain_tmem(s0a, 128, 1, w->node_b0, 128, 1);
   b.add(A_TMEM, 128, 128, 64, 384, 0, 1, 0);
   Op& s0b = b.add(A_SMEM, 0, D, 128, 0, 0, 0, 1);
-  Builder::drain_tmem(s0b, 128, 1, w->node_b0 + 128, 128, 1);
+  b.drain_tmem(s0b, 128, 1, w->node_b0 + 128, 128, 1);
   Op& s1b = b.add(A_TMEM, 128, 128, 64, 384, 1, 1, 1);
   s1b.drain = DR_TMEM_STORE; s1b.dn = 64; s1b.relu = 0; s1b.bias = w->node_b1; s1b.dst_col = 0; s1b.arrive = 1;
   s1b.out = xprime; s1b.ldo = 64; s1b.out_col0 = 0;
   Op& s2 = b.add(A_TMEM, 0, 64, 64, 448, 0, 1, 1);
-  Builder::drain_store(s2, 64, 0, nullptr, pq, 64, 0, 0);
+  b.drain_store(s2, 64, 0, nullptr, pq, 64, 0, 0);
   b.ev(EV_STAGE, 0); b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 2); b.ev(EV_DRAIN, 3); b.ev(EV_DRAIN, 4);
+  if (ypre != nullptr) {
+    // pairwise layers: Y = x' W_init0^T (no bias), the per-node half of init_MLP's first Linear (see the edge chain)
+    Op& s3 = b.add(A_TMEM, 0, 64, 128, 128, 0, 0, 1);
+    b.drain_store(s3, 128, 0, nullptr, ypre, 128, 0, 0);
+    b.ev(EV_DRAIN, 5);
+  }
   a.stage_mode = ST_ROWS; a.src0 = h; a.ld0 = D; a.k_src0 = D;
   return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_pre_w), "node_pre_tf32", st);
 }
@@ -610,13 +766,12 @@ bool agg_in_tf32_fits(int D, int T) { return D >= 8 && D <= 128 && (D & 7) == 0 
 int launch_agg_in_tf32(const float* h, long long R, int D, int T, const gn_stage_weights* w, float* P, cudaStream_t st) {
   if (!w->tf_aggin_w) return GN_E_NULL;
   if (R <= 0) return GN_OK;
-  Builder b;
+  Builder b(D, 1, false, false);
   Args& a = b.a;
-  b.a0_K = D; b.nbuf = 1;
   b.ev(EV_STAGE, 0);
   for (int t = 0; t < T; ++t) {
     Op& o = b.add(A_SMEM, 0, D, 128, (t & 1) * 128, 0, (t == 0 || t >= 2) ? 1 : 0, 1);
-    Builder::drain_store(o, 128, 0, nullptr, P, static_cast<long long>(T) * 128, 0, (t + 2 < T) ? 1 : 0);
+    b.drain_store(o, 128, 0, nullptr, P, static_cast<long long>(T) * 128, 0, (t + 2 < T) ? 1 : 0);
     o.out = P + t * 128;                 // column block t (out_col0 is a short: keep it 0)
     b.ev(EV_DRAIN, t);
   }
@@ -626,16 +781,15 @@ int launch_agg_in_tf32(const float* h, long long R, int D, int T, const gn_stage
 
 // ---- pairwise aggregation, second half: agg = G W1cat^T + S b1, K = T*128 streamed through two staged buffers
 bool agg_out_tf32_fits(int D, int T) {
-  return D >= 32 && D <= 128 && (D & 31) == 0 && T >= 1 && 2 * T <= MAX_OPS && 4 * T + 2 <= MAX_EV;
+  return (D == 64 || D == 128) && T >= 1 && 2 * T <= MAX_OPS && 4 * T + 2 <= MAX_EV;
 }
 
 int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int T, const gn_stage_weights* w,
                         float* agg, cudaStream_t st) {
   if (!w->tf_aggout_w) return GN_E_NULL;
   if (R <= 0) return GN_OK;
-  Builder b;
+  Builder b(64, 2, false, false);
   Args& a = b.a;
-  b.a0_K = 64; b.nbuf = 2;
   const int n = 2 * T;                    // K chunks of 64
   // chunk c accumulates into accumulator c % NACC (columns 128 apart): four short chains instead of one long one,
   // summed in fp32 by the final drain (the tensor core's accumulation rounds toward zero)
@@ -645,7 +799,7 @@ int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int 
     o.st_k0 = static_cast<short>(64 * c);
     if (c == n - 1) {
       // the last chunk goes to accumulator 0, where the drain starts summing (any accumulator may take it)
-      Builder::drain_store(o, D, 0, nullptr, agg, D, 0, 0);
+      b.drain_store(o, D, 0, nullptr, agg, D, 0, 0);
       o.acc_col = 0; o.accumulate = 1; o.nsum = static_cast<short>(NACC); o.sum_stride = 128;
       o.use_bm = 1;
     } else {
@@ -667,20 +821,19 @@ int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int 
 // ---- hyper edge_aggregation as written (:259-265): ef = sum_t edge_feat_t * (W1_t relu(W0_t eo + b0_t) + b1_t)
 // TMEM columns: acc_hid 0 | A_hid 128,256 | acc_ef 384
 bool hyper_agg_tf32_fits(int D, int T) {
-  return D >= 32 && D <= 128 && (D & 31) == 0 && T >= 1 && 2 * T <= MAX_OPS;
+  return (D == 64 || D == 128) && T >= 1 && 2 * T <= MAX_OPS;
 }
 
 int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, int D, int T,
                           const gn_stage_weights* w, float* ef, cudaStream_t st) {
   if (!w->tf_hagg_w) return GN_E_NULL;
   if (R <= 0) return GN_OK;
-  Builder b;
+  Builder b(D, 1, false, false);
   Args& a = b.a;
-  b.a0_K = D; b.nbuf = 1;
   b.ev(EV_STAGE, 0);
   for (int t = 0; t < T; ++t) {
     Op& g1 = b.add(A_SMEM, 0, D, 128, 0, 0, t == 0 ? 1 : 0, 1);
-    Builder::drain_tmem(g1, 128, 1, w->agg_b0 + t * 128, 128, 1);
+    b.drain_tmem(g1, 128, 1, w->agg_b0 + t * 128, 128, 1);
     g1.rs_idx = static_cast<short>(t);
     b.ev(EV_DRAIN, 2 * t);
     // two short accumulation chains (even / odd t) when they fit beside A_hid, summed in fp32 by the final drain
@@ -688,7 +841,7 @@ int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, 
     const bool last = t == T - 1;
     Op& g2 = b.add(A_TMEM, 128, 128, D, last ? 384 : 384 + (t % NACC) * 64, (last ? t > 0 : t >= NACC) ? 1 : 0, 1, last ? 1 : 0);
     if (last) {
-      Builder::drain_store(g2, D, 0, nullptr, ef, D, 0, 0);
+      b.drain_store(g2, D, 0, nullptr, ef, D, 0, 0);
       g2.nsum = static_cast<short>(NACC); g2.sum_stride = 64;
       g2.use_bm = 1;
       b.ev(EV_DRAIN, 2 * t + 1);
@@ -701,7 +854,7 @@ int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, 
 
 // ---- closing MLP on [agg | h] / N (:120,:355,:195,:441): 2D -> 128 (ReLU) -> Dout
 bool node_post_tf32_fits(int D, int Dout, long long ld_out, const float* node_out) {
-  return D >= 4 && D <= 64 && (D & 3) == 0 && Dout >= 32 && Dout <= 128 && (Dout & 31) == 0 && (ld_out & 3) == 0 &&
+  return D >= 4 && D <= 64 && (D & 3) == 0 && (Dout == 64 || Dout == 128) && (ld_out & 3) == 0 &&
          (reinterpret_cast<uintptr_t>(node_out) & 15) == 0;
 }
 
@@ -709,13 +862,12 @@ int launch_node_post_tf32(const float* agg, const float* h, long long R, int D, 
                           const gn_stage_weights* w, float* node_out, long long ld_out, cudaStream_t st) {
   if (!w->tf_post_w) return GN_E_NULL;
   if (R <= 0) return GN_OK;
-  Builder b;
+  Builder b(2 * D, 1, false, false);
   Args& a = b.a;
-  b.a0_K = 2 * D; b.nbuf = 1;
   Op& p0 = b.add(A_SMEM, 0, 2 * D, 128, 0, 0, 1, 1);
-  Builder::drain_tmem(p0, 128, 1, w->post_b0, 128, 1);
+  b.drain_tmem(p0, 128, 1, w->post_b0, 128, 1);
   Op& p1 = b.add(A_TMEM, 128, 128, Dout, 384, 0, 1, 1);
-  Builder::drain_store(p1, Dout, 0, w->post_b1, node_out, ld_out, 0, 0);
+  b.drain_store(p1, Dout, 0, w->post_b1, node_out, ld_out, 0, 0);
   b.ev(EV_STAGE, 0); b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 1);
   a.stage_mode = ST_ROWS; a.src0 = agg; a.ld0 = D; a.k_src0 = D; a.src1 = h; a.ld1 = D;
   a.a_div = static_cast<float>(Nagents);

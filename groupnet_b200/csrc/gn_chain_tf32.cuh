@@ -7,11 +7,32 @@ namespace gn { namespace tfe {
 
 constexpr int MAX_OPS = 32;
 constexpr int MAX_EV = 72;
-constexpr uint32_t STAGE_BYTES = 16384;        // one weight-ring stage: a [N x kc] chunk, hi then lo
+// weight-ring stage (a [N x kc] chunk, hi then lo): the largest of 64 / 32 / 16 KB that leaves room for two stages
+// beside the staged A buffers; must match packing.tf_stage_bytes
+constexpr uint32_t SMEM_BUDGET = 227 * 1024;
 constexpr int NBAR = 4;                        // depth of the a_ready / acc_ready mbarrier rings
-constexpr int MAXN = 36, NLD = 68;             // ST_PAIR node block: rows a tile may span, padded row (floats)
+// ST_PAIR node block: the rows a tile may span, pq rows padded to NLD floats, Y rows to YLD (rows 4 banks apart)
+constexpr int MAXN = 36, NLD = 68, YLD = 132;
+__host__ __device__ constexpr uint32_t node_block_bytes() { return static_cast<uint32_t>(MAXN) * (NLD + YLD) * 4; }
+constexpr int NSLICE = 4;                      // threads per tile row (column slices); 16 row warps
+constexpr uint32_t SCR_BYTES = (NSLICE * 128 * 2 + NSLICE * 128 + 128 * 17) * 4;   // logit partials | dot partials | y
+constexpr int AUX_FLOATS = 2048;               // small constants (biases, attention tail, factor head) kept in smem:
+                                               // with ~227 KB of shared memory carved out there is no L1 left
+constexpr int MAX_AUX = 12;
+constexpr uint32_t FIXED_BYTES = SCR_BYTES + AUX_FLOATS * 4 + 1024;                // + barriers + alignment slack
+inline uint32_t ring_stage_bytes(int a0_K, int nbuf, bool node_block) {
+  const uint32_t used = static_cast<uint32_t>(nbuf) * a0_K * 1024u + (node_block ? node_block_bytes() : 0u) + FIXED_BYTES;
+  const uint32_t avail = used < SMEM_BUDGET ? SMEM_BUDGET - used : 0u;
+  return avail >= 2 * 65536u ? 65536u : (avail >= 2 * 32768u ? 32768u : 16384u);
+}
 
 enum { EV_STAGE = 0, EV_DRAIN = 1 };
+// trace layout: tile t (< TR_TILES) owns TR_SLOTS stamps: [0, 3*MAX_OPS) issuer (per op: operands ready, first weight
+// chunk landed, all MMAs issued); [TR_ROWS, TR_ROWS + 3*MAX_EV) row thread 0 (per event: start, wait done, end)
+constexpr int TR_TILES = 6, TR_ROWS = 3 * MAX_OPS, TR_CHUNK = TR_ROWS + 3 * MAX_EV, TR_MAXCH = 40;
+// [TR_CHUNK, +4*TR_MAXCH): per weight chunk: producer issued the copy | issuer: wait start, wait end, MMAs issued
+constexpr int TR_STAGE = TR_CHUNK + 4 * TR_MAXCH;      // 8 sub-stamps inside the (pairwise) staging pass
+constexpr int TR_SLOTS = TR_STAGE + 8;
 enum { DR_NONE = 0, DR_TMEM = 1, DR_STORE = 2, DR_TMEM_STORE = 3, DR_DOT = 4, DR_GUMBEL = 5 };
 enum { ST_ROWS = 0, ST_PAIR = 1 };
 enum { A_SMEM = 0, A_TMEM = 1 };
@@ -35,6 +56,7 @@ struct Op {
   short use_bm;       // DR_STORE: v += sum_t rs[row * rs_ld + t] * bm[t * bm_ld + col]
   short out_col0;
   short nsum, sum_stride;  // drain value = sum of nsum accumulators, sum_stride columns apart (0/1 = just acc_col)
+  short bias_off;     // >= 0: bias[dn] at this float offset of the smem constants (else `bias`, global, or none)
   const float* bias;  // [dn] or null
   float* out;         // DR_STORE / DR_TMEM_STORE: row-major fp32, row stride ldo
   long long ldo;
@@ -53,24 +75,29 @@ struct Args {
   const float* src0; long long ld0; int k_src0;
   const float* src1; long long ld1;
   float a_div;
-  // ST_PAIR: fused pairwise node2edge (model/MS_HGNN_batch.py:122-141)
-  const float* xprime; const float* pq;
-  const float* att_b0; const float* att_w1; const float* att_b1;
+  // ST_PAIR: fused pairwise node2edge (model/MS_HGNN_batch.py:122-141) + the first Linear of init_MLP, which commutes
+  // with the weighted gather: relu(w_i Y_i + w_j Y_j + b), Y = x' W^T per NODE (ypre, 128 columns), written straight
+  // into tensor memory as the A operand of the chain's first op
+  const float* ypre; const float* pq;
+  int att_off, yb_off;             // smem constants: attention tail b0[32] | w1[32] | b1[4]; bias of the commuted Linear
+  // smem constants, copied once per CTA: aux_n[i] floats from aux_src[i] to float offset aux_off[i]
+  const float* aux_src[MAX_AUX]; short aux_n[MAX_AUX], aux_off[MAX_AUX]; int naux;
   int N, E, tps;
   // per-row scales (edge_feat or S) and the rank-T bias of the aggregation output
   const float* rs; int rs_ld;
   const float* bm; int bm_T; int bm_ld;
   // DR_DOT: carry = sum_k relu(acc_k + bias_k) * dot_w[k * dot_stride]
-  const float* dot_w; int dot_stride;
+  int dot_off;                     // smem constants
   // DR_GUMBEL (MLP_dict_softmax tail, :45-53, :446-520)
-  const float* g_bias; int T;
+  int gb_off; int T;               // smem constants: df_b1[16]
   const float* U; int noise_mode; unsigned long long seed; long long scene_offset; int stage_index;
   float* dist_out; float* edge_feat;
   // shared-memory layout
   uint32_t off_a0, a0_buf_bytes;   // staged A buffers: buffer b at off_a0 + b * a0_buf_bytes, hi then lo
   uint32_t a0_half_bytes;          // bytes of one (hi or lo) copy = 128 * K_buf * 4
-  uint32_t off_ring; int nstage;
-  uint32_t off_node, off_bar;
+  uint32_t off_ring; int nstage; uint32_t stage_bytes;
+  uint32_t off_node, off_scr, off_aux, off_bar;
+  unsigned long long* trace;       // optional (gn_profile_set_trace): clock64 stamps of block 0's first tiles, see TR_* below
 };
 
 }}  // namespace gn::tfe

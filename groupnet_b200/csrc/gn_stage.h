@@ -77,13 +77,13 @@ int launch_node_chain_tc(const NodeChainArgs& a, const char* name, cudaStream_t 
 
 // 3xTF32 chains on tcgen05 (gn_chain_tf32.cu): the fp32-grade tensor-core path, precision GN_TF32X3
 bool edge_chain_tf32_fits(bool pair, int N, int T);
-int launch_edge_chain_tf32(bool pair, const float* edges, const float* xprime, const float* pq,
+int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, const float* pq,
                            int N, int E, int T, long long R, const gn_stage_weights* w,
                            const float* U, int noise_mode, unsigned long long seed, long long scene_offset,
                            int stage_index, float* dist_out, float* edge_feat, cudaStream_t st);
 bool node_pre_tf32_fits(int D);
 int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weights* w, float* xprime, float* pq,
-                         cudaStream_t st);
+                         float* ypre, cudaStream_t st);
 bool agg_in_tf32_fits(int D, int T);
 int launch_agg_in_tf32(const float* h, long long R, int D, int T, const gn_stage_weights* w, float* P, cudaStream_t st);
 bool agg_out_tf32_fits(int D, int T);

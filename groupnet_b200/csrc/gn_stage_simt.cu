@@ -865,7 +865,7 @@ namespace gn {
 struct StagePlan {
   int Dp, Dc, K2p, Doutc;
   bool tc_nodes;          // node-level / aggregation GEMMs on tcgen05 (bf16 path, D % 16 == 0, Dout % 16 == 0)
-  size_t off_xprime, off_pq, off_P, off_edges, off_eo, off_efeat, off_ef, off_G, off_S, off_agg;
+  size_t off_xprime, off_pq, off_P, off_edges, off_eo, off_efeat, off_ef, off_G, off_S, off_agg, off_Y;
   size_t off_hid, off_hid2, off_hidden;   // bf16 scratch of the tensor-core path
   size_t total;
 };
@@ -889,7 +889,8 @@ static int make_plan(const gn_stage_cfg* c, StagePlan& p) {
   p.off_pq = take(R * 64 * 4);
   p.off_edges = take(RE * 64 * 4);
   p.off_efeat = take(RE * c->T * 4);
-  p.off_P = p.off_G = p.off_S = p.off_eo = p.off_ef = p.off_agg = 0;
+  p.off_P = p.off_G = p.off_S = p.off_eo = p.off_ef = p.off_agg = p.off_Y = 0;
+  if (c->pairwise && c->precision == GN_TF32X3) p.off_Y = take(R * 128 * 4);   // Y = x' W_init0^T per node
   p.off_hid = p.off_hid2 = p.off_hidden = 0;
   if (c->pairwise) {
     p.off_P = take(R * c->T * 128 * 4);
@@ -1050,6 +1051,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   float* eo = fptr(p.off_eo);
   float* ef = fptr(p.off_ef);
   float* agg = fptr(p.off_agg);
+  float* Ypre = fptr(p.off_Y);
   __nv_bfloat16* hid = reinterpret_cast<__nv_bfloat16*>(base + p.off_hid);
   __nv_bfloat16* hid2 = reinterpret_cast<__nv_bfloat16*>(base + p.off_hid2);
   __nv_bfloat16* hidden = reinterpret_cast<__nv_bfloat16*>(base + p.off_hidden);
@@ -1066,6 +1068,12 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   if (!c->pairwise && !H) return GN_E_NULL;
   const bool tcn = p.tc_nodes;
   const bool tf = c->precision == GN_TF32X3;       // fp32-grade tensor-core chains where the shape fits
+  const long long RE_ = static_cast<long long>(B) * E;
+  const bool tf_pre = tf && w->tf_pre_w && node_pre_tf32_fits(D) && (!c->pairwise || (w->tf_aggin_w && agg_in_tf32_fits(D, T)));
+  // pairwise edge chain with node2edge and the first Linear of init_MLP folded into its staging pass: needs the
+  // tensor-core prologue (which emits Y) and an h_dim of 64 (the prologue's Y op reads the 64-wide x' operand)
+  const bool tf_pair_y = tf_pre && c->pairwise && w->tf_chain_w != nullptr && edge_chain_tf32_fits(true, N, T) &&
+                         RE_ < (1LL << 31);
   const bool fused_agg = tcn && c->pairwise && pair_agg_fits(N, D, T);   // P / G stay on chip
   if (tcn && (!w->tc_node_w0 || !w->tc_node_w1 || !w->tc_att_wpq || !w->tc_agg_w0 || !w->tc_agg_w1 ||
               !w->tc_post_w0 || !w->tc_post_w1)) return GN_E_NULL;
@@ -1111,8 +1119,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
         GN_TRY(launch_tc_linear(a, "agg_in_tc", st));
       }
     }
-  } else if (tf && w->tf_pre_w && node_pre_tf32_fits(D) && (!c->pairwise || (w->tf_aggin_w && agg_in_tf32_fits(D, T)))) {
-    GN_TRY(launch_node_pre_tf32(h, R, D, w, xprime, pq, st));
+  } else if (tf_pre) {
+    GN_TRY(launch_node_pre_tf32(h, R, D, w, xprime, pq, tf_pair_y ? Ypre : nullptr, st));
     if (c->pairwise) GN_TRY(launch_agg_in_tf32(h, R, D, T, w, P, st));
   } else {
     constexpr int TM = 64, LD = TM + 4;
@@ -1128,7 +1136,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   // ---- k2: node2edge (fused into the tensor-core chain for the pairwise bf16 path)
   const bool tc = c->precision == GN_BF16_TC;
   const bool tf_chain = tf && w->tf_chain_w != nullptr;
-  const bool fuse_pair = c->pairwise && ((tc && edge_chain_pair_fits(N)) || (tf_chain && edge_chain_tf32_fits(true, N, T)));
+  const bool fuse_pair = c->pairwise && ((tc && edge_chain_pair_fits(N)) || tf_pair_y);
   const bool out_aligned = (reinterpret_cast<uintptr_t>(node_out) & 15) == 0;   // fused tails store 128-bit rows
   const bool fused_hyper64 = tcn && !c->pairwise && out_aligned && hyper_fused64_fits(N, E, D, T, c->Dout, ld_out);
   const bool fused_hyper = fused_hyper64 || (tcn && !c->pairwise && hyper_fused_fits(N, E, D, T));   // eo / ef never leave the SM
@@ -1142,7 +1150,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     GN_TRY(launch_edge_chain_tc(fuse_pair, edges, xprime, pq, N, E, T, RE, w, U, c->noise_mode,
                                 c->seed, c->scene_offset, c->stage_index, dist_out, efeat, st));
   } else if (tf_chain) {
-    GN_TRY(launch_edge_chain_tf32(fuse_pair, edges, xprime, pq, N, E, T, RE, w, U, c->noise_mode,
+    GN_TRY(launch_edge_chain_tf32(fuse_pair, edges, Ypre, pq, N, E, T, RE, w, U, c->noise_mode,
                                   c->seed, c->scene_offset, c->stage_index, dist_out, efeat, st));
   } else {
     constexpr int TM = 128, LD = TM + 4;

@@ -22,6 +22,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / tcgen05.commit take their operands from the uniform
+// datapath: issue them from warp-uniform control flow, predicated by this, so descriptors stay in uniform
+// registers.  Issued from a divergent `if (tid == k)` branch instead, every MMA costs a register->uniform
+// transfer sequence plus an election loop: measured 160 clk (kind::f16) / 287 clk (kind::tf32) per MMA whatever
+// its N (profiles/probes/mma_probe.cu), i.e. several times the tensor-pipe time of the small MMAs used here.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout) ----
 //  [0,14) start address >> 4 | [16,30) LBO >> 4 | [32,46) SBO >> 4 | [46,48) version = 1
 //  [49,52) base offset = 0 | [52] lbo mode = 0 | [61,64) layout type = 0 (no swizzle)

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .layers import MLP
-from .packing import PackCache, pack_decoder_block
+from .packing import PackCache, RuntimeStateMixin, pack_decoder_block
 
 
 class DecomposeBlock(nn.Module):
@@ -50,7 +50,7 @@ class DecomposeBlock(nn.Module):
         raise RuntimeError("groupnet_b200.DecomposeBlock is evaluated by groupnet_b200.Decoder (gn_decoder_fwd)")
 
 
-class Decoder(nn.Module):
+class Decoder(RuntimeStateMixin, nn.Module):
     def __init__(self, args):
         super().__init__()
         self.args = args
@@ -64,9 +64,15 @@ class Decoder(nn.Module):
         self.decompose = nn.ModuleList(
             [DecomposeBlock(self.args.past_length, self.args.future_length, input_dim)
              for _ in range(self.num_decompose)])
-        self._pack_key = None
-        self._packed = None
-        self._ws = ops.Workspace()
+        self._reset_runtime()
+        self._install_runtime_hooks()
+
+    _RUNTIME_ATTRS = ("_pack_key", "_packed", "_ws")
+
+    def _reset_runtime(self) -> None:
+        self.__dict__["_pack_key"] = None
+        self.__dict__["_packed"] = None
+        self.__dict__["_ws"] = ops.Workspace()
 
     def _packs(self, device):
         key = PackCache._fingerprint(self, device)

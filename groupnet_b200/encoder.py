@@ -23,6 +23,7 @@ import torch.nn as nn
 from . import _lib, ops
 from .interaction import MultiScaleInteraction, _HYPER_NAMES
 from .layers import MS_HGNN_hyper, MS_HGNN_oridinary
+from .packing import RuntimeStateMixin
 
 
 class PositionalAgentEncoding(nn.Module):
@@ -46,7 +47,7 @@ class PositionalAgentEncoding(nn.Module):
         raise RuntimeError("groupnet_b200.PositionalAgentEncoding is a parameter container (gn_past_frontend)")
 
 
-class PastEncoder(nn.Module):
+class PastEncoder(RuntimeStateMixin, nn.Module):
     def __init__(self, args, in_dim=4):
         super().__init__()
         self.args = args
@@ -63,9 +64,15 @@ class PastEncoder(nn.Module):
             setattr(self, name, MS_HGNN_hyper(embedding_dim=d, h_dim=d, mlp_dim=64, bottleneck_dim=d,
                                               batch_norm=0, nmp_layers=1, scale=scale))
         self.pos_encoder = PositionalAgentEncoding(d, 0.1, concat=True)
-        self._fold_key = None
-        self._fold = None
-        self._block = None
+        self._reset_runtime()
+        self._install_runtime_hooks()
+
+    _RUNTIME_ATTRS = ("_fold_key", "_fold", "_block")
+
+    def _reset_runtime(self) -> None:
+        self.__dict__["_fold_key"] = None
+        self.__dict__["_fold"] = None
+        self.__dict__["_block"] = None
 
     # ------------------------------------------------------------------
     def _interaction_block(self) -> MultiScaleInteraction:
@@ -130,9 +137,15 @@ class PastEncoder(nn.Module):
         rows, length, in_dim = inputs.shape
         if rows != batch_size * agent_num:
             raise RuntimeError("shape mismatch: inputs must be (batch_size*agent_num, T, in_dim)")
-        if self.training and torch.is_grad_enabled():
+        if self.training:
             raise NotImplementedError("groupnet_b200.PastEncoder: the fused front-end is eval-only "
-                                      "(pos_encoder.dropout is active in training)")
+                                      "(pos_encoder.dropout is active in training): call .eval() first")
+        if torch.is_grad_enabled() and (inputs.requires_grad or any(
+                p.requires_grad for p in (self.input_fc.weight, self.input_fc2.weight, self.input_fc3.weight,
+                                          self.pos_encoder.fc.weight))):
+            raise NotImplementedError("groupnet_b200.PastEncoder: the folded front-end has no backward, so gradients "
+                                      "to input_fc* / pos_encoder would be dropped silently: wrap the call in "
+                                      "torch.no_grad() (or freeze the front-end parameters)")
         mt, bias = self.folded_frontend(agent_num, length, inputs.device)
         x = inputs.contiguous()
         out = torch.empty(batch_size, agent_num, self.model_dim, dtype=torch.float32, device=inputs.device)

@@ -22,10 +22,25 @@ import torch.nn as nn
 
 from . import ops
 from .layers import MS_HGNN_hyper, MS_HGNN_oridinary
+from .packing import RuntimeStateMixin
 
 _HYPER_NAMES = ("interaction_hyper", "interaction_hyper2", "interaction_hyper3")
 
 _cudart = None
+
+
+def _loaded_cudart_path() -> str:
+    """The CUDA runtime this process already uses (the one torch / libgroupnet_b200.so loaded), whatever its
+    major version; opening a second runtime by a hard-coded soname would be wrong under another CUDA build."""
+    try:
+        with open("/proc/self/maps") as maps:
+            for line in maps:
+                path = line.rsplit(" ", 1)[-1].strip()
+                if "libcudart" in path and ".so" in path:
+                    return path
+    except OSError:
+        pass
+    return "libcudart.so"
 
 
 def _memcpy2d_d2h(dst_host: torch.Tensor, src_dev: torch.Tensor, col0: int, ncols: int, stream) -> None:
@@ -34,7 +49,7 @@ def _memcpy2d_d2h(dst_host: torch.Tensor, src_dev: torch.Tensor, col0: int, ncol
     global _cudart
     import ctypes
     if _cudart is None:
-        _cudart = ctypes.CDLL("libcudart.so.12")
+        _cudart = ctypes.CDLL(_loaded_cudart_path())
         _cudart.cudaMemcpy2DAsync.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                               ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
         _cudart.cudaMemcpy2DAsync.restype = ctypes.c_int
@@ -46,7 +61,13 @@ def _memcpy2d_d2h(dst_host: torch.Tensor, src_dev: torch.Tensor, col0: int, ncol
         raise RuntimeError(f"cudaMemcpy2DAsync failed with cudaError {rc}")
 
 
-class MultiScaleInteraction(nn.Module):
+class MultiScaleInteraction(RuntimeStateMixin, nn.Module):
+    _RUNTIME_ATTRS = ("_stream_cache", "_buf_cache")
+
+    def _reset_runtime(self) -> None:
+        self.__dict__.pop("_stream_cache", None)
+        self.__dict__.pop("_buf_cache", None)
+
     def __init__(self, model_dim: int = 64, hyper_scales: Sequence[int] = (5, 11), nmp_layers: int = 1):
         super().__init__()
         if len(hyper_scales) > 3:
@@ -124,12 +145,17 @@ class MultiScaleInteraction(nn.Module):
     @torch.no_grad()
     def forward_host(self, x_host: torch.Tensor, out_feature_host: Optional[torch.Tensor] = None,
                      out_H_host: Optional[torch.Tensor] = None, chunk_scenes: int = 8192,
-                     device: Optional[torch.device] = None, input_slice: str = "auto"):
+                     device: Optional[torch.device] = None, input_slice: str = "auto", sync: bool = True):
         """Host tensors in, host tensors out; copies and compute overlapped.
 
         x_host (B,N,D) fp32, ideally pinned.  Returns (final_feature, new_H) on
-        the host (pinned).  Scene i of chunk c gets Philox offset = global scene
-        index, so the result does not depend on `chunk_scenes`."""
+        the host (pinned).  With `sync=True` (default) the call returns when the
+        outputs are complete on the host; `sync=False` returns as soon as the work
+        is enqueued and hands back a third value, the CUDA event to wait on before
+        reading them.  Scene i of chunk c gets Philox offset = global scene index,
+        and with rng="cpu-compat" the uniforms of the WHOLE batch are drawn first,
+        one torch.rand(B,E,T) per layer in the reference's order
+        (model/MS_HGNN_batch.py:454), so the result does not depend on `chunk_scenes`."""
         if x_host.is_cuda:
             raise ValueError("forward_host takes host tensors; call forward() for device tensors")
         dev = device or next(self.parameters()).device
@@ -165,6 +191,13 @@ class MultiScaleInteraction(nn.Module):
             s_in.wait_event(start)
             s_out.wait_event(start)
             nchunk = (b + cs - 1) // cs
+            full_noise = None
+            if nchunk > 1 and any(l.rng == "cpu-compat" for l in self.layers()):
+                if any(l.nmp_layers > 1 for l in self.layers()):
+                    raise ValueError('forward_host: rng="cpu-compat" with nmp_layers > 1 needs the whole batch in one '
+                                     "chunk (chunk_scenes >= B) to keep the reference's draw order")
+                full_noise = [torch.rand(b, e_l, l.edge_types).float() if l.rng == "cpu-compat" else None
+                              for l, e_l in zip(self.layers(), [n * n] + [ops.incidence_rows(n, s_) for s_ in self.hyper_scales])]
             for c in range(nchunk):
                 b0, b1 = c * cs, min(b, (c + 1) * cs)
                 k, m = c & 1, b1 - b0
@@ -181,7 +214,8 @@ class MultiScaleInteraction(nn.Module):
                     l.scene_offset, l._philox_calls = off + b0, calls
                 # the x slice of final_feature is already on the host: do not move it over PCIe twice
                 self.forward(xd[:m], out_feature=fd[:m], out_H=hd[:m] if rows else None,
-                             write_input_slice=not on_host)
+                             write_input_slice=not on_host,
+                             noise=None if full_noise is None else [None if u is None else [u[b0:b1]] for u in full_noise])
                 ev_cmp[k].record(main)
                 with torch.cuda.stream(s_out):
                     s_out.wait_event(ev_cmp[k])
@@ -197,7 +231,12 @@ class MultiScaleInteraction(nn.Module):
             for l, off, calls in zip(self.layers(), base_offsets, base_calls):
                 l.scene_offset, l._philox_calls = off, calls + 1
             main.wait_stream(s_out)
-        return out_feature_host, out_H_host
+            done = torch.cuda.Event()
+            done.record(main)
+        if sync:
+            done.synchronize()                                   # the D2H copies are non_blocking: wait for them here
+            return out_feature_host, out_H_host
+        return out_feature_host, out_H_host, done
 
     def _streams(self, dev):
         cache = self.__dict__.setdefault("_stream_cache", {})

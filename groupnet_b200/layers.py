@@ -26,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .packing import PackCache
+from .packing import PackCache, RuntimeStateMixin
 
 _MASK64 = (1 << 64) - 1
 # "fp32": FFMA kernels (1e-5); "tf32": the same 1e-5 contract on tensor cores (3xTF32 tcgen05 chains);
@@ -38,6 +38,66 @@ _PHILOX_CALL_STRIDE = 0x9E3779B97F4A7C15        # seed of call k = philox_seed +
 def _as_int64(v: int) -> int:
     v &= _MASK64
     return v - (1 << 64) if v >= (1 << 63) else v
+
+
+# --------------------------------------------------------------------------
+# module-level helpers of the reference that nothing on the path calls: kept importable
+# under their names with the reference's behaviour; plain tensor utilities, no kernels involved
+# --------------------------------------------------------------------------
+def encode_onehot(labels):
+    """One-hot rows in first-seen class order of `set(labels)` (model/MS_HGNN_batch.py:9-15)."""
+    import numpy as np
+    classes = set(labels)
+    classes_dict = {c: np.identity(len(classes))[i, :] for i, c in enumerate(classes)}
+    return np.array(list(map(classes_dict.get, labels)), dtype=np.int32)
+
+
+def make_mlp(dim_list, activation='relu', batch_norm=True, dropout=0):
+    """nn.Sequential of Linear (+BatchNorm1d) (+ReLU / LeakyReLU) (+Dropout) blocks (model/MS_HGNN_batch.py:17-29)."""
+    blocks = []
+    for dim_in, dim_out in zip(dim_list[:-1], dim_list[1:]):
+        blocks.append(nn.Linear(dim_in, dim_out))
+        if batch_norm:
+            blocks.append(nn.BatchNorm1d(dim_out))
+        if activation == 'relu':
+            blocks.append(nn.ReLU())
+        elif activation == 'leakyrelu':
+            blocks.append(nn.LeakyReLU())
+        if dropout > 0:
+            blocks.append(nn.Dropout(p=dropout))
+    return nn.Sequential(*blocks)
+
+
+def sample_gumbel(shape, eps=1e-10):
+    """-log(eps - log(U + eps)), U ~ torch.rand(shape) on the CPU generator (model/MS_HGNN_batch.py:446-455)."""
+    uniform = torch.rand(shape).float()
+    return -torch.log(eps - torch.log(uniform + eps))
+
+
+def my_softmax(input, axis=1):
+    """Softmax over `axis` through a transpose, as model/MS_HGNN_batch.py:517-520 computes it for the 3-D
+    tensors the layers pass (for those the reference's implicit-dim softmax acts on dim 0 of the transposed
+    tensor, i.e. on `axis`)."""
+    trans_input = input.transpose(axis, 0).contiguous()
+    soft_max_1d = torch.softmax(trans_input, dim=0 if trans_input.dim() in (0, 1, 3) else 1)
+    return soft_max_1d.transpose(axis, 0)
+
+
+def gumbel_softmax_sample(logits, tau=1, eps=1e-10):
+    """softmax((logits + g) / tau) over the last dim (model/MS_HGNN_batch.py:458-473)."""
+    gumbel_noise = sample_gumbel(logits.size(), eps=eps).to(logits.device)
+    return my_softmax((logits + gumbel_noise) / tau, axis=-1)
+
+
+def gumbel_softmax(logits, tau=1, hard=False, eps=1e-10):
+    """Gumbel-softmax sample, optionally straight-through one-hot (model/MS_HGNN_batch.py:475-515)."""
+    y_soft = gumbel_softmax_sample(logits, tau=tau, eps=eps)
+    if not hard:
+        return y_soft
+    _, k = y_soft.data.max(-1)
+    y_hard = torch.zeros(*logits.size(), device=logits.device)
+    y_hard = y_hard.scatter_(-1, k.view(tuple(logits.size()[:-1]) + (1,)), 1.0)
+    return (y_hard - y_soft.data) + y_soft
 
 
 # --------------------------------------------------------------------------
@@ -103,9 +163,15 @@ class edge_aggregation(nn.Module):
 # --------------------------------------------------------------------------
 # shared machinery of both layers
 # --------------------------------------------------------------------------
-class _MessagePassingLayer(nn.Module):
+class _MessagePassingLayer(RuntimeStateMixin, nn.Module):
     edge_types: int
     _pairwise: bool
+    _RUNTIME_ATTRS = ("_packs", "_ws", "_seed_dev")
+
+    def _reset_runtime(self) -> None:
+        self.__dict__["_packs"] = PackCache()
+        self.__dict__["_ws"] = ops.Workspace()
+        self.__dict__.pop("_seed_dev", None)
 
     def _build_tree(self, h_dim, bottleneck_dim, nmp_layers):
         """Sub-module tree in the reference's registration order (:75-91 / :296-311)."""
@@ -121,9 +187,9 @@ class _MessagePassingLayer(nn.Module):
         self.edge_aggregation_list = nn.ModuleList(
             edge_aggregation(input_dim=h_dim, output_dim=bottleneck_dim, hidden_size=(128,), edge_types=t)
             for _ in range(nmp_layers))
-        # runtime (not part of the state_dict)
-        self._packs = PackCache()
-        self._ws = ops.Workspace()
+        # runtime (not part of the state_dict, dropped by deepcopy / pickle: RuntimeStateMixin)
+        self._reset_runtime()
+        self._install_runtime_hooks()
         self.rng = "cpu-compat"
         self.precision = "fp32"
         self.philox_seed = 0
@@ -194,6 +260,12 @@ class _MessagePassingLayer(nn.Module):
         if h_states.dim() != 3:
             raise ValueError("h_states must be (B, N, h_dim)")
         if torch.is_grad_enabled() and (h_states.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if self.precision != "fp32" and not self.__dict__.get("_warned_train_precision"):
+                import warnings
+                warnings.warn(f'groupnet_b200: precision="{self.precision}" is an inference path; with autograd enabled '
+                              "the differentiable fp32 kernels run instead (wrap inference in torch.no_grad())",
+                              RuntimeWarning, stacklevel=3)
+                self.__dict__["_warned_train_precision"] = True
             return self._run_train(h_states, inc, e, noise, node_out, want_dist)
         h = h_states.detach().contiguous()
         b, n, d = h.shape
@@ -271,6 +343,9 @@ class _MessagePassingLayer(nn.Module):
         stages = self._packs.get(self, dev)
         n_stage = len(stages)
         t = self.edge_types
+        if b == 0:                                   # empty batch: empty outputs, like the inference path
+            out = h_states.new_zeros(0, n, stages[-1].dout) + 0.0 * h_states.sum()
+            return out, (h_states.new_zeros(0, e, t) if want_dist else None)
         us = self._noise_list(noise, b, e, n_stage, dev)
         if us is None:
             if self.rng == "philox-device":

@@ -170,7 +170,18 @@ def hyper_fused_stream(agg_params, d: int) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 # 3xTF32 weight streams (csrc/gn_chain_tf32.cu, csrc/gn_tf32.cuh)
 # ---------------------------------------------------------------------------
-TF_STAGE_BYTES = 16384
+TF_SMEM_BUDGET = 227 * 1024
+TF_NODE_BLOCK = 36 * (68 + 132) * 4
+TF_FIXED = (4 * 128 * 2 + 4 * 128 + 128 * 17) * 4 + 2048 * 4 + 1024
+
+
+def tf_stage_bytes(a0_k: int, nbuf: int, node_block: bool) -> int:
+    """Weight-ring stage of a chain whose staged A buffers hold `nbuf` x (128 x a0_k) hi+lo operands: the largest of
+    64 / 32 / 16 KB that leaves room for two stages; must match tfe::ring_stage_bytes (csrc/gn_chain_tf32.cuh)."""
+    used = nbuf * a0_k * 1024 + (TF_NODE_BLOCK if node_block else 0) + TF_FIXED
+    avail = max(TF_SMEM_BUDGET - used, 0)
+    return 65536 if avail >= 2 * 65536 else (32768 if avail >= 2 * 32768 else 16384)
+
 
 
 def tf32_split(w: torch.Tensor):
@@ -183,10 +194,10 @@ def tf32_split(w: torch.Tensor):
     return hi, rnd(w - hi)
 
 
-def tf_chunk_k(n: int, k: int) -> int:
-    """Largest multiple of 8 that divides K and keeps an (N x kc) hi+lo chunk inside one 16 KB ring stage;
+def tf_chunk_k(n: int, k: int, stage_bytes: int) -> int:
+    """Largest multiple of 8 that divides K and keeps an (N x kc) hi+lo chunk inside one ring stage;
     must match tfe::Builder::chunk_k."""
-    kc = (TF_STAGE_BYTES // 8) // n // 8 * 8
+    kc = (stage_bytes // 8) // n // 8 * 8
     kc = min(kc, k)
     while kc > 8 and k % kc:
         kc -= 8
@@ -199,18 +210,20 @@ def _canon32(m: torch.Tensor) -> torch.Tensor:
     return m.reshape(r, k // 4, 4).permute(1, 0, 2).contiguous().reshape(-1)
 
 
-def tf_stream(mats) -> torch.Tensor:
+def tf_stream(mats, stage_bytes: int, tail=None) -> torch.Tensor:
     """Weight stream of a chain: for every nn.Linear.weight (N, K) in consumption order, K chunks of kc columns,
-    each chunk = canonical hi copy followed by canonical lo copy."""
+    each chunk = canonical hi copy followed by canonical lo copy; `tail`: plain fp32 values appended after the chunks."""
     parts = []
     for w in mats:
         n, k = w.shape
         assert n % 16 == 0 and 16 <= n <= 256 and k % 8 == 0, (n, k)
-        kc = tf_chunk_k(n, k)
+        kc = tf_chunk_k(n, k, stage_bytes)
         hi, lo = tf32_split(w.contiguous())
         for c in range(k // kc):
             parts.append(_canon32(hi[:, c * kc:(c + 1) * kc].contiguous()))
             parts.append(_canon32(lo[:, c * kc:(c + 1) * kc].contiguous()))
+    if tail is not None:
+        parts.append(tail.reshape(-1).to(torch.float32))
     return torch.cat(parts).contiguous()
 
 
@@ -324,24 +337,29 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
     w4 = torch.zeros(16, 128, dtype=torch.float32, device=device)
     w4[:t] = dev(dist[1].weight)
     out["tf_chain_w"] = tf_stream([dev(init[0].weight), dev(init[1].weight), dev(fac[0].weight),
-                                   dev(dist[0].weight), w4])
+                                   dev(dist[0].weight), w4], min(tf_stage_bytes(64, 1, False), tf_stage_bytes(0, 1, True)),
+                                  tail=dev(fac[1].weight))            # the factor head (128 -> 1) is a dot in the drain
     if d % 8 == 0 and d <= 128:
         nw0, nw1 = dev(node[0].weight), dev(node[1].weight)
-        out["tf_pre_w"] = tf_stream([nw0[:128], nw1[:, :128], nw0[128:], nw1[:, 128:],
-                                     torch.cat((w0[:, :64], w0[:, 64:]), dim=0)])
+        pre = [nw0[:128], nw1[:, :128], nw0[128:], nw1[:, 128:], torch.cat((w0[:, :64], w0[:, 64:]), dim=0)]
         if layer._pairwise:
-            out["tf_aggin_w"] = tf_stream([dev(m.layers[0].weight) for m in agg])
-    if d % 32 == 0 and d <= 128:
+            pre.append(dev(init[0].weight))          # Y = x' W_init0^T per node (csrc/gn_chain_tf32.cu, pair form)
+        out["tf_pre_w"] = tf_stream(pre, tf_stage_bytes(d, 1, False))
+        if layer._pairwise:
+            out["tf_aggin_w"] = tf_stream([dev(m.layers[0].weight) for m in agg], tf_stage_bytes(d, 1, False))
+    if d in (64, 128):
         if layer._pairwise:
             w1cat = torch.cat([dev(m.layers[1].weight) for m in agg], dim=1)      # (D, T*128)
-            out["tf_aggout_w"] = tf_stream([w1cat[:, 64 * c:64 * (c + 1)] for c in range(2 * t)])
+            out["tf_aggout_w"] = tf_stream([w1cat[:, 64 * c:64 * (c + 1)] for c in range(2 * t)],
+                                           tf_stage_bytes(64, 2, False))
         else:
             mats = []
             for m in agg:
                 mats += [dev(m.layers[0].weight), dev(m.layers[1].weight)]
-            out["tf_hagg_w"] = tf_stream(mats)
-    if d % 4 == 0 and d <= 64 and dout % 32 == 0 and dout <= 128:
-        out["tf_post_w"] = tf_stream([dev(post_mod.layers[0].weight), dev(post_mod.layers[1].weight)])
+            out["tf_hagg_w"] = tf_stream(mats, tf_stage_bytes(d, 1, False))
+    if d % 4 == 0 and d <= 64 and dout in (64, 128):
+        out["tf_post_w"] = tf_stream([dev(post_mod.layers[0].weight), dev(post_mod.layers[1].weight)],
+                                     tf_stage_bytes(2 * d, 1, False))
 
     out["post_w0t"] = _kmajor(dev(post_mod.layers[0].weight), k2p, 128, 128)
     out["post_b0"] = dev(post_mod.layers[0].bias)
@@ -367,9 +385,56 @@ class PackedStage:
             setattr(self.struct, name, C.c_void_p(tens.data_ptr()))
 
 
+def _invalidate_after_load(module, incompatible_keys) -> None:
+    """load_state_dict post-hook (module-level so that modules carrying it still pickle)."""
+    module.invalidate_packs()
+
+
+class RuntimeStateMixin:
+    """Runtime caches (packed weights, workspaces, streams) live as plain attributes on the modules; they hold
+    ctypes structures and device scratch that must not travel with a copy of the module.  Subclasses list the
+    attribute names in `_RUNTIME_ATTRS` and rebuild them in `_reset_runtime()`:
+
+      * `copy.deepcopy(m)`, `pickle` / `torch.save(m)` drop them and the copy starts with fresh caches;
+      * `nn.DataParallel` replicas (shallow `__dict__` copies) get their own caches, not a shared workspace;
+      * `load_state_dict` invalidates the packed weights;
+      * `invalidate_packs()` is the explicit hook for writes that autograd's version counter does not see
+        (`p.data.mul_(2)`, `nn.init.*_(p.data)`): the pack cache is keyed on (data_ptr, _version)."""
+    _RUNTIME_ATTRS: Tuple[str, ...] = ()
+
+    def _reset_runtime(self) -> None:          # pragma: no cover - overridden
+        pass
+
+    def invalidate_packs(self):
+        """Forget every packed / folded copy of the weights held by this module and its sub-modules."""
+        for m in self.modules():
+            if isinstance(m, RuntimeStateMixin):
+                m._reset_runtime()
+        return self
+
+    def _install_runtime_hooks(self) -> None:
+        self.register_load_state_dict_post_hook(_invalidate_after_load)
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._RUNTIME_ATTRS:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._reset_runtime()
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica._reset_runtime()
+        return replica
+
+
 class PackCache:
     """Per-layer cache of PackedStage objects, invalidated when a parameter is
-    modified in place (optimizer step, load_state_dict) or moved."""
+    modified in place through autograd-visible ops (optimizer step, load_state_dict, copy_) or moved.
+    Writes through `.data` do not bump `_version`: call `invalidate_packs()` on the module after them."""
 
     def __init__(self) -> None:
         self._key = None

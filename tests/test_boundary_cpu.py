@@ -323,3 +323,80 @@ def test_pack_cache_is_reused_until_a_parameter_changes():
     assert fourth is not third and torch.count_nonzero(fourth[-1].tensors["post_w0t"]) == 0
     m.double().float()                                                       # storage replaced, same values
     assert m._packs.get(m, cpu) is not fourth
+
+
+# ---- the reference's unused module-level helpers stay importable ----------------------
+@pytest.mark.skipif(not have_reference(), reason="reference tree not present")
+def test_unused_helpers_match_the_reference():
+    import sys
+    sys.path.insert(0, REFERENCE_DIR)
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            from model import MS_HGNN_batch as R
+            assert (gb.encode_onehot([3, 1, 3, 2]) == R.encode_onehot([3, 1, 3, 2])).all()
+            torch.manual_seed(5)
+            a = gb.make_mlp([4, 8, 3], activation='leakyrelu', batch_norm=True, dropout=0.1)
+            torch.manual_seed(5)
+            b = R.make_mlp([4, 8, 3], activation='leakyrelu', batch_norm=True, dropout=0.1)
+            assert [type(m) for m in a] == [type(m) for m in b]
+            assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))
+            torch.manual_seed(6)
+            g1 = gb.sample_gumbel((3, 4, 5))
+            torch.manual_seed(6)
+            assert torch.equal(g1, R.sample_gumbel((3, 4, 5)))
+            x = torch.randn(2, 3, 5)
+            for axis in (1, 2, -1):
+                assert torch.allclose(gb.my_softmax(x, axis), R.my_softmax(x, axis), atol=1e-7)
+            assert torch.allclose(gb.my_softmax(x[0], 1), R.my_softmax(x[0], 1), atol=1e-7)   # the 2-D quirk (axis 0 wins)
+            for hard in (False, True):
+                torch.manual_seed(7)
+                y1 = gb.gumbel_softmax(x, tau=0.5, hard=hard)
+                torch.manual_seed(7)
+                y2 = R.gumbel_softmax(x, tau=0.5, hard=hard)
+                assert torch.allclose(y1, y2, atol=1e-6)
+            torch.manual_seed(8)
+            y1 = gb.gumbel_softmax_sample(x, tau=0.5)
+            torch.manual_seed(8)
+            assert torch.allclose(y1, R.gumbel_softmax_sample(x, tau=0.5), atol=1e-7)
+    finally:
+        sys.path.remove(REFERENCE_DIR)
+
+
+# ---- runtime caches never travel with a copy of the module ----------------------------------
+def test_modules_deepcopy_and_pickle_without_their_runtime_caches():
+    import copy
+    import io
+    import types
+    from groupnet_b200.packing import PackCache
+    m = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=3)
+    m._packs._stages = [ctypes.c_void_p(1234)]            # what a forward leaves behind: ctypes objects do not pickle
+    m._packs._key = ("stale",)
+    c = copy.deepcopy(m)
+    assert isinstance(c._packs, PackCache) and c._packs is not m._packs and c._packs._key is None
+    assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), m.state_dict().values()))
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert r._packs._key is None and r.scale == 3 and list(r.state_dict()) == list(m.state_dict())
+    # explicit invalidation and the load_state_dict hook
+    m.invalidate_packs()
+    assert m._packs._key is None
+    m._packs._key = ("stale",)
+    m.load_state_dict(c.state_dict())
+    assert m._packs._key is None
+    # DataParallel-style replicas get their own caches
+    rep = m._replicate_for_data_parallel()
+    assert rep._packs is not m._packs and rep._ws is not m._ws
+    enc = gb.PastEncoder(types.SimpleNamespace(hidden_dim=64, hyper_scales=[5], past_length=5))
+    enc._fold_key = ("stale",)
+    e2 = copy.deepcopy(enc)
+    assert e2._fold_key is None and e2._block is None
+    enc.invalidate_packs()
+    assert enc._fold_key is None
+    dec = gb.Decoder(types.SimpleNamespace(hidden_dim=64, hyper_scales=[5, 11], zdim=32, past_length=5,
+                                           future_length=10, num_decompose=1))
+    dec._pack_key = ("stale",)
+    assert copy.deepcopy(dec)._pack_key is None

@@ -27,7 +27,7 @@ def _inference_mode(request):
 
 def test_native_library_is_loaded():
     lib = _lib.load()
-    assert lib.gn_abi_version() == 2
+    assert lib.gn_abi_version() == _lib.ABI_VERSION == 3
     maps = open("/proc/self/maps").read()
     assert "libgroupnet_b200.so" in maps
 
@@ -328,9 +328,49 @@ def test_multiscale_interaction_matches_layers_and_host_pipeline():
     for cs, mode in ((1000, "auto"), (256, "host"), (77, "device"), (300, "device")):
         m.set_rng("philox", seed=11)
         f_host, h_host = m.forward_host(x.pin_memory(), chunk_scenes=cs, input_slice=mode)
-        torch.cuda.synchronize()
+        # no synchronize here: forward_host returns when its outputs are complete on the host
         assert torch.equal(f_host, f_dev.cpu()) and torch.equal(h_host, h_dev.cpu()), (cs, mode)
+    m.set_rng("philox", seed=11)
+    f_host, h_host, done = m.forward_host(x.pin_memory(), chunk_scenes=300, sync=False)
+    done.synchronize()
+    assert torch.equal(f_host, f_dev.cpu()) and torch.equal(h_host, h_dev.cpu())
     assert m.launches_per_forward(b, n) == 1 + 5 + 6 + 6
+    # reference RNG contract through the host pipeline: the whole batch's uniforms are drawn first, per layer in
+    # the reference's order, so chunking does not change which draw a scene gets
+    m.set_rng("cpu-compat")
+    torch.manual_seed(99)
+    f_one, _ = m(x.to(DEV))
+    for cs in (1000, 256):
+        torch.manual_seed(99)
+        f_chunked, _ = m.forward_host(x.pin_memory(), chunk_scenes=cs)
+        assert torch.equal(f_chunked, f_one.cpu()), cs
+
+
+def test_pack_cache_invalidation_and_module_copies():
+    """ADVICE r1: writes through .data are invisible to the (data_ptr, _version) key -> invalidate_packs();
+    deepcopy after a forward must work and give an independent module."""
+    import copy
+    torch.manual_seed(4)
+    m = gb.MS_HGNN_oridinary(16, 64, 64, 64, batch_norm=0, nmp_layers=1).to(DEV).eval()
+    h = torch.randn(5, 6, 64, device=DEV)
+    u = torch.rand(5, 36, 6, device=DEV)
+    out1, _ = m(h, noise=[u])
+    w = m.nmp_mlp_end.layers[1].weight
+    w.data.mul_(2.0)                                    # does not bump w._version
+    m.invalidate_packs()
+    out2, _ = m(h, noise=[u])
+    assert not torch.equal(out1, out2)
+    c = copy.deepcopy(m)                                 # the original holds ctypes structs by now
+    out3, _ = c(h, noise=[u])
+    assert torch.equal(out2, out3)
+    with torch.no_grad():
+        c.nmp_mlp_end.layers[1].weight.mul_(0.5)         # autograd-visible in-place write: cache key changes
+    out4, _ = c(h, noise=[u])
+    assert torch.equal(out4, out1)                        # x2 then x0.5 is exact
+    assert torch.equal(m(h, noise=[u])[0], out2)         # the copy's update did not touch the original
+    sd = {k: v.clone() for k, v in c.state_dict().items()}
+    m.load_state_dict(sd)                                # post-hook invalidates
+    assert torch.equal(m(h, noise=[u])[0], out4)
 
 
 # ---- bf16 tensor-core (tcgen05) path: 2e-2 (BASELINE.json north_star) ------------------

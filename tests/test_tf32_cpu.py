@@ -38,12 +38,12 @@ def test_three_term_product_reaches_fp32_grade():
     assert (one.double() - ref).abs().max() / scale > 1e-5
 
 
-def _decode(stream: torch.Tensor, shapes):
+def _decode(stream: torch.Tensor, shapes, stage_bytes, tail=0):
     """Inverse of packing.tf_stream: rebuild every (N, K) matrix (hi + lo) from the chunked canonical stream."""
     out, off = [], 0
     for n, k in shapes:
-        kc = packing.tf_chunk_k(n, k)
-        assert n * kc * 8 <= packing.TF_STAGE_BYTES and k % kc == 0 and kc % 8 == 0
+        kc = packing.tf_chunk_k(n, k, stage_bytes)
+        assert n * kc * 8 <= stage_bytes and k % kc == 0 and kc % 8 == 0
         w = torch.zeros(n, k, dtype=torch.float64)
         for c in range(k // kc):
             for part in range(2):                                   # hi, then lo
@@ -51,7 +51,7 @@ def _decode(stream: torch.Tensor, shapes):
                 w[:, c * kc:(c + 1) * kc] += blk.permute(1, 0, 2).reshape(n, kc).double()
                 off += n * kc
         out.append(w)
-    assert off == stream.numel()
+    assert off + tail == stream.numel()
     return out
 
 
@@ -67,27 +67,32 @@ def test_weight_streams_follow_the_documented_order():
     def close(a, b):
         return (a - b.detach().double()).abs().max() <= b.abs().max() * 2.0 ** -21
 
-    w = _decode(t["tf_chain_w"], [(128, 64), (64, 128), (128, 64), (128, 64), (16, 128)])
+    s64, s32 = 65536, 32768
+    assert packing.tf_stage_bytes(0, 1, True) == s64 and packing.tf_stage_bytes(64, 1, False) == s64
+    assert packing.tf_stage_bytes(64, 2, False) == s32 and packing.tf_stage_bytes(128, 1, False) == s32
+    w = _decode(t["tf_chain_w"], [(128, 64), (64, 128), (128, 64), (128, 64), (16, 128)], s64, tail=128)
+    assert torch.equal(t["tf_chain_w"][-128:], ms.MLP_factor.layers[1].weight.detach().reshape(-1))
     assert close(w[0], ms.init_MLP.layers[0].weight) and close(w[1], ms.init_MLP.layers[1].weight)
     assert close(w[2], ms.MLP_factor.layers[0].weight) and close(w[3], ms.MLP_distribution.layers[0].weight)
     assert close(w[4][:6], ms.MLP_distribution.layers[1].weight) and w[4][6:].abs().max() == 0
-    w = _decode(t["tf_pre_w"], [(128, 64), (64, 128), (128, 64), (64, 128), (64, 64)])
+    w = _decode(t["tf_pre_w"], [(128, 64), (64, 128), (128, 64), (64, 128), (64, 64), (128, 64)], s64)
+    assert close(w[5], ms.init_MLP.layers[0].weight)              # pairwise layers: Y = x' W_init0^T in the prologue
     assert close(w[0], node[0].weight[:128]) and close(w[2], node[0].weight[128:])
     assert close(w[1], node[1].weight[:, :128]) and close(w[3], node[1].weight[:, 128:])
     assert close(w[4], torch.cat((att[:, :64], att[:, 64:]), dim=0))
-    w = _decode(t["tf_aggin_w"], [(128, 64)] * 6)
+    w = _decode(t["tf_aggin_w"], [(128, 64)] * 6, s64)
     assert all(close(w[i], agg[i].layers[0].weight) for i in range(6))
-    w = _decode(t["tf_aggout_w"], [(64, 64)] * 12)
+    w = _decode(t["tf_aggout_w"], [(64, 64)] * 12, s32)
     for i in range(6):
         assert close(torch.cat((w[2 * i], w[2 * i + 1]), dim=1), agg[i].layers[1].weight)
-    w = _decode(t["tf_post_w"], [(128, 128), (64, 128)])
+    w = _decode(t["tf_post_w"], [(128, 128), (64, 128)], s32)
     assert close(w[0], pair.nmp_mlp_end.layers[0].weight) and close(w[1], pair.nmp_mlp_end.layers[1].weight)
     assert "tf_hagg_w" not in t
 
     hyp = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=5)
     t = packing.pack_stage(hyp, 0, torch.device("cpu"))
     agg = hyp.edge_aggregation_list[0].agg_mlp
-    w = _decode(t["tf_hagg_w"], [(128, 64), (64, 128)] * 10)
+    w = _decode(t["tf_hagg_w"], [(128, 64), (64, 128)] * 10, 65536)
     for i in range(10):
         assert close(w[2 * i], agg[i].layers[0].weight) and close(w[2 * i + 1], agg[i].layers[1].weight)
     assert "tf_aggin_w" not in t and "tf_aggout_w" not in t
@@ -96,4 +101,6 @@ def test_weight_streams_follow_the_documented_order():
 def test_chunk_rule_matches_the_ring_stage():
     for n, k, want in [(128, 64, 16), (64, 128, 32), (16, 128, 128), (64, 64, 32), (128, 128, 16), (256, 64, 8),
                        (48, 128, 32), (96, 128, 16), (32, 128, 64)]:
-        assert packing.tf_chunk_k(n, k) == want
+        assert packing.tf_chunk_k(n, k, 16384) == want
+    for n, k, want in [(128, 64, 64), (64, 128, 128), (16, 128, 128), (128, 128, 64)]:
+        assert packing.tf_chunk_k(n, k, 65536) == want
