@@ -268,11 +268,14 @@ edge_chain_tc_kernel(TcChainArgs a) {
     GN_TRACE(1);
 
     // ---- G1: 64 -> 128 ----
-    if (gtid == 0) {
+    if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
       fence_after_thread_sync();
-      issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB1, 128);
-      issue_gemm(tmem_grp, sA0_addr, sbase + OFF_W1, 128, 64, true);
-      mma_commit(mbar);
+      if (elect_one()) {
+        issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB1, 128);
+        issue_gemm(tmem_grp, sA0_addr, sbase + OFF_W1, 128, 64, true);
+        mma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase); phase ^= 1;
     GN_TRACE(2);
@@ -283,11 +286,14 @@ edge_chain_tc_kernel(TcChainArgs a) {
     chain_group_bar(grp);
 
     // ---- G2: 128 -> 64 (z) ----
-    if (gtid == 0) {
+    if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
       fence_after_thread_sync();
-      issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB2, 64);
-      issue_gemm(tmem_grp, sA1_addr, sbase + OFF_W2, 64, 128, true);
-      mma_commit(mbar);
+      if (elect_one()) {
+        issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB2, 64);
+        issue_gemm(tmem_grp, sA1_addr, sbase + OFF_W2, 64, 128, true);
+        mma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase); phase ^= 1;
     GN_TRACE(4);
@@ -298,11 +304,14 @@ edge_chain_tc_kernel(TcChainArgs a) {
     chain_group_bar(grp);
 
     // ---- G3: 64 -> 256 ([distribution | factor] hidden), accumulator drained in two halves ----
-    if (gtid == 0) {
+    if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
       fence_after_thread_sync();
-      issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB3, 256);
-      issue_gemm(tmem_grp, sA0_addr, sbase + OFF_W3, 256, 64, true);
-      mma_commit(mbar);
+      if (elect_one()) {
+        issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB3, 256);
+        issue_gemm(tmem_grp, sA0_addr, sbase + OFF_W3, 256, 64, true);
+        mma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase); phase ^= 1;
     GN_TRACE(6);
@@ -312,11 +321,14 @@ edge_chain_tc_kernel(TcChainArgs a) {
     fence_before_thread_sync();
     chain_group_bar(grp);
     // G4a: bias + k in [0,128) -> TMEM columns [0,16) (already drained)
-    if (gtid == 0) {
+    if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
       fence_after_thread_sync();
-      issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB4, 16);
-      issue_gemm(tmem_grp, sA1_addr, sbase + OFF_W4, 16, 128, true);
-      mma_commit(mbar);
+      if (elect_one()) {
+        issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB4, 16);
+        issue_gemm(tmem_grp, sA1_addr, sbase + OFF_W4, 16, 128, true);
+        mma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase); phase ^= 1;
     GN_TRACE(8);       // A1 is free again
@@ -326,10 +338,13 @@ edge_chain_tc_kernel(TcChainArgs a) {
     fence_before_thread_sync();
     chain_group_bar(grp);
     // G4b: k in [128,256), accumulate
-    if (gtid == 0) {
+    if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
       fence_after_thread_sync();
-      issue_gemm(tmem_grp, sA1_addr, sbase + OFF_W4 + 16 * (16 * 16), 16, 128, true);
-      mma_commit(mbar);
+      if (elect_one()) {
+        issue_gemm(tmem_grp, sA1_addr, sbase + OFF_W4 + 16 * (16 * 16), 16, 128, true);
+        mma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase); phase ^= 1;
     GN_TRACE(10);

@@ -125,11 +125,14 @@ hyper_agg_tc_kernel(HyperAggArgs a) {
     fence_proxy_async_smem();
     fence_before_thread_sync();
     hagg_group_bar(grp);
-    if (gtid == 0) {
+    if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
       fence_after_thread_sync();
-      issue_bias(tmem_grp, sbase + OFF_ONES, gbase + G_BB, 128);
-      issue_gemm(tmem_grp, gbase + G_A, gbase + G_W0, 128, 64, true);
-      mma_commit(mbarA);
+      if (elect_one()) {
+        issue_bias(tmem_grp, sbase + OFF_ONES, gbase + G_BB, 128);
+        issue_gemm(tmem_grp, gbase + G_A, gbase + G_W0, 128, 64, true);
+        mma_commit(mbarA);
+      }
+      __syncwarp();
     }
 
 #pragma unroll 1
@@ -168,15 +171,18 @@ hyper_agg_tc_kernel(HyperAggArgs a) {
       fence_proxy_async_smem();
       fence_before_thread_sync();
       hagg_group_bar(grp);
-      if (gtid == 0) {
+      if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
         fence_after_thread_sync();
-        issue_gemm(tmem_grp + 128, gbase + G_A1, gbase + G_W1 + (t & 1) * (64 * 128 * 2), 64, 128, t > 0);
-        mma_commit(mbarB);
-        if (t + 1 < T) {                                 // next hidden right behind it on the tensor pipe
-          issue_bias(tmem_grp, sbase + OFF_ONES, gbase + G_BB, 128);
-          issue_gemm(tmem_grp, gbase + G_A, gbase + G_W0, 128, 64, true);
-          mma_commit(mbarA);
+        if (elect_one()) {
+          issue_gemm(tmem_grp + 128, gbase + G_A1, gbase + G_W1 + (t & 1) * (64 * 128 * 2), 64, 128, t > 0);
+          mma_commit(mbarB);
+          if (t + 1 < T) {                                 // next hidden right behind it on the tensor pipe
+            issue_bias(tmem_grp, sbase + OFF_ONES, gbase + G_BB, 128);
+            issue_gemm(tmem_grp, gbase + G_A, gbase + G_W0, 128, 64, true);
+            mma_commit(mbarA);
+          }
         }
+        __syncwarp();
       }
     }
     // ---- epilogue: ef = acc + sum_t edge_feat[row][t] b1_t

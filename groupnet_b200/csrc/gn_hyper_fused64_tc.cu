@@ -55,8 +55,8 @@ struct HyperFused64Args {
 
 namespace {
 __device__ __forceinline__ void arrive(uint64_t* b) { tc::mbar_arrive(b); }
-__device__ __forceinline__ void expect_tx(uint64_t* b, uint32_t bytes) { tc::mbar_expect_tx(b, bytes); }
-using tc::bulk_g2s; using tc::drain_bar; using tc::stage_raw_H;
+// producer-warp forms: every lane calls them, one elected lane issues (gn_tc.cuh, tcu)
+using tcu::expect_tx; using tcu::bulk_g2s; using tc::drain_bar; using tc::stage_raw_H;
 }  // namespace
 
 __global__ void __launch_bounds__(hf64::THREADS, 2)
@@ -89,7 +89,7 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
 
   if (warp == 8) {
     // ------------------------------------------------------------------ weight stream producer
-    if (lane == 0) {
+    {                                                   // all 32 lanes: warp-uniform control flow, elected issue
       uint32_t ph_empty = 0x3u, ph_eofull = 0u, ph_agg = 0u;
       int stage = 0;
       auto load = [&](const unsigned char*& src, uint32_t bytes) {
@@ -120,15 +120,15 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {                                                   // all 32 lanes: warp-uniform control flow, elected issue
       uint32_t ph = 1u << B_HFREE;                       // "free" barrier: the first wait passes
       int stage = 0;
       auto wait = [&](int i) { tc::mbar_wait(bars + i, (ph >> i) & 1u); ph ^= 1u << i; };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         wait(B_STAGE);
         tc::fence_after_thread_sync();
-        tc::issue_gemm(tmem + TM_S, sbase + OFF_SCR, sbase + OFF_HT, 64, 128, false);          // eo = Hblk * h
-        tc::mma_commit(bars + B_EOFULL);
+        tcu::issue_gemm(tmem + TM_S, sbase + OFF_SCR, sbase + OFF_HT, 64, 128, false);          // eo = Hblk * h
+        tcu::mma_commit(bars + B_EOFULL);
         wait(B_EOREADY);
         tc::fence_after_thread_sync();
         for (int s = 0; s <= T; ++s) {
@@ -136,37 +136,37 @@ hyper_fused64_tc_kernel(HyperFused64Args a) {
             wait(B_HFREE);
             wait(B_WFULL + stage);
             tc::fence_after_thread_sync();
-            tc::issue_gemm(tmem + TM_HID, sbase + OFF_EO, sbase + OFF_SCR + stage * STAGE, 128, 80, false);
-            tc::mma_commit(bars + B_WEMPTY + stage);
-            tc::mma_commit(bars + B_HFULL);
+            tcu::issue_gemm(tmem + TM_HID, sbase + OFF_EO, sbase + OFF_SCR + stage * STAGE, 128, 80, false);
+            tcu::mma_commit(bars + B_WEMPTY + stage);
+            tcu::mma_commit(bars + B_HFULL);
             stage ^= 1;
           }
           if (s >= 1) {
             wait(B_A2FULL);
             wait(B_WFULL + stage);
             tc::fence_after_thread_sync();
-            tc::issue_gemm(tmem + TM_S, sbase + OFF_A2, sbase + OFF_SCR + stage * STAGE, 64, 144, s > 1);
-            tc::mma_commit(bars + B_WEMPTY + stage);
-            tc::mma_commit(bars + B_A2FREE);
+            tcu::issue_gemm(tmem + TM_S, sbase + OFF_A2, sbase + OFF_SCR + stage * STAGE, 64, 144, s > 1);
+            tcu::mma_commit(bars + B_WEMPTY + stage);
+            tcu::mma_commit(bars + B_A2FREE);
             stage ^= 1;
           }
         }
-        tc::mma_commit(bars + B_EFFULL);
+        tcu::mma_commit(bars + B_EFFULL);
         wait(B_EFTREADY);
         tc::fence_after_thread_sync();
-        tc::issue_gemm(tmem + TM_S, sbase + OFF_SCR, sbase + OFF_HT, 64, 128, false);          // agg = HblkT * ef
-        tc::mma_commit(bars + B_AGGFULL);
+        tcu::issue_gemm(tmem + TM_S, sbase + OFF_SCR, sbase + OFF_HT, 64, 128, false);          // agg = HblkT * ef
+        tcu::mma_commit(bars + B_AGGFULL);
         wait(B_PAREADY);
         wait(B_PFULL0);
         tc::fence_after_thread_sync();
-        tc::issue_gemm(tmem + TM_HID, sbase + OFF_A2, sbase + OFF_SCR, 128, 144, false);       // o1 (pre-ReLU)
-        tc::mma_commit(bars + B_O1FULL);
+        tcu::issue_gemm(tmem + TM_HID, sbase + OFF_A2, sbase + OFF_SCR, 128, 144, false);       // o1 (pre-ReLU)
+        tcu::mma_commit(bars + B_O1FULL);
         wait(B_O1READY);
         wait(B_PFULL1);
         tc::fence_after_thread_sync();
-        tc::issue_gemm(tmem + TM_S, sbase + OFF_A2, sbase + OFF_EO, a.Dout, 128, false);
-        tc::issue_gemm(tmem + TM_S, sbase + OFF_A2 + 16 * 2048, sbase + OFF_PB, a.Dout, 16, true);
-        tc::mma_commit(bars + B_OUTFULL);
+        tcu::issue_gemm(tmem + TM_S, sbase + OFF_A2, sbase + OFF_EO, a.Dout, 128, false);
+        tcu::issue_gemm(tmem + TM_S, sbase + OFF_A2 + 16 * 2048, sbase + OFF_PB, a.Dout, 16, true);
+        tcu::mma_commit(bars + B_OUTFULL);
       }
     }
   } else {

@@ -63,7 +63,9 @@ struct HyperFusedArgs {
   unsigned long long* trace;          // optional: clock64() per phase, block 0, first tiles (gn_profile_set_trace)
 };
 
-using tc::mbar_arrive; using tc::mbar_expect_tx; using tc::bulk_g2s; using tc::drain_bar; using tc::stage_raw_H;
+// producer-warp forms: every lane calls them, one elected lane issues (gn_tc.cuh, tcu)
+using tc::mbar_arrive; using tcu::bulk_g2s; using tc::drain_bar; using tc::stage_raw_H;
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) { tcu::expect_tx(b, bytes); }
 
 __global__ void __launch_bounds__(hf::THREADS, 1)
 hyper_fused_tc_kernel(HyperFusedArgs a) {
@@ -94,7 +96,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
 
   if (warp == 8) {
     // ------------------------------------------------------------------ weight stream producer
-    if (lane == 0) {
+    {                                                   // all 32 lanes: warp-uniform control flow, elected issue
       uint32_t ph_empty = 0x7u, ph_eofull = 0u, ph_px = 1u, ph_agg = 0u;
       int stage = 0;
       auto load = [&](const unsigned char*& src, uint32_t bytes) {
@@ -138,7 +140,7 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {                                                   // all 32 lanes: warp-uniform control flow, elected issue
       uint32_t ph = 0u;                                  // bit i = parity to wait for on barrier i
       ph |= 0xFu << B_HFREE;                             // "free" barriers: the first wait passes
       int stage = 0;
@@ -159,8 +161,8 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
 #endif
         wait(B_STAGE);
         tc::fence_after_thread_sync();
-        tc::issue_gemm(tmem + TM_EF, sbase + OFF_A2, sbase + OFF_RING, 256, 128, false);     // eo = Hblk * h
-        tc::mma_commit(bars + B_EOFULL);
+        tcu::issue_gemm(tmem + TM_EF, sbase + OFF_A2, sbase + OFF_RING, 256, 128, false);     // eo = Hblk * h
+        tcu::mma_commit(bars + B_EOFULL);
         wait(B_EOREADY);
         tc::fence_after_thread_sync();
         stage = NSTAGE - 1;
@@ -170,15 +172,15 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
             wait_t(B_HFREE + p, 0);
             wait_t(B_WFULL + stage, 1);
             tc::fence_after_thread_sync();
-            tc::issue_gemm(tmem + TM_HB + p * 128, sbase + OFF_EO, sbase + OFF_RING + stage * STAGE, 128, 128, false);
-            tc::mma_commit(bars + B_WEMPTY + stage);
+            tcu::issue_gemm(tmem + TM_HB + p * 128, sbase + OFF_EO, sbase + OFF_RING + stage * STAGE, 128, 128, false);
+            tcu::mma_commit(bars + B_WEMPTY + stage);
             stage = stage == NSTAGE - 1 ? 0 : stage + 1;
             wait_t(B_WFULL + stage, 1);
             tc::fence_after_thread_sync();
-            tc::issue_gemm(tmem + TM_HB + p * 128, sbase + OFF_EO + 16 * 2048, sbase + OFF_RING + stage * STAGE,
+            tcu::issue_gemm(tmem + TM_HB + p * 128, sbase + OFF_EO + 16 * 2048, sbase + OFF_RING + stage * STAGE,
                            128, 144, true);
-            tc::mma_commit(bars + B_WEMPTY + stage);
-            tc::mma_commit(bars + B_HFULL + p);
+            tcu::mma_commit(bars + B_WEMPTY + stage);
+            tcu::mma_commit(bars + B_HFULL + p);
             stage = stage == NSTAGE - 1 ? 0 : stage + 1;
           }
           if (s >= 1) {
@@ -186,53 +188,53 @@ hyper_fused_tc_kernel(HyperFusedArgs a) {
               wait_t(B_A2FULL + j, 2);
               wait_t(B_WFULL + stage, 3);
               tc::fence_after_thread_sync();
-              tc::issue_gemm(tmem + TM_EF, sbase + (j ? OFF_A2_1 : OFF_A2), sbase + OFF_RING + stage * STAGE,
+              tcu::issue_gemm(tmem + TM_EF, sbase + (j ? OFF_A2_1 : OFF_A2), sbase + OFF_RING + stage * STAGE,
                              256, j ? 64 : 80, !(s == 1 && j == 0));
-              tc::mma_commit(bars + B_WEMPTY + stage);
-              tc::mma_commit(bars + B_A2FREE + j);
+              tcu::mma_commit(bars + B_WEMPTY + stage);
+              tcu::mma_commit(bars + B_A2FREE + j);
               stage = stage == NSTAGE - 1 ? 0 : stage + 1;
             }
           }
         }
-        tc::mma_commit(bars + B_EFFULL);
+        tcu::mma_commit(bars + B_EFFULL);
         wait(B_EFTREADY);
         tc::fence_after_thread_sync();
-        tc::issue_gemm(tmem + TM_AGG, sbase + OFF_A2, sbase + OFF_EO, 256, 128, false);       // agg = HblkT * ef
-        tc::mma_commit(bars + B_AGGFULL);
+        tcu::issue_gemm(tmem + TM_AGG, sbase + OFF_A2, sbase + OFF_EO, 256, 128, false);       // agg = HblkT * ef
+        tcu::mma_commit(bars + B_AGGFULL);
         if (a.post) {
           // o1 = relu([agg | h]/N W0^T + b0): four K chunks of 128 (A: eo region, then ring stages 0-1)
           wait(B_PAREADY);
           wait(B_WFULL + 2);
           tc::fence_after_thread_sync();
-          tc::issue_gemm(tmem + TM_O1, sbase + OFF_EO, sbase + OFF_Y, 128, 128, false);
-          tc::mma_commit(bars + B_WEMPTY + 2);
+          tcu::issue_gemm(tmem + TM_O1, sbase + OFF_EO, sbase + OFF_Y, 128, 128, false);
+          tcu::mma_commit(bars + B_WEMPTY + 2);
           wait(B_PXFULL);
           tc::fence_after_thread_sync();
-          tc::issue_gemm(tmem + TM_O1, sbase + OFF_EO + 16 * 2048, sbase + OFF_X, 128, 128, true);
-          tc::mma_commit(bars + B_PXEMPTY);
+          tcu::issue_gemm(tmem + TM_O1, sbase + OFF_EO + 16 * 2048, sbase + OFF_X, 128, 128, true);
+          tcu::mma_commit(bars + B_PXEMPTY);
           wait(B_WFULL + 2);
           tc::fence_after_thread_sync();
-          tc::issue_gemm(tmem + TM_O1, sbase + OFF_AH, sbase + OFF_Y, 128, 128, true);
-          tc::mma_commit(bars + B_WEMPTY + 2);
+          tcu::issue_gemm(tmem + TM_O1, sbase + OFF_AH, sbase + OFF_Y, 128, 128, true);
+          tcu::mma_commit(bars + B_WEMPTY + 2);
           wait(B_PXFULL);
           tc::fence_after_thread_sync();
-          tc::issue_gemm(tmem + TM_O1, sbase + OFF_AH + 16 * 2048, sbase + OFF_X, 128, 128, true);
-          tc::issue_gemm(tmem + TM_O1, sbase + OFF_ONES, sbase + OFF_X + P0_CHUNK, 128, 16, true);
-          tc::mma_commit(bars + B_PXEMPTY);
-          tc::mma_commit(bars + B_O1FULL);
+          tcu::issue_gemm(tmem + TM_O1, sbase + OFF_AH + 16 * 2048, sbase + OFF_X, 128, 128, true);
+          tcu::issue_gemm(tmem + TM_O1, sbase + OFF_ONES, sbase + OFF_X + P0_CHUNK, 128, 16, true);
+          tcu::mma_commit(bars + B_PXEMPTY);
+          tcu::mma_commit(bars + B_O1FULL);
           // out = o1 W1^T + b1: two K chunks of 64
           wait(B_O1READY);
           wait(B_WFULL + 2);
           tc::fence_after_thread_sync();
-          tc::issue_gemm(tmem + TM_OUT, sbase + OFF_EO, sbase + OFF_Y, a.Dout, 64, false);
-          tc::issue_gemm(tmem + TM_OUT, sbase + OFF_ONES, sbase + OFF_Y + static_cast<uint32_t>(a.Dout) * 128u,
+          tcu::issue_gemm(tmem + TM_OUT, sbase + OFF_EO, sbase + OFF_Y, a.Dout, 64, false);
+          tcu::issue_gemm(tmem + TM_OUT, sbase + OFF_ONES, sbase + OFF_Y + static_cast<uint32_t>(a.Dout) * 128u,
                          a.Dout, 16, true);
-          tc::mma_commit(bars + B_WEMPTY + 2);
+          tcu::mma_commit(bars + B_WEMPTY + 2);
           wait(B_PXFULL);
           tc::fence_after_thread_sync();
-          tc::issue_gemm(tmem + TM_OUT, sbase + OFF_EO + 8 * 2048, sbase + OFF_X, a.Dout, 64, true);
-          tc::mma_commit(bars + B_PXEMPTY);
-          tc::mma_commit(bars + B_OUTFULL);
+          tcu::issue_gemm(tmem + TM_OUT, sbase + OFF_EO + 8 * 2048, sbase + OFF_X, a.Dout, 64, true);
+          tcu::mma_commit(bars + B_PXEMPTY);
+          tcu::mma_commit(bars + B_OUTFULL);
         }
       }
     }

@@ -105,11 +105,14 @@ node_chain_tc_kernel(NodeChainArgs a) {
       const uint32_t w_addr = sbase + OFF_W + woff[s];
       const uint32_t a_addr = gbase + cur * BUF_BYTES;
       if (!acc_pending) {
-        if (gtid == 0) {
+        if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
           fence_after_thread_sync();
-          if (st.bias != nullptr) issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB + boff[s], st.N);
-          issue_gemm(tmem_grp, a_addr, w_addr, st.N, Kcur, st.bias != nullptr);
-          mma_commit(mbar);
+          if (elect_one()) {
+            if (st.bias != nullptr) issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB + boff[s], st.N);
+            issue_gemm(tmem_grp, a_addr, w_addr, st.N, Kcur, st.bias != nullptr);
+            mma_commit(mbar);
+          }
+          __syncwarp();
         }
         mbar_wait(mbar, phase); phase ^= 1;
         fence_after_thread_sync();
@@ -141,12 +144,15 @@ node_chain_tc_kernel(NodeChainArgs a) {
           fence_proxy_async_smem();
           fence_before_thread_sync();
           nchain_group_bar(grp);
-          if (gtid == 0) {
+          if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
             fence_after_thread_sync();
-            if (hh == 0 && sn.bias != nullptr) issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB + boff[s + 1], sn.N);
-            // K chunk hh of W_{s+1}: k-groups [16*hh, 16*hh+16), each sn.N * 16 bytes
-            issue_gemm(tmem_grp, smem_u32(nxt), wn_addr + hh * 16 * (sn.N * 16), sn.N, 128, hh == 1 || sn.bias != nullptr);
-            mma_commit(mbar);
+            if (elect_one()) {
+              if (hh == 0 && sn.bias != nullptr) issue_bias(tmem_grp, sbase + OFF_ONES, sbase + OFF_BB + boff[s + 1], sn.N);
+              // K chunk hh of W_{s+1}: k-groups [16*hh, 16*hh+16), each sn.N * 16 bytes
+              issue_gemm(tmem_grp, smem_u32(nxt), wn_addr + hh * 16 * (sn.N * 16), sn.N, 128, hh == 1 || sn.bias != nullptr);
+              mma_commit(mbar);
+            }
+            __syncwarp();
           }
           mbar_wait(mbar, phase); phase ^= 1;     // chunk consumed: the buffer is free / the result is ready
           fence_after_thread_sync();

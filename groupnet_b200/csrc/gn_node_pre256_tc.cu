@@ -40,9 +40,9 @@ struct NodePre256Args {
 };
 
 __device__ __forceinline__ void np_arrive(uint64_t* b) { tc::mbar_arrive(b); }
-__device__ __forceinline__ void np_expect_tx(uint64_t* b, uint32_t bytes) { tc::mbar_expect_tx(b, bytes); }
+__device__ __forceinline__ void np_expect_tx(uint64_t* b, uint32_t bytes) { tcu::expect_tx(b, bytes); }
 __device__ __forceinline__ void np_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  tc::bulk_g2s(dst, src, bytes, bar);
+  tcu::bulk_g2s(dst, src, bytes, bar);
 }
 
 __global__ void __launch_bounds__(np2::THREADS, 1)
@@ -71,7 +71,7 @@ node_pre256_tc_kernel(NodePre256Args a) {
 
   if (warp == 8) {
     // ------------------------------------------------------------------ weight stream producer
-    if (lane == 0) {
+    {                                                   // all 32 lanes: warp-uniform control flow, elected issue
       uint32_t ph_empty = 0x3u;
       int stage = 0;
       auto load = [&](const unsigned char*& src, uint32_t bytes) {
@@ -91,7 +91,7 @@ node_pre256_tc_kernel(NodePre256Args a) {
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {                                                   // all 32 lanes: warp-uniform control flow, elected issue
       uint32_t ph = 0u;
       int stage = 0, buf = 0;
       auto wait = [&](int i) { tc::mbar_wait(bars + i, (ph >> i) & 1u); ph ^= 1u << i; };
@@ -103,31 +103,31 @@ node_pre256_tc_kernel(NodePre256Args a) {
           wait(B_WFULL + stage);
           tc::fence_after_thread_sync();
           const uint32_t wb = sbase + OFF_RING + stage * STAGE;
-          tc::issue_gemm(tmem + TM_HID, abuf + kc * 8 * 2048, wb, 256, 64, kc > 0);
-          if (kc == 3) tc::issue_gemm(tmem + TM_HID, sbase + OFF_ONES, wb + W0K, 256, 16, true);
-          tc::mma_commit(bars + B_WEMPTY + stage);
+          tcu::issue_gemm(tmem + TM_HID, abuf + kc * 8 * 2048, wb, 256, 64, kc > 0);
+          if (kc == 3) tcu::issue_gemm(tmem + TM_HID, sbase + OFF_ONES, wb + W0K, 256, 16, true);
+          tcu::mma_commit(bars + B_WEMPTY + stage);
           stage ^= 1;
         }
-        tc::mma_commit(bars + B_HIDFULL);
+        tcu::mma_commit(bars + B_HIDFULL);
         wait(B_HIDREADY);
         wait(B_WFULL + stage);
         tc::fence_after_thread_sync();
         {
           const uint32_t wb = sbase + OFF_RING + stage * STAGE;
-          tc::issue_gemm(tmem + TM_X, abuf, wb, 64, 256, false);
-          tc::issue_gemm(tmem + TM_X, sbase + OFF_ONES, wb + 64 * 256 * 2, 64, 16, true);
-          tc::mma_commit(bars + B_WEMPTY + stage);
+          tcu::issue_gemm(tmem + TM_X, abuf, wb, 64, 256, false);
+          tcu::issue_gemm(tmem + TM_X, sbase + OFF_ONES, wb + 64 * 256 * 2, 64, 16, true);
+          tcu::mma_commit(bars + B_WEMPTY + stage);
           stage ^= 1;
         }
-        tc::mma_commit(bars + B_XFULL);
+        tcu::mma_commit(bars + B_XFULL);
         wait(B_XREADY);
         wait(B_WFULL + stage);
         tc::fence_after_thread_sync();
-        tc::issue_gemm(tmem + TM_PQ, abuf, sbase + OFF_RING + stage * STAGE, 64, 64, false);
-        tc::mma_commit(bars + B_WEMPTY + stage);
+        tcu::issue_gemm(tmem + TM_PQ, abuf, sbase + OFF_RING + stage * STAGE, 64, 64, false);
+        tcu::mma_commit(bars + B_WEMPTY + stage);
         stage ^= 1;
-        tc::mma_commit(bars + B_PQFULL);
-        tc::mma_commit(bars + B_AFREE + buf);
+        tcu::mma_commit(bars + B_PQFULL);
+        tcu::mma_commit(bars + B_AFREE + buf);
       }
     }
   } else if (warp >= 4) {

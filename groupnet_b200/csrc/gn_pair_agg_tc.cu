@@ -155,7 +155,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
       fence_proxy_async_smem();
       fence_before_thread_sync();
       __syncthreads();
-      if (tid == 0) { fence_after_thread_sync(); issue_gemm1(0); }
+      if (warp == 0) { fence_after_thread_sync(); if (elect_one()) issue_gemm1(0); __syncwarp(); }   // warp-uniform issue
     }
 
     for (int t = 0; t < T; ++t) {
@@ -180,7 +180,7 @@ pair_agg_tc_kernel(PairAggArgs a) {
       fence_before_thread_sync();
       __syncthreads();                                       // P'_t visible; W0_{t+1} / bias operand staged
       // (c) tensor core: P'_{t+1} while the SIMT part of step t runs
-      if (tid == 0 && t + 1 < T) { fence_after_thread_sync(); issue_gemm1(t + 1); }
+      if (warp == 0 && t + 1 < T) { fence_after_thread_sync(); if (elect_one()) issue_gemm1(t + 1); __syncwarp(); }
       // GEMM 2 of step t-1 has had a whole drain to finish: its operand buffers are free again
       if (t > 0) {
         mbar_wait(mbarB, phB); phB ^= 1;
@@ -233,10 +233,13 @@ pair_agg_tc_kernel(PairAggArgs a) {
       fence_before_thread_sync();
       __syncthreads();                                       // also: everyone is done reading P'_t
       // (e) agg += G_t W1_t^T
-      if (tid == 0) {
+      if (warp == 0) {
         fence_after_thread_sync();
-        issue_gemm(tmem_base + TM_AGG, sbase + OFF_G, sbase + OFF_W1, D, 128, t > 0);
-        mma_commit(mbarB);
+        if (elect_one()) {
+          issue_gemm(tmem_base + TM_AGG, sbase + OFF_G, sbase + OFF_W1, D, 128, t > 0);
+          mma_commit(mbarB);
+        }
+        __syncwarp();
       }
     }
     // ---- epilogue: agg = acc + sum_t S[row][t] b1_t ----

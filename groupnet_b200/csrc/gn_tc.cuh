@@ -286,3 +286,25 @@ __device__ __forceinline__ void stage_raw_H(float* raw, const float* __restrict_
 }
 
 }}  // namespace gn::tc
+
+// Warp-uniform forms for dedicated producer / issuer warps: EVERY lane of the warp calls them from converged control
+// flow, one elected lane executes the asynchronous instruction (see tc::elect_one).
+namespace gn { namespace tcu {
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_saddr, uint32_t b_saddr, int N, int K,
+                                           bool accumulate_first) {
+  if (tc::elect_one()) tc::issue_gemm(tmem_d, a_saddr, b_saddr, N, K, accumulate_first);
+  __syncwarp();
+}
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+  if (tc::elect_one()) tc::mma_commit(mbar);
+  __syncwarp();
+}
+__device__ __forceinline__ void expect_tx(uint64_t* mbar, uint32_t bytes) {
+  if (tc::elect_one()) tc::mbar_expect_tx(mbar, bytes);
+  __syncwarp();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* mbar) {
+  if (tc::elect_one()) tc::bulk_g2s(dst_saddr, src, bytes, mbar);
+  __syncwarp();
+}
+}}  // namespace gn::tcu

@@ -147,10 +147,13 @@ tc_linear_kernel(TcLinArgs a) {
       fence_proxy_async_smem();
       fence_before_thread_sync();
       group_bar(grp);
-      if (gtid == 0) {
+      if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
         fence_after_thread_sync();
-        issue_gemm(tmem_grp, sA_addr, sW_addr, N, kcw, kc0 > 0);
-        mma_commit(mbar);
+        if (elect_one()) {
+          issue_gemm(tmem_grp, sA_addr, sW_addr, N, kcw, kc0 > 0);
+          mma_commit(mbar);
+        }
+        __syncwarp();
       }
     }
     mbar_wait(mbar, phase); phase ^= 1;
