@@ -42,45 +42,45 @@ struct Bars {
   uint32_t tmem_slot, pad;
 };
 
-// One pass of a thread's share of a drain: 16 accumulator columns [c0, c0 + 16) of its row -> fp32 epilogue -> HBM
-// and / or the next op's A operand in tensor memory (hi | lo split).  16 columns per pass keep the 512 row threads
-// inside their 96-register budget (a spill costs an L2 round trip here: the shared-memory carve-out leaves no L1).
-__device__ __forceinline__ void drain_cols(const Args& a, const Op& op, const float* aux, uint32_t tmem_row, int c0,
-                                           long long grow, bool live, float& carry) {
+// One pass of a thread's share of a drain: 16 accumulator columns [c0, c0 + 16) of its row (already loaded into r) ->
+// fp32 epilogue -> HBM and / or the next op's A operand in tensor memory (hi | lo split).  16 columns per pass keep
+// the 512 row threads inside their 96-register budget (a spill costs an L2 round trip here: the shared-memory
+// carve-out leaves no L1).  The epilogue is specialised at compile time on (kind, ReLU, per-row scale / rank-T bias):
+// an interpreted version cost ~2.5x the instructions.  rsb: this row's per-row scales, staged in shared memory.
+template <int KIND, bool RELU, bool RS>
+__device__ __forceinline__ void drain_pass(const Args& a, const Op& op, const float* aux, const float* rsb, uint32_t (&r)[16],
+                                           uint32_t tmem_row, int c0, long long grow, bool live, float& carry) {
   constexpr int W = 16;
-  uint32_t r[W];
-  tf::tmem_ld16_nowait(tmem_row + op.acc_col + c0, r);
-  tc::tmem_ld_wait();
   // partial sums kept in separate accumulators (short accumulation chains in the tensor core) meet in fp32 here
-  for (int pi = 1; pi < op.nsum; ++pi) {
-    uint32_t q[W];
-    tf::tmem_ld16_nowait(tmem_row + op.acc_col + pi * op.sum_stride + c0, q);
-    tc::tmem_ld_wait();
+  if (KIND == DR_STORE && RS) {
+    for (int pi = 1; pi < op.nsum; ++pi) {
+      uint32_t q[W];
+      tf::tmem_ld16_nowait(tmem_row + op.acc_col + pi * op.sum_stride + c0, q);
+      tc::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < W; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+      for (int j = 0; j < W; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(q[j]));
+    }
   }
-  if (op.bias_off >= 0 || op.bias != nullptr) {
+  if (op.bias_off >= 0) {
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
-      const float4 b = op.bias_off >= 0 ? *reinterpret_cast<const float4*>(aux + op.bias_off + c0 + 4 * q)
-                                        : ldg_f4(op.bias + c0 + 4 * q);
+      const float4 b = *reinterpret_cast<const float4*>(aux + op.bias_off + c0 + 4 * q);
       r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + b.x);
       r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + b.y);
       r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + b.z);
       r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + b.w);
     }
   }
-  if (op.relu) {
+  if (RELU) {
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
   }
-  if (op.rs_idx >= 0) {
-    const float scale = live ? __ldg(a.rs + grow * a.rs_ld + op.rs_idx) : 0.f;
+  if (RS && KIND != DR_STORE) {                 // per-row scale (edge_feat_t)
+    const float scale = rsb[op.rs_idx];
 #pragma unroll
     for (int j = 0; j < W; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * scale);
   }
-  const int kind = op.drain;
-  if (kind == DR_DOT) {
+  if (KIND == DR_DOT) {
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
       const float4 wv = *reinterpret_cast<const float4*>(aux + a.dot_off + c0 + 4 * q);
@@ -91,13 +91,13 @@ __device__ __forceinline__ void drain_cols(const Args& a, const Op& op, const fl
     }
     return;
   }
-  if (op.use_bm && live) {
+  if (RS && KIND == DR_STORE) {                 // rank-T bias: v += sum_t rs[row][t] * bm[t][col]
+    const float* bm = aux + a.bm_off + op.out_col0 + c0;
     for (int t = 0; t < a.bm_T; ++t) {
-      const float st = __ldg(a.rs + grow * a.rs_ld + t);
-      const float* bt = a.bm + static_cast<size_t>(t) * a.bm_ld + op.out_col0 + c0;
+      const float st = rsb[t];
 #pragma unroll
       for (int q = 0; q < W / 4; ++q) {
-        const float4 b = ldg_f4(bt + 4 * q);
+        const float4 b = *reinterpret_cast<const float4*>(bm + t * a.bm_ld + 4 * q);
         r[4 * q] = __float_as_uint(fmaf(st, b.x, __uint_as_float(r[4 * q])));
         r[4 * q + 1] = __float_as_uint(fmaf(st, b.y, __uint_as_float(r[4 * q + 1])));
         r[4 * q + 2] = __float_as_uint(fmaf(st, b.z, __uint_as_float(r[4 * q + 2])));
@@ -105,13 +105,13 @@ __device__ __forceinline__ void drain_cols(const Args& a, const Op& op, const fl
       }
     }
   }
-  if ((kind == DR_STORE || kind == DR_TMEM_STORE) && live) {
+  if ((KIND == DR_STORE || KIND == DR_TMEM_STORE) && live) {
     float* dst = op.out + grow * op.ldo + op.out_col0 + c0;
 #pragma unroll
     for (int q = 0; q < W / 4; ++q)
       *reinterpret_cast<uint4*>(dst + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
   }
-  if (kind == DR_TMEM || kind == DR_TMEM_STORE) {
+  if (KIND == DR_TMEM || KIND == DR_TMEM_STORE) {
     uint32_t lo[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) tf::split_tf32(__uint_as_float(r[j]), r[j], lo[j]);
@@ -119,6 +119,30 @@ __device__ __forceinline__ void drain_cols(const Args& a, const Op& op, const fl
     tf::tmem_st16(tmem_row + op.dst_col + op.dn + c0, lo);
   }
 }
+
+// A thread's share of a drain: columns [sl*w, sl*w + w), w = dn / NSLICE = 16 or 32; both 16-column halves of a
+// 32-column share are in flight from tensor memory before the first is processed.
+template <int KIND, bool RELU, bool RS>
+__device__ __forceinline__ void drain_slice(const Args& a, const Op& op, const float* aux, const float* rsb,
+                                            uint32_t tmem_row, int sl, long long grow, bool live, float& carry) {
+  const int w = op.dn / NSLICE;
+  uint32_t r0[16];
+  tf::tmem_ld16_nowait(tmem_row + op.acc_col + sl * w, r0);
+  if (w == 32) {
+    uint32_t r1[16];
+    tf::tmem_ld16_nowait(tmem_row + op.acc_col + sl * w + 16, r1);
+    tc::tmem_ld_wait();
+    drain_pass<KIND, RELU, RS>(a, op, aux, rsb, r0, tmem_row, sl * w, grow, live, carry);
+    drain_pass<KIND, RELU, RS>(a, op, aux, rsb, r1, tmem_row, sl * w + 16, grow, live, carry);
+  } else {
+    tc::tmem_ld_wait();
+    drain_pass<KIND, RELU, RS>(a, op, aux, rsb, r0, tmem_row, sl * w, grow, live, carry);
+  }
+  if (KIND == DR_TMEM || KIND == DR_TMEM_STORE) tf::tmem_st_wait();
+}
+
+// drain variants the launchers use (Op::variant)
+enum { DV_TMEM = 0, DV_TMEM_RELU, DV_TMEM_RELU_RS, DV_TMEM_STORE, DV_STORE, DV_STORE_BM, DV_DOT_RELU, DV_COUNT };
 
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tf32_kernel(const __grid_constant__ Args a) {
@@ -391,6 +415,13 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
           }
           mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
           if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
+          if (e == 0 && a.rs != nullptr) {
+            // this row's per-row scales (edge_feat / S) -> shared memory, once per tile: every slice of the row needs them
+            // in every drain, and without an L1 each global read is an L2 round trip
+            row_bar();                                    // the previous tile's drains are done with the buffer
+            for (int t = sl; t < a.rs_n; t += NSLICE) ybuf[row * 17 + t] = live ? __ldg(a.rs + grow * a.rs_ld + t) : 0.f;
+            row_bar();
+          }
           if (e == 0 && a.edge_feat != nullptr) {
             // Gumbel noise of this tile's rows (slice sl: edge types [sl*tq, sl*tq + tq)), computed now, while the first
             // GEMM runs and the row threads would only wait: g = -log(eps - log(U + eps))  (:446-455) -> ybuf
@@ -467,9 +498,16 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
           }
           row_bar();                              // ybuf / dotp are rewritten by the next tile
         } else if (kind != DR_NONE) {
-          const int w = op.dn / NSLICE;                     // 16 or 32 columns per thread
-          for (int c0 = sl * w; c0 < sl * w + w; c0 += 16) drain_cols(a, op, aux, tmem_row, c0, grow, live, carry);
-          if (kind == DR_TMEM || kind == DR_TMEM_STORE) tf::tmem_st_wait();
+          const float* rsb = ybuf + row * 17;               // per-row scales staged at tile start (programs with a.rs)
+          switch (op.variant) {
+            case DV_TMEM:         drain_slice<DR_TMEM, false, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
+            case DV_TMEM_RELU:    drain_slice<DR_TMEM, true, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
+            case DV_TMEM_RELU_RS: drain_slice<DR_TMEM, true, true>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
+            case DV_TMEM_STORE:   drain_slice<DR_TMEM_STORE, false, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
+            case DV_STORE:        drain_slice<DR_STORE, false, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
+            case DV_STORE_BM:     drain_slice<DR_STORE, false, true>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
+            default:              drain_slice<DR_DOT, true, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
+          }
         }
         if (op.arrive) {
           fence_before_thread_sync();
@@ -555,11 +593,24 @@ struct Builder {
 
 // Replays the row-thread / issuer protocol: arrivals must equal waits per tile, signals must equal drains, TMEM
 // ranges must fit, and neither side may get NBAR phases ahead of the other (an mbarrier ring would alias).
-static int validate_program(const Args& a) {
+// the compiled drain variant of an op; -1: the combination is not built
+static int drain_variant(const Op& op) {
+  const bool rs = op.rs_idx >= 0;
+  switch (op.drain) {
+    case DR_TMEM: return op.use_bm ? -1 : (rs ? (op.relu ? DV_TMEM_RELU_RS : -1) : (op.relu ? DV_TMEM_RELU : DV_TMEM));
+    case DR_TMEM_STORE: return (rs || op.relu || op.use_bm) ? -1 : DV_TMEM_STORE;
+    case DR_STORE: return (rs || op.relu) ? -1 : (op.use_bm ? DV_STORE_BM : DV_STORE);
+    case DR_DOT: return (rs || !op.relu || op.use_bm) ? -1 : DV_DOT_RELU;
+    default: return 0;
+  }
+}
+
+static int validate_program(Args& a) {
   if (a.nops < 1 || a.nops > MAX_OPS || a.nev < 1 || a.nev > MAX_EV) return GN_E_SHAPE;
+  if (a.rs != nullptr && (a.edge_feat != nullptr || a.rs_n < 1 || a.rs_n > 16)) return GN_E_SHAPE;   // one smem buffer
   int waits = 0, signals = 0;
   for (int o = 0; o < a.nops; ++o) {
-    const Op& op = a.ops[o];
+    Op& op = a.ops[o];
     if (op.N < 16 || op.N > 256 || (op.N & 15) || op.K < 8 || (op.K & 7) || op.kc < 8 || (op.kc & 7) || op.K % op.kc) return GN_E_SHAPE;
     if (static_cast<uint32_t>(op.N) * op.kc * 8 > a.stage_bytes) return GN_E_SHAPE;
     if (op.acc_col < 0 || op.acc_col + op.N > 512) return GN_E_SHAPE;
@@ -572,7 +623,12 @@ static int validate_program(const Args& a) {
       if ((op.drain == DR_TMEM || op.drain == DR_TMEM_STORE) && (op.dst_col < 0 || op.dst_col + 2 * op.dn > 512)) return GN_E_SHAPE;
       if ((op.drain == DR_STORE || op.drain == DR_TMEM_STORE) &&
           (!op.out || (op.ldo & 3) || (op.out_col0 & 3) || (reinterpret_cast<uintptr_t>(op.out) & 15))) return GN_E_ALIGN;
-      if (op.bias && (reinterpret_cast<uintptr_t>(op.bias) & 15)) return GN_E_ALIGN;
+      if (op.bias != nullptr) return GN_E_SHAPE;            // biases live in the smem constants (Builder::set_bias)
+      if (op.nsum > 1 && !(op.drain == DR_STORE && op.use_bm)) return GN_E_SHAPE;
+      if (op.use_bm && a.bm_off < 0) return GN_E_SHAPE;
+      const int dv = drain_variant(op);
+      if (dv < 0) return GN_E_SHAPE;
+      a.ops[o].variant = static_cast<short>(dv);
       ++signals;
     } else if (op.arrive) return GN_E_SHAPE;
     waits += op.wait_n;
@@ -745,7 +801,7 @@ int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weig
   Op& s0b = b.add(A_SMEM, 0, D, 128, 0, 0, 0, 1);
   b.drain_tmem(s0b, 128, 1, w->node_b0 + 128, 128, 1);
   Op& s1b = b.add(A_TMEM, 128, 128, 64, 384, 1, 1, 1);
-  s1b.drain = DR_TMEM_STORE; s1b.dn = 64; s1b.relu = 0; s1b.bias = w->node_b1; s1b.dst_col = 0; s1b.arrive = 1;
+  s1b.drain = DR_TMEM_STORE; s1b.dn = 64; s1b.relu = 0; b.set_bias(s1b, w->node_b1, 64); s1b.dst_col = 0; s1b.arrive = 1;
   s1b.out = xprime; s1b.ldo = 64; s1b.out_col0 = 0;
   Op& s2 = b.add(A_TMEM, 0, 64, 64, 448, 0, 1, 1);
   b.drain_store(s2, 64, 0, nullptr, pq, 64, 0, 0);
@@ -814,14 +870,15 @@ int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int 
     if (c + 2 < n) b.ev(EV_STAGE, c + 2);
   }
   a.stage_mode = ST_ROWS; a.src0 = G; a.ld0 = static_cast<long long>(T) * 128; a.k_src0 = T * 128;
-  a.rs = S; a.rs_ld = 16; a.bm = w->agg_b1; a.bm_T = T; a.bm_ld = D;
+  a.rs = S; a.rs_ld = 16; a.rs_n = T; a.bm = w->agg_b1; a.bm_T = T; a.bm_ld = D; a.bm_off = b.aux(w->agg_b1, T * D);
   return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_aggout_w), "agg_out_tf32", st);
 }
 
 // ---- hyper edge_aggregation as written (:259-265): ef = sum_t edge_feat_t * (W1_t relu(W0_t eo + b0_t) + b1_t)
 // TMEM columns: acc_hid 0 | A_hid 128,256 | acc_ef 384
 bool hyper_agg_tf32_fits(int D, int T) {
-  return (D == 64 || D == 128) && T >= 1 && 2 * T <= MAX_OPS;
+  // biases (T x 128) and the rank-T output bias (T x D) must fit the smem constants
+  return (D == 64 || D == 128) && T >= 1 && 2 * T <= MAX_OPS && T * 128 + T * D <= AUX_FLOATS;
 }
 
 int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, int D, int T,
@@ -848,7 +905,7 @@ int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, 
     }
   }
   a.stage_mode = ST_ROWS; a.src0 = eo; a.ld0 = D; a.k_src0 = D;
-  a.rs = edge_feat; a.rs_ld = T; a.bm = w->agg_b1; a.bm_T = T; a.bm_ld = D;
+  a.rs = edge_feat; a.rs_ld = T; a.rs_n = T; a.bm = w->agg_b1; a.bm_T = T; a.bm_ld = D; a.bm_off = b.aux(w->agg_b1, T * D);
   return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_hagg_w), "hyper_agg_tf32", st);
 }
 

@@ -56,7 +56,8 @@ struct Op {
   short use_bm;       // DR_STORE: v += sum_t rs[row * rs_ld + t] * bm[t * bm_ld + col]
   short out_col0;
   short nsum, sum_stride;  // drain value = sum of nsum accumulators, sum_stride columns apart (0/1 = just acc_col)
-  short bias_off;     // >= 0: bias[dn] at this float offset of the smem constants (else `bias`, global, or none)
+  short bias_off;     // >= 0: bias[dn] at this float offset of the smem constants
+  short variant;      // compiled drain specialisation (set by validate_program)
   const float* bias;  // [dn] or null
   float* out;         // DR_STORE / DR_TMEM_STORE: row-major fp32, row stride ldo
   long long ldo;
@@ -84,8 +85,8 @@ struct Args {
   const float* aux_src[MAX_AUX]; short aux_n[MAX_AUX], aux_off[MAX_AUX]; int naux;
   int N, E, tps;
   // per-row scales (edge_feat or S) and the rank-T bias of the aggregation output
-  const float* rs; int rs_ld;
-  const float* bm; int bm_T; int bm_ld;
+  const float* rs; int rs_ld; int rs_n;   // rs_n leading values of every row are staged in shared memory per tile
+  const float* bm; int bm_T; int bm_ld; int bm_off;   // bm_off >= 0: bm lives in the smem constants
   // DR_DOT: carry = sum_k relu(acc_k + bias_k) * dot_w[k * dot_stride]
   int dot_off;                     // smem constants
   // DR_GUMBEL (MLP_dict_softmax tail, :45-53, :446-520)
