@@ -70,6 +70,9 @@ def kernel_work(b, n, d, precision="bf16"):
             add("node_post_tf32", post_flops, rn * 3 * d * 4, "tensor")
             if pair:
                 add("edge_chain_pair_tf32", 2 * re * mlp_macs + re * 600, (rn * 128 + re * t) * 4, "tensor")
+                # fused pairwise aggregation: P GEMM + symmetric relu-sum (3 FLOP per (n,j,t,c)) + G GEMM; h, edge_feat in, agg out
+                add("pair_agg_tf32", 2 * rn * agg_macs_row + rn * n * t * 128 * 3, (rn * 2 * d + re * t) * 4, "tensor")
+                # the unfused trio (shapes the fused kernel does not take)
                 add("agg_in_tf32", 2 * rn * d * t * 128, rn * (d + t * 128) * 4, "tensor")
                 add("edge2node_pair", rn * n * t * 128 * 4, (rn * (2 * t * 128 + 16) + re * t) * 4, "hbm")
                 add("agg_out_tf32", 2 * rn * t * 128 * d, rn * (t * 128 + 16 + d) * 4, "tensor")

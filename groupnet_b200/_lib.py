@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgroupnet_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 GN_MAX_AGENTS = 64
 GN_MAX_SCALES = 8
@@ -58,7 +58,7 @@ class StageWeights(C.Structure):
         "post_w0t", "post_b0", "post_w1t", "post_b1",
         "tc_init_w0", "tc_init_w1", "tc_df_w0", "tc_df_w1",
         "tc_node_w0", "tc_node_w1", "tc_att_wpq", "tc_agg_w0", "tc_agg_w1", "tc_post_w0", "tc_post_w1", "tc_hfuse_w", "tc_npre_w",
-        "tf_chain_w", "tf_pre_w", "tf_aggin_w", "tf_aggout_w", "tf_hagg_w", "tf_post_w",
+        "tf_chain_w", "tf_pre_w", "tf_aggin_w", "tf_aggout_w", "tf_hagg_w", "tf_post_w", "tf_pagg_w",
     )
     _fields_ = [(name, C.c_void_p) for name in FIELDS]
 

@@ -388,6 +388,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
             }
             if (tr) trp[TR_STAGE - TR_ROWS + 4] = clock64();
             fence_before_thread_sync();
+            mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;     // the MMAs start while the node block is refilled
             if (tr) trp[TR_STAGE - TR_ROWS + 5] = clock64();
             row_bar();                          // every thread is done with the node block: refill it for the next tile
             if (tr) trp[TR_STAGE - TR_ROWS + 6] = clock64();
@@ -412,8 +413,8 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
             }
             fence_proxy_async_smem();
             fence_before_thread_sync();
+            mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
           }
-          mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
           if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
           if (e == 0 && a.rs != nullptr) {
             // this row's per-row scales (edge_feat / S) -> shared memory, once per tile: every slice of the row needs them
@@ -874,6 +875,9 @@ int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int 
   return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_aggout_w), "agg_out_tf32", st);
 }
 
+// (A pipelined form with 64-unit halves — two hidden accumulators, the first Linear two unit steps ahead — measured
+//  SLOWER, 2.5 vs 1.9 ms: a 128 x 64 x 8 tf32 MMA holds the tensor pipe ~50 clk against ~66 for 128 x 128 x 8, so
+//  halving N costs 1.5x the tensor time)
 // ---- hyper edge_aggregation as written (:259-265): ef = sum_t edge_feat_t * (W1_t relu(W0_t eo + b0_t) + b1_t)
 // TMEM columns: acc_hid 0 | A_hid 128,256 | acc_ef 384
 bool hyper_agg_tf32_fits(int D, int T) {

@@ -5,7 +5,7 @@
 
 namespace gn { namespace tfe {
 
-constexpr int MAX_OPS = 32;
+constexpr int MAX_OPS = 64;
 constexpr int MAX_EV = 72;
 // weight-ring stage (a [N x kc] chunk, hi then lo): the largest of 64 / 32 / 16 KB that leaves room for two stages
 // beside the staged A buffers; must match packing.tf_stage_bytes

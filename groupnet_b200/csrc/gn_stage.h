@@ -89,6 +89,10 @@ int launch_agg_in_tf32(const float* h, long long R, int D, int T, const gn_stage
 bool agg_out_tf32_fits(int D, int T);
 int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int T, const gn_stage_weights* w,
                         float* agg, cudaStream_t st);
+// fused pairwise aggregation, 3xTF32 (gn_pair_agg_tf32.cu): replaces agg_in_tf32 + edge2node_pair + agg_out_tf32
+bool pair_agg_tf32_fits(int N, int D, int T);
+int launch_pair_agg_tf32(const float* h, const float* edge_feat, int B, int N, int T,
+                         const gn_stage_weights* w, float* agg, cudaStream_t st);
 bool hyper_agg_tf32_fits(int D, int T);
 int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, int D, int T,
                           const gn_stage_weights* w, float* ef, cudaStream_t st);

@@ -1069,7 +1069,10 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   const bool tcn = p.tc_nodes;
   const bool tf = c->precision == GN_TF32X3;       // fp32-grade tensor-core chains where the shape fits
   const long long RE_ = static_cast<long long>(B) * E;
-  const bool tf_pre = tf && w->tf_pre_w && node_pre_tf32_fits(D) && (!c->pairwise || (w->tf_aggin_w && agg_in_tf32_fits(D, T)));
+  // pairwise aggregation fused into one kernel (P / G stay on chip) where the shape fits
+  const bool tf_fused_agg = tf && c->pairwise && w->tf_pagg_w != nullptr && pair_agg_tf32_fits(N, D, T);
+  const bool tf_pre = tf && w->tf_pre_w && node_pre_tf32_fits(D) &&
+                      (!c->pairwise || tf_fused_agg || (w->tf_aggin_w && agg_in_tf32_fits(D, T)));
   // pairwise edge chain with node2edge and the first Linear of init_MLP folded into its staging pass: needs the
   // tensor-core prologue (which emits Y) and an h_dim of 64 (the prologue's Y op reads the 64-wide x' operand)
   const bool tf_pair_y = tf_pre && c->pairwise && w->tf_chain_w != nullptr && edge_chain_tf32_fits(true, N, T) &&
@@ -1121,7 +1124,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     }
   } else if (tf_pre) {
     GN_TRY(launch_node_pre_tf32(h, R, D, w, xprime, pq, tf_pair_y ? Ypre : nullptr, st));
-    if (c->pairwise) GN_TRY(launch_agg_in_tf32(h, R, D, T, w, P, st));
+    if (c->pairwise && !tf_fused_agg) GN_TRY(launch_agg_in_tf32(h, R, D, T, w, P, st));
   } else {
     constexpr int TM = 64, LD = TM + 4;
     size_t smem = static_cast<size_t>(p.Dp + 128 + 64) * LD * 4 + 2 * KC * 128 * 4;
@@ -1168,6 +1171,7 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   // ---- k4/k5: aggregation
   if (c->pairwise) {
     if (fused_agg) GN_TRY(launch_pair_agg_tc(h, efeat, B, N, T, w, agg, st));
+    else if (tf_fused_agg && tf_pre) GN_TRY(launch_pair_agg_tf32(h, efeat, B, N, T, w, agg, st));
     else GN_TRY(launch_edge2node_pair(P, efeat, B, N, T, w, G, S, st));
   } else if (fused_hyper64) {
     return launch_hyper_fused64_tc(h, H, efeat, B, N, T, hstride, w, node_out, ld_out, c->Dout, st);
@@ -1227,6 +1231,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
   }
 
   // ---- k6: closing MLP on [agg | h] / N
+  const bool pagg_done = tf_fused_agg && tf_pre;        // agg already holds G W1cat^T + S b1
+  const int post_pair = (c->pairwise && !pagg_done) ? 1 : 0;
   if (tcn) {
     TcLinArgs a;
     if (c->pairwise && !fused_agg) {                 // agg = G W1cat^T + S b1  (second half of the collapse)
@@ -1260,8 +1266,8 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
     a.bias = w->post_b1; a.out = node_out; a.out_is_f32 = 1; a.ldo = ld_out;
     GN_TRY(launch_tc_linear(a, "post_mlp1_tc", st));
   } else if (tf && w->tf_post_w && node_post_tf32_fits(D, c->Dout, ld_out, node_out) &&
-             (!c->pairwise || (w->tf_aggout_w && agg_out_tf32_fits(D, T)))) {
-    if (c->pairwise) GN_TRY(launch_agg_out_tf32(G, S, R, D, T, w, agg, st));
+             (!c->pairwise || pagg_done || (w->tf_aggout_w && agg_out_tf32_fits(D, T)))) {
+    if (c->pairwise && !pagg_done) GN_TRY(launch_agg_out_tf32(G, S, R, D, T, w, agg, st));
     GN_TRY(launch_node_post_tf32(agg, h, R, D, N, c->Dout, w, node_out, ld_out, st));
   } else {
     constexpr int TM = 64, LD = TM + 4;
@@ -1271,17 +1277,17 @@ int stage_fwd(const gn_stage_cfg* c, const gn_stage_weights* w, const float* h,
       auto kern = node_post_kernel<TM, 64, 1>;
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("node_post", st);
-        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out, c->pairwise ? agg : nullptr); }
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, post_pair, *w, node_out, ld_out, post_pair ? agg : nullptr); }
     } else if (D <= 128) {
       auto kern = node_post_kernel<TM, 128, 1>;
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("node_post", st);
-        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out, c->pairwise ? agg : nullptr); }
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, post_pair, *w, node_out, ld_out, post_pair ? agg : nullptr); }
     } else {
       auto kern = node_post_kernel<TM, 128, 2>;
       GN_TRY(set_smem(kern, smem));
       { ProfScope ps__("node_post", st);
-        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, c->pairwise, *w, node_out, ld_out, c->pairwise ? agg : nullptr); }
+        kern<<<grid, GN_THREADS, smem, st>>>(h, agg, G, S, R, N, D, p.Dc, p.K2p, T, c->Dout, p.Doutc, post_pair, *w, node_out, ld_out, post_pair ? agg : nullptr); }
     }
     GN_LAUNCH_CHECK();
   }
@@ -1307,11 +1313,12 @@ int stage_launch_count(const gn_stage_cfg* c) {
   if (c->precision == GN_TF32X3) {
     // upper bound when every chain fits (weights present): pre (+P), chain (node2edge fused for the pairwise layer),
     // aggregation, post
-    const bool pre = node_pre_tf32_fits(c->D) && (!c->pairwise || agg_in_tf32_fits(c->D, c->T));
+    const bool fagg = c->pairwise && pair_agg_tf32_fits(c->N, c->D, c->T);
+    const bool pre = node_pre_tf32_fits(c->D) && (!c->pairwise || fagg || agg_in_tf32_fits(c->D, c->T));
     const bool post = node_post_tf32_fits(c->D, c->Dout, c->out_ld > 0 ? c->out_ld : c->Dout, nullptr) &&
-                      (!c->pairwise || agg_out_tf32_fits(c->D, c->T));
+                      (!c->pairwise || fagg || agg_out_tf32_fits(c->D, c->T));
     const int fused_tf = (c->pairwise && edge_chain_tf32_fits(true, c->N, c->T)) ? 1 : 0;
-    if (c->pairwise) return (pre ? 2 : 1) + (2 - fused_tf) + 1 + (post ? 2 : 1);
+    if (c->pairwise) return ((pre && !fagg) ? 2 : 1) + (2 - fused_tf) + 1 + ((post && !fagg) ? 2 : 1);
     return 1 + 1 + 1 + 1 + 1 + 1;
   }
   const int fused = (c->precision == GN_BF16_TC && c->pairwise && edge_chain_pair_fits(c->N)) ? 1 : 0;

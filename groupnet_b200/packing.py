@@ -227,6 +227,28 @@ def tf_stream(mats, stage_bytes: int, tail=None) -> torch.Tensor:
     return torch.cat(parts).contiguous()
 
 
+def pair_agg_tf32_stream(w0s, w1s) -> torch.Tensor:
+    """Weight stream of the fused pairwise aggregation (csrc/gn_pair_agg_tf32.cu): one (64 x 64) hi | lo chunk per
+    GEMM in issue order.  Unit step u = 2t + half uses A(u) = W0_t[64 half : 64 half + 64, :] (first Linear, 64 of its
+    128 hidden units) and B(u) = W1_t[:, 64 half : 64 half + 64] (second Linear, the matching K slice); GEMM 1 runs two
+    unit steps ahead: A(0), A(1), then B(u), A(u + 2) for u = 0..2T-1."""
+    t = len(w0s)
+    u_n = 2 * t
+
+    def a_of(u):
+        return w0s[u // 2][64 * (u % 2):64 * (u % 2) + 64, :]
+
+    def b_of(u):
+        return w1s[u // 2][:, 64 * (u % 2):64 * (u % 2) + 64]
+
+    mats = [a_of(0), a_of(1)]
+    for u in range(u_n):
+        mats.append(b_of(u))
+        if u + 2 < u_n:
+            mats.append(a_of(u + 2))
+    return tf_stream([m.contiguous() for m in mats], 32768)
+
+
 def agg_out_cols(d: int) -> Tuple[int, int]:
     """(Dc, TN) of the aggregation output GEMM; must match make_plan() in
     csrc/gn_stage_simt.cu."""
@@ -352,6 +374,9 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
             w1cat = torch.cat([dev(m.layers[1].weight) for m in agg], dim=1)      # (D, T*128)
             out["tf_aggout_w"] = tf_stream([w1cat[:, 64 * c:64 * (c + 1)] for c in range(2 * t)],
                                            tf_stage_bytes(64, 2, False))
+            if d == 64:
+                out["tf_pagg_w"] = pair_agg_tf32_stream([dev(m.layers[0].weight) for m in agg],
+                                                        [dev(m.layers[1].weight) for m in agg])
         else:
             mats = []
             for m in agg:

@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 3     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams */
+#define GN_ABI_VERSION 4     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams;
+                                 4: + tf_pagg_w (fused pairwise aggregation, csrc/gn_pair_agg_tf32.cu) */
 
 #define GN_MAX_AGENTS 64      /* N <= 64: one 64-bit membership word per hyperedge */
 #define GN_MAX_SCALES 8
@@ -140,6 +141,11 @@ typedef struct gn_stage_weights {
   const void* tf_aggout_w; /* cat_t agg_mlp[t].layers.1 along K, (D x T*128), in K blocks of 64 */
   const void* tf_hagg_w;   /* per t: agg_mlp[t].layers.0 (128xD), agg_mlp[t].layers.1 (Dx128) */
   const void* tf_post_w;   /* closing MLP layers.0 (128x2D), layers.1 (Doutx128) */
+  /* fused pairwise aggregation (csrc/gn_pair_agg_tf32.cu; pairwise layers with D == 64, else NULL): 32 KB chunks
+   * (64 x 64, hi then lo) in MMA issue order.  With unit step u = 2t + half, A(u) = agg_mlp[t].layers.0.weight
+   * rows [64 half, 64 half + 64) (64 x D) and B(u) = agg_mlp[t].layers.1.weight columns [64 half, 64 half + 64)
+   * (D x 64):  A(0), A(1), then for u = 0..2T-1: B(u), A(u+2) (the latter while u + 2 < 2T). */
+  const void* tf_pagg_w;
 } gn_stage_weights;
 
 typedef struct gn_stage_cfg {

@@ -10,7 +10,7 @@ import torch
 import groupnet_b200 as gb
 from groupnet_b200 import _lib
 
-MAX_OPS, MAX_EV, TR_TILES = 32, 72, 6
+MAX_OPS, MAX_EV, TR_TILES = 64, 72, 6
 TR_ROWS, TR_MAXCH = 3 * MAX_OPS, 40
 TR_CHUNK = TR_ROWS + 3 * MAX_EV
 TR_STAGE = TR_CHUNK + 4 * TR_MAXCH
@@ -30,7 +30,7 @@ hn = torch.nn.functional.normalize(x, p=2, dim=2)
 corr = hn @ hn.transpose(1, 2)
 lib = _lib.load()
 buf = torch.zeros(TR_TILES * TR_SLOTS, dtype=torch.int64, device="cuda")
-STREAMS = ("tf_chain_w", "tf_pre_w", "tf_aggin_w", "tf_aggout_w", "tf_hagg_w", "tf_post_w")
+STREAMS = ("tf_chain_w", "tf_pre_w", "tf_aggin_w", "tf_aggout_w", "tf_hagg_w", "tf_post_w", "tf_pagg_w")
 with torch.no_grad():
     run = (lambda: m(x)) if kind == "pair" else (lambda: m(x, corr))
     run()

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_lib.StageWeights) == 43 * ctypes.sizeof(ctypes.c_void_p)
+    assert ctypes.sizeof(_lib.StageWeights) == 44 * ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.StageCfg) == 12 * 4 + 8 + 8
     text = open(os.path.join(ROOT, "include", "groupnet_b200.h")).read()
     body = text[text.index("typedef struct gn_stage_weights"):text.index("} gn_stage_weights;")]

@@ -88,6 +88,19 @@ def test_weight_streams_follow_the_documented_order():
     w = _decode(t["tf_post_w"], [(128, 128), (64, 128)], s32)
     assert close(w[0], pair.nmp_mlp_end.layers[0].weight) and close(w[1], pair.nmp_mlp_end.layers[1].weight)
     assert "tf_hagg_w" not in t
+    # fused pairwise aggregation: A(0), A(1), then B(u), A(u + 2) per unit step u = 2t + half (csrc/gn_pair_agg_tf32.cu)
+    w = _decode(t["tf_pagg_w"], [(64, 64)] * 24, s32)
+    order = [("a", 0), ("a", 1)]
+    for u in range(12):
+        order.append(("b", u))
+        if u + 2 < 12:
+            order.append(("a", u + 2))
+    assert len(order) == 24
+    for got, (kind, u) in zip(w, order):
+        tt, half = divmod(u, 2)
+        want = (agg[tt].layers[0].weight[64 * half:64 * half + 64, :] if kind == "a"
+                else agg[tt].layers[1].weight[:, 64 * half:64 * half + 64])
+        assert close(got, want), (kind, u)
 
     hyp = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=5)
     t = packing.pack_stage(hyp, 0, torch.device("cpu"))

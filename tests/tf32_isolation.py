@@ -13,7 +13,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-STREAMS = ("tf_chain_w", "tf_pre_w", "tf_aggin_w", "tf_aggout_w", "tf_hagg_w", "tf_post_w")
+STREAMS = ("tf_chain_w", "tf_pre_w", "tf_aggin_w", "tf_aggout_w", "tf_hagg_w", "tf_post_w", "tf_pagg_w")
 CASES = {
     "pair11": ("pairwise", 11, 64, 64, 0, 300),
     "pair8": ("pairwise", 8, 64, 64, 0, 500),
@@ -22,7 +22,7 @@ CASES = {
     "hyper11": ("hyper", 11, 64, 64, 11, 700),
     "hyper20": ("hyper", 20, 64, 32, 8, 200),
 }
-KEEPS = ("tf_pre_w", "tf_pre_w+tf_aggin_w", "tf_chain_w", "tf_hagg_w", "tf_post_w", "tf_aggout_w+tf_post_w", "all")
+KEEPS = ("tf_pre_w", "tf_pre_w+tf_aggin_w", "tf_pre_w+tf_pagg_w", "tf_chain_w", "tf_hagg_w", "tf_post_w", "tf_aggout_w+tf_post_w", "all")
 
 
 def run_case(case: str, keep: str) -> None:
