@@ -302,6 +302,7 @@ def run_train(args, rank, world, local):
     the GPUs of one box with ONE NCCL all-reduce of the flat gradient bucket per step."""
     import torch.distributed as dist
     import groupnet_b200 as gb
+    from groupnet_b200 import _lib
     from groupnet_b200.ddp import FlatGradBucket
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -317,45 +318,135 @@ def run_train(args, rank, world, local):
     x = torch.randn(b, n, d, generator=torch.Generator().manual_seed(rank)).to(dev)
     wgt = torch.randn(b, n, model.feature_width(), generator=torch.Generator().manual_seed(100 + rank)).to(dev)
 
-    def step():
+    x_host = x.cpu().pin_memory()
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def step(from_host=False):
+        if from_host:                       # e2e: the step's inputs come from pinned host memory, the loss goes back
+            x.copy_(x_host, non_blocking=True)
         for p in model.parameters():
             p.grad = None
         feat, _ = model(x)
         loss = (feat * wgt).sum() / b
         loss.backward()
         bucket.allreduce_mean()
+        if from_host:
+            loss_host.copy_(loss.detach(), non_blocking=True)
         return loss
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
         step()
-    torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    step(True)
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
     e0.record()
-    for _ in range(args.steps):
-        loss = step()
+    for _ in range(e2e_steps):
+        step(True)
+        torch.cuda.current_stream(dev).synchronize()      # the caller reads the loss before the next step
     e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+    _lib.profile_enable(True)
+    step()
     torch.cuda.synchronize(dev)
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1) / args.steps
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
     if rank == 0:
-        print(json.dumps({
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        kernels = {k: {"ms_per_step": round(t, 3), "launches_per_step": c} for k, (t, c) in prof.items()}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        # 41.4 MFLOP per scene forward; backward = dgrad + wgrad of every Linear = 2x
+        fl = 3 * 41.4e6 * b
+        ach = fl / (ms * 1e-3) / 1e12
+        pk = float(peaks.get("bf16_tflops", 1590.0))
+        roof = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": pk, "unit": "TFLOP/s",
+                "frac": round(ach / pk, 5), "traffic": None,
+                "note": "whole-step algorithmic FLOP rate (3 x 41.4 MFLOP per scene); the training kernels are fp32 FFMA "
+                        "(SIMT, nominal 74 TFLOP/s), so the tensor-core peak is the ceiling they do not use; "
+                        f"dominant kernel by time: {dom}",
+                "share_of_step": round(kernels[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()), 3)}
+        line = {
             "metric": "ms_hgnn_train_step_scenes_per_sec", "value": world * b / (ms * 1e-3), "unit": "scenes/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "nba_train_step_fwd_bwd_3layers", "scenes_per_gpu": b, "agents": n, "h_dim": d,
                        "scales": list(SCALES), "grad_bucket_floats": bucket.numel,
-                       "collective": "one NCCL all-reduce(sum) of the flat fp32 gradient bucket per step"},
-            "loss": float(loss.item())}), flush=True)
+                       "collective": "one NCCL all-reduce(sum) of the flat fp32 gradient bucket per step",
+                       "l2": "no flush: the per-step scratch (GBs) exceeds the 126 MB L2"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": world * b / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "api": "MultiScaleInteraction.forward + backward + FlatGradBucket.allreduce_mean; x from pinned host "
+                           "memory every step, loss read back"},
+            "gpu_launches": sum(c for _, c in prof.values()) * args.steps,
+            "roofline": roof, "kernels": kernels, "loss": float(loss.item())}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_train()
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_train(budget_s=12.0):
+    """Reference CPU path of the training step: torch autograd through the oracle restatement (fwd + bwd of the three
+    layers, the same loss), all host threads, chunks of 128 scenes until the budget is spent."""
+    from oracle import ms_hgnn_oracle as O
+    import groupnet_b200 as gb
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    m = gb.MultiScaleInteraction(HDIM, SCALES)
+    sds = [{k: v.detach().clone().requires_grad_(True) for k, v in l.state_dict().items()} for l in m.layers()]
+
+    def fwd_bwd(x):
+        bb, nn_, _ = x.shape
+        corr = O.feature_correlation(x)
+        outs = [O.forward_pairwise(sds[0], x, [torch.rand(bb, nn_ * nn_, 6)])[0]]
+        for sd, sc in zip(sds[1:], SCALES):
+            outs.append(O.forward_hyper(sd, x, corr, sc, [torch.rand(bb, 1 if sc == nn_ else nn_, 10)])[0])
+        loss = sum(o.sum() for o in outs) / bb
+        loss.backward()
+        for sd in sds:
+            for v in sd.values():
+                v.grad = None
+
+    gen = torch.Generator().manual_seed(0)
+    fwd_bwd(torch.randn(64, AGENTS, HDIM, generator=gen))          # warm-up
+    done, spent = 0, 0.0
+    while spent < budget_s:
+        x = torch.randn(128, AGENTS, HDIM, generator=gen)
+        t0 = time.perf_counter()
+        fwd_bwd(x)
+        spent += time.perf_counter() - t0
+        done += 128
+    return {"value": done / spent, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} scenes in chunks of 128, fwd + bwd by torch autograd through the oracle port, {spent:.1f} s"}
 
 
 def run_crowd(args, rank, world, local):
@@ -418,6 +509,60 @@ def run_crowd(args, rank, world, local):
         torch.cuda.synchronize(dev)
         prof = _lib.profile_collect()
         _lib.profile_enable(False)
+
+        # ---- end to end: host (pinned) features in, host features + incidence out, streamed in chunks of scenes over
+        # three streams (the whole shard is 17 GB in / 73 GB out: it never sits in host memory at once — the chunk
+        # buffers are the application's staging area and every chunk's bytes cross PCIe inside the timed region)
+        ck = min(4096, b)
+        nck = (b + ck - 1) // ck
+        x_pin = torch.randn(ck, n, d).pin_memory()
+        f_pin = torch.empty(ck, n, d * len(scales)).pin_memory()
+        h_pin = torch.empty(ck, hcat.shape[1], n).pin_memory()
+        xd = [torch.empty(ck, n, d, device=dev) for _ in range(2)]
+        fd = [torch.empty(ck, n, d * len(scales), device=dev) for _ in range(2)]
+        hd = [torch.empty(ck, hcat.shape[1], n, device=dev) for _ in range(2)]
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        main_s = torch.cuda.current_stream(dev)
+
+        def step_e2e():
+            ev_in = [None, None]; ev_cmp = [None, None]; ev_out = [None, None]
+            for c in range(nck):
+                k = c & 1
+                m = min(ck, b - c * ck)
+                with torch.cuda.stream(s_in):
+                    if ev_cmp[k] is not None:
+                        s_in.wait_event(ev_cmp[k])              # the chunk that used this input buffer has been computed
+                    xd[k][:m].copy_(x_pin[:m], non_blocking=True)
+                    ev_in[k] = torch.cuda.Event(); ev_in[k].record(s_in)
+                main_s.wait_event(ev_in[k])
+                if ev_out[k] is not None:
+                    main_s.wait_event(ev_out[k])                # its output buffers have been copied out
+                for l in layers:
+                    l.set_rng("philox", seed=l.philox_seed, scene_offset=rank * b + c * ck)
+                hs = ops.corr_topk_h_into(xd[k][:m], list(scales), hd[k][:m])
+                for i, l in enumerate(layers):
+                    l(xd[k][:m], H=hs[i], out=fd[k][:m, :, i * d:(i + 1) * d], want_factors=False)
+                ev_cmp[k] = torch.cuda.Event(); ev_cmp[k].record(main_s)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[k])
+                    f_pin[:m].copy_(fd[k][:m], non_blocking=True)
+                    h_pin[:m].copy_(hd[k][:m], non_blocking=True)
+                    ev_out[k] = torch.cuda.Event(); ev_out[k].record(s_out)
+            main_s.wait_stream(s_out)
+
+        step_e2e()
+        barrier()
+        e2e_steps = max(1, min(args.steps, 2))
+        e0.record()
+        for _ in range(e2e_steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        e2e_ms = e0.elapsed_time(e1) / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
     if rank == 0:
         peaks = {}
         try:
@@ -446,9 +591,49 @@ def run_crowd(args, rank, world, local):
                        "sharding": "batch-sharded, no collective on the forward path"},
             "flops_per_scene": 451e6, "tflops_at_survey_flops": 451e6 * world * b / (ms * 1e-3) / 1e12,
             "clocks": clocks.summary(), "gpu_launches": sum(c for _, c in prof.values()) * args.steps,
-            "roofline": roof, "kernels": kernels}), flush=True)
+            "e2e": {"value": world * b / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": b * n * d * 4,
+                    "d2h_bytes_per_step": b * n * d * len(scales) * 4 + b * hcat.shape[1] * n * 4, "steps": e2e_steps,
+                    "api": f"corr_topk_h + 4 x MS_HGNN_hyper.forward per chunk of {ck} scenes; pinned host chunk in, "
+                           "features + incidence out, 3-stream pipeline"},
+            "roofline": roof, "kernels": kernels,
+            **({"cpu_baseline": cpu_baseline_crowd()} if world == 1 and not args.no_cpu_baseline else {})}),
+            flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def cpu_baseline_crowd(budget_s=12.0):
+    """Reference CPU path of the crowd step (oracle port, as written): corr + top-k + four MS_HGNN_hyper layers at
+    N = 64, h_dim 256, chunks of 8 scenes (the reference materialises 2 MB per scene and layer)."""
+    from oracle import ms_hgnn_oracle as O
+    import groupnet_b200 as gb
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n, d, scales = 64, 256, (2, 4, 8, 16)
+    torch.manual_seed(1234)
+    sds = []
+    for sc in scales:
+        l = gb.MS_HGNN_hyper(d, d, 64, d, batch_norm=0, nmp_layers=1, scale=sc)
+        sds.append({k: v.detach().clone() for k, v in l.state_dict().items()})
+    gen = torch.Generator().manual_seed(0)
+
+    def fwd(x):
+        with torch.no_grad():
+            corr = O.feature_correlation(x)
+            for sd, sc in zip(sds, scales):
+                O.forward_hyper(sd, x, corr, sc, [torch.rand(x.shape[0], n, 10)])
+
+    fwd(torch.randn(8, n, d, generator=gen))
+    done, spent = 0, 0.0
+    while spent < budget_s:
+        x = torch.randn(8, n, d, generator=gen)
+        t0 = time.perf_counter()
+        fwd(x)
+        spent += time.perf_counter() - t0
+        done += 8
+    return {"value": done / spent, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{done} scenes in chunks of 8 (oracle port, fp32 torch CPU, as-written algorithm), {spent:.1f} s"}
 
 
 # ---------------------------------------------------------------------------
@@ -607,6 +792,10 @@ def main():
                          "scales {2,4,8,16}, 262,144 scenes sharded over the GPUs (strong scaling); fish8 / fish20: "
                          "configs[1], the MS_HGNN layers at the fish dataset shapes (8 agents, scales {3,5,8}; "
                          "20 agents, scales {5,8}; SURVEY.md 8d), 65,536 synthetic scenes per GPU")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="nba / fish lines.  weak (default, the driver's curve): --scenes per GPU.  strong: --scenes is "
+                         "the GLOBAL batch, split evenly over the ranks (SURVEY.md 8e: 65,536 / 8 = 8,192 scenes per "
+                         "GPU), and a step is ONE CUDA-graph launch per rank (device-resident Philox seed)")
     ap.add_argument("--mode", default="forward", choices=["forward", "train"],
                     help="train: fwd+bwd through the three layers + one NCCL all-reduce of the flat gradient "
                          "bucket (BASELINE config 5); per-GPU batch --scenes (default 8192 in this mode)")
@@ -647,11 +836,14 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    b, n, d = args.scenes, AGENTS, HDIM
+    strong = args.scaling == "strong"
+    if strong and args.scenes % world:
+        raise SystemExit("--scaling strong needs --scenes divisible by the number of ranks")
+    b, n, d = (args.scenes // world if strong else args.scenes), AGENTS, HDIM
 
     torch.manual_seed(1234)                         # weights
     model = gb.MultiScaleInteraction(d, SCALES).to(dev).eval().set_precision(args.precision)
-    model.set_rng("philox", seed=0, scene_offset=rank * b)
+    model.set_rng("philox-device" if strong else "philox", seed=0, scene_offset=rank * b)
     for l in model.layers():
         l.workspace_limit_bytes = 9 << 30          # one launch per kernel for the whole shard
     x_host = torch.randn(b, n, d, generator=torch.Generator().manual_seed(rank)).pin_memory()
@@ -699,13 +891,33 @@ def main():
         with torch.no_grad():
             for _ in range(args.warmup):
                 model(x, out_feature=feat, out_H=hcat)
+            graph = None
+            if strong:
+                # 8,192 scenes per GPU is ~2 ms of kernels behind ~20 launches: one graph launch per step keeps the
+                # host out of the way; the captured kernels read and advance the Philox seed in device memory, so
+                # every replay draws fresh noise
+                torch.cuda.synchronize(dev)
+                side = torch.cuda.Stream(device=dev)
+                with torch.cuda.stream(side):
+                    model(x, out_feature=feat, out_H=hcat)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    model(x, out_feature=feat, out_H=hcat)
+                for _ in range(args.warmup):
+                    graph.replay()
             barrier()
             with ClockSampler(local) as clocks:
                 e0.record()
                 for _ in range(steps):
-                    model(x, out_feature=feat, out_H=hcat)
+                    if graph is not None:
+                        graph.replay()
+                    else:
+                        model(x, out_feature=feat, out_H=hcat)
                 e1.record()
                 barrier()
+            del graph
             region_ms = e0.elapsed_time(e1)
             ms_step = max_over_ranks(region_ms / steps)
             # per-kernel durations, CUDA events on the launch stream (library profiling hook)
@@ -808,7 +1020,7 @@ def main():
 
     line = {
         "metric": METRIC, "value": head["value"], "unit": "scenes/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": head["dtype"], "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenes_per_gpu": b, "agents": n, "h_dim": d, "scales": list(SCALES),
                    "noise": "philox on device (distribution-equal to the reference's torch.rand)",
@@ -816,7 +1028,9 @@ def main():
                    "outputs": "node features of the 1+S layers and every H_s written per step; the layers' `factors` "
                               "are not (want_factors=False, as PastEncoder discards them, model/GroupNet_nba.py:290-299)",
                    "l2": "no flush: x (184 MB) and the per-step scratch (GBs) exceed the 126 MB L2",
-                   "sharding": "batch-sharded, no collective on the forward path"},
+                   "sharding": "batch-sharded, no collective on the forward path"
+                               + (f"; strong scaling: global batch {args.scenes} split over {world} ranks, one CUDA-graph "
+                                  "launch per rank and step" if strong else "")},
         "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "parity": head["parity"],
         "roofline": head["roofline"], "kernels": head["kernels"],
         "paths": {k: v for k, v in paths.items() if k != args.precision},

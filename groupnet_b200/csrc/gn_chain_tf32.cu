@@ -141,6 +141,41 @@ __device__ __forceinline__ void drain_slice(const Args& a, const Op& op, const f
   if (KIND == DR_TMEM || KIND == DR_TMEM_STORE) tf::tmem_st_wait();
 }
 
+// x / d with r = 1 / d correctly rounded: one Newton correction gives the correctly rounded quotient (d is an agent
+// count: no overflow / denormal corner cases)
+__device__ __forceinline__ float div_by(float x, float d, float r) {
+  const float q0 = x * r;
+  return fmaf(fmaf(-q0, d, x), r, q0);
+}
+
+// DR_DOTG: this thread's share of the distribution head: lg[t] = sum over its 32 hidden units k of
+// relu(acc[k] + b[k]) * W[k][t], W = [128][TP] fp32 in the smem constants (rows of TP = 8, 12 or 16 logits, zero padded)
+template <int TP>
+__device__ __forceinline__ void dot_logits(const Op& op, const float* aux, const float* w4, uint32_t tmem_row, int sl,
+                                           float (&lg)[16]) {
+#pragma unroll
+  for (int t = 0; t < 16; ++t) lg[t] = 0.f;
+  uint32_t r0[16], r1[16];
+  tf::tmem_ld16_nowait(tmem_row + op.acc_col + 32 * sl, r0);
+  tf::tmem_ld16_nowait(tmem_row + op.acc_col + 32 * sl + 16, r1);
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int c0 = 32 * sl + 16 * half;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = fmaxf(__uint_as_float(half ? r1[j] : r0[j]) + aux[op.bias_off + c0 + j], 0.f);
+      const float* wr = w4 + (c0 + j) * TP;
+#pragma unroll
+      for (int t4 = 0; t4 < TP / 4; ++t4) {
+        const float4 wv = *reinterpret_cast<const float4*>(wr + 4 * t4);
+        lg[4 * t4] = fmaf(v, wv.x, lg[4 * t4]); lg[4 * t4 + 1] = fmaf(v, wv.y, lg[4 * t4 + 1]);
+        lg[4 * t4 + 2] = fmaf(v, wv.z, lg[4 * t4 + 2]); lg[4 * t4 + 3] = fmaf(v, wv.w, lg[4 * t4 + 3]);
+      }
+    }
+  }
+}
+
 // drain variants the launchers use (Op::variant)
 enum { DV_TMEM = 0, DV_TMEM_RELU, DV_TMEM_RELU_RS, DV_TMEM_STORE, DV_STORE, DV_STORE_BM, DV_DOT_RELU, DV_COUNT };
 
@@ -397,19 +432,33 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
           } else {
             const int K = op.K, k0 = op.st_k0;
             const bool div = a.a_div != 0.f;
-            for (int k4 = sl; k4 < (K >> 2); k4 += NSLICE) {
-              const int k = k0 + 4 * k4;
-              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (live) {
-                const float* src = (k < a.k_src0) ? a.src0 + grow * a.ld0 + k : a.src1 + grow * a.ld1 + (k - a.k_src0);
-                x = ldg_f4(src);
-                if (div) { x.x /= a.a_div; x.y /= a.a_div; x.z /= a.a_div; x.w /= a.a_div; }
+            const float rdiv = div ? 1.f / a.a_div : 0.f;
+            // all of the thread's loads go out before the first one is consumed (K <= 128: at most 8 x 16 B per
+            // thread); a load -> split -> store loop exposed one DRAM latency per iteration
+            constexpr int MAXI = 128 / 4 / NSLICE;
+            float4 xs[MAXI];
+#pragma unroll
+            for (int i = 0; i < MAXI; ++i) {
+              const int k4 = sl + NSLICE * i, k = k0 + 4 * k4;
+              xs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (live && k4 < (K >> 2))
+                xs[i] = ldg_f4((k < a.k_src0) ? a.src0 + grow * a.ld0 + k : a.src1 + grow * a.ld1 + (k - a.k_src0));
+            }
+#pragma unroll
+            for (int i = 0; i < MAXI; ++i) {
+              const int k4 = sl + NSLICE * i;
+              if (k4 < (K >> 2)) {
+                float4 x = xs[i];
+                if (div) {                       // x / d as q0 = x r, q = q0 + (x - q0 d) r: the IEEE quotient without the
+                  x.x = div_by(x.x, a.a_div, rdiv); x.y = div_by(x.y, a.a_div, rdiv);   // ~30-instruction div.rn sequence
+                  x.z = div_by(x.z, a.a_div, rdiv); x.w = div_by(x.w, a.a_div, rdiv);   // (32 per thread and tile)
+                }
+                uint4 h4, l4;
+                tf::split_tf32(x.x, h4.x, l4.x); tf::split_tf32(x.y, h4.y, l4.y);
+                tf::split_tf32(x.z, h4.z, l4.z); tf::split_tf32(x.w, h4.w, l4.w);
+                *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
+                *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
               }
-              uint4 h4, l4;
-              tf::split_tf32(x.x, h4.x, l4.x); tf::split_tf32(x.y, h4.y, l4.y);
-              tf::split_tf32(x.z, h4.z, l4.z); tf::split_tf32(x.w, h4.w, l4.w);
-              *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
-              *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
             }
             fence_proxy_async_smem();
             fence_before_thread_sync();
@@ -454,50 +503,65 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         fence_after_thread_sync();
         if (tr) trp[3 * e + 1] = clock64();
         const int kind = op.drain;
-        if (kind == DR_GUMBEL) {
-          // slice sl handles the edge types t in [sl*tq, sl*tq + tq): y = (logit + g) / tau with the noise g left in ybuf
-          // by the staging event; the row's y meet in shared memory for the softmax; factor = sigmoid of the dot
-          // partials left by the DR_DOT drain
-          float v[16];
-          tmem_ld16(tmem_row + op.acc_col, v);
-          const int T = a.T, tq = (T + NSLICE - 1) / NSLICE;
-          constexpr int TQ = (GN_SMALL_OUT - 1 + NSLICE - 1) / NSLICE;
-          const int t0 = sl * tq;
+        if (kind == DR_DOTG) {
+          // The distribution head (128 -> T) as fp32 dot products inside this drain — no A-operand split, no MMA, no
+          // accumulator round trip (the GEMM form cost a 256-column hi | lo store, a K = 128 MMA chain and a handoff) —
+          // followed by the Gumbel softmax / sigmoid tail (:45-53).  Slice sl holds 32 of the 128 hidden units: its T
+          // partial logits, and the factor head's partial from the DR_DOT drain, meet the other slices' through spare
+          // TENSOR MEMORY columns (the row's four threads share TMEM lanes, not a warp).
+          float lg[16];
+          if (a.w4_tp == 8) dot_logits<8>(op, aux, aux + a.w4_off, tmem_row, sl, lg);
+          else if (a.w4_tp == 12) dot_logits<12>(op, aux, aux + a.w4_off, tmem_row, sl, lg);
+          else dot_logits<16>(op, aux, aux + a.w4_off, tmem_row, sl, lg);
+          lg[15] = carry;
+          {
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = __float_as_uint(lg[j]);
+            tf::tmem_st16(tmem_row + op.dst_col + 16 * sl, pk);
+            tf::tmem_st_wait();
+          }
+          fence_before_thread_sync();
+          row_bar();
+          fence_after_thread_sync();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) lg[j] = 0.f;
+#pragma unroll
+          for (int s4 = 0; s4 < NSLICE; ++s4) {          // fixed order: every slice gets the same sums
+            float qv[16];
+            tmem_ld16(tmem_row + op.dst_col + 16 * s4, qv);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lg[j] += qv[j];
+          }
+          const int T = a.T, tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
           if (live) {
+            // y = (logit + g) / tau with the noise g left in ybuf by the staging event
+            float mx = -INFINITY;
 #pragma unroll
-            for (int jj = 0; jj < TQ; ++jj) {
-              const int t = t0 + jj;
-              if (jj < tq && t < T) {
-                float lg = 0.f;
-#pragma unroll
-                for (int o = 0; o < GN_SMALL_OUT; ++o) if (o == t) lg = v[o];
-                ybuf[row * 17 + t] = (lg + aux[a.gb_off + t] + ybuf[row * 17 + t]) / 0.5f;
+            for (int t = 0; t < GN_SMALL_OUT - 1; ++t) {
+              if (t < T) {
+                lg[t] = (lg[t] + aux[a.gb_off + t] + ybuf[row * 17 + t]) / 0.5f;
+                mx = fmaxf(mx, lg[t]);
               }
             }
-          }
-          dotp[sl * 128 + row] = carry;
-          row_bar();
-          if (live) {
-            float mx = -INFINITY;
-            for (int t = 0; t < T; ++t) mx = fmaxf(mx, ybuf[row * 17 + t]);
             // ex2.approx-based exponentials: 2 ulp, three orders of magnitude inside the 1e-5 bound of outputs in [0, 1]
             float den = 0.f;
-            for (int t = 0; t < T; ++t) den += __expf(ybuf[row * 17 + t] - mx);
-            float fl = aux[a.gb_off + T];
 #pragma unroll
-            for (int s4 = 0; s4 < NSLICE; ++s4) fl += dotp[s4 * 128 + row];
-            const float factor = 1.f / (1.f + __expf(-fl));
+            for (int t = 0; t < GN_SMALL_OUT - 1; ++t) {
+              if (t < T) { lg[t] = __expf(lg[t] - mx); den += lg[t]; }
+            }
+            const float factor = 1.f / (1.f + __expf(-(lg[15] + aux[a.gb_off + T])));
 #pragma unroll
-            for (int jj = 0; jj < TQ; ++jj) {
-              const int t = t0 + jj;
-              if (jj < tq && t < T) {
-                const float dd = __expf(ybuf[row * 17 + t] - mx) / den;
+            for (int t = 0; t < GN_SMALL_OUT - 1; ++t) {
+              if (t >= t0 && t < t0 + tq && t < T) {
+                const float dd = lg[t] / den;
                 if (a.dist_out != nullptr) a.dist_out[static_cast<size_t>(grow) * T + t] = dd;
                 a.edge_feat[static_cast<size_t>(grow) * T + t] = factor * dd;
               }
             }
           }
-          row_bar();                              // ybuf / dotp are rewritten by the next tile
+          fence_before_thread_sync();
+          row_bar();                              // ybuf and the exchange columns are rewritten by the next tile
         } else if (kind != DR_NONE) {
           const float* rsb = ybuf + row * 17;               // per-row scales staged at tile start (programs with a.rs)
           switch (op.variant) {
@@ -602,6 +666,7 @@ static int drain_variant(const Op& op) {
     case DR_TMEM_STORE: return (rs || op.relu || op.use_bm) ? -1 : DV_TMEM_STORE;
     case DR_STORE: return (rs || op.relu) ? -1 : (op.use_bm ? DV_STORE_BM : DV_STORE);
     case DR_DOT: return (rs || !op.relu || op.use_bm) ? -1 : DV_DOT_RELU;
+    case DR_DOTG: return (rs || !op.relu || op.use_bm) ? -1 : 0;
     default: return 0;
   }
 }
@@ -616,9 +681,9 @@ static int validate_program(Args& a) {
     if (static_cast<uint32_t>(op.N) * op.kc * 8 > a.stage_bytes) return GN_E_SHAPE;
     if (op.acc_col < 0 || op.acc_col + op.N > 512) return GN_E_SHAPE;
     if (op.a_src == A_TMEM && (op.a_col < 0 || op.a_col + 2 * op.K > 512)) return GN_E_SHAPE;
-    if (op.a_src == A_SMEM && static_cast<uint32_t>(op.K) * 128 * 4 > a.a0_half_bytes) return GN_E_SHAPE;
+    if (op.a_src == A_SMEM && (static_cast<uint32_t>(op.K) * 128 * 4 > a.a0_half_bytes || op.K > 128)) return GN_E_SHAPE;
     if (op.signal) {
-      if (op.drain == DR_GUMBEL) { if (op.dn != 16) return GN_E_SHAPE; }
+      if (op.drain == DR_DOTG) { if (op.dn != 128 || op.dst_col < 0 || op.dst_col + 16 * NSLICE > 512 || a.w4_off < 0) return GN_E_SHAPE; }
       else if (op.drain != DR_NONE && ((op.dn != 64 && op.dn != 128) || op.dn > op.N)) return GN_E_SHAPE;   // NSLICE x 16 / 32
       if (op.nsum > 1 && (op.sum_stride < op.dn || op.acc_col + (op.nsum - 1) * op.sum_stride + op.dn > 512)) return GN_E_SHAPE;
       if ((op.drain == DR_TMEM || op.drain == DR_TMEM_STORE) && (op.dst_col < 0 || op.dst_col + 2 * op.dn > 512)) return GN_E_SHAPE;
@@ -723,8 +788,8 @@ using namespace tfe;
 
 // ---- per-edge chain: init_MLP -> [MLP_distribution | MLP_factor] -> Gumbel softmax / sigmoid (:41-53)
 //   G1 64->128 (ReLU)  G2 128->64 (z)  G3f 64->128 (factor hidden, ReLU; its 128->1 head is a dot in the drain)
-//   G3d 64->128 (distribution hidden, ReLU)  G4 128->16 (T logits)  -> epilogue
-// TMEM columns: acc1 0 | A1 128,256 | acc2 384 | A2 0,64 | acc3f 128 | acc3d 256 | A3 0,128 | acc4 384
+//   G3d 64->128 (distribution hidden, ReLU; its 128->T head is T dots in the drain)  -> Gumbel softmax / sigmoid
+// TMEM columns: acc1 0 | A1 128,256 | acc2 384 | A2 0,64 | acc3f 128 | acc3d 256 | logit exchange 0..63
 bool edge_chain_tf32_fits(bool pair, int N, int T) {
   if (T < 1 || T > GN_SMALL_OUT - 1) return false;
   if (!pair) return true;
@@ -762,22 +827,27 @@ int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, con
   Op& g3f = b.add(A_TMEM, 0, 64, 128, 128, 0, 1, 1);
   g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; b.set_bias(g3f, w->df_b0 + 128, 128); g3f.arrive = 0;
   Op& g3d = b.add(A_TMEM, 0, 64, 128, 256, 0, 0, 1);
-  b.drain_tmem(g3d, 128, 1, w->df_b0, 0, 1);
-  Op& g4 = b.add(A_TMEM, 0, 128, 16, 384, 0, 1, 1);
-  g4.drain = DR_GUMBEL; g4.dn = 16; g4.arrive = 0;
+  // the distribution head (128 -> T) and the Gumbel softmax run inside the drain of G3d (DR_DOTG); the slices' partial
+  // logits meet in columns 0..63: A2 is dead once G3d has completed (which that drain waits for), whereas the factor
+  // accumulator next to it may still be read by a slower slice's DR_DOT drain
+  g3d.drain = DR_DOTG; g3d.dn = 128; g3d.relu = 1; b.set_bias(g3d, w->df_b0, 128); g3d.dst_col = 0; g3d.arrive = 0;
   b.ev(EV_STAGE, 0);
-  for (int o = 0; o < 4 + first; ++o) b.ev(EV_DRAIN, o);
+  for (int o = 0; o < 3 + first; ++o) b.ev(EV_DRAIN, o);
   a.stage_mode = pair ? ST_PAIR : ST_ROWS;
   a.src0 = edges; a.ld0 = 64; a.k_src0 = 64; a.src1 = nullptr; a.ld1 = 0; a.a_div = 0.f;
   a.ypre = ypre; a.pq = pq;
   a.N = N; a.E = E;
   a.tps = (pair && E >= 128) ? (E + 127) / 128 : 0;
   // the stream: init_MLP.0 (64 KB, skipped by the pair form) | the chunks of the ops above | MLP_factor.layers.1.weight
+  // (128 floats) | MLP_distribution.layers.1.weight as [128][8, 12 or 16] fp32 (k-major rows of T logits, zero padded)
   const unsigned char* stream = static_cast<const unsigned char*>(w->tf_chain_w);
   const size_t w1_bytes = 128 * 64 * 8;
-  a.dot_off = b.aux(reinterpret_cast<const float*>(stream + (pair ? w1_bytes : 0) + b.wbytes), 128);
+  const float* tail = reinterpret_cast<const float*>(stream + (pair ? w1_bytes : 0) + b.wbytes);
+  a.dot_off = b.aux(tail, 128);
+  a.w4_tp = T <= 8 ? 8 : (T <= 12 ? 12 : 16);
+  a.w4_off = b.aux(tail + 128, 128 * a.w4_tp);
   a.gb_off = b.aux(w->df_b1, GN_SMALL_OUT);
-  if (a.dot_off < 0 || a.gb_off < 0 || (pair && (a.yb_off < 0 || a.att_off < 0))) return GN_E_SHAPE;
+  if (a.dot_off < 0 || a.w4_off < 0 || a.gb_off < 0 || g3d.bias_off < 0 || (pair && (a.yb_off < 0 || a.att_off < 0))) return GN_E_SHAPE;
   a.T = T;
   a.U = U; a.noise_mode = noise_mode; a.seed = seed; a.scene_offset = scene_offset; a.stage_index = stage_index;
   a.dist_out = dist_out; a.edge_feat = edge_feat;

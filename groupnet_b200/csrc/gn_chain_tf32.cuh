@@ -16,7 +16,7 @@ constexpr int MAXN = 36, NLD = 68, YLD = 132;
 __host__ __device__ constexpr uint32_t node_block_bytes() { return static_cast<uint32_t>(MAXN) * (NLD + YLD) * 4; }
 constexpr int NSLICE = 4;                      // threads per tile row (column slices); 16 row warps
 constexpr uint32_t SCR_BYTES = (NSLICE * 128 * 2 + NSLICE * 128 + 128 * 17) * 4;   // logit partials | dot partials | y
-constexpr int AUX_FLOATS = 2048;               // small constants (biases, attention tail, factor head) kept in smem:
+constexpr int AUX_FLOATS = 3072;               // small constants (biases, attention tail, factor head) kept in smem:
                                                // with ~227 KB of shared memory carved out there is no L1 left
 constexpr int MAX_AUX = 12;
 constexpr uint32_t FIXED_BYTES = SCR_BYTES + AUX_FLOATS * 4 + 1024;                // + barriers + alignment slack
@@ -33,7 +33,7 @@ constexpr int TR_TILES = 6, TR_ROWS = 3 * MAX_OPS, TR_CHUNK = TR_ROWS + 3 * MAX_
 // [TR_CHUNK, +4*TR_MAXCH): per weight chunk: producer issued the copy | issuer: wait start, wait end, MMAs issued
 constexpr int TR_STAGE = TR_CHUNK + 4 * TR_MAXCH;      // 8 sub-stamps inside the (pairwise) staging pass
 constexpr int TR_SLOTS = TR_STAGE + 8;
-enum { DR_NONE = 0, DR_TMEM = 1, DR_STORE = 2, DR_TMEM_STORE = 3, DR_DOT = 4, DR_GUMBEL = 5 };
+enum { DR_NONE = 0, DR_TMEM = 1, DR_STORE = 2, DR_TMEM_STORE = 3, DR_DOT = 4, DR_DOTG = 5 };
 enum { ST_ROWS = 0, ST_PAIR = 1 };
 enum { A_SMEM = 0, A_TMEM = 1 };
 
@@ -89,8 +89,9 @@ struct Args {
   const float* bm; int bm_T; int bm_ld; int bm_off;   // bm_off >= 0: bm lives in the smem constants
   // DR_DOT: carry = sum_k relu(acc_k + bias_k) * dot_w[k * dot_stride]
   int dot_off;                     // smem constants
-  // DR_GUMBEL (MLP_dict_softmax tail, :45-53, :446-520)
+  // DR_DOTG (distribution head + MLP_dict_softmax tail, :45-53, :446-520)
   int gb_off; int T;               // smem constants: df_b1[16]
+  int w4_off, w4_tp;               // smem constants: MLP_distribution.layers.1.weight as [128][w4_tp], w4_tp = 8, 12 or 16
   const float* U; int noise_mode; unsigned long long seed; long long scene_offset; int stage_index;
   float* dist_out; float* edge_feat;
   // shared-memory layout

@@ -727,15 +727,18 @@ __global__ void gumbel_bwd_kernel(const float* __restrict__ efeat, const float* 
   if (r >= R) return;
   float f = 0.f;
   for (int t = 0; t < T; ++t) f += efeat[r * T + t];
+  // a sigmoid that underflowed to 0 makes dist = 0 / 0: the categorical is then unobservable from edge_feat, and every
+  // gradient through this row carries the factor f = 0 anyway — use the uniform distribution instead of NaN
+  const float inv = f > 0.f ? 1.f / f : 0.f, fallback = f > 0.f ? 0.f : 1.f / static_cast<float>(T);
   float df = 0.f, dot = 0.f;
   for (int t = 0; t < T; ++t) {
-    const float dist = efeat[r * T + t] / f;
+    const float dist = fmaf(efeat[r * T + t], inv, fallback);
     const float dd = d_efeat[r * T + t] * f + (d_dist_ext ? d_dist_ext[r * T + t] : 0.f);
     df = fmaf(d_efeat[r * T + t], dist, df);
     dot = fmaf(dist, dd, dot);
   }
   for (int t = 0; t < T; ++t) {
-    const float dist = efeat[r * T + t] / f;
+    const float dist = fmaf(efeat[r * T + t], inv, fallback);
     const float dd = d_efeat[r * T + t] * f + (d_dist_ext ? d_dist_ext[r * T + t] : 0.f);
     d_logits[r * T + t] = 2.f * dist * (dd - dot);
   }

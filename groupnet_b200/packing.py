@@ -172,7 +172,7 @@ def hyper_fused_stream(agg_params, d: int) -> torch.Tensor:
 # ---------------------------------------------------------------------------
 TF_SMEM_BUDGET = 227 * 1024
 TF_NODE_BLOCK = 36 * (68 + 132) * 4
-TF_FIXED = (4 * 128 * 2 + 4 * 128 + 128 * 17) * 4 + 2048 * 4 + 1024
+TF_FIXED = (4 * 128 * 2 + 4 * 128 + 128 * 17) * 4 + 3072 * 4 + 1024
 
 
 def tf_stage_bytes(a0_k: int, nbuf: int, node_block: bool) -> int:
@@ -356,11 +356,13 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
 
     # fp32-grade tensor-core path (GN_TF32X3): 3xTF32 weight streams of the chains whose shape fits
     # (the *_tf32_fits() predicates of csrc/gn_chain_tf32.cu; absent streams fall back to the FFMA kernels)
-    w4 = torch.zeros(16, 128, dtype=torch.float32, device=device)
-    w4[:t] = dev(dist[1].weight)
-    out["tf_chain_w"] = tf_stream([dev(init[0].weight), dev(init[1].weight), dev(fac[0].weight),
-                                   dev(dist[0].weight), w4], min(tf_stage_bytes(64, 1, False), tf_stage_bytes(0, 1, True)),
-                                  tail=dev(fac[1].weight))            # the factor head (128 -> 1) is a dot in the drain
+    # the factor head (128 -> 1) and the distribution head (128 -> T) are fp32 dots in the drains: plain fp32 tail,
+    # the latter k-major as [128][8, 12 or 16] (rows of T logits, zero padded)
+    w4 = torch.zeros(128, 8 if t <= 8 else (12 if t <= 12 else 16), dtype=torch.float32, device=device)
+    w4[:, :t] = dev(dist[1].weight).t()
+    out["tf_chain_w"] = tf_stream([dev(init[0].weight), dev(init[1].weight), dev(fac[0].weight), dev(dist[0].weight)],
+                                  min(tf_stage_bytes(64, 1, False), tf_stage_bytes(0, 1, True)),
+                                  tail=torch.cat((dev(fac[1].weight).reshape(-1), w4.reshape(-1))))
     if d % 8 == 0 and d <= 128:
         nw0, nw1 = dev(node[0].weight), dev(node[1].weight)
         pre = [nw0[:128], nw1[:, :128], nw0[128:], nw1[:, 128:], torch.cat((w0[:, :64], w0[:, 64:]), dim=0)]

@@ -135,7 +135,9 @@ typedef struct gn_stage_weights {
    * to 11 significand bits), each in the canonical K-major no-swizzle layout with 32-bit elements
    * byte(n,k) = (k/4)*(N*16) + n*16 + (k%4)*4   (csrc/gn_tf32.cuh) */
   const void* tf_chain_w;  /* init_MLP.0 (128x64), init_MLP.1 (64x128), MLP_factor.0 (128x64), MLP_distribution.0
-                              (128x64), MLP_distribution.1 zero-padded to (16x128) */
+                              (128x64); then plain fp32: MLP_factor.1 (128 floats), MLP_distribution.1 k-major as
+                              [128][8] (T <= 8), [128][12] (T <= 12) or [128][16], rows of T logits zero padded (both heads are fp32 dot
+                              products inside the drains) */
   const void* tf_pre_w;    /* node W0[0:128] (128xD), W1[:,0:128] (64x128), W0[128:256], W1[:,128:256], [Wp;Wq] (64x64) */
   const void* tf_aggin_w;  /* agg_mlp[t].layers.0 (128xD) for t < T */
   const void* tf_aggout_w; /* cat_t agg_mlp[t].layers.1 along K, (D x T*128), in K blocks of 64 */
