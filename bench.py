@@ -787,6 +787,8 @@ def main():
                          "kernels (1e-5 parity).  The other tensor-core path is measured the same way and printed as a "
                          "full object under `paths`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", action="store_true",
+                    help="measure only the headline --precision path (profiling runs: keeps the ncu launch list short)")
     ap.add_argument("--workload", default="nba", choices=["nba", "crowd", "fish8", "fish20", "decoder"],
                     help="nba: BASELINE configs[2] (the headline line); crowd: configs[3], N=64, h_dim 256, "
                          "scales {2,4,8,16}, 262,144 scenes sharded over the GPUs (strong scaling); fish8 / fish20: "
@@ -879,15 +881,19 @@ def main():
     out_h = torch.empty(b, model.incidence_rows(n), n, dtype=torch.float32).pin_memory()
     # x slice of final_feature: filled on the host when this rank has cores to spare, else written by the GPU
     # and copied back with the rest (8 ranks x 2 threads: the host-side fill was the bottleneck)
-    slice_mode = os.environ.get("GN_E2E_INPUT_SLICE") or ("host" if torch.get_num_threads() >= 16 else "device")
     h2d = b * n * d * 4
-    d2h = b * n * (model.feature_width() - (d if slice_mode == "host" else 0)) * 4 + out_h.numel() * 4
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def measure(precision, steps):
         """One full measurement of a precision path: device-resident throughput (CUDA events, max over ranks),
         per-kernel durations, roofline of its dominant kernel, and the end-to-end figure through forward_host."""
         model.set_precision(precision)
+        # x slice of final_feature: the fp32-grade path is compute-bound end to end, so the launch thread must not
+        # spend time copying on the host ("device": the GPU writes the slice, whole rows go back); the bf16 path is
+        # PCIe-bound, so it saves the 25 % of D2H bytes ("host") — profiles/e2e_sweep.py
+        slice_mode = os.environ.get("GN_E2E_INPUT_SLICE") or (
+            "host" if (torch.get_num_threads() >= 16 and precision == "bf16") else "device")
+        d2h = b * n * (model.feature_width() - (d if slice_mode == "host" else 0)) * 4 + out_h.numel() * 4
         with torch.no_grad():
             for _ in range(args.warmup):
                 model(x, out_feature=feat, out_H=hcat)
@@ -989,9 +995,9 @@ def main():
     head = measure(args.precision, args.steps)
     paths = {args.precision: head}
     for other in ("tf32", "bf16"):                 # the other tensor-core path, measured by the same protocol
-        if other not in paths:
+        if other not in paths and not args.only:
             paths[other] = measure(other, args.steps)
-    if "fp32" not in paths and os.environ.get("GN_BENCH_FFMA", "1") != "0":
+    if "fp32" not in paths and os.environ.get("GN_BENCH_FFMA", "1") != "0" and not args.only:
         # the FFMA kernels (where shapes the chains do not cover fall back to): device-resident figure only
         model.set_precision("fp32")
         with torch.no_grad():
