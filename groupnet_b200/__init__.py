@@ -9,13 +9,13 @@ from .layers import (MLP, MLP_dict, MLP_dict_softmax, MS_HGNN_hyper, MS_HGNN_ori
 from .encoder import PastEncoder, PositionalAgentEncoding
 from .interaction import MultiScaleInteraction
 from .decoder import Decoder, DecomposeBlock
-from .rollout import GraphedPastEncoder
+from .rollout import GraphedInference, GraphedPastEncoder, inference_simulator
 from .ops import corr_topk_h, topk_h
 from ._lib import GroupNetLibraryError, LIB_PATH
 
 __all__ = [
     "MS_HGNN_oridinary", "MS_HGNN_hyper", "MLP", "MLP_dict", "MLP_dict_softmax",
     "edge_aggregation", "encode_onehot", "make_mlp", "sample_gumbel", "gumbel_softmax_sample", "gumbel_softmax",
-    "my_softmax", "MultiScaleInteraction", "PastEncoder", "PositionalAgentEncoding", "GraphedPastEncoder", "Decoder", "DecomposeBlock", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
+    "my_softmax", "MultiScaleInteraction", "PastEncoder", "PositionalAgentEncoding", "GraphedPastEncoder", "GraphedInference", "inference_simulator", "Decoder", "DecomposeBlock", "corr_topk_h", "topk_h", "GroupNetLibraryError", "LIB_PATH",
 ]
 __version__ = "0.1.0"
