@@ -894,6 +894,7 @@ def main():
         slice_mode = os.environ.get("GN_E2E_INPUT_SLICE") or (
             "host" if (torch.get_num_threads() >= 16 and precision == "bf16") else "device")
         d2h = b * n * (model.feature_width() - (d if slice_mode == "host" else 0)) * 4 + out_h.numel() * 4
+        e2e_chunk = min(8192, max(1024, b // 4))      # >= 4 chunks per shard so copies and compute overlap
         with torch.no_grad():
             for _ in range(args.warmup):
                 model(x, out_feature=feat, out_H=hcat)
@@ -937,15 +938,36 @@ def main():
             launches_per_step = sum(c for _, c in prof.values()) // prof_steps
             # end to end through the public host API: pinned host in, pinned host out
             for _ in range(2):
-                model.forward_host(x_host, out_f, out_h, input_slice=slice_mode)
+                model.forward_host(x_host, out_f, out_h, input_slice=slice_mode, chunk_scenes=e2e_chunk)
             barrier()
             e2e_steps = max(3, min(steps, 10))
             e0.record()
             for _ in range(e2e_steps):
-                model.forward_host(x_host, out_f, out_h, input_slice=slice_mode)
+                model.forward_host(x_host, out_f, out_h, input_slice=slice_mode, chunk_scenes=e2e_chunk)
             e1.record()
             barrier()
             e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+            # copies-only ceiling of this box: the same H2D and D2H bytes as contiguous pinned copies on two streams with no
+            # compute between them — all ranks at once, so a shared host (PCIe switches, memory controllers) shows
+            n_out = (d2h - out_h.numel() * 4) // 4
+            s_a, s_b = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            def copies():
+                with torch.cuda.stream(s_a):
+                    x.copy_(x_host, non_blocking=True)
+                with torch.cuda.stream(s_b):
+                    out_f.view(-1)[:n_out].copy_(feat.view(-1)[:n_out], non_blocking=True)
+                    out_h.copy_(hcat, non_blocking=True)
+            copies()
+            torch.cuda.current_stream(dev).wait_stream(s_a); torch.cuda.current_stream(dev).wait_stream(s_b)
+            barrier()
+            e0.record()
+            s_a.wait_event(e0); s_b.wait_event(e0)
+            for _ in range(e2e_steps):
+                copies()
+            torch.cuda.current_stream(dev).wait_stream(s_a); torch.cuda.current_stream(dev).wait_stream(s_b)
+            e1.record()
+            barrier()
+            copy_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
         # a region shorter than ~1 s runs at burst clocks: compare with the burst peak; longer: the sustained one
         burst = region_ms < 1000.0
         tensor_peak = float(peaks.get("bf16_tflops" if burst else "bf16_tflops_sustained",
@@ -983,6 +1005,10 @@ def main():
             "warmup": args.warmup, "clocks": clocks.summary(),
             "e2e": {"value": world * b / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "input_slice": slice_mode, "steps": e2e_steps,
+                    "copy_ceiling": {"ms_per_step": copy_ms, "value": world * b / (copy_ms * 1e-3), "unit": "scenes/s",
+                                     "frac": round(copy_ms / e2e_ms, 4),
+                                     "what": "the step's H2D + D2H bytes as plain pinned copies on two streams, no compute, "
+                                             "all ranks at once: the PCIe / host-memory ceiling of this box"},
                     "api": "MultiScaleInteraction.forward_host (pinned host in/out, 3-stream chunk pipeline)"},
             "gpu_launches": launches_per_step * steps,
             "parity": {"path": precision, "tolerance": tol,
