@@ -318,6 +318,51 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     if (a.noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && a.U != nullptr)
       seed = __ldg(reinterpret_cast<const unsigned long long*>(a.U));
 
+    // ST_ROWS staging of one tile row: fp32 input columns -> split hi | lo -> canonical smem operand -> arrive on a_ready
+    auto stage_rows = [&](const Op& op, long long g_row, bool lv) {
+      unsigned char* hi = a0 + op.a_buf * a.a0_buf_bytes;
+      unsigned char* lo = hi + a.a0_half_bytes;
+      const int K = op.K, k0 = op.st_k0;
+      const bool div = a.a_div != 0.f;
+      const float rdiv = div ? 1.f / a.a_div : 0.f;
+      // all of the thread's loads go out before the first one is consumed (K <= 128: at most 8 x 16 B per
+      // thread); a load -> split -> store loop exposed one DRAM latency per iteration
+      constexpr int MAXI = 128 / 4 / NSLICE;
+      float4 xs[MAXI];
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int k4 = sl + NSLICE * i, k = k0 + 4 * k4;
+        xs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lv && k4 < (K >> 2))
+          xs[i] = ldg_f4((k < a.k_src0) ? a.src0 + g_row * a.ld0 + k : a.src1 + g_row * a.ld1 + (k - a.k_src0));
+      }
+#pragma unroll
+      for (int i = 0; i < MAXI; ++i) {
+        const int k4 = sl + NSLICE * i;
+        if (k4 < (K >> 2)) {
+          float4 x = xs[i];
+          if (div) {                       // x / d as q0 = x r, q = q0 + (x - q0 d) r: the IEEE quotient without the
+            x.x = div_by(x.x, a.a_div, rdiv); x.y = div_by(x.y, a.a_div, rdiv);   // ~30-instruction div.rn sequence
+            x.z = div_by(x.z, a.a_div, rdiv); x.w = div_by(x.w, a.a_div, rdiv);   // (32 per thread and tile)
+          }
+          uint4 h4, l4;
+          tf::split_tf32(x.x, h4.x, l4.x); tf::split_tf32(x.y, h4.y, l4.y);
+          tf::split_tf32(x.z, h4.z, l4.z); tf::split_tf32(x.w, h4.w, l4.w);
+          *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
+          *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
+        }
+      }
+      fence_proxy_async_smem();
+      fence_before_thread_sync();
+      mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
+    };
+    // programs with EV_STAGE_NEXT stage tile i + 1 inside tile i (after the last MMA that reads the staged buffer):
+    // the input rows' DRAM latency hides behind the rest of the chain; the first tile is staged here
+    if (a.stage_first >= 0 && static_cast<long long>(blockIdx.x) < a.ntiles) {
+      const long long g0 = static_cast<long long>(blockIdx.x) * 128 + row;
+      stage_rows(a.ops[a.stage_first], g0, g0 < a.R);
+    }
+
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
       const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && tid == 0;
@@ -331,9 +376,14 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       for (int e = 0; e < a.nev; ++e) {
         const Op& op = a.ops[a.ev_op[e]];
         if (tr) trp[3 * e] = clock64();
+        if (a.ev_type[e] == EV_STAGE_NEXT) {
+          const long long nt = tile + gridDim.x;
+          const long long gn = nt * 128 + row;
+          stage_rows(op, gn, nt < a.ntiles && gn < a.R);
+          if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
+          continue;
+        }
         if (a.ev_type[e] == EV_STAGE) {
-          unsigned char* hi = a0 + op.a_buf * a.a0_buf_bytes;
-          unsigned char* lo = hi + a.a0_half_bytes;
           if (pair) {
             // fused node2edge of the pairwise layer: attention over the (<= 2) members of edge (i,j), softmax over ALL N
             // nodes (non-members enter with logit 0), self loops carry incidence 2 (:124,:135-137).  Slice sl sums 8 of
@@ -430,39 +480,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
             prefetch_nodes(tile + gridDim.x);
             if (tr) trp[TR_STAGE - TR_ROWS + 7] = clock64();
           } else {
-            const int K = op.K, k0 = op.st_k0;
-            const bool div = a.a_div != 0.f;
-            const float rdiv = div ? 1.f / a.a_div : 0.f;
-            // all of the thread's loads go out before the first one is consumed (K <= 128: at most 8 x 16 B per
-            // thread); a load -> split -> store loop exposed one DRAM latency per iteration
-            constexpr int MAXI = 128 / 4 / NSLICE;
-            float4 xs[MAXI];
-#pragma unroll
-            for (int i = 0; i < MAXI; ++i) {
-              const int k4 = sl + NSLICE * i, k = k0 + 4 * k4;
-              xs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (live && k4 < (K >> 2))
-                xs[i] = ldg_f4((k < a.k_src0) ? a.src0 + grow * a.ld0 + k : a.src1 + grow * a.ld1 + (k - a.k_src0));
-            }
-#pragma unroll
-            for (int i = 0; i < MAXI; ++i) {
-              const int k4 = sl + NSLICE * i;
-              if (k4 < (K >> 2)) {
-                float4 x = xs[i];
-                if (div) {                       // x / d as q0 = x r, q = q0 + (x - q0 d) r: the IEEE quotient without the
-                  x.x = div_by(x.x, a.a_div, rdiv); x.y = div_by(x.y, a.a_div, rdiv);   // ~30-instruction div.rn sequence
-                  x.z = div_by(x.z, a.a_div, rdiv); x.w = div_by(x.w, a.a_div, rdiv);   // (32 per thread and tile)
-                }
-                uint4 h4, l4;
-                tf::split_tf32(x.x, h4.x, l4.x); tf::split_tf32(x.y, h4.y, l4.y);
-                tf::split_tf32(x.z, h4.z, l4.z); tf::split_tf32(x.w, h4.w, l4.w);
-                *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
-                *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
-              }
-            }
-            fence_proxy_async_smem();
-            fence_before_thread_sync();
-            mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;
+            stage_rows(op, grow, live);
           }
           if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
           if (e == 0 && a.rs != nullptr) {
@@ -605,6 +623,7 @@ struct Builder {
   // pairwise and hyper forms, so both use the pairwise layout)
   Builder(int a0_K_, int nbuf_, bool node_block_, bool layout_node) : a0_K(a0_K_), nbuf(nbuf_), node_block(node_block_) {
     memset(&a, 0, sizeof(a));
+    a.stage_first = -1;
     stage_bytes = ring_stage_bytes(a0_K, nbuf, layout_node);
   }
 
@@ -702,21 +721,39 @@ static int validate_program(Args& a) {
   int arrivals = 0, drains = 0;
   for (int e = 0; e < a.nev; ++e) {
     const Op& op = a.ops[a.ev_op[e]];
-    if (a.ev_type[e] == EV_STAGE) ++arrivals;
+    if (a.ev_type[e] == EV_STAGE || a.ev_type[e] == EV_STAGE_NEXT) ++arrivals;
     else { ++drains; if (!op.signal) return GN_E_SHAPE; arrivals += op.arrive; }
   }
   if (arrivals != waits || drains != signals) return GN_E_SHAPE;
+  if (a.stage_first >= 0) {
+    // per-tile side work hangs off an EV_STAGE at e == 0; the staged buffer feeds the tile's FIRST op
+    if (a.stage_first != 0 || a.ops[0].a_src != A_SMEM || a.ops[0].wait_n != 1 || a.stage_mode != ST_ROWS || a.tps != 0 ||
+        a.rs != nullptr || a.edge_feat != nullptr) return GN_E_SHAPE;
+    // a_ready arrivals are consumed in op order: the next tile's staging arrival must be the LAST arrival of this tile,
+    // and it may only overwrite the buffer after the last op that reads it has completed (its drain event precedes)
+    int n_next = 0, last_reader = 0;
+    for (int o = 0; o < a.nops; ++o) if (a.ops[o].a_src == A_SMEM) { if (a.ops[o].a_buf != a.ops[0].a_buf) return GN_E_SHAPE; last_reader = o; }
+    bool reader_drained = false;
+    for (int e = 0; e < a.nev; ++e) {
+      if (a.ev_type[e] == EV_STAGE) return GN_E_SHAPE;
+      if (a.ev_type[e] == EV_STAGE_NEXT) { if (!reader_drained || a.ev_op[e] != 0) return GN_E_SHAPE; ++n_next; continue; }
+      if (a.ev_op[e] >= last_reader) reader_drained = true;      // acc_ready signals complete in op order
+      if (n_next > 0 && a.ops[a.ev_op[e]].arrive) return GN_E_SHAPE;
+    }
+    if (n_next != 1) return GN_E_SHAPE;
+  }
   // run-ahead check over two consecutive tiles: greedy row threads against a lazy issuer and vice versa
   for (int greedy_rows = 0; greedy_rows < 2; ++greedy_rows) {
     int io = 0, ie = 0;                       // issuer op index / row event index (over 2 tiles)
-    int arr = 0, cons = 0, sig = 0, dr = 0;   // produced arrivals, consumed arrivals, produced signals, consumed signals
+    int arr = a.stage_first >= 0 ? 1 : 0;     // produced arrivals (the first tile of such a program is staged up front)
+    int cons = 0, sig = 0, dr = 0;            // consumed arrivals, produced signals, consumed signals
     int pend_wait = a.ops[0].wait_n;
     const int NO = 2 * a.nops, NE = 2 * a.nev;
     auto step_rows = [&]() -> bool {
       if (ie >= NE) return false;
       const int e = ie % a.nev;
       const Op& op = a.ops[a.ev_op[e]];
-      if (a.ev_type[e] == EV_STAGE) { ++arr; ++ie; return true; }
+      if (a.ev_type[e] == EV_STAGE || a.ev_type[e] == EV_STAGE_NEXT) { ++arr; ++ie; return true; }
       if (dr < sig) { ++dr; arr += op.arrive; ++ie; return true; }
       return false;
     };
@@ -876,7 +913,12 @@ int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weig
   s1b.out = xprime; s1b.ldo = 64; s1b.out_col0 = 0;
   Op& s2 = b.add(A_TMEM, 0, 64, 64, 448, 0, 1, 1);
   b.drain_store(s2, 64, 0, nullptr, pq, 64, 0, 0);
-  b.ev(EV_STAGE, 0); b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 2); b.ev(EV_DRAIN, 3); b.ev(EV_DRAIN, 4);
+  // the staged h tile is read by ops 0 and 2: once the drain of op 2 has seen its accumulator the buffer is free, and the
+  // next tile's rows are staged while the rest of the chain runs
+  // (after the drain of op 3: the issuer consumes a_ready arrivals in op order, and the staging arrival belongs to
+  // the NEXT tile's first op, so it must follow the last arriving drain of this tile)
+  a.stage_first = 0;
+  b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 2); b.ev(EV_DRAIN, 3); b.ev(EV_STAGE_NEXT, 0); b.ev(EV_DRAIN, 4);
   if (ypre != nullptr) {
     // pairwise layers: Y = x' W_init0^T (no bias), the per-node half of init_MLP's first Linear (see the edge chain)
     Op& s3 = b.add(A_TMEM, 0, 64, 128, 128, 0, 0, 1);
@@ -999,7 +1041,8 @@ int launch_node_post_tf32(const float* agg, const float* h, long long R, int D, 
   b.drain_tmem(p0, 128, 1, w->post_b0, 128, 1);
   Op& p1 = b.add(A_TMEM, 128, 128, Dout, 384, 0, 1, 1);
   b.drain_store(p1, Dout, 0, w->post_b1, node_out, ld_out, 0, 0);
-  b.ev(EV_STAGE, 0); b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 1);
+  a.stage_first = 0;                      // [agg | h] of the next tile is staged while the second Linear runs
+  b.ev(EV_DRAIN, 0); b.ev(EV_STAGE_NEXT, 0); b.ev(EV_DRAIN, 1);
   a.stage_mode = ST_ROWS; a.src0 = agg; a.ld0 = D; a.k_src0 = D; a.src1 = h; a.ld1 = D;
   a.a_div = static_cast<float>(Nagents);
   return launch(b, R, (R + 127) / 128, static_cast<const unsigned char*>(w->tf_post_w), "node_post_tf32", st);

@@ -26,7 +26,7 @@ inline uint32_t ring_stage_bytes(int a0_K, int nbuf, bool node_block) {
   return avail >= 2 * 65536u ? 65536u : (avail >= 2 * 32768u ? 32768u : 16384u);
 }
 
-enum { EV_STAGE = 0, EV_DRAIN = 1 };
+enum { EV_STAGE = 0, EV_DRAIN = 1, EV_STAGE_NEXT = 2 };   // STAGE_NEXT: ST_ROWS staging of tile i + 1 inside tile i
 // trace layout: tile t (< TR_TILES) owns TR_SLOTS stamps: [0, 3*MAX_OPS) issuer (per op: operands ready, first weight
 // chunk landed, all MMAs issued); [TR_ROWS, TR_ROWS + 3*MAX_EV) row thread 0 (per event: start, wait done, end)
 constexpr int TR_TILES = 6, TR_ROWS = 3 * MAX_OPS, TR_CHUNK = TR_ROWS + 3 * MAX_EV, TR_MAXCH = 40;
@@ -68,6 +68,7 @@ struct Args {
   int nops;
   unsigned char ev_type[MAX_EV], ev_op[MAX_EV];
   int nev;
+  int stage_first;                 // >= 0: the program stages with EV_STAGE_NEXT; this op's buffer is staged for a CTA's first tile
   const unsigned char* wstream;    // the tile's weight chunks in op / chunk order (same for every tile)
   long long R;                     // rows
   long long ntiles;
