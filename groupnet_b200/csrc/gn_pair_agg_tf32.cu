@@ -11,18 +11,21 @@
 // It replaces agg_in_tf32 + edge2node_pair + agg_out_tf32 (P and G: 2 x 2.2 GB written and read back per NBA step).
 //
 // One persistent CTA per SM; a tile = SC = floor(128 / N) whole scenes = SC * N <= 128 node rows; the work of a tile is
-// cut into U = 2T unit steps u = (t, half): 64 of the 128 hidden columns of agg_mlp[t].
-//   warps 0-15  "row" threads (row = TMEM lane, 16-column slice) drain P_u from tensor memory into a padded fp32 tile in
-//               shared memory, then regroup as "scene" threads (warp = scene, lane = 2 columns): the N rows of the scene
-//               sit in registers, every unordered pair (i <= j) is evaluated once and added to G_i and G_j, G overwrites
-//               P in place (a (scene, column pair) block of the tile belongs to exactly one thread); back as row threads
-//               they split G into tf32 hi / lo and write it to TENSOR MEMORY, where GEMM 2 reads it as its A operand
-//               (TS mode).  h is staged the same way once per tile and feeds all 2T GEMM 1s.
+// cut into U = 2T unit steps u = (t, half): 64 of the 128 hidden columns of agg_mlp[t].  Roles:
+//   warps 0-11  "scene" warps (warp = scene, lane = 2 columns): the N rows of the scene's P tile sit in registers, every
+//               unordered pair (i <= j) is evaluated once and added to G_i and G_j, G overwrites P in place (a (scene,
+//               column pair) block of the tile belongs to exactly one thread).  This is the FMA-pipe-bound phase.
+//   warps 12-15 "drain" warps, one per TMEM lane quarter (thread = tile row): WHILE the scene warps work on unit step u
+//               they split G_{u-1} into tf32 hi | lo and write it to TENSOR MEMORY, where GEMM 2 reads it as its A
+//               operand (TS mode), and they drain P_{u+1} (+ b0 / 2) from its accumulator into the other P tile
+//               (double-buffered by unit-step parity); one 512-thread barrier per unit step.
+//   all 16      stage h (hi | lo, once per tile, feeds all 2T GEMM 1s), build the symmetric weight table, and add the
+//               output partial of unit step u - 2 into 16 fp32 registers each (thread = (row, 16-column slice)).
 //   warp 16     weight producer: TMA bulk copies of the host-packed stream (one [64 x 64] hi | lo chunk per GEMM, in
 //               issue order) into a ring of 32 KB stages.
-//   warp 17     MMA issuer: GEMM 1 runs two unit steps ahead of the SIMT work (double-buffered accumulator); every
-//               GEMM 2 writes a fresh accumulator (24 MMAs) that the row threads add up in fp32 — the tensor core's own
-//               accumulation truncates, so long chains in one accumulator cost accuracy (see agg_out_tf32).
+//   warp 17     MMA issuer: GEMM 1 of step j + 2 goes out when accumulator j & 1 has been drained (p_free), GEMM 2 of
+//               step j when G_j is in tensor memory (g_ready); every GEMM 2 writes a fresh accumulator (24 MMAs) —
+//               the tensor core's own accumulation truncates, so long chains in one accumulator cost accuracy.
 // TMEM columns: h hi|lo 0..127 | P_u 128..255 (2 x 64) | G_u hi|lo 256..383 | agg partial 384..511 (2 x 64).
 //
 // Bound: SIMT issue of the relu-sum, 4 instructions per (unordered pair, column): N(N+1)/2 * 128 * T * 4 per scene;
@@ -39,13 +42,14 @@ namespace pat {
 constexpr int ROW_THREADS = 512, THREADS = ROW_THREADS + 64;
 constexpr int PLD = 68;                       // padded P / G row (floats): rows 4 banks apart, 128-bit row access conflict-free
 constexpr uint32_t STAGE_BYTES = 32768;       // one [64 x 64] chunk, hi then lo
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = 3;
+constexpr int SCENE_WARPS = 12;                // warps 0-11: relu-sum (warp = scene); warps 12-15: drain warps, one per TMEM lane quarter
 constexpr int MAXN = 11;
 constexpr uint32_t TM_A = 0, TM_P = 128, TM_G = 256, TM_AGG = 384;
 
 struct Bars {
   uint64_t full[NSTAGE], empty[NSTAGE];
-  uint64_t a_ready, g_ready, p_ready[2], agg_ready[2];
+  uint64_t a_ready, g_ready, p_free, p_ready[2], agg_ready[2];
   uint32_t tmem_slot, pad;
 };
 
@@ -153,7 +157,8 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
-    mbar_init(&bars->a_ready, ROW_THREADS); mbar_init(&bars->g_ready, ROW_THREADS);
+    mbar_init(&bars->a_ready, ROW_THREADS);
+    mbar_init(&bars->g_ready, ROW_THREADS - SCENE_WARPS * 32); mbar_init(&bars->p_free, ROW_THREADS - SCENE_WARPS * 32);
     for (int i = 0; i < 2; ++i) { mbar_init(&bars->p_ready[i], 1); mbar_init(&bars->agg_ready[i], 1); }
   }
   if (warp == 0) tmem_alloc(&bars->tmem_slot, 512);
@@ -193,7 +198,7 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
     }
   } else if (warp == ROW_THREADS / 32 + 1) {
     // ------------------------------------------------------------------ MMA issuer
-    int s = 0; uint32_t ph = 0, apar = 0, gpar = 0;
+    int s = 0; uint32_t ph = 0, apar = 0, gpar = 0, fpar = 0;
     auto gemm = [&](uint32_t d, uint32_t a_hi, uint64_t* done) {
       mbar_wait(&bars->full[s], ph);
       fence_after_thread_sync();
@@ -210,13 +215,27 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
       mbar_wait(&bars->a_ready, apar); apar ^= 1u;
       fence_after_thread_sync();
       gemm(tmem + TM_P, tmem + TM_A, &bars->p_ready[0]);
-      if (U > 1) gemm(tmem + TM_P + 64, tmem + TM_A, &bars->p_ready[1]);
-      for (int u = 0; u < U; ++u) {
-        mbar_wait(&bars->g_ready, gpar); gpar ^= 1u;
-        fence_after_thread_sync();
-        gemm(tmem + TM_AGG + (u & 1) * 64, tmem + TM_G, &bars->agg_ready[u & 1]);
-        if (u + 2 < U) gemm(tmem + TM_P + (u & 1) * 64, tmem + TM_A, &bars->p_ready[u & 1]);
+      gemm(tmem + TM_P + 64, tmem + TM_A, &bars->p_ready[1]);
+      // GEMM 1 of unit step j + 2 goes out as soon as the drain warps have read accumulator j & 1 (p_free), GEMM 2 of unit
+      // step j as soon as G_j is in tensor memory (g_ready); the drain warps signal in exactly this order
+      mbar_wait(&bars->p_free, fpar); fpar ^= 1u;
+      fence_after_thread_sync();
+      if (U > 2) gemm(tmem + TM_P, tmem + TM_A, &bars->p_ready[0]);
+      for (int st = 0; st < U; ++st) {
+        if (st >= 1) {
+          mbar_wait(&bars->g_ready, gpar); gpar ^= 1u;
+          fence_after_thread_sync();
+          gemm(tmem + TM_AGG + ((st - 1) & 1) * 64, tmem + TM_G, &bars->agg_ready[(st - 1) & 1]);
+        }
+        if (st + 1 < U) {
+          mbar_wait(&bars->p_free, fpar); fpar ^= 1u;
+          fence_after_thread_sync();
+          if (st + 3 < U) gemm(tmem + TM_P + ((st + 3) & 1) * 64, tmem + TM_A, &bars->p_ready[(st + 3) & 1]);
+        }
       }
+      mbar_wait(&bars->g_ready, gpar); gpar ^= 1u;
+      fence_after_thread_sync();
+      gemm(tmem + TM_AGG + ((U - 1) & 1) * 64, tmem + TM_G, &bars->agg_ready[(U - 1) & 1]);
     }
   } else {
     // ------------------------------------------------------------------ row / scene threads
@@ -310,7 +329,8 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
         for (int t = sl; t < T; t += 4) {
           const float* sy = sSym + (rsc * T + t) * NP4;
           float sum = 0.f;
-          for (int j = 0; j < N; ++j) sum += sy[sPidx[ri * N + j]];
+#pragma unroll 4
+          for (int j = 0; j < N; ++j) sum += sy[sPidx[ri * N + j]];      // unrolled: the loads of four terms in flight
           sS[row * 16 + t] = sum;
         }
       }
@@ -319,80 +339,102 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
       float acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-      for (int u = 0; u < U; ++u) {
+      // one output partial (GEMM 2 of unit step k, accumulator k & 1) -> this thread's 16 fp32 sums
+      auto add_partial = [&](int k) {
+        const int b = k & 1;
+        float v[16];
+        mbar_wait(&bars->agg_ready[b], (pha >> b) & 1u); pha ^= 1u << b;
+        fence_after_thread_sync();
+        tmem_ld16(tmem_row + TM_AGG + b * 64 + 16 * sl, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] += v[j];
+      };
+      // drain warps: P_u (+ b0 / 2) from its accumulator -> P tile u & 1 in shared memory; the accumulator is then free
+      auto r1 = [&](int u) {
         const int b = u & 1, t = u >> 1;
-        unsigned long long* tru = trp + 8 + 8 * (u < 14 ? u : 13);
-        if (tr) tru[0] = clock64();
-        // ---- R1: P_u (+ b0 / 2) -> shared memory
-        {
-          uint32_t r[16];
-          mbar_wait(&bars->p_ready[b], (php >> b) & 1u); php ^= 1u << b;
-          fence_after_thread_sync();
-          if (tr) tru[1] = clock64();
-          tf::tmem_ld16_nowait(tmem_row + TM_P + b * 64 + 16 * sl, r);
+        mbar_wait(&bars->p_ready[b], (php >> b) & 1u); php ^= 1u << b;
+        fence_after_thread_sync();
+        const float* bb = sB0 + t * 128 + b * 64;
+        float* dst = sP + b * (128 * PLD) + row * PLD;
+#pragma unroll
+        for (int c = 0; c < 4; c += 2) {
+          uint32_t ra[16], rb[16];
+          tf::tmem_ld16_nowait(tmem_row + TM_P + b * 64 + 16 * c, ra);
+          tf::tmem_ld16_nowait(tmem_row + TM_P + b * 64 + 16 * c + 16, rb);
           tmem_ld_wait();
-          const float* bb = sB0 + t * 128 + b * 64 + 16 * sl;
-          float* dst = sP + row * PLD + 16 * sl;
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            const float4 bv = *reinterpret_cast<const float4*>(bb + 4 * k4);
-            *reinterpret_cast<float4*>(dst + 4 * k4) =
-                make_float4(__uint_as_float(r[4 * k4]) + bv.x, __uint_as_float(r[4 * k4 + 1]) + bv.y,
-                            __uint_as_float(r[4 * k4 + 2]) + bv.z, __uint_as_float(r[4 * k4 + 3]) + bv.w);
+            const float4 bv = *reinterpret_cast<const float4*>(bb + 16 * c + 4 * k4);
+            *reinterpret_cast<float4*>(dst + 16 * c + 4 * k4) =
+                make_float4(__uint_as_float(ra[4 * k4]) + bv.x, __uint_as_float(ra[4 * k4 + 1]) + bv.y,
+                            __uint_as_float(ra[4 * k4 + 2]) + bv.z, __uint_as_float(ra[4 * k4 + 3]) + bv.w);
+          }
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bb + 16 * c + 16 + 4 * k4);
+            *reinterpret_cast<float4*>(dst + 16 * c + 16 + 4 * k4) =
+                make_float4(__uint_as_float(rb[4 * k4]) + bv.x, __uint_as_float(rb[4 * k4 + 1]) + bv.y,
+                            __uint_as_float(rb[4 * k4 + 2]) + bv.z, __uint_as_float(rb[4 * k4 + 3]) + bv.w);
           }
         }
-        if (tr) tru[2] = clock64();
-        row_bar();
-        if (tr) tru[3] = clock64();
-        // ---- scene threads: symmetric relu-sum, G overwrites P
-        for (int s = warp; s < ns; s += ROW_THREADS / 32)
-          relu_sum_n(N, sP + s * N * PLD, sSym + (s * T + t) * NP4, lane);
-        if (tr) tru[4] = clock64();
-        row_bar();
-        if (tr) tru[5] = clock64();
-        // ---- R2: the previous unit step's output partial -> registers (its GEMM 2 had a whole relu-sum to finish, and
-        //      it must be complete before G is overwritten); G_u -> tf32 hi | lo in tensor memory
-        {
-          uint32_t qv[16];
-          if (u > 0) {
-            mbar_wait(&bars->agg_ready[b ^ 1], (pha >> (b ^ 1)) & 1u); pha ^= 1u << (b ^ 1);
-            fence_after_thread_sync();
-            tf::tmem_ld16_nowait(tmem_row + TM_AGG + (b ^ 1) * 64 + 16 * sl, qv);
-          }
-          const float* src = sP + row * PLD + 16 * sl;
+        fence_before_thread_sync();
+        mbar_arrive(&bars->p_free);
+      };
+      // drain warps: G_u (P tile u & 1, overwritten by the relu-sum) -> tf32 hi | lo in tensor memory
+      auto r2 = [&](int u) {
+        const float* src = sP + (u & 1) * (128 * PLD) + row * PLD;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
           uint32_t hv[16], lv[16];
 #pragma unroll
           for (int k4 = 0; k4 < 4; ++k4) {
-            const float4 g = *reinterpret_cast<const float4*>(src + 4 * k4);
+            const float4 g = *reinterpret_cast<const float4*>(src + 16 * c + 4 * k4);
             tf::split_tf32(g.x, hv[4 * k4], lv[4 * k4]); tf::split_tf32(g.y, hv[4 * k4 + 1], lv[4 * k4 + 1]);
             tf::split_tf32(g.z, hv[4 * k4 + 2], lv[4 * k4 + 2]); tf::split_tf32(g.w, hv[4 * k4 + 3], lv[4 * k4 + 3]);
           }
-          tf::tmem_st16(tmem_row + TM_G + 16 * sl, hv);
-          tf::tmem_st16(tmem_row + TM_G + 64 + 16 * sl, lv);
-          if (u > 0) {
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(qv[j]);
-          }
-          tf::tmem_st_wait();
-          fence_before_thread_sync();
-          mbar_arrive(&bars->g_ready);
+          tf::tmem_st16(tmem_row + TM_G + 16 * c, hv);
+          tf::tmem_st16(tmem_row + TM_G + 64 + 16 * c, lv);
         }
-        if (tr) tru[6] = clock64();
+        tf::tmem_st_wait();
+        fence_before_thread_sync();
+        mbar_arrive(&bars->g_ready);
+      };
+      const bool is_drain = warp >= SCENE_WARPS;
+      const bool trd = a.trace != nullptr && blockIdx.x == 0 && tid == SCENE_WARPS * 32 && titer < TR_TILES;
+      if (is_drain) r1(0);
+      row_bar();
+      for (int u = 0; u < U; ++u) {
+        const int t = u >> 1;
+        unsigned long long* tru = trp + 8 + 8 * (u < 14 ? u : 13);
+        if (tr) tru[0] = clock64();
+        // every thread: the output partial of unit step u - 2 (its GEMM 2 had a whole unit step to finish; it also
+        // guarantees that G of step u - 1 may overwrite the operand GEMM 2 of step u - 2 read)
+        if (u >= 2) add_partial(u - 2);
+        if (tr) tru[1] = clock64();
+        if (!is_drain) {
+          // scene warps: symmetric relu-sum of unit step u, G overwrites P in place
+          for (int s = warp; s < ns; s += SCENE_WARPS)
+            relu_sum_n(N, sP + (u & 1) * (128 * PLD) + s * N * PLD, sSym + (s * T + t) * NP4, lane);
+          if (tr) tru[2] = clock64();
+        } else {
+          // drain warps, meanwhile: G of the previous unit step -> tensor memory, P of the next one -> shared memory
+          if (u >= 1) r2(u - 1);
+          if (trd) tru[4] = clock64();
+          if (u + 1 < U) r1(u + 1);
+          if (trd) tru[5] = clock64();
+        }
+        row_bar();
+        if (tr) tru[3] = clock64();
       }
-      // ---- epilogue: last partial, rank-T bias, store; the next tile's h rows are requested first
+      // ---- tail and epilogue: last two partials, rank-T bias, store; the next tile's h rows are requested first
       {
-        const int b = (U - 1) & 1;
-        float v[16];
         if (tr) trp[120] = clock64();
-        load_h(tile + gridDim.x, x);
-        mbar_wait(&bars->agg_ready[b], (pha >> b) & 1u); pha ^= 1u << b;
-        fence_after_thread_sync();
+        load_h(tile + gridDim.x, x);          // the next tile's h rows: their DRAM latency hides behind the epilogue
+        if (U >= 2) add_partial(U - 2);
+        if (is_drain) r2(U - 1);
         if (tr) trp[121] = clock64();
-        tmem_ld16(tmem_row + TM_AGG + b * 64 + 16 * sl, v);
+        add_partial(U - 1);
         if (live) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] += v[j];
           for (int t = 0; t < T; ++t) {
             const float st = sS[row * 16 + t];
             const float* b1 = sB1 + t * 64 + 16 * sl;
@@ -411,7 +453,7 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
         }
         if (tr) trp[123] = clock64();
         fence_before_thread_sync();
-        row_bar();                                        // S / s table are rewritten by the next tile
+        row_bar();                                        // S / s table / P tiles are rewritten by the next tile
         if (tr) trp[124] = clock64();
       }
     }
@@ -452,7 +494,7 @@ int launch_pair_agg_tf32(const float* h, const float* edge_feat, int B, int N, i
     if (only != nullptr && strcmp(only, "pair_agg_tf32") == 0) a.trace = g_trace_buffer;
   }
   uint32_t o = NSTAGE * STAGE_BYTES;
-  a.off_p = o; o += 128 * PLD * 4;
+  a.off_p = o; o += 2 * 128 * PLD * 4;             // P / G tile, double-buffered by unit-step parity
   a.off_sym = o; o += static_cast<uint32_t>(a.SC) * T * a.NP4 * 4;
   a.off_s = o; o += 128 * 16 * 4;
   a.off_b0 = o; o += static_cast<uint32_t>(T) * 128 * 4;

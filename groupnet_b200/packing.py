@@ -230,8 +230,8 @@ def tf_stream(mats, stage_bytes: int, tail=None) -> torch.Tensor:
 def pair_agg_tf32_stream(w0s, w1s) -> torch.Tensor:
     """Weight stream of the fused pairwise aggregation (csrc/gn_pair_agg_tf32.cu): one (64 x 64) hi | lo chunk per
     GEMM in issue order.  Unit step u = 2t + half uses A(u) = W0_t[64 half : 64 half + 64, :] (first Linear, 64 of its
-    128 hidden units) and B(u) = W1_t[:, 64 half : 64 half + 64] (second Linear, the matching K slice); GEMM 1 runs two
-    unit steps ahead: A(0), A(1), then B(u), A(u + 2) for u = 0..2T-1."""
+    128 hidden units) and B(u) = W1_t[:, 64 half : 64 half + 64] (second Linear, the matching K slice).  GEMM 1 runs
+    ahead of the drains: A(0), A(1), A(2), then per step st = 0..U-1: B(st - 1) (st >= 1), A(st + 3) (st + 3 < U); B(U - 1)."""
     t = len(w0s)
     u_n = 2 * t
 
@@ -241,12 +241,23 @@ def pair_agg_tf32_stream(w0s, w1s) -> torch.Tensor:
     def b_of(u):
         return w1s[u // 2][:, 64 * (u % 2):64 * (u % 2) + 64]
 
-    mats = [a_of(0), a_of(1)]
-    for u in range(u_n):
-        mats.append(b_of(u))
-        if u + 2 < u_n:
-            mats.append(a_of(u + 2))
-    return tf_stream([m.contiguous() for m in mats], 32768)
+    return tf_stream([m.contiguous() for _, m in pair_agg_tf32_order(u_n, a_of, b_of)], 32768)
+
+
+def pair_agg_tf32_order(u_n: int, a_of=None, b_of=None):
+    """[(("a" | "b", u), matrix or None)] in the issue order of pair_agg_tf32_kernel's MMA warp."""
+    a_of = a_of or (lambda u: None)
+    b_of = b_of or (lambda u: None)
+    out = [(("a", 0), a_of(0)), (("a", 1), a_of(1))]
+    if u_n > 2:
+        out.append((("a", 2), a_of(2)))
+    for st in range(u_n):
+        if st >= 1:
+            out.append((("b", st - 1), b_of(st - 1)))
+        if st + 3 < u_n:
+            out.append((("a", st + 3), a_of(st + 3)))
+    out.append((("b", u_n - 1), b_of(u_n - 1)))
+    return out
 
 
 def agg_out_cols(d: int) -> Tuple[int, int]:

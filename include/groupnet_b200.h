@@ -146,7 +146,7 @@ typedef struct gn_stage_weights {
   /* fused pairwise aggregation (csrc/gn_pair_agg_tf32.cu; pairwise layers with D == 64, else NULL): 32 KB chunks
    * (64 x 64, hi then lo) in MMA issue order.  With unit step u = 2t + half, A(u) = agg_mlp[t].layers.0.weight
    * rows [64 half, 64 half + 64) (64 x D) and B(u) = agg_mlp[t].layers.1.weight columns [64 half, 64 half + 64)
-   * (D x 64):  A(0), A(1), then for u = 0..2T-1: B(u), A(u+2) (the latter while u + 2 < 2T). */
+   * (D x 64):  A(0), A(1), A(2), then for st = 0..2T-1: B(st-1) (st >= 1), A(st+3) (st + 3 < 2T); finally B(2T-1). */
   const void* tf_pagg_w;
 } gn_stage_weights;
 

@@ -28,8 +28,9 @@ for it in range(1, TR_TILES):
     r = t[it].tolist()
     base = r[0]
     print(f"tile iter {it}: previous tile started {base - t[it - 1][0].item()} clk earlier")
-    print("  prologue: s table written %d | h staged %d | barrier %d | S done %d" % tuple(r[i] - base for i in (1, 2, 3, 4)))
+    print("  prologue: h staged %d | s table written %d | barrier %d | S done %d" % tuple(r[i] - base for i in (1, 2, 3, 4)))
     for u in range(12):
         s = r[8 + 8 * u: 8 + 8 * u + 7]
-        print(f"  u{u:2d}: start {s[0]-base:6d} | P ready +{s[1]-s[0]:5d} | R1 +{s[2]-s[1]:5d} | bar +{s[3]-s[2]:5d} | relu-sum +{s[4]-s[3]:5d} | bar +{s[5]-s[4]:5d} | R2 +{s[6]-s[5]:5d}")
-    print("  epilogue: start %d | last partial ready %d | end %d" % tuple(r[i] - base for i in (120, 121, 122)))
+        print(f"  u{u:2d}: start {s[0]-base:6d} | partial u-2 +{s[1]-s[0]:5d} | relu-sum +{s[2]-s[1]:5d} | barrier +{s[3]-s[2]:5d}"
+              f"   || drain warp: G(u-1) -> TMEM done at {s[4]-base if s[4] else 0:6d}, P(u+1) -> smem done at {s[5]-base if s[5] else 0:6d}")
+    print("  epilogue: start %d | G(U-1) written %d | bias done %d | stored %d | end %d" % tuple(r[i] - base for i in (120, 121, 122, 123, 124)))

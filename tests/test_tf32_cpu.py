@@ -90,14 +90,13 @@ def test_weight_streams_follow_the_documented_order():
     w = _decode(t["tf_post_w"], [(128, 128), (64, 128)], s32)
     assert close(w[0], pair.nmp_mlp_end.layers[0].weight) and close(w[1], pair.nmp_mlp_end.layers[1].weight)
     assert "tf_hagg_w" not in t
-    # fused pairwise aggregation: A(0), A(1), then B(u), A(u + 2) per unit step u = 2t + half (csrc/gn_pair_agg_tf32.cu)
+    # fused pairwise aggregation: chunks in the issue order of the kernel's MMA warp (csrc/gn_pair_agg_tf32.cu)
     w = _decode(t["tf_pagg_w"], [(64, 64)] * 24, s32)
-    order = [("a", 0), ("a", 1)]
-    for u in range(12):
-        order.append(("b", u))
-        if u + 2 < 12:
-            order.append(("a", u + 2))
-    assert len(order) == 24
+    order = [k for k, _ in packing.pair_agg_tf32_order(12)]
+    assert len(order) == 24 and sorted(order) == sorted([("a", u) for u in range(12)] + [("b", u) for u in range(12)])
+    assert order[:5] == [("a", 0), ("a", 1), ("a", 2), ("a", 3), ("b", 0)] and order[-3:] == [("b", 9), ("b", 10), ("b", 11)]
+    for u in range(12):                        # every GEMM 1 precedes the GEMM 2 of its unit step
+        assert order.index(("a", u)) < order.index(("b", u))
     for got, (kind, u) in zip(w, order):
         tt, half = divmod(u, 2)
         want = (agg[tt].layers[0].weight[64 * half:64 * half + 64, :] if kind == "a"
