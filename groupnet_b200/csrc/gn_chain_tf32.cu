@@ -200,6 +200,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
   fence_after_thread_sync();
   const uint32_t tmem = bars->tmem_slot;
   const uint32_t sbase = smem_u32(smem);
+  pdl_trigger();                         // the next kernel's CTAs may take over SMs as this grid's CTAs retire
 
   // The producer and issuer warps run their loops with ALL 32 lanes (warp-uniform control flow and addresses) and
   // predicate only the asynchronous instructions with elect.sync: tcgen05.mma / tcgen05.commit / cp.async.bulk take
@@ -288,6 +289,9 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     const int q = warp & 3, sl = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t tmem_row = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    // everything above (and the weight producer, which reads only packed weights) ran under the predecessor's tail;
+    // the activations it wrote are read from here on
+    pdl_wait();
     unsigned char* a0 = smem + a.off_a0;
     float* part = reinterpret_cast<float*>(smem + a.off_scr);    // [NSLICE][128][2] attention-logit partials
     float* dotp = part + NSLICE * 128 * 2;                       // [NSLICE][128]    DR_DOT partials
@@ -813,7 +817,8 @@ static int launch(Builder& b, long long R, long long ntiles, const unsigned char
   const int grid = ntiles < GN_SM_COUNT ? static_cast<int>(ntiles) : GN_SM_COUNT;
   {
     ProfScope ps__(name, st);
-    chain_tf32_kernel<<<grid, THREADS, smem, st>>>(a);
+    cudaError_t le = launch_pdl(chain_tf32_kernel, dim3(grid), dim3(THREADS), smem, st, a);
+    if (le != cudaSuccess) return static_cast<int>(le);
   }
   GN_LAUNCH_CHECK();
   return GN_OK;

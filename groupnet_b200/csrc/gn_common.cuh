@@ -74,6 +74,14 @@ __device__ __forceinline__ float gumbel_from_uniform(float u) {
   return -logf(1e-10f - logf(u + 1e-10f));
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its predecessor in the
+// stream is still draining its last wave; everything that reads the predecessor's output must come after pdl_wait()
+// (blocks until the prerequisite grids have completed and their writes are visible).  pdl_trigger() lets the NEXT
+// kernel's CTAs be scheduled as soon as SMs free up.  Static data (weights, constants) may be fetched before the wait:
+// the kernels' prologues (TMEM allocation, barrier init, constants, first weight chunks) overlap the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline size_t round_up_sz(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
@@ -87,6 +95,20 @@ struct ProfScope {
   ~ProfScope();
   const char* name_; cudaStream_t st_; void* rec_;
 };
+}  // namespace gn
+
+namespace gn {
+// <<<grid, block, smem, st>>> with the programmatic-stream-serialization attribute (see pdl_wait above)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 }  // namespace gn
 
 #define GN_LAUNCH_CHECK()                                  \

@@ -179,6 +179,7 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
   const uint32_t tmem = bars->tmem_slot;
   const uint32_t sbase = smem_u32(smem);
   const int ntiles = (a.B + SC - 1) / SC;
+  pdl_trigger();                         // programmatic dependent launch, see gn_common.cuh
 
   if (warp == ROW_THREADS / 32) {
     // ------------------------------------------------------------------ weight producer (warp-uniform, elect.sync)
@@ -246,6 +247,7 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
     uint32_t php = 0u, pha = 0u;             // phase bits of p_ready[b] / agg_ready[b] (bit b)
     const bool use_raw = a.off_raw != 0;
     unsigned char* sRaw = smem + a.off_raw;
+    pdl_wait();                          // h and edge_feat are the predecessors' outputs
     // edge_feat of a tile -> shared memory (cp.async, 16-byte chunks from the aligned-down tile base)
     auto prefetch_raw = [&](int tile) {
       if (use_raw && tile < ntiles) {
@@ -515,7 +517,8 @@ int launch_pair_agg_tf32(const float* h, const float* edge_feat, int B, int N, i
   const int grid = ntiles < GN_SM_COUNT ? ntiles : GN_SM_COUNT;
   {
     ProfScope ps__("pair_agg_tf32", st);
-    pair_agg_tf32_kernel<<<grid, THREADS, smem, st>>>(a);
+    cudaError_t le = launch_pdl(pair_agg_tf32_kernel, dim3(grid), dim3(THREADS), smem, st, a);
+    if (le != cudaSuccess) return static_cast<int>(le);
   }
   GN_LAUNCH_CHECK();
   return GN_OK;
