@@ -324,8 +324,7 @@ def run_train(args, rank, world, local):
     def step(from_host=False):
         if from_host:                       # e2e: the step's inputs come from pinned host memory, the loss goes back
             x.copy_(x_host, non_blocking=True)
-        for p in model.parameters():
-            p.grad = None
+        bucket.zero_grad()                  # one memset; .grad are views into the flat bucket (no pack / unpack copies)
         feat, _ = model(x)
         loss = (feat * wgt).sum() / b
         loss.backward()

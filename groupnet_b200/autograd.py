@@ -74,7 +74,20 @@ class StageFunction(torch.autograd.Function):
         t = cfg.T
         d_out = d_out.contiguous() if d_out is not None else torch.zeros(cfg.B, cfg.N, cfg.Dout, device=dev)
         d_dist = d_dist.contiguous() if d_dist is not None else None
-        grads = [torch.zeros_like(p, dtype=torch.float32) for p in params]
+        # wgrad kernels ACCUMULATE into their dW / db buffers.  A parameter whose .grad already exists as a dense fp32
+        # tensor (e.g. a view into ddp.FlatGradBucket's arena) takes its gradient in place and autograd gets None for
+        # it — no per-parameter allocation, memset, accumulation or bucket copy; all others get fresh zeroed buffers
+        # carved out of ONE allocation
+        inplace = [p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+                   and p.grad.device == p.device and p.grad.shape == p.shape for p in params]
+        fresh = torch.zeros(sum(p.numel() for p, ip in zip(params, inplace) if not ip), dtype=torch.float32, device=dev)
+        grads, off = [], 0
+        for p, ip in zip(params, inplace):
+            if ip:
+                grads.append(p.grad)
+            else:
+                grads.append(fresh[off:off + p.numel()].view(p.shape))
+                off += p.numel()
         it = iter(range(len(params)))
 
         def nxt():
@@ -112,5 +125,5 @@ class StageFunction(torch.autograd.Function):
                                   C.c_void_p(d_h.data_ptr()), C.c_void_p(bws.data_ptr()), bws.numel(),
                                   ops._stream_ptr(dev))
         _lib.check(rc, "gn_stage_bwd")
-        grads[4].copy_(torch.cat((dwpq[:32], dwpq[32:]), dim=1))                  # attention layers.0.weight
-        return (d_h, None, None, None, None, *grads)
+        grads[4].add_(torch.cat((dwpq[:32], dwpq[32:]), dim=1))                   # attention layers.0.weight
+        return (d_h, None, None, None, None, *[None if ip else g for g, ip in zip(grads, inplace)])

@@ -10,7 +10,16 @@
 #endif
 #endif
 
-#define GN_SM_COUNT 148
+// SMs of the current device (148 on a B200): persistent grids are sized from it at launch time
+namespace gn {
+static inline int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) return n;
+  return 148;
+}
+}  // namespace gn
+#define GN_SM_COUNT (gn::sm_count())
 #define GN_THREADS 256
 
 namespace gn {

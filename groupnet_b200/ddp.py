@@ -47,11 +47,39 @@ class FlatGradBucket:
                 p.grad.copy_(self.flat[off:off + n].view_as(p.grad))
             off += n
 
+    def zero_grad(self) -> None:
+        """Arena mode: ONE memset, and every parameter's .grad becomes a view into the flat bucket.  The layers'
+        backward then accumulates its weight gradients straight into the bucket (autograd.StageFunction) and
+        `allreduce_mean` reduces it in place: no per-parameter copies around the collective (the pack / unpack pair
+        was ~400 launches per step for one 3.1 MB all-reduce).  Never-used parameters hold zeros instead of None."""
+        dev = self.params[0].device
+        self._ensure(dev)
+        self.flat.zero_()
+        if not self._views_installed():
+            off = 0
+            for p in self.params:
+                n = p.numel()
+                p.grad = self.flat[off:off + n].view(p.shape)
+                off += n
+
+    def _views_installed(self) -> bool:
+        if self.flat is None:
+            return False
+        off = 0
+        for p in self.params:
+            g = p.grad
+            if g is None or g.data_ptr() != self.flat.data_ptr() + 4 * off or g.shape != p.shape:
+                return False
+            off += p.numel()
+        return True
+
     def allreduce_mean(self, group=None) -> None:
         """grads <- mean over ranks of grads (one collective)."""
         import torch.distributed as dist
-        flat = self.pack()
+        arena = self._views_installed()
+        flat = self.flat if arena else self.pack()
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
             flat.div_(dist.get_world_size(group))
-        self.unpack()
+        if not arena:
+            self.unpack()

@@ -541,6 +541,43 @@ def test_backward_accumulates_and_optimizer_step_repacks():
     assert not torch.equal(out1.detach(), out2)                       # packed weights were refreshed
 
 
+@pytest.mark.train
+def test_flat_grad_arena_takes_the_gradients_in_place():
+    """ddp.FlatGradBucket.zero_grad(): .grad are views into one flat buffer, the backward accumulates into them and
+    the all-reduce runs on the buffer itself; values equal the plain backward (wgrad uses float atomics: 1e-5)."""
+    from groupnet_b200.ddp import FlatGradBucket
+    x = torch.randn(6, 11, 64, device=DEV)
+    wgt = torch.randn(6, 11, 256, device=DEV)
+    noise = [torch.rand(6, 121, 6, device=DEV), torch.rand(6, 11, 10, device=DEV), torch.rand(6, 1, 10, device=DEV)]
+
+    def run(arena):
+        torch.manual_seed(77)
+        m = gb.MultiScaleInteraction(64, (5, 11)).to(DEV).train()
+        bucket = FlatGradBucket(m.parameters())
+        for _ in range(2):                                            # the second step reuses the installed views
+            if arena:
+                bucket.zero_grad()
+            else:
+                for p in m.parameters():
+                    p.grad = None
+            feat, _ = m(x, noise=noise)
+            (feat * wgt).sum().backward()
+            bucket.allreduce_mean()
+        return m, bucket
+
+    plain, _ = run(False)
+    arena, bucket = run(True)
+    assert bucket._views_installed()
+    off = 0
+    for (name, p), (_, q) in zip(plain.named_parameters(), arena.named_parameters()):
+        assert q.grad is not None and q.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off
+        off += q.numel()
+        if p.grad is None:
+            assert q.grad.abs().max().item() == 0.0, name              # never-used parameter: zeros in the arena
+        else:
+            assert_close(q.grad, p.grad, 1e-5, f"arena grad {name}", atol=1e-7)
+
+
 # ---- T6 / §8(f) rank 1: the whole PastEncoder against the reference's own PastEncoder --------
 @pytest.mark.parametrize("name", golden_names("pastenc"))
 @pytest.mark.parametrize("precision,tol", [("fp32", FP32_REL), ("tf32", FP32_REL), ("bf16", BF16_REL)])

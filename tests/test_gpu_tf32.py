@@ -116,3 +116,35 @@ def test_tf32_many_tiles_vs_fp32_path(kind, b):
     m.set_precision("tf32").set_rng("philox", seed=5)
     again = m(h) if kind == "pairwise" else m(h, corr)[:2]
     assert torch.equal(again[0], outs["tf32"][0]) and torch.equal(again[1], outs["tf32"][1])
+
+
+@pytest.mark.parametrize("precision,tol", [("tf32", FP32_REL), ("bf16", 2e-2)])
+@pytest.mark.parametrize("kind,b", [("pairwise", 300), ("hyper5", 1800), ("hyper11", 19200)])
+def test_tensor_core_paths_vs_oracle_at_more_tiles_than_sms(kind, b, precision, tol):
+    """Both tensor-core paths against the ORACLE (not the repo's own fp32 path) at NBA shape with more 128-row tiles
+    than the GPU has SMs, so every persistent CTA loops: pairwise 300 x 121 = 284 edge tiles; scale 5: 1,800 x 11 =
+    155 tiles of edge / node rows; scale 11: 19,200 node rows = 150 tiles (one all-ones hyperedge per scene)."""
+    torch.manual_seed(4000 + b)
+    n, d = 11, 64
+    if kind == "pairwise":
+        m = gb.MS_HGNN_oridinary(16, d, 64, 64, batch_norm=0, nmp_layers=1)
+        e, t, scale = n * n, 6, 0
+    else:
+        scale = 5 if kind == "hyper5" else 11
+        m = gb.MS_HGNN_hyper(d, d, 64, 64, batch_norm=0, nmp_layers=1, scale=scale)
+        e, t = (1 if scale == n else n), 10
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    gen = torch.Generator().manual_seed(b)
+    h = torch.randn(b, n, d, generator=gen)
+    noise = [torch.rand(b, e, t, generator=gen)]
+    m = m.to(DEV).set_precision(precision)
+    if kind == "pairwise":
+        ref_node, ref_fac = O.forward_pairwise(sd, h, noise)
+        node, fac = m(h.to(DEV), noise=noise)
+    else:
+        corr = O.feature_correlation(h)
+        ref_node, ref_fac, ref_h = O.forward_hyper(sd, h, corr, scale, noise)
+        node, fac, hm = m(h.to(DEV), corr.to(DEV), noise=noise)
+        assert torch.equal(hm.cpu(), ref_h)
+    assert_close(fac, ref_fac, tol, f"{kind} {precision} factors")
+    assert_close(node, ref_node, tol, f"{kind} {precision} node_feat")
