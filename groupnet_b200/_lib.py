@@ -40,6 +40,12 @@ EXPORTS = (
     "gn_profile_enable",
     "gn_profile_collect",
     "gn_profile_set_trace",
+    "gn_fish_alpha_im",
+    "gn_fish_bmm_t",
+    "gn_fish_mlp",
+    "gn_fish_hga_core",
+    "gn_fish_gat_edges",
+    "gn_fish_dynamic_graph",
 )
 
 
@@ -161,6 +167,19 @@ def load() -> C.CDLL:
         lib.gn_profile_enable.argtypes = [C.c_int]
         lib.gn_profile_collect.restype = C.c_int
         lib.gn_profile_collect.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
+        vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+        for name, args in (
+            ("gn_fish_alpha_im", [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, vp]),
+            ("gn_fish_bmm_t", [vp, i64, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+            ("gn_fish_mlp", [vp, i64, i64, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(i32), C.POINTER(i32),
+                             C.POINTER(f32), vp, i64, vp]),
+            ("gn_fish_hga_core", [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp]),
+            ("gn_fish_gat_edges", [vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp]),
+            ("gn_fish_dynamic_graph", [vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]),
+        ):
+            fn = getattr(lib, name)
+            fn.restype = C.c_int
+            fn.argtypes = args
         got = lib.gn_abi_version()
         if got != ABI_VERSION:
             raise GroupNetLibraryError(f"{LIB_PATH} has ABI version {got}, expected {ABI_VERSION}")

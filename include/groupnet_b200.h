@@ -29,7 +29,7 @@ extern "C" {
 #endif
 
 #define GN_ABI_VERSION 4     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams;
-                                 4: + tf_pagg_w (fused pairwise aggregation, csrc/gn_pair_agg_tf32.cu) */
+                                 4: + tf_pagg_w (fused pairwise aggregation, csrc/gn_pair_agg_tf32.cu), gn_fish_* entry points */
 
 #define GN_MAX_AGENTS 64      /* N <= 64: one 64-bit membership word per hyperedge */
 #define GN_MAX_SCALES 8
@@ -315,6 +315,46 @@ int gn_profile_collect(char* names, int names_len, float* total_ms, int* counts,
 /* Optional device buffer (>= 2*8*16 uint64) that the edge-chain kernel fills with clock64() phase stamps of
  * block 0's first tiles; NULL (default) disables tracing. */
 void gn_profile_set_trace(unsigned long long* device_buffer);
+
+/* ---- group-wise operators of the fish model (csrc/gn_fish.cu, fp32, eval-mode semantics) ----
+ * All tensors fp32, contiguous, batch-major; rel_rec / rel_send are (E, N) per scene, `rel_stride` floats apart
+ * (0: one matrix shared by every scene, as the reference's expand() does).  BatchNorm layers are folded into the
+ * Linears by the host (running statistics). */
+
+/* compute_alpha_im (model/encoder.py:261-303): alpha_ij (B,E), I_HG (B,N,M) -> out (B,N,M). */
+int gn_fish_alpha_im(const float* alpha_ij, const float* I_HG, const float* rel_rec, const float* rel_send,
+                     int64_t rel_stride, int32_t B, int32_t E, int32_t N, int32_t M, float* out, gn_stream_t stream);
+
+/* Per-scene C = A^T B with optional column normalisation of A (A / (column sum + 1e-8), MLPHGE :236-241) and optional
+ * per-row weights: A (R,Cn) [A_stride floats between scenes, 0 = shared], Bm (R,F), roww (batch,R) or NULL -> C (Cn,F).
+ * einsum('bnm,bnf->bmf') (model/encoder.py:241,183), ('bmn,bmf->bnf') (:177), ('behd,ben->bnhd') (:454). */
+int gn_fish_bmm_t(const float* A, int64_t A_stride, const float* Bm, const float* roww, int32_t batch, int32_t R,
+                  int32_t Cn, int32_t F, int32_t norm_cols, float* C, gn_stream_t stream);
+
+/* Row MLP: nlayers <= 3 Linears, Wt[l] = weight^T as [K][N] (BatchNorm folded in), bias[l] [N] or NULL, activation
+ * act[l] in {0 none, 1 LeakyReLU(slope[l]), 2 ELU} after every layer; x (R,K0) rows ldx apart -> out (R,N_last) rows
+ * ldo apart.  The Linear / BatchNorm1d / activation stacks of model/encoder.py:125-139, :244-248, :364-381. */
+int gn_fish_mlp(const float* x, int64_t ldx, int64_t R, int32_t K0, int32_t nlayers, const float* const* Wt,
+                const float* const* bias, const int32_t* N, const int32_t* act, const float* slope,
+                float* out, int64_t ldo, gn_stream_t stream);
+
+/* HyperEdgeAttention core (model/encoder.py:160-177): e_proj (B,M,Hd), v_proj (B,N,Hd), attention vector (2 Hd),
+ * I_HG (B,N,M), e_HG (B,M,F) -> v1 (B,N,F) = softmax over the member nodes of leaky(logit) / 100, times e_HG. */
+int gn_fish_hga_core(const float* e_proj, const float* v_proj, const float* attention_vector, const float* I_HG,
+                     const float* e_HG, int32_t B, int32_t N, int32_t M, int32_t Hd, int32_t F, float slope, float* v1,
+                     gn_stream_t stream);
+
+/* TemporalGATLayer edge stage (model/encoder.py:404-447): v_proj (B,N,H*D) -> edge_input (B,E,H,2D), alpha_ij (B,E,H). */
+int gn_fish_gat_edges(const float* v_proj, const float* rel_rec, const float* rel_send, int64_t rel_stride,
+                      const float* a_forward, const float* a_backward, int32_t B, int32_t E, int32_t N, int32_t H,
+                      int32_t D, float slope, float* edge_input, float* alpha_ij, gn_stream_t stream);
+
+/* build_dynamic_graph_and_hypergraph (utilities/utils.py:191-244): z_CG (B,E,Lc), z_HG (B,M,Lh) -> edges / hyperedges
+ * whose argmax type is 0 are zeroed in new_rel_rec / new_rel_send (B,E,N) and new_I_HG (B,N,M); types as int64. */
+int gn_fish_dynamic_graph(const float* z_CG, const float* z_HG, const float* rel_rec, const float* rel_send,
+                          int64_t rel_stride, const float* I_HG, int32_t B, int32_t E, int32_t N, int32_t M,
+                          int32_t Lc, int32_t Lh, float* new_rel_rec, float* new_rel_send, float* new_I_HG,
+                          int64_t* edge_types, int64_t* hyperedge_types, gn_stream_t stream);
 
 #ifdef __cplusplus
 }
