@@ -636,6 +636,158 @@ def cpu_baseline_crowd(budget_s=12.0):
 
 
 # ---------------------------------------------------------------------------
+def run_fishops(args, rank, world, local):
+    """the fish model's group-wise operators in the order HGNNModelFish.forward chains them
+    (model/HGNN_model_fish.py:96-150): TemporalGATLayer -> compute_alpha_im -> MLPHGE -> HyperEdgeAttention ->
+    build_dynamic_graph_and_hypergraph, at the fish scripts' dimensions (test_fish.py:326-339: n_hid 128, n_out 5, one
+    head, M = 5 hyperedges) with 11 agents (the dataset test_fish.py actually loads).  One step = that chain on
+    --scenes scenes per GPU (default 16,384; weak scaling, scenes are independent, no collective)."""
+    import torch.distributed as dist
+    import groupnet_b200 as gb
+    from groupnet_b200 import _lib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fish_schema import fish_inputs, randomize_bn
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    b = args.scenes if args.scenes != SCENES else 16384
+    n, m, n_hid, n_fc = 11, 5, 128, 5
+    f_v = n_hid + n_fc
+    torch.manual_seed(1234)
+    gat = gb.TemporalGATLayer(out_dim=n_hid, input_dim=10, hidden_dim=n_hid, num_heads=1, concat_heads=True)
+    hge = gb.MLPHGE(f_v, n_hid, n_fc * 3, 0.0)
+    hga = gb.HyperEdgeAttention(n_fc * 3, f_v, n_hid, n_fc * 5)
+    for i, mod in enumerate((gat, hge, hga)):
+        randomize_bn(mod, 4321 + i)
+    cpu_mods = [mod.eval() for mod in (gat, hge, hga)]
+    sds = [{k: v.detach().clone() for k, v in mod.state_dict().items()} for mod in cpu_mods]
+    gat, hge, hga = (mod.to(dev).eval() for mod in cpu_mods)
+    small = fish_inputs(64, n, m, f_v, n_hid, rank)
+    rep = (b + 63) // 64
+    host = {k: v.repeat(rep, *([1] * (v.dim() - 1)))[:b].contiguous() for k, v in small.items()}
+    host["v_self"] = torch.randn(b, n, n_hid, generator=torch.Generator().manual_seed(rank))
+    host["v_combined"] = torch.randn(b, n, f_v, generator=torch.Generator().manual_seed(100 + rank))
+    rel_rec, rel_send = small["rel_rec"][:1].to(dev), small["rel_send"][:1].to(dev)      # one (E, N) pair for every scene
+    e = rel_rec.shape[1]
+    pin = {k: host[k].pin_memory() for k in ("v_self", "v_combined", "I_HG", "z_CG", "z_HG")}
+    d = {k: v.to(dev) for k, v in pin.items()}
+
+    def step():
+        v_social, alpha_ij = gat(d["v_self"], rel_rec, rel_send)
+        alpha_im = gb.compute_alpha_im(alpha_ij, d["I_HG"], rel_rec, rel_send)
+        e_hg = hge(alpha_im, d["v_combined"])
+        e2 = hga(e_hg, d["v_combined"], d["I_HG"])
+        dyn = gb.build_dynamic_graph_and_hypergraph(d["z_CG"], d["z_HG"], rel_rec, rel_send, d["I_HG"])
+        return v_social, e2, dyn
+
+    def step_e2e():
+        for k in pin:
+            d[k].copy_(pin[k], non_blocking=True)
+        v_social, e2, dyn = step()
+        return v_social.cpu(), e2.cpu()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        with ClockSampler(local) as clocks:
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        step_e2e()
+        barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(e2e_steps):
+            step_e2e()
+        e1.record()
+        barrier()
+        e2e_ms = max_over_ranks(e0.elapsed_time(e1) / e2e_steps)
+        _lib.profile_enable(True)
+        step()
+        torch.cuda.synchronize(dev)
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        kernels = {k: {"ms_per_step": round(t, 3), "launches_per_step": c} for k, (t, c) in prof.items()}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        # dense-contraction FLOPs of the chain per scene (2 x MAC): GAT projection + edge MLP + node MLP, MLPHGE, attention MLPs
+        d_ = n_hid
+        fl_scene = 2 * (n * d_ * d_ + e * (2 * d_ * d_ + d_ * d_) + n * (d_ * d_ + d_ * d_) +
+                        m * (f_v * d_ + d_ * d_ + d_ * 15) + m * 15 * d_ + n * f_v * d_ + n * (15 * d_ + d_ * 25) + m * (25 * d_ + d_ * 25))
+        ach = fl_scene * b / (ms * 1e-3) / 1e12
+        pk = float(peaks.get("bf16_tflops", 1590.0))
+        h2d = sum(v.numel() * 4 for v in pin.values())
+        d2h = b * n * n_hid * 4 + b * m * 25 * 4
+        line = {
+            "metric": "fish_group_ops_scenes_per_sec", "value": world * b / (ms * 1e-3), "unit": "scenes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"fish_group_ops_B{b}_N{n}_M{m}_hid{n_hid}", "scenes_per_gpu": b, "agents": n,
+                       "hyperedges": m, "edges": e, "n_hid": n_hid,
+                       "chain": "TemporalGATLayer -> compute_alpha_im -> MLPHGE -> HyperEdgeAttention -> "
+                                "build_dynamic_graph_and_hypergraph (eval mode, BatchNorm folded)",
+                       "l2": "no flush: the edge-level intermediates (GBs) exceed the 126 MB L2"},
+            "clocks": clocks.summary(),
+            "e2e": {"value": world * b / (e2e_ms * 1e-3), "unit": "scenes/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "api": "the five drop-in calls; inputs from pinned host memory every step, v_social and e_HG_2 read back"},
+            "gpu_launches": sum(c for _, c in prof.values()) * args.steps,
+            "roofline": {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": pk, "unit": "TFLOP/s",
+                         "frac": round(ach / pk, 5), "traffic": None,
+                         "note": "whole-chain algorithmic FLOP rate; these kernels are fp32 FFMA (SIMT, nominal 74 TFLOP/s): "
+                                 "the tensor-core peak is the ceiling they do not use yet",
+                         "share_of_step": round(kernels[dom]["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()), 3)},
+            "kernels": kernels}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import fish_oracle as FO
+            torch.set_num_threads(os.cpu_count() or 1)
+            done, spent = 0, 0.0
+            cb = 256
+            with torch.no_grad():
+                while spent < 10.0:
+                    lo = (done % max(b - cb, 1))
+                    sl = {k: v[lo:lo + cb] for k, v in host.items()}
+                    t0 = time.perf_counter()
+                    v_s, a_ij = FO.temporal_gat(sds[0], sl["v_self"], sl["rel_rec"], sl["rel_send"], 1, n_hid)
+                    a_im = FO.compute_alpha_im(a_ij, sl["I_HG"], sl["rel_rec"], sl["rel_send"])
+                    e_h = FO.mlp_hge(sds[1], a_im, sl["v_combined"])
+                    FO.hyperedge_attention(sds[2], e_h, sl["v_combined"], sl["I_HG"])
+                    FO.build_dynamic_graph_and_hypergraph(sl["z_CG"], sl["z_HG"], sl["rel_rec"], sl["rel_send"], sl["I_HG"])
+                    spent += time.perf_counter() - t0
+                    done += cb
+            line["cpu_baseline"] = {"value": done / spent, "unit": "scenes/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{done} scenes in chunks of {cb} (oracle port of model/encoder.py, fp32 torch CPU, "
+                                              f"as-written algorithm), {spent:.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_decoder(args, rank, world, local):
     """the trajectory decoder (model/GroupNet_nba.py:441-505) at the NBA inference shape —
     11 agents x 20 samples per scene, 2 DecomposeBlocks, fp32 FFMA path.  One step = Decoder.forward on
@@ -788,7 +940,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", action="store_true",
                     help="measure only the headline --precision path (profiling runs: keeps the ncu launch list short)")
-    ap.add_argument("--workload", default="nba", choices=["nba", "crowd", "fish8", "fish20", "decoder"],
+    ap.add_argument("--workload", default="nba", choices=["nba", "crowd", "fish8", "fish20", "decoder", "fishops"],
                     help="nba: BASELINE configs[2] (the headline line); crowd: configs[3], N=64, h_dim 256, "
                          "scales {2,4,8,16}, 262,144 scenes sharded over the GPUs (strong scaling); fish8 / fish20: "
                          "configs[1], the MS_HGNN layers at the fish dataset shapes (8 agents, scales {3,5,8}; "
@@ -827,6 +979,8 @@ def main():
         return run_crowd(args, rank, world, local)
     if args.workload == "decoder":
         return run_decoder(args, rank, world, local)
+    if args.workload == "fishops":
+        return run_fishops(args, rank, world, local)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     # torchrun pins OMP_NUM_THREADS=1; the host side of the e2e pipeline (x slice of final_feature)
