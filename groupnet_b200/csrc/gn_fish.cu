@@ -147,7 +147,23 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_kernel(const MlpArgs a) {
 #pragma unroll
         for (int r = 0; r < MLP_ROWS; ++r) acc[r] = bv;
         const float* w = a.Wt[l] + n;
-        for (int k = 0; k < K; ++k) {
+        int k = 0;
+        for (; k + 8 <= K; k += 8) {                 // eight weight loads in flight (they come from L2 / L1)
+          float wv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + static_cast<size_t>(k + u) * N);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4* row = reinterpret_cast<const float4*>(in + (k + u) * MLP_ROWS);
+#pragma unroll
+            for (int q = 0; q < MLP_ROWS / 4; ++q) {
+              const float4 v = row[q];
+              acc[4 * q] = fmaf(v.x, wv[u], acc[4 * q]); acc[4 * q + 1] = fmaf(v.y, wv[u], acc[4 * q + 1]);
+              acc[4 * q + 2] = fmaf(v.z, wv[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(v.w, wv[u], acc[4 * q + 3]);
+            }
+          }
+        }
+        for (; k < K; ++k) {
           const float wv = __ldg(w + static_cast<size_t>(k) * N);
           const float4* row = reinterpret_cast<const float4*>(in + k * MLP_ROWS);
 #pragma unroll
