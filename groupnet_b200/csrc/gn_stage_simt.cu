@@ -856,6 +856,7 @@ node_post_kernel(const float* __restrict__ h, const float* __restrict__ aggin,
 // ===========================================================================
 // host side: one stage = a fixed sequence of launches on the caller's stream
 // ===========================================================================
+#include <cstdlib>
 #include "gn_stage.h"
 
 namespace gn {
@@ -950,9 +951,10 @@ static int launch_node2edge_hyper(const float* xprime, const float* pq, const fl
       size_t nodes = static_cast<size_t>(sc) * N, ed = static_cast<size_t>(sc) * E;
       return (2 * nodes * N2E_LD + ((ed * N + 3) & ~size_t(3)) + (eo ? nodes * (D + 4) : 0)) * 4;
     };
+    static const int cap_kb = getenv("GN_N2E_SMEM_KB") ? atoi(getenv("GN_N2E_SMEM_KB")) : 72;
     int SC = 128 / E;                                             // two 64-edge passes per tile: half the barriers per edge
     if (SC < 1) SC = 1;
-    while (SC > 1 && qbytes(SC) > 72 * 1024) --SC;
+    while (SC > 1 && qbytes(SC) > static_cast<size_t>(cap_kb) * 1024) --SC;
     const size_t smem = qbytes(SC);
     const int ntiles = (B + SC - 1) / SC;
     auto go = [&](auto kern) -> int {
@@ -1014,12 +1016,16 @@ static int launch_edge2node_hyper(const float* ef, const float* H, int B, int N,
   auto bytes = [&](int sc) -> size_t {
     return (static_cast<size_t>(sc) * E * (D + 4) + static_cast<size_t>(sc) * E * (N + 1)) * 4;
   };
+  // 24 KB tiles x 8 CTAs per SM: twice the loads in flight of the 48 KB x 4 configuration (0.260 -> 0.169 ms at the
+  // NBA shape, profiles/hbm_kernel_sweep.py); the knobs stay for that sweep
+  static const int cap_kb = getenv("GN_E2N_SMEM_KB") ? atoi(getenv("GN_E2N_SMEM_KB")) : 24;
+  static const int per_sm_env = getenv("GN_E2N_CTAS") ? atoi(getenv("GN_E2N_CTAS")) : 8;
   int SC = N2H_THREADS / N; if (SC < 1) SC = 1; if (SC > 16) SC = 16;
-  while (SC > 1 && bytes(SC) > 48 * 1024) --SC;
+  while (SC > 1 && bytes(SC) > static_cast<size_t>(cap_kb) * 1024) --SC;
   size_t smem = bytes(SC);
   GN_TRY(set_smem(edge2node_hyper_kernel, smem));
   const int ntiles = (B + SC - 1) / SC;
-  int grid = ntiles < GN_SM_COUNT * 4 ? ntiles : GN_SM_COUNT * 4;
+  int grid = ntiles < GN_SM_COUNT * per_sm_env ? ntiles : GN_SM_COUNT * per_sm_env;
   { ProfScope ps__("edge2node_hyper", st);
     edge2node_hyper_kernel<<<grid, N2H_THREADS, smem, st>>>(ef, H, B, N, E, D, hstride, SC, agg); }
   GN_LAUNCH_CHECK();
