@@ -103,24 +103,43 @@ def have_reference() -> bool:
     return os.path.exists(os.path.join(REFERENCE_DIR, "model", "MS_HGNN_batch.py"))
 
 
-def diagnose_oracle_mismatch(first, run_oracle, run_gpu, ref, got):
+def diagnose_oracle_mismatch(first, run_oracle, run_gpu, ref, got, tol=None):
     """a GPU-vs-oracle mismatch on a case that normally passes at ~3e-7.  Says which side moved:
     both sides are run again, the oracle is also evaluated in float64 (same restatement, double inputs / weights) and
     with one torch thread, and every result is measured against the float64 evaluation.  `run_oracle(dtype, threads)`
-    and `run_gpu()` return (node, factors); `ref` / `got` are the results that disagreed."""
+    and `run_gpu()` return (node, factors); `ref` / `got` are the results that disagreed.
+
+    Verdict: the float64 evaluation of the reference's math is the arbiter.  If the GPU result is inside the tolerance
+    of it while the float32 CPU evaluation that disagreed is NOT (the proxy moved, not the kernel), the comparison is
+    accepted with a warning that carries the whole diagnosis; in every other case the test fails with it."""
     import platform
+    import warnings
+    tol = FP32_REL if tol is None else tol
     r64 = run_oracle(torch.float64, None)
     r32 = run_oracle(torch.float32, None)
     r32_1 = run_oracle(torch.float32, 1)
     g2 = run_gpu()
+
+    def errs(x):
+        return rel_err(x[0], r64[0]), rel_err(x[1], r64[1])
+
     def e(x):
-        return f"node {rel_err(x[0], r64[0]):.3e} factors {rel_err(x[1], r64[1]):.3e}"
+        en, ef = errs(x)
+        return f"node {en:.3e} factors {ef:.3e}"
+
     d = (torch.as_tensor(ref[1], dtype=torch.float64) - r64[1]).abs().reshape(ref[1].shape[0], -1).max(dim=1).values
     bad = (d > 1e-5 * r64[1].abs().max()).nonzero().flatten().tolist()
-    raise AssertionError(
+    report = (
         f"{first} || vs the float64 oracle: oracle-1 (the failing reference) {e(ref)}; oracle-2 {e(r32)}; "
         f"oracle 1 thread {e(r32_1)}; GPU-1 {e(got)}; GPU-2 {e(g2)}; oracle rerun bit-identical "
         f"{torch.equal(r32[0], ref[0]) and torch.equal(r32[1], ref[1])}; GPU rerun bit-identical "
         f"{torch.equal(g2[0], got[0]) and torch.equal(g2[1], got[1])}; scenes where oracle-1 is off: "
         f"{bad[:8]}..{bad[-3:]} ({len(bad)}); torch threads {torch.get_num_threads()}, cpus {os.cpu_count()}, "
-        f"{platform.processor()} {torch.__config__.parallel_info().splitlines()[1:4]}") from None
+        f"{platform.processor()} {torch.__config__.parallel_info().splitlines()[1:4]}")
+    gpu_ok = max(errs(got)) <= tol and max(errs(g2)) <= tol
+    oracle_moved = max(errs(ref)) > tol
+    if gpu_ok and oracle_moved:
+        warnings.warn("GPU result accepted against the float64 evaluation of the oracle; the float32 CPU evaluation it was "
+                      "first compared with is the outlier (DESIGN.md 7a): " + report, RuntimeWarning)
+        return
+    raise AssertionError(report) from None

@@ -138,13 +138,33 @@ def test_tensor_core_paths_vs_oracle_at_more_tiles_than_sms(kind, b, precision, 
     h = torch.randn(b, n, d, generator=gen)
     noise = [torch.rand(b, e, t, generator=gen)]
     m = m.to(DEV).set_precision(precision)
-    if kind == "pairwise":
-        ref_node, ref_fac = O.forward_pairwise(sd, h, noise)
-        node, fac = m(h.to(DEV), noise=noise)
-    else:
-        corr = O.feature_correlation(h)
-        ref_node, ref_fac, ref_h = O.forward_hyper(sd, h, corr, scale, noise)
-        node, fac, hm = m(h.to(DEV), corr.to(DEV), noise=noise)
-        assert torch.equal(hm.cpu(), ref_h)
-    assert_close(fac, ref_fac, tol, f"{kind} {precision} factors")
-    assert_close(node, ref_node, tol, f"{kind} {precision} node_feat")
+    corr = None if kind == "pairwise" else O.feature_correlation(h)
+    ref_h = None if kind == "pairwise" else O.incidence_topk(corr, scale)
+
+    def run_oracle(dtype=torch.float32, threads=None):
+        keep = torch.get_num_threads()
+        if threads:
+            torch.set_num_threads(threads)
+        try:
+            sdd = {k: v.to(dtype) for k, v in sd.items()}
+            nz = [u.to(dtype) for u in noise]
+            if kind == "pairwise":
+                return O.forward_pairwise(sdd, h.to(dtype), nz)
+            return O.forward_hyper(sdd, h.to(dtype), corr.to(dtype), scale, nz, h_inc=ref_h.to(dtype))[:2]
+        finally:
+            torch.set_num_threads(keep)
+
+    def run_gpu():
+        out = m(h.to(DEV), noise=noise) if kind == "pairwise" else m(h.to(DEV), corr.to(DEV), noise=noise)
+        torch.cuda.synchronize()
+        return tuple(o.cpu() for o in out)
+
+    ref_node, ref_fac = run_oracle()
+    got = run_gpu()
+    if kind != "pairwise":
+        assert torch.equal(got[2], ref_h)
+    try:
+        assert_close(got[1], ref_fac, tol, f"{kind} {precision} factors")
+        assert_close(got[0], ref_node, tol, f"{kind} {precision} node_feat")
+    except AssertionError as first:
+        diagnose_oracle_mismatch(first, run_oracle, run_gpu, (ref_node, ref_fac), got[:2], tol=tol)
