@@ -179,6 +179,9 @@ __device__ __forceinline__ void dot_logits(const Op& op, const float* aux, const
 // drain variants the launchers use (Op::variant)
 enum { DV_TMEM = 0, DV_TMEM_RELU, DV_TMEM_RELU_RS, DV_TMEM_STORE, DV_STORE, DV_STORE_BM, DV_DOT_RELU, DV_COUNT };
 
+// PAIR: the fused pairwise node2edge staging (ST_PAIR programs) is compiled in; the ST_ROWS instance carries none of its
+// code or register state (one kernel for both cost the node chains ~10 %)
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tf32_kernel(const __grid_constant__ Args a) {
   using namespace tc;
@@ -209,76 +212,94 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
   if (warp == ROW_THREADS / 32) {
     // ------------------------------------------------------------------ weight producer
     int s = 0; uint32_t ph = 0;
+    int ci = 0;
+    bool tr = false;
+    unsigned long long* trp = a.trace;
+    auto stream_op = [&](const Op& op) {
+      const uint32_t bytes = static_cast<uint32_t>(op.N) * op.kc * 8;
+      const int nch = op.K / op.kc;
+      const unsigned char* src = a.wstream + op.w_off;
+      for (int c = 0; c < nch; ++c, ++ci) {
+        mbar_wait(&bars->empty[s], ph ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&bars->full[s], bytes);
+          bulk_g2s(sbase + a.off_ring + s * a.stage_bytes, src, bytes, &bars->full[s]);
+        }
+        __syncwarp();
+        if (tr && ci < TR_MAXCH) trp[4 * ci] = clock64();
+        src += bytes;
+        if (++s == a.nstage) { s = 0; ph ^= 1u; }
+      }
+    };
+    if (a.pro_op >= 0 && static_cast<long long>(blockIdx.x) < a.ntiles) stream_op(a.ops[a.pro_op]);
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
-      const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
-      unsigned long long* trp = a.trace + titer * TR_SLOTS + TR_CHUNK;
-      int ci = 0;
-      const unsigned char* src = a.wstream;
+      tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
+      trp = a.trace + titer * TR_SLOTS + TR_CHUNK;
+      ci = 0;
+      const bool last = tile + gridDim.x >= a.ntiles;
       for (int o = 0; o < a.nops; ++o) {
-        const Op& op = a.ops[o];
-        const uint32_t bytes = static_cast<uint32_t>(op.N) * op.kc * 8;
-        const int nch = op.K / op.kc;
-        for (int c = 0; c < nch; ++c, ++ci) {
-          mbar_wait(&bars->empty[s], ph ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(&bars->full[s], bytes);
-            bulk_g2s(sbase + a.off_ring + s * a.stage_bytes, src, bytes, &bars->full[s]);
-          }
-          __syncwarp();
-          if (tr && ci < TR_MAXCH) trp[4 * ci] = clock64();
-          src += bytes;
-          if (++s == a.nstage) { s = 0; ph ^= 1u; }
-        }
+        if (last && o == a.skip_last_op) continue;
+        stream_op(a.ops[o]);
       }
     }
   } else if (warp == ROW_THREADS / 32 + 1) {
     // ------------------------------------------------------------------ MMA issuer
     int s = 0; uint32_t ph = 0;
     uint32_t aw = 0, sg = 0;               // a_ready phases consumed, acc_ready phases produced
+    int ci = 0;
+    bool tr = false;
+    unsigned long long* trp = a.trace;
+    auto issue_op = [&](const Op& op, int o) {
+      // weights first (they landed long ago: the producer runs a stage ahead), so that the MMAs go out as soon as the
+      // row threads publish the operands
+      mbar_wait(&bars->full[s], ph);
+      for (int w = 0; w < op.wait_n; ++w) { mbar_wait(&bars->a_ready[aw & (NBAR - 1)], (aw / NBAR) & 1u); ++aw; }
+      fence_after_thread_sync();
+      if (tr) trp[3 * o] = clock64();
+      const int N = op.N, K = op.K, kc = op.kc, nch = K / kc;
+      const uint32_t d = tmem + op.acc_col;
+      const uint32_t half = static_cast<uint32_t>(N) * kc * 4;
+      for (int c = 0; c < nch; ++c, ++ci) {
+        if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 1] = clock64();
+        if (c > 0) { mbar_wait(&bars->full[s], ph); fence_after_thread_sync(); }
+        if (tr && c == 0) trp[3 * o + 1] = clock64();
+        if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 2] = clock64();
+        const uint32_t b_hi = sbase + a.off_ring + s * a.stage_bytes, b_lo = b_hi + half;
+        const bool acc_first = (c > 0) || (op.accumulate != 0);
+        if (elect_one()) {
+          if (op.a_src == A_SMEM) {
+            const uint32_t a_hi = sbase + a.off_a0 + op.a_buf * a.a0_buf_bytes + static_cast<uint32_t>(c * kc / 4) * 2048u;
+            tf::issue_x3_ss(d, a_hi, a_hi + a.a0_half_bytes, b_hi, b_lo, N, kc, acc_first);
+          } else {
+            const uint32_t ta = tmem + op.a_col + c * kc;
+            tf::issue_x3_ts(d, ta, ta + K, b_hi, b_lo, N, kc, acc_first);
+          }
+          mma_commit(&bars->empty[s]);
+        }
+        __syncwarp();
+        if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 3] = clock64();
+        if (++s == a.nstage) { s = 0; ph ^= 1u; }
+      }
+      if (op.signal) {
+        if (elect_one()) mma_commit(&bars->acc_ready[sg & (NBAR - 1)]);
+        __syncwarp();
+        ++sg;
+      }
+      if (tr) trp[3 * o + 2] = clock64();
+    };
+    // software-pipelined programs issue one op of a CTA's FIRST tile up front (pro_op) and skip the op that belongs to
+    // the tile after the LAST one (skip_last_op)
+    if (a.pro_op >= 0 && static_cast<long long>(blockIdx.x) < a.ntiles) issue_op(a.ops[a.pro_op], MAX_OPS - 1);
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
-      const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
-      unsigned long long* trp = a.trace + titer * TR_SLOTS;
-      int ci = 0;
+      tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
+      trp = a.trace + titer * TR_SLOTS;
+      ci = 0;
+      const bool last = tile + gridDim.x >= a.ntiles;
       for (int o = 0; o < a.nops; ++o) {
-        const Op& op = a.ops[o];
-        // weights first (they landed long ago: the producer runs a stage ahead), so that the MMAs go out as soon as the
-        // row threads publish the operands
-        mbar_wait(&bars->full[s], ph);
-        for (int w = 0; w < op.wait_n; ++w) { mbar_wait(&bars->a_ready[aw & (NBAR - 1)], (aw / NBAR) & 1u); ++aw; }
-        fence_after_thread_sync();
-        if (tr) trp[3 * o] = clock64();
-        const int N = op.N, K = op.K, kc = op.kc, nch = K / kc;
-        const uint32_t d = tmem + op.acc_col;
-        const uint32_t half = static_cast<uint32_t>(N) * kc * 4;
-        for (int c = 0; c < nch; ++c, ++ci) {
-          if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 1] = clock64();
-          if (c > 0) { mbar_wait(&bars->full[s], ph); fence_after_thread_sync(); }
-          if (tr && c == 0) trp[3 * o + 1] = clock64();
-          if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 2] = clock64();
-          const uint32_t b_hi = sbase + a.off_ring + s * a.stage_bytes, b_lo = b_hi + half;
-          const bool acc_first = (c > 0) || (op.accumulate != 0);
-          if (elect_one()) {
-            if (op.a_src == A_SMEM) {
-              const uint32_t a_hi = sbase + a.off_a0 + op.a_buf * a.a0_buf_bytes + static_cast<uint32_t>(c * kc / 4) * 2048u;
-              tf::issue_x3_ss(d, a_hi, a_hi + a.a0_half_bytes, b_hi, b_lo, N, kc, acc_first);
-            } else {
-              const uint32_t ta = tmem + op.a_col + c * kc;
-              tf::issue_x3_ts(d, ta, ta + K, b_hi, b_lo, N, kc, acc_first);
-            }
-            mma_commit(&bars->empty[s]);
-          }
-          __syncwarp();
-          if (tr && ci < TR_MAXCH) trp[TR_CHUNK + 4 * ci + 3] = clock64();
-          if (++s == a.nstage) { s = 0; ph ^= 1u; }
-        }
-        if (op.signal) {
-          if (elect_one()) mma_commit(&bars->acc_ready[sg & (NBAR - 1)]);
-          __syncwarp();
-          ++sg;
-        }
-        if (tr) trp[3 * o + 2] = clock64();
+        if (last && o == a.skip_last_op) continue;
+        issue_op(a.ops[o], o);
       }
     }
   } else {
@@ -297,7 +318,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     float* dotp = part + NSLICE * 128 * 2;                       // [NSLICE][128]    DR_DOT partials
     float* ybuf = dotp + NSLICE * 128;                           // [128][17]        Gumbel-softmax logits
     uint32_t ar = 0, sg = 0;                 // a_ready phases produced, acc_ready phases consumed
-    const bool pair = a.stage_mode == ST_PAIR;
+    constexpr bool pair = PAIR;
     float* np = reinterpret_cast<float*>(smem + a.off_node);     // pq rows of the tile's node block   [MAXN][NLD]
     float* ny = np + MAXN * NLD;                                 // Y = x' W^T rows                    [MAXN][YLD]
     // pair mode: R < 2^31 (checked by the launcher), so the scene / edge index math is 32-bit unsigned
@@ -367,6 +388,142 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       stage_rows(a.ops[a.stage_first], g0, g0 < a.R);
     }
 
+    // ---- fused node2edge of the pairwise layer, in two parts so that a software-pipelined program can run them for
+    // tile i + 1 inside the MMA waits of tile i.  Part A (shared memory only): attention over the (<= 2) members of edge
+    // (i,j), softmax over ALL N nodes (non-members enter with logit 0), self loops carry incidence 2 (:124,:135-137);
+    // slice sl sums 8 of the 32 attention hidden units, the partial logits meet in shared memory.  Its results — the two
+    // weights and the node-block rows of the edge — stay in registers for part B.
+    float s_wi = 0.f, s_wj = 0.f;
+    int s_li = 0, s_lj = 0;
+    auto pair_stage_a = [&](long long t, bool tr, unsigned long long* trp) {
+      const long long tsc = tps ? static_cast<long long>(static_cast<uint32_t>(t) / static_cast<uint32_t>(tps)) : 0;
+      const int tch = tps ? static_cast<int>(t - tsc * tps) : 0;
+      const long long g_row = tps ? tsc * a.E + tch * 128 + row : t * 128 + row;
+      const bool lv = g_row < a.R && (!tps || tch * 128 + row < a.E);
+      cp_async_wait<0>();
+      row_bar();
+      if (tr) trp[TR_STAGE - TR_ROWS + 0] = clock64();
+      const uint32_t b_lo = tps ? static_cast<uint32_t>(tsc) : (static_cast<uint32_t>(t) * 128u) / uE;
+      const int N = a.N;
+      const float* att = aux + a.att_off;                  // b0[32] | w1[32] | b1
+      int li = 0, lj = 0, i = 0, j = 0;
+      if (lv) {
+        const uint32_t b = static_cast<uint32_t>(g_row) / uE;
+        const uint32_t eidx = static_cast<uint32_t>(g_row) - b * uE;
+        i = static_cast<int>(eidx / uN); j = static_cast<int>(eidx) - i * N;
+        li = static_cast<int>(b - b_lo) * N + i; lj = static_cast<int>(b - b_lo) * N + j;
+        const float* pi = np + li * NLD;
+        const float* pj = np + lj * NLD;
+        float ai = 0.f, aj = 0.f;
+#pragma unroll
+        for (int k4 = 8 * sl; k4 < 8 * sl + 8; k4 += 4) {
+          const float4 ni = *reinterpret_cast<const float4*>(pi + k4);
+          const float4 nj = *reinterpret_cast<const float4*>(pj + k4);
+          const float4 qi = *reinterpret_cast<const float4*>(pi + 32 + k4);
+          const float4 qj = *reinterpret_cast<const float4*>(pj + 32 + k4);
+          const float4 b0 = *reinterpret_cast<const float4*>(att + k4);
+          const float4 w1 = *reinterpret_cast<const float4*>(att + 32 + k4);
+          const float p0 = qi.x + qj.x + b0.x, p1 = qi.y + qj.y + b0.y;
+          const float p2 = qi.z + qj.z + b0.z, p3 = qi.w + qj.w + b0.w;
+          ai = fmaf(fmaxf(ni.x + p0, 0.f), w1.x, ai); aj = fmaf(fmaxf(nj.x + p0, 0.f), w1.x, aj);
+          ai = fmaf(fmaxf(ni.y + p1, 0.f), w1.y, ai); aj = fmaf(fmaxf(nj.y + p1, 0.f), w1.y, aj);
+          ai = fmaf(fmaxf(ni.z + p2, 0.f), w1.z, ai); aj = fmaf(fmaxf(nj.z + p2, 0.f), w1.z, aj);
+          ai = fmaf(fmaxf(ni.w + p3, 0.f), w1.w, ai); aj = fmaf(fmaxf(nj.w + p3, 0.f), w1.w, aj);
+        }
+        *reinterpret_cast<float2*>(part + (sl * 128 + row) * 2) = make_float2(ai, aj);
+      }
+      if (tr) trp[TR_STAGE - TR_ROWS + 1] = clock64();
+      row_bar();
+      if (tr) trp[TR_STAGE - TR_ROWS + 2] = clock64();
+      float wi = 0.f, wj = 0.f;
+      if (lv) {
+        float ai = 0.f, aj = 0.f;
+#pragma unroll
+        for (int s4 = 0; s4 < NSLICE; ++s4) {          // fixed order: every slice gets the same sums
+          const float2 p = *reinterpret_cast<const float2*>(part + (s4 * 128 + row) * 2);
+          ai += p.x; aj += p.y;
+        }
+        const float b1v = att[64];
+        if (i == j) {
+          const float si = 2.f * (ai + b1v);
+          const float mx = (N > 1) ? fmaxf(si, 0.f) : si;
+          const float ei = expf(si - mx);
+          wi = ei / (ei + static_cast<float>(N - 1) * expf(-mx)) * 2.f;
+          wj = 0.f;
+        } else {
+          const float si = ai + b1v, sj = aj + b1v;
+          float mx = fmaxf(si, sj);
+          if (N > 2) mx = fmaxf(mx, 0.f);
+          const float ei = expf(si - mx), ej = expf(sj - mx);
+          const float den = ei + ej + static_cast<float>(N - 2) * expf(-mx);
+          wi = ei / den; wj = ej / den;
+        }
+      }
+      s_wi = wi; s_wj = wj; s_li = li; s_lj = lj;
+      if (tr) trp[TR_STAGE - TR_ROWS + 3] = clock64();
+    };
+    // Part B: hidden = relu(w_i Y_i + w_j Y_j + b), this slice's 32 of the 128 columns -> tensor memory (hi | lo) as the A
+    // operand of `op`; then the node block is refilled for the tile after `t`.
+    auto pair_stage_b = [&](const Op& op, long long t, bool tr, unsigned long long* trp) {
+      const float wi = s_wi, wj = s_wj;
+      const float* yi = ny + s_li * YLD + 32 * sl;
+      const float* yj = ny + s_lj * YLD + 32 * sl;
+      const float* yb = aux + a.yb_off + 32 * sl;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t hv[16], lv[16];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const float4 u = *reinterpret_cast<const float4*>(yi + 16 * half + 4 * q4);
+          const float4 v = *reinterpret_cast<const float4*>(yj + 16 * half + 4 * q4);
+          const float4 bb = *reinterpret_cast<const float4*>(yb + 16 * half + 4 * q4);
+          tf::split_tf32(fmaxf(fmaf(wi, u.x, fmaf(wj, v.x, bb.x)), 0.f), hv[4 * q4], lv[4 * q4]);
+          tf::split_tf32(fmaxf(fmaf(wi, u.y, fmaf(wj, v.y, bb.y)), 0.f), hv[4 * q4 + 1], lv[4 * q4 + 1]);
+          tf::split_tf32(fmaxf(fmaf(wi, u.z, fmaf(wj, v.z, bb.z)), 0.f), hv[4 * q4 + 2], lv[4 * q4 + 2]);
+          tf::split_tf32(fmaxf(fmaf(wi, u.w, fmaf(wj, v.w, bb.w)), 0.f), hv[4 * q4 + 3], lv[4 * q4 + 3]);
+        }
+        tf::tmem_st16(tmem_row + op.a_col + 32 * sl + 16 * half, hv);
+        tf::tmem_st16(tmem_row + op.a_col + 128 + 32 * sl + 16 * half, lv);
+      }
+      tf::tmem_st_wait();
+      if (tr) trp[TR_STAGE - TR_ROWS + 4] = clock64();
+      fence_before_thread_sync();
+      mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;     // the MMAs start while the node block is refilled
+      if (tr) trp[TR_STAGE - TR_ROWS + 5] = clock64();
+      row_bar();                          // every thread is done with the node block: refill it for the next tile
+      if (tr) trp[TR_STAGE - TR_ROWS + 6] = clock64();
+      prefetch_nodes(t + gridDim.x);
+      if (tr) trp[TR_STAGE - TR_ROWS + 7] = clock64();
+    };
+    // Gumbel noise of a tile's rows (slice sl: edge types [sl*tq, sl*tq + tq)): g = -log(eps - log(U + eps)) (:446-455)
+    // -> ybuf, computed while the row threads would otherwise wait for a GEMM
+    auto tile_noise = [&](long long g_row, bool lv) {
+      const int T = a.T, tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
+      constexpr int TQ = (GN_SMALL_OUT - 1 + NSLICE - 1) / NSLICE;
+      if (lv) {
+#pragma unroll
+        for (int jj = 0; jj < TQ; ++jj) {
+          const int t = t0 + jj;
+          if (jj < tq && t < T) {
+            float u;
+            if (a.noise_mode == GN_NOISE_GIVEN) {
+              u = __ldg(a.U + static_cast<size_t>(g_row) * T + t);
+            } else {
+              const unsigned long long el =
+                  (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(g_row)) * T + t;
+              u = Philox::uniform(el, static_cast<uint32_t>(a.stage_index), seed);
+            }
+            ybuf[row * 17 + t] = gumbel_from_uniform(u);
+          }
+        }
+      }
+    };
+    // software-pipelined pairwise program: the first tile is staged up front (its G2 is the issuer's pro_op)
+    if (a.pro_op >= 0 && static_cast<long long>(blockIdx.x) < a.ntiles) {
+      pair_stage_a(blockIdx.x, false, a.trace);
+      pair_stage_b(a.ops[a.pro_op], blockIdx.x, false, a.trace);
+    }
+
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
       const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && tid == 0;
@@ -376,10 +533,22 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       const long long grow = tps ? tscene * a.E + tchunk * 128 + row : tile * 128 + row;
       const bool live = grow < a.R && (!tps || tchunk * 128 + row < a.E);
       float carry = 0.f;
+      if (a.pro_op >= 0 && a.edge_feat != nullptr) tile_noise(grow, live);   // ybuf is free: the previous tile ended on a barrier
+      const bool has_next = tile + gridDim.x < a.ntiles;
 
       for (int e = 0; e < a.nev; ++e) {
         const Op& op = a.ops[a.ev_op[e]];
         if (tr) trp[3 * e] = clock64();
+        if (a.ev_type[e] == EV_PAIR_A_NEXT || a.ev_type[e] == EV_PAIR_B_NEXT) {
+          // the NEXT tile's fused node2edge, inside this tile's MMA waits (the op is skipped by the issuer on a CTA's
+          // last tile, and so is the arrival)
+          if (has_next) {
+            if (a.ev_type[e] == EV_PAIR_A_NEXT) pair_stage_a(tile + gridDim.x, tr, trp);
+            else pair_stage_b(op, tile + gridDim.x, tr, trp);
+          }
+          if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
+          continue;
+        }
         if (a.ev_type[e] == EV_STAGE_NEXT) {
           const long long nt = tile + gridDim.x;
           const long long gn = nt * 128 + row;
@@ -389,100 +558,8 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         }
         if (a.ev_type[e] == EV_STAGE) {
           if (pair) {
-            // fused node2edge of the pairwise layer: attention over the (<= 2) members of edge (i,j), softmax over ALL N
-            // nodes (non-members enter with logit 0), self loops carry incidence 2 (:124,:135-137).  Slice sl sums 8 of
-            // the 32 attention hidden units; the partial logits meet in shared memory.
-            cp_async_wait<0>();
-            row_bar();
-            if (tr) trp[TR_STAGE - TR_ROWS + 0] = clock64();
-            const uint32_t b_lo = tps ? static_cast<uint32_t>(tscene) : (static_cast<uint32_t>(tile) * 128u) / uE;
-            const int N = a.N;
-            const float* att = aux + a.att_off;                  // b0[32] | w1[32] | b1
-            int li = 0, lj = 0, i = 0, j = 0;
-            if (live) {
-              const uint32_t b = static_cast<uint32_t>(grow) / uE;
-              const uint32_t eidx = static_cast<uint32_t>(grow) - b * uE;
-              i = static_cast<int>(eidx / uN); j = static_cast<int>(eidx) - i * N;
-              li = static_cast<int>(b - b_lo) * N + i; lj = static_cast<int>(b - b_lo) * N + j;
-              const float* pi = np + li * NLD;
-              const float* pj = np + lj * NLD;
-              float ai = 0.f, aj = 0.f;
-#pragma unroll
-              for (int k4 = 8 * sl; k4 < 8 * sl + 8; k4 += 4) {
-                const float4 ni = *reinterpret_cast<const float4*>(pi + k4);
-                const float4 nj = *reinterpret_cast<const float4*>(pj + k4);
-                const float4 qi = *reinterpret_cast<const float4*>(pi + 32 + k4);
-                const float4 qj = *reinterpret_cast<const float4*>(pj + 32 + k4);
-                const float4 b0 = *reinterpret_cast<const float4*>(att + k4);
-                const float4 w1 = *reinterpret_cast<const float4*>(att + 32 + k4);
-                const float p0 = qi.x + qj.x + b0.x, p1 = qi.y + qj.y + b0.y;
-                const float p2 = qi.z + qj.z + b0.z, p3 = qi.w + qj.w + b0.w;
-                ai = fmaf(fmaxf(ni.x + p0, 0.f), w1.x, ai); aj = fmaf(fmaxf(nj.x + p0, 0.f), w1.x, aj);
-                ai = fmaf(fmaxf(ni.y + p1, 0.f), w1.y, ai); aj = fmaf(fmaxf(nj.y + p1, 0.f), w1.y, aj);
-                ai = fmaf(fmaxf(ni.z + p2, 0.f), w1.z, ai); aj = fmaf(fmaxf(nj.z + p2, 0.f), w1.z, aj);
-                ai = fmaf(fmaxf(ni.w + p3, 0.f), w1.w, ai); aj = fmaf(fmaxf(nj.w + p3, 0.f), w1.w, aj);
-              }
-              *reinterpret_cast<float2*>(part + (sl * 128 + row) * 2) = make_float2(ai, aj);
-            }
-            if (tr) trp[TR_STAGE - TR_ROWS + 1] = clock64();
-            row_bar();
-            if (tr) trp[TR_STAGE - TR_ROWS + 2] = clock64();
-            float wi = 0.f, wj = 0.f;
-            if (live) {
-              float ai = 0.f, aj = 0.f;
-#pragma unroll
-              for (int s4 = 0; s4 < NSLICE; ++s4) {          // fixed order: every slice gets the same sums
-                const float2 p = *reinterpret_cast<const float2*>(part + (s4 * 128 + row) * 2);
-                ai += p.x; aj += p.y;
-              }
-              const float b1v = att[64];
-              if (i == j) {
-                const float si = 2.f * (ai + b1v);
-                const float mx = (N > 1) ? fmaxf(si, 0.f) : si;
-                const float ei = expf(si - mx);
-                wi = ei / (ei + static_cast<float>(N - 1) * expf(-mx)) * 2.f;
-                wj = 0.f;
-              } else {
-                const float si = ai + b1v, sj = aj + b1v;
-                float mx = fmaxf(si, sj);
-                if (N > 2) mx = fmaxf(mx, 0.f);
-                const float ei = expf(si - mx), ej = expf(sj - mx);
-                const float den = ei + ej + static_cast<float>(N - 2) * expf(-mx);
-                wi = ei / den; wj = ej / den;
-              }
-            }
-            if (tr) trp[TR_STAGE - TR_ROWS + 3] = clock64();
-            // hidden = relu(w_i Y_i + w_j Y_j + b): this slice's 32 of the 128 columns -> tensor memory (hi | lo)
-            {
-              const float* yi = ny + li * YLD + 32 * sl;
-              const float* yj = ny + lj * YLD + 32 * sl;
-              const float* yb = aux + a.yb_off + 32 * sl;
-#pragma unroll 1
-              for (int half = 0; half < 2; ++half) {
-                uint32_t hv[16], lv[16];
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                  const float4 u = *reinterpret_cast<const float4*>(yi + 16 * half + 4 * q4);
-                  const float4 v = *reinterpret_cast<const float4*>(yj + 16 * half + 4 * q4);
-                  const float4 bb = *reinterpret_cast<const float4*>(yb + 16 * half + 4 * q4);
-                  tf::split_tf32(fmaxf(fmaf(wi, u.x, fmaf(wj, v.x, bb.x)), 0.f), hv[4 * q4], lv[4 * q4]);
-                  tf::split_tf32(fmaxf(fmaf(wi, u.y, fmaf(wj, v.y, bb.y)), 0.f), hv[4 * q4 + 1], lv[4 * q4 + 1]);
-                  tf::split_tf32(fmaxf(fmaf(wi, u.z, fmaf(wj, v.z, bb.z)), 0.f), hv[4 * q4 + 2], lv[4 * q4 + 2]);
-                  tf::split_tf32(fmaxf(fmaf(wi, u.w, fmaf(wj, v.w, bb.w)), 0.f), hv[4 * q4 + 3], lv[4 * q4 + 3]);
-                }
-                tf::tmem_st16(tmem_row + op.a_col + 32 * sl + 16 * half, hv);
-                tf::tmem_st16(tmem_row + op.a_col + 128 + 32 * sl + 16 * half, lv);
-              }
-              tf::tmem_st_wait();
-            }
-            if (tr) trp[TR_STAGE - TR_ROWS + 4] = clock64();
-            fence_before_thread_sync();
-            mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;     // the MMAs start while the node block is refilled
-            if (tr) trp[TR_STAGE - TR_ROWS + 5] = clock64();
-            row_bar();                          // every thread is done with the node block: refill it for the next tile
-            if (tr) trp[TR_STAGE - TR_ROWS + 6] = clock64();
-            prefetch_nodes(tile + gridDim.x);
-            if (tr) trp[TR_STAGE - TR_ROWS + 7] = clock64();
+            pair_stage_a(tile, tr, trp);
+            pair_stage_b(op, tile, tr, trp);
           } else {
             stage_rows(op, grow, live);
           }
@@ -494,29 +571,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
             for (int t = sl; t < a.rs_n; t += NSLICE) ybuf[row * 17 + t] = live ? __ldg(a.rs + grow * a.rs_ld + t) : 0.f;
             row_bar();
           }
-          if (e == 0 && a.edge_feat != nullptr) {
-            // Gumbel noise of this tile's rows (slice sl: edge types [sl*tq, sl*tq + tq)), computed now, while the first
-            // GEMM runs and the row threads would only wait: g = -log(eps - log(U + eps))  (:446-455) -> ybuf
-            const int T = a.T, tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
-            constexpr int TQ = (GN_SMALL_OUT - 1 + NSLICE - 1) / NSLICE;
-            if (live) {
-#pragma unroll
-              for (int jj = 0; jj < TQ; ++jj) {
-                const int t = t0 + jj;
-                if (jj < tq && t < T) {
-                  float u;
-                  if (a.noise_mode == GN_NOISE_GIVEN) {
-                    u = __ldg(a.U + static_cast<size_t>(grow) * T + t);
-                  } else {
-                    const unsigned long long el =
-                        (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(grow)) * T + t;
-                    u = Philox::uniform(el, static_cast<uint32_t>(a.stage_index), seed);
-                  }
-                  ybuf[row * 17 + t] = gumbel_from_uniform(u);
-                }
-              }
-            }
-          }
+          if (e == 0 && a.edge_feat != nullptr) tile_noise(grow, live);   // while the first GEMM runs
           continue;
         }
 
@@ -627,7 +682,7 @@ struct Builder {
   // pairwise and hyper forms, so both use the pairwise layout)
   Builder(int a0_K_, int nbuf_, bool node_block_, bool layout_node) : a0_K(a0_K_), nbuf(nbuf_), node_block(node_block_) {
     memset(&a, 0, sizeof(a));
-    a.stage_first = -1;
+    a.stage_first = -1; a.pro_op = -1; a.skip_last_op = -1;
     stage_bytes = ring_stage_bytes(a0_K, nbuf, layout_node);
   }
 
@@ -648,6 +703,7 @@ struct Builder {
     o.acc_col = static_cast<short>(acc_col); o.accumulate = static_cast<short>(accumulate);
     o.wait_n = static_cast<short>(wait_n); o.signal = static_cast<short>(signal);
     o.rs_idx = -1; o.bias_off = -1;
+    o.w_off = static_cast<int>(wbytes);
     wbytes += static_cast<size_t>(N) * K * 8;
     return o;
   }
@@ -725,10 +781,13 @@ static int validate_program(Args& a) {
   int arrivals = 0, drains = 0;
   for (int e = 0; e < a.nev; ++e) {
     const Op& op = a.ops[a.ev_op[e]];
-    if (a.ev_type[e] == EV_STAGE || a.ev_type[e] == EV_STAGE_NEXT) ++arrivals;
+    if (a.ev_type[e] == EV_PAIR_A_NEXT) continue;
+    if (a.ev_type[e] == EV_STAGE || a.ev_type[e] == EV_STAGE_NEXT || a.ev_type[e] == EV_PAIR_B_NEXT) ++arrivals;
     else { ++drains; if (!op.signal) return GN_E_SHAPE; arrivals += op.arrive; }
   }
   if (arrivals != waits || drains != signals) return GN_E_SHAPE;
+  if (a.pro_op >= 0 && (a.pro_op >= a.nops || a.skip_last_op != a.pro_op || a.stage_mode != ST_PAIR || a.stage_first >= 0 ||
+                        a.ops[a.pro_op].a_src != A_TMEM || a.ops[a.pro_op].wait_n != 1 || a.rs != nullptr)) return GN_E_SHAPE;
   if (a.stage_first >= 0) {
     // per-tile side work hangs off an EV_STAGE at e == 0; the staged buffer feeds the tile's FIRST op
     if (a.stage_first != 0 || a.ops[0].a_src != A_SMEM || a.ops[0].wait_n != 1 || a.stage_mode != ST_ROWS || a.tps != 0 ||
@@ -750,14 +809,16 @@ static int validate_program(Args& a) {
   for (int greedy_rows = 0; greedy_rows < 2; ++greedy_rows) {
     int io = 0, ie = 0;                       // issuer op index / row event index (over 2 tiles)
     int arr = a.stage_first >= 0 ? 1 : 0;     // produced arrivals (the first tile of such a program is staged up front)
-    int cons = 0, sig = 0, dr = 0;            // consumed arrivals, produced signals, consumed signals
+    int cons = 0, dr = 0;                     // consumed arrivals, consumed signals
+    int sig = a.pro_op >= 0 ? a.ops[a.pro_op].signal : 0;   // produced signals (a pro_op was staged and issued up front)
     int pend_wait = a.ops[0].wait_n;
     const int NO = 2 * a.nops, NE = 2 * a.nev;
     auto step_rows = [&]() -> bool {
       if (ie >= NE) return false;
       const int e = ie % a.nev;
       const Op& op = a.ops[a.ev_op[e]];
-      if (a.ev_type[e] == EV_STAGE || a.ev_type[e] == EV_STAGE_NEXT) { ++arr; ++ie; return true; }
+      if (a.ev_type[e] == EV_PAIR_A_NEXT) { ++ie; return true; }
+      if (a.ev_type[e] == EV_STAGE || a.ev_type[e] == EV_STAGE_NEXT || a.ev_type[e] == EV_PAIR_B_NEXT) { ++arr; ++ie; return true; }
       if (dr < sig) { ++dr; arr += op.arrive; ++ie; return true; }
       return false;
     };
@@ -812,12 +873,13 @@ static int launch(Builder& b, long long R, long long ntiles, const unsigned char
   int rc = validate_program(a);
   if (rc != GN_OK) return rc;
   if (!wstream || (reinterpret_cast<uintptr_t>(wstream) & 15)) return GN_E_NULL;
-  cudaError_t e = cudaFuncSetAttribute(chain_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  auto kern = a.stage_mode == ST_PAIR ? chain_tf32_kernel<true> : chain_tf32_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = ntiles < GN_SM_COUNT ? static_cast<int>(ntiles) : GN_SM_COUNT;
   {
     ProfScope ps__(name, st);
-    cudaError_t le = launch_pdl(chain_tf32_kernel, dim3(grid), dim3(THREADS), smem, st, a);
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(THREADS), smem, st, a);
     if (le != cudaSuccess) return static_cast<int>(le);
   }
   GN_LAUNCH_CHECK();
@@ -853,28 +915,53 @@ int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, con
   Builder b(pair ? 0 : 64, 1, pair, pair);
   if (b.stage_bytes != 65536u) return GN_E_SHAPE;          // the stream is packed for 64 KB stages in both forms
   Args& a = b.a;
-  int first = 0;
+  Op* g3d_p = nullptr;
   if (!pair) {
     Op& g1 = b.add(A_SMEM, 0, 64, 128, 0, 0, 1, 1);
     b.drain_tmem(g1, 128, 1, w->init_b0, 128, 1);
-    first = 1;
+    Op& g2 = b.add(A_TMEM, 128, 128, 64, 384, 0, 1, 1);
+    b.drain_tmem(g2, 64, 0, w->init_b1, 0, 1);
+    Op& g3f = b.add(A_TMEM, 0, 64, 128, 128, 0, 1, 1);
+    g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; b.set_bias(g3f, w->df_b0 + 128, 128); g3f.arrive = 0;
+    Op& g3d = b.add(A_TMEM, 0, 64, 128, 256, 0, 0, 1);
+    // the distribution head (128 -> T) and the Gumbel softmax run inside the drain of G3d (DR_DOTG); the slices' partial
+    // logits meet in columns 0..63: A2 is dead once G3d has completed (which that drain waits for), whereas the factor
+    // accumulator next to it may still be read by a slower slice's DR_DOT drain
+    g3d.drain = DR_DOTG; g3d.dn = 128; g3d.relu = 1; b.set_bias(g3d, w->df_b0, 128); g3d.dst_col = 0; g3d.arrive = 0;
+    g3d_p = &g3d;
+    b.ev(EV_STAGE, 0);
+    for (int o = 0; o < 4; ++o) b.ev(EV_DRAIN, o);
   } else {
+    // Software-pipelined pairwise form.  The row threads are the bottleneck of this chain (SIMT ~14 K clk per tile
+    // against ~7 K of tensor time), so the fused node2edge of tile i + 1 runs inside the MMA waits of tile i:
+    //   issuer per tile:  G3f(i)              G3d(i)              G2(i+1)
+    //   row threads:      D2(i)  stage A(i+1) DOTf(i) stage B(i+1) DOTG(i)      (stage A: attention, B: hidden -> TMEM)
+    // G2 of a CTA's first tile is issued up front (pro_op) and skipped after its last tile.  The hidden operand of G2
+    // owns columns 0..255 (free again once G2 has completed, which D2 waits for); everything else lives in 256..511:
+    // acc2 384 -> A2 hi in place 384 | lo 448 -> ONE accumulator 256..383 for G3f then G3d -> logit exchange 448.
     a.yb_off = b.aux(w->init_b0, 128);
     a.att_off = b.aux(w->att_b0, 32);
     b.aux(w->att_w1, 32);
     b.aux(w->att_b1, 1);
+    const size_t g2_bytes = 64 * 128 * 8;
+    Op& g3f = b.add(A_TMEM, 384, 64, 128, 256, 0, 1, 1);
+    g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; b.set_bias(g3f, w->df_b0 + 128, 128);
+    g3f.arrive = 1;                                          // the accumulator is free for G3d
+    Op& g3d = b.add(A_TMEM, 384, 64, 128, 256, 0, 1, 1);
+    g3d.drain = DR_DOTG; g3d.dn = 128; g3d.relu = 1; b.set_bias(g3d, w->df_b0, 128); g3d.dst_col = 448; g3d.arrive = 0;
+    g3d_p = &g3d;
+    Op& g2 = b.add(A_TMEM, 0, 128, 64, 384, 0, 1, 1);
+    b.drain_tmem(g2, 64, 0, w->init_b1, 384, 1);
+    // stream order is G2 | G3f | G3d (packing.py): the ops were added in issue order, fix their offsets
+    g2.w_off = 0; g3f.w_off = static_cast<int>(g2_bytes); g3d.w_off = static_cast<int>(g2_bytes + 128 * 64 * 8);
+    a.pro_op = 2; a.skip_last_op = 2;
+    b.ev(EV_DRAIN, 2);            // D2(i): acc2 -> A2, releases G3f(i)
+    b.ev(EV_PAIR_A_NEXT, 2);
+    b.ev(EV_DRAIN, 0);            // DOTf(i), releases G3d(i)
+    b.ev(EV_PAIR_B_NEXT, 2);      // hidden of tile i + 1 -> columns 0..255, releases G2(i+1)
+    b.ev(EV_DRAIN, 1);            // DOTG(i)
   }
-  Op& g2 = b.add(A_TMEM, 128, 128, 64, 384, 0, 1, 1);
-  b.drain_tmem(g2, 64, 0, w->init_b1, 0, 1);
-  Op& g3f = b.add(A_TMEM, 0, 64, 128, 128, 0, 1, 1);
-  g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; b.set_bias(g3f, w->df_b0 + 128, 128); g3f.arrive = 0;
-  Op& g3d = b.add(A_TMEM, 0, 64, 128, 256, 0, 0, 1);
-  // the distribution head (128 -> T) and the Gumbel softmax run inside the drain of G3d (DR_DOTG); the slices' partial
-  // logits meet in columns 0..63: A2 is dead once G3d has completed (which that drain waits for), whereas the factor
-  // accumulator next to it may still be read by a slower slice's DR_DOT drain
-  g3d.drain = DR_DOTG; g3d.dn = 128; g3d.relu = 1; b.set_bias(g3d, w->df_b0, 128); g3d.dst_col = 0; g3d.arrive = 0;
-  b.ev(EV_STAGE, 0);
-  for (int o = 0; o < 3 + first; ++o) b.ev(EV_DRAIN, o);
+  Op& g3d = *g3d_p;
   a.stage_mode = pair ? ST_PAIR : ST_ROWS;
   a.src0 = edges; a.ld0 = 64; a.k_src0 = 64; a.src1 = nullptr; a.ld1 = 0; a.a_div = 0.f;
   a.ypre = ypre; a.pq = pq;

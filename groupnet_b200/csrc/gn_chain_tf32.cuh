@@ -26,7 +26,7 @@ inline uint32_t ring_stage_bytes(int a0_K, int nbuf, bool node_block) {
   return avail >= 2 * 65536u ? 65536u : (avail >= 2 * 32768u ? 32768u : 16384u);
 }
 
-enum { EV_STAGE = 0, EV_DRAIN = 1, EV_STAGE_NEXT = 2 };   // STAGE_NEXT: ST_ROWS staging of tile i + 1 inside tile i
+enum { EV_STAGE = 0, EV_DRAIN = 1, EV_STAGE_NEXT = 2, EV_PAIR_A_NEXT = 3, EV_PAIR_B_NEXT = 4 };   // STAGE_NEXT: ST_ROWS staging of tile i + 1 inside tile i
 // trace layout: tile t (< TR_TILES) owns TR_SLOTS stamps: [0, 3*MAX_OPS) issuer (per op: operands ready, first weight
 // chunk landed, all MMAs issued); [TR_ROWS, TR_ROWS + 3*MAX_EV) row thread 0 (per event: start, wait done, end)
 constexpr int TR_TILES = 6, TR_ROWS = 3 * MAX_OPS, TR_CHUNK = TR_ROWS + 3 * MAX_EV, TR_MAXCH = 40;
@@ -58,6 +58,7 @@ struct Op {
   short nsum, sum_stride;  // drain value = sum of nsum accumulators, sum_stride columns apart (0/1 = just acc_col)
   short bias_off;     // >= 0: bias[dn] at this float offset of the smem constants
   short variant;      // compiled drain specialisation (set by validate_program)
+  int w_off;          // byte offset of the op's first weight chunk in the stream
   const float* bias;  // [dn] or null
   float* out;         // DR_STORE / DR_TMEM_STORE: row-major fp32, row stride ldo
   long long ldo;
@@ -69,6 +70,8 @@ struct Args {
   unsigned char ev_type[MAX_EV], ev_op[MAX_EV];
   int nev;
   int stage_first;                 // >= 0: the program stages with EV_STAGE_NEXT; this op's buffer is staged for a CTA's first tile
+  int pro_op, skip_last_op;        // software-pipelined pairwise edge chain: op issued once before a CTA's first tile
+                                   // (its operand staged by pair_stage_a/b there) and skipped on its last tile; -1: none
   const unsigned char* wstream;    // the tile's weight chunks in op / chunk order (same for every tile)
   long long R;                     // rows
   long long ntiles;
