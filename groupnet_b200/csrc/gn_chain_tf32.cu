@@ -231,16 +231,16 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
       }
     };
-    if (a.pro_op >= 0 && static_cast<long long>(blockIdx.x) < a.ntiles) stream_op(a.ops[a.pro_op]);
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
       tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
       trp = a.trace + titer * TR_SLOTS + TR_CHUNK;
       ci = 0;
       const bool last = tile + gridDim.x >= a.ntiles;
-      for (int o = 0; o < a.nops; ++o) {
+      // o == -1: the pro_op of a CTA's first tile (one call site keeps the lambda inlined and its state in registers)
+      for (int o = (titer == 0 && a.pro_op >= 0) ? -1 : 0; o < a.nops; ++o) {
         if (last && o == a.skip_last_op) continue;
-        stream_op(a.ops[o]);
+        stream_op(a.ops[o < 0 ? a.pro_op : o]);
       }
     }
   } else if (warp == ROW_THREADS / 32 + 1) {
@@ -290,16 +290,15 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     };
     // software-pipelined programs issue one op of a CTA's FIRST tile up front (pro_op) and skip the op that belongs to
     // the tile after the LAST one (skip_last_op)
-    if (a.pro_op >= 0 && static_cast<long long>(blockIdx.x) < a.ntiles) issue_op(a.ops[a.pro_op], MAX_OPS - 1);
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
       tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
       trp = a.trace + titer * TR_SLOTS;
       ci = 0;
       const bool last = tile + gridDim.x >= a.ntiles;
-      for (int o = 0; o < a.nops; ++o) {
+      for (int o = (titer == 0 && a.pro_op >= 0) ? -1 : 0; o < a.nops; ++o) {     // o == -1: the pro_op
         if (last && o == a.skip_last_op) continue;
-        issue_op(a.ops[o], o);
+        issue_op(a.ops[o < 0 ? a.pro_op : o], o < 0 ? MAX_OPS - 1 : o);
       }
     }
   } else {
