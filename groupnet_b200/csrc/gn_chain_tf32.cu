@@ -217,7 +217,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     unsigned long long* trp = a.trace;
     auto stream_op = [&](const Op& op) {
       const uint32_t bytes = static_cast<uint32_t>(op.N) * op.kc * 8;
-      const int nch = op.kc ? op.K / op.kc : 0;             // K == 0: a virtual op (a second drain of an accumulator)
+      const int nch = op.K / op.kc;
       const unsigned char* src = a.wstream + op.w_off;
       for (int c = 0; c < nch; ++c, ++ci) {
         mbar_wait(&bars->empty[s], ph ^ 1u);
@@ -253,11 +253,11 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     auto issue_op = [&](const Op& op, int o) {
       // weights first (they landed long ago: the producer runs a stage ahead), so that the MMAs go out as soon as the
       // row threads publish the operands
-      if (op.K > 0) mbar_wait(&bars->full[s], ph);
+      mbar_wait(&bars->full[s], ph);
       for (int w = 0; w < op.wait_n; ++w) { mbar_wait(&bars->a_ready[aw & (NBAR - 1)], (aw / NBAR) & 1u); ++aw; }
       fence_after_thread_sync();
       if (tr) trp[3 * o] = clock64();
-      const int N = op.N, K = op.K, kc = op.kc, nch = kc ? K / kc : 0;   // K == 0: virtual op, only its commit below
+      const int N = op.N, K = op.K, kc = op.kc, nch = K / kc;
       const uint32_t d = tmem + op.acc_col;
       const uint32_t half = static_cast<uint32_t>(N) * kc * 4;
       for (int c = 0; c < nch; ++c, ++ci) {
@@ -755,16 +755,11 @@ static int validate_program(Args& a) {
   int waits = 0, signals = 0;
   for (int o = 0; o < a.nops; ++o) {
     Op& op = a.ops[o];
-    const bool virt = op.K == 0 && op.kc == 0;            // no MMA: a further drain of the accumulator the previous op filled
-    if (virt) {
-      if (o == 0 || !op.signal || op.wait_n != 0 || op.drain == DR_NONE) return GN_E_SHAPE;
-    } else if (op.N < 16 || op.N > 256 || (op.N & 15) || op.K < 8 || (op.K & 7) || op.kc < 8 || (op.kc & 7) || op.K % op.kc) {
-      return GN_E_SHAPE;
-    }
+    if (op.N < 16 || op.N > 256 || (op.N & 15) || op.K < 8 || (op.K & 7) || op.kc < 8 || (op.kc & 7) || op.K % op.kc) return GN_E_SHAPE;
     if (static_cast<uint32_t>(op.N) * op.kc * 8 > a.stage_bytes) return GN_E_SHAPE;
     if (op.acc_col < 0 || op.acc_col + op.N > 512) return GN_E_SHAPE;
-    if (!virt && op.a_src == A_TMEM && (op.a_col < 0 || op.a_col + 2 * op.K > 512)) return GN_E_SHAPE;
-    if (!virt && op.a_src == A_SMEM && (static_cast<uint32_t>(op.K) * 128 * 4 > a.a0_half_bytes || op.K > 128)) return GN_E_SHAPE;
+    if (op.a_src == A_TMEM && (op.a_col < 0 || op.a_col + 2 * op.K > 512)) return GN_E_SHAPE;
+    if (op.a_src == A_SMEM && (static_cast<uint32_t>(op.K) * 128 * 4 > a.a0_half_bytes || op.K > 128)) return GN_E_SHAPE;
     if (op.signal) {
       if (op.drain == DR_DOTG) { if (op.dn != 128 || op.dst_col < 0 || op.dst_col + 16 * NSLICE > 512 || a.w4_off < 0) return GN_E_SHAPE; }
       else if (op.drain != DR_NONE && ((op.dn != 64 && op.dn != 128) || op.dn > op.N)) return GN_E_SHAPE;   // NSLICE x 16 / 32
@@ -1090,7 +1085,7 @@ int launch_agg_out_tf32(const float* G, const float* S, long long R, int D, int 
 // TMEM columns: acc_hid 0 | A_hid 128,256 | acc_ef 384
 bool hyper_agg_tf32_fits(int D, int T) {
   // biases (T x 128) and the rank-T output bias (T x D) must fit the smem constants
-  return (D == 64 || D == 128) && T >= 1 && 4 * T <= MAX_OPS && 4 * T + 1 <= MAX_EV && T * 128 + T * D <= AUX_FLOATS;
+  return (D == 64 || D == 128) && T >= 1 && 2 * T <= MAX_OPS && T * 128 + T * D <= AUX_FLOATS;
 }
 
 int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, int D, int T,
@@ -1100,75 +1095,20 @@ int launch_hyper_agg_tf32(const float* eo, const float* edge_feat, long long R, 
   Builder b(D, 1, false, false);
   Args& a = b.a;
   b.ev(EV_STAGE, 0);
-  if (D == 64) b.stage_bytes = 32768;      // 32 KB chunks (G1 in two K halves): a 4-deep ring keeps three GEMMs' weights in flight
-  if (D == 64) {
-    // Pipelined form.  The hidden accumulator (N = 128: narrower MMAs lose) is drained in two 64-column
-    // halves into two A operands (h0: 128..255, h1: 256..383), and the second Linear is two K = 64 MMAs, so a half of
-    // the operand is free again as soon as ITS MMA has completed.  Issue order per edge type t:
-    //     G2a(t) | G1(t+1) | G2b(t)                    (4.0 K clk of tensor work, back to back)
-    // while the row threads run  wait G2a(t) | drain h0(t+1) | wait G2b(t) | drain h1(t+1):  G1(t+1) overwrites the
-    // hidden accumulator once both halves of t are drained, drain h0(t+1) overwrites h0 once G2a(t) is done.  The serial
-    // form waited for G1 -> drain -> G2 in turn (7 K clk per t).  "V" is a virtual op: no MMA, a second drain of the
-    // accumulator its predecessor filled.
-    const int b0_off = b.aux(w->agg_b0, T * 128);
-    if (b0_off < 0) return GN_E_SHAPE;
-    const int blk = (128 * 64 + 2 * 64 * 64) * 8;            // stream bytes per t: W0_t | W1_t[:, 0:64] | W1_t[:, 64:128]
-    int g1_op[GN_SMALL_OUT], v_op[GN_SMALL_OUT], g2a_op[GN_SMALL_OUT], g2b_op[GN_SMALL_OUT];
-    auto add_g1 = [&](int t, int wait_n) {
-      g1_op[t] = a.nops;
-      Op& g1 = b.add(A_SMEM, 0, D, 128, 0, 0, wait_n, 1);
-      b.drain_tmem(g1, 64, 1, nullptr, 128, 1);
-      g1.bias_off = static_cast<short>(b0_off + t * 128); g1.rs_idx = static_cast<short>(t);
-      g1.w_off = t * blk;
-      v_op[t] = a.nops;
-      Op& v = b.add(A_SMEM, 0, 0, 128, 64, 0, 0, 1);
-      v.kc = 0;
-      b.drain_tmem(v, 64, 1, nullptr, 256, 1);
-      v.bias_off = static_cast<short>(b0_off + t * 128 + 64); v.rs_idx = static_cast<short>(t);
-      v.w_off = 0;
-    };
-    const int NACC = T >= 2 ? 2 : 1;
-    add_g1(0, 1);
-    for (int t = 0; t < T; ++t) {
-      const bool last = t == T - 1;
-      const int acc = last ? 384 : 384 + (t % NACC) * 64;
-      g2a_op[t] = a.nops;
-      Op& g2a = b.add(A_TMEM, 128, 64, D, acc, (last ? t > 0 : t >= NACC) ? 1 : 0, 1, 1);
-      g2a.drain = DR_NONE;
-      g2a.w_off = t * blk + 128 * 64 * 8;
-      if (!last) add_g1(t + 1, 1);
-      g2b_op[t] = a.nops;
-      Op& g2b = b.add(A_TMEM, 256, 64, D, acc, 1, last ? 1 : 0, 1);
-      g2b.w_off = t * blk + 128 * 64 * 8 + 64 * 64 * 8;
-      if (last) {
-        b.drain_store(g2b, D, 0, nullptr, ef, D, 0, 0);
-        g2b.nsum = static_cast<short>(NACC); g2b.sum_stride = 64;
-        g2b.use_bm = 1;
-      } else {
-        g2b.drain = DR_NONE;
-      }
-    }
-    b.ev(EV_DRAIN, g1_op[0]);
-    b.ev(EV_DRAIN, v_op[0]);
-    for (int t = 0; t < T; ++t) {
-      b.ev(EV_DRAIN, g2a_op[t]);
-      if (t + 1 < T) b.ev(EV_DRAIN, g1_op[t + 1]);
-      b.ev(EV_DRAIN, g2b_op[t]);
-      if (t + 1 < T) b.ev(EV_DRAIN, v_op[t + 1]);
-    }
-  } else {
-    for (int t = 0; t < T; ++t) {
-      Op& g1 = b.add(A_SMEM, 0, D, 128, 0, 0, t == 0 ? 1 : 0, 1);
-      b.drain_tmem(g1, 128, 1, w->agg_b0 + t * 128, 128, 1);
-      g1.rs_idx = static_cast<short>(t);
-      b.ev(EV_DRAIN, 2 * t);
-      const bool last = t == T - 1;
-      Op& g2 = b.add(A_TMEM, 128, 128, D, 384, t > 0 ? 1 : 0, 1, last ? 1 : 0);
-      if (last) {
-        b.drain_store(g2, D, 0, nullptr, ef, D, 0, 0);
-        g2.use_bm = 1;
-        b.ev(EV_DRAIN, 2 * t + 1);
-      }
+  for (int t = 0; t < T; ++t) {
+    Op& g1 = b.add(A_SMEM, 0, D, 128, 0, 0, t == 0 ? 1 : 0, 1);
+    b.drain_tmem(g1, 128, 1, w->agg_b0 + t * 128, 128, 1);
+    g1.rs_idx = static_cast<short>(t);
+    b.ev(EV_DRAIN, 2 * t);
+    // two short accumulation chains (even / odd t) when they fit beside A_hid, summed in fp32 by the final drain
+    const int NACC = (D <= 64 && T >= 2) ? 2 : 1;
+    const bool last = t == T - 1;
+    Op& g2 = b.add(A_TMEM, 128, 128, D, last ? 384 : 384 + (t % NACC) * 64, (last ? t > 0 : t >= NACC) ? 1 : 0, 1, last ? 1 : 0);
+    if (last) {
+      b.drain_store(g2, D, 0, nullptr, ef, D, 0, 0);
+      g2.nsum = static_cast<short>(NACC); g2.sum_stride = 64;
+      g2.use_bm = 1;
+      b.ev(EV_DRAIN, 2 * t + 1);
     }
   }
   a.stage_mode = ST_ROWS; a.src0 = eo; a.ld0 = D; a.k_src0 = D;

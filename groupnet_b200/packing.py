@@ -393,12 +393,8 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
         else:
             mats = []
             for m in agg:
-                w1 = dev(m.layers[1].weight)
-                if d == 64:      # pipelined form (launch_hyper_agg_tf32): the second Linear as two K = 64 operands
-                    mats += [dev(m.layers[0].weight), w1[:, :64].contiguous(), w1[:, 64:].contiguous()]
-                else:
-                    mats += [dev(m.layers[0].weight), w1]
-            out["tf_hagg_w"] = tf_stream(mats, 32768 if d == 64 else tf_stage_bytes(d, 1, False))
+                mats += [dev(m.layers[0].weight), dev(m.layers[1].weight)]
+            out["tf_hagg_w"] = tf_stream(mats, tf_stage_bytes(d, 1, False))
     if d % 4 == 0 and d <= 64 and dout in (64, 128):
         out["tf_post_w"] = tf_stream([dev(post_mod.layers[0].weight), dev(post_mod.layers[1].weight)],
                                      tf_stage_bytes(2 * d, 1, False))

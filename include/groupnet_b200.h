@@ -141,8 +141,7 @@ typedef struct gn_stage_weights {
   const void* tf_pre_w;    /* node W0[0:128] (128xD), W1[:,0:128] (64x128), W0[128:256], W1[:,128:256], [Wp;Wq] (64x64) */
   const void* tf_aggin_w;  /* agg_mlp[t].layers.0 (128xD) for t < T */
   const void* tf_aggout_w; /* cat_t agg_mlp[t].layers.1 along K, (D x T*128), in K blocks of 64 */
-  const void* tf_hagg_w;   /* per t: agg_mlp[t].layers.0 (128xD), agg_mlp[t].layers.1 (Dx128); for D == 64 the latter as two
-                              K = 64 operands: layers.1[:, 0:64] (64x64), layers.1[:, 64:128] (64x64) */
+  const void* tf_hagg_w;   /* per t: agg_mlp[t].layers.0 (128xD), agg_mlp[t].layers.1 (Dx128) */
   const void* tf_post_w;   /* closing MLP layers.0 (128x2D), layers.1 (Doutx128) */
   /* fused pairwise aggregation (csrc/gn_pair_agg_tf32.cu; pairwise layers with D == 64, else NULL): 32 KB chunks
    * (64 x 64, hi then lo) in MMA issue order.  With unit step u = 2t + half, A(u) = agg_mlp[t].layers.0.weight

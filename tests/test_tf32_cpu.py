@@ -106,11 +106,9 @@ def test_weight_streams_follow_the_documented_order():
     hyp = gb.MS_HGNN_hyper(64, 64, 64, 64, batch_norm=0, nmp_layers=1, scale=5)
     t = packing.pack_stage(hyp, 0, torch.device("cpu"))
     agg = hyp.edge_aggregation_list[0].agg_mlp
-    # h_dim 64: per edge type W0_t, then the second Linear as two K = 64 operands (pipelined hyper_agg_tf32)
-    w = _decode(t["tf_hagg_w"], [(128, 64), (64, 64), (64, 64)] * 10, 32768)
+    w = _decode(t["tf_hagg_w"], [(128, 64), (64, 128)] * 10, 65536)
     for i in range(10):
-        assert close(w[3 * i], agg[i].layers[0].weight)
-        assert close(torch.cat((w[3 * i + 1], w[3 * i + 2]), dim=1), agg[i].layers[1].weight)
+        assert close(w[2 * i], agg[i].layers[0].weight) and close(w[2 * i + 1], agg[i].layers[1].weight)
     assert "tf_aggin_w" not in t and "tf_aggout_w" not in t
 
 
