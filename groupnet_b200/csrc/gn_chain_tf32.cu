@@ -22,6 +22,7 @@
 // whose producers could run NBAR phases ahead of its consumers.
 //
 // Roofline: tensor pipe at 1/6 of the bf16 rate (tf32 = 1/2, three MMAs per product): 64*N/2 clk per 128 x N x 8.
+#include <type_traits>
 #include <cstdlib>
 #include <cstring>
 #include "gn_chain_tf32.cuh"
@@ -149,12 +150,13 @@ __device__ __forceinline__ float div_by(float x, float d, float r) {
 }
 
 // DR_DOTG: this thread's share of the distribution head: lg[t] = sum over its 32 hidden units k of
-// relu(acc[k] + b[k]) * W[k][t], W = [128][TP] fp32 in the smem constants (rows of TP = 8, 12 or 16 logits, zero padded)
+// relu(acc[k] + b[k]) * W[k][t], W = [128][TP] fp32 in the smem constants (rows of TP = 6, 8 or 16 logits, zero padded;
+// TP = 6 is the NBA shape's exact T: two hidden units share three 16-byte reads)
 template <int TP>
 __device__ __forceinline__ void dot_logits(const Op& op, const float* aux, const float* w4, uint32_t tmem_row, int sl,
-                                           float (&lg)[16]) {
+                                           float (&lg)[TP]) {
 #pragma unroll
-  for (int t = 0; t < 16; ++t) lg[t] = 0.f;
+  for (int t = 0; t < TP; ++t) lg[t] = 0.f;
   uint32_t r0[16], r1[16];
   tf::tmem_ld16_nowait(tmem_row + op.acc_col + 32 * sl, r0);
   tf::tmem_ld16_nowait(tmem_row + op.acc_col + 32 * sl + 16, r1);
@@ -162,15 +164,29 @@ __device__ __forceinline__ void dot_logits(const Op& op, const float* aux, const
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int c0 = 32 * sl + 16 * half;
+    if constexpr (TP == 6) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float v = fmaxf(__uint_as_float(half ? r1[j] : r0[j]) + aux[op.bias_off + c0 + j], 0.f);
-      const float* wr = w4 + (c0 + j) * TP;
+      for (int j = 0; j < 16; j += 2) {
+        const float v0 = fmaxf(__uint_as_float(half ? r1[j] : r0[j]) + aux[op.bias_off + c0 + j], 0.f);
+        const float v1 = fmaxf(__uint_as_float(half ? r1[j + 1] : r0[j + 1]) + aux[op.bias_off + c0 + j + 1], 0.f);
+        const float4* wr = reinterpret_cast<const float4*>(w4 + (c0 + j) * 6);
+        const float4 wa = wr[0], wb = wr[1], wc = wr[2];
+        lg[0] = fmaf(v0, wa.x, lg[0]); lg[1] = fmaf(v0, wa.y, lg[1]); lg[2] = fmaf(v0, wa.z, lg[2]);
+        lg[3] = fmaf(v0, wa.w, lg[3]); lg[4] = fmaf(v0, wb.x, lg[4]); lg[5] = fmaf(v0, wb.y, lg[5]);
+        lg[0] = fmaf(v1, wb.z, lg[0]); lg[1] = fmaf(v1, wb.w, lg[1]); lg[2] = fmaf(v1, wc.x, lg[2]);
+        lg[3] = fmaf(v1, wc.y, lg[3]); lg[4] = fmaf(v1, wc.z, lg[4]); lg[5] = fmaf(v1, wc.w, lg[5]);
+      }
+    } else {
 #pragma unroll
-      for (int t4 = 0; t4 < TP / 4; ++t4) {
-        const float4 wv = *reinterpret_cast<const float4*>(wr + 4 * t4);
-        lg[4 * t4] = fmaf(v, wv.x, lg[4 * t4]); lg[4 * t4 + 1] = fmaf(v, wv.y, lg[4 * t4 + 1]);
-        lg[4 * t4 + 2] = fmaf(v, wv.z, lg[4 * t4 + 2]); lg[4 * t4 + 3] = fmaf(v, wv.w, lg[4 * t4 + 3]);
+      for (int j = 0; j < 16; ++j) {
+        const float v = fmaxf(__uint_as_float(half ? r1[j] : r0[j]) + aux[op.bias_off + c0 + j], 0.f);
+        const float* wr = w4 + (c0 + j) * TP;
+#pragma unroll
+        for (int t4 = 0; t4 < TP / 4; ++t4) {
+          const float4 wv = *reinterpret_cast<const float4*>(wr + 4 * t4);
+          lg[4 * t4] = fmaf(v, wv.x, lg[4 * t4]); lg[4 * t4 + 1] = fmaf(v, wv.y, lg[4 * t4 + 1]);
+          lg[4 * t4 + 2] = fmaf(v, wv.z, lg[4 * t4 + 2]); lg[4 * t4 + 3] = fmaf(v, wv.w, lg[4 * t4 + 3]);
+        }
       }
     }
   }
@@ -181,7 +197,9 @@ enum { DV_TMEM = 0, DV_TMEM_RELU, DV_TMEM_RELU_RS, DV_TMEM_STORE, DV_STORE, DV_S
 
 // PAIR: the fused pairwise node2edge staging (ST_PAIR programs) is compiled in; the ST_ROWS instance carries none of its
 // code or register state (one kernel for both cost the node chains ~10 %)
-template <bool PAIR>
+// VM: bit v = drain variant v is compiled in, bit DV_COUNT = the DR_DOTG drain is (the launcher picks the smallest
+// instantiated superset of the program's variants: the row warps' instruction footprint is what a program can reach)
+template <bool PAIR, uint32_t VM>
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tf32_kernel(const __grid_constant__ Args a) {
   using namespace tc;
@@ -579,76 +597,102 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         fence_after_thread_sync();
         if (tr) trp[3 * e + 1] = clock64();
         const int kind = op.drain;
-        if (kind == DR_DOTG) {
+        if (((VM >> DV_COUNT) & 1u) && kind == DR_DOTG) {
           // The distribution head (128 -> T) as fp32 dot products inside this drain — no A-operand split, no MMA, no
           // accumulator round trip (the GEMM form cost a 256-column hi | lo store, a K = 128 MMA chain and a handoff) —
           // followed by the Gumbel softmax / sigmoid tail (:45-53).  Slice sl holds 32 of the 128 hidden units: its T
           // partial logits, and the factor head's partial from the DR_DOT drain, meet the other slices' through spare
           // TENSOR MEMORY columns (the row's four threads share TMEM lanes, not a warp).
-          float lg[16];
-          if (a.w4_tp == 8) dot_logits<8>(op, aux, aux + a.w4_off, tmem_row, sl, lg);
-          else if (a.w4_tp == 12) dot_logits<12>(op, aux, aux + a.w4_off, tmem_row, sl, lg);
-          else dot_logits<16>(op, aux, aux + a.w4_off, tmem_row, sl, lg);
-          lg[15] = carry;
-          {
-            uint32_t pk[16];
+          // TP logits per row, XW exchange columns per slice (the factor head's partial rides in column XW - 1)
+          auto dotg = [&](auto tp_c, auto xw_c) {
+            constexpr int TP = decltype(tp_c)::value, XW = decltype(xw_c)::value;
+            constexpr int TMAX = TP < XW - 1 ? TP : XW - 1;
+            float lg[XW];
+            {
+              float part[TP];
+              dot_logits<TP>(op, aux, aux + a.w4_off, tmem_row, sl, part);
+              uint32_t pk[XW];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = __float_as_uint(lg[j]);
-            tf::tmem_st16(tmem_row + op.dst_col + 16 * sl, pk);
-            tf::tmem_st_wait();
-          }
-          fence_before_thread_sync();
-          row_bar();
-          fence_after_thread_sync();
+              for (int j = 0; j < XW; ++j) pk[j] = j < TMAX ? __float_as_uint(part[j]) : 0u;
+              pk[XW - 1] = __float_as_uint(carry);
+              if constexpr (XW == 8) tf::tmem_st8(tmem_row + op.dst_col + XW * sl, pk);
+              else tf::tmem_st16(tmem_row + op.dst_col + XW * sl, pk);
+              tf::tmem_st_wait();
+            }
+            fence_before_thread_sync();
+            row_bar();
+            fence_after_thread_sync();
+            {
+              // fixed order: every slice gets the same sums
+              static_assert(NSLICE == 4, "exchange reads the four slices' partials in two pairs");
+              auto ldx = [&](int s4, uint32_t (&q)[XW]) {
+                if constexpr (XW == 8) tf::tmem_ld8_nowait(tmem_row + op.dst_col + XW * s4, q);
+                else tf::tmem_ld16_nowait(tmem_row + op.dst_col + XW * s4, q);
+              };
+              uint32_t qa[XW], qb[XW];
+              ldx(0, qa); ldx(1, qb);
+              if constexpr (XW == 8) {
+                uint32_t qc[XW], qd[XW];
+                ldx(2, qc); ldx(3, qd);
+                tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) lg[j] = 0.f;
+                for (int j = 0; j < XW; ++j)
+                  lg[j] = ((__uint_as_float(qa[j]) + __uint_as_float(qb[j])) + __uint_as_float(qc[j])) + __uint_as_float(qd[j]);
+              } else {
+                tc::tmem_ld_wait();
 #pragma unroll
-          for (int s4 = 0; s4 < NSLICE; ++s4) {          // fixed order: every slice gets the same sums
-            float qv[16];
-            tmem_ld16(tmem_row + op.dst_col + 16 * s4, qv);
+                for (int j = 0; j < XW; ++j) lg[j] = __uint_as_float(qa[j]) + __uint_as_float(qb[j]);
+                ldx(2, qa); ldx(3, qb);
+                tc::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) lg[j] += qv[j];
-          }
-          const int T = a.T, tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
-          if (live) {
-            // y = (logit + g) / tau with the noise g left in ybuf by the staging event
-            float mx = -INFINITY;
-#pragma unroll
-            for (int t = 0; t < GN_SMALL_OUT - 1; ++t) {
-              if (t < T) {
-                lg[t] = (lg[t] + aux[a.gb_off + t] + ybuf[row * 17 + t]) / 0.5f;
-                mx = fmaxf(mx, lg[t]);
+                for (int j = 0; j < XW; ++j) lg[j] = (lg[j] + __uint_as_float(qa[j])) + __uint_as_float(qb[j]);
               }
             }
-            // ex2.approx-based exponentials: 2 ulp, three orders of magnitude inside the 1e-5 bound of outputs in [0, 1]
-            float den = 0.f;
+            const int T = a.T, tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
+            if (live) {
+              // y = (logit + g) / tau with the noise g left in ybuf by the staging event
+              float mx = -INFINITY;
 #pragma unroll
-            for (int t = 0; t < GN_SMALL_OUT - 1; ++t) {
-              if (t < T) { lg[t] = __expf(lg[t] - mx); den += lg[t]; }
-            }
-            const float factor = 1.f / (1.f + __expf(-(lg[15] + aux[a.gb_off + T])));
+              for (int t = 0; t < TMAX; ++t) {
+                if (t < T) {
+                  lg[t] = (lg[t] + aux[a.gb_off + t] + ybuf[row * 17 + t]) / 0.5f;
+                  mx = fmaxf(mx, lg[t]);
+                }
+              }
+              // ex2.approx-based exponentials: 2 ulp, three orders of magnitude inside the 1e-5 bound of outputs in [0, 1]
+              float den = 0.f;
 #pragma unroll
-            for (int t = 0; t < GN_SMALL_OUT - 1; ++t) {
-              if (t >= t0 && t < t0 + tq && t < T) {
-                const float dd = lg[t] / den;
-                if (a.dist_out != nullptr) a.dist_out[static_cast<size_t>(grow) * T + t] = dd;
-                a.edge_feat[static_cast<size_t>(grow) * T + t] = factor * dd;
+              for (int t = 0; t < TMAX; ++t) {
+                if (t < T) { lg[t] = __expf(lg[t] - mx); den += lg[t]; }
+              }
+              const float factor = 1.f / (1.f + __expf(-(lg[XW - 1] + aux[a.gb_off + T])));
+#pragma unroll
+              for (int t = 0; t < TMAX; ++t) {
+                if (t >= t0 && t < t0 + tq && t < T) {
+                  const float dd = lg[t] / den;
+                  if (a.dist_out != nullptr) a.dist_out[static_cast<size_t>(grow) * T + t] = dd;
+                  a.edge_feat[static_cast<size_t>(grow) * T + t] = factor * dd;
+                }
               }
             }
-          }
+          };
+          if (a.w4_tp == 6) dotg(std::integral_constant<int, 6>{}, std::integral_constant<int, 8>{});
+          else if (a.w4_tp == 8) dotg(std::integral_constant<int, 8>{}, std::integral_constant<int, 16>{});
+          else dotg(std::integral_constant<int, 16>{}, std::integral_constant<int, 16>{});
           fence_before_thread_sync();
           row_bar();                              // ybuf and the exchange columns are rewritten by the next tile
         } else if (kind != DR_NONE) {
           const float* rsb = ybuf + row * 17;               // per-row scales staged at tile start (programs with a.rs)
-          switch (op.variant) {
-            case DV_TMEM:         drain_slice<DR_TMEM, false, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
-            case DV_TMEM_RELU:    drain_slice<DR_TMEM, true, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
-            case DV_TMEM_RELU_RS: drain_slice<DR_TMEM, true, true>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
-            case DV_TMEM_STORE:   drain_slice<DR_TMEM_STORE, false, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
-            case DV_STORE:        drain_slice<DR_STORE, false, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
-            case DV_STORE_BM:     drain_slice<DR_STORE, false, true>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
-            default:              drain_slice<DR_DOT, true, false>(a, op, aux, rsb, tmem_row, sl, grow, live, carry); break;
-          }
+          const int v = op.variant;
+#define GN_DV(V, ...) if (((VM >> (V)) & 1u) && v == (V)) drain_slice<__VA_ARGS__>(a, op, aux, rsb, tmem_row, sl, grow, live, carry)
+          GN_DV(DV_TMEM, DR_TMEM, false, false);
+          else GN_DV(DV_TMEM_RELU, DR_TMEM, true, false);
+          else GN_DV(DV_TMEM_RELU_RS, DR_TMEM, true, true);
+          else GN_DV(DV_TMEM_STORE, DR_TMEM_STORE, false, false);
+          else GN_DV(DV_STORE, DR_STORE, false, false);
+          else GN_DV(DV_STORE_BM, DR_STORE, false, true);
+          else GN_DV(DV_DOT_RELU, DR_DOT, true, false);
+#undef GN_DV
         }
         if (op.arrive) {
           fence_before_thread_sync();
@@ -845,6 +889,11 @@ static int validate_program(Args& a) {
 extern unsigned long long* g_trace_buffer;      // gn_profile_set_trace (gn_edge_mlp_tc.cu)
 namespace tfe {
 
+constexpr uint32_t VM_CHAIN = (1u << DV_TMEM) | (1u << DV_TMEM_RELU) | (1u << DV_DOT_RELU) | (1u << DV_COUNT);
+constexpr uint32_t VM_NODE = (1u << DV_TMEM) | (1u << DV_TMEM_RELU) | (1u << DV_TMEM_STORE) | (1u << DV_STORE);
+constexpr uint32_t VM_HAGG = (1u << DV_TMEM_RELU) | (1u << DV_TMEM_RELU_RS) | (1u << DV_STORE) | (1u << DV_STORE_BM);
+constexpr uint32_t VM_ALL = (2u << DV_COUNT) - 1u;
+
 static int launch(Builder& b, long long R, long long ntiles, const unsigned char* wstream, const char* name, cudaStream_t st) {
   Args& a = b.a;
   a.trace = g_trace_buffer;
@@ -872,7 +921,17 @@ static int launch(Builder& b, long long R, long long ntiles, const unsigned char
   int rc = validate_program(a);
   if (rc != GN_OK) return rc;
   if (!wstream || (reinterpret_cast<uintptr_t>(wstream) & 15)) return GN_E_NULL;
-  auto kern = a.stage_mode == ST_PAIR ? chain_tf32_kernel<true> : chain_tf32_kernel<false>;
+  uint32_t need = 0;
+  for (int o = 0; o < a.nops; ++o)
+    if (a.ops[o].signal && a.ops[o].drain != DR_NONE) need |= a.ops[o].drain == DR_DOTG ? (1u << DV_COUNT) : (1u << a.ops[o].variant);
+  void (*kern)(Args) = nullptr;
+  if (a.stage_mode == ST_PAIR) {
+    if (need & ~VM_CHAIN) return GN_E_SHAPE;
+    kern = chain_tf32_kernel<true, VM_CHAIN>;
+  } else if (!(need & ~VM_NODE)) kern = chain_tf32_kernel<false, VM_NODE>;
+  else if (!(need & ~VM_HAGG)) kern = chain_tf32_kernel<false, VM_HAGG>;
+  else if (!(need & ~VM_CHAIN)) kern = chain_tf32_kernel<false, VM_CHAIN>;
+  else kern = chain_tf32_kernel<false, VM_ALL>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = ntiles < GN_SM_COUNT ? static_cast<int>(ntiles) : GN_SM_COUNT;
@@ -967,12 +1026,12 @@ int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, con
   a.N = N; a.E = E;
   a.tps = (pair && E >= 128) ? (E + 127) / 128 : 0;
   // the stream: init_MLP.0 (64 KB, skipped by the pair form) | the chunks of the ops above | MLP_factor.layers.1.weight
-  // (128 floats) | MLP_distribution.layers.1.weight as [128][8, 12 or 16] fp32 (k-major rows of T logits, zero padded)
+  // (128 floats) | MLP_distribution.layers.1.weight as [128][6, 8 or 16] fp32 (k-major rows of T logits, zero padded)
   const unsigned char* stream = static_cast<const unsigned char*>(w->tf_chain_w);
   const size_t w1_bytes = 128 * 64 * 8;
   const float* tail = reinterpret_cast<const float*>(stream + (pair ? w1_bytes : 0) + b.wbytes);
   a.dot_off = b.aux(tail, 128);
-  a.w4_tp = T <= 8 ? 8 : (T <= 12 ? 12 : 16);
+  a.w4_tp = T <= 6 ? 6 : (T <= 8 ? 8 : 16);
   a.w4_off = b.aux(tail + 128, 128 * a.w4_tp);
   a.gb_off = b.aux(w->df_b1, GN_SMALL_OUT);
   if (a.dot_off < 0 || a.w4_off < 0 || a.gb_off < 0 || g3d.bias_off < 0 || (pair && (a.yb_off < 0 || a.att_off < 0))) return GN_E_SHAPE;

@@ -85,6 +85,18 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+      :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
