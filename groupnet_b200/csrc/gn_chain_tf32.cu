@@ -40,6 +40,7 @@ __device__ __forceinline__ void row_bar() { asm volatile("bar.sync 1, 512;" ::: 
 
 struct Bars {
   uint64_t full[8], empty[8], a_ready[NBAR], acc_ready[NBAR];
+  uint64_t node_full, node_empty;        // ST_PAIR node block: filled by the producer warp's bulk copies, freed by the row threads
   uint32_t tmem_slot, pad;
 };
 
@@ -210,6 +211,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
   if (tid == 0) {
     for (int s = 0; s < a.nstage; ++s) { mbar_init(&bars->full[s], 1); mbar_init(&bars->empty[s], 1); }
     for (int i = 0; i < NBAR; ++i) { mbar_init(&bars->a_ready[i], ROW_THREADS); mbar_init(&bars->acc_ready[i], 1); }
+    mbar_init(&bars->node_full, 1); mbar_init(&bars->node_empty, ROW_THREADS);
   }
   if (warp == 0) tmem_alloc(&bars->tmem_slot, 512);
   float* aux = reinterpret_cast<float*>(smem + a.off_aux);
@@ -249,7 +251,41 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         if (++s == a.nstage) { s = 0; ph ^= 1u; }
       }
     };
+    // ST_PAIR: the node block of a tile (pq and Y rows of the nodes its <= 128 edges touch) also comes in as bulk copies
+    // from this warp — one per node row, the rows are padded in shared memory — so the row threads spend no LSU
+    // instructions on it (as 16-byte cp.async from the row threads it cost ~1.7 K clk of each tile's ~16 K).  Block k + 1
+    // may overwrite block k once every row thread has finished part B of block k (node_empty).
+    int nb = 0;                             // next node block to issue (the CTA's nb-th tile)
+    auto node_block = [&]() {
+      const long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(nb) * gridDim.x;
+      if (t < a.ntiles) {
+        if (nb > 0) mbar_wait(&bars->node_empty, static_cast<uint32_t>(nb - 1) & 1u);
+        const uint32_t uE = static_cast<uint32_t>(a.E), uN = static_cast<uint32_t>(a.N), ut = static_cast<uint32_t>(t);
+        uint32_t node0, cnt;
+        if (a.tps) { node0 = ut / static_cast<uint32_t>(a.tps) * uN; cnt = uN; }
+        else {
+          const uint32_t r_last = min(ut * 128u + 127u, static_cast<uint32_t>(a.R) - 1u);
+          const uint32_t b_lo = ut * 128u / uE, b_hi = r_last / uE;
+          node0 = b_lo * uN; cnt = (b_hi - b_lo + 1u) * uN;
+        }
+        const uint32_t np_s = sbase + a.off_node, ny_s = np_s + MAXN * NLD * 4;
+        if (elect_one()) mbar_expect_tx(&bars->node_full, cnt * (64u + 128u) * 4u);
+        __syncwarp();
+        for (uint32_t n = 0; n < cnt; ++n) {
+          if (elect_one()) {
+            bulk_g2s(np_s + n * (NLD * 4), a.pq + static_cast<size_t>(node0 + n) * 64, 64 * 4, &bars->node_full);
+            bulk_g2s(ny_s + n * (YLD * 4), a.ypre + static_cast<size_t>(node0 + n) * 128, 128 * 4, &bars->node_full);
+          }
+          __syncwarp();
+        }
+      }
+      ++nb;
+    };
     int titer = 0;
+    if (PAIR) {
+      pdl_wait();                           // pq / Y are the previous kernel's output
+      node_block();
+    }
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
       tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
       trp = a.trace + titer * TR_SLOTS + TR_CHUNK;
@@ -259,7 +295,11 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       for (int o = (titer == 0 && a.pro_op >= 0) ? -1 : 0; o < a.nops; ++o) {
         if (last && o == a.skip_last_op) continue;
         stream_op(a.ops[o < 0 ? a.pro_op : o]);
+        // a pipelined program consumes block k + 1 inside tile k: the CTA's second block follows the pro_op's weights
+        if (PAIR && o < 0) node_block();
       }
+      // here, not earlier: the wait for the row threads' part B must not hold back this tile's weights
+      if (PAIR) node_block();
     }
   } else if (warp == ROW_THREADS / 32 + 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -342,20 +382,6 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     const uint32_t uE = static_cast<uint32_t>(a.E > 0 ? a.E : 1), uN = static_cast<uint32_t>(a.N);
     const uint32_t total_nodes = pair ? static_cast<uint32_t>(a.R) / uE * uN : 0u;
     const int tps = pair ? a.tps : 0;
-    auto prefetch_nodes = [&](long long t) {
-      if (t < a.ntiles) {
-        const uint32_t ut = static_cast<uint32_t>(t);
-        const uint32_t node0 = (tps ? ut / static_cast<uint32_t>(tps) : (ut * 128u) / uE) * uN;
-        const int cnt = static_cast<int>(min(static_cast<uint32_t>(MAXN), total_nodes - node0));
-        for (int i = tid; i < cnt * 48; i += ROW_THREADS) {       // 16 x 16 B of pq + 32 x 16 B of Y per node
-          const int n = i / 48, c = i - n * 48;
-          if (c < 16) cp_async16(np + n * NLD + 4 * c, a.pq + static_cast<size_t>(node0 + n) * 64 + 4 * c);
-          else cp_async16(ny + n * YLD + 4 * (c - 16), a.ypre + static_cast<size_t>(node0 + n) * 128 + 4 * (c - 16));
-        }
-      }
-      cp_async_commit();
-    };
-    if (pair) prefetch_nodes(blockIdx.x);
     unsigned long long seed = a.seed;
     if (a.noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && a.U != nullptr)
       seed = __ldg(reinterpret_cast<const unsigned long long*>(a.U));
@@ -412,13 +438,13 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     // weights and the node-block rows of the edge — stay in registers for part B.
     float s_wi = 0.f, s_wj = 0.f;
     int s_li = 0, s_lj = 0;
+    uint32_t nk = 0;                       // node blocks consumed
     auto pair_stage_a = [&](long long t, bool tr, unsigned long long* trp) {
       const long long tsc = tps ? static_cast<long long>(static_cast<uint32_t>(t) / static_cast<uint32_t>(tps)) : 0;
       const int tch = tps ? static_cast<int>(t - tsc * tps) : 0;
       const long long g_row = tps ? tsc * a.E + tch * 128 + row : t * 128 + row;
       const bool lv = g_row < a.R && (!tps || tch * 128 + row < a.E);
-      cp_async_wait<0>();
-      row_bar();
+      mbar_wait(&bars->node_full, nk & 1u);                // the producer warp's bulk copies of this tile's node block
       if (tr) trp[TR_STAGE - TR_ROWS + 0] = clock64();
       const uint32_t b_lo = tps ? static_cast<uint32_t>(tsc) : (static_cast<uint32_t>(t) * 128u) / uE;
       const int N = a.N;
@@ -507,10 +533,8 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       fence_before_thread_sync();
       mbar_arrive(&bars->a_ready[ar & (NBAR - 1)]); ++ar;     // the MMAs start while the node block is refilled
       if (tr) trp[TR_STAGE - TR_ROWS + 5] = clock64();
-      row_bar();                          // every thread is done with the node block: refill it for the next tile
-      if (tr) trp[TR_STAGE - TR_ROWS + 6] = clock64();
-      prefetch_nodes(t + gridDim.x);
-      if (tr) trp[TR_STAGE - TR_ROWS + 7] = clock64();
+      mbar_arrive(&bars->node_empty); ++nk;                   // this thread is done with the node block
+      if (tr) { trp[TR_STAGE - TR_ROWS + 6] = clock64(); trp[TR_STAGE - TR_ROWS + 7] = trp[TR_STAGE - TR_ROWS + 6]; }
     };
     // Gumbel noise of a tile's rows (slice sl: edge types [sl*tq, sl*tq + tq)): g = -log(eps - log(U + eps)) (:446-455)
     // -> ybuf, computed while the row threads would otherwise wait for a GEMM
