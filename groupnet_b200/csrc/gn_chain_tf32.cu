@@ -66,11 +66,9 @@ __device__ __forceinline__ void drain_pass(const Args& a, const Op& op, const fl
   if (op.bias_off >= 0) {
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
-      const float4 b = *reinterpret_cast<const float4*>(aux + op.bias_off + c0 + 4 * q);
-      r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + b.x);
-      r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + b.y);
-      r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + b.z);
-      r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + b.w);
+      const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(aux + op.bias_off + c0 + 4 * q);
+      tf::upk2u(tf::add2(tf::pk2u(r[4 * q], r[4 * q + 1]), b.x), r[4 * q], r[4 * q + 1]);
+      tf::upk2u(tf::add2(tf::pk2u(r[4 * q + 2], r[4 * q + 3]), b.y), r[4 * q + 2], r[4 * q + 3]);
     }
   }
   if (RELU) {
@@ -79,31 +77,34 @@ __device__ __forceinline__ void drain_pass(const Args& a, const Op& op, const fl
   }
   if (RS && KIND != DR_STORE) {                 // per-row scale (edge_feat_t)
     const float scale = rsb[op.rs_idx];
+    const unsigned long long s2 = tf::pk2f(scale, scale);
 #pragma unroll
-    for (int j = 0; j < W; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * scale);
+    for (int j = 0; j < W; j += 2) tf::upk2u(tf::mul2(tf::pk2u(r[j], r[j + 1]), s2), r[j], r[j + 1]);
   }
   if (KIND == DR_DOT) {
+    // even | odd columns in the two lanes of a packed accumulator; the lanes meet at the end of the pass
+    unsigned long long c2 = tf::pk2f(carry, 0.f);
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
-      const float4 wv = *reinterpret_cast<const float4*>(aux + a.dot_off + c0 + 4 * q);
-      carry = fmaf(__uint_as_float(r[4 * q]), wv.x, carry);
-      carry = fmaf(__uint_as_float(r[4 * q + 1]), wv.y, carry);
-      carry = fmaf(__uint_as_float(r[4 * q + 2]), wv.z, carry);
-      carry = fmaf(__uint_as_float(r[4 * q + 3]), wv.w, carry);
+      const ulonglong2 wv = *reinterpret_cast<const ulonglong2*>(aux + a.dot_off + c0 + 4 * q);
+      c2 = tf::fma2(tf::pk2u(r[4 * q], r[4 * q + 1]), wv.x, c2);
+      c2 = tf::fma2(tf::pk2u(r[4 * q + 2], r[4 * q + 3]), wv.y, c2);
     }
+    float ce, co;
+    tf::upk2f(c2, ce, co);
+    carry = ce + co;
     return;
   }
   if (RS && KIND == DR_STORE) {                 // rank-T bias: v += sum_t rs[row][t] * bm[t][col]
     const float* bm = aux + a.bm_off + op.out_col0 + c0;
     for (int t = 0; t < a.bm_T; ++t) {
       const float st = rsb[t];
+      const unsigned long long st2 = tf::pk2f(st, st);
 #pragma unroll
       for (int q = 0; q < W / 4; ++q) {
-        const float4 b = *reinterpret_cast<const float4*>(bm + t * a.bm_ld + 4 * q);
-        r[4 * q] = __float_as_uint(fmaf(st, b.x, __uint_as_float(r[4 * q])));
-        r[4 * q + 1] = __float_as_uint(fmaf(st, b.y, __uint_as_float(r[4 * q + 1])));
-        r[4 * q + 2] = __float_as_uint(fmaf(st, b.z, __uint_as_float(r[4 * q + 2])));
-        r[4 * q + 3] = __float_as_uint(fmaf(st, b.w, __uint_as_float(r[4 * q + 3])));
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(bm + t * a.bm_ld + 4 * q);
+        tf::upk2u(tf::fma2(st2, b.x, tf::pk2u(r[4 * q], r[4 * q + 1])), r[4 * q], r[4 * q + 1]);
+        tf::upk2u(tf::fma2(st2, b.y, tf::pk2u(r[4 * q + 2], r[4 * q + 3])), r[4 * q + 2], r[4 * q + 3]);
       }
     }
   }
@@ -151,13 +152,16 @@ __device__ __forceinline__ float div_by(float x, float d, float r) {
 }
 
 // DR_DOTG: this thread's share of the distribution head: lg[t] = sum over its 32 hidden units k of
-// relu(acc[k] + b[k]) * W[k][t], W = [128][TP] fp32 in the smem constants (rows of TP = 6, 8 or 16 logits, zero padded;
-// TP = 6 is the NBA shape's exact T: two hidden units share three 16-byte reads)
+// relu(acc[k] + b[k]) * W[k][t], W = [128][TP] fp32 in the smem constants (rows of TP logits, zero padded; TP is the
+// even number >= T among 6, 8, 10, 12, 16 — the reference's T = 6 (pairwise) and 10 (hyper) exactly; two hidden units
+// share TP / 2 16-byte reads)
 template <int TP>
 __device__ __forceinline__ void dot_logits(const Op& op, const float* aux, const float* w4, uint32_t tmem_row, int sl,
                                            float (&lg)[TP]) {
+  static_assert(TP % 2 == 0 && TP <= 16, "rows of two hidden units are read as float4s");
+  unsigned long long acc[TP / 2];          // logits (2q, 2q + 1) in the lanes of packed accumulator q
 #pragma unroll
-  for (int t = 0; t < TP; ++t) lg[t] = 0.f;
+  for (int q = 0; q < TP / 2; ++q) acc[q] = 0ull;
   uint32_t r0[16], r1[16];
   tf::tmem_ld16_nowait(tmem_row + op.acc_col + 32 * sl, r0);
   tf::tmem_ld16_nowait(tmem_row + op.acc_col + 32 * sl + 16, r1);
@@ -165,32 +169,25 @@ __device__ __forceinline__ void dot_logits(const Op& op, const float* aux, const
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const int c0 = 32 * sl + 16 * half;
-    if constexpr (TP == 6) {
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float v0 = fmaxf(__uint_as_float(half ? r1[j] : r0[j]) + aux[op.bias_off + c0 + j], 0.f);
-        const float v1 = fmaxf(__uint_as_float(half ? r1[j + 1] : r0[j + 1]) + aux[op.bias_off + c0 + j + 1], 0.f);
-        const float4* wr = reinterpret_cast<const float4*>(w4 + (c0 + j) * 6);
-        const float4 wa = wr[0], wb = wr[1], wc = wr[2];
-        lg[0] = fmaf(v0, wa.x, lg[0]); lg[1] = fmaf(v0, wa.y, lg[1]); lg[2] = fmaf(v0, wa.z, lg[2]);
-        lg[3] = fmaf(v0, wa.w, lg[3]); lg[4] = fmaf(v0, wb.x, lg[4]); lg[5] = fmaf(v0, wb.y, lg[5]);
-        lg[0] = fmaf(v1, wb.z, lg[0]); lg[1] = fmaf(v1, wb.w, lg[1]); lg[2] = fmaf(v1, wc.x, lg[2]);
-        lg[3] = fmaf(v1, wc.y, lg[3]); lg[4] = fmaf(v1, wc.z, lg[4]); lg[5] = fmaf(v1, wc.w, lg[5]);
-      }
-    } else {
+    for (int j = 0; j < 16; j += 2) {
+      const unsigned long long b2 = *reinterpret_cast<const unsigned long long*>(aux + op.bias_off + c0 + j);
+      float v0, v1;
+      tf::upk2f(tf::add2(half ? tf::pk2u(r1[j], r1[j + 1]) : tf::pk2u(r0[j], r0[j + 1]), b2), v0, v1);
+      v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);
+      const unsigned long long v0p = tf::pk2f(v0, v0), v1p = tf::pk2f(v1, v1);
+      const ulonglong2* wr = reinterpret_cast<const ulonglong2*>(w4 + (c0 + j) * TP);
+      unsigned long long wf[TP];             // TP packed pairs: unit j's TP / 2, then unit j + 1's
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float v = fmaxf(__uint_as_float(half ? r1[j] : r0[j]) + aux[op.bias_off + c0 + j], 0.f);
-        const float* wr = w4 + (c0 + j) * TP;
+      for (int q = 0; q < TP / 2; ++q) { const ulonglong2 wv = wr[q]; wf[2 * q] = wv.x; wf[2 * q + 1] = wv.y; }
 #pragma unroll
-        for (int t4 = 0; t4 < TP / 4; ++t4) {
-          const float4 wv = *reinterpret_cast<const float4*>(wr + 4 * t4);
-          lg[4 * t4] = fmaf(v, wv.x, lg[4 * t4]); lg[4 * t4 + 1] = fmaf(v, wv.y, lg[4 * t4 + 1]);
-          lg[4 * t4 + 2] = fmaf(v, wv.z, lg[4 * t4 + 2]); lg[4 * t4 + 3] = fmaf(v, wv.w, lg[4 * t4 + 3]);
-        }
-      }
+      for (int q = 0; q < TP / 2; ++q) acc[q] = tf::fma2(v0p, wf[q], acc[q]);
+#pragma unroll
+      for (int q = 0; q < TP / 2; ++q) acc[q] = tf::fma2(v1p, wf[TP / 2 + q], acc[q]);
     }
   }
+#pragma unroll
+  for (int q = 0; q < TP / 2; ++q) tf::upk2f(acc[q], lg[2 * q], lg[2 * q + 1]);
 }
 
 // drain variants the launchers use (Op::variant)
@@ -539,22 +536,31 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     // Gumbel noise of a tile's rows (slice sl: edge types [sl*tq, sl*tq + tq)): g = -log(eps - log(U + eps)) (:446-455)
     // -> ybuf, computed while the row threads would otherwise wait for a GEMM
     auto tile_noise = [&](long long g_row, bool lv) {
-      const int T = a.T, tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
-      constexpr int TQ = (GN_SMALL_OUT - 1 + NSLICE - 1) / NSLICE;
-      if (lv) {
+      const int T = a.T;
+      if (!lv) return;
+      if (a.noise_mode == GN_NOISE_GIVEN) {
+        const int tq = (T + NSLICE - 1) / NSLICE, t0 = sl * tq;
+        constexpr int TQ = (GN_SMALL_OUT - 1 + NSLICE - 1) / NSLICE;
 #pragma unroll
         for (int jj = 0; jj < TQ; ++jj) {
           const int t = t0 + jj;
-          if (jj < tq && t < T) {
-            float u;
-            if (a.noise_mode == GN_NOISE_GIVEN) {
-              u = __ldg(a.U + static_cast<size_t>(g_row) * T + t);
-            } else {
-              const unsigned long long el =
-                  (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(g_row)) * T + t;
-              u = Philox::uniform(el, static_cast<uint32_t>(a.stage_index), seed);
-            }
-            ybuf[row * 17 + t] = gumbel_from_uniform(u);
+          if (jj < tq && t < T) ybuf[row * 17 + t] = gumbel_from_uniform(__ldg(a.U + static_cast<size_t>(g_row) * T + t));
+        }
+      } else {
+        // Philox: the row's T consecutive elements span <= T / 4 + 2 counter blocks of four; each block is generated ONCE
+        // (by slice = block mod 4) instead of once per element — a third of the rounds at T = 6 or 10
+        const unsigned long long e0 =
+            (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(g_row)) * T;
+        const unsigned long long b_last = (e0 + T - 1) >> 2;
+        for (unsigned long long bk = (e0 >> 2) + sl; bk <= b_last; bk += NSLICE) {
+          const uint4 blk = Philox::block(bk, static_cast<uint32_t>(a.stage_index), seed);
+          const uint32_t wv[4] = {blk.x, blk.y, blk.z, blk.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const unsigned long long el = bk * 4 + w;
+            if (el >= e0 && el < e0 + T)
+              ybuf[row * 17 + static_cast<int>(el - e0)] =
+                  gumbel_from_uniform(static_cast<float>(wv[w] >> 8) * (1.0f / 16777216.0f));
           }
         }
       }
@@ -574,7 +580,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       const long long grow = tps ? tscene * a.E + tchunk * 128 + row : tile * 128 + row;
       const bool live = grow < a.R && (!tps || tchunk * 128 + row < a.E);
       float carry = 0.f;
-      if (a.pro_op >= 0 && a.edge_feat != nullptr) tile_noise(grow, live);   // ybuf is free: the previous tile ended on a barrier
+      if ((a.pro_op >= 0 || a.stage_first >= 0) && a.edge_feat != nullptr) tile_noise(grow, live);   // ybuf is free: the previous tile ended on a barrier
       const bool has_next = tile + gridDim.x < a.ntiles;
 
       for (int e = 0; e < a.nev; ++e) {
@@ -701,7 +707,9 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
             }
           };
           if (a.w4_tp == 6) dotg(std::integral_constant<int, 6>{}, std::integral_constant<int, 8>{});
+          else if (a.w4_tp == 10) dotg(std::integral_constant<int, 10>{}, std::integral_constant<int, 16>{});
           else if (a.w4_tp == 8) dotg(std::integral_constant<int, 8>{}, std::integral_constant<int, 16>{});
+          else if (a.w4_tp == 12) dotg(std::integral_constant<int, 12>{}, std::integral_constant<int, 16>{});
           else dotg(std::integral_constant<int, 16>{}, std::integral_constant<int, 16>{});
           fence_before_thread_sync();
           row_bar();                              // ybuf and the exchange columns are rewritten by the next tile
@@ -858,7 +866,7 @@ static int validate_program(Args& a) {
   if (a.stage_first >= 0) {
     // per-tile side work hangs off an EV_STAGE at e == 0; the staged buffer feeds the tile's FIRST op
     if (a.stage_first != 0 || a.ops[0].a_src != A_SMEM || a.ops[0].wait_n != 1 || a.stage_mode != ST_ROWS || a.tps != 0 ||
-        a.rs != nullptr || a.edge_feat != nullptr) return GN_E_SHAPE;
+        a.rs != nullptr) return GN_E_SHAPE;
     // a_ready arrivals are consumed in op order: the next tile's staging arrival must be the LAST arrival of this tile,
     // and it may only overwrite the buffer after the last op that reads it has completed (its drain event precedes)
     int n_next = 0, last_reader = 0;
@@ -975,7 +983,7 @@ using namespace tfe;
 // ---- per-edge chain: init_MLP -> [MLP_distribution | MLP_factor] -> Gumbel softmax / sigmoid (:41-53)
 //   G1 64->128 (ReLU)  G2 128->64 (z)  G3f 64->128 (factor hidden, ReLU; its 128->1 head is a dot in the drain)
 //   G3d 64->128 (distribution hidden, ReLU; its 128->T head is T dots in the drain)  -> Gumbel softmax / sigmoid
-// TMEM columns: acc1 0 | A1 128,256 | acc2 384 | A2 0,64 | acc3f 128 | acc3d 256 | logit exchange 0..63
+// TMEM columns: acc1 0 | A1 128,256 | acc2 384 | A2 0,64 | acc3f 128 | acc3d 256 | logit exchange 448..511
 bool edge_chain_tf32_fits(bool pair, int N, int T) {
   if (T < 1 || T > GN_SMALL_OUT - 1) return false;
   if (!pair) return true;
@@ -1007,12 +1015,18 @@ int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, con
     g3f.drain = DR_DOT; g3f.dn = 128; g3f.relu = 1; b.set_bias(g3f, w->df_b0 + 128, 128); g3f.arrive = 0;
     Op& g3d = b.add(A_TMEM, 0, 64, 128, 256, 0, 0, 1);
     // the distribution head (128 -> T) and the Gumbel softmax run inside the drain of G3d (DR_DOTG); the slices' partial
-    // logits meet in columns 0..63: A2 is dead once G3d has completed (which that drain waits for), whereas the factor
-    // accumulator next to it may still be read by a slower slice's DR_DOT drain
-    g3d.drain = DR_DOTG; g3d.dn = 128; g3d.relu = 1; b.set_bias(g3d, w->df_b0, 128); g3d.dst_col = 0; g3d.arrive = 0;
+    // logits meet in columns 448..511, the only ones no accumulator or operand of this chain uses (G1 of the NEXT tile,
+    // whose rows are staged early, may already be accumulating into 0..127 by then)
+    g3d.drain = DR_DOTG; g3d.dn = 128; g3d.relu = 1; b.set_bias(g3d, w->df_b0, 128); g3d.dst_col = 448; g3d.arrive = 0;
     g3d_p = &g3d;
-    b.ev(EV_STAGE, 0);
-    for (int o = 0; o < 4; ++o) b.ev(EV_DRAIN, o);
+    // the next tile's rows are staged (HBM -> split -> smem) and its Gumbel noise drawn while the two head GEMMs run:
+    // G1 has completed (D1 waited for it), and the staging arrival is the tile's last (D2 releases both heads)
+    a.stage_first = 0;
+    b.ev(EV_DRAIN, 0);
+    b.ev(EV_DRAIN, 1);
+    b.ev(EV_STAGE_NEXT, 0);
+    b.ev(EV_DRAIN, 2);
+    b.ev(EV_DRAIN, 3);
   } else {
     // Software-pipelined pairwise form.  The row threads are the bottleneck of this chain (SIMT ~14 K clk per tile
     // against ~7 K of tensor time), so the fused node2edge of tile i + 1 runs inside the MMA waits of tile i:
@@ -1050,12 +1064,12 @@ int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, con
   a.N = N; a.E = E;
   a.tps = (pair && E >= 128) ? (E + 127) / 128 : 0;
   // the stream: init_MLP.0 (64 KB, skipped by the pair form) | the chunks of the ops above | MLP_factor.layers.1.weight
-  // (128 floats) | MLP_distribution.layers.1.weight as [128][6, 8 or 16] fp32 (k-major rows of T logits, zero padded)
+  // (128 floats) | MLP_distribution.layers.1.weight as [128][6, 8, 10, 12 or 16] fp32 (k-major rows of T logits, zero padded)
   const unsigned char* stream = static_cast<const unsigned char*>(w->tf_chain_w);
   const size_t w1_bytes = 128 * 64 * 8;
   const float* tail = reinterpret_cast<const float*>(stream + (pair ? w1_bytes : 0) + b.wbytes);
   a.dot_off = b.aux(tail, 128);
-  a.w4_tp = T <= 6 ? 6 : (T <= 8 ? 8 : 16);
+  a.w4_tp = T <= 6 ? 6 : (T <= 8 ? 8 : (T <= 10 ? 10 : (T <= 12 ? 12 : 16)));
   a.w4_off = b.aux(tail + 128, 128 * a.w4_tp);
   a.gb_off = b.aux(w->df_b1, GN_SMALL_OUT);
   if (a.dot_off < 0 || a.w4_off < 0 || a.gb_off < 0 || g3d.bias_off < 0 || (pair && (a.yb_off < 0 || a.att_off < 0))) return GN_E_SHAPE;

@@ -95,7 +95,7 @@ struct Args {
   int dot_off;                     // smem constants
   // DR_DOTG (distribution head + MLP_dict_softmax tail, :45-53, :446-520)
   int gb_off; int T;               // smem constants: df_b1[16]
-  int w4_off, w4_tp;               // smem constants: MLP_distribution.layers.1.weight as [128][w4_tp], w4_tp = 6, 8 or 16
+  int w4_off, w4_tp;               // smem constants: MLP_distribution.layers.1.weight as [128][w4_tp], w4_tp = 6, 8, 10, 12 or 16
   const float* U; int noise_mode; unsigned long long seed; long long scene_offset; int stage_index;
   float* dist_out; float* edge_feat;
   // shared-memory layout

@@ -368,8 +368,8 @@ def pack_stage(layer, s: int, device: torch.device) -> Dict[str, torch.Tensor]:
     # fp32-grade tensor-core path (GN_TF32X3): 3xTF32 weight streams of the chains whose shape fits
     # (the *_tf32_fits() predicates of csrc/gn_chain_tf32.cu; absent streams fall back to the FFMA kernels)
     # the factor head (128 -> 1) and the distribution head (128 -> T) are fp32 dots in the drains: plain fp32 tail,
-    # the latter k-major as [128][6, 8 or 16] (rows of T logits, zero padded)
-    w4 = torch.zeros(128, 6 if t <= 6 else (8 if t <= 8 else 16), dtype=torch.float32, device=device)
+    # the latter k-major as [128][6, 8, 10, 12 or 16] (rows of T logits, zero padded)
+    w4 = torch.zeros(128, next(tp for tp in (6, 8, 10, 12, 16) if t <= tp), dtype=torch.float32, device=device)
     w4[:, :t] = dev(dist[1].weight).t()
     out["tf_chain_w"] = tf_stream([dev(init[0].weight), dev(init[1].weight), dev(fac[0].weight), dev(dist[0].weight)],
                                   min(tf_stage_bytes(64, 1, False), tf_stage_bytes(0, 1, True)),

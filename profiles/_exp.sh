@@ -7,4 +7,4 @@ d=json.loads([l for l in open("gpurun_out/exp_vm.json").read().splitlines() if l
 print(d["value"], d["ms_per_step"])
 for k,v in d.get("kernels", {}).items(): print(k, v["ms_per_step"])
 PY
-timeout 120 python profiles/trace_tf32.py pair 2>&1 | tail -12
+timeout 120 python profiles/trace_tf32.py hyper 2>&1 | grep -A6 "tile iter 3"
