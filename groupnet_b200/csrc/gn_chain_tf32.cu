@@ -197,10 +197,14 @@ enum { DV_TMEM = 0, DV_TMEM_RELU, DV_TMEM_RELU_RS, DV_TMEM_STORE, DV_STORE, DV_S
 // code or register state (one kernel for both cost the node chains ~10 %)
 // VM: bit v = drain variant v is compiled in, bit DV_COUNT = the DR_DOTG drain is (the launcher picks the smallest
 // instantiated superset of the program's variants: the row warps' instruction footprint is what a program can reach)
-template <bool PAIR, uint32_t VM>
+// TRACE: the clock64 phase stamps (profiles/trace_tf32.py) are compiled in; the production instances carry none of them
+template <bool PAIR, uint32_t VM, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 chain_tf32_kernel(const __grid_constant__ Args a) {
   using namespace tc;
+  // the Gumbel noise belongs to the DR_DOTG drain, the per-row scales to the RS variants: other instances carry neither
+  constexpr bool HAS_DOTG = (VM >> DV_COUNT) & 1u;
+  constexpr bool HAS_RS = (VM & ((1u << DV_TMEM_RELU_RS) | (1u << DV_STORE_BM))) != 0;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   Bars* bars = reinterpret_cast<Bars*>(smem + a.off_bar);
@@ -284,7 +288,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       node_block();
     }
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
-      tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
+      tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
       trp = a.trace + titer * TR_SLOTS + TR_CHUNK;
       ci = 0;
       const bool last = tile + gridDim.x >= a.ntiles;
@@ -347,7 +351,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     // the tile after the LAST one (skip_last_op)
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
-      tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
+      tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && lane == 0;
       trp = a.trace + titer * TR_SLOTS;
       ci = 0;
       const bool last = tile + gridDim.x >= a.ntiles;
@@ -380,7 +384,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     const uint32_t total_nodes = pair ? static_cast<uint32_t>(a.R) / uE * uN : 0u;
     const int tps = pair ? a.tps : 0;
     unsigned long long seed = a.seed;
-    if (a.noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && a.U != nullptr)
+    if (HAS_DOTG && a.noise_mode == GN_NOISE_PHILOX_DEVICE_SEED && a.U != nullptr)
       seed = __ldg(reinterpret_cast<const unsigned long long*>(a.U));
 
     // ST_ROWS staging of one tile row: fp32 input columns -> split hi | lo -> canonical smem operand -> arrive on a_ready
@@ -390,31 +394,35 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
       const int K = op.K, k0 = op.st_k0;
       const bool div = a.a_div != 0.f;
       const float rdiv = div ? 1.f / a.a_div : 0.f;
-      // all of the thread's loads go out before the first one is consumed (K <= 128: at most 8 x 16 B per
-      // thread); a load -> split -> store loop exposed one DRAM latency per iteration
-      constexpr int MAXI = 128 / 4 / NSLICE;
-      float4 xs[MAXI];
+      // a batch of four 16-byte loads per thread goes out before the first one is consumed (a load -> split -> store loop
+      // exposed one DRAM latency per iteration); K <= 64 is one batch, K = 128 two (eight in flight cost 32 registers of
+      // the 96 and spilled the loop state of the row threads)
+      constexpr int BATCH = 4;
+#pragma unroll 1
+      for (int i0 = 0; NSLICE * i0 < (K >> 2); i0 += BATCH) {
+        float4 xs[BATCH];
 #pragma unroll
-      for (int i = 0; i < MAXI; ++i) {
-        const int k4 = sl + NSLICE * i, k = k0 + 4 * k4;
-        xs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lv && k4 < (K >> 2))
-          xs[i] = ldg_f4((k < a.k_src0) ? a.src0 + g_row * a.ld0 + k : a.src1 + g_row * a.ld1 + (k - a.k_src0));
-      }
+        for (int i = 0; i < BATCH; ++i) {
+          const int k4 = sl + NSLICE * (i0 + i), k = k0 + 4 * k4;
+          xs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lv && k4 < (K >> 2))
+            xs[i] = ldg_f4((k < a.k_src0) ? a.src0 + g_row * a.ld0 + k : a.src1 + g_row * a.ld1 + (k - a.k_src0));
+        }
 #pragma unroll
-      for (int i = 0; i < MAXI; ++i) {
-        const int k4 = sl + NSLICE * i;
-        if (k4 < (K >> 2)) {
-          float4 x = xs[i];
-          if (div) {                       // x / d as q0 = x r, q = q0 + (x - q0 d) r: the IEEE quotient without the
-            x.x = div_by(x.x, a.a_div, rdiv); x.y = div_by(x.y, a.a_div, rdiv);   // ~30-instruction div.rn sequence
-            x.z = div_by(x.z, a.a_div, rdiv); x.w = div_by(x.w, a.a_div, rdiv);   // (32 per thread and tile)
+        for (int i = 0; i < BATCH; ++i) {
+          const int k4 = sl + NSLICE * (i0 + i);
+          if (k4 < (K >> 2)) {
+            float4 x = xs[i];
+            if (div) {                       // x / d as q0 = x r, q = q0 + (x - q0 d) r: the IEEE quotient without the
+              x.x = div_by(x.x, a.a_div, rdiv); x.y = div_by(x.y, a.a_div, rdiv);   // ~30-instruction div.rn sequence
+              x.z = div_by(x.z, a.a_div, rdiv); x.w = div_by(x.w, a.a_div, rdiv);   // (32 per thread and tile)
+            }
+            uint4 h4, l4;
+            tf::split_tf32(x.x, h4.x, l4.x); tf::split_tf32(x.y, h4.y, l4.y);
+            tf::split_tf32(x.z, h4.z, l4.z); tf::split_tf32(x.w, h4.w, l4.w);
+            *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
+            *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
           }
-          uint4 h4, l4;
-          tf::split_tf32(x.x, h4.x, l4.x); tf::split_tf32(x.y, h4.y, l4.y);
-          tf::split_tf32(x.z, h4.z, l4.z); tf::split_tf32(x.w, h4.w, l4.w);
-          *reinterpret_cast<uint4*>(hi + tf::canon_off32(row, k4, 128)) = h4;
-          *reinterpret_cast<uint4*>(lo + tf::canon_off32(row, k4, 128)) = l4;
         }
       }
       fence_proxy_async_smem();
@@ -457,18 +465,20 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         float ai = 0.f, aj = 0.f;
 #pragma unroll
         for (int k4 = 8 * sl; k4 < 8 * sl + 8; k4 += 4) {
-          const float4 ni = *reinterpret_cast<const float4*>(pi + k4);
-          const float4 nj = *reinterpret_cast<const float4*>(pj + k4);
-          const float4 qi = *reinterpret_cast<const float4*>(pi + 32 + k4);
-          const float4 qj = *reinterpret_cast<const float4*>(pj + 32 + k4);
-          const float4 b0 = *reinterpret_cast<const float4*>(att + k4);
+          const ulonglong2 ni = *reinterpret_cast<const ulonglong2*>(pi + k4);
+          const ulonglong2 nj = *reinterpret_cast<const ulonglong2*>(pj + k4);
+          const ulonglong2 qi = *reinterpret_cast<const ulonglong2*>(pi + 32 + k4);
+          const ulonglong2 qj = *reinterpret_cast<const ulonglong2*>(pj + 32 + k4);
+          const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(att + k4);
           const float4 w1 = *reinterpret_cast<const float4*>(att + 32 + k4);
-          const float p0 = qi.x + qj.x + b0.x, p1 = qi.y + qj.y + b0.y;
-          const float p2 = qi.z + qj.z + b0.z, p3 = qi.w + qj.w + b0.w;
-          ai = fmaf(fmaxf(ni.x + p0, 0.f), w1.x, ai); aj = fmaf(fmaxf(nj.x + p0, 0.f), w1.x, aj);
-          ai = fmaf(fmaxf(ni.y + p1, 0.f), w1.y, ai); aj = fmaf(fmaxf(nj.y + p1, 0.f), w1.y, aj);
-          ai = fmaf(fmaxf(ni.z + p2, 0.f), w1.z, ai); aj = fmaf(fmaxf(nj.z + p2, 0.f), w1.z, aj);
-          ai = fmaf(fmaxf(ni.w + p3, 0.f), w1.w, ai); aj = fmaf(fmaxf(nj.w + p3, 0.f), w1.w, aj);
+          const unsigned long long p01 = tf::add2(tf::add2(qi.x, qj.x), b0.x), p23 = tf::add2(tf::add2(qi.y, qj.y), b0.y);
+          float i0, i1, i2, i3, j0, j1, j2, j3;
+          tf::upk2f(tf::add2(ni.x, p01), i0, i1); tf::upk2f(tf::add2(ni.y, p23), i2, i3);
+          tf::upk2f(tf::add2(nj.x, p01), j0, j1); tf::upk2f(tf::add2(nj.y, p23), j2, j3);
+          ai = fmaf(fmaxf(i0, 0.f), w1.x, ai); aj = fmaf(fmaxf(j0, 0.f), w1.x, aj);
+          ai = fmaf(fmaxf(i1, 0.f), w1.y, ai); aj = fmaf(fmaxf(j1, 0.f), w1.y, aj);
+          ai = fmaf(fmaxf(i2, 0.f), w1.z, ai); aj = fmaf(fmaxf(j2, 0.f), w1.z, aj);
+          ai = fmaf(fmaxf(i3, 0.f), w1.w, ai); aj = fmaf(fmaxf(j3, 0.f), w1.w, aj);
         }
         *reinterpret_cast<float2*>(part + (sl * 128 + row) * 2) = make_float2(ai, aj);
       }
@@ -488,15 +498,15 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
           const float si = 2.f * (ai + b1v);
           const float mx = (N > 1) ? fmaxf(si, 0.f) : si;
           const float ei = expf(si - mx);
-          wi = ei / (ei + static_cast<float>(N - 1) * expf(-mx)) * 2.f;
+          wi = ei * __frcp_rn(ei + static_cast<float>(N - 1) * expf(-mx)) * 2.f;   // e * rcp(d): within 1 ulp of e / d
           wj = 0.f;
         } else {
           const float si = ai + b1v, sj = aj + b1v;
           float mx = fmaxf(si, sj);
           if (N > 2) mx = fmaxf(mx, 0.f);
           const float ei = expf(si - mx), ej = expf(sj - mx);
-          const float den = ei + ej + static_cast<float>(N - 2) * expf(-mx);
-          wi = ei / den; wj = ej / den;
+          const float rden = __frcp_rn(ei + ej + static_cast<float>(N - 2) * expf(-mx));
+          wi = ei * rden; wj = ej * rden;
         }
       }
       s_wi = wi; s_wj = wj; s_li = li; s_lj = lj;
@@ -505,7 +515,7 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
     // Part B: hidden = relu(w_i Y_i + w_j Y_j + b), this slice's 32 of the 128 columns -> tensor memory (hi | lo) as the A
     // operand of `op`; then the node block is refilled for the tile after `t`.
     auto pair_stage_b = [&](const Op& op, long long t, bool tr, unsigned long long* trp) {
-      const float wi = s_wi, wj = s_wj;
+      const unsigned long long wi2 = tf::pk2f(s_wi, s_wi), wj2 = tf::pk2f(s_wj, s_wj);
       const float* yi = ny + s_li * YLD + 32 * sl;
       const float* yj = ny + s_lj * YLD + 32 * sl;
       const float* yb = aux + a.yb_off + 32 * sl;
@@ -514,13 +524,16 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         uint32_t hv[16], lv[16];
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const float4 u = *reinterpret_cast<const float4*>(yi + 16 * half + 4 * q4);
-          const float4 v = *reinterpret_cast<const float4*>(yj + 16 * half + 4 * q4);
-          const float4 bb = *reinterpret_cast<const float4*>(yb + 16 * half + 4 * q4);
-          tf::split_tf32(fmaxf(fmaf(wi, u.x, fmaf(wj, v.x, bb.x)), 0.f), hv[4 * q4], lv[4 * q4]);
-          tf::split_tf32(fmaxf(fmaf(wi, u.y, fmaf(wj, v.y, bb.y)), 0.f), hv[4 * q4 + 1], lv[4 * q4 + 1]);
-          tf::split_tf32(fmaxf(fmaf(wi, u.z, fmaf(wj, v.z, bb.z)), 0.f), hv[4 * q4 + 2], lv[4 * q4 + 2]);
-          tf::split_tf32(fmaxf(fmaf(wi, u.w, fmaf(wj, v.w, bb.w)), 0.f), hv[4 * q4 + 3], lv[4 * q4 + 3]);
+          const ulonglong2 u = *reinterpret_cast<const ulonglong2*>(yi + 16 * half + 4 * q4);
+          const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(yj + 16 * half + 4 * q4);
+          const ulonglong2 bb = *reinterpret_cast<const ulonglong2*>(yb + 16 * half + 4 * q4);
+          float x0, x1, x2, x3;
+          tf::upk2f(tf::fma2(wi2, u.x, tf::fma2(wj2, v.x, bb.x)), x0, x1);
+          tf::upk2f(tf::fma2(wi2, u.y, tf::fma2(wj2, v.y, bb.y)), x2, x3);
+          tf::split_tf32(fmaxf(x0, 0.f), hv[4 * q4], lv[4 * q4]);
+          tf::split_tf32(fmaxf(x1, 0.f), hv[4 * q4 + 1], lv[4 * q4 + 1]);
+          tf::split_tf32(fmaxf(x2, 0.f), hv[4 * q4 + 2], lv[4 * q4 + 2]);
+          tf::split_tf32(fmaxf(x3, 0.f), hv[4 * q4 + 3], lv[4 * q4 + 3]);
         }
         tf::tmem_st16(tmem_row + op.a_col + 32 * sl + 16 * half, hv);
         tf::tmem_st16(tmem_row + op.a_col + 128 + 32 * sl + 16 * half, lv);
@@ -551,8 +564,23 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
         // (by slice = block mod 4) instead of once per element — a third of the rounds at T = 6 or 10
         const unsigned long long e0 =
             (static_cast<unsigned long long>(a.scene_offset) * a.E + static_cast<unsigned long long>(g_row)) * T;
-        const unsigned long long b_last = (e0 + T - 1) >> 2;
-        for (unsigned long long bk = (e0 >> 2) + sl; bk <= b_last; bk += NSLICE) {
+        const unsigned long long b_first = e0 >> 2, b_last = (e0 + T - 1) >> 2;
+        if (b_last - b_first <= 1) {
+          // <= 2 blocks (T <= 6): a thread's critical path is what counts here (the row warps run in lock step, ~8 clk per
+          // dependent instruction), so each block is generated by TWO slices and each draws two of its four elements
+          const unsigned long long bk = b_first + (sl >> 1);
+          if (bk <= b_last) {
+            const uint4 blk = Philox::block(bk, static_cast<uint32_t>(a.stage_index), seed);
+            const uint32_t w0 = (sl & 1) ? blk.z : blk.x, w1 = (sl & 1) ? blk.w : blk.y;
+            const unsigned long long el = bk * 4 + 2 * (sl & 1);
+            if (el >= e0 && el < e0 + T)
+              ybuf[row * 17 + static_cast<int>(el - e0)] = gumbel_from_uniform(static_cast<float>(w0 >> 8) * (1.0f / 16777216.0f));
+            if (el + 1 >= e0 && el + 1 < e0 + T)
+              ybuf[row * 17 + static_cast<int>(el + 1 - e0)] = gumbel_from_uniform(static_cast<float>(w1 >> 8) * (1.0f / 16777216.0f));
+          }
+          return;
+        }
+        for (unsigned long long bk = b_first + sl; bk <= b_last; bk += NSLICE) {
           const uint4 blk = Philox::block(bk, static_cast<uint32_t>(a.stage_index), seed);
           const uint32_t wv[4] = {blk.x, blk.y, blk.z, blk.w};
 #pragma unroll
@@ -573,19 +601,20 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
 
     int titer = 0;
     for (long long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++titer) {
-      const bool tr = a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && tid == 0;
+      const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && titer < TR_TILES && tid == 0;
       unsigned long long* trp = a.trace + titer * TR_SLOTS + TR_ROWS;
       const long long tscene = tps ? static_cast<long long>(static_cast<uint32_t>(tile) / static_cast<uint32_t>(tps)) : 0;
       const int tchunk = tps ? static_cast<int>(tile - tscene * tps) : 0;
       const long long grow = tps ? tscene * a.E + tchunk * 128 + row : tile * 128 + row;
       const bool live = grow < a.R && (!tps || tchunk * 128 + row < a.E);
       float carry = 0.f;
-      if ((a.pro_op >= 0 || a.stage_first >= 0) && a.edge_feat != nullptr) tile_noise(grow, live);   // ybuf is free: the previous tile ended on a barrier
+      if (HAS_DOTG && (a.pro_op >= 0 || a.stage_first >= 0) && a.edge_feat != nullptr) tile_noise(grow, live);   // ybuf is free: the previous tile ended on a barrier
       const bool has_next = tile + gridDim.x < a.ntiles;
 
       for (int e = 0; e < a.nev; ++e) {
         const Op& op = a.ops[a.ev_op[e]];
-        if (tr) trp[3 * e] = clock64();
+        long long ev_t0 = 0;
+        if (tr) { ev_t0 = clock64(); trp[3 * e] = ev_t0; }
         if (a.ev_type[e] == EV_PAIR_A_NEXT || a.ev_type[e] == EV_PAIR_B_NEXT) {
           // the NEXT tile's fused node2edge, inside this tile's MMA waits (the op is skipped by the issuer on a CTA's
           // last tile, and so is the arrival)
@@ -593,14 +622,14 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
             if (a.ev_type[e] == EV_PAIR_A_NEXT) pair_stage_a(tile + gridDim.x, tr, trp);
             else pair_stage_b(op, tile + gridDim.x, tr, trp);
           }
-          if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
+          if (tr) { trp[3 * e + 1] = ev_t0; trp[3 * e + 2] = clock64(); }
           continue;
         }
         if (a.ev_type[e] == EV_STAGE_NEXT) {
           const long long nt = tile + gridDim.x;
           const long long gn = nt * 128 + row;
           stage_rows(op, gn, nt < a.ntiles && gn < a.R);
-          if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
+          if (tr) { trp[3 * e + 1] = ev_t0; trp[3 * e + 2] = clock64(); }
           continue;
         }
         if (a.ev_type[e] == EV_STAGE) {
@@ -610,15 +639,15 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
           } else {
             stage_rows(op, grow, live);
           }
-          if (tr) { trp[3 * e + 1] = trp[3 * e]; trp[3 * e + 2] = clock64(); }
-          if (e == 0 && a.rs != nullptr) {
+          if (tr) { trp[3 * e + 1] = ev_t0; trp[3 * e + 2] = clock64(); }
+          if (HAS_RS && e == 0 && a.rs != nullptr) {
             // this row's per-row scales (edge_feat / S) -> shared memory, once per tile: every slice of the row needs them
             // in every drain, and without an L1 each global read is an L2 round trip
             row_bar();                                    // the previous tile's drains are done with the buffer
             for (int t = sl; t < a.rs_n; t += NSLICE) ybuf[row * 17 + t] = live ? __ldg(a.rs + grow * a.rs_ld + t) : 0.f;
             row_bar();
           }
-          if (e == 0 && a.edge_feat != nullptr) tile_noise(grow, live);   // while the first GEMM runs
+          if (HAS_DOTG && e == 0 && a.edge_feat != nullptr) tile_noise(grow, live);   // while the first GEMM runs
           continue;
         }
 
@@ -695,11 +724,12 @@ chain_tf32_kernel(const __grid_constant__ Args a) {
               for (int t = 0; t < TMAX; ++t) {
                 if (t < T) { lg[t] = __expf(lg[t] - mx); den += lg[t]; }
               }
-              const float factor = 1.f / (1.f + __expf(-(lg[XW - 1] + aux[a.gb_off + T])));
+              const float factor = __frcp_rn(1.f + __expf(-(lg[XW - 1] + aux[a.gb_off + T])));
+              const float rden = __frcp_rn(den);              // e * rcp(den): within 1 ulp of e / den
 #pragma unroll
               for (int t = 0; t < TMAX; ++t) {
                 if (t >= t0 && t < t0 + tq && t < T) {
-                  const float dd = lg[t] / den;
+                  const float dd = lg[t] * rden;
                   if (a.dist_out != nullptr) a.dist_out[static_cast<size_t>(grow) * T + t] = dd;
                   a.edge_feat[static_cast<size_t>(grow) * T + t] = factor * dd;
                 }
@@ -956,14 +986,20 @@ static int launch(Builder& b, long long R, long long ntiles, const unsigned char
   uint32_t need = 0;
   for (int o = 0; o < a.nops; ++o)
     if (a.ops[o].signal && a.ops[o].drain != DR_NONE) need |= a.ops[o].drain == DR_DOTG ? (1u << DV_COUNT) : (1u << a.ops[o].variant);
+  // the kernel instances compile the noise / per-row-scale staging in only next to the drains that consume them
+  if (a.edge_feat != nullptr && !(need & (1u << DV_COUNT))) return GN_E_SHAPE;
+  if (a.rs != nullptr && !(need & ((1u << DV_TMEM_RELU_RS) | (1u << DV_STORE_BM)))) return GN_E_SHAPE;
   void (*kern)(Args) = nullptr;
+  const bool trc = a.trace != nullptr;
+#define GN_KERN(P, M) (trc ? chain_tf32_kernel<P, M, true> : chain_tf32_kernel<P, M, false>)
   if (a.stage_mode == ST_PAIR) {
     if (need & ~VM_CHAIN) return GN_E_SHAPE;
-    kern = chain_tf32_kernel<true, VM_CHAIN>;
-  } else if (!(need & ~VM_NODE)) kern = chain_tf32_kernel<false, VM_NODE>;
-  else if (!(need & ~VM_HAGG)) kern = chain_tf32_kernel<false, VM_HAGG>;
-  else if (!(need & ~VM_CHAIN)) kern = chain_tf32_kernel<false, VM_CHAIN>;
-  else kern = chain_tf32_kernel<false, VM_ALL>;
+    kern = GN_KERN(true, VM_CHAIN);
+  } else if (!(need & ~VM_NODE)) kern = GN_KERN(false, VM_NODE);
+  else if (!(need & ~VM_HAGG)) kern = GN_KERN(false, VM_HAGG);
+  else if (!(need & ~VM_CHAIN)) kern = GN_KERN(false, VM_CHAIN);
+  else kern = GN_KERN(false, VM_ALL);
+#undef GN_KERN
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int grid = ntiles < GN_SM_COUNT ? static_cast<int>(ntiles) : GN_SM_COUNT;

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_tf32.py -x -q 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_tf32.py -x -q 2>&1 | tail -2
 timeout 300 python bench.py --only --no-cpu-baseline --steps 20 > gpurun_out/exp_vm.json 2> gpurun_out/exp_vm.err
 python - <<'PY'
 import json
@@ -7,4 +7,3 @@ d=json.loads([l for l in open("gpurun_out/exp_vm.json").read().splitlines() if l
 print(d["value"], d["ms_per_step"])
 for k,v in d.get("kernels", {}).items(): print(k, v["ms_per_step"])
 PY
-timeout 120 python profiles/trace_tf32.py hyper 2>&1 | grep -A6 "tile iter 3"
