@@ -139,6 +139,8 @@ __device__ __forceinline__ void relu_sum_n(int N, float* Ps, const float* sym, i
 }
 
 // 18 warps: 5 on one scheduler partition (16 K registers each) caps a thread at 96 registers
+// TRACE: the clock64 phase stamps (profiles/trace_pair_agg_tf32.py) are compiled in
+template <bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 pair_agg_tf32_kernel(const __grid_constant__ Args a) {
   using namespace tc;
@@ -277,7 +279,7 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
       const size_t grow0 = static_cast<size_t>(b0s) * N;
       const bool live = row < nv;
       const int titer = (tile - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x);
-      const bool tr = a.trace != nullptr && blockIdx.x == 0 && tid == 0 && titer < TR_TILES;
+      const bool tr = TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == 0 && titer < TR_TILES;
       unsigned long long* trp = a.trace + titer * TR_SLOTS;
       if (tr) trp[0] = clock64();
 
@@ -402,7 +404,7 @@ pair_agg_tf32_kernel(const __grid_constant__ Args a) {
         mbar_arrive(&bars->g_ready);
       };
       const bool is_drain = warp >= SCENE_WARPS;
-      const bool trd = a.trace != nullptr && blockIdx.x == 0 && tid == SCENE_WARPS * 32 && titer < TR_TILES;
+      const bool trd = TRACE && a.trace != nullptr && blockIdx.x == 0 && tid == SCENE_WARPS * 32 && titer < TR_TILES;
       if (is_drain) r1(0);
       row_bar();
       for (int u = 0; u < U; ++u) {
@@ -511,13 +513,14 @@ int launch_pair_agg_tf32(const float* h, const float* edge_feat, int B, int N, i
     a.off_raw = align_up(smem, 16);
     smem = a.off_raw + raw_bytes;
   }
-  cudaError_t e = cudaFuncSetAttribute(pair_agg_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  void (*kern)(Args) = a.trace != nullptr ? pair_agg_tf32_kernel<true> : pair_agg_tf32_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
   const int ntiles = (B + a.SC - 1) / a.SC;
   const int grid = ntiles < GN_SM_COUNT ? ntiles : GN_SM_COUNT;
   {
     ProfScope ps__("pair_agg_tf32", st);
-    cudaError_t le = launch_pdl(pair_agg_tf32_kernel, dim3(grid), dim3(THREADS), smem, st, a);
+    cudaError_t le = launch_pdl(kern, dim3(grid), dim3(THREADS), smem, st, a);
     if (le != cudaSuccess) return static_cast<int>(le);
   }
   GN_LAUNCH_CHECK();
