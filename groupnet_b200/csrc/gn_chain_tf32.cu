@@ -130,10 +130,10 @@ __device__ __forceinline__ void drain_slice(const Args& a, const Op& op, const f
                                             uint32_t tmem_row, int sl, long long grow, bool live, float& carry) {
   const int w = op.dn / NSLICE;
   uint32_t r0[16];
-  tf::tmem_ld16_nowait(tmem_row + op.acc_col + sl * w, r0);
+  tf::tmem_ld16_nowait(tmem_row + op.drain_col + sl * w, r0);
   if (w == 32) {
     uint32_t r1[16];
-    tf::tmem_ld16_nowait(tmem_row + op.acc_col + sl * w + 16, r1);
+    tf::tmem_ld16_nowait(tmem_row + op.drain_col + sl * w + 16, r1);
     tc::tmem_ld_wait();
     drain_pass<KIND, RELU, RS>(a, op, aux, rsb, r0, tmem_row, sl * w, grow, live, carry);
     drain_pass<KIND, RELU, RS>(a, op, aux, rsb, r1, tmem_row, sl * w + 16, grow, live, carry);
@@ -805,7 +805,7 @@ struct Builder {
     o.a_src = static_cast<short>(a_src);
     if (a_src == A_SMEM) o.a_buf = static_cast<short>(a_buf_or_col); else o.a_col = static_cast<short>(a_buf_or_col);
     o.K = static_cast<short>(K); o.N = static_cast<short>(N); o.kc = static_cast<short>(chunk_k(N, K));
-    o.acc_col = static_cast<short>(acc_col); o.accumulate = static_cast<short>(accumulate);
+    o.acc_col = static_cast<short>(acc_col); o.drain_col = -1; o.accumulate = static_cast<short>(accumulate);
     o.wait_n = static_cast<short>(wait_n); o.signal = static_cast<short>(signal);
     o.rs_idx = -1; o.bias_off = -1;
     o.w_off = static_cast<int>(wbytes);
@@ -861,6 +861,7 @@ static int validate_program(Args& a) {
   int waits = 0, signals = 0;
   for (int o = 0; o < a.nops; ++o) {
     Op& op = a.ops[o];
+    if (op.drain_col < 0) op.drain_col = op.acc_col;        // the default: an op's drain reads its own accumulator
     if (op.N < 16 || op.N > 256 || (op.N & 15) || op.K < 8 || (op.K & 7) || op.kc < 8 || (op.kc & 7) || op.K % op.kc) return GN_E_SHAPE;
     if (static_cast<uint32_t>(op.N) * op.kc * 8 > a.stage_bytes) return GN_E_SHAPE;
     if (op.acc_col < 0 || op.acc_col + op.N > 512) return GN_E_SHAPE;
@@ -868,7 +869,9 @@ static int validate_program(Args& a) {
     if (op.a_src == A_SMEM && (static_cast<uint32_t>(op.K) * 128 * 4 > a.a0_half_bytes || op.K > 128)) return GN_E_SHAPE;
     if (op.signal) {
       if (op.drain == DR_DOTG) { if (op.dn != 128 || op.dst_col < 0 || op.dst_col + 16 * NSLICE > 512 || a.w4_off < 0) return GN_E_SHAPE; }
-      else if (op.drain != DR_NONE && ((op.dn != 64 && op.dn != 128) || op.dn > op.N)) return GN_E_SHAPE;   // NSLICE x 16 / 32
+      else if (op.drain != DR_NONE && ((op.dn != 64 && op.dn != 128) || (op.drain_col == op.acc_col && op.dn > op.N))) return GN_E_SHAPE;   // NSLICE x 16 / 32
+      if (op.drain_col != op.acc_col && (op.drain_col < 0 || op.drain_col + op.dn > 512 || op.nsum > 1 ||
+                                         op.drain == DR_DOT || op.drain == DR_DOTG)) return GN_E_SHAPE;
       if (op.nsum > 1 && (op.sum_stride < op.dn || op.acc_col + (op.nsum - 1) * op.sum_stride + op.dn > 512)) return GN_E_SHAPE;
       if ((op.drain == DR_TMEM || op.drain == DR_TMEM_STORE) && (op.dst_col < 0 || op.dst_col + 2 * op.dn > 512)) return GN_E_SHAPE;
       if ((op.drain == DR_STORE || op.drain == DR_TMEM_STORE) &&
@@ -1118,7 +1121,6 @@ int launch_edge_chain_tf32(bool pair, const float* edges, const float* ypre, con
 
 // ---- node prologue: x' = node2edge_start_mlp(h) (D -> 256 -> 64, :84,:125), pq = split attention layer 0 (:80,:134)
 // the 256-wide hidden layer runs as two 128-column halves feeding the second Linear as two K = 128 chunks
-// TMEM columns: acc 0 | A_hid 128,256 | acc_x 384 | A_x 0,64 | acc_pq 448
 bool node_pre_tf32_fits(int D) { return D >= 8 && D <= 128 && (D & 7) == 0; }
 
 int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weights* w, float* xprime, float* pq,
@@ -1127,26 +1129,36 @@ int launch_node_pre_tf32(const float* h, long long R, int D, const gn_stage_weig
   if (R <= 0) return GN_OK;
   Builder b(D, 1, false, false);
   Args& a = b.a;
+  // Both halves of the 256-wide hidden layer are issued back to back (accumulators 0 and 384), so the second one runs
+  // while the row threads drain the first; the second Linear's first K chunk then accumulates over the drained
+  // accumulator (0..63) and SIGNALS for the second half's drain (drain_col 384): by then it has finished reading the
+  // hidden operand that drain overwrites.  x' is split in place (0..127); pq and Y accumulate over the dead hidden operand.
+  // TMEM columns: acc_a 0 | acc_b 384 | A_hid 128,256 | acc_x 0 -> A_x 0,64 | acc_Y 128 | acc_pq 256
+  const int w0_bytes = 128 * D * 8, w1_bytes = 64 * 128 * 8;
   Op& s0a = b.add(A_SMEM, 0, D, 128, 0, 0, 1, 1);
   b.drain_tmem(s0a, 128, 1, w->node_b0, 128, 1);
-  b.add(A_TMEM, 128, 128, 64, 384, 0, 1, 0);
-  Op& s0b = b.add(A_SMEM, 0, D, 128, 0, 0, 0, 1);
-  b.drain_tmem(s0b, 128, 1, w->node_b0 + 128, 128, 1);
-  Op& s1b = b.add(A_TMEM, 128, 128, 64, 384, 1, 1, 1);
+  Op& s0b = b.add(A_SMEM, 0, D, 128, 384, 0, 0, 0);
+  Op& s1a = b.add(A_TMEM, 128, 128, 64, 0, 0, 1, 1);
+  b.drain_tmem(s1a, 128, 1, w->node_b0 + 128, 128, 1);
+  s1a.drain_col = 384;
+  Op& s1b = b.add(A_TMEM, 128, 128, 64, 0, 1, 1, 1);
   s1b.drain = DR_TMEM_STORE; s1b.dn = 64; s1b.relu = 0; b.set_bias(s1b, w->node_b1, 64); s1b.dst_col = 0; s1b.arrive = 1;
   s1b.out = xprime; s1b.ldo = 64; s1b.out_col0 = 0;
-  Op& s2 = b.add(A_TMEM, 0, 64, 64, 448, 0, 1, 1);
+  Op& s2 = b.add(A_TMEM, 0, 64, 64, 256, 0, 1, 1);
   b.drain_store(s2, 64, 0, nullptr, pq, 64, 0, 0);
-  // the staged h tile is read by ops 0 and 2: once the drain of op 2 has seen its accumulator the buffer is free, and the
-  // next tile's rows are staged while the rest of the chain runs
-  // (after the drain of op 3: the issuer consumes a_ready arrivals in op order, and the staging arrival belongs to
-  // the NEXT tile's first op, so it must follow the last arriving drain of this tile)
+  // the stream is packed W0[:128] | W1[:, :128] | W0[128:] | W1[:, 128:] | pq | Y (packing.py): fix the offsets
+  s0a.w_off = 0; s1a.w_off = w0_bytes; s0b.w_off = w0_bytes + w1_bytes; s1b.w_off = 2 * w0_bytes + w1_bytes;
+  s2.w_off = 2 * w0_bytes + 2 * w1_bytes;
+  // the staged h tile is read by ops 0 and 1: both have completed before the first drain event returns.  The next tile's
+  // rows are staged after the drain of op 3: the issuer consumes a_ready arrivals in op order, and the staging arrival
+  // belongs to the NEXT tile's first op, so it must follow the last arriving drain of this tile
   a.stage_first = 0;
   b.ev(EV_DRAIN, 0); b.ev(EV_DRAIN, 2); b.ev(EV_DRAIN, 3); b.ev(EV_STAGE_NEXT, 0); b.ev(EV_DRAIN, 4);
   if (ypre != nullptr) {
     // pairwise layers: Y = x' W_init0^T (no bias), the per-node half of init_MLP's first Linear (see the edge chain)
     Op& s3 = b.add(A_TMEM, 0, 64, 128, 128, 0, 0, 1);
     b.drain_store(s3, 128, 0, nullptr, ypre, 128, 0, 0);
+    s3.w_off = 2 * w0_bytes + 2 * w1_bytes + 64 * 64 * 8;
     b.ev(EV_DRAIN, 5);
   }
   a.stage_mode = ST_ROWS; a.src0 = h; a.ld0 = D; a.k_src0 = D;

@@ -43,6 +43,7 @@ struct Op {
   short a_buf, a_col;
   short K, N, kc;
   short acc_col;
+  short drain_col;    // accumulator columns the drain reads (acc_col unless the op signals for an EARLIER op's accumulator)
   short accumulate;   // first MMA adds onto the accumulator's content
   short wait_n;       // a_ready phases the issuer consumes before issuing
   short signal;       // commit acc_ready afterwards (a DRAIN event consumes it)
