@@ -9,6 +9,8 @@ python bench.py --workload fishops --steps 10 > gpurun_out/bench_r2_final_fishop
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tf32|node2edge|edge2node|corr_topk" -c 120 --csv --log-file gpurun_out/launches_r2_final_tf32.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --only > gpurun_out/ncu1.log 2>&1
 ncu --set full --clock-control none -k regex:"tf32|node2edge|edge2node|corr_topk" -s 51 -c 17 -o /tmp/prof_r2_final_tf32_step python bench.py --steps 2 --warmup 3 --no-cpu-baseline --only > gpurun_out/ncu2.log 2>&1
 python profiles/summarize_ncu.py /tmp/prof_r2_final_tf32_step.ncu-rep > gpurun_out/ncu_full_r2_final_tf32_nba.txt   # the report itself exceeds what gpurun copies back
+python profiles/ncu_pipes.py /tmp/prof_r2_final_tf32_step.ncu-rep > gpurun_out/ncu_pipes_r2_final_tf32_nba.txt          # issue slots, pipes, stall reasons per launch
+python profiles/tf32_error_margin.py > gpurun_out/tf32_error_margin_r2.txt 2>&1
 for f in gpurun_out/bench_r2_final_*.json; do python - "$f" <<'PY'
 import json,sys
 try:

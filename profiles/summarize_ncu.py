@@ -13,7 +13,10 @@ want = [
     ("tensor pipe active % (realtime)", "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed"),
     ("tensor-memory (operand fetch) cycles active %", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"),
     ("tmem pipe inst % ", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active"),
-    ("issue active %", "smsp__issue_active.avg.pct"),
+    ("issue slots used %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+    ("fma pipe inst %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+    ("alu pipe inst %", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+    ("local-memory (spill) load requests", "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum"),
     ("warps active % of peak", "sm__warps_active.avg.pct_of_peak_sustained_active"),
     ("sm throughput %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
     ("lsu shared wavefronts % of peak", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
