@@ -1041,11 +1041,12 @@ def main():
         """One full measurement of a precision path: device-resident throughput (CUDA events, max over ranks),
         per-kernel durations, roofline of its dominant kernel, and the end-to-end figure through forward_host."""
         model.set_precision(precision)
-        # x slice of final_feature: the fp32-grade path is compute-bound end to end, so the launch thread must not
-        # spend time copying on the host ("device": the GPU writes the slice, whole rows go back); the bf16 path is
-        # PCIe-bound, so it saves the 25 % of D2H bytes ("host") — profiles/e2e_sweep.py
+        # x slice of final_feature: both tensor-core paths are PCIe-bound end to end (10.4 / 5.2 ms of kernels against
+        # >= 11 ms of copies), so the host fills the x columns itself and 25 % of the D2H bytes stay home ("host":
+        # 14.0 ms against 17.0 ms with "device" on the fp32-grade path, profiles/e2e_sweep.py); the FFMA path is
+        # compute-bound and keeps the launch thread free ("device": the GPU writes the slice, whole rows go back)
         slice_mode = os.environ.get("GN_E2E_INPUT_SLICE") or (
-            "host" if (torch.get_num_threads() >= 16 and precision == "bf16") else "device")
+            "host" if (torch.get_num_threads() >= 16 and precision in ("bf16", "tf32")) else "device")
         d2h = b * n * (model.feature_width() - (d if slice_mode == "host" else 0)) * 4 + out_h.numel() * 4
         e2e_chunk = min(8192, max(1024, b // 4))      # >= 4 chunks per shard so copies and compute overlap
         with torch.no_grad():
