@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgroupnet_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 GN_MAX_AGENTS = 64
 GN_MAX_SCALES = 8
@@ -34,6 +34,8 @@ EXPORTS = (
     "gn_past_frontend",
     "gn_decoder_workspace_bytes",
     "gn_decoder_fwd",
+    "gn_decoder_tc_workspace_bytes",
+    "gn_decoder_fwd_tc",
     "gn_stage_saved_offsets",
     "gn_stage_bwd_workspace_bytes",
     "gn_stage_bwd",
@@ -74,6 +76,13 @@ class DecoderWeights(C.Structure):
     FIELDS = ("conv_w", "conv_b", "gru_wx", "gru_wh", "gru_b",
               "x_w0", "x_b0", "x_w1", "x_b1", "x_w2", "x_b2",
               "y_w0", "y_b0", "y_w1", "y_b1", "y_w2", "y_b2")
+    _fields_ = [(name, C.c_void_p) for name in FIELDS]
+
+
+class DecoderTcWeights(C.Structure):
+    """struct gn_decoder_tc_weights (14 device pointers, header order)."""
+    FIELDS = ("conv_w", "conv_b", "gru_w", "gru_b", "w0", "b0",
+              "x_w1", "x_b1", "x_w2", "x_b2", "y_w1", "y_b1", "y_w2", "y_b2")
     _fields_ = [(name, C.c_void_p) for name in FIELDS]
 
 
@@ -153,6 +162,12 @@ def load() -> C.CDLL:
         lib.gn_decoder_fwd.argtypes = [C.POINTER(DecoderWeights), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.gn_decoder_tc_workspace_bytes.restype = C.c_size_t
+        lib.gn_decoder_tc_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        lib.gn_decoder_fwd_tc.restype = C.c_int
+        lib.gn_decoder_fwd_tc.argtypes = [C.POINTER(DecoderTcWeights), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         lib.gn_stage_saved_offsets.restype = C.c_int
         lib.gn_stage_saved_offsets.argtypes = [C.POINTER(StageCfg), C.POINTER(C.c_size_t)]
         lib.gn_stage_bwd_workspace_bytes.restype = C.c_size_t

@@ -7,9 +7,10 @@ default weights and state_dict schema) and the same forward signature and output
                           past_traj (A, T_p, 2), cur_location (A, 1, 2), sample_num, mode='train')
         -> (out_seq (A*S, T_f, 2)  [(A, S, T_f, 2) when mode == 'inference'],  recover_pre_seq (A*S, T_p, 2))
 
-The forward is `gn_decoder_fwd` (csrc/gn_decoder_simt.cu, fp32 FFMA path): one kernel launch per
-DecomposeBlock; there is no PyTorch implementation of the math here.  Inference only in this round
-(no autograd through the decoder).
+The forward is `gn_decoder_fwd` (csrc/gn_decoder_simt.cu, fp32 FFMA path, 1e-5 parity: one kernel launch per
+DecomposeBlock) or, after `set_precision("bf16")`, `gn_decoder_fwd_tc` (csrc/gn_decoder_tc.cu, tcgen05 tensor cores,
+bf16 operands / fp32 accumulation, 2e-2 parity); there is no PyTorch implementation of the math here.  Inference
+only in this round (no autograd through the decoder).
 """
 from __future__ import annotations
 
@@ -20,7 +21,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .layers import MLP
-from .packing import PackCache, RuntimeStateMixin, pack_decoder_block
+from .packing import PackCache, RuntimeStateMixin, pack_decoder_block, pack_decoder_block_tc
 
 
 class DecomposeBlock(nn.Module):
@@ -64,10 +65,20 @@ class Decoder(RuntimeStateMixin, nn.Module):
         self.decompose = nn.ModuleList(
             [DecomposeBlock(self.args.past_length, self.args.future_length, input_dim)
              for _ in range(self.num_decompose)])
+        self.precision = "fp32"
         self._reset_runtime()
         self._install_runtime_hooks()
 
     _RUNTIME_ATTRS = ("_pack_key", "_packed", "_ws")
+
+    def set_precision(self, precision: str):
+        """"fp32": the FFMA kernel (1e-5 of the reference); "bf16": the tcgen05 path (2e-2)."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("Decoder precision must be 'fp32' or 'bf16'")
+        if precision != self.precision:
+            self.precision = precision
+            self.invalidate_packs()
+        return self
 
     def _reset_runtime(self) -> None:
         self.__dict__["_pack_key"] = None
@@ -75,13 +86,15 @@ class Decoder(RuntimeStateMixin, nn.Module):
         self.__dict__["_ws"] = ops.Workspace()
 
     def _packs(self, device):
-        key = PackCache._fingerprint(self, device)
+        tc = self.precision == "bf16"
+        key = (tc,) + tuple(PackCache._fingerprint(self, device))
         if key != self._pack_key:
-            tensors = [pack_decoder_block(blk, device) for blk in self.decompose]
-            structs = (_lib.DecoderWeights * len(tensors))()
+            pack, struct = (pack_decoder_block_tc, _lib.DecoderTcWeights) if tc else (pack_decoder_block, _lib.DecoderWeights)
+            tensors = [pack(blk, device) for blk in self.decompose]
+            structs = (struct * len(tensors))()
             for st, t in zip(structs, tensors):
-                for name in _lib.DecoderWeights.FIELDS:
-                    assert t[name].is_contiguous() and t[name].dtype == torch.float32
+                for name in struct.FIELDS:
+                    assert t[name].is_contiguous() and t[name].dtype in (torch.float32, torch.bfloat16)
                     setattr(st, name, C.c_void_p(t[name].data_ptr()))
             self._packed, self._pack_key = (tensors, structs), key
         return self._packed[1]
@@ -115,14 +128,20 @@ class Decoder(RuntimeStateMixin, nn.Module):
         if rows:
             lib = _lib.load()
             structs = self._packs(dev)
-            ws = self._ws.get(int(lib.gn_decoder_workspace_bytes(agents, s, self.past_length)), dev)
+            if self.precision == "bf16":
+                fn, name = lib.gn_decoder_fwd_tc, "gn_decoder_fwd_tc"
+                need = lib.gn_decoder_tc_workspace_bytes(agents, s, f_dim, z_dim, self.past_length, self.future_length)
+            else:
+                fn, name = lib.gn_decoder_fwd, "gn_decoder_fwd"
+                need = lib.gn_decoder_workspace_bytes(agents, s, self.past_length)
+            ws = self._ws.get(int(need), dev)
             with torch.cuda.device(dev):
-                rc = lib.gn_decoder_fwd(structs, len(self.decompose), C.c_void_p(pf.data_ptr()),
-                                        C.c_void_p(zz.data_ptr()), C.c_void_p(pt.data_ptr()), C.c_void_p(cl.data_ptr()),
-                                        agents, s, f_dim, z_dim, self.past_length, self.future_length,
-                                        C.c_void_p(out_seq.data_ptr()), C.c_void_p(recover.data_ptr()),
-                                        C.c_void_p(ws.data_ptr()), ws.numel(), ops._stream_ptr(dev))
-            _lib.check(rc, "gn_decoder_fwd")
+                rc = fn(structs, len(self.decompose), C.c_void_p(pf.data_ptr()),
+                        C.c_void_p(zz.data_ptr()), C.c_void_p(pt.data_ptr()), C.c_void_p(cl.data_ptr()),
+                        agents, s, f_dim, z_dim, self.past_length, self.future_length,
+                        C.c_void_p(out_seq.data_ptr()), C.c_void_p(recover.data_ptr()),
+                        C.c_void_p(ws.data_ptr()), ws.numel(), ops._stream_ptr(dev))
+            _lib.check(rc, name)
         if mode == 'inference':
             out_seq = out_seq.view(-1, s, *out_seq.shape[1:])
         return out_seq, recover

@@ -556,3 +556,52 @@ def pack_decoder_block(block, device: torch.device) -> Dict[str, torch.Tensor]:
         b2[:l2.bias.numel()] = dev(l2.bias)
         out[f"{tag}_b2"] = b2
     return out
+
+
+def pack_decoder_block_tc(block, device: torch.device) -> Dict[str, torch.Tensor]:
+    """Tensors of one `struct gn_decoder_tc_weights` (bf16 tensor-core decoder, csrc/gn_decoder_tc.cu) from a
+    DecomposeBlock (model/GroupNet_nba.py:13-46).  bf16 tensors are flat canonical operands ([K/8][N][8])."""
+
+    def dev(x):
+        return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    gru = block.encoder_past
+    if gru.hidden_size != DEC_STATE or gru.input_size != 32 or gru.num_layers != 1 or gru.bidirectional:
+        raise ValueError("decoder kernel is built for GRU(32 -> 96), one layer")
+    h = DEC_STATE
+    w_ih, w_hh = dev(gru.weight_ih_l0), dev(gru.weight_hh_l0)                     # (288, 32), (288, 96); gates r|z|n
+    # gate matrix over K = [e (32) | h (96)]: r and z see both, n_x only e, n_h only h (it is scaled by r in the drain)
+    rz = torch.cat([w_ih[:2 * h], w_hh[:2 * h]], dim=1)                           # (192, 128)
+    nx = torch.cat([w_ih[2 * h:], torch.zeros(h, h, device=device)], dim=1)       # (96, 128)
+    nh = torch.cat([torch.zeros(h, 32, device=device), w_hh[2 * h:]], dim=1)      # (96, 128)
+    out: Dict[str, torch.Tensor] = {}
+    out["conv_w"] = dev(block.conv_past.weight)
+    out["conv_b"] = dev(block.conv_past.bias)
+    out["gru_w"] = torch.cat([_canon(rz), _canon(torch.cat([nx, nh], dim=0))]).contiguous()
+    b_ih, b_hh = dev(gru.bias_ih_l0), dev(gru.bias_hh_l0)
+    gb = torch.zeros(4, DEC_GATE, dtype=torch.float32, device=device)
+    gb[0, :h] = b_ih[:h] + b_hh[:h]
+    gb[1, :h] = b_ih[h:2 * h] + b_hh[h:2 * h]
+    gb[2, :h] = b_ih[2 * h:]
+    gb[3, :h] = b_hh[2 * h:]
+    out["gru_b"] = gb
+    x0, x1, x2 = block.decoder_x.layers
+    y0, y1, y2 = block.decoder_y.layers
+    for l0, l1, l2 in ((x0, x1, x2), (y0, y1, y2)):
+        if l0.weight.shape[0] != 512 or l1.weight.shape != (256, 512) or l2.weight.shape[1] != 256 \
+                or l2.weight.shape[0] > 64 or l0.weight.shape[1] % 16:
+            raise ValueError("tensor-core decoder is built for MLPs in (multiple of 16) -> 512 -> 256 -> (<= 64)")
+    out["w0"] = _canon(torch.cat([dev(x0.weight), dev(y0.weight)], dim=0))
+    out["b0"] = torch.cat([dev(x0.bias), dev(y0.bias)]).contiguous()
+    for tag, l1, l2 in (("x", x1, x2), ("y", y1, y2)):
+        out[f"{tag}_w1"] = _canon(dev(l1.weight))
+        out[f"{tag}_b1"] = dev(l1.bias)
+        n_out = l2.weight.shape[0]
+        pad = _round_up(n_out, 16)
+        w2 = torch.zeros(pad, 256, dtype=torch.float32, device=device)
+        w2[:n_out] = dev(l2.weight)
+        b2 = torch.zeros(pad, dtype=torch.float32, device=device)
+        b2[:n_out] = dev(l2.bias)
+        out[f"{tag}_w2"] = _canon(w2)
+        out[f"{tag}_b2"] = b2
+    return out

@@ -28,8 +28,9 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 4     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams;
-                                 4: + tf_pagg_w (fused pairwise aggregation, csrc/gn_pair_agg_tf32.cu), gn_fish_* entry points */
+#define GN_ABI_VERSION 5     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams;
+                                 4: + tf_pagg_w (fused pairwise aggregation, csrc/gn_pair_agg_tf32.cu), gn_fish_* entry points;
+                                 5: + gn_decoder_fwd_tc (bf16 tensor-core decoder, csrc/gn_decoder_tc.cu) */
 
 #define GN_MAX_AGENTS 64      /* N <= 64: one 64-bit membership word per hyperedge */
 #define GN_MAX_SCALES 8
@@ -261,6 +262,35 @@ int gn_decoder_fwd(const gn_decoder_weights* blocks, int32_t num_blocks, const f
                    const float* past_traj, const float* cur_location, int64_t A, int32_t S, int32_t F, int32_t Z,
                    int32_t Tp, int32_t Tf, float* out_seq, float* recover, void* workspace, size_t workspace_bytes,
                    gn_stream_t stream);
+
+/* ---- trajectory decoder, bf16 tensor-core path (tcgen05, 2e-2 parity) --------------------------
+ * The same contract as gn_decoder_fwd (Decoder.forward, model/GroupNet_nba.py:461-505; DecomposeBlock.forward
+ * :48-79) with bf16 operands and fp32 accumulation: the GRU step as one K = 128 contraction per time step with
+ * the gate math in the accumulator drain (fp32 state), decoder_x / decoder_y as row-tile GEMMs.
+ * One gn_decoder_tc_weights per DecomposeBlock, packed by groupnet_b200/packing.py::pack_decoder_block_tc;
+ * "canonical" = the K-major no-swizzle UMMA operand layout [K/8][N][8] of bf16 (csrc/gn_tc.cuh). */
+typedef struct gn_decoder_tc_weights {
+  const float* conv_w;   /* conv_past.weight (32,2,3) as stored */
+  const float* conv_b;   /* (32) */
+  const void* gru_w;     /* bf16, two canonical [192 x 128] operands: rows (r | z), then (n_x | n_h); K = e (32) | h (96),
+                            zero blocks where a gate half does not see e or h */
+  const float* gru_b;    /* (4,128): b_ir+b_hr | b_iz+b_hz | b_in | b_hn, zero padded */
+  const void* w0;        /* bf16 canonical [(F+Z+96)/8][1024][8]: rows 0..511 decoder_x layer 0, 512..1023 decoder_y */
+  const float* b0;       /* (1024) */
+  const void* x_w1; const float* x_b1;   /* bf16 canonical [64][256][8], (256) */
+  const void* x_w2; const float* x_b2;   /* bf16 canonical [32][P][8], (P): P = 2*Tp rounded up to 16, zero rows */
+  const void* y_w1; const float* y_b1;
+  const void* y_w2; const float* y_b2;   /* P = 2*Tf rounded up to 16 */
+} gn_decoder_tc_weights;
+
+/* Bytes of device scratch gn_decoder_fwd_tc needs (x_hat, the bf16 feature rows and hidden activations). */
+size_t gn_decoder_tc_workspace_bytes(int64_t A, int32_t S, int32_t F, int32_t Z, int32_t Tp, int32_t Tf);
+
+/* Arguments as gn_decoder_fwd.  Limits: F % 8 == 0, Z % 8 == 0, (F + Z) % 16 == 0, Tp <= 32, Tf <= 32. */
+int gn_decoder_fwd_tc(const gn_decoder_tc_weights* blocks, int32_t num_blocks, const float* past_feature,
+                      const float* z, const float* past_traj, const float* cur_location, int64_t A, int32_t S,
+                      int32_t F, int32_t Z, int32_t Tp, int32_t Tf, float* out_seq, float* recover, void* workspace,
+                      size_t workspace_bytes, gn_stream_t stream);
 
 /* ---- training: backward of one stage (fp32) -------------------------------------------------
  * Gradients flow to h_in and to every parameter the forward uses; H, corr and the noise get none

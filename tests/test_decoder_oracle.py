@@ -258,6 +258,56 @@ def test_bf16_operand_plan_for_the_decoder_stays_inside_the_bf16_tolerance(name)
     assert_close(rec, g["recover_pre_seq"], 1e-2, f"{name} recover_pre_seq (bf16 plan)")
 
 
+def _uncanon(flat, n, k):
+    """flat canonical bf16 operand [K/8][N][8] -> (N, K) fp32."""
+    return flat.view(k // 8, n, 8).permute(1, 0, 2).reshape(n, k).float()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_tensor_core_decoder_packs_evaluate_to_the_reference(name):
+    """The host side of gn_decoder_fwd_tc: the algorithm of csrc/gn_decoder_tc.cu (gate matrix [r | z | n_x | n_h] over
+    K = [e | h], both first Linears as one 1024-row operand, zero-padded last Linears) evaluated on the PACKED bf16
+    tensors with bf16 operand rounding must reproduce the reference fixtures inside the bf16 bar."""
+    import torch.nn.functional as F
+    from groupnet_b200.packing import pack_decoder_block_tc
+    g = _load(name)
+    m = _schema(g)
+    s, tp, tf = g["sample_num"], g["past_length"], g["future_length"]
+    bf = lambda v: v.to(torch.bfloat16).float()
+    f = torch.cat((torch.from_numpy(g["past_feature_per_agent"]).repeat_interleave(s, 0), torch.from_numpy(g["z"])), 1)
+    x_true = torch.from_numpy(g["past_traj"]).repeat_interleave(s, 0)
+    x_hat, pred, rec = torch.zeros_like(x_true), 0.0, 0.0
+    kf = f.shape[1] + 96
+    with torch.no_grad():
+        for blk in m.decompose:
+            p = pack_decoder_block_tc(blk, torch.device("cpu"))
+            assert p["gru_w"].dtype == torch.bfloat16 and p["gru_w"].numel() == 2 * 192 * 128
+            wg = torch.cat([_uncanon(p["gru_w"][:192 * 128], 192, 128), _uncanon(p["gru_w"][192 * 128:], 192, 128)])
+            e = torch.relu(F.conv1d((x_true - x_hat).transpose(1, 2), p["conv_w"], p["conv_b"], padding=1)).transpose(1, 2)
+            h = torch.zeros(x_true.shape[0], 96)
+            for t in range(tp):
+                acc = bf(torch.cat([e[:, t], h], 1)) @ wg.t()                  # (R, 384): r | z | n_x | n_h
+                rg = torch.sigmoid(acc[:, :96] + p["gru_b"][0, :96])
+                zg = torch.sigmoid(acc[:, 96:192] + p["gru_b"][1, :96])
+                ng = torch.tanh(acc[:, 192:288] + p["gru_b"][2, :96] + rg * (acc[:, 288:] + p["gru_b"][3, :96]))
+                h = (1 - zg) * ng + zg * h
+            feat = bf(torch.cat((f, h), 1))
+            hid1 = bf(torch.relu(feat @ _uncanon(p["w0"], 1024, kf).t() + p["b0"]))
+            outs = []
+            for i, (tag, width) in enumerate((("x", tp), ("y", tf))):
+                hid2 = bf(torch.relu(hid1[:, 512 * i:512 * (i + 1)] @ _uncanon(p[f"{tag}_w1"], 256, 512).t() + p[f"{tag}_b1"]))
+                pad = p[f"{tag}_b2"].numel()
+                assert pad % 16 == 0 and pad >= 2 * width
+                o = hid2 @ _uncanon(p[f"{tag}_w2"], pad, 256).t() + p[f"{tag}_b2"]
+                assert torch.all(o[:, 2 * width:] == 0)
+                outs.append(o[:, :2 * width].reshape(-1, width, 2))
+            x_hat = outs[0]
+            pred, rec = pred + outs[1], rec + x_hat
+        out = pred + torch.from_numpy(g["cur_location"]).repeat_interleave(s, 0)
+    assert_close(out, torch.from_numpy(g["out_seq"]).reshape(out.shape), 1e-2, f"{name} out_seq (tc packs)")
+    assert_close(rec, g["recover_pre_seq"], 1e-2, f"{name} recover_pre_seq (tc packs)")
+
+
 # ---- randomized differential pin against the live reference (build container only) ---------------------
 try:
     from hypothesis import HealthCheck, given, settings, strategies as st

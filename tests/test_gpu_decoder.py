@@ -4,7 +4,7 @@ from the reference and against the CPU oracle.  fp32 c
 import pytest
 import torch
 
-from helpers import FP32_REL, assert_close
+from helpers import BF16_REL, FP32_REL, assert_close
 from oracle import decoder_oracle as DO
 from test_decoder_oracle import NAMES, _load, _schema
 
@@ -64,6 +64,60 @@ def test_decoder_vs_oracle(batch, agents, s, blocks, hidden, scales, zdim, tp, t
     assert_close(rec, ref_rec, FP32_REL, "recover_pre_seq")
     out2, rec2 = m(pf.to(DEV), z.to(DEV), batch, agents, past.to(DEV), cur.to(DEV), s, mode="inference")
     assert torch.equal(out, out2) and torch.equal(rec, rec2)          # the running sums restart on every call
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_decoder_bf16_tensor_core_path_vs_golden(name):
+    """gn_decoder_fwd_tc (tcgen05: GRU step as one MMA chain per time step, MLPs as row-tile GEMMs) against the
+    fixtures of the unmodified reference; bf16 criterion 2e-2 * max|ref|."""
+    g = _load(name)
+    m = _schema(g).to(DEV).set_precision("bf16")
+    s = g["sample_num"]
+    pf = torch.from_numpy(g["past_feature_per_agent"]).repeat_interleave(s, dim=0).to(DEV)
+    args = (pf, torch.from_numpy(g["z"]).to(DEV), g["batch"], g["agents"], torch.from_numpy(g["past_traj"]).to(DEV),
+            torch.from_numpy(g["cur_location"]).to(DEV), s)
+    out_seq, recover = m(*args, mode=g["mode"])
+    assert tuple(out_seq.shape) == g["out_seq"].shape and tuple(recover.shape) == g["recover_pre_seq"].shape
+    assert_close(out_seq, g["out_seq"], BF16_REL, f"{name} out_seq (bf16)")
+    assert_close(recover, g["recover_pre_seq"], BF16_REL, f"{name} recover_pre_seq (bf16)")
+    # the two paths share one module: switching back restores the 1e-5 path
+    out32, rec32 = m.set_precision("fp32")(*args, mode=g["mode"])
+    assert_close(out32, g["out_seq"], FP32_REL, f"{name} out_seq (fp32 after bf16)")
+    assert_close(rec32, g["recover_pre_seq"], FP32_REL, f"{name} recover_pre_seq (fp32 after bf16)")
+
+
+@pytest.mark.parametrize("batch,agents,s,blocks,hidden,scales,zdim,tp,tf", [
+    (7, 11, 20, 2, 64, [5, 11], 32, 5, 10),       # 1,540 rows: 12 full tiles + a ragged one
+    (1, 13, 5, 3, 32, [3], 16, 8, 12),            # 65 rows, three blocks, feature width 208 (K tail of 80)
+    (2, 8, 4, 1, 64, [2, 4, 8, 16], 32, 1, 32),   # single step GRU, widest output (64 columns), feature width 512
+    (180, 11, 10, 2, 64, [5, 11], 32, 5, 10),     # 19,800 rows = 155 tiles: more tiles than SMs
+])
+def test_decoder_bf16_tensor_core_path_vs_oracle(batch, agents, s, blocks, hidden, scales, zdim, tp, tf):
+    import groupnet_b200 as gb
+    import types
+    torch.manual_seed(batch + agents + s)
+    m = gb.Decoder(types.SimpleNamespace(hidden_dim=hidden, hyper_scales=scales, zdim=zdim, past_length=tp,
+                                         future_length=tf, num_decompose=blocks))
+    for blk in m.decompose:
+        torch.nn.init.normal_(blk.encoder_past.bias_ih_l0, std=0.3)
+        torch.nn.init.normal_(blk.encoder_past.bias_hh_l0, std=0.3)
+        torch.nn.init.normal_(blk.conv_past.bias, std=0.3)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    a = batch * agents
+    gen = torch.Generator().manual_seed(3)
+    pf = torch.randn(a, (2 + len(scales)) * hidden, generator=gen).repeat_interleave(s, dim=0)
+    z = torch.randn(a * s, zdim, generator=gen)
+    past = torch.randn(a, tp, 2, generator=gen)
+    cur = torch.randn(a, 1, 2, generator=gen)
+    ref_out, ref_rec = DO.decoder_forward(sd, pf, z, batch, agents, past, cur, s, past_len=tp, future_len=tf,
+                                          num_decompose=blocks, mode="inference")
+    m = m.to(DEV).set_precision("bf16")
+    out, rec = m(pf.to(DEV), z.to(DEV), batch, agents, past.to(DEV), cur.to(DEV), s, mode="inference")
+    assert tuple(out.shape) == (a, s, tf, 2)
+    assert_close(out, ref_out, BF16_REL, "out_seq (bf16)")
+    assert_close(rec, ref_rec, BF16_REL, "recover_pre_seq (bf16)")
+    out2, rec2 = m(pf.to(DEV), z.to(DEV), batch, agents, past.to(DEV), cur.to(DEV), s, mode="inference")
+    assert torch.equal(out, out2) and torch.equal(rec, rec2)
 
 
 def test_decoder_error_paths():
