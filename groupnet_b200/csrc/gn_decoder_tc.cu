@@ -3,11 +3,11 @@
 // model/GroupNet_nba.py:48-79 (DecomposeBlock.forward) and :461-505 (Decoder.forward); the math is the one
 // gn_decoder_simt.cu states.  Per DecomposeBlock:
 //
-//   decoder_gru_tc     tile = 128 rows (scene-agent x sample), 256 threads = 2 per row.  The GRU step is ONE
+//   decoder_gru_tc     tile = 128 rows (scene-agent x sample), 512 threads = 4 per row.  The GRU step is ONE
 //                      K = 128 contraction per time step: A = [e_t (32) | h (96)] as a bf16 operand in shared
 //                      memory, B = the resident gate matrix [r | z | n_x | n_h] (384 x 128, zero blocks where a
 //                      gate does not see e or h; two N = 192 MMAs chains), accumulators in 384 TMEM columns; the
-//                      gate math (sigmoid, tanh, blend) runs in the drain on the row's two threads, the state stays
+//                      gate math (sigmoid, tanh, blend) runs in the drain on the row's four threads, the state stays
 //                      fp32 in their registers and only its bf16 operand copy goes back to shared memory.  conv1d +
 //                      ReLU of the residual is evaluated per step while the operand is built.  Writes the bf16
 //                      feature row [past_feature | z | state] the MLPs read.
@@ -23,7 +23,7 @@
 namespace gn {
 
 namespace dtc {
-constexpr int TM = 128, THREADS = 256;
+constexpr int TM = 128, THREADS = 512;
 constexpr int CONV = 32, STATE = 96, KG = 128;            // K of the gate contraction: e_t | h
 constexpr int NG = 192;                                   // one gate operand: two gates of 96 rows
 constexpr int RES_LD = 65;                                // 2 * Tp <= 64 residual values per row (+1: bank spread)
@@ -47,7 +47,13 @@ struct DecGruArgs {
   int S, F, Z, Tp, first;
 };
 
-__device__ __forceinline__ float fast_sigmoid(float v) { return __frcp_rn(1.f + __expf(-v)); }
+// MUFU-based gate functions (ex2 / rcp / tanh approximations: ~1e-6 .. 5e-4 absolute, far inside the bf16 operand rounding)
+__device__ __forceinline__ float fast_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ float fast_tanh(float v) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(v));
@@ -67,7 +73,7 @@ decoder_gru_tc_kernel(DecGruArgs a) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int hf = warp >> 2;                                         // which half of the row's columns
+  const int hf = warp >> 2;                                         // which quarter of the row's columns
   const int row = (warp & 3) * 32 + lane;                           // tile row = TMEM lane
   const int Kf = a.F + a.Z + STATE, FZ = a.F + a.Z, tp2 = 2 * a.Tp;
 
@@ -118,17 +124,17 @@ decoder_gru_tc_kernel(DecGruArgs a) {
             make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
       }
     }
-    // h_0 = 0: the state half of the operand (k-groups 4 + 6 hf ..)
+    // h_0 = 0: the state part of the operand (this thread's k-groups 4 + 3 hf ..)
 #pragma unroll
-    for (int g8 = 0; g8 < 6; ++g8)
-      *reinterpret_cast<uint4*>(sA + canon_off(row, 4 + 6 * hf + g8, TM)) = make_uint4(0u, 0u, 0u, 0u);
-    float hreg[48];
+    for (int g8 = 0; g8 < 3; ++g8)
+      *reinterpret_cast<uint4*>(sA + canon_off(row, 4 + 3 * hf + g8, TM)) = make_uint4(0u, 0u, 0u, 0u);
+    float hreg[24];
 #pragma unroll
-    for (int j = 0; j < 48; ++j) hreg[j] = 0.f;
+    for (int j = 0; j < 24; ++j) hreg[j] = 0.f;
     __syncthreads();                                   // res complete
 
     for (int t = 0; t < a.Tp; ++t) {
-      // e_t = relu(conv1d(res)) for this thread's 16 of the 32 channels -> k-groups 2 hf, 2 hf + 1
+      // e_t = relu(conv1d(res)) for this thread's 8 of the 32 channels -> k-group hf
       {
         float xin[6];                                  // res[t-1], res[t], res[t+1] x (x, y); zero padding
 #pragma unroll
@@ -138,13 +144,13 @@ decoder_gru_tc_kernel(DecGruArgs a) {
           xin[kk] = in ? res[row * RES_LD + 2 * tt] : 0.f;
           xin[3 + kk] = in ? res[row * RES_LD + 2 * tt + 1] : 0.f;
         }
-        uint32_t pk[8];
+        uint32_t pk[4];
 #pragma unroll
-        for (int c2 = 0; c2 < 8; ++c2) {
+        for (int c2 = 0; c2 < 4; ++c2) {
           float e[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int c = 16 * hf + 2 * c2 + u;
+            const int c = 8 * hf + 2 * c2 + u;
             const float* wc = scw + c * 6;
             float acc = scb[c];
 #pragma unroll
@@ -156,8 +162,7 @@ decoder_gru_tc_kernel(DecGruArgs a) {
           }
           pk[c2] = pack_bf16_relu(e[0], e[1]);
         }
-        *reinterpret_cast<uint4*>(sA + canon_off(row, 2 * hf, TM)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(sA + canon_off(row, 2 * hf + 1, TM)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(sA + canon_off(row, hf, TM)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       fence_proxy_async_smem();
       fence_before_thread_sync();
@@ -173,41 +178,42 @@ decoder_gru_tc_kernel(DecGruArgs a) {
       }
       mbar_wait(mbar, phase); phase ^= 1;
       fence_after_thread_sync();
-      // gate math on this thread's 48 state columns [48 hf, 48 hf + 48), 16 at a time
+      // gate math on this thread's 24 state columns [24 hf, 24 hf + 24), 8 (= one operand k-group) at a time
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const int j0 = 48 * hf + 16 * c;
-        float vr[16], vz[16], vx[16], vh[16];
-        tmem_ld16(tmem_row + j0, vr);
-        tmem_ld16(tmem_row + STATE + j0, vz);
-        tmem_ld16(tmem_row + 2 * STATE + j0, vx);
-        tmem_ld16(tmem_row + 3 * STATE + j0, vh);
-        uint32_t pk[8];
+        const int j0 = 24 * hf + 8 * c;
+        uint32_t vr[8], vz[8], vx[8], vh[8];
+        tmem_ld8_nowait(tmem_row + j0, vr);
+        tmem_ld8_nowait(tmem_row + STATE + j0, vz);
+        tmem_ld8_nowait(tmem_row + 2 * STATE + j0, vx);
+        tmem_ld8_nowait(tmem_row + 3 * STATE + j0, vh);
+        tmem_ld_wait();
+        uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
+        for (int j = 0; j < 8; j += 2) {
           float hn[2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int col = j0 + j + u;
-            const float rg = fast_sigmoid(vr[j + u] + sgb[col]);
-            const float zg = fast_sigmoid(vz[j + u] + sgb[STATE + col]);
-            const float ng = fast_tanh(vx[j + u] + sgb[2 * STATE + col] + rg * (vh[j + u] + sgb[3 * STATE + col]));
-            const float hold = hreg[16 * c + j + u];
-            hn[u] = (1.f - zg) * ng + zg * hold;
-            hreg[16 * c + j + u] = hn[u];
+            const float rg = fast_sigmoid(__uint_as_float(vr[j + u]) + sgb[col]);
+            const float zg = fast_sigmoid(__uint_as_float(vz[j + u]) + sgb[STATE + col]);
+            const float ng = fast_tanh(__uint_as_float(vx[j + u]) + sgb[2 * STATE + col] +
+                                       rg * (__uint_as_float(vh[j + u]) + sgb[3 * STATE + col]));
+            const float hold = hreg[8 * c + j + u];
+            hn[u] = fmaf(zg, hold - ng, ng);           // (1 - z) n + z h
+            hreg[8 * c + j + u] = hn[u];
           }
           pk[j >> 1] = pack_bf16(hn[0], hn[1]);
         }
         // the MMAs of this step have completed (mbarrier): the operand buffer is free for h_t
-        *reinterpret_cast<uint4*>(sA + canon_off(row, 4 + 6 * hf + 2 * c, TM)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(sA + canon_off(row, 4 + 6 * hf + 2 * c + 1, TM)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        *reinterpret_cast<uint4*>(sA + canon_off(row, 4 + 3 * hf + c, TM)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
     }
-    // state -> feature columns [F + Z + 48 hf, + 48)
+    // state -> feature columns [F + Z + 24 hf, + 24)
     if (row < nrows) {
-      __nv_bfloat16* dst = a.feat + (row0 + row) * Kf + FZ + 48 * hf;
+      __nv_bfloat16* dst = a.feat + (row0 + row) * Kf + FZ + 24 * hf;
 #pragma unroll
-      for (int g8 = 0; g8 < 6; ++g8)
+      for (int g8 = 0; g8 < 3; ++g8)
         *reinterpret_cast<uint4*>(dst + 8 * g8) =
             make_uint4(pack_bf16(hreg[8 * g8], hreg[8 * g8 + 1]), pack_bf16(hreg[8 * g8 + 2], hreg[8 * g8 + 3]),
                        pack_bf16(hreg[8 * g8 + 4], hreg[8 * g8 + 5]), pack_bf16(hreg[8 * g8 + 6], hreg[8 * g8 + 7]));

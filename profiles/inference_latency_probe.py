@@ -33,8 +33,9 @@ def wall(fn, iters=200):
     return (time.perf_counter() - t0) * 1e6 / iters
 
 
-for precision in ("fp32", "tf32", "bf16"):
+for precision, dec_precision in (("fp32", "fp32"), ("tf32", "fp32"), ("bf16", "fp32"), ("tf32", "bf16"), ("bf16", "bf16")):
     enc._interaction_block().set_precision(precision)
+    dec.set_precision(dec_precision)
     for b in (1, 8):
         data = torch.randn(b, 11, 5, 2, device=DEV)
         enc._interaction_block().set_rng("cpu-compat")
@@ -43,5 +44,5 @@ for precision in ("fp32", "tf32", "bf16"):
         t_cpu = wall(lambda: g_cpu(data))
         g_dev = gb.GraphedInference(enc, dec, b, 11, rng="philox", seed=3)
         t_dev = wall(lambda: g_dev(data))
-        print(f"encoder {precision:5s} B={b}: eager {eager:8.1f} us | graph, CPU-generator noise {t_cpu:8.1f} us | "
+        print(f"encoder {precision:5s} decoder {dec_precision:5s} B={b}: eager {eager:8.1f} us | graph, CPU-generator noise {t_cpu:8.1f} us | "
               f"graph, device noise {t_dev:8.1f} us", flush=True)
