@@ -8,9 +8,10 @@
 // Structure: persistent CTAs of 256 threads = two independent 128-thread
 // groups.  Each group owns its own tile stream (tile = 128 rows), its own
 // shared-memory operand buffers, mbarrier and 256 TMEM columns, and runs
-//   for each 128-wide K chunk:  stage A (fp32|bf16 row-major -> bf16 canonical),
-//                               stage W (flat cp.async of the pre-arranged chunk),
-//                               one thread issues the chunk's tcgen05.mma's
+//   for each 64-wide K chunk:   stage A (fp32 row-major -> bf16 canonical through registers, or bf16 row-major
+//                               by cp.async), stage W (bulk copies of the pre-arranged chunk, mbarrier complete_tx),
+//                               one thread issues the chunk's tcgen05.mma's; two stages per group, so chunk g + 1
+//                               loads while chunk g multiplies and the next tile's first chunk under the epilogue
 //   epilogue: tcgen05.ld -> bias / ReLU / per-row scale / rank-T bias -> global
 // so one group's loads and epilogue overlap the other group's MMAs (the tensor
 // core executes both groups' instructions in issue order).
@@ -23,14 +24,16 @@
 namespace gn {
 
 namespace tclin {
-constexpr int KCH = 128;                               // K chunk
-constexpr uint32_t A_BYTES = 128 * KCH * 2;            // 32 KB
-constexpr uint32_t W_BYTES = 256 * KCH * 2;            // 64 KB
-constexpr uint32_t GRP_BYTES = A_BYTES + W_BYTES;
+constexpr int KCH = 64;                                // K chunk = one pipeline stage
+constexpr int NST = 2;                                 // stages per group: chunk g + 1 loads while chunk g multiplies
+constexpr uint32_t A_BYTES = 128 * KCH * 2;            // 16 KB
+constexpr uint32_t W_BYTES = 256 * KCH * 2;            // 32 KB
+constexpr uint32_t STG_BYTES = A_BYTES + W_BYTES;
+constexpr uint32_t GRP_BYTES = NST * STG_BYTES;        // 96 KB
 constexpr uint32_t OFF_BIAS = 2 * GRP_BYTES;           // bias[256] floats
 constexpr uint32_t OFF_BMAT = OFF_BIAS + 256 * 4;      // bias_mat[16][256] floats
-constexpr uint32_t OFF_BAR = OFF_BMAT + 16 * 256 * 4;  // 2 MMA mbarriers | tmem slot | 2 weight-copy mbarriers
-constexpr uint32_t SMEM_BYTES = OFF_BAR + 48;
+constexpr uint32_t OFF_BAR = OFF_BMAT + 16 * 256 * 4;  // MMA mbarriers [grp][stage] | weight-copy mbarriers [grp][stage] | tmem slot
+constexpr uint32_t SMEM_BYTES = OFF_BAR + 80;
 enum { MODE_PLAIN = 0, MODE_ROWSCALE = 1, MODE_BIASMAT = 2 };
 }  // namespace tclin
 
@@ -76,13 +79,12 @@ tc_linear_kernel(TcLinArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127;
   const int q = (gtid >> 5), lane = tid & 31, row = q * 32 + lane;
-  unsigned char* sA = smem + grp * GRP_BYTES;
-  unsigned char* sW = sA + A_BYTES;
+  unsigned char* sG = smem + grp * GRP_BYTES;
   float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
   float* sbmat = reinterpret_cast<float*>(smem + OFF_BMAT);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + OFF_BAR) + grp;
-  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + OFF_BAR + 24) + grp;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 16);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + OFF_BAR) + grp * NST;        // [stage]: its MMAs have completed
+  uint64_t* wbar = reinterpret_cast<uint64_t*>(smem + OFF_BAR + 32) + grp * NST;   // [stage]: its weight chunk has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_BAR + 64);
   const int K = a.K0 + a.K1, N = a.N;
 
   for (int i = tid; i < 256; i += GN_THREADS)
@@ -94,51 +96,56 @@ tc_linear_kernel(TcLinArgs a) {
     }
   }
   if ((tid >> 5) == 0) tmem_alloc(tmem_slot, 512);
-  if (gtid == 32) { mbar_init(mbar, 1); mbar_init(wbar, 1); }
+  if (gtid == 32) {
+    for (int st = 0; st < NST; ++st) { mbar_init(mbar + st, 1); mbar_init(wbar + st, 1); }
+  }
   fence_before_thread_sync();
   __syncthreads();
   fence_after_thread_sync();
   const uint32_t tmem_grp = *tmem_slot + grp * 256;
   const uint32_t tmem_row = tmem_grp + (static_cast<uint32_t>(q * 32) << 16);
-  const uint32_t sA_addr = smem_u32(sA), sW_addr = smem_u32(sW);
-  uint32_t phase = 0, wphase = 0;
   const long long ntiles = (a.R + 127) / 128;
+  const int nch = (K + KCH - 1) / KCH;
+  const long long tstep = static_cast<long long>(gridDim.x) * 2;
+  const long long tile0 = static_cast<long long>(blockIdx.x) * 2 + grp;
+  const bool from_bf16 = !a.a0_is_f32;
+  const bool a_async = from_bf16 && a.K1 == 0 && a.a_div == 0.f;
 
-  for (long long tile = static_cast<long long>(blockIdx.x) * 2 + grp; tile < ntiles;
-       tile += static_cast<long long>(gridDim.x) * 2) {
+  // The group's chunks form one sequence over its tiles (g = running index, stage = g & 1).  produce(g) loads chunk g
+  // into its stage once the MMAs of chunk g - 2 have released it; consume(g) waits for the loads and issues the MMAs.
+  // produce(g + 1) runs BEFORE consume(g): a chunk's loads are in flight under the previous chunk's wait and MMAs, and
+  // the first chunk of the next tile under this tile's epilogue.
+  auto produce = [&](long long tile, int c, uint32_t g) {
+    const uint32_t st = g & 1u;
+    if (g >= static_cast<uint32_t>(NST)) mbar_wait(mbar + st, ((g >> 1) - 1u) & 1u);
+    unsigned char* sA = sG + st * STG_BYTES;
+    const uint32_t sW_addr = smem_u32(sA + A_BYTES);
     const long long row0 = tile * 128;
     const int nrows = static_cast<int>(min(128LL, a.R - row0));
-    for (int kc0 = 0; kc0 < K; kc0 += KCH) {
-      const int kcw = min(KCH, K - kc0), nk8 = kcw >> 3;
-      if (kc0 > 0) { mbar_wait(mbar, phase); phase ^= 1; }   // previous chunk's MMAs released the buffers
-      // ---- W chunk: rows [n0, n0+N) of k-groups [kc0/8, kc0/8 + nk8): N*16 contiguous bytes per k-group, one bulk copy
-      // each (issued by the group's first warp, completion counted in bytes on wbar; 32 cp.async + index arithmetic per
-      // thread before)
-      if (gtid < 32) {
-        tcu::expect_tx(wbar, static_cast<uint32_t>(nk8) * N * 16);
-        for (int k8 = 0; k8 < nk8; ++k8)
-          tcu::bulk_g2s(sW_addr + static_cast<uint32_t>(k8) * N * 16,
-                        a.W + (static_cast<size_t>((kc0 >> 3) + k8) * a.Ntot + a.n0) * 8, static_cast<uint32_t>(N) * 16, wbar);
-      }
-      // ---- A chunk: task = (row, k-group)
-      const bool from_bf16 = !a.a0_is_f32;
-      if (from_bf16 && a.K1 == 0 && a.a_div == 0.f) {
-        // a bf16 row-major source needs no conversion: its 16-byte k-groups go straight to their place in the canonical
-        // operand by cp.async, all of a chunk's loads in flight at once (through registers the loop below exposes one
-        // DRAM round trip per batch of four k-groups: 4 per chunk, ~10 us of a 13 us chunk on the decoder MLPs)
-        const int r = gtid;
-        if (r < nrows) {
-          const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(a.A0) + static_cast<size_t>(row0 + r) * a.lda0 + kc0;
+    const int kc0 = c * KCH, kcw = min(KCH, K - kc0), nk8 = kcw >> 3;
+    // ---- W chunk: rows [n0, n0+N) of k-groups [kc0/8, kc0/8 + nk8): N*16 contiguous bytes per k-group, one bulk copy
+    // each (issued by the group's first warp, completion counted in bytes on the stage's wbar)
+    if (gtid < 32) {
+      tcu::expect_tx(wbar + st, static_cast<uint32_t>(nk8) * N * 16);
+      for (int k8 = 0; k8 < nk8; ++k8)
+        tcu::bulk_g2s(sW_addr + static_cast<uint32_t>(k8) * N * 16,
+                      a.W + (static_cast<size_t>((kc0 >> 3) + k8) * a.Ntot + a.n0) * 8, static_cast<uint32_t>(N) * 16, wbar + st);
+    }
+    // ---- A chunk: task = (row, k-group)
+    const int r = gtid;
+    if (a_async) {
+      // a bf16 row-major source needs no conversion: its 16-byte k-groups go straight to their place in the canonical
+      // operand by cp.async, all of a chunk's loads in flight at once
+      if (r < nrows) {
+        const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(a.A0) + static_cast<size_t>(row0 + r) * a.lda0 + kc0;
 #pragma unroll 4
-          for (int k8 = 0; k8 < nk8; ++k8) cp_async16(sA + canon_off(r, k8, 128), src + 8 * k8);
-        } else {
-          for (int k8 = 0; k8 < nk8; ++k8) *reinterpret_cast<uint4*>(sA + canon_off(r, k8, 128)) = make_uint4(0u, 0u, 0u, 0u);
-        }
-        cp_async_commit();
-      } else
+        for (int k8 = 0; k8 < nk8; ++k8) cp_async16(sA + canon_off(r, k8, 128), src + 8 * k8);
+      } else {
+        for (int k8 = 0; k8 < nk8; ++k8) *reinterpret_cast<uint4*>(sA + canon_off(r, k8, 128)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else {
 #pragma unroll 4
       for (int k8 = 0; k8 < nk8; ++k8) {
-        const int r = gtid;
         const int k = kc0 + k8 * 8;
         uint4 pk = make_uint4(0u, 0u, 0u, 0u);
         if (r < nrows) {
@@ -160,22 +167,41 @@ tc_linear_kernel(TcLinArgs a) {
         }
         *reinterpret_cast<uint4*>(sA + canon_off(r, k8, 128)) = pk;
       }
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      fence_before_thread_sync();
-      group_bar(grp);
-      if (gtid < 32) {                       // warp-uniform issue: one elected lane, operands stay uniform
-        mbar_wait(wbar, wphase);             // the weight chunk has landed
-        fence_after_thread_sync();
-        if (elect_one()) {
-          issue_gemm(tmem_grp, sA_addr, sW_addr, N, kcw, kc0 > 0);
-          mma_commit(mbar);
-        }
-        __syncwarp();
-      }
-      wphase ^= 1;
     }
-    mbar_wait(mbar, phase); phase ^= 1;
+    cp_async_commit();                       // one group per chunk, empty on the conversion path
+  };
+  auto consume = [&](int c, uint32_t g, bool next_in_flight) {
+    const uint32_t st = g & 1u;
+    if (next_in_flight) cp_async_wait<1>(); else cp_async_wait<0>();
+    fence_proxy_async_smem();
+    fence_before_thread_sync();
+    group_bar(grp);
+    if (gtid < 32) {                         // warp-uniform issue: one elected lane, operands stay uniform
+      mbar_wait(wbar + st, (g >> 1) & 1u);   // the weight chunk has landed
+      fence_after_thread_sync();
+      if (elect_one()) {
+        const uint32_t sA_addr = smem_u32(sG + st * STG_BYTES);
+        issue_gemm(tmem_grp, sA_addr, sA_addr + A_BYTES, N, min(KCH, K - c * KCH), c > 0);
+        mma_commit(mbar + st);
+      }
+      __syncwarp();
+    }
+  };
+
+  uint32_t g = 0;
+  if (tile0 < ntiles) produce(tile0, 0, 0u);
+  for (long long tile = tile0; tile < ntiles; tile += tstep) {
+    const long long row0 = tile * 128;
+    const int nrows = static_cast<int>(min(128LL, a.R - row0));
+    for (int c = 0; c < nch; ++c, ++g) {
+      long long nt = tile;
+      int nc = c + 1;
+      if (nc == nch) { nt = tile + tstep; nc = 0; }
+      const bool more = nt < ntiles;
+      if (more) produce(nt, nc, g + 1u);
+      consume(c, g, more);
+    }
+    mbar_wait(mbar + ((g - 1u) & 1u), ((g - 1u) >> 1) & 1u);   // the tile's last chunk: the accumulator is complete
     fence_after_thread_sync();
 
     // ---- epilogue: this thread owns tile row `row`
@@ -208,7 +234,7 @@ tc_linear_kernel(TcLinArgs a) {
         scale = __ldg(a.rowscale + static_cast<size_t>(grow) * a.rs_ld + ((a.n0 + nfull) >> a.rs_shift));
       if (live) epilogue_chunk<RELU, OUTF32, MODE, 16>(a, v, nfull, grow, sbias, sbmat, rs, scale);
     }
-    // next tile's first MMA overwrites this group's TMEM columns and operand buffers
+    // next tile's first MMA overwrites this group's TMEM columns
     fence_before_thread_sync();
     group_bar(grp);
   }
