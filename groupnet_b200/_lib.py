@@ -11,7 +11,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgroupnet_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 GN_MAX_AGENTS = 64
 GN_MAX_SCALES = 8
@@ -80,9 +80,9 @@ class DecoderWeights(C.Structure):
 
 
 class DecoderTcWeights(C.Structure):
-    """struct gn_decoder_tc_weights (14 device pointers, header order)."""
+    """struct gn_decoder_tc_weights (16 device pointers, header order)."""
     FIELDS = ("conv_w", "conv_b", "gru_w", "gru_b", "w0", "b0",
-              "x_w1", "x_b1", "x_w2", "x_b2", "y_w1", "y_b1", "y_w2", "y_b2")
+              "x_w1", "x_b1", "x_w2", "x_b2", "y_w1", "y_b1", "y_w2", "y_b2", "mlp_stream", "mlp_bias")
     _fields_ = [(name, C.c_void_p) for name in FIELDS]
 
 

@@ -15,6 +15,7 @@
 //                      as one K = F + Z + 96 -> 1024 contraction (4 launches of N = 256), 512 -> 256 per MLP,
 //                      256 -> 2 T (zero-padded to a multiple of 16) per MLP; bf16 activations between them.
 //   decoder_finish     x_hat, reconstruction += x_hat, out_seq += y_hat (+ cur_location after the last block).
+#include <cstdlib>
 #include "gn_tc.cuh"
 #include "gn_stage.h"
 
@@ -232,6 +233,245 @@ decoder_gru_tc_kernel(DecGruArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// decoder_x / decoder_y FUSED: feat -> 512 -> 256 -> 2 T for both MLPs of a 128-row tile in one kernel; the hidden
+// activations never leave the SM (the row-tile GEMMs spent their time moving hid1 / hid2 and re-streaming weights).
+//
+//   warps 0-7   drain (warp w: TMEM lane quarter w & 3, column half w >> 2): D1 hidden-1 chunk (128 columns) -> bias, ReLU,
+//               bf16 -> the A2 operand in shared memory; D2 hidden-2 (256 columns) -> the A3 operand; D3 the 32 output
+//               columns -> + bias -> fp32 rows in HBM
+//   warp 8      producer: the tile's feature rows (cp.async, once per tile for both MLPs) and the host-packed weight
+//               stream — 16 KB stages in the issuer's consumption order, one bulk copy each — through a ring of 3
+//   warp 9      issuer, per MLP:  G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3) G3
+//                 G1(c)  acc1[c & 1] (128 cols) = feat (K = Kf) x W0[c]          K / 64 stages
+//                 G2(c)  acc2 (256 cols)      += A2[c & 1] (K = 128) x W1[:, c]  4 stages (2 K halves x 2 N halves)
+//                 G3     acc1[0] (32 cols)     = A3 (K = 256) x W2               4 stages
+//               so D1(c) runs under G1(c + 1), and the second Linear consumes hidden-1 chunk by chunk
+// TMEM: acc1[0] 0..127 | acc1[1] 128..255 | acc2 256..511.  A3 occupies both A2 buffers (all of G2 has completed).
+namespace dfu {
+constexpr int NST = 3, DRAIN_WARPS = 8, THREADS = (DRAIN_WARPS + 2) * 32;
+constexpr int KF_MAX = 384;
+constexpr uint32_t STG_BYTES = 16384;
+constexpr uint32_t OFF_FEAT = 0;                              // [Kf/8][128][8] bf16, <= 96 KB
+constexpr uint32_t OFF_A2 = 128 * KF_MAX * 2;                 // 2 x 32 KB
+constexpr uint32_t OFF_W = OFF_A2 + 2 * 32768;                // NST x 16 KB
+constexpr uint32_t OFF_BIAS = OFF_W + NST * STG_BYTES;        // b0[1024] | b1[512] | b2[64]
+constexpr uint32_t OFF_BAR = OFF_BIAS + 1600 * 4;
+enum { B_WFULL = 0, B_WEMPTY = 3, B_FEATFULL = 6, B_FEATEMPTY, B_ACC1FULL, B_ACC1EMPTY = 10, B_A2FULL = 12, B_A2EMPTY = 14,
+       B_ACC2FULL = 16, B_ACC2EMPTY, B_COUNT };
+constexpr uint32_t SMEM_BYTES = OFF_BAR + B_COUNT * 8 + 16;
+}  // namespace dfu
+
+struct DecFusedArgs {
+  const __nv_bfloat16* feat; int Kf;            // (R, Kf) bf16, Kf % 64 == 0, Kf <= 384
+  const __nv_bfloat16* stream;                  // per MLP: 4 * (Kf / 64) + 16 + 4 stages of 8,192 bf16
+  const float* bias;                            // b0[1024] | b1x[256] b1y[256] | b2x[32] b2y[32]
+  float* ox; float* oy;                         // (R, 32) fp32 each
+  long long R;
+};
+
+__global__ void __launch_bounds__(dfu::THREADS, 1)
+decoder_mlp_fused_kernel(DecFusedArgs a) {
+  using namespace dfu;
+  using namespace tc;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* sfeat = smem + OFF_FEAT;
+  float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + B_COUNT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nk1 = a.Kf >> 6;                    // stages of one G1
+  const int per_mlp = 4 * nk1 + 16 + 4;
+
+  for (int i = tid; i < 1600; i += THREADS) sbias[i] = __ldg(a.bias + i);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (tid == 32) {
+    for (int i = 0; i < NST; ++i) { mbar_init(bar + B_WFULL + i, 1); mbar_init(bar + B_WEMPTY + i, 1); }
+    mbar_init(bar + B_FEATFULL, 32); mbar_init(bar + B_FEATEMPTY, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar + B_ACC1FULL + b, 1); mbar_init(bar + B_ACC1EMPTY + b, DRAIN_WARPS * 32);
+      mbar_init(bar + B_A2FULL + b, DRAIN_WARPS * 32); mbar_init(bar + B_A2EMPTY + b, 1);
+    }
+    mbar_init(bar + B_ACC2FULL, 1); mbar_init(bar + B_ACC2EMPTY, DRAIN_WARPS * 32);
+  }
+  fence_before_thread_sync();
+  __syncthreads();
+  fence_after_thread_sync();
+  const uint32_t tmem = *tmem_slot;
+  const long long ntiles = (a.R + 127) / 128;
+  // every role walks the same static schedule and counts its own barrier phases: cnt[b] = completed waits on bar[b].
+  // "full" barriers are waited with the phase's own parity, "empty" ones with the opposite (a fresh barrier passes)
+  uint32_t cnt[B_COUNT];
+#pragma unroll
+  for (int i = 0; i < B_COUNT; ++i) cnt[i] = 0;
+  auto wait_full = [&](int b) { mbar_wait(bar + b, cnt[b] & 1u); ++cnt[b]; };
+  auto wait_empty = [&](int b) { mbar_wait(bar + b, (cnt[b] & 1u) ^ 1u); ++cnt[b]; };
+
+  if (warp == DRAIN_WARPS) {
+    // ---------------- producer ----------------
+    auto load_feat = [&](long long tile) {
+      wait_empty(B_FEATEMPTY);
+      const long long row0 = tile * 128;
+      const int nrows = static_cast<int>(min(128LL, a.R - row0));
+      const int nk8 = a.Kf >> 3;
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) {
+        const int r = rb * 32 + lane;
+        if (r < nrows) {
+          const __nv_bfloat16* src = a.feat + static_cast<size_t>(row0 + r) * a.Kf;
+          for (int k8 = 0; k8 < nk8; ++k8) cp_async16(sfeat + canon_off(r, k8, 128), src + 8 * k8);
+        } else {
+          for (int k8 = 0; k8 < nk8; ++k8)
+            *reinterpret_cast<uint4*>(sfeat + canon_off(r, k8, 128)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      cp_async_commit();
+    };
+    auto publish_feat = [&]() {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(bar + B_FEATFULL);
+    };
+    uint32_t g = 0;
+    // the next tile's rows are requested once the issuer is past the last read of this tile's (second MLP, G1(3))
+    const int feat_at = per_mlp + 4 * nk1 + 8 + 3;
+    if (static_cast<long long>(blockIdx.x) < ntiles) { load_feat(blockIdx.x); publish_feat(); }
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const bool has_next = tile + gridDim.x < ntiles;
+      for (int i = 0; i < 2 * per_mlp; ++i, ++g) {
+        if (i == feat_at && has_next) load_feat(tile + gridDim.x);
+        const uint32_t st = g % NST;
+        mbar_wait(bar + B_WEMPTY + st, ((g / NST) & 1u) ^ 1u);
+        const int im = i % per_mlp;
+        const uint32_t bytes = im >= per_mlp - 4 ? 4096u : STG_BYTES;       // the last Linear's stages: 32 rows x 64 K
+        tcu::expect_tx(bar + B_WFULL + st, bytes);
+        tcu::bulk_g2s(smem_u32(smem + OFF_W + st * STG_BYTES), a.stream + static_cast<size_t>(i) * (STG_BYTES / 2), bytes,
+                      bar + B_WFULL + st);
+      }
+      if (has_next) publish_feat();
+    }
+  } else if (warp == DRAIN_WARPS + 1) {
+    // ---------------- MMA issuer ----------------
+    uint32_t g = 0;
+    const uint32_t feat_addr = smem_u32(sfeat), a2_addr = smem_u32(smem + OFF_A2);
+    auto stage_mma = [&](uint32_t tmem_d, uint32_t a_addr, int N, bool accumulate) {   // one 64-wide K stage
+      const uint32_t st = g % NST;
+      mbar_wait(bar + B_WFULL + st, (g / NST) & 1u);
+      fence_after_thread_sync();
+      if (elect_one()) {
+        issue_gemm(tmem_d, a_addr, smem_u32(smem + OFF_W + st * STG_BYTES), N, 64, accumulate);
+        mma_commit(bar + B_WEMPTY + st);
+      }
+      __syncwarp();
+      ++g;
+    };
+    auto commit = [&](int b) {
+      if (elect_one()) mma_commit(bar + b);
+      __syncwarp();
+    };
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      wait_full(B_FEATFULL);
+      fence_after_thread_sync();
+      for (int m = 0; m < 2; ++m) {
+        auto G1 = [&](int c) {
+          const int b = c & 1;
+          wait_empty(B_ACC1EMPTY + b);
+          fence_after_thread_sync();
+          for (int ks = 0; ks < nk1; ++ks) stage_mma(tmem + b * 128u, feat_addr + ks * (8u * 2048u), 128, ks > 0);
+          commit(B_ACC1FULL + b);
+        };
+        auto G2 = [&](int c) {
+          const int b = c & 1;
+          wait_full(B_A2FULL + b);
+          if (c == 0) wait_empty(B_ACC2EMPTY);
+          fence_after_thread_sync();
+          for (int kh = 0; kh < 2; ++kh)
+            for (int nh = 0; nh < 2; ++nh)
+              stage_mma(tmem + 256u + nh * 128u, a2_addr + b * 32768u + kh * (8u * 2048u), 128, c > 0 || kh > 0);
+          commit(B_A2EMPTY + b);
+        };
+        G1(0); G1(1); G2(0); G1(2); G2(1); G1(3);
+        if (m == 1) commit(B_FEATEMPTY);
+        G2(2); G2(3);
+        commit(B_ACC2FULL);
+        // G3: A3 (K = 256) lives in both A2 buffers
+        wait_full(B_A2FULL + 0); wait_full(B_A2FULL + 1);
+        wait_empty(B_ACC1EMPTY + 0);
+        fence_after_thread_sync();
+        for (int ks = 0; ks < 4; ++ks) stage_mma(tmem, a2_addr + ks * (8u * 2048u), 32, ks > 0);
+        commit(B_ACC1FULL + 0);
+        commit(B_A2EMPTY + 0); commit(B_A2EMPTY + 1);
+      }
+    }
+  } else {
+    // ---------------- drain ----------------
+    const int q = warp & 3, ch = warp >> 2, row = q * 32 + lane;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    unsigned char* sA2 = smem + OFF_A2;
+    // `ncols` accumulator columns starting at TMEM column tcol (this warp's half) -> + bias, ReLU -> bf16 k-groups kg0.. of dst
+    auto to_operand = [&](uint32_t tcol, int ncols, const float* bias, unsigned char* dst, int kg0) {
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + tcol + c0, v);
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_bf16_relu(v[j] + bias[c0 + j], v[j + 1] + bias[c0 + j + 1]);
+        *reinterpret_cast<uint4*>(dst + canon_off(row, kg0 + (c0 >> 3), 128)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(dst + canon_off(row, kg0 + (c0 >> 3) + 1, 128)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    };
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const long long grow = tile * 128 + row;
+      for (int m = 0; m < 2; ++m) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                    // D1(c): hidden-1 chunk c -> A2[c & 1]
+          const int b = c & 1;
+          wait_full(B_ACC1FULL + b);
+          wait_empty(B_A2EMPTY + b);
+          fence_after_thread_sync();
+          to_operand(b * 128u + ch * 64u, 64, sbias + m * 512 + c * 128 + ch * 64, sA2 + b * 32768, ch * 8);
+          fence_proxy_async_smem();
+          fence_before_thread_sync();
+          mbar_arrive(bar + B_A2FULL + b);
+          mbar_arrive(bar + B_ACC1EMPTY + b);
+        }
+        // D2: hidden-2 (256 columns) -> A3 over both A2 buffers
+        wait_full(B_ACC2FULL);
+        wait_empty(B_A2EMPTY + 0); wait_empty(B_A2EMPTY + 1);
+        fence_after_thread_sync();
+        to_operand(256u + ch * 128u, 128, sbias + 1024 + m * 256 + ch * 128, sA2, ch * 16);
+        fence_proxy_async_smem();
+        fence_before_thread_sync();
+        mbar_arrive(bar + B_A2FULL + 0); mbar_arrive(bar + B_A2FULL + 1);
+        mbar_arrive(bar + B_ACC2EMPTY);
+        // D3: the 32 output columns (this warp: 16) -> + bias -> HBM
+        wait_full(B_ACC1FULL + 0);
+        fence_after_thread_sync();
+        {
+          float v[16];
+          tmem_ld16(trow + ch * 16u, v);
+          const float* b2 = sbias + 1536 + m * 32 + ch * 16;
+          if (grow < a.R) {
+            float* dst = (m == 0 ? a.ox : a.oy) + static_cast<size_t>(grow) * 32 + ch * 16;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(v[j] + b2[j], v[j + 1] + b2[j + 1], v[j + 2] + b2[j + 2], v[j + 3] + b2[j + 3]);
+          }
+        }
+        fence_before_thread_sync();
+        mbar_arrive(bar + B_ACC1EMPTY + 0);
+      }
+    }
+  }
+
+  fence_before_thread_sync();
+  __syncthreads();
+  if (warp == 0) {
+    fence_after_thread_sync();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 struct DecFinishArgs {
   const float* ox; const float* oy; int ldx, ldy;      // last Linears' outputs (R, ldx) / (R, ldy), biases included
   const float* cur_location;
@@ -275,8 +515,8 @@ static DecTcLayout dec_tc_layout(long long R, int F, int Z, int Tp, int Tf) {
   l.feat = off;  off += align256(static_cast<size_t>(R) * (F + Z + dtc::STATE) * 2);
   l.hid1 = off;  off += align256(static_cast<size_t>(R) * 1024 * 2);
   l.hid2 = off;  off += align256(static_cast<size_t>(R) * 512 * 2);
-  l.ox = off;    off += align256(static_cast<size_t>(R) * pad16(2 * Tp) * 4);
-  l.oy = off;    off += align256(static_cast<size_t>(R) * pad16(2 * Tf) * 4);
+  l.ox = off;    off += align256(static_cast<size_t>(R) * ((2 * Tp + 31) & ~31) * 4);   // >= 32 columns: the fused MLP kernel's rows
+  l.oy = off;    off += align256(static_cast<size_t>(R) * ((2 * Tf + 31) & ~31) * 4);
   l.total = off;
   return l;
 }
@@ -350,19 +590,39 @@ extern "C" int gn_decoder_fwd_tc(const gn_decoder_tc_weights* blocks, int32_t nu
       decoder_gru_tc_kernel<<<grid, dtc::THREADS, dtc::SMEM_BYTES, st>>>(g);
     }
     GN_LAUNCH_CHECK();
-    const __nv_bfloat16* w0 = static_cast<const __nv_bfloat16*>(w.w0);
-    for (int c = 0; c < 4; ++c)
-      GN_TRY(linear(feat, Kf, Kf, w0, 1024, 256 * c, 256, w.b0, 1, hid1, 0, 1024, 256 * c, "decoder_mlp0_tc"));
-    GN_TRY(linear(hid1, 1024, 512, static_cast<const __nv_bfloat16*>(w.x_w1), 256, 0, 256, w.x_b1, 1, hid2, 0, 512, 0,
-                  "decoder_mlp1_tc"));
-    GN_TRY(linear(hid1 + 512, 1024, 512, static_cast<const __nv_bfloat16*>(w.y_w1), 256, 0, 256, w.y_b1, 1, hid2, 0,
-                  512, 256, "decoder_mlp1_tc"));
-    GN_TRY(linear(hid2, 512, 256, static_cast<const __nv_bfloat16*>(w.x_w2), n3x, 0, n3x, w.x_b2, 0, ox, 1, n3x, 0,
-                  "decoder_mlp2_tc"));
-    GN_TRY(linear(hid2 + 256, 512, 256, static_cast<const __nv_bfloat16*>(w.y_w2), n3y, 0, n3y, w.y_b2, 0, oy, 1, n3y,
-                  0, "decoder_mlp2_tc"));
+    // the fused MLP kernel (hidden activations stay on chip) covers feature widths up to 384 and up to 16 time steps per
+    // output; other shapes run the row-tile GEMMs.  GN_DECODER_MLP=rowtile forces the latter (A/B measurements).
+    static const bool force_rowtile = [] { const char* v = getenv("GN_DECODER_MLP"); return v && v[0] == 'r'; }();
+    const bool fused = !force_rowtile && w.mlp_stream && w.mlp_bias && Kf <= dfu::KF_MAX && (Kf & 63) == 0 && Tp <= 16 && Tf <= 16;
+    int ldx = n3x, ldy = n3y;
+    if (fused) {
+      e = cudaFuncSetAttribute(decoder_mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(dfu::SMEM_BYTES));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      DecFusedArgs fa;
+      fa.feat = feat; fa.Kf = Kf; fa.stream = static_cast<const __nv_bfloat16*>(w.mlp_stream); fa.bias = w.mlp_bias;
+      fa.ox = ox; fa.oy = oy; fa.R = R;
+      {
+        ProfScope prof("decoder_mlp_fused", st);
+        decoder_mlp_fused_kernel<<<grid, dfu::THREADS, dfu::SMEM_BYTES, st>>>(fa);
+      }
+      GN_LAUNCH_CHECK();
+      ldx = ldy = 32;
+    } else {
+      const __nv_bfloat16* w0 = static_cast<const __nv_bfloat16*>(w.w0);
+      for (int c = 0; c < 4; ++c)
+        GN_TRY(linear(feat, Kf, Kf, w0, 1024, 256 * c, 256, w.b0, 1, hid1, 0, 1024, 256 * c, "decoder_mlp0_tc"));
+      GN_TRY(linear(hid1, 1024, 512, static_cast<const __nv_bfloat16*>(w.x_w1), 256, 0, 256, w.x_b1, 1, hid2, 0, 512, 0,
+                    "decoder_mlp1_tc"));
+      GN_TRY(linear(hid1 + 512, 1024, 512, static_cast<const __nv_bfloat16*>(w.y_w1), 256, 0, 256, w.y_b1, 1, hid2, 0,
+                    512, 256, "decoder_mlp1_tc"));
+      GN_TRY(linear(hid2, 512, 256, static_cast<const __nv_bfloat16*>(w.x_w2), n3x, 0, n3x, w.x_b2, 0, ox, 1, n3x, 0,
+                    "decoder_mlp2_tc"));
+      GN_TRY(linear(hid2 + 256, 512, 256, static_cast<const __nv_bfloat16*>(w.y_w2), n3y, 0, n3y, w.y_b2, 0, oy, 1, n3y,
+                    0, "decoder_mlp2_tc"));
+    }
     DecFinishArgs f;
-    f.ox = ox; f.oy = oy; f.ldx = n3x; f.ldy = n3y; f.cur_location = cur_location;
+    f.ox = ox; f.oy = oy; f.ldx = ldx; f.ldy = ldy; f.cur_location = cur_location;
     f.x_hat = x_hat; f.recover = recover; f.out_seq = out_seq; f.R = R; f.S = S;
     f.tp2 = 2 * Tp; f.tf2 = 2 * Tf; f.first = b == 0; f.last = b == num_blocks - 1;
     const long long total = R * (f.tp2 + f.tf2);

@@ -95,7 +95,7 @@ class Decoder(RuntimeStateMixin, nn.Module):
             for st, t in zip(structs, tensors):
                 for name in struct.FIELDS:
                     assert t[name].is_contiguous() and t[name].dtype in (torch.float32, torch.bfloat16)
-                    setattr(st, name, C.c_void_p(t[name].data_ptr()))
+                    setattr(st, name, C.c_void_p(t[name].data_ptr() if t[name].numel() else 0))
             self._packed, self._pack_key = (tensors, structs), key
         return self._packed[1]
 

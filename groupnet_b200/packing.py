@@ -604,4 +604,53 @@ def pack_decoder_block_tc(block, device: torch.device) -> Dict[str, torch.Tensor
         b2[:n_out] = dev(l2.bias)
         out[f"{tag}_w2"] = _canon(w2)
         out[f"{tag}_b2"] = b2
+    out["mlp_stream"], out["mlp_bias"] = decoder_mlp_stream(block, device)
     return out
+
+
+def decoder_mlp_stream(block, device: torch.device):
+    """Weights of decoder_x then decoder_y as the stage stream of `decoder_mlp_fused_kernel` (csrc/gn_decoder_tc.cu): 16 KB
+    stages of canonical [8 k-groups][rows][8] bf16 tiles in the issuer's order per MLP,
+        G1(0) G1(1) G2(0) G1(2) G2(1) G1(3) G2(2) G2(3) G3
+    G1(c): K / 64 stages W0[c*128:(c+1)*128, ks*64:(ks+1)*64];  G2(c): 4 stages W1[nh*128:(nh+1)*128, c*128 + kh*64 : + 64]
+    (kh outer, nh inner);  G3: 4 stages W2 (rows zero-padded to 32)[:, ks*64:(ks+1)*64], 4 KB used of each 16 KB slot.
+    Biases: b0 x (512) | b0 y (512) | b1 x (256) | b1 y (256) | b2 x (32) | b2 y (32).  Feature widths that are not a
+    multiple of 64 get no stream (a zero-length tensor: the row-tile GEMMs run)."""
+    def dev(x):
+        return x.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    kf = block.decoder_x.layers[0].weight.shape[1]
+    bias = torch.zeros(1600, dtype=torch.float32, device=device)
+    if kf % 64 or kf > 384 or block.decoder_x.layers[2].weight.shape[0] > 32 or block.decoder_y.layers[2].weight.shape[0] > 32:
+        return torch.zeros(0, dtype=torch.bfloat16, device=device), bias
+    stage = 8192                                                     # bf16 elements per 16 KB slot
+    chunks = []
+
+    def put(tile):
+        flat = _canon(tile)
+        slot = torch.zeros(stage, dtype=torch.bfloat16, device=device)
+        slot[:flat.numel()] = flat
+        chunks.append(slot)
+
+    for i, mlp in enumerate((block.decoder_x, block.decoder_y)):
+        l0, l1, l2 = mlp.layers
+        w0, w1 = dev(l0.weight), dev(l1.weight)
+        w2 = torch.zeros(32, 256, dtype=torch.float32, device=device)
+        w2[:l2.weight.shape[0]] = dev(l2.weight)
+
+        def g1(c):
+            for ks in range(kf // 64):
+                put(w0[c * 128:(c + 1) * 128, ks * 64:(ks + 1) * 64])
+
+        def g2(c):
+            for kh in range(2):
+                for nh in range(2):
+                    put(w1[nh * 128:(nh + 1) * 128, c * 128 + kh * 64:c * 128 + (kh + 1) * 64])
+
+        g1(0); g1(1); g2(0); g1(2); g2(1); g1(3); g2(2); g2(3)
+        for ks in range(4):
+            put(w2[:, ks * 64:(ks + 1) * 64])
+        bias[i * 512:(i + 1) * 512] = dev(l0.bias)
+        bias[1024 + i * 256:1024 + (i + 1) * 256] = dev(l1.bias)
+        bias[1536 + i * 32:1536 + i * 32 + l2.bias.numel()] = dev(l2.bias)
+    return torch.cat(chunks).contiguous(), bias

@@ -28,9 +28,10 @@
 extern "C" {
 #endif
 
-#define GN_ABI_VERSION 5     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams;
+#define GN_ABI_VERSION 6     /* 3: precision GN_TF32X3, gn_stage_weights gained the six tf_* weight streams;
                                  4: + tf_pagg_w (fused pairwise aggregation, csrc/gn_pair_agg_tf32.cu), gn_fish_* entry points;
-                                 5: + gn_decoder_fwd_tc (bf16 tensor-core decoder, csrc/gn_decoder_tc.cu) */
+                                 5: + gn_decoder_fwd_tc (bf16 tensor-core decoder, csrc/gn_decoder_tc.cu);
+                                 6: gn_decoder_tc_weights gained mlp_stream / mlp_bias (fused MLP kernel) */
 
 #define GN_MAX_AGENTS 64      /* N <= 64: one 64-bit membership word per hyperedge */
 #define GN_MAX_SCALES 8
@@ -281,6 +282,9 @@ typedef struct gn_decoder_tc_weights {
   const void* x_w2; const float* x_b2;   /* bf16 canonical [32][P][8], (P): P = 2*Tp rounded up to 16, zero rows */
   const void* y_w1; const float* y_b1;
   const void* y_w2; const float* y_b2;   /* P = 2*Tf rounded up to 16 */
+  const void* mlp_stream;  /* bf16: both MLPs' weights as 16 KB stages in the fused kernel's consumption order
+                              (packing.py::decoder_mlp_stream); NULL: the row-tile GEMMs run instead */
+  const float* mlp_bias;   /* b0 (1024) | x_b1 (256) | y_b1 (256) | x_b2 (32) | y_b2 (32), zero padded */
 } gn_decoder_tc_weights;
 
 /* Bytes of device scratch gn_decoder_fwd_tc needs (x_hat, the bf16 feature rows and hidden activations). */

@@ -27,7 +27,7 @@ def _inference_mode(request):
 
 def test_native_library_is_loaded():
     lib = _lib.load()
-    assert lib.gn_abi_version() == _lib.ABI_VERSION == 5
+    assert lib.gn_abi_version() == _lib.ABI_VERSION == 6
     maps = open("/proc/self/maps").read()
     assert "libgroupnet_b200.so" in maps
 
