@@ -1,5 +1,5 @@
 """ncu target: three steps of the bf16 tensor-core decoder (gn_decoder_fwd_tc) at the bench shape (1,024 scenes x 11 agents
-x 20 samples, 2 DecomposeBlocks = 20 launches per step).  ncu -k regex:"decoder|tc_linear" -s 40 -c 20 captures the third step."""
+x 20 samples, 2 DecomposeBlocks = 6 launches per step: gru_tc, mlp_fused, finish per block).  ncu -k regex:decoder -s 12 -c 6 captures the third step."""
 import os
 import sys
 import types

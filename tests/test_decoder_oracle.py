@@ -308,6 +308,60 @@ def test_tensor_core_decoder_packs_evaluate_to_the_reference(name):
     assert_close(rec, g["recover_pre_seq"], 1e-2, f"{name} recover_pre_seq (tc packs)")
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_fused_mlp_stage_stream_holds_the_weights_in_the_issue_order(name):
+    """decoder_mlp_stream: walking the 16 KB stages in the fused kernel's issue order (G1(0) G1(1) G2(0) G1(2) G2(1) G1(3)
+    G2(2) G2(3) G3 per MLP, csrc/gn_decoder_tc.cu) must reassemble bf16(W0), bf16(W1) and the zero-padded bf16(W2) of
+    decoder_x and decoder_y exactly, and the bias block must hold b0 | b1 | b2 at the offsets the drain reads."""
+    from groupnet_b200.packing import decoder_mlp_stream
+    g = _load(name)
+    m = _schema(g)
+    for blk in m.decompose:
+        stream, bias = decoder_mlp_stream(blk, torch.device("cpu"))
+        kf = blk.decoder_x.layers[0].weight.shape[1]
+        if kf % 64 or kf > 384:
+            assert stream.numel() == 0
+            continue
+        nk1, slot = kf // 64, 8192
+        assert stream.dtype == torch.bfloat16 and stream.numel() == 2 * (4 * nk1 + 20) * slot
+        pos = 0
+
+        def take(rows):
+            nonlocal pos
+            flat = stream[pos * slot:(pos + 1) * slot]
+            pos += 1
+            assert torch.all(flat[rows * 64:] == 0)
+            return _uncanon(flat[:rows * 64], rows, 64)
+
+        for i, mlp in enumerate((blk.decoder_x, blk.decoder_y)):
+            w0 = torch.zeros(512, kf)
+            w1 = torch.zeros(256, 512)
+            w2 = torch.zeros(32, 256)
+
+            def g1(c):
+                for ks in range(nk1):
+                    w0[c * 128:(c + 1) * 128, ks * 64:(ks + 1) * 64] = take(128)
+
+            def g2(c):
+                for kh in range(2):
+                    for nh in range(2):
+                        w1[nh * 128:(nh + 1) * 128, c * 128 + kh * 64:c * 128 + (kh + 1) * 64] = take(128)
+
+            g1(0); g1(1); g2(0); g1(2); g2(1); g1(3); g2(2); g2(3)
+            for ks in range(4):
+                w2[:, ks * 64:(ks + 1) * 64] = take(32)
+            l0, l1, l2 = mlp.layers
+            bf = lambda v: v.detach().to(torch.bfloat16).float()
+            assert torch.equal(w0, bf(l0.weight)) and torch.equal(w1, bf(l1.weight))
+            n_out = l2.weight.shape[0]
+            assert torch.equal(w2[:n_out], bf(l2.weight)) and torch.all(w2[n_out:] == 0)
+            assert torch.equal(bias[i * 512:(i + 1) * 512], l0.bias.detach())
+            assert torch.equal(bias[1024 + i * 256:1024 + (i + 1) * 256], l1.bias.detach())
+            assert torch.equal(bias[1536 + i * 32:1536 + i * 32 + n_out], l2.bias.detach())
+            assert torch.all(bias[1536 + i * 32 + n_out:1536 + (i + 1) * 32] == 0)
+        assert pos * slot == stream.numel()
+
+
 # ---- randomized differential pin against the live reference (build container only) ---------------------
 try:
     from hypothesis import HealthCheck, given, settings, strategies as st

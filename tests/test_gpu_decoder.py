@@ -120,6 +120,32 @@ def test_decoder_bf16_tensor_core_path_vs_oracle(batch, agents, s, blocks, hidde
     assert torch.equal(out, out2) and torch.equal(rec, rec2)
 
 
+def test_decoder_bf16_fused_and_row_tile_mlp_paths_agree(monkeypatch):
+    """The NBA shape runs the fused MLP kernel (decoder_mlp_fused_kernel); without the stage stream the same module runs
+    the row-tile GEMMs (the path of feature widths above 384 / not a multiple of 64).  Both must meet the bf16 bar
+    against the reference fixture and agree with each other far inside it."""
+    from groupnet_b200 import packing
+    g = _load("nba_inference")
+    s = g["sample_num"]
+    pf = torch.from_numpy(g["past_feature_per_agent"]).repeat_interleave(s, dim=0).to(DEV)
+    args = (pf, torch.from_numpy(g["z"]).to(DEV), g["batch"], g["agents"], torch.from_numpy(g["past_traj"]).to(DEV),
+            torch.from_numpy(g["cur_location"]).to(DEV), s)
+    m = _schema(g).to(DEV).set_precision("bf16")
+    out_f, rec_f = m(*args, mode=g["mode"])
+    assert m._packed[0][0]["mlp_stream"].numel() > 0                      # the fused kernel's stream exists at this shape
+    real = packing.decoder_mlp_stream
+    monkeypatch.setattr(packing, "decoder_mlp_stream",
+                        lambda blk, dev: (torch.zeros(0, dtype=torch.bfloat16, device=dev), real(blk, dev)[1]))
+    m.invalidate_packs()
+    out_r, rec_r = m(*args, mode=g["mode"])
+    assert m._packed[0][0]["mlp_stream"].numel() == 0
+    for out, rec, tag in ((out_f, rec_f, "fused"), (out_r, rec_r, "row-tile")):
+        assert_close(out, g["out_seq"], BF16_REL, f"out_seq ({tag})")
+        assert_close(rec, g["recover_pre_seq"], BF16_REL, f"recover_pre_seq ({tag})")
+    assert_close(out_f, out_r, 5e-3, "out_seq fused vs row-tile")
+    assert_close(rec_f, rec_r, 5e-3, "recover_pre_seq fused vs row-tile")
+
+
 def test_decoder_error_paths():
     g = _load("single_block_single_row")
     m = _schema(g).to(DEV)
