@@ -11,8 +11,11 @@
 //                      fp32 in their registers and only its bf16 operand copy goes back to shared memory.  conv1d +
 //                      ReLU of the residual is evaluated per step while the operand is built.  Writes the bf16
 //                      feature row [past_feature | z | state] the MLPs read.
-//   tc_linear x 8      decoder_x / decoder_y as row-tile GEMMs (gn_tc_linear.cu): the first Linears of both MLPs
-//                      as one K = F + Z + 96 -> 1024 contraction (4 launches of N = 256), 512 -> 256 per MLP,
+//   decoder_mlp_fused  decoder_x and decoder_y (feat -> 512 -> 256 -> 2 T) of a 128-row tile in ONE role-split kernel:
+//                      the hidden activations go from tensor memory to shared memory and back into the next MMA, the
+//                      weights arrive as a host-packed stream of 16 KB stages (feature width <= 384, T <= 16);
+//   tc_linear x 8      other shapes: the same Linears as row-tile GEMMs (gn_tc_linear.cu), the first Linears of both
+//                      MLPs as one K = F + Z + 96 -> 1024 contraction (4 launches of N = 256), 512 -> 256 per MLP,
 //                      256 -> 2 T (zero-padded to a multiple of 16) per MLP; bf16 activations between them.
 //   decoder_finish     x_hat, reconstruction += x_hat, out_seq += y_hat (+ cur_location after the last block).
 #include <cstdlib>

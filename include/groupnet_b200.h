@@ -267,7 +267,8 @@ int gn_decoder_fwd(const gn_decoder_weights* blocks, int32_t num_blocks, const f
 /* ---- trajectory decoder, bf16 tensor-core path (tcgen05, 2e-2 parity) --------------------------
  * The same contract as gn_decoder_fwd (Decoder.forward, model/GroupNet_nba.py:461-505; DecomposeBlock.forward
  * :48-79) with bf16 operands and fp32 accumulation: the GRU step as one K = 128 contraction per time step with
- * the gate math in the accumulator drain (fp32 state), decoder_x / decoder_y as row-tile GEMMs.
+ * the gate math in the accumulator drain (fp32 state), decoder_x / decoder_y fused in one kernel with the hidden
+ * activations on chip (row-tile GEMMs for feature widths above 384 or not a multiple of 64, or more than 16 time steps).
  * One gn_decoder_tc_weights per DecomposeBlock, packed by groupnet_b200/packing.py::pack_decoder_block_tc;
  * "canonical" = the K-major no-swizzle UMMA operand layout [K/8][N][8] of bf16 (csrc/gn_tc.cuh). */
 typedef struct gn_decoder_tc_weights {
