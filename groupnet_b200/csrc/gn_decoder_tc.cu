@@ -510,14 +510,22 @@ decoder_finish_kernel(DecFinishArgs a) {
 static inline size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
 static inline int pad16(int v) { return (v + 15) & ~15; }
 
+// shapes the fused MLP kernel covers (GN_DECODER_MLP=rowtile forces the row-tile GEMMs: A/B measurements)
+static bool dec_mlp_fused_shape(int F, int Z, int Tp, int Tf) {
+  static const bool force_rowtile = [] { const char* v = getenv("GN_DECODER_MLP"); return v && v[0] == 'r'; }();
+  const int Kf = F + Z + dtc::STATE;
+  return !force_rowtile && Kf <= dfu::KF_MAX && (Kf & 63) == 0 && Tp <= 16 && Tf <= 16;
+}
+
 struct DecTcLayout { size_t x_hat, feat, hid1, hid2, ox, oy, total; };
 static DecTcLayout dec_tc_layout(long long R, int F, int Z, int Tp, int Tf) {
   DecTcLayout l;
   size_t off = 0;
+  const bool hidden = !dec_mlp_fused_shape(F, Z, Tp, Tf);   // the fused kernel keeps both hidden layers on chip
   l.x_hat = off; off += align256(static_cast<size_t>(R) * 2 * Tp * 4);
   l.feat = off;  off += align256(static_cast<size_t>(R) * (F + Z + dtc::STATE) * 2);
-  l.hid1 = off;  off += align256(static_cast<size_t>(R) * 1024 * 2);
-  l.hid2 = off;  off += align256(static_cast<size_t>(R) * 512 * 2);
+  l.hid1 = off;  off += hidden ? align256(static_cast<size_t>(R) * 1024 * 2) : 0;
+  l.hid2 = off;  off += hidden ? align256(static_cast<size_t>(R) * 512 * 2) : 0;
   l.ox = off;    off += align256(static_cast<size_t>(R) * ((2 * Tp + 31) & ~31) * 4);   // >= 32 columns: the fused MLP kernel's rows
   l.oy = off;    off += align256(static_cast<size_t>(R) * ((2 * Tf + 31) & ~31) * 4);
   l.total = off;
@@ -595,8 +603,8 @@ extern "C" int gn_decoder_fwd_tc(const gn_decoder_tc_weights* blocks, int32_t nu
     GN_LAUNCH_CHECK();
     // the fused MLP kernel (hidden activations stay on chip) covers feature widths up to 384 and up to 16 time steps per
     // output; other shapes run the row-tile GEMMs.  GN_DECODER_MLP=rowtile forces the latter (A/B measurements).
-    static const bool force_rowtile = [] { const char* v = getenv("GN_DECODER_MLP"); return v && v[0] == 'r'; }();
-    const bool fused = !force_rowtile && w.mlp_stream && w.mlp_bias && Kf <= dfu::KF_MAX && (Kf & 63) == 0 && Tp <= 16 && Tf <= 16;
+    const bool fused = dec_mlp_fused_shape(F, Z, Tp, Tf);
+    if (fused && (!w.mlp_stream || !w.mlp_bias)) return GN_E_NULL;   // the workspace holds no hidden-layer buffers at this shape
     int ldx = n3x, ldy = n3y;
     if (fused) {
       e = cudaFuncSetAttribute(decoder_mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

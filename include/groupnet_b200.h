@@ -284,11 +284,13 @@ typedef struct gn_decoder_tc_weights {
   const void* y_w1; const float* y_b1;
   const void* y_w2; const float* y_b2;   /* P = 2*Tf rounded up to 16 */
   const void* mlp_stream;  /* bf16: both MLPs' weights as 16 KB stages in the fused kernel's consumption order
-                              (packing.py::decoder_mlp_stream); NULL: the row-tile GEMMs run instead */
+                              (packing.py::decoder_mlp_stream); required when F + Z + 96 <= 384 is a multiple of 64 and
+                              Tp, Tf <= 16 (the fused kernel's shapes), NULL otherwise (the row-tile GEMMs run) */
   const float* mlp_bias;   /* b0 (1024) | x_b1 (256) | y_b1 (256) | x_b2 (32) | y_b2 (32), zero padded */
 } gn_decoder_tc_weights;
 
-/* Bytes of device scratch gn_decoder_fwd_tc needs (x_hat, the bf16 feature rows and hidden activations). */
+/* Bytes of device scratch gn_decoder_fwd_tc needs: x_hat, the bf16 feature rows, the last Linears' outputs and — only at
+ * shapes the fused MLP kernel does not cover — the hidden activations (1.1 KB against 4.2 KB per row at the NBA shape). */
 size_t gn_decoder_tc_workspace_bytes(int64_t A, int32_t S, int32_t F, int32_t Z, int32_t Tp, int32_t Tf);
 
 /* Arguments as gn_decoder_fwd.  Limits: F % 8 == 0, Z % 8 == 0, (F + Z) % 16 == 0, Tp <= 32, Tf <= 32. */

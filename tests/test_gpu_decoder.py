@@ -120,25 +120,43 @@ def test_decoder_bf16_tensor_core_path_vs_oracle(batch, agents, s, blocks, hidde
     assert torch.equal(out, out2) and torch.equal(rec, rec2)
 
 
-def test_decoder_bf16_fused_and_row_tile_mlp_paths_agree(monkeypatch):
-    """The NBA shape runs the fused MLP kernel (decoder_mlp_fused_kernel); without the stage stream the same module runs
-    the row-tile GEMMs (the path of feature widths above 384 / not a multiple of 64).  Both must meet the bf16 bar
-    against the reference fixture and agree with each other far inside it."""
-    from groupnet_b200 import packing
+_ROWTILE_CHILD = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from test_decoder_oracle import _load, _schema
+g = _load("nba_inference")
+s = g["sample_num"]
+with torch.no_grad():
+    m = _schema(g).to("cuda:0").set_precision("bf16")
+    pf = torch.from_numpy(g["past_feature_per_agent"]).repeat_interleave(s, dim=0).cuda()
+    out, rec = m(pf, torch.from_numpy(g["z"]).cuda(), g["batch"], g["agents"], torch.from_numpy(g["past_traj"]).cuda(),
+                 torch.from_numpy(g["cur_location"]).cuda(), s, mode=g["mode"])
+np.savez(sys.argv[2], out=out.cpu().numpy(), rec=rec.cpu().numpy())
+"""
+
+
+def test_decoder_bf16_fused_and_row_tile_mlp_paths_agree(tmp_path):
+    """The NBA shape runs the fused MLP kernel (decoder_mlp_fused_kernel); GN_DECODER_MLP=rowtile (read once per process,
+    hence the child process) runs the same module on the row-tile GEMMs, the path of feature widths above 384 / not a
+    multiple of 64.  Both must meet the bf16 bar against the reference fixture and agree with each other inside it."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
     g = _load("nba_inference")
     s = g["sample_num"]
     pf = torch.from_numpy(g["past_feature_per_agent"]).repeat_interleave(s, dim=0).to(DEV)
-    args = (pf, torch.from_numpy(g["z"]).to(DEV), g["batch"], g["agents"], torch.from_numpy(g["past_traj"]).to(DEV),
-            torch.from_numpy(g["cur_location"]).to(DEV), s)
     m = _schema(g).to(DEV).set_precision("bf16")
-    out_f, rec_f = m(*args, mode=g["mode"])
+    out_f, rec_f = m(pf, torch.from_numpy(g["z"]).to(DEV), g["batch"], g["agents"], torch.from_numpy(g["past_traj"]).to(DEV),
+                     torch.from_numpy(g["cur_location"]).to(DEV), s, mode=g["mode"])
     assert m._packed[0][0]["mlp_stream"].numel() > 0                      # the fused kernel's stream exists at this shape
-    real = packing.decoder_mlp_stream
-    monkeypatch.setattr(packing, "decoder_mlp_stream",
-                        lambda blk, dev: (torch.zeros(0, dtype=torch.bfloat16, device=dev), real(blk, dev)[1]))
-    m.invalidate_packs()
-    out_r, rec_r = m(*args, mode=g["mode"])
-    assert m._packed[0][0]["mlp_stream"].numel() == 0
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dst = str(tmp_path / "rowtile.npz")
+    r = subprocess.run([sys.executable, "-c", _ROWTILE_CHILD, root, dst], env=dict(os.environ, GN_DECODER_MLP="rowtile"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    child = np.load(dst)
+    out_r, rec_r = torch.from_numpy(child["out"]), torch.from_numpy(child["rec"])
     for out, rec, tag in ((out_f, rec_f, "fused"), (out_r, rec_r, "row-tile")):
         assert_close(out, g["out_seq"], BF16_REL, f"out_seq ({tag})")
         assert_close(rec, g["recover_pre_seq"], BF16_REL, f"recover_pre_seq ({tag})")
